@@ -1,0 +1,109 @@
+// rzk_arith.cuh -- word-level modular arithmetic shared by the sm_100a kernels and
+// the host-side lane emulator (tests/cpp/emu_check.cpp compiles this with g++).
+//
+// Replaces the per-coefficient arithmetic of Polynomial<ZqI64<Q>, N>'s `* + -`
+// (crate poly-ring-xnp1; called from /root/reference/src/mat.rs:109-110,135-136,
+// 160-161,176).  q = 3515337053 admits no length-512 NTT (q-1 = 2^2*2389*367867),
+// so products are computed exactly over the integers through NTT-friendly
+// auxiliary primes p < 2^30 (Harvey lazy butterflies, Shoup constants) and
+// recombined by CRT before the centred reduction mod q.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define RZK_HD __host__ __device__ __forceinline__
+#define RZK_D __device__ __forceinline__
+#else
+#define RZK_HD inline
+#define RZK_D inline
+#endif
+
+namespace rzk {
+
+RZK_HD uint32_t mulhi32(uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+RZK_HD uint64_t mulhi64(uint64_t a, uint64_t b)
+{
+#if defined(__CUDA_ARCH__)
+    return __umul64hi(a, b);
+#else
+    return (uint64_t)(((unsigned __int128)a * (unsigned __int128)b) >> 64);
+#endif
+}
+
+RZK_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
+
+// x in [0, 2m) -> [0, m)  (unsigned wrap makes x - m huge when x < m)
+RZK_HD uint32_t csub(uint32_t x, uint32_t m) { return umin32(x, x - m); }
+
+// Shoup multiplication by a constant w with companion wp = floor(w * 2^32 / p).
+// Valid for ANY 32-bit y; result in [0, 2p).
+RZK_HD uint32_t shoup_mul(uint32_t w, uint32_t wp, uint32_t y, uint32_t p)
+{
+    uint32_t q = mulhi32(wp, y);
+    return w * y - q * p;
+}
+
+// Montgomery product a*b*2^-32 mod p for a*b < p*2^32; pinv = p^-1 mod 2^32.
+// Result in (0, 2p).
+RZK_HD uint32_t mont_mul(uint32_t a, uint32_t b, uint32_t p, uint32_t pinv)
+{
+    uint32_t lo = a * b;
+    uint32_t hi = mulhi32(a, b);
+    uint32_t m = lo * pinv;
+    uint32_t mh = mulhi32(m, p);
+    return hi - mh + p;
+}
+
+// Cooley-Tukey (forward) butterfly, Harvey lazy form: inputs in [0, 4p), outputs in [0, 4p).
+RZK_HD void ct_bfly(uint32_t &x, uint32_t &y, uint32_t w, uint32_t wp, uint32_t p, uint32_t p2)
+{
+    uint32_t xr = csub(x, p2);
+    uint32_t t = shoup_mul(w, wp, y, p);
+    x = xr + t;
+    y = xr - t + p2;
+}
+
+// Gentleman-Sande (inverse) butterfly: inputs in [0, 2p), outputs in [0, 2p).
+RZK_HD void gs_bfly(uint32_t &x, uint32_t &y, uint32_t w, uint32_t wp, uint32_t p, uint32_t p2)
+{
+    uint32_t s = csub(x + y, p2);
+    uint32_t d = x - y + p2;
+    x = s;
+    y = shoup_mul(w, wp, d, p);
+}
+
+// Canonical centred representative of an arbitrary i32 representative of a class mod q
+// (what ZqI64::from(i64) does).  q < 2^32 < 2q so one step suffices.
+RZK_HD int32_t canon_q(int32_t v, uint32_t q)
+{
+    const int32_t half = (int32_t)((q - 1u) >> 1);
+    uint32_t u = (uint32_t)v;
+    if (v > half) u -= q;
+    else if (v < -half) u += q;
+    return (int32_t)u;
+}
+
+// Signed 64-bit value w with -kq <= w < 2^64 - kq  ->  centred residue mod q.
+// bar = floor(2^64 / q), kq = q * 2^29 (offset that makes the operand non-negative;
+// Barrett with floor(2^64/q) under-estimates the quotient by at most 1 for any u64).
+RZK_HD int32_t reduce_q_centered(int64_t w, uint32_t q, uint64_t bar, uint64_t kq)
+{
+    uint64_t wp = (uint64_t)w + kq;                 // in (0, 2^61.6)
+    uint64_t qh = mulhi64(wp, bar);                 // floor(wp/q) or one less
+    uint64_t rem = wp - qh * (uint64_t)q;           // [0, 2q)
+    if (rem >= (uint64_t)q) rem -= q;
+    const uint64_t half = (uint64_t)((q - 1u) >> 1);
+    int64_t r = (int64_t)rem;
+    if (rem > half) r -= (int64_t)q;
+    return (int32_t)r;
+}
+
+}  // namespace rzk

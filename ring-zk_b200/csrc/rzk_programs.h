@@ -1,0 +1,169 @@
+// rzk_programs.h -- lowers each protocol phase of ring-zk to a polynomial-op program
+// (rzk_vm.h).  Shapes are the reference's default (n, k, l) = (1, 3, 1)
+// (/root/reference/src/params.rs:121-138): the key is a1 = [1, a11, a12],
+// a2 = [0, 1, a22] (commit.rs:33-60), so
+//     A1 . v = v0 + a11*v1 + a12*v2        A2 . v = v1 + a22*v2
+// and the products with the structural 1 / 0 blocks that Mat::dot executes
+// (mat.rs:106-113) become plain additions / disappear.
+//
+// Key polynomial indices: 0 = a11, 1 = a12, 2 = a22.
+#pragma once
+#include <string.h>
+#include "rzk_vm.h"
+
+namespace rzk {
+
+struct Prog {
+    VmLaunch *K;
+    int n = 0;
+    explicit Prog(VmLaunch *k) : K(k) { memset(K->ops, 0, sizeof(K->ops)); }
+    void add(uint8_t code, int a = 0, int b = 0, int c = 0, int off = 0, int step = 0)
+    {
+        Op &o = K->ops[n++];
+        o.code = code; o.a = (uint8_t)a; o.b = (uint8_t)b; o.c = (uint8_t)c;
+        o.off = (uint16_t)off; o.step = (uint16_t)step;
+    }
+    void end() { add(OP_END); }
+};
+
+// ---- 2-prime programs -------------------------------------------------------------
+
+// [c1; c2] = [a1; a2] . r + [0; x]                       commit.rs:88-128
+// streams: 0 = x (1 poly), 1 = r (3 polys), 2 = c out (2 polys)
+inline void prog_commit(Prog &P, int sx = 0, int sr = 1, int sc = 2, bool with_norm = true)
+{
+    if (with_norm) P.add(OP_NORM, sr, /*commit bound*/ 0, /*count*/ 3, 0);     // commit.rs:102
+    P.add(OP_SEG);
+    P.add(OP_FWD, sr, 0, 0, 1);
+    P.add(OP_MACK, 0, 0, MAC_INIT);
+    P.add(OP_FWD, sr, 0, 0, 2);
+    P.add(OP_MACK, 0, 1, 0);
+    P.add(OP_MACK, 1, 2, MAC_INIT);
+    P.add(OP_INV, 0, 0);
+    P.add(OP_ADDP, sr, 0, 0, 0);
+    P.add(OP_FIN, sc, FIN_STORE, 0, 0);
+    P.add(OP_INV, 1, 1);
+    P.add(OP_ADDP, sr, 0, 0, 1);
+    P.add(OP_ADDP, sx, 0, 0, 0);
+    P.add(OP_FIN, sc, FIN_STORE, 0, 1);
+}
+
+// t = A1 . y  (open.rs:97, linear.rs:118-121, sum.rs:145-151) and optionally w = A2 . y
+// (the inner factor of u, linear.rs:124-129 / sum.rs:154-160).
+// sv = y stream (3 polys), st = t out (or -1), sw = w out (or -1)
+inline void prog_keymatvec(Prog &P, int sv, int st, int sw, bool check_small)
+{
+    const int fl = check_small ? FWD_CHECK_SMALL : 0;
+    P.add(OP_SEG);
+    if (st >= 0) {
+        P.add(OP_FWD, sv, fl, 0, 1);
+        P.add(OP_MACK, 0, 0, MAC_INIT);
+    }
+    P.add(OP_FWD, sv, fl, 0, 2);
+    if (st >= 0) P.add(OP_MACK, 0, 1, 0);
+    if (sw >= 0) P.add(OP_MACK, 1, 2, MAC_INIT);
+    if (st >= 0) {
+        P.add(OP_INV, 0, 0);
+        P.add(OP_ADDP, sv, 0, 0, 0);
+        P.add(OP_FIN, st, FIN_STORE, 0, 0);
+    }
+    if (sw >= 0) {
+        P.add(OP_INV, 1, 1);
+        P.add(OP_ADDP, sv, 0, 0, 1);
+        P.add(OP_FIN, sw, FIN_STORE, 0, 0);
+    }
+}
+
+// check_verify_constraint(z) and A1.z == t + c1*d            open.rs:162-174
+// optionally also w = A2.z - c2*d  (left/right sides of the third equation folded
+// together, linear.rs:236-249 / sum.rs:300-319).
+// sz = z (3 polys), st = t, sc = commitment c (2 polys: c1, c2), sd = d, sw = w out or -1
+inline void prog_verify_first(Prog &P, int sz, int st, int sc, int sd, int sw)
+{
+    P.add(OP_SEG);
+    P.add(OP_FWD, sd, FWD_SCALED, 0, 0);
+    P.add(OP_ST);
+    P.add(OP_FWD, sz, 0, 0, 1);
+    P.add(OP_MACK, 0, 0, MAC_INIT);
+    P.add(OP_FWD, sz, 0, 0, 2);
+    P.add(OP_MACK, 0, 1, 0);
+    if (sw >= 0) P.add(OP_MACK, 1, 2, MAC_INIT);
+    P.add(OP_FWD, sc, 0, 0, 0);
+    P.add(OP_MACV, 0, 0, MAC_NEG);
+    if (sw >= 0) {
+        P.add(OP_FWD, sc, 0, 0, 1);
+        P.add(OP_MACV, 1, 0, MAC_NEG);
+    }
+    P.add(OP_INV, 0, 0);
+    P.add(OP_ADDP, sz, 0, 0, 0);
+    P.add(OP_ADDP, st, 0, MAC_NEG, 0);
+    P.add(OP_FIN, 0, FIN_CMPZ, 0, 0);
+    if (sw >= 0) {
+        P.add(OP_INV, 1, 1);
+        P.add(OP_ADDP, sz, 0, 0, 1);
+        P.add(OP_FIN, sw, FIN_STORE, 0, 0);
+    }
+}
+
+inline void prog_norm_verify(Prog &P, int sz)
+{
+    P.add(OP_NORM, sz, /*verify bound*/ 1, 3, 0);      // params.rs:112-118
+}
+
+// ---- 1-prime program ---------------------------------------------------------------
+
+// z = y + r.componentwise_mul(d)                          open.rs:113-115
+// streams: sy = y (3), sr = r (3), sd = d (1), sz = z out (3)
+inline void prog_respond(Prog &P, int sy, int sr, int sd, int sz)
+{
+    P.add(OP_SEG);
+    P.add(OP_FWD, sd, FWD_SCALED, 0, 0);
+    P.add(OP_ST);
+    P.add(OP_FWD, sr, 0, 0, 0);
+    P.add(OP_MACV, 0, 0, MAC_INIT);
+    P.add(OP_FWD, sr, 0, 0, 1);
+    P.add(OP_MACV, 1, 0, MAC_INIT);
+    P.add(OP_INV, 0, 0);
+    P.add(OP_ADDP, sy, 0, 0, 0);
+    P.add(OP_FIN, sz, FIN_STORE, 0, 0);
+    P.add(OP_INV, 1, 0);
+    P.add(OP_ADDP, sy, 0, 0, 1);
+    P.add(OP_FIN, sz, FIN_STORE, 0, 1);
+    P.add(OP_SEG);
+    P.add(OP_FWD, sd, FWD_SCALED, 0, 0);
+    P.add(OP_ST);
+    P.add(OP_FWD, sr, 0, 0, 2);
+    P.add(OP_MACV, 0, 0, MAC_INIT);
+    P.add(OP_INV, 0, 0);
+    P.add(OP_ADDP, sy, 0, 0, 2);
+    P.add(OP_FIN, sz, FIN_STORE, 0, 2);
+}
+
+// ---- 3-prime program ---------------------------------------------------------------
+
+// out = sum_{i<T} a_i * b_i  -  sub0  -  sub1          (large x large products)
+//   g*x (linear.rs:91-95), sum g_i*x_i (sum.rs:107-115), u (linear.rs:124-129, sum.rs:154-160),
+//   third-equation check (linear.rs:236-249, sum.rs:300-319) with mode = FIN_CMPZ.
+// sa, sb: streams holding T polys per item; ssub0/ssub1: single-poly streams or -1.
+inline void prog_mulsum(Prog &P, int T, int sa, int sb, int ssub0, int ssub1, int sout, int mode)
+{
+    P.add(OP_SEG);
+    P.add(OP_FWD, sb, FWD_SCALED, 0, 0);
+    P.add(OP_ST);
+    P.add(OP_FWD, sa, 0, 0, 0);
+    P.add(OP_MACV, 0, 0, MAC_INIT);
+    if (T > 1) {
+        P.add(OP_LOOP, 0, 0, 0, T - 1);
+        P.add(OP_FWD, sb, FWD_SCALED, 0, 1, 1);
+        P.add(OP_ST);
+        P.add(OP_FWD, sa, 0, 0, 1, 1);
+        P.add(OP_MACV, 0, 0, 0);
+        P.add(OP_ENDLOOP);
+    }
+    P.add(OP_INV, 0, 0);
+    if (ssub0 >= 0) P.add(OP_ADDP, ssub0, 0, MAC_NEG, 0);
+    if (ssub1 >= 0) P.add(OP_ADDP, ssub1, 0, MAC_NEG, 0);
+    P.add(OP_FIN, sout >= 0 ? sout : 0, mode, 0, 0);
+}
+
+}  // namespace rzk

@@ -1,0 +1,118 @@
+// rzk_vm.h -- data model of the polynomial-op "program" that every protocol phase of
+// the R_q hot path is lowered to.  Shared by the host composer (rzk_engine.cu), the
+// sm_100a kernel (rzk_kernels.cu) and the host lane emulator (tests/cpp/emu_check.cpp).
+//
+// One half-warp (16 lanes, 32 coefficients per lane) evaluates one batch item.  A
+// program is a list of NORM ops followed by segments; every segment is run once per
+// auxiliary prime and ends in inverse transforms whose residues are CRT-combined,
+// reduced mod q and either stored or compared with zero.
+//
+//   out = reduce_q( sum_i key_i (*) in_i  +  sum_j in_a (*) in_b  +  sum_k +-plain_k )
+//
+// which covers Mat::dot / componentwise_mul / add / sub of /root/reference/src/mat.rs:95-178
+// as composed by commit.rs:88-128 and prove/{open,linear,sum}.rs.
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+namespace rzk {
+
+constexpr int kN = 512;            // ring degree handled by the NTT kernels
+constexpr int kLanes = 16;         // lanes per item (half warp)
+constexpr int kElems = 32;         // coefficients per lane
+constexpr int kMaxPrimes = 3;
+constexpr int kNumPrimeSlots = 6;  // global static prime list (rzk_tables.cpp)
+constexpr int kPadWords = 576;     // 512 + 4 words of padding per 32 (conflict-free uint4 rows)
+constexpr int kBufWords = 592;     // transpose buffer per half-warp (+16: bank shift between halves)
+constexpr int kSlotWords = 512;    // lane-private slot (uint4 chunks interleaved over lanes)
+constexpr int kG2Words = 60;       // lane-specific twiddle words per (direction, prime, lane)
+constexpr int kKeyPolys = 3;       // non-trivial key polynomials a1'[0], a1'[1], a2'[0] at (n,k,l)=(1,3,1)
+constexpr int kMaxOps = 56;
+constexpr int kMaxStreams = 12;
+
+enum OpCode : uint8_t {
+    OP_END = 0,
+    OP_SEG,      // start of a segment (ops up to the next SEG/END run once per prime)
+    OP_FWD,      // cur = NTT_p(stream a, poly off [+ it*step]);  b: FWD_* flags
+    OP_MACK,     // acc[a] (+)= key[b] (.) cur            c: MAC_* flags
+    OP_MACV,     // acc[a] (+)= slot (.) cur (Montgomery)  c: MAC_* flags
+    OP_ST,       // slot = cur  (cur must come from a FWD_SCALED transform)
+    OP_INV,      // inverse NTT of acc[a]; stash b; on the last prime: CRT -> V
+    OP_ADDP,     // (last prime only) V += +-stream a poly off      c: MAC_NEG
+    OP_FIN,      // (last prime only) res = reduce_q(V);  b: FIN_* flags (store to stream a / compare with 0)
+    OP_NORM,     // (once) squared 2-norm check of c consecutive polys of stream a from off; b = bound select
+    OP_LOOP,     // repeat the ops up to OP_ENDLOOP `off` times (iteration index scales `step`)
+    OP_ENDLOOP,
+};
+
+enum : uint8_t { FWD_SCALED = 1, FWD_CHECK_SMALL = 2 };
+enum : uint8_t { MAC_INIT = 1, MAC_NEG = 2 };
+enum : uint8_t { FIN_STORE = 1, FIN_CMPZ = 2 };
+enum : uint8_t { DT_I32 = 0, DT_I8 = 1 };
+enum : uint32_t { FLAG_FAIL = 1u, FLAG_RANGE = 2u };
+
+struct Op {
+    uint8_t code, a, b, c;
+    uint16_t off, step;
+};
+
+struct Stream {
+    const void *base;     // device pointer
+    uint32_t stride;      // polynomials per item group
+    uint32_t div;         // item group = item / div
+    uint32_t dtype;       // DT_I32 / DT_I8
+    uint32_t pad_;
+};
+
+struct PrimeC {
+    uint32_t p, p2, pinv;   // p, 2p, p^-1 mod 2^32
+    uint32_t rn, rnp;       // R * N^-1 mod p (R = 2^32) and its Shoup companion
+    uint32_t slot;          // index into the global static prime list (selects G1 twiddles)
+    uint32_t half;          // (p-1)/2
+    uint32_t pad_;
+};
+
+struct CrtC {
+    // Garner: V = a0 + p0*h1 + p0*p1*h2
+    uint32_t inv01, inv01p;       // p0^-1 mod p1 (Shoup pair)
+    uint32_t p0modp2, p0modp2p;   // p0 mod p2 (Shoup pair w.r.t. p2)
+    uint32_t inv012, inv012p;     // (p0*p1)^-1 mod p2 (Shoup pair)
+    uint32_t pad0_, pad1_;
+    uint64_t P01;                 // p0*p1
+    uint64_t P01half;             // (p0*p1 - 1)/2          (centring for 2 primes)
+    uint64_t P01modq;             // (p0*p1) mod q
+    uint64_t Pmodq;               // (p0*p1*p2) mod q
+    uint64_t Phalf_lo;            // (p0*p1*p2 - 1)/2, low 64 bits
+    uint64_t Phalf_hi;            //                    high bits
+};
+
+struct VmLaunch {
+    Op ops[kMaxOps];
+    Stream st[kMaxStreams];
+    PrimeC pc[kMaxPrimes];
+    CrtC crt;
+    uint64_t bar;              // floor(2^64 / q)
+    uint64_t kq;               // q * 2^29
+    uint64_t norm_sq_lim[2];   // (bound+1)^2 - 1 for [0]=commit, [1]=verify constraint
+    uint32_t norm_abs_lim[2];  // bound
+    uint32_t q;
+    uint32_t small_lim;        // |v| limit for FWD_CHECK_SMALL operands
+    uint32_t n_items;
+    uint32_t flag_div;         // flags index = item / flag_div
+    uint32_t np;               // primes in this launch
+    uint32_t pad_;
+    uint32_t *flags;           // device, one word per item group
+    const uint32_t *g2tab;     // device, [prime slot][dir][16][60]
+    const uint32_t *keytab;    // device, [prime slot][3][2][576]
+};
+
+// Host-side twiddle tables for one prime (built in rzk_tables.cpp).
+struct PrimeTables {
+    uint32_t p;
+    uint32_t g1[2][32][2];                 // [dir][twiddle index][w, w']  (indices 1..31 used)
+    uint32_t g2[2][kLanes][kG2Words];      // [dir][lane][...]
+    uint32_t psi, psi_inv, ninv, r, rn, rnp, pinv;
+    uint32_t tw[2][kN][2];                 // full tables (reference transform, key setup)
+};
+
+}  // namespace rzk

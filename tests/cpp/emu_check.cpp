@@ -1,0 +1,374 @@
+// emu_check.cpp -- host lane emulator for the polynomial-op programs.
+//
+// Compiles ring-zk_b200/csrc/rzk_vm_exec.cuh with g++ (16 explicit lanes per item) and
+// checks every program shape used by the engine against the CPU oracle on seeded random
+// inputs.  Test infrastructure only (run by tests/test_emulator.py): it lets the exact
+// kernel arithmetic and shared-memory layouts be validated without a GPU.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <vector>
+
+#include "../../ring-zk_b200/csrc/rzk_vm_exec.cuh"
+#include "../../ring-zk_b200/csrc/rzk_programs.h"
+#include "../../ring-zk_b200/csrc/rzk_tables.h"
+extern "C" {
+#include "../../oracle/ringzk_oracle.h"
+}
+
+using namespace rzk;
+
+static uint64_t rng_state = 0x9E3779B97F4A7C15ull;
+static uint64_t rnd()
+{
+    uint64_t z = (rng_state += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+static const int64_t Q = 3515337053LL;
+static int32_t rnd_q() { return (int32_t)((int64_t)(rnd() % (uint64_t)Q) - (Q - 1) / 2); }
+static double rnd_u() { return ((rnd() >> 11) + 0.5) / 9007199254740992.0; }
+static int32_t rnd_gauss(double sigma)
+{
+    double u1 = rnd_u(), u2 = rnd_u();
+    return (int32_t)trunc(sigma * sqrt(-2.0 * log(u1)) * cos(2 * M_PI * u2));
+}
+
+struct Emu {
+    int np;
+    int slots[3];
+    std::vector<uint32_t> g1, g2, key, flags;
+    VmLaunch K;
+    std::vector<uint32_t> buf, slot, stash;
+
+    Emu(int np_, const int *sl, const int64_t *keypolys /*[3][512]*/, size_t nflags)
+    {
+        np = np_;
+        memset(&K, 0, sizeof(K));
+        g1.resize(kNumPrimeSlots * 2 * 32 * 2);
+        g2.resize((size_t)np * 2 * kLanes * kG2Words);
+        key.resize((size_t)np * kKeyPolys * 2 * kPadWords);
+        for (int s = 0; s < kNumPrimeSlots; ++s) {
+            const PrimeTables &T = prime_tables(s);
+            memcpy(&g1[(size_t)s * 2 * 32 * 2], T.g1, sizeof(T.g1));
+        }
+        for (int i = 0; i < np; ++i) {
+            slots[i] = sl[i];
+            const PrimeTables &T = prime_tables(sl[i]);
+            memcpy(&g2[(size_t)i * 2 * kLanes * kG2Words], T.g2, sizeof(T.g2));
+            for (int k = 0; k < kKeyPolys; ++k)
+                key_image(T, keypolys + (size_t)k * kN, &key[((size_t)i * kKeyPolys + k) * 2 * kPadWords]);
+            K.pc[i] = make_prime_consts(sl[i]);
+        }
+        K.crt = make_crt_consts(sl, np, (uint64_t)Q);
+        K.q = (uint32_t)Q;
+        K.bar = (uint64_t)((((unsigned __int128)1) << 64) / (uint64_t)Q);
+        K.kq = (uint64_t)Q << 29;
+        rzko_params P = rzko_default_params(kN);
+        uint64_t cb = rzko_commit_bound(&P), vb = rzko_verify_bound(&P);
+        K.norm_abs_lim[0] = (uint32_t)cb; K.norm_sq_lim[0] = (cb + 1) * (cb + 1) - 1;
+        K.norm_abs_lim[1] = (uint32_t)vb; K.norm_sq_lim[1] = (vb + 1) * (vb + 1) - 1;
+        K.small_lim = 1u << 18;
+        K.np = np;
+        K.flag_div = 1;
+        flags.assign(nflags, 0);
+        K.flags = flags.data();
+        buf.resize(kBufWords);
+        slot.resize(kSlotWords);
+        stash.resize(2 * 2 * kSlotWords);
+    }
+    void stream(int i, const void *base, uint32_t stride, uint32_t dtype, uint32_t div = 1)
+    {
+        K.st[i].base = base; K.st[i].stride = stride; K.st[i].dtype = dtype; K.st[i].div = div;
+    }
+    void run(uint32_t n_items)
+    {
+        K.n_items = n_items;
+        static Lane lanes[16];
+        for (uint32_t it = 0; it < n_items; ++it) {
+            ItemCtx c;
+            c.buf = buf.data(); c.slot = slot.data(); c.stash = stash.data();
+            c.g2 = g2.data(); c.key = key.data(); c.g1 = g1.data();
+            c.item = it; c.active = true;
+            if (np == 1) vm_run_item<1, 2>(K, c, lanes, 0);
+            else if (np == 2) vm_run_item<2, 2>(K, c, lanes, 0);
+            else vm_run_item<3, 2>(K, c, lanes, 0);
+        }
+    }
+};
+
+static int nfail = 0;
+#define CHECK(cond, ...) do { if (!(cond)) { printf("FAIL %s:%d: ", __FILE__, __LINE__); printf(__VA_ARGS__); printf("\n"); ++nfail; } } while (0)
+
+static std::vector<int64_t> widen(const std::vector<int32_t> &v) { return std::vector<int64_t>(v.begin(), v.end()); }
+static std::vector<int64_t> widen8(const std::vector<int8_t> &v) { return std::vector<int64_t>(v.begin(), v.end()); }
+static bool same(const std::vector<int32_t> &a, const std::vector<int64_t> &b)
+{
+    if (a.size() != b.size()) return false;
+    for (size_t i = 0; i < a.size(); ++i) if ((int64_t)a[i] != b[i]) return false;
+    return true;
+}
+
+int main(int argc, char **argv)
+{
+    const int B = argc > 1 ? atoi(argv[1]) : 3;
+    const int T = 3;
+    rzko_params P = rzko_default_params(kN);
+    const size_t N = kN;
+
+    // key
+    std::vector<int64_t> keyp(3 * N);
+    for (auto &v : keyp) v = rnd_q();
+    std::vector<int64_t> a1(3 * N), a2(3 * N);
+    rzko_key_expand(&P, keyp.data(), keyp.data() + 2 * N, a1.data(), a2.data());
+
+    // inputs
+    std::vector<int32_t> x(B * N), g(B * N), y(B * 3 * N), yp(B * 3 * N);
+    std::vector<int8_t> r(B * 3 * N), rp(B * 3 * N), d(B * N, 0);
+    for (auto &v : x) v = rnd_q();
+    for (auto &v : g) v = rnd_q();
+    for (auto &v : r) v = (int8_t)((int)(rnd() % 3) - 1);
+    for (auto &v : rp) v = (int8_t)((int)(rnd() % 3) - 1);
+    for (auto &v : y) v = rnd_gauss(15444.0);
+    for (auto &v : yp) v = rnd_gauss(15444.0);
+    for (int b = 0; b < B; ++b)
+        for (int k = 0; k < 36;) {
+            int pos = (int)(rnd() % N);
+            if (d[b * N + pos]) continue;
+            d[b * N + pos] = (rnd() & 1) ? 1 : -1;
+            ++k;
+        }
+    // ragged message: zero tail on item 0 (tests/test.rs:95-99)
+    for (size_t i = 5; i < N; ++i) x[i] = 0;
+    auto x64 = widen(x), g64 = widen(g), y64 = widen(y), yp64 = widen(yp);
+    auto r64 = widen8(r), rp64 = widen8(rp), d64 = widen8(d);
+
+    const int L2[3] = {0, 1, 2};
+
+    // ---------------- commit + open commit (2 primes) ----------------
+    std::vector<int64_t> c_o(B * 2 * N), t_o(B * N);
+    std::vector<uint8_t> ok_o(B);
+    rzko_open_commit_batch(&P, a1.data(), a2.data(), B, x64.data(), r64.data(), y64.data(), c_o.data(), t_o.data(), ok_o.data(), 1);
+    std::vector<int32_t> c_e(B * 2 * N), t_e(B * N), w_e(B * N);
+    {
+        Emu E(2, L2, keyp.data(), B);
+        Prog pr(&E.K);
+        prog_commit(pr, 0, 1, 2);
+        prog_keymatvec(pr, 3, 4, 5, true);
+        pr.end();
+        E.stream(0, x.data(), 1, DT_I32); E.stream(1, r.data(), 3, DT_I8); E.stream(2, c_e.data(), 2, DT_I32);
+        E.stream(3, y.data(), 3, DT_I32); E.stream(4, t_e.data(), 1, DT_I32); E.stream(5, w_e.data(), 1, DT_I32);
+        E.run(B);
+        CHECK(same(c_e, c_o), "commit c mismatch");
+        CHECK(same(t_e, t_o), "open commit t mismatch");
+        for (int b = 0; b < B; ++b) CHECK(E.flags[b] == 0 && ok_o[b] == 1, "commit flags item %d: %u", b, E.flags[b]);
+        // w = A2.y against the oracle's mat_dot
+        std::vector<int64_t> w_o(N);
+        for (int b = 0; b < B; ++b) {
+            rzko_mat_dot(&P, 1, 3, 1, a2.data(), y64.data() + (size_t)b * 3 * N, w_o.data());
+            for (size_t i = 0; i < N; ++i) CHECK(w_o[i] == w_e[b * N + i], "w mismatch item %d coef %zu", b, i);
+        }
+        printf("commit/open_commit: ops=%d\n", pr.n);
+    }
+    // commit-constraint failure and range flag
+    {
+        std::vector<int32_t> rbig(B * 3 * N, 0), ybig(y);
+        for (int b = 0; b < B; ++b) rbig[(b * 3 + 1) * N + 7] = 1359073;        // > commit bound
+        ybig[5] = (1 << 18) + 1;                                                 // item 0, poly 0: not transformed -> no flag
+        ybig[N + 5] = (1 << 18) + 1;                                             // item 0, poly 1: flagged
+        Emu E(2, L2, keyp.data(), B);
+        Prog pr(&E.K);
+        prog_commit(pr, 0, 1, 2);
+        prog_keymatvec(pr, 3, 4, -1, true);
+        pr.end();
+        E.stream(0, x.data(), 1, DT_I32); E.stream(1, rbig.data(), 3, DT_I32); E.stream(2, c_e.data(), 2, DT_I32);
+        E.stream(3, ybig.data(), 3, DT_I32); E.stream(4, t_e.data(), 1, DT_I32);
+        E.run(B);
+        CHECK(E.flags[0] == (FLAG_FAIL | FLAG_RANGE), "flags[0]=%u", E.flags[0]);
+        for (int b = 1; b < B; ++b) CHECK(E.flags[b] == FLAG_FAIL, "flags[%d]=%u", b, E.flags[b]);
+        auto rb64 = widen(rbig);
+        std::vector<int64_t> c2(B * 2 * N);
+        std::vector<uint8_t> ok2(B);
+        rzko_commit_batch(&P, a1.data(), a2.data(), B, x64.data(), rb64.data(), c2.data(), ok2.data(), 1);
+        CHECK(same(c_e, c2), "commit with large r mismatch");
+        for (int b = 0; b < B; ++b) CHECK(ok2[b] == 0, "oracle ok");
+    }
+
+    // ---------------- respond (1 prime) ----------------
+    std::vector<int64_t> z_o(B * 3 * N), zp_o(B * 3 * N);
+    rzko_linear_respond_batch(&P, B, y64.data(), yp64.data(), r64.data(), rp64.data(), d64.data(), z_o.data(), zp_o.data(), 1);
+    std::vector<int32_t> z_e(B * 3 * N), zp_e(B * 3 * N);
+    {
+        const int L1[1] = {0};
+        Emu E(1, L1, keyp.data(), B);
+        Prog pr(&E.K);
+        prog_respond(pr, 0, 1, 2, 3);
+        prog_respond(pr, 4, 5, 2, 6);
+        pr.end();
+        E.stream(0, y.data(), 3, DT_I32); E.stream(1, r.data(), 3, DT_I8); E.stream(2, d.data(), 1, DT_I8);
+        E.stream(3, z_e.data(), 3, DT_I32);
+        E.stream(4, yp.data(), 3, DT_I32); E.stream(5, rp.data(), 3, DT_I8); E.stream(6, zp_e.data(), 3, DT_I32);
+        E.run(B);
+        CHECK(same(z_e, z_o), "respond z mismatch");
+        CHECK(same(zp_e, zp_o), "respond zp mismatch");
+        printf("respond: ops=%d\n", pr.n);
+    }
+
+    // ---------------- open verify (2 primes) ----------------
+    {
+        std::vector<int32_t> c32(c_o.begin(), c_o.end()), t32(t_o.begin(), t_o.end());
+        for (int variant = 0; variant < 5; ++variant) {
+            std::vector<int32_t> zz(z_e), tt(t32), cc(c32);
+            std::vector<int8_t> dd(d);
+            if (variant == 1) for (int b = 0; b < B; ++b) zz[(b * 3 + 2) * N + 11] += 1;
+            if (variant == 2) for (int b = 0; b < B; ++b) tt[b * N + 500] -= 1;
+            if (variant == 3) for (int b = 0; b < B; ++b) cc[(b * 2) * N + 1] += 1;
+            if (variant == 4) for (int b = 0; b < B; ++b) zz[(b * 3) * N + 3] = 679537;   // norm check
+            Emu E(2, L2, keyp.data(), B);
+            Prog pr(&E.K);
+            prog_norm_verify(pr, 0);
+            prog_verify_first(pr, 0, 1, 2, 3, -1);
+            pr.end();
+            E.stream(0, zz.data(), 3, DT_I32); E.stream(1, tt.data(), 1, DT_I32);
+            E.stream(2, cc.data(), 2, DT_I32); E.stream(3, dd.data(), 1, DT_I8);
+            E.run(B);
+            auto z64 = widen(zz), t64 = widen(tt), c64 = widen(cc);
+            std::vector<int64_t> c1(B * N);
+            for (int b = 0; b < B; ++b) memcpy(&c1[b * N], &c64[(size_t)b * 2 * N], N * sizeof(int64_t));
+            std::vector<uint8_t> okv(B);
+            rzko_open_verify_batch(&P, a1.data(), B, z64.data(), t64.data(), c1.data(), d64.data(), okv.data(), 1);
+            for (int b = 0; b < B; ++b) {
+                CHECK((E.flags[b] == 0) == (okv[b] == 1), "open verify variant %d item %d: emu flags %u oracle %u", variant, b, E.flags[b], okv[b]);
+                CHECK((okv[b] == 1) == (variant == 0), "oracle verdict variant %d", variant);
+            }
+        }
+        printf("open verify ok\n");
+    }
+
+    // ---------------- linear proof: full lowering vs oracle ----------------
+    {
+        std::vector<int64_t> gx_o(B * N), cp_o(B * 2 * N), c2_o(B * 2 * N), tl_o(B * N), tp_o(B * N), u_o(B * N);
+        std::vector<uint8_t> okl(B);
+        rzko_linear_commit_batch(&P, a1.data(), a2.data(), B, g64.data(), x64.data(), rp64.data(), r64.data(), y64.data(), yp64.data(),
+                                 gx_o.data(), cp_o.data(), c2_o.data(), tl_o.data(), tp_o.data(), u_o.data(), okl.data(), 1);
+        // launch A (3 primes): gx = g*x
+        std::vector<int32_t> gx_e(B * N), cp_e(B * 2 * N), cl_e(B * 2 * N), tl_e(B * N), tp_e(B * N), w_l(B * N), wp_l(B * N), u_e(B * N);
+        {
+            Emu E(3, L2, keyp.data(), B);
+            Prog pr(&E.K);
+            prog_mulsum(pr, 1, 0, 1, -1, -1, 2, FIN_STORE);
+            pr.end();
+            E.stream(0, g.data(), 1, DT_I32); E.stream(1, x.data(), 1, DT_I32); E.stream(2, gx_e.data(), 1, DT_I32);
+            E.run(B);
+            CHECK(same(gx_e, gx_o), "linear gx mismatch");
+        }
+        // launch B (2 primes): both commits, t, tp, w, wp
+        {
+            Emu E(2, L2, keyp.data(), B);
+            Prog pr(&E.K);
+            prog_commit(pr, 0, 1, 2);
+            prog_commit(pr, 3, 4, 5);
+            prog_keymatvec(pr, 6, 7, 8, true);
+            prog_keymatvec(pr, 9, 10, 11, true);
+            pr.end();
+            CHECK(pr.n <= kMaxOps, "too many ops %d", pr.n);
+            E.stream(0, gx_e.data(), 1, DT_I32); E.stream(1, rp.data(), 3, DT_I8); E.stream(2, cp_e.data(), 2, DT_I32);
+            E.stream(3, x.data(), 1, DT_I32); E.stream(4, r.data(), 3, DT_I8); E.stream(5, cl_e.data(), 2, DT_I32);
+            E.stream(6, y.data(), 3, DT_I32); E.stream(7, tl_e.data(), 1, DT_I32); E.stream(8, w_l.data(), 1, DT_I32);
+            E.stream(9, yp.data(), 3, DT_I32); E.stream(10, tp_e.data(), 1, DT_I32); E.stream(11, wp_l.data(), 1, DT_I32);
+            E.run(B);
+            CHECK(same(cp_e, cp_o) && same(cl_e, c2_o), "linear commitments mismatch");
+            CHECK(same(tl_e, tl_o) && same(tp_e, tp_o), "linear t/tp mismatch");
+            printf("linear commit launch B: ops=%d\n", pr.n);
+        }
+        // launch C (3 primes): u = g*w - wp
+        {
+            Emu E(3, L2, keyp.data(), B);
+            Prog pr(&E.K);
+            prog_mulsum(pr, 1, 0, 1, 2, -1, 3, FIN_STORE);
+            pr.end();
+            E.stream(0, g.data(), 1, DT_I32); E.stream(1, w_l.data(), 1, DT_I32); E.stream(2, wp_l.data(), 1, DT_I32);
+            E.stream(3, u_e.data(), 1, DT_I32);
+            E.run(B);
+            CHECK(same(u_e, u_o), "linear u mismatch");
+        }
+        // verify: launch A (2 primes) + launch B (3 primes), honest and tampered
+        for (int variant = 0; variant < 4; ++variant) {
+            std::vector<int32_t> zz(z_e), zzp(zp_e), uu(u_e), gg(g);
+            if (variant == 1) for (int b = 0; b < B; ++b) uu[b * N + 9] += 1;
+            if (variant == 2) for (int b = 0; b < B; ++b) gg[b * N + 100] ^= 1;
+            if (variant == 3) for (int b = 0; b < B; ++b) zzp[(b * 3 + 1) * N + 17] -= 1;
+            std::vector<uint32_t> flags(B, 0);
+            std::vector<int32_t> wv(B * N), wvp(B * N);
+            {
+                Emu E(2, L2, keyp.data(), B);
+                Prog pr(&E.K);
+                prog_norm_verify(pr, 0);
+                prog_norm_verify(pr, 4);
+                prog_verify_first(pr, 0, 1, 2, 3, 8);
+                prog_verify_first(pr, 4, 5, 6, 3, 9);
+                pr.end();
+                CHECK(pr.n <= kMaxOps, "too many ops %d", pr.n);
+                E.stream(0, zz.data(), 3, DT_I32); E.stream(1, tl_e.data(), 1, DT_I32); E.stream(2, cl_e.data(), 2, DT_I32);
+                E.stream(3, d.data(), 1, DT_I8);
+                E.stream(4, zzp.data(), 3, DT_I32); E.stream(5, tp_e.data(), 1, DT_I32); E.stream(6, cp_e.data(), 2, DT_I32);
+                E.stream(8, wv.data(), 1, DT_I32); E.stream(9, wvp.data(), 1, DT_I32);
+                E.run(B);
+                flags = E.flags;
+                if (variant == 0) printf("linear verify launch A: ops=%d\n", pr.n);
+            }
+            {
+                Emu E(3, L2, keyp.data(), B);
+                Prog pr(&E.K);
+                prog_mulsum(pr, 1, 0, 1, 2, 3, -1, FIN_CMPZ);
+                pr.end();
+                E.stream(0, gg.data(), 1, DT_I32); E.stream(1, wv.data(), 1, DT_I32); E.stream(2, wvp.data(), 1, DT_I32);
+                E.stream(3, uu.data(), 1, DT_I32);
+                E.run(B);
+                for (int b = 0; b < B; ++b) flags[b] |= E.flags[b];
+            }
+            auto z64 = widen(zz), zp64 = widen(zzp), u64 = widen(uu), gg64 = widen(gg);
+            std::vector<uint8_t> okv(B);
+            rzko_linear_verify_batch(&P, a1.data(), a2.data(), B, z64.data(), zp64.data(), c2_o.data(), cp_o.data(), gg64.data(),
+                                     tl_o.data(), tp_o.data(), u64.data(), d64.data(), okv.data(), 1);
+            for (int b = 0; b < B; ++b) {
+                CHECK((flags[b] == 0) == (okv[b] == 1), "linear verify variant %d item %d: emu %u oracle %u", variant, b, flags[b], okv[b]);
+                CHECK((okv[b] == 1) == (variant == 0), "oracle linear verdict variant %d", variant);
+            }
+        }
+        printf("linear ok\n");
+    }
+
+    // ---------------- sum of T large products (3 primes, looped program) ----------------
+    {
+        std::vector<int32_t> gs(B * T * N), xs(B * T * N), sub(B * N), out_e(B * N);
+        for (auto &v : gs) v = rnd_q();
+        for (auto &v : xs) v = rnd_q();
+        for (auto &v : sub) v = rnd_q();
+        // worst-case magnitudes on item 0 to exercise the 3-prime range
+        for (size_t i = 0; i < T * N; ++i) { gs[i] = (i & 1) ? (int32_t)((Q - 1) / 2) : -(int32_t)((Q - 1) / 2); xs[i] = (int32_t)((Q - 1) / 2); }
+        Emu E(3, L2, keyp.data(), B);
+        Prog pr(&E.K);
+        prog_mulsum(pr, T, 0, 1, 2, -1, 3, FIN_STORE);
+        pr.end();
+        E.stream(0, gs.data(), T, DT_I32); E.stream(1, xs.data(), T, DT_I32); E.stream(2, sub.data(), 1, DT_I32);
+        E.stream(3, out_e.data(), 1, DT_I32);
+        E.run(B);
+        auto gs64 = widen(gs), xs64 = widen(xs), sub64 = widen(sub);
+        std::vector<int64_t> acc(N), tmp(N);
+        for (int b = 0; b < B; ++b) {
+            for (int i = 0; i < T; ++i) {
+                rzko_poly_mul(&P, xs64.data() + ((size_t)b * T + i) * N, gs64.data() + ((size_t)b * T + i) * N, i ? tmp.data() : acc.data());
+                if (i) rzko_poly_add(&P, acc.data(), tmp.data(), acc.data());
+            }
+            rzko_poly_sub(&P, acc.data(), sub64.data() + (size_t)b * N, acc.data());
+            for (size_t i = 0; i < N; ++i) CHECK(acc[i] == out_e[b * N + i], "mulsum item %d coef %zu: %lld vs %d", b, i, (long long)acc[i], out_e[b * N + i]);
+        }
+        printf("mulsum T=%d ok, ops=%d\n", T, pr.n);
+    }
+
+    printf(nfail ? "EMU_CHECK FAILED (%d)\n" : "EMU_CHECK PASSED\n", nfail);
+    return nfail ? 1 : 0;
+}
