@@ -1,0 +1,191 @@
+/*
+ * ringzk_b200.h -- C ABI of the B200-native batched engine for ring-zk's R_q hot path.
+ *
+ * This is the drop-in boundary.  The reference (AlvinHon/ring-zk, pure Rust) has no FFI;
+ * the entry points below are what a thin Rust shim binds so that the reference's public
+ * surface (lib.rs:5-24) keeps working, with `*_batch` methods added alongside.  Each entry
+ * point cites the reference function it replaces (paths relative to /root/reference/src).
+ * INTEGRATION.md shows the Rust-side `extern "C"` block and the wrappers.
+ *
+ * Conventions
+ *   - Every call returns an int status (RZK_OK == 0) and never unwinds; rzk_last_error()
+ *     gives the message.  The Rust shim turns RZK_ERR_INVALID into the reference's
+ *     assert!/panic behaviour (params.rs:71, commit.rs:95, sum.rs:105).
+ *   - Polynomials are arrays of N coefficients, coefficient i at index i, zero padded,
+ *     batch-major row-major: [B][polys per item][N].
+ *   - Coefficients are the canonical centred residues mod q in [-(q-1)/2, (q-1)/2]
+ *     (what ZqI64<Q> -> i64 yields).  Any i32/i64 representative is accepted on input
+ *     and canonicalised.  Compact types: int32_t for full-size values, int8_t for the
+ *     small randomness r in [-b, b] and the challenge d in {-1, 0, 1}.
+ *   - Shapes are the reference's default (n, k, l) = (1, 3, 1), N = 512,
+ *     q = 3515337053 (params.rs:121-138); other sets return RZK_ERR_UNSUPPORTED.
+ *   - "ok"/verify results are bitmaps: bit (i & 7) of byte (i >> 3) is item i.
+ *   - Host entry points take host pointers (pinned memory recommended: rzk_host_alloc)
+ *     and pipeline H2D / kernels / D2H over chunks.  `_dev` entry points take device
+ *     pointers, enqueue on the given cudaStream_t (as void*) and do not synchronise.
+ *   - One engine is bound to one CUDA device and is externally synchronised.
+ *   - The randomness r, y, d is drawn by the caller (host side, seeded RNG) and passed in;
+ *     nothing is sampled on the device.
+ *   - There is no CPU fallback: without a CUDA device rzk_create fails with RZK_ERR_CUDA.
+ */
+#ifndef RINGZK_B200_H
+#define RINGZK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RZK_OK 0
+#define RZK_ERR_INVALID 1       /* null pointer / bad shape / T == 0 */
+#define RZK_ERR_UNSUPPORTED 2   /* parameter set or key structure outside the accelerated instantiation */
+#define RZK_ERR_CUDA 3          /* CUDA runtime failure (message in rzk_last_error) */
+#define RZK_ERR_RANGE 4         /* a masking vector y exceeded the exactness bound rzk_small_limit() */
+#define RZK_ERR_NOKEY 5         /* rzk_set_key has not been called */
+
+typedef struct rzk_engine rzk_engine;
+
+/* Params<ZqI64<Q>> (params.rs:18-36) + const generic N.  q is the modulus Q. */
+typedef struct {
+    int64_t q;
+    int64_t b;
+    int32_t N, n, k, l;
+    int32_t kappa;
+} rzk_params;
+
+/* Params::default() (params.rs:121-138) at ring degree N. */
+rzk_params rzk_default_params(int32_t N);
+
+/* Engine lifetime.  device < 0 selects the current CUDA device. */
+int rzk_create(const rzk_params *params, int device, rzk_engine **out);
+void rzk_destroy(rzk_engine *e);
+const char *rzk_last_error(const rzk_engine *e);   /* e may be NULL: last creation error */
+int rzk_device(const rzk_engine *e);
+
+/* params.rs:94-98 sigma, params.rs:104 / 114 norm bounds, and the |y| bound under which the
+ * two-prime products are exact (violations are reported as RZK_ERR_RANGE, never silently). */
+uint64_t rzk_sigma(const rzk_engine *e);
+uint64_t rzk_commit_bound(const rzk_engine *e);
+uint64_t rzk_verify_bound(const rzk_engine *e);
+uint32_t rzk_small_limit(const rzk_engine *e);
+
+/* CommitmentKey (commit.rs:19-60): a1 [n][k][N], a2 [l][k][N] as the reference stores them.
+ * The identity / zero blocks are verified (else RZK_ERR_UNSUPPORTED); the random blocks are
+ * transformed once and stay resident on the device in NTT form. */
+int rzk_set_key(rzk_engine *e, const int64_t *a1, const int64_t *a2);
+
+/* Pinned host memory helpers for the host entry points. */
+void *rzk_host_alloc(size_t bytes);
+void rzk_host_free(void *p);
+/* Blocks until everything enqueued by `_dev` calls on `stream` has finished. */
+int rzk_sync(rzk_engine *e, void *stream);
+
+/* ---------------------------------------------------------------- commitment
+ * CommitmentKey::commit (commit.rs:88-128) with r supplied:  c = [a1;a2].r + [0;x].
+ *   x [B][1][N] i32, r [B][3][N] i8, c [B][2][N] i32,
+ *   ok bitmap: check_commit_constraint(r) (commit.rs:102; the reference redraws r on 0). */
+int rzk_commit_batch(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r,
+                     int32_t *c, uint8_t *ok_bitmap);
+
+/* ---------------------------------------------------------------- Open proof
+ * OpenProofProver::commit (open.rs:80-103): commitment c plus t = A1.y.   y [B][3][N] i32, t [B][1][N] */
+int rzk_open_commit_batch(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r,
+                          const int32_t *y, int32_t *c, int32_t *t, uint8_t *ok_bitmap);
+/* OpenProofProver::create_response (open.rs:107-117): z = y + d*r.   d [B][N] i8, z [B][3][N] */
+int rzk_open_respond_batch(rzk_engine *e, size_t B, const int32_t *y, const int8_t *r,
+                           const int8_t *d, int32_t *z);
+/* OpenProofVerifier::verify (open.rs:162-174): norm check on z, then A1.z == t + c1*d.
+ *   c1 [B][1][N] (first rows of c, commit.rs:213-218). */
+int rzk_open_verify_batch(rzk_engine *e, size_t B, const int32_t *z, const int32_t *t,
+                          const int32_t *c1, const int8_t *d, uint8_t *verify_bitmap);
+
+/* ---------------------------------------------------------------- Linear proof
+ * LinearProofProver::commit (linear.rs:82-140).  g, x [B][N]; rp, r [B][3][N] i8; y, yp [B][3][N];
+ * outputs gx (= opening_p.x), cp, c [B][2][N], t, tp, u [B][N]. */
+int rzk_linear_commit_batch(rzk_engine *e, size_t B, const int32_t *g, const int32_t *x,
+                            const int8_t *rp, const int8_t *r, const int32_t *y, const int32_t *yp,
+                            int32_t *gx, int32_t *cp, int32_t *c, int32_t *t, int32_t *tp, int32_t *u,
+                            uint8_t *ok_bitmap);
+/* LinearProofProver::create_response (linear.rs:144-158) */
+int rzk_linear_respond_batch(rzk_engine *e, size_t B, const int32_t *y, const int32_t *yp,
+                             const int8_t *r, const int8_t *rp, const int8_t *d,
+                             int32_t *z, int32_t *zp);
+/* LinearProofVerifier::verify (linear.rs:213-250).  c, cp are the full commitments [B][2][N]. */
+int rzk_linear_verify_batch(rzk_engine *e, size_t B, const int32_t *z, const int32_t *zp,
+                            const int32_t *c, const int32_t *cp, const int32_t *g,
+                            const int32_t *t, const int32_t *tp, const int32_t *u,
+                            const int8_t *d, uint8_t *verify_bitmap);
+
+/* ---------------------------------------------------------------- Sum proof, T terms
+ * SumProofProver::commit (sum.rs:99-178).  gs, xs [B][T][N]; rs, ys [B][T][3][N]; rp, yp [B][3][N];
+ * outputs xp [B][N], cp [B][2][N], cs [B][T][2][N], ts [B][T][N], tp, u [B][N]. */
+int rzk_sum_commit_batch(rzk_engine *e, size_t B, uint32_t T, const int32_t *gs, const int32_t *xs,
+                         const int8_t *rp, const int8_t *rs, const int32_t *ys, const int32_t *yp,
+                         int32_t *xp, int32_t *cp, int32_t *cs, int32_t *ts, int32_t *tp, int32_t *u,
+                         uint8_t *ok_bitmap);
+/* SumProofProver::create_response (sum.rs:182-200) */
+int rzk_sum_respond_batch(rzk_engine *e, size_t B, uint32_t T, const int32_t *ys, const int32_t *yp,
+                          const int8_t *rs, const int8_t *rp, const int8_t *d,
+                          int32_t *zs, int32_t *zp);
+/* SumProofVerifier::verify (sum.rs:257-320) */
+int rzk_sum_verify_batch(rzk_engine *e, size_t B, uint32_t T, const int32_t *zs, const int32_t *zp,
+                         const int32_t *cs, const int32_t *cp, const int32_t *gs,
+                         const int32_t *ts, const int32_t *tp, const int32_t *u,
+                         const int8_t *d, uint8_t *verify_bitmap);
+
+/* ---------------------------------------------------------------- device-resident variants
+ * Same semantics; every pointer is a device pointer on the engine's device.  `flags` is one
+ * uint32_t per item (bit 0: check failed, bit 1: range error) and is OR-ed into, so the caller
+ * zeroes it; rzk_flags_to_bitmap_dev packs "flags == 0" into a bitmap.  c_stride is the number of
+ * polynomials per item in the commitment array handed to verify (1: c1 only, 2: full c). */
+int rzk_commit_batch_dev(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r,
+                         int32_t *c, uint32_t *flags, void *stream);
+int rzk_open_commit_batch_dev(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r,
+                              const int32_t *y, int32_t *c, int32_t *t, uint32_t *flags, void *stream);
+int rzk_open_respond_batch_dev(rzk_engine *e, size_t B, const int32_t *y, const int8_t *r,
+                               const int8_t *d, int32_t *z, void *stream);
+int rzk_open_verify_batch_dev(rzk_engine *e, size_t B, const int32_t *z, const int32_t *t,
+                              const int32_t *c, uint32_t c_stride, const int8_t *d,
+                              uint32_t *flags, void *stream);
+int rzk_linear_commit_batch_dev(rzk_engine *e, size_t B, const int32_t *g, const int32_t *x,
+                                const int8_t *rp, const int8_t *r, const int32_t *y, const int32_t *yp,
+                                int32_t *gx, int32_t *cp, int32_t *c, int32_t *t, int32_t *tp, int32_t *u,
+                                uint32_t *flags, void *stream);
+int rzk_linear_respond_batch_dev(rzk_engine *e, size_t B, const int32_t *y, const int32_t *yp,
+                                 const int8_t *r, const int8_t *rp, const int8_t *d,
+                                 int32_t *z, int32_t *zp, void *stream);
+int rzk_linear_verify_batch_dev(rzk_engine *e, size_t B, const int32_t *z, const int32_t *zp,
+                                const int32_t *c, const int32_t *cp, const int32_t *g,
+                                const int32_t *t, const int32_t *tp, const int32_t *u,
+                                const int8_t *d, uint32_t *flags, void *stream);
+int rzk_sum_commit_batch_dev(rzk_engine *e, size_t B, uint32_t T, const int32_t *gs, const int32_t *xs,
+                             const int8_t *rp, const int8_t *rs, const int32_t *ys, const int32_t *yp,
+                             int32_t *xp, int32_t *cp, int32_t *cs, int32_t *ts, int32_t *tp, int32_t *u,
+                             uint32_t *flags, void *stream);
+int rzk_sum_respond_batch_dev(rzk_engine *e, size_t B, uint32_t T, const int32_t *ys, const int32_t *yp,
+                              const int8_t *rs, const int8_t *rp, const int8_t *d,
+                              int32_t *zs, int32_t *zp, void *stream);
+int rzk_sum_verify_batch_dev(rzk_engine *e, size_t B, uint32_t T, const int32_t *zs, const int32_t *zp,
+                             const int32_t *cs, const int32_t *cp, const int32_t *gs,
+                             const int32_t *ts, const int32_t *tp, const int32_t *u,
+                             const int8_t *d, uint32_t *flags, void *stream);
+/* bitmap[i>>3] bit (i&7) = (flags[i] & 1) == 0;  *range_any (device word, may be NULL) |= any bit 1 */
+int rzk_flags_to_bitmap_dev(rzk_engine *e, size_t B, const uint32_t *flags, uint8_t *bitmap,
+                            uint32_t *range_any, void *stream);
+
+/* ---------------------------------------------------------------- i64 staging (device)
+ * The reference's coefficient type converts through Into<i64>/From<i64> (tests/test.rs:16,
+ * params.rs:126); these convert whole arrays on the device: any i64 representative ->
+ * canonical centred i32, and back.  Host pointers; count = number of coefficients. */
+int rzk_pack_i64(rzk_engine *e, size_t count, const int64_t *src, int32_t *dst);
+int rzk_unpack_i64(rzk_engine *e, size_t count, const int32_t *src, int64_t *dst);
+
+/* Counters for the benchmark harness: kernels launched by this engine since creation. */
+uint64_t rzk_kernel_launches(const rzk_engine *e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,926 @@
+// rzk_engine.cu -- sm_100a kernels and the C ABI of include/ringzk_b200.h.
+//
+// One persistent kernel template (rzk_vm_kernel) evaluates a polynomial-op program
+// (rzk_vm.h / rzk_programs.h) for every batch item: one half warp per item, 32
+// coefficients per lane in registers, forward / inverse negacyclic NTTs over 1..3
+// auxiliary primes with shared-memory transposes, key images and twiddles resident in
+// shared memory, Garner CRT and the centred reduction mod q in the epilogue.
+// This file contains no CPU fallback: every entry point fails with RZK_ERR_CUDA when the
+// device is unavailable.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/ringzk_b200.h"
+#include "rzk_vm.h"
+
+namespace rzk {
+__constant__ uint32_t c_g1[kNumPrimeSlots][2][32][2];
+}
+#include "rzk_vm_exec.cuh"
+#include "rzk_programs.h"
+#include "rzk_tables.h"
+
+using namespace rzk;
+
+// ------------------------------------------------------------------------------ kernels
+
+template <int NP, int NSTASH>
+struct VmSmem {
+    static constexpr int kG2 = NP * 2 * kLanes * kG2Words;
+    static constexpr int kKey = NP * kKeyPolys * 2 * kPadWords;
+    static constexpr int kPerHw = kBufWords + 2 * kSlotWords + NSTASH * (NP - 1) * kSlotWords;
+    static_assert(kPerHw % 32 == 16, "half-warp regions must be shifted by 16 banks");
+    static constexpr size_t bytes(int warps) { return sizeof(uint32_t) * (size_t)(kG2 + kKey + warps * 2 * kPerHw); }
+};
+
+template <int NP, int NSTASH, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) rzk_vm_kernel(const __grid_constant__ VmLaunch K)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    using S = VmSmem<NP, NSTASH>;
+    uint32_t *s_g2 = smem;
+    uint32_t *s_key = s_g2 + S::kG2;
+    uint32_t *s_hw = s_key + S::kKey;
+
+    // stage the lane-specific twiddles and the key image of every prime of this launch
+    for (int i = 0; i < NP; ++i) {
+        const uint32_t slot = K.pc[i].slot;
+        const uint4 *g2src = reinterpret_cast<const uint4 *>(K.g2tab + (size_t)slot * (2 * kLanes * kG2Words));
+        uint4 *g2dst = reinterpret_cast<uint4 *>(s_g2 + i * (2 * kLanes * kG2Words));
+        for (int w = threadIdx.x; w < 2 * kLanes * kG2Words / 4; w += WARPS * 32) g2dst[w] = g2src[w];
+        const uint4 *ksrc = reinterpret_cast<const uint4 *>(K.keytab + (size_t)slot * (kKeyPolys * 2 * kPadWords));
+        uint4 *kdst = reinterpret_cast<uint4 *>(s_key + i * (kKeyPolys * 2 * kPadWords));
+        for (int w = threadIdx.x; w < kKeyPolys * 2 * kPadWords / 4; w += WARPS * 32) kdst[w] = ksrc[w];
+    }
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, hw = lane >> 4, t = lane & 15;
+    uint32_t *mine = s_hw + (warp * 2 + hw) * S::kPerHw;
+    ItemCtx ctx;
+    ctx.buf = mine;
+    ctx.slot = mine + kBufWords;
+    ctx.acc1 = mine + kBufWords + kSlotWords;
+    ctx.stash = mine + kBufWords + 2 * kSlotWords;
+    ctx.g2 = s_g2;
+    ctx.key = s_key;
+    ctx.g1 = nullptr;
+
+    const uint32_t per_grid = gridDim.x * WARPS * 2;
+    const uint32_t first = (blockIdx.x * WARPS + warp) * 2 + hw;
+    const uint32_t iters = (K.n_items + per_grid - 1) / per_grid;
+    Lane L;
+#pragma unroll 1
+    for (uint32_t it = 0; it < iters; ++it) {
+        const uint32_t item = first + it * per_grid;
+        ctx.active = item < K.n_items;
+        ctx.item = ctx.active ? item : K.n_items - 1;
+        vm_run_item<NP, NSTASH>(K, ctx, &L, t);
+    }
+}
+
+// bitmap[i>>3] bit (i&7) = (flags[i] & FLAG_FAIL) == 0 ; range_any |= FLAG_RANGE bits
+__global__ void rzk_flags_to_bitmap_kernel(size_t n, const uint32_t *__restrict__ flags,
+                                           uint8_t *__restrict__ bitmap, uint32_t *range_any)
+{
+    const size_t byte = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nbytes = (n + 7) / 8;
+    if (byte >= nbytes) return;
+    uint32_t bits = 0, rng = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const size_t i = byte * 8 + j;
+        if (i < n) {
+            const uint32_t f = flags[i];
+            bits |= ((f & FLAG_FAIL) ? 0u : 1u) << j;
+            rng |= f & FLAG_RANGE;
+        }
+    }
+    bitmap[byte] = (uint8_t)bits;
+    if (rng && range_any) atomicOr(range_any, rng);
+}
+
+// ZqI64::from(i64) for whole arrays: any representative -> canonical centred i32
+__global__ void rzk_pack_i64_kernel(size_t n, const int64_t *__restrict__ src, int32_t *__restrict__ dst, int64_t q)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const int64_t half = (q - 1) / 2;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        int64_t r = src[i] % q;
+        if (r > half) r -= q;
+        else if (r < -half) r += q;
+        dst[i] = (int32_t)r;
+    }
+}
+
+__global__ void rzk_unpack_i64_kernel(size_t n, const int32_t *__restrict__ src, int64_t *__restrict__ dst)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
+}
+
+// ------------------------------------------------------------------------------ engine
+
+namespace {
+
+constexpr int kPipe = 3;
+constexpr int kWarps1 = 8, kWarps2 = 8, kWarps3 = 6;
+
+struct PipeSlot {
+    cudaStream_t stream = nullptr;
+    char *arena = nullptr;
+    size_t cap = 0;
+};
+
+thread_local std::string g_create_err;
+
+}  // namespace
+
+struct rzk_engine {
+    rzk_params P;
+    int device = 0;
+    int num_sms = 0;
+    std::string err;
+    uint32_t *d_g2tab = nullptr;
+    uint32_t *d_keytab = nullptr;
+    uint32_t *d_misc = nullptr;     // [0] range word, [1] dummy flags word
+    bool has_key = false;
+    uint64_t sigma = 0, cbound = 0, vbound = 0;
+    uint32_t small_lim = 0;
+    PipeSlot pipe[kPipe];
+    char *scratch = nullptr;        // scratch of the `_dev` entry points
+    size_t scratch_cap = 0;
+    uint64_t launches = 0;
+};
+
+namespace {
+
+int fail(rzk_engine *e, int code, const std::string &msg)
+{
+    if (e) e->err = msg;
+    else g_create_err = msg;
+    return code;
+}
+
+#define RZK_CUDA(e, call)                                                                       \
+    do {                                                                                        \
+        cudaError_t err__ = (call);                                                             \
+        if (err__ != cudaSuccess)                                                               \
+            return fail((e), RZK_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(err__)); \
+    } while (0)
+
+uint64_t isqrt64(uint64_t v)
+{
+    uint64_t x = 0;
+    for (uint64_t bit = 1ull << 31; bit; bit >>= 1)
+        if ((x + bit) * (x + bit) <= v) x += bit;
+    return x;
+}
+
+struct Guard {
+    int prev = -1;
+    explicit Guard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~Guard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+void fill_common(const rzk_engine *e, VmLaunch &K, int np, uint32_t n_items, uint32_t flag_div, uint32_t *flags)
+{
+    static const int slots[3] = {0, 1, 2};
+    const uint64_t q = (uint64_t)e->P.q;
+    for (int i = 0; i < np; ++i) K.pc[i] = make_prime_consts(slots[i]);
+    K.crt = make_crt_consts(slots, np, q);
+    K.q = (uint32_t)q;
+    K.bar = (uint64_t)((((unsigned __int128)1) << 64) / q);
+    K.kq = q << 29;
+    K.norm_abs_lim[0] = (uint32_t)e->cbound; K.norm_sq_lim[0] = (e->cbound + 1) * (e->cbound + 1) - 1;
+    K.norm_abs_lim[1] = (uint32_t)e->vbound; K.norm_sq_lim[1] = (e->vbound + 1) * (e->vbound + 1) - 1;
+    K.small_lim = e->small_lim;
+    K.n_items = n_items;
+    K.np = (uint32_t)np;
+    if (flags) { K.flags = flags; K.flag_div = flag_div; }
+    else { K.flags = e->d_misc + 1; K.flag_div = 0xFFFFFFFFu; }
+    K.g2tab = e->d_g2tab;
+    K.keytab = e->d_keytab;
+}
+
+void set_stream(VmLaunch &K, int i, const void *base, uint32_t stride, uint32_t dtype, uint32_t div = 1)
+{
+    K.st[i].base = base; K.st[i].stride = stride; K.st[i].dtype = dtype; K.st[i].div = div; K.st[i].pad_ = 0;
+}
+
+template <int NP, int NSTASH, int WARPS>
+int launch_vm(rzk_engine *e, const VmLaunch &K, cudaStream_t s)
+{
+    if (K.n_items == 0) return RZK_OK;
+    auto kern = rzk_vm_kernel<NP, NSTASH, WARPS>;
+    const size_t smem = VmSmem<NP, NSTASH>::bytes(WARPS);
+    static bool configured[16] = {};   // per device
+    if (!configured[e->device & 15]) {
+        RZK_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[e->device & 15] = true;
+    }
+    const uint32_t per_cta = WARPS * 2;
+    uint32_t grid = (K.n_items + per_cta - 1) / per_cta;
+    if (grid > (uint32_t)e->num_sms) grid = (uint32_t)e->num_sms;
+    kern<<<grid, WARPS * 32, smem, s>>>(K);
+    RZK_CUDA(e, cudaGetLastError());
+    e->launches++;
+    return RZK_OK;
+}
+
+int launch_np(rzk_engine *e, int np, const VmLaunch &K, cudaStream_t s)
+{
+    if (np == 1) return launch_vm<1, 0, kWarps1>(e, K, s);
+    if (np == 2) return launch_vm<2, 2, kWarps2>(e, K, s);
+    return launch_vm<3, 1, kWarps3>(e, K, s);
+}
+
+int check_ready(rzk_engine *e, bool need_key = true)
+{
+    if (!e) return RZK_ERR_INVALID;
+    if (need_key && !e->has_key) return fail(e, RZK_ERR_NOKEY, "rzk_set_key has not been called");
+    return RZK_OK;
+}
+
+int ensure_scratch(rzk_engine *e, size_t bytes)
+{
+    if (bytes <= e->scratch_cap) return RZK_OK;
+    RZK_CUDA(e, cudaDeviceSynchronize());
+    if (e->scratch) cudaFree(e->scratch);
+    e->scratch = nullptr; e->scratch_cap = 0;
+    RZK_CUDA(e, cudaMalloc(&e->scratch, bytes));
+    e->scratch_cap = bytes;
+    return RZK_OK;
+}
+
+constexpr size_t kPolyBytes = (size_t)kN * sizeof(int32_t);
+
+// ---- phase lowering on device pointers (scratch supplied by the caller of these helpers) ----
+
+int dev_commit(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r, int32_t *c, uint32_t *flags, cudaStream_t s)
+{
+    VmLaunch K; memset(&K, 0, sizeof(K));
+    Prog p(&K);
+    prog_commit(p, 0, 1, 2);
+    p.end();
+    fill_common(e, K, 2, (uint32_t)B, 1, flags);
+    set_stream(K, 0, x, 1, DT_I32); set_stream(K, 1, r, 3, DT_I8); set_stream(K, 2, c, 2, DT_I32);
+    return launch_np(e, 2, K, s);
+}
+
+int dev_open_commit(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r, const int32_t *y,
+                    int32_t *c, int32_t *t, uint32_t *flags, cudaStream_t s)
+{
+    VmLaunch K; memset(&K, 0, sizeof(K));
+    Prog p(&K);
+    prog_commit(p, 0, 1, 2);
+    prog_keymatvec(p, 3, 4, -1, true);
+    p.end();
+    fill_common(e, K, 2, (uint32_t)B, 1, flags);
+    set_stream(K, 0, x, 1, DT_I32); set_stream(K, 1, r, 3, DT_I8); set_stream(K, 2, c, 2, DT_I32);
+    set_stream(K, 3, y, 3, DT_I32); set_stream(K, 4, t, 1, DT_I32);
+    return launch_np(e, 2, K, s);
+}
+
+int dev_respond(rzk_engine *e, size_t items, const int32_t *y, const int8_t *r, const int8_t *d, uint32_t d_div,
+                int32_t *z, cudaStream_t s)
+{
+    VmLaunch K; memset(&K, 0, sizeof(K));
+    Prog p(&K);
+    prog_respond(p, 0, 1, 2, 3);
+    p.end();
+    fill_common(e, K, 1, (uint32_t)items, 1, nullptr);
+    set_stream(K, 0, y, 3, DT_I32); set_stream(K, 1, r, 3, DT_I8); set_stream(K, 2, d, 1, DT_I8, d_div);
+    set_stream(K, 3, z, 3, DT_I32);
+    return launch_np(e, 1, K, s);
+}
+
+// norm check + first equation (+ optional w = A2.z - c2*d) for `items` responses
+int dev_verify_first(rzk_engine *e, size_t items, const int32_t *z, const int32_t *t, const int32_t *c, uint32_t c_stride,
+                     const int8_t *d, uint32_t d_div, int32_t *w, uint32_t *flags, uint32_t flag_div, cudaStream_t s)
+{
+    VmLaunch K; memset(&K, 0, sizeof(K));
+    Prog p(&K);
+    prog_norm_verify(p, 0);
+    prog_verify_first(p, 0, 1, 2, 3, w ? 4 : -1);
+    p.end();
+    fill_common(e, K, 2, (uint32_t)items, flag_div, flags);
+    set_stream(K, 0, z, 3, DT_I32); set_stream(K, 1, t, 1, DT_I32); set_stream(K, 2, c, c_stride, DT_I32);
+    set_stream(K, 3, d, 1, DT_I8, d_div);
+    if (w) set_stream(K, 4, w, 1, DT_I32);
+    return launch_np(e, 2, K, s);
+}
+
+// out = sum_{i<T} a_i*b_i - sub0 - sub1 (store) or == 0 (compare)
+int dev_mulsum(rzk_engine *e, size_t B, uint32_t T, const int32_t *a, const int32_t *b, const int32_t *sub0,
+               const int32_t *sub1, int32_t *out, uint32_t *flags, cudaStream_t s)
+{
+    VmLaunch K; memset(&K, 0, sizeof(K));
+    Prog p(&K);
+    prog_mulsum(p, (int)T, 0, 1, sub0 ? 2 : -1, sub1 ? 3 : -1, out ? 4 : -1, out ? FIN_STORE : FIN_CMPZ);
+    p.end();
+    fill_common(e, K, 3, (uint32_t)B, 1, flags);
+    set_stream(K, 0, a, T, DT_I32); set_stream(K, 1, b, T, DT_I32);
+    if (sub0) set_stream(K, 2, sub0, 1, DT_I32);
+    if (sub1) set_stream(K, 3, sub1, 1, DT_I32);
+    if (out) set_stream(K, 4, out, 1, DT_I32);
+    return launch_np(e, 3, K, s);
+}
+
+// commit(x; r) -> c  and  t = A1.y, w = A2.y  for `items` (x, r, y) triples
+int dev_commit_matvec(rzk_engine *e, size_t items, const int32_t *x, const int8_t *r, const int32_t *y,
+                      int32_t *c, int32_t *t, int32_t *w, uint32_t *flags, uint32_t flag_div, cudaStream_t s)
+{
+    VmLaunch K; memset(&K, 0, sizeof(K));
+    Prog p(&K);
+    prog_commit(p, 0, 1, 2);
+    prog_keymatvec(p, 3, 4, 5, true);
+    p.end();
+    fill_common(e, K, 2, (uint32_t)items, flag_div, flags);
+    set_stream(K, 0, x, 1, DT_I32); set_stream(K, 1, r, 3, DT_I8); set_stream(K, 2, c, 2, DT_I32);
+    set_stream(K, 3, y, 3, DT_I32); set_stream(K, 4, t, 1, DT_I32); set_stream(K, 5, w, 1, DT_I32);
+    return launch_np(e, 2, K, s);
+}
+
+#define RZK_TRY(x) do { int rc__ = (x); if (rc__ != RZK_OK) return rc__; } while (0)
+
+// scratch: 2*B polys
+int dev_linear_commit(rzk_engine *e, size_t B, const int32_t *g, const int32_t *x, const int8_t *rp, const int8_t *r,
+                      const int32_t *y, const int32_t *yp, int32_t *gx, int32_t *cp, int32_t *c, int32_t *t,
+                      int32_t *tp, int32_t *u, uint32_t *flags, int32_t *scratch, cudaStream_t s)
+{
+    int32_t *w = scratch, *wp = scratch + B * kN;
+    RZK_TRY(dev_mulsum(e, B, 1, g, x, nullptr, nullptr, gx, flags, s));                 // linear.rs:91-95
+    RZK_TRY(dev_commit_matvec(e, B, gx, rp, yp, cp, tp, wp, flags, 1, s));              // linear.rs:96,121,129
+    RZK_TRY(dev_commit_matvec(e, B, x, r, y, c, t, w, flags, 1, s));                    // linear.rs:97,118,124-127
+    return dev_mulsum(e, B, 1, g, w, wp, nullptr, u, flags, s);                         // linear.rs:124-129
+}
+
+int dev_linear_verify(rzk_engine *e, size_t B, const int32_t *z, const int32_t *zp, const int32_t *c, const int32_t *cp,
+                      const int32_t *g, const int32_t *t, const int32_t *tp, const int32_t *u, const int8_t *d,
+                      uint32_t *flags, int32_t *scratch, cudaStream_t s)
+{
+    int32_t *w = scratch, *wp = scratch + B * kN;
+    RZK_TRY(dev_verify_first(e, B, z, t, c, 2, d, 1, w, flags, 1, s));                  // linear.rs:218,225-229
+    RZK_TRY(dev_verify_first(e, B, zp, tp, cp, 2, d, 1, wp, flags, 1, s));              // linear.rs:221,231-235
+    return dev_mulsum(e, B, 1, g, w, wp, u, nullptr, flags, s);                         // linear.rs:236-249
+}
+
+// scratch: (B*T + B) polys
+int dev_sum_commit(rzk_engine *e, size_t B, uint32_t T, const int32_t *gs, const int32_t *xs, const int8_t *rp,
+                   const int8_t *rs, const int32_t *ys, const int32_t *yp, int32_t *xp, int32_t *cp, int32_t *cs,
+                   int32_t *ts, int32_t *tp, int32_t *u, uint32_t *flags, int32_t *scratch, cudaStream_t s)
+{
+    int32_t *ws = scratch, *wp = scratch + B * T * kN;
+    RZK_TRY(dev_mulsum(e, B, T, gs, xs, nullptr, nullptr, xp, flags, s));               // sum.rs:107-115
+    RZK_TRY(dev_commit_matvec(e, B, xp, rp, yp, cp, tp, wp, flags, 1, s));              // sum.rs:116,151,160
+    RZK_TRY(dev_commit_matvec(e, B * T, xs, rs, ys, cs, ts, ws, flags, T, s));          // sum.rs:117-120,145-148,157
+    return dev_mulsum(e, B, T, gs, ws, wp, nullptr, u, flags, s);                       // sum.rs:154-160
+}
+
+int dev_sum_verify(rzk_engine *e, size_t B, uint32_t T, const int32_t *zs, const int32_t *zp, const int32_t *cs,
+                   const int32_t *cp, const int32_t *gs, const int32_t *ts, const int32_t *tp, const int32_t *u,
+                   const int8_t *d, uint32_t *flags, int32_t *scratch, cudaStream_t s)
+{
+    int32_t *ws = scratch, *wp = scratch + B * T * kN;
+    RZK_TRY(dev_verify_first(e, B * T, zs, ts, cs, 2, d, T, ws, flags, T, s));          // sum.rs:262-268,277-291
+    RZK_TRY(dev_verify_first(e, B, zp, tp, cp, 2, d, 1, wp, flags, 1, s));              // sum.rs:269,293-298
+    return dev_mulsum(e, B, T, gs, ws, wp, u, nullptr, flags, s);                       // sum.rs:300-319
+}
+
+// ---- chunked host pipeline -----------------------------------------------------------------
+
+struct HArr {
+    const void *in;      // host input  (or nullptr)
+    void *out;           // host output (or nullptr)
+    size_t per_item;     // bytes per item
+};
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// fn(chunk_items, dptr[], scratch, flags, stream)
+template <class F>
+int run_chunked(rzk_engine *e, size_t B, std::vector<HArr> &arrs, size_t scratch_per_item, uint8_t *bitmap, F &&fn)
+{
+    if (B == 0) return RZK_OK;
+    Guard g(e->device);
+    size_t per_item = scratch_per_item + sizeof(uint32_t) + 1;
+    for (auto &a : arrs) per_item += a.per_item;
+    size_t chunk = (size_t)(96ull << 20) / per_item;
+    chunk = std::max<size_t>(8, std::min<size_t>(chunk, 16384)) / 8 * 8;
+    if (chunk > B) chunk = align_up(B, 8);
+    // arena layout for one pipeline slot
+    std::vector<size_t> offs(arrs.size());
+    size_t off = 0;
+    for (size_t i = 0; i < arrs.size(); ++i) { offs[i] = off; off += align_up(arrs[i].per_item * chunk, 256); }
+    const size_t off_scratch = off; off += align_up(scratch_per_item * chunk, 256);
+    const size_t off_flags = off; off += align_up(sizeof(uint32_t) * chunk, 256);
+    const size_t off_bitmap = off; off += align_up(chunk / 8 + 1, 256);
+    const size_t need = off;
+    for (int i = 0; i < kPipe; ++i) {
+        PipeSlot &ps = e->pipe[i];
+        if (ps.cap < need) {
+            RZK_CUDA(e, cudaStreamSynchronize(ps.stream));
+            if (ps.arena) cudaFree(ps.arena);
+            ps.arena = nullptr; ps.cap = 0;
+            RZK_CUDA(e, cudaMalloc(&ps.arena, need));
+            ps.cap = need;
+        }
+    }
+    RZK_CUDA(e, cudaMemsetAsync(e->d_misc, 0, sizeof(uint32_t), e->pipe[0].stream));
+    RZK_CUDA(e, cudaStreamSynchronize(e->pipe[0].stream));
+    std::vector<void *> dptr(arrs.size());
+    int ci = 0;
+    for (size_t c0 = 0; c0 < B; c0 += chunk, ++ci) {
+        const size_t n = std::min(chunk, B - c0);
+        PipeSlot &ps = e->pipe[ci % kPipe];
+        cudaStream_t s = ps.stream;
+        for (size_t i = 0; i < arrs.size(); ++i) {
+            dptr[i] = ps.arena + offs[i];
+            if (arrs[i].in)
+                RZK_CUDA(e, cudaMemcpyAsync(dptr[i], (const char *)arrs[i].in + c0 * arrs[i].per_item,
+                                            n * arrs[i].per_item, cudaMemcpyHostToDevice, s));
+        }
+        uint32_t *dflags = reinterpret_cast<uint32_t *>(ps.arena + off_flags);
+        RZK_CUDA(e, cudaMemsetAsync(dflags, 0, sizeof(uint32_t) * n, s));
+        RZK_TRY(fn(n, dptr.data(), ps.arena + off_scratch, dflags, s));
+        if (bitmap) {
+            uint8_t *dbm = reinterpret_cast<uint8_t *>(ps.arena + off_bitmap);
+            const size_t nbytes = (n + 7) / 8;
+            rzk_flags_to_bitmap_kernel<<<(unsigned)((nbytes + 127) / 128), 128, 0, s>>>(n, dflags, dbm, e->d_misc);
+            RZK_CUDA(e, cudaGetLastError());
+            e->launches++;
+            RZK_CUDA(e, cudaMemcpyAsync(bitmap + c0 / 8, dbm, nbytes, cudaMemcpyDeviceToHost, s));
+        }
+        for (size_t i = 0; i < arrs.size(); ++i)
+            if (arrs[i].out)
+                RZK_CUDA(e, cudaMemcpyAsync((char *)arrs[i].out + c0 * arrs[i].per_item, dptr[i],
+                                            n * arrs[i].per_item, cudaMemcpyDeviceToHost, s));
+    }
+    for (int i = 0; i < kPipe; ++i) RZK_CUDA(e, cudaStreamSynchronize(e->pipe[i].stream));
+    uint32_t range = 0;
+    RZK_CUDA(e, cudaMemcpy(&range, e->d_misc, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (range & FLAG_RANGE)
+        return fail(e, RZK_ERR_RANGE, "a masking vector y exceeds rzk_small_limit(); affected outputs are not exact");
+    return RZK_OK;
+}
+
+bool any_null(std::initializer_list<const void *> ps)
+{
+    for (auto p : ps) if (!p) return true;
+    return false;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------ C ABI
+
+extern "C" {
+
+rzk_params rzk_default_params(int32_t N)
+{
+    rzk_params P;
+    P.q = 3515337053LL; P.b = 1; P.N = N; P.n = 1; P.k = 3; P.l = 1; P.kappa = 36;   // params.rs:121-138
+    return P;
+}
+
+const char *rzk_last_error(const rzk_engine *e) { return e ? e->err.c_str() : g_create_err.c_str(); }
+int rzk_device(const rzk_engine *e) { return e ? e->device : -1; }
+uint64_t rzk_sigma(const rzk_engine *e) { return e->sigma; }
+uint64_t rzk_commit_bound(const rzk_engine *e) { return e->cbound; }
+uint64_t rzk_verify_bound(const rzk_engine *e) { return e->vbound; }
+uint32_t rzk_small_limit(const rzk_engine *e) { return e->small_lim; }
+uint64_t rzk_kernel_launches(const rzk_engine *e) { return e->launches; }
+
+int rzk_create(const rzk_params *params, int device, rzk_engine **out)
+{
+    if (!params || !out) return fail(nullptr, RZK_ERR_INVALID, "null argument");
+    *out = nullptr;
+    const rzk_params &P = *params;
+    if (P.N != kN || P.n != 1 || P.k != 3 || P.l != 1)
+        return fail(nullptr, RZK_ERR_UNSUPPORTED, "only N=512, (n,k,l)=(1,3,1) is accelerated");
+    if (P.q != 3515337053LL || P.b < 1 || P.b > 127 || P.kappa < 1)
+        return fail(nullptr, RZK_ERR_UNSUPPORTED, "only q=3515337053 with 1 <= b <= 127 is accelerated");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(nullptr, RZK_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(ce));
+    if (device < 0) RZK_CUDA(nullptr, cudaGetDevice(&device));
+    if (device >= ndev) return fail(nullptr, RZK_ERR_INVALID, "device index out of range");
+    rzk_engine *e = new rzk_engine();
+    e->P = P;
+    e->device = device;
+    Guard g(device);
+    cudaDeviceProp prop;
+    ce = cudaGetDeviceProperties(&prop, device);
+    if (ce != cudaSuccess) { delete e; return fail(nullptr, RZK_ERR_CUDA, cudaGetErrorString(ce)); }
+    if (prop.major < 10) { delete e; return fail(nullptr, RZK_ERR_CUDA, "an sm_100a (Blackwell) device is required"); }
+    e->num_sms = prop.multiProcessorCount;
+    // params.rs:94-98, 104, 114
+    e->sigma = (uint64_t)P.b * (uint64_t)(11 * P.kappa) * isqrt64((uint64_t)P.k * (uint64_t)P.N);
+    e->cbound = 4 * e->sigma * isqrt64((uint64_t)P.N);
+    e->vbound = 2 * e->sigma * isqrt64((uint64_t)P.N);
+    {
+        // |y| bound keeping  y0 + a11*y1 + a12*y2  inside the centred range of the two-prime CRT
+        static const int slots[2] = {0, 1};
+        CrtC c = make_crt_consts(slots, 2, (uint64_t)P.q);
+        const uint64_t half = (uint64_t)(P.q - 1) / 2;
+        e->small_lim = (uint32_t)((c.P01half - (1ull << 33)) / ((uint64_t)(P.k - P.n) * (uint64_t)P.N * half));
+    }
+    // static tables
+    std::vector<uint32_t> g1((size_t)kNumPrimeSlots * 2 * 32 * 2), g2((size_t)kNumPrimeSlots * 2 * kLanes * kG2Words);
+    for (int s = 0; s < kNumPrimeSlots; ++s) {
+        const PrimeTables &T = prime_tables(s);
+        memcpy(&g1[(size_t)s * 2 * 32 * 2], T.g1, sizeof(T.g1));
+        memcpy(&g2[(size_t)s * 2 * kLanes * kG2Words], T.g2, sizeof(T.g2));
+    }
+    int rc = RZK_OK;
+    auto cu = [&](cudaError_t err, const char *what) {
+        if (err != cudaSuccess && rc == RZK_OK) rc = fail(nullptr, RZK_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(err));
+    };
+    cu(cudaMemcpyToSymbol(c_g1, g1.data(), g1.size() * sizeof(uint32_t)), "cudaMemcpyToSymbol(c_g1)");
+    cu(cudaMalloc(&e->d_g2tab, g2.size() * sizeof(uint32_t)), "cudaMalloc(g2)");
+    if (rc == RZK_OK) cu(cudaMemcpy(e->d_g2tab, g2.data(), g2.size() * sizeof(uint32_t), cudaMemcpyHostToDevice), "cudaMemcpy(g2)");
+    cu(cudaMalloc(&e->d_keytab, (size_t)kNumPrimeSlots * kKeyPolys * 2 * kPadWords * sizeof(uint32_t)), "cudaMalloc(key)");
+    cu(cudaMalloc(&e->d_misc, 64), "cudaMalloc(misc)");
+    if (rc == RZK_OK) cu(cudaMemset(e->d_misc, 0, 64), "cudaMemset(misc)");
+    for (int i = 0; i < kPipe && rc == RZK_OK; ++i) cu(cudaStreamCreateWithFlags(&e->pipe[i].stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    if (rc != RZK_OK) { rzk_destroy(e); return rc; }
+    *out = e;
+    return RZK_OK;
+}
+
+void rzk_destroy(rzk_engine *e)
+{
+    if (!e) return;
+    Guard g(e->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < kPipe; ++i) {
+        if (e->pipe[i].arena) cudaFree(e->pipe[i].arena);
+        if (e->pipe[i].stream) cudaStreamDestroy(e->pipe[i].stream);
+    }
+    if (e->scratch) cudaFree(e->scratch);
+    if (e->d_g2tab) cudaFree(e->d_g2tab);
+    if (e->d_keytab) cudaFree(e->d_keytab);
+    if (e->d_misc) cudaFree(e->d_misc);
+    delete e;
+}
+
+int rzk_set_key(rzk_engine *e, const int64_t *a1, const int64_t *a2)
+{
+    RZK_TRY(check_ready(e, false));
+    if (!a1 || !a2) return fail(e, RZK_ERR_INVALID, "null key");
+    Guard g(e->device);
+    const int k = e->P.k;
+    // commit.rs:38-57: a1 = [1 | a11 a12], a2 = [0 | 1 | a22]
+    auto is_const = [&](const int64_t *p, int64_t c0) {
+        if (p[0] != c0) return false;
+        for (int i = 1; i < kN; ++i) if (p[i] != 0) return false;
+        return true;
+    };
+    if (!is_const(a1, 1) || !is_const(a2, 0) || !is_const(a2 + kN, 1))
+        return fail(e, RZK_ERR_UNSUPPORTED, "key does not have the [I | a1'], [0 | I | a2'] structure of commit.rs:33-60");
+    (void)k;
+    const int64_t *polys[kKeyPolys] = {a1 + kN, a1 + 2 * kN, a2 + 2 * kN};
+    std::vector<uint32_t> img((size_t)kNumPrimeSlots * kKeyPolys * 2 * kPadWords, 0);
+    const int64_t q = e->P.q, half = (q - 1) / 2;
+    std::vector<int64_t> cen(kN);
+    for (int s = 0; s < 3; ++s) {               // the 30-bit prime slots used by the launches
+        const PrimeTables &T = prime_tables(s);
+        for (int kk = 0; kk < kKeyPolys; ++kk) {
+            for (int i = 0; i < kN; ++i) {
+                int64_t r = polys[kk][i] % q;
+                if (r > half) r -= q; else if (r < -half) r += q;
+                cen[i] = r;
+            }
+            key_image(T, cen.data(), &img[((size_t)s * kKeyPolys + kk) * 2 * kPadWords]);
+        }
+    }
+    RZK_CUDA(e, cudaDeviceSynchronize());
+    RZK_CUDA(e, cudaMemcpy(e->d_keytab, img.data(), img.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    e->has_key = true;
+    return RZK_OK;
+}
+
+void *rzk_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void rzk_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int rzk_sync(rzk_engine *e, void *stream)
+{
+    RZK_TRY(check_ready(e, false));
+    Guard g(e->device);
+    RZK_CUDA(e, cudaStreamSynchronize((cudaStream_t)stream));
+    return RZK_OK;
+}
+
+// ---- device-resident entry points ----
+
+int rzk_commit_batch_dev(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r, int32_t *c, uint32_t *flags, void *stream)
+{
+    RZK_TRY(check_ready(e));
+    if (any_null({x, r, c, flags})) return fail(e, RZK_ERR_INVALID, "null argument");
+    Guard g(e->device);
+    return dev_commit(e, B, x, r, c, flags, (cudaStream_t)stream);
+}
+
+int rzk_open_commit_batch_dev(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r, const int32_t *y,
+                              int32_t *c, int32_t *t, uint32_t *flags, void *stream)
+{
+    RZK_TRY(check_ready(e));
+    if (any_null({x, r, y, c, t, flags})) return fail(e, RZK_ERR_INVALID, "null argument");
+    Guard g(e->device);
+    return dev_open_commit(e, B, x, r, y, c, t, flags, (cudaStream_t)stream);
+}
+
+int rzk_open_respond_batch_dev(rzk_engine *e, size_t B, const int32_t *y, const int8_t *r, const int8_t *d, int32_t *z, void *stream)
+{
+    RZK_TRY(check_ready(e));
+    if (any_null({y, r, d, z})) return fail(e, RZK_ERR_INVALID, "null argument");
+    Guard g(e->device);
+    return dev_respond(e, B, y, r, d, 1, z, (cudaStream_t)stream);
+}
+
+int rzk_open_verify_batch_dev(rzk_engine *e, size_t B, const int32_t *z, const int32_t *t, const int32_t *c, uint32_t c_stride,
+                              const int8_t *d, uint32_t *flags, void *stream)
+{
+    RZK_TRY(check_ready(e));
+    if (any_null({z, t, c, d, flags}) || c_stride < 1) return fail(e, RZK_ERR_INVALID, "null argument");
+    Guard g(e->device);
+    return dev_verify_first(e, B, z, t, c, c_stride, d, 1, nullptr, flags, 1, (cudaStream_t)stream);
+}
+
+int rzk_linear_commit_batch_dev(rzk_engine *e, size_t B, const int32_t *g, const int32_t *x, const int8_t *rp, const int8_t *r,
+                                const int32_t *y, const int32_t *yp, int32_t *gx, int32_t *cp, int32_t *c, int32_t *t,
+                                int32_t *tp, int32_t *u, uint32_t *flags, void *stream)
+{
+    RZK_TRY(check_ready(e));
+    if (any_null({g, x, rp, r, y, yp, gx, cp, c, t, tp, u, flags})) return fail(e, RZK_ERR_INVALID, "null argument");
+    Guard gd(e->device);
+    RZK_TRY(ensure_scratch(e, 2 * B * kPolyBytes));
+    return dev_linear_commit(e, B, g, x, rp, r, y, yp, gx, cp, c, t, tp, u, flags, (int32_t *)e->scratch, (cudaStream_t)stream);
+}
+
+int rzk_linear_respond_batch_dev(rzk_engine *e, size_t B, const int32_t *y, const int32_t *yp, const int8_t *r, const int8_t *rp,
+                                 const int8_t *d, int32_t *z, int32_t *zp, void *stream)
+{
+    RZK_TRY(check_ready(e));
+    if (any_null({y, yp, r, rp, d, z, zp})) return fail(e, RZK_ERR_INVALID, "null argument");
+    Guard g(e->device);
+    RZK_TRY(dev_respond(e, B, y, r, d, 1, z, (cudaStream_t)stream));           // linear.rs:150-152
+    return dev_respond(e, B, yp, rp, d, 1, zp, (cudaStream_t)stream);          // linear.rs:154-156
+}
+
+int rzk_linear_verify_batch_dev(rzk_engine *e, size_t B, const int32_t *z, const int32_t *zp, const int32_t *c, const int32_t *cp,
+                                const int32_t *g, const int32_t *t, const int32_t *tp, const int32_t *u, const int8_t *d,
+                                uint32_t *flags, void *stream)
+{
+    RZK_TRY(check_ready(e));
+    if (any_null({z, zp, c, cp, g, t, tp, u, d, flags})) return fail(e, RZK_ERR_INVALID, "null argument");
+    Guard gd(e->device);
+    RZK_TRY(ensure_scratch(e, 2 * B * kPolyBytes));
+    return dev_linear_verify(e, B, z, zp, c, cp, g, t, tp, u, d, flags, (int32_t *)e->scratch, (cudaStream_t)stream);
+}
+
+int rzk_sum_commit_batch_dev(rzk_engine *e, size_t B, uint32_t T, const int32_t *gs, const int32_t *xs, const int8_t *rp,
+                             const int8_t *rs, const int32_t *ys, const int32_t *yp, int32_t *xp, int32_t *cp, int32_t *cs,
+                             int32_t *ts, int32_t *tp, int32_t *u, uint32_t *flags, void *stream)
+{
+    RZK_TRY(check_ready(e));
+    if (T == 0 || T > 65535) return fail(e, RZK_ERR_INVALID, "T must be in 1..65535 (sum.rs:105)");
+    if (any_null({gs, xs, rp, rs, ys, yp, xp, cp, cs, ts, tp, u, flags})) return fail(e, RZK_ERR_INVALID, "null argument");
+    Guard gd(e->device);
+    RZK_TRY(ensure_scratch(e, (B * T + B) * kPolyBytes));
+    return dev_sum_commit(e, B, T, gs, xs, rp, rs, ys, yp, xp, cp, cs, ts, tp, u, flags, (int32_t *)e->scratch, (cudaStream_t)stream);
+}
+
+int rzk_sum_respond_batch_dev(rzk_engine *e, size_t B, uint32_t T, const int32_t *ys, const int32_t *yp, const int8_t *rs,
+                              const int8_t *rp, const int8_t *d, int32_t *zs, int32_t *zp, void *stream)
+{
+    RZK_TRY(check_ready(e));
+    if (T == 0 || T > 65535) return fail(e, RZK_ERR_INVALID, "T must be in 1..65535");
+    if (any_null({ys, yp, rs, rp, d, zs, zp})) return fail(e, RZK_ERR_INVALID, "null argument");
+    Guard g(e->device);
+    RZK_TRY(dev_respond(e, B * T, ys, rs, d, T, zs, (cudaStream_t)stream));    // sum.rs:188-193
+    return dev_respond(e, B, yp, rp, d, 1, zp, (cudaStream_t)stream);          // sum.rs:195-197
+}
+
+int rzk_sum_verify_batch_dev(rzk_engine *e, size_t B, uint32_t T, const int32_t *zs, const int32_t *zp, const int32_t *cs,
+                             const int32_t *cp, const int32_t *gs, const int32_t *ts, const int32_t *tp, const int32_t *u,
+                             const int8_t *d, uint32_t *flags, void *stream)
+{
+    RZK_TRY(check_ready(e));
+    if (T == 0 || T > 65535) return fail(e, RZK_ERR_INVALID, "T must be in 1..65535");
+    if (any_null({zs, zp, cs, cp, gs, ts, tp, u, d, flags})) return fail(e, RZK_ERR_INVALID, "null argument");
+    Guard gd(e->device);
+    RZK_TRY(ensure_scratch(e, (B * T + B) * kPolyBytes));
+    return dev_sum_verify(e, B, T, zs, zp, cs, cp, gs, ts, tp, u, d, flags, (int32_t *)e->scratch, (cudaStream_t)stream);
+}
+
+int rzk_flags_to_bitmap_dev(rzk_engine *e, size_t B, const uint32_t *flags, uint8_t *bitmap, uint32_t *range_any, void *stream)
+{
+    RZK_TRY(check_ready(e, false));
+    if (any_null({flags, bitmap})) return fail(e, RZK_ERR_INVALID, "null argument");
+    if (B == 0) return RZK_OK;
+    Guard g(e->device);
+    const size_t nbytes = (B + 7) / 8;
+    rzk_flags_to_bitmap_kernel<<<(unsigned)((nbytes + 127) / 128), 128, 0, (cudaStream_t)stream>>>(B, flags, bitmap, range_any);
+    RZK_CUDA(e, cudaGetLastError());
+    e->launches++;
+    return RZK_OK;
+}
+
+// ---- host entry points ----
+
+int rzk_commit_batch(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r, int32_t *c, uint8_t *ok)
+{
+    RZK_TRY(check_ready(e));
+    if (any_null({x, r, c, ok})) return fail(e, RZK_ERR_INVALID, "null argument");
+    std::vector<HArr> a = {{x, nullptr, kPolyBytes}, {r, nullptr, 3 * kN}, {nullptr, c, 2 * kPolyBytes}};
+    return run_chunked(e, B, a, 0, ok, [&](size_t n, void **d, char *, uint32_t *fl, cudaStream_t s) {
+        return dev_commit(e, n, (const int32_t *)d[0], (const int8_t *)d[1], (int32_t *)d[2], fl, s);
+    });
+}
+
+int rzk_open_commit_batch(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r, const int32_t *y,
+                          int32_t *c, int32_t *t, uint8_t *ok)
+{
+    RZK_TRY(check_ready(e));
+    if (any_null({x, r, y, c, t, ok})) return fail(e, RZK_ERR_INVALID, "null argument");
+    std::vector<HArr> a = {{x, nullptr, kPolyBytes}, {r, nullptr, 3 * kN}, {y, nullptr, 3 * kPolyBytes},
+                           {nullptr, c, 2 * kPolyBytes}, {nullptr, t, kPolyBytes}};
+    return run_chunked(e, B, a, 0, ok, [&](size_t n, void **d, char *, uint32_t *fl, cudaStream_t s) {
+        return dev_open_commit(e, n, (const int32_t *)d[0], (const int8_t *)d[1], (const int32_t *)d[2],
+                               (int32_t *)d[3], (int32_t *)d[4], fl, s);
+    });
+}
+
+int rzk_open_respond_batch(rzk_engine *e, size_t B, const int32_t *y, const int8_t *r, const int8_t *dch, int32_t *z)
+{
+    RZK_TRY(check_ready(e));
+    if (any_null({y, r, dch, z})) return fail(e, RZK_ERR_INVALID, "null argument");
+    std::vector<HArr> a = {{y, nullptr, 3 * kPolyBytes}, {r, nullptr, 3 * kN}, {dch, nullptr, kN}, {nullptr, z, 3 * kPolyBytes}};
+    return run_chunked(e, B, a, 0, nullptr, [&](size_t n, void **d, char *, uint32_t *, cudaStream_t s) {
+        return dev_respond(e, n, (const int32_t *)d[0], (const int8_t *)d[1], (const int8_t *)d[2], 1, (int32_t *)d[3], s);
+    });
+}
+
+int rzk_open_verify_batch(rzk_engine *e, size_t B, const int32_t *z, const int32_t *t, const int32_t *c1, const int8_t *dch, uint8_t *bm)
+{
+    RZK_TRY(check_ready(e));
+    if (any_null({z, t, c1, dch, bm})) return fail(e, RZK_ERR_INVALID, "null argument");
+    std::vector<HArr> a = {{z, nullptr, 3 * kPolyBytes}, {t, nullptr, kPolyBytes}, {c1, nullptr, kPolyBytes}, {dch, nullptr, kN}};
+    return run_chunked(e, B, a, 0, bm, [&](size_t n, void **d, char *, uint32_t *fl, cudaStream_t s) {
+        return dev_verify_first(e, n, (const int32_t *)d[0], (const int32_t *)d[1], (const int32_t *)d[2], 1,
+                                (const int8_t *)d[3], 1, nullptr, fl, 1, s);
+    });
+}
+
+int rzk_linear_commit_batch(rzk_engine *e, size_t B, const int32_t *g, const int32_t *x, const int8_t *rp, const int8_t *r,
+                            const int32_t *y, const int32_t *yp, int32_t *gx, int32_t *cp, int32_t *c, int32_t *t,
+                            int32_t *tp, int32_t *u, uint8_t *ok)
+{
+    RZK_TRY(check_ready(e));
+    if (any_null({g, x, rp, r, y, yp, gx, cp, c, t, tp, u, ok})) return fail(e, RZK_ERR_INVALID, "null argument");
+    std::vector<HArr> a = {{g, nullptr, kPolyBytes}, {x, nullptr, kPolyBytes}, {rp, nullptr, 3 * kN}, {r, nullptr, 3 * kN},
+                           {y, nullptr, 3 * kPolyBytes}, {yp, nullptr, 3 * kPolyBytes},
+                           {nullptr, gx, kPolyBytes}, {nullptr, cp, 2 * kPolyBytes}, {nullptr, c, 2 * kPolyBytes},
+                           {nullptr, t, kPolyBytes}, {nullptr, tp, kPolyBytes}, {nullptr, u, kPolyBytes}};
+    return run_chunked(e, B, a, 2 * kPolyBytes, ok, [&](size_t n, void **d, char *sc, uint32_t *fl, cudaStream_t s) {
+        return dev_linear_commit(e, n, (const int32_t *)d[0], (const int32_t *)d[1], (const int8_t *)d[2], (const int8_t *)d[3],
+                                 (const int32_t *)d[4], (const int32_t *)d[5], (int32_t *)d[6], (int32_t *)d[7], (int32_t *)d[8],
+                                 (int32_t *)d[9], (int32_t *)d[10], (int32_t *)d[11], fl, (int32_t *)sc, s);
+    });
+}
+
+int rzk_linear_respond_batch(rzk_engine *e, size_t B, const int32_t *y, const int32_t *yp, const int8_t *r, const int8_t *rp,
+                             const int8_t *dch, int32_t *z, int32_t *zp)
+{
+    RZK_TRY(check_ready(e));
+    if (any_null({y, yp, r, rp, dch, z, zp})) return fail(e, RZK_ERR_INVALID, "null argument");
+    std::vector<HArr> a = {{y, nullptr, 3 * kPolyBytes}, {yp, nullptr, 3 * kPolyBytes}, {r, nullptr, 3 * kN}, {rp, nullptr, 3 * kN},
+                           {dch, nullptr, kN}, {nullptr, z, 3 * kPolyBytes}, {nullptr, zp, 3 * kPolyBytes}};
+    return run_chunked(e, B, a, 0, nullptr, [&](size_t n, void **d, char *, uint32_t *, cudaStream_t s) {
+        RZK_TRY(dev_respond(e, n, (const int32_t *)d[0], (const int8_t *)d[2], (const int8_t *)d[4], 1, (int32_t *)d[5], s));
+        return dev_respond(e, n, (const int32_t *)d[1], (const int8_t *)d[3], (const int8_t *)d[4], 1, (int32_t *)d[6], s);
+    });
+}
+
+int rzk_linear_verify_batch(rzk_engine *e, size_t B, const int32_t *z, const int32_t *zp, const int32_t *c, const int32_t *cp,
+                            const int32_t *g, const int32_t *t, const int32_t *tp, const int32_t *u, const int8_t *dch, uint8_t *bm)
+{
+    RZK_TRY(check_ready(e));
+    if (any_null({z, zp, c, cp, g, t, tp, u, dch, bm})) return fail(e, RZK_ERR_INVALID, "null argument");
+    std::vector<HArr> a = {{z, nullptr, 3 * kPolyBytes}, {zp, nullptr, 3 * kPolyBytes}, {c, nullptr, 2 * kPolyBytes},
+                           {cp, nullptr, 2 * kPolyBytes}, {g, nullptr, kPolyBytes}, {t, nullptr, kPolyBytes},
+                           {tp, nullptr, kPolyBytes}, {u, nullptr, kPolyBytes}, {dch, nullptr, kN}};
+    return run_chunked(e, B, a, 2 * kPolyBytes, bm, [&](size_t n, void **d, char *sc, uint32_t *fl, cudaStream_t s) {
+        return dev_linear_verify(e, n, (const int32_t *)d[0], (const int32_t *)d[1], (const int32_t *)d[2], (const int32_t *)d[3],
+                                 (const int32_t *)d[4], (const int32_t *)d[5], (const int32_t *)d[6], (const int32_t *)d[7],
+                                 (const int8_t *)d[8], fl, (int32_t *)sc, s);
+    });
+}
+
+int rzk_sum_commit_batch(rzk_engine *e, size_t B, uint32_t T, const int32_t *gs, const int32_t *xs, const int8_t *rp,
+                         const int8_t *rs, const int32_t *ys, const int32_t *yp, int32_t *xp, int32_t *cp, int32_t *cs,
+                         int32_t *ts, int32_t *tp, int32_t *u, uint8_t *ok)
+{
+    RZK_TRY(check_ready(e));
+    if (T == 0 || T > 65535) return fail(e, RZK_ERR_INVALID, "T must be in 1..65535 (sum.rs:105)");
+    if (any_null({gs, xs, rp, rs, ys, yp, xp, cp, cs, ts, tp, u, ok})) return fail(e, RZK_ERR_INVALID, "null argument");
+    std::vector<HArr> a = {{gs, nullptr, T * kPolyBytes}, {xs, nullptr, T * kPolyBytes}, {rp, nullptr, 3 * kN},
+                           {rs, nullptr, (size_t)T * 3 * kN}, {ys, nullptr, T * 3 * kPolyBytes}, {yp, nullptr, 3 * kPolyBytes},
+                           {nullptr, xp, kPolyBytes}, {nullptr, cp, 2 * kPolyBytes}, {nullptr, cs, T * 2 * kPolyBytes},
+                           {nullptr, ts, T * kPolyBytes}, {nullptr, tp, kPolyBytes}, {nullptr, u, kPolyBytes}};
+    return run_chunked(e, B, a, (T + 1) * kPolyBytes, ok, [&](size_t n, void **d, char *sc, uint32_t *fl, cudaStream_t s) {
+        return dev_sum_commit(e, n, T, (const int32_t *)d[0], (const int32_t *)d[1], (const int8_t *)d[2], (const int8_t *)d[3],
+                              (const int32_t *)d[4], (const int32_t *)d[5], (int32_t *)d[6], (int32_t *)d[7], (int32_t *)d[8],
+                              (int32_t *)d[9], (int32_t *)d[10], (int32_t *)d[11], fl, (int32_t *)sc, s);
+    });
+}
+
+int rzk_sum_respond_batch(rzk_engine *e, size_t B, uint32_t T, const int32_t *ys, const int32_t *yp, const int8_t *rs,
+                          const int8_t *rp, const int8_t *dch, int32_t *zs, int32_t *zp)
+{
+    RZK_TRY(check_ready(e));
+    if (T == 0 || T > 65535) return fail(e, RZK_ERR_INVALID, "T must be in 1..65535");
+    if (any_null({ys, yp, rs, rp, dch, zs, zp})) return fail(e, RZK_ERR_INVALID, "null argument");
+    std::vector<HArr> a = {{ys, nullptr, T * 3 * kPolyBytes}, {yp, nullptr, 3 * kPolyBytes}, {rs, nullptr, (size_t)T * 3 * kN},
+                           {rp, nullptr, 3 * kN}, {dch, nullptr, kN}, {nullptr, zs, T * 3 * kPolyBytes}, {nullptr, zp, 3 * kPolyBytes}};
+    return run_chunked(e, B, a, 0, nullptr, [&](size_t n, void **d, char *, uint32_t *, cudaStream_t s) {
+        RZK_TRY(dev_respond(e, n * T, (const int32_t *)d[0], (const int8_t *)d[2], (const int8_t *)d[4], T, (int32_t *)d[5], s));
+        return dev_respond(e, n, (const int32_t *)d[1], (const int8_t *)d[3], (const int8_t *)d[4], 1, (int32_t *)d[6], s);
+    });
+}
+
+int rzk_sum_verify_batch(rzk_engine *e, size_t B, uint32_t T, const int32_t *zs, const int32_t *zp, const int32_t *cs,
+                         const int32_t *cp, const int32_t *gs, const int32_t *ts, const int32_t *tp, const int32_t *u,
+                         const int8_t *dch, uint8_t *bm)
+{
+    RZK_TRY(check_ready(e));
+    if (T == 0 || T > 65535) return fail(e, RZK_ERR_INVALID, "T must be in 1..65535");
+    if (any_null({zs, zp, cs, cp, gs, ts, tp, u, dch, bm})) return fail(e, RZK_ERR_INVALID, "null argument");
+    std::vector<HArr> a = {{zs, nullptr, T * 3 * kPolyBytes}, {zp, nullptr, 3 * kPolyBytes}, {cs, nullptr, T * 2 * kPolyBytes},
+                           {cp, nullptr, 2 * kPolyBytes}, {gs, nullptr, T * kPolyBytes}, {ts, nullptr, T * kPolyBytes},
+                           {tp, nullptr, kPolyBytes}, {u, nullptr, kPolyBytes}, {dch, nullptr, kN}};
+    return run_chunked(e, B, a, (T + 1) * kPolyBytes, bm, [&](size_t n, void **d, char *sc, uint32_t *fl, cudaStream_t s) {
+        return dev_sum_verify(e, n, T, (const int32_t *)d[0], (const int32_t *)d[1], (const int32_t *)d[2], (const int32_t *)d[3],
+                              (const int32_t *)d[4], (const int32_t *)d[5], (const int32_t *)d[6], (const int32_t *)d[7],
+                              (const int8_t *)d[8], fl, (int32_t *)sc, s);
+    });
+}
+
+// ---- i64 staging ----
+
+int rzk_pack_i64(rzk_engine *e, size_t count, const int64_t *src, int32_t *dst)
+{
+    RZK_TRY(check_ready(e, false));
+    if (any_null({src, dst})) return fail(e, RZK_ERR_INVALID, "null argument");
+    const int64_t q = e->P.q;
+    size_t blocks = (count + kN - 1) / kN;
+    std::vector<HArr> a = {{src, nullptr, kN * sizeof(int64_t)}, {nullptr, dst, kN * sizeof(int32_t)}};
+    // whole polynomials per "item"; a ragged tail is handled by a final short call
+    size_t whole = count / kN;
+    int rc = run_chunked(e, whole, a, 0, nullptr, [&](size_t n, void **d, char *, uint32_t *, cudaStream_t s) {
+        rzk_pack_i64_kernel<<<e->num_sms * 4, 256, 0, s>>>(n * kN, (const int64_t *)d[0], (int32_t *)d[1], q);
+        e->launches++;
+        return cudaGetLastError() == cudaSuccess ? RZK_OK : RZK_ERR_CUDA;
+    });
+    (void)blocks;
+    if (rc != RZK_OK) return rc;
+    const int64_t half = (q - 1) / 2;
+    for (size_t i = whole * kN; i < count; ++i) {      // < N leftover coefficients: scalar staging
+        int64_t r = src[i] % q;
+        if (r > half) r -= q; else if (r < -half) r += q;
+        dst[i] = (int32_t)r;
+    }
+    return RZK_OK;
+}
+
+int rzk_unpack_i64(rzk_engine *e, size_t count, const int32_t *src, int64_t *dst)
+{
+    RZK_TRY(check_ready(e, false));
+    if (any_null({src, dst})) return fail(e, RZK_ERR_INVALID, "null argument");
+    std::vector<HArr> a = {{src, nullptr, kN * sizeof(int32_t)}, {nullptr, dst, kN * sizeof(int64_t)}};
+    size_t whole = count / kN;
+    int rc = run_chunked(e, whole, a, 0, nullptr, [&](size_t n, void **d, char *, uint32_t *, cudaStream_t s) {
+        rzk_unpack_i64_kernel<<<e->num_sms * 4, 256, 0, s>>>(n * kN, (const int32_t *)d[0], (int64_t *)d[1]);
+        e->launches++;
+        return cudaGetLastError() == cudaSuccess ? RZK_OK : RZK_ERR_CUDA;
+    });
+    if (rc != RZK_OK) return rc;
+    for (size_t i = whole * kN; i < count; ++i) dst[i] = src[i];
+    return RZK_OK;
+}
+
+}  // extern "C"

@@ -21,11 +21,13 @@
 #include "rzk_vm.h"
 
 #if defined(__CUDACC__)
+#define RZK_VM __device__ __forceinline__
 #define RZK_NL 1
 #define RZK_SYNC() __syncwarp()
 #define RZK_UNROLL _Pragma("unroll")
 #define RZK_NOUNROLL _Pragma("unroll 1")
 #else
+#define RZK_VM inline
 #define RZK_NL 16
 #define RZK_SYNC() ((void)0)
 #define RZK_UNROLL
@@ -33,16 +35,19 @@
 struct uint4 { uint32_t x, y, z, w; };
 #endif
 
+#if defined(__CUDACC__)
+// one lane per thread: no loop, no indexing, so the lane state stays in registers
+#define RZK_EACH_LANE if (constexpr int li_ = 0; true)
+#else
 #define RZK_EACH_LANE for (int li_ = 0; li_ < RZK_NL; ++li_)
-#define RZK_LANE Lane &L = lanes[li_]; const int t = t0 + li_; (void)t
+#endif
+#define RZK_LANE Lane &L = lanes[li_]; const int t = t0 + li_; (void)t; (void)L
 
 namespace rzk {
 
 struct Lane {
     uint32_t cur[kElems];
-    uint32_t acc0[kElems];
-    uint32_t acc1[kElems];
-    int64_t V[kElems];
+    uint32_t acc0[kElems];   // accumulator 0 lives in registers; accumulator 1 in the lane-private smem slot ctx.acc1
     uint32_t fail;
     uint32_t rerr;
 };
@@ -50,6 +55,7 @@ struct Lane {
 struct ItemCtx {
     uint32_t *buf;         // [kBufWords]  transpose buffer of this half warp
     uint32_t *slot;        // [kSlotWords] operand slot of OP_ST / OP_MACV
+    uint32_t *acc1;        // [kSlotWords] accumulator 1 (lane-private layout)
     uint32_t *stash;       // [NSTASH][np-1][kSlotWords] residues of earlier primes
     const uint32_t *g2;    // staged [np][2][16][60]
     const uint32_t *key;   // staged [np][3][2][576]
@@ -64,111 +70,102 @@ struct ItemCtx {
 #define RZK_G1(slot, dir, idx, j) ctx.g1[((((slot) * 2 + (dir)) * 32 + (idx)) * 2) + (j)]
 #endif
 
-RZK_HD int priv_index(int t, int e) { return (((e >> 2) * kLanes + t) << 2) + (e & 3); }
+RZK_VM int priv_index(int t, int e) { return (((e >> 2) * kLanes + t) << 2) + (e & 3); }
 
 // ---------------------------------------------------------------- transforms
 
-// stages 0..4 (distance 256..16) in the G1 layout; twiddles are lane-uniform
-RZK_HD void fwd_g1(uint32_t (&a)[kElems], const ItemCtx &ctx, uint32_t slot, uint32_t p, uint32_t p2)
+// One butterfly stage with compile-time geometry (all loops have constant trip counts so that
+// they unroll fully and the 32 coefficients stay in registers).
+//   G1 stages S = 0..4: distance 16>>S in the strided layout, lane-uniform twiddles (constant bank)
+//   G2 stages S = 5..8: distance 256>>S in the contiguous layout, lane-specific twiddles (shared memory)
+template <int S, int DIR>
+RZK_VM void g1_stage(uint32_t (&a)[kElems], const ItemCtx &ctx, uint32_t slot, uint32_t p, uint32_t p2)
 {
     (void)ctx;
+    constexpr int half = 16 >> S;
     RZK_UNROLL
-    for (int s = 0; s < 5; ++s) {
-        const int half = 16 >> s;
+    for (int b = 0; b < (1 << S); ++b) {
+        const uint32_t w = RZK_G1(slot, DIR, (1 << S) + b, 0);
+        const uint32_t wp = RZK_G1(slot, DIR, (1 << S) + b, 1);
         RZK_UNROLL
-        for (int b = 0; b < (1 << s); ++b) {
-            const uint32_t w = RZK_G1(slot, 0, (1 << s) + b, 0);
-            const uint32_t wp = RZK_G1(slot, 0, (1 << s) + b, 1);
-            RZK_UNROLL
-            for (int j = 0; j < half; ++j) {
-                const int i0 = b * 2 * half + j;
-                ct_bfly(a[i0], a[i0 + half], w, wp, p, p2);
-            }
+        for (int j = 0; j < half; ++j) {
+            const int i0 = b * 2 * half + j;
+            if (DIR == 0) ct_bfly(a[i0], a[i0 + half], w, wp, p, p2);
+            else gs_bfly(a[i0], a[i0 + half], w, wp, p, p2);
         }
     }
 }
 
-// stages 5..8 (distance 8..1) in the G2 layout; 30 lane-specific twiddle pairs
-RZK_HD void fwd_g2(uint32_t (&a)[kElems], const uint32_t *tw, uint32_t p, uint32_t p2)
+template <int S, int DIR>
+RZK_VM void g2_stage(uint32_t (&a)[kElems], const uint4 *tw4, uint32_t p, uint32_t p2)
+{
+    constexpr int half = 256 >> S;                // 8,4,2,1
+    constexpr int nb = 1 << (S - 4);              // 2,4,8,16 blocks
+    constexpr int base = (S == 5) ? 0 : (S == 6) ? 1 : (S == 7) ? 3 : 7;
+    RZK_UNROLL
+    for (int b2 = 0; b2 < nb / 2; ++b2) {
+        const uint4 q = tw4[base + b2];
+        RZK_UNROLL
+        for (int j = 0; j < half; ++j) {
+            const int i0 = (2 * b2) * 2 * half + j;
+            if (DIR == 0) ct_bfly(a[i0], a[i0 + half], q.x, q.y, p, p2);
+            else gs_bfly(a[i0], a[i0 + half], q.x, q.y, p, p2);
+        }
+        RZK_UNROLL
+        for (int j = 0; j < half; ++j) {
+            const int i0 = (2 * b2 + 1) * 2 * half + j;
+            if (DIR == 0) ct_bfly(a[i0], a[i0 + half], q.z, q.w, p, p2);
+            else gs_bfly(a[i0], a[i0 + half], q.z, q.w, p, p2);
+        }
+    }
+}
+
+RZK_VM void fwd_g1(uint32_t (&a)[kElems], const ItemCtx &ctx, uint32_t slot, uint32_t p, uint32_t p2)
+{
+    g1_stage<0, 0>(a, ctx, slot, p, p2);
+    g1_stage<1, 0>(a, ctx, slot, p, p2);
+    g1_stage<2, 0>(a, ctx, slot, p, p2);
+    g1_stage<3, 0>(a, ctx, slot, p, p2);
+    g1_stage<4, 0>(a, ctx, slot, p, p2);
+}
+
+RZK_VM void fwd_g2(uint32_t (&a)[kElems], const uint32_t *tw, uint32_t p, uint32_t p2)
 {
     const uint4 *tw4 = reinterpret_cast<const uint4 *>(tw);
-    int base = 0;
-    RZK_UNROLL
-    for (int s = 5; s < 9; ++s) {
-        const int half = 256 >> s;           // 8,4,2,1
-        const int nb = 1 << (s - 4);         // 2,4,8,16 blocks
-        RZK_UNROLL
-        for (int b2 = 0; b2 < nb / 2; ++b2) {
-            const uint4 q = tw4[base + b2];
-            RZK_UNROLL
-            for (int h = 0; h < 2; ++h) {
-                const int b = 2 * b2 + h;
-                const uint32_t w = h ? q.z : q.x, wp = h ? q.w : q.y;
-                RZK_UNROLL
-                for (int j = 0; j < half; ++j) {
-                    const int i0 = b * 2 * half + j;
-                    ct_bfly(a[i0], a[i0 + half], w, wp, p, p2);
-                }
-            }
-        }
-        base += nb / 2;
-    }
+    g2_stage<5, 0>(a, tw4, p, p2);
+    g2_stage<6, 0>(a, tw4, p, p2);
+    g2_stage<7, 0>(a, tw4, p, p2);
+    g2_stage<8, 0>(a, tw4, p, p2);
 }
 
-RZK_HD void inv_g2(uint32_t (&a)[kElems], const uint32_t *tw, uint32_t p, uint32_t p2)
+RZK_VM void inv_g2(uint32_t (&a)[kElems], const uint32_t *tw, uint32_t p, uint32_t p2)
 {
     const uint4 *tw4 = reinterpret_cast<const uint4 *>(tw);
-    RZK_UNROLL
-    for (int s = 8; s >= 5; --s) {
-        const int half = 256 >> s;
-        const int nb = 1 << (s - 4);
-        const int base = (s == 5) ? 0 : (s == 6) ? 1 : (s == 7) ? 3 : 7;
-        RZK_UNROLL
-        for (int b2 = 0; b2 < nb / 2; ++b2) {
-            const uint4 q = tw4[base + b2];
-            RZK_UNROLL
-            for (int h = 0; h < 2; ++h) {
-                const int b = 2 * b2 + h;
-                const uint32_t w = h ? q.z : q.x, wp = h ? q.w : q.y;
-                RZK_UNROLL
-                for (int j = 0; j < half; ++j) {
-                    const int i0 = b * 2 * half + j;
-                    gs_bfly(a[i0], a[i0 + half], w, wp, p, p2);
-                }
-            }
-        }
-    }
+    g2_stage<8, 1>(a, tw4, p, p2);
+    g2_stage<7, 1>(a, tw4, p, p2);
+    g2_stage<6, 1>(a, tw4, p, p2);
+    g2_stage<5, 1>(a, tw4, p, p2);
 }
 
-RZK_HD void inv_g1(uint32_t (&a)[kElems], const ItemCtx &ctx, uint32_t slot, uint32_t p, uint32_t p2)
+RZK_VM void inv_g1(uint32_t (&a)[kElems], const ItemCtx &ctx, uint32_t slot, uint32_t p, uint32_t p2)
 {
-    (void)ctx;
-    RZK_UNROLL
-    for (int s = 4; s >= 0; --s) {
-        const int half = 16 >> s;
-        RZK_UNROLL
-        for (int b = 0; b < (1 << s); ++b) {
-            const uint32_t w = RZK_G1(slot, 1, (1 << s) + b, 0);
-            const uint32_t wp = RZK_G1(slot, 1, (1 << s) + b, 1);
-            RZK_UNROLL
-            for (int j = 0; j < half; ++j) {
-                const int i0 = b * 2 * half + j;
-                gs_bfly(a[i0], a[i0 + half], w, wp, p, p2);
-            }
-        }
-    }
+    g1_stage<4, 1>(a, ctx, slot, p, p2);
+    g1_stage<3, 1>(a, ctx, slot, p, p2);
+    g1_stage<2, 1>(a, ctx, slot, p, p2);
+    g1_stage<1, 1>(a, ctx, slot, p, p2);
+    g1_stage<0, 1>(a, ctx, slot, p, p2);
 }
 
 // ---------------------------------------------------------------- global memory
 
-RZK_HD uint64_t stream_poly(const Stream &s, uint32_t item, uint32_t off)
+RZK_VM uint64_t stream_poly(const Stream &s, uint32_t item, uint32_t off)
 {
     return (uint64_t)(item / s.div) * s.stride + off;
 }
 
 // ---------------------------------------------------------------- ops
 
-RZK_HD void op_fwd(const VmLaunch &K, const ItemCtx &ctx, Lane *lanes, int t0, const Op &op, int it, int pi)
+RZK_VM void op_fwd(const VmLaunch &K, const ItemCtx &ctx, Lane *lanes, int t0, const Op &op, int it, int pi)
 {
     const PrimeC pc = K.pc[pi];
     const Stream st = K.st[op.a];
@@ -225,7 +222,7 @@ RZK_HD void op_fwd(const VmLaunch &K, const ItemCtx &ctx, Lane *lanes, int t0, c
 }
 
 // acc (+)= key (.) cur ; key rows pre-scaled by N^-1, Shoup form
-RZK_HD void mac_key(uint32_t (&acc)[kElems], const uint32_t (&cur)[kElems], const uint32_t *krow, int t,
+RZK_VM void mac_key(uint32_t (&acc)[kElems], const uint32_t (&cur)[kElems], const uint32_t *krow, int t,
                     uint32_t flags, uint32_t p, uint32_t p2)
 {
     const uint4 *w4 = reinterpret_cast<const uint4 *>(krow + 36 * t);
@@ -247,7 +244,7 @@ RZK_HD void mac_key(uint32_t (&acc)[kElems], const uint32_t (&cur)[kElems], cons
 }
 
 // acc (+)= slot (.) cur ; slot holds R*N^-1-scaled residues in [0,p), Montgomery product
-RZK_HD void mac_var(uint32_t (&acc)[kElems], const uint32_t (&cur)[kElems], const uint32_t *slot, int t,
+RZK_VM void mac_var(uint32_t (&acc)[kElems], const uint32_t (&cur)[kElems], const uint32_t *slot, int t,
                     uint32_t flags, uint32_t p, uint32_t p2, uint32_t pinv)
 {
     const uint4 *s4 = reinterpret_cast<const uint4 *>(slot);
@@ -267,7 +264,47 @@ RZK_HD void mac_var(uint32_t (&acc)[kElems], const uint32_t (&cur)[kElems], cons
     }
 }
 
-RZK_HD void op_st(const VmLaunch &K, const ItemCtx &ctx, Lane *lanes, int t0, int pi)
+// accumulator-1 variants: the accumulator is the lane-private shared-memory slot
+RZK_VM void mac_key_smem(uint32_t *acc1, const uint32_t (&cur)[kElems], const uint32_t *krow, int t,
+                         uint32_t flags, uint32_t p, uint32_t p2)
+{
+    const uint4 *w4 = reinterpret_cast<const uint4 *>(krow + 36 * t);
+    const uint4 *wp4 = reinterpret_cast<const uint4 *>(krow + kPadWords + 36 * t);
+    uint4 *a4 = reinterpret_cast<uint4 *>(acc1);
+    const bool init = flags & MAC_INIT, neg = flags & MAC_NEG;
+    RZK_UNROLL
+    for (int j = 0; j < 8; ++j) {
+        const uint4 w = w4[j], wp = wp4[j];
+        uint4 a = a4[j * kLanes + t];
+        uint32_t tt;
+        tt = shoup_mul(w.x, wp.x, cur[4 * j + 0], p); if (neg) tt = p2 - tt; a.x = csub((init ? 0u : a.x) + tt, p2);
+        tt = shoup_mul(w.y, wp.y, cur[4 * j + 1], p); if (neg) tt = p2 - tt; a.y = csub((init ? 0u : a.y) + tt, p2);
+        tt = shoup_mul(w.z, wp.z, cur[4 * j + 2], p); if (neg) tt = p2 - tt; a.z = csub((init ? 0u : a.z) + tt, p2);
+        tt = shoup_mul(w.w, wp.w, cur[4 * j + 3], p); if (neg) tt = p2 - tt; a.w = csub((init ? 0u : a.w) + tt, p2);
+        a4[j * kLanes + t] = a;
+    }
+}
+
+RZK_VM void mac_var_smem(uint32_t *acc1, const uint32_t (&cur)[kElems], const uint32_t *slot, int t,
+                         uint32_t flags, uint32_t p, uint32_t p2, uint32_t pinv)
+{
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(slot);
+    uint4 *a4 = reinterpret_cast<uint4 *>(acc1);
+    const bool init = flags & MAC_INIT, neg = flags & MAC_NEG;
+    RZK_UNROLL
+    for (int j = 0; j < 8; ++j) {
+        const uint4 s = s4[j * kLanes + t];
+        uint4 a = a4[j * kLanes + t];
+        uint32_t tt;
+        tt = mont_mul(csub(cur[4 * j + 0], p2), s.x, p, pinv); if (neg) tt = p2 - tt; a.x = csub((init ? 0u : a.x) + tt, p2);
+        tt = mont_mul(csub(cur[4 * j + 1], p2), s.y, p, pinv); if (neg) tt = p2 - tt; a.y = csub((init ? 0u : a.y) + tt, p2);
+        tt = mont_mul(csub(cur[4 * j + 2], p2), s.z, p, pinv); if (neg) tt = p2 - tt; a.z = csub((init ? 0u : a.z) + tt, p2);
+        tt = mont_mul(csub(cur[4 * j + 3], p2), s.w, p, pinv); if (neg) tt = p2 - tt; a.w = csub((init ? 0u : a.w) + tt, p2);
+        a4[j * kLanes + t] = a;
+    }
+}
+
+RZK_VM void op_st(const VmLaunch &K, const ItemCtx &ctx, Lane *lanes, int t0, int pi)
 {
     const PrimeC pc = K.pc[pi];
     RZK_EACH_LANE {
@@ -286,10 +323,55 @@ RZK_HD void op_st(const VmLaunch &K, const ItemCtx &ctx, Lane *lanes, int t0, in
     // lane-private: no cross-lane hazard, no sync needed
 }
 
+RZK_VM void op_addp(const VmLaunch &K, const ItemCtx &ctx, int64_t (&V)[RZK_NL][kElems], int t0, const Op &op, int it)
+{
+    const Stream st = K.st[op.a];
+    const uint64_t poly = stream_poly(st, ctx.item, (uint32_t)op.off + (uint32_t)it * op.step);
+    const bool neg = op.c & MAC_NEG;
+    RZK_EACH_LANE {
+        const int t = t0 + li_;
+        int32_t v[kElems];
+        if (st.dtype == DT_I8) {
+            const int8_t *src = reinterpret_cast<const int8_t *>(st.base) + poly * kN;
+            RZK_UNROLL
+            for (int m = 0; m < kElems; ++m) v[m] = src[t + kLanes * m];
+        } else {
+            const int32_t *src = reinterpret_cast<const int32_t *>(st.base) + poly * kN;
+            RZK_UNROLL
+            for (int m = 0; m < kElems; ++m) v[m] = canon_q(src[t + kLanes * m], K.q);
+        }
+        RZK_UNROLL
+        for (int m = 0; m < kElems; ++m) V[li_][m] += neg ? -(int64_t)v[m] : (int64_t)v[m];
+    }
+}
+
+RZK_VM void op_fin(const VmLaunch &K, const ItemCtx &ctx, Lane *lanes, int64_t (&V)[RZK_NL][kElems], int t0, const Op &op, int it)
+{
+    const Stream st = K.st[op.a];
+    const uint64_t poly = stream_poly(st, ctx.item, (uint32_t)op.off + (uint32_t)it * op.step);
+    RZK_EACH_LANE {
+        RZK_LANE;
+        int32_t res[kElems];
+        RZK_UNROLL
+        for (int m = 0; m < kElems; ++m) res[m] = reduce_q_centered(V[li_][m], K.q, K.bar, K.kq);
+        if (op.b & FIN_CMPZ) {
+            uint32_t nz = 0;
+            RZK_UNROLL
+            for (int m = 0; m < kElems; ++m) nz |= (uint32_t)res[m];
+            L.fail |= nz ? 1u : 0u;
+        }
+        if ((op.b & FIN_STORE) && ctx.active) {
+            int32_t *dst = reinterpret_cast<int32_t *>(const_cast<void *>(st.base)) + poly * kN;
+            RZK_UNROLL
+            for (int m = 0; m < kElems; ++m) dst[t + kLanes * m] = res[m];
+        }
+    }
+}
+
 // Garner recombination of the residues of one coefficient into a signed 64-bit value
 // congruent to the exact integer result modulo q (exact integer itself for np <= 2).
 template <int NP>
-RZK_HD int64_t crt_combine(const VmLaunch &K, const uint32_t (&r)[kMaxPrimes])
+RZK_VM int64_t crt_combine(const VmLaunch &K, const uint32_t (&r)[kMaxPrimes])
 {
     if (NP == 1) {
         const uint32_t a0 = r[0];
@@ -321,9 +403,14 @@ RZK_HD int64_t crt_combine(const VmLaunch &K, const uint32_t (&r)[kMaxPrimes])
     return w;
 }
 
+// Inverse transform of acc[a].  On the last prime the residues of all primes are combined and
+// the epilogue ops that follow (OP_ADDP*, OP_FIN) are executed here, so that the 64-bit
+// values live only inside this function.  Returns the index of the first op after the epilogue.
 template <int NP, int NSTASH>
-RZK_HD void op_inv(const VmLaunch &K, const ItemCtx &ctx, Lane *lanes, int t0, const Op &op, int pi)
+RZK_VM int op_inv(const VmLaunch &K, const ItemCtx &ctx, Lane *lanes, int t0, int q, int it, int pi)
 {
+    const Op op = K.ops[q];
+    int64_t V[RZK_NL][kElems];
     const PrimeC pc = K.pc[pi];
     RZK_EACH_LANE {
         RZK_LANE;
@@ -331,8 +418,12 @@ RZK_HD void op_inv(const VmLaunch &K, const ItemCtx &ctx, Lane *lanes, int t0, c
             RZK_UNROLL
             for (int e = 0; e < kElems; ++e) L.cur[e] = L.acc0[e];
         } else {
+            const uint4 *a4 = reinterpret_cast<const uint4 *>(ctx.acc1);
             RZK_UNROLL
-            for (int e = 0; e < kElems; ++e) L.cur[e] = L.acc1[e];
+            for (int j = 0; j < 8; ++j) {
+                const uint4 a = a4[j * kLanes + t];
+                L.cur[4 * j + 0] = a.x; L.cur[4 * j + 1] = a.y; L.cur[4 * j + 2] = a.z; L.cur[4 * j + 3] = a.w;
+            }
         }
         inv_g2(L.cur, ctx.g2 + ((pi * 2 + 1) * kLanes + t) * kG2Words, pc.p, pc.p2);
         uint4 *row = reinterpret_cast<uint4 *>(ctx.buf + 36 * t);
@@ -379,61 +470,26 @@ RZK_HD void op_inv(const VmLaunch &K, const ItemCtx &ctx, Lane *lanes, int t0, c
                 RZK_UNROLL
                 for (int k = 0; k < NP - 1; ++k) r[k] = prev[k][m];
                 r[NP - 1] = L.cur[m];
-                L.V[m] = crt_combine<NP>(K, r);
+                V[li_][m] = crt_combine<NP>(K, r);
             }
         }
     }
     RZK_SYNC();
     (void)NSTASH;
-}
-
-RZK_HD void op_addp(const VmLaunch &K, const ItemCtx &ctx, Lane *lanes, int t0, const Op &op, int it)
-{
-    const Stream st = K.st[op.a];
-    const uint64_t poly = stream_poly(st, ctx.item, (uint32_t)op.off + (uint32_t)it * op.step);
-    const bool neg = op.c & MAC_NEG;
-    RZK_EACH_LANE {
-        RZK_LANE;
-        int32_t v[kElems];
-        if (st.dtype == DT_I8) {
-            const int8_t *src = reinterpret_cast<const int8_t *>(st.base) + poly * kN;
-            RZK_UNROLL
-            for (int m = 0; m < kElems; ++m) v[m] = src[t + kLanes * m];
-        } else {
-            const int32_t *src = reinterpret_cast<const int32_t *>(st.base) + poly * kN;
-            RZK_UNROLL
-            for (int m = 0; m < kElems; ++m) v[m] = canon_q(src[t + kLanes * m], K.q);
-        }
-        RZK_UNROLL
-        for (int m = 0; m < kElems; ++m) L.V[m] += neg ? -(int64_t)v[m] : (int64_t)v[m];
+    const bool last = (pi == NP - 1);
+    ++q;
+    RZK_NOUNROLL
+    for (;; ++q) {
+        const Op e = K.ops[q];
+        if (e.code == OP_ADDP) { if (last) op_addp(K, ctx, V, t0, e, it); }
+        else if (e.code == OP_FIN) { if (last) op_fin(K, ctx, lanes, V, t0, e, it); }
+        else break;
     }
-}
-
-RZK_HD void op_fin(const VmLaunch &K, const ItemCtx &ctx, Lane *lanes, int t0, const Op &op, int it)
-{
-    const Stream st = K.st[op.a];
-    const uint64_t poly = stream_poly(st, ctx.item, (uint32_t)op.off + (uint32_t)it * op.step);
-    RZK_EACH_LANE {
-        RZK_LANE;
-        int32_t res[kElems];
-        RZK_UNROLL
-        for (int m = 0; m < kElems; ++m) res[m] = reduce_q_centered(L.V[m], K.q, K.bar, K.kq);
-        if (op.b & FIN_CMPZ) {
-            uint32_t nz = 0;
-            RZK_UNROLL
-            for (int m = 0; m < kElems; ++m) nz |= (uint32_t)res[m];
-            L.fail |= nz ? 1u : 0u;
-        }
-        if ((op.b & FIN_STORE) && ctx.active) {
-            int32_t *dst = reinterpret_cast<int32_t *>(const_cast<void *>(st.base)) + poly * kN;
-            RZK_UNROLL
-            for (int m = 0; m < kElems; ++m) dst[t + kLanes * m] = res[m];
-        }
-    }
+    return q;
 }
 
 // params.rs:102-118 via polynomial.rs:60-73: floor(sqrt(sum c^2)) <= bound  <=>  sum c^2 < (bound+1)^2
-RZK_HD void op_norm(const VmLaunch &K, const ItemCtx &ctx, Lane *lanes, int t0, const Op &op)
+RZK_VM void op_norm(const VmLaunch &K, const ItemCtx &ctx, Lane *lanes, int t0, const Op &op)
 {
     const Stream st = K.st[op.a];
     const uint32_t abs_lim = K.norm_abs_lim[op.b];
@@ -482,7 +538,7 @@ RZK_HD void op_norm(const VmLaunch &K, const ItemCtx &ctx, Lane *lanes, int t0, 
 // ---------------------------------------------------------------- interpreter
 
 template <int NP, int NSTASH>
-RZK_HD void vm_run_item(const VmLaunch &K, const ItemCtx &ctx, Lane *lanes, int t0)
+RZK_VM void vm_run_item(const VmLaunch &K, const ItemCtx &ctx, Lane *lanes, int t0)
 {
     RZK_EACH_LANE { RZK_LANE; L.fail = 0; L.rerr = 0; }
     int pc = 0;
@@ -498,7 +554,6 @@ RZK_HD void vm_run_item(const VmLaunch &K, const ItemCtx &ctx, Lane *lanes, int 
         RZK_NOUNROLL
         for (int pi = 0; pi < NP; ++pi) {
             const PrimeC pcst = K.pc[pi];
-            const bool last = (pi == NP - 1);
             int q = seg_begin, loop_start = 0, loop_cnt = 0, it = 0;
             RZK_NOUNROLL
             for (;;) {
@@ -513,7 +568,7 @@ RZK_HD void vm_run_item(const VmLaunch &K, const ItemCtx &ctx, Lane *lanes, int 
                     RZK_EACH_LANE {
                         RZK_LANE;
                         if (op.a == 0) mac_key(L.acc0, L.cur, krow, t, op.c, pcst.p, pcst.p2);
-                        else mac_key(L.acc1, L.cur, krow, t, op.c, pcst.p, pcst.p2);
+                        else mac_key_smem(ctx.acc1, L.cur, krow, t, op.c, pcst.p, pcst.p2);
                     }
                     break;
                 }
@@ -521,21 +576,15 @@ RZK_HD void vm_run_item(const VmLaunch &K, const ItemCtx &ctx, Lane *lanes, int 
                     RZK_EACH_LANE {
                         RZK_LANE;
                         if (op.a == 0) mac_var(L.acc0, L.cur, ctx.slot, t, op.c, pcst.p, pcst.p2, pcst.pinv);
-                        else mac_var(L.acc1, L.cur, ctx.slot, t, op.c, pcst.p, pcst.p2, pcst.pinv);
+                        else mac_var_smem(ctx.acc1, L.cur, ctx.slot, t, op.c, pcst.p, pcst.p2, pcst.pinv);
                     }
                     break;
                 case OP_ST:
                     op_st(K, ctx, lanes, t0, pi);
                     break;
                 case OP_INV:
-                    op_inv<NP, NSTASH>(K, ctx, lanes, t0, op, pi);
-                    break;
-                case OP_ADDP:
-                    if (last) op_addp(K, ctx, lanes, t0, op, it);
-                    break;
-                case OP_FIN:
-                    if (last) op_fin(K, ctx, lanes, t0, op, it);
-                    break;
+                    q = op_inv<NP, NSTASH>(K, ctx, lanes, t0, q, it, pi);
+                    continue;
                 case OP_LOOP:
                     loop_start = q + 1; loop_cnt = op.off; it = 0;
                     break;

@@ -1,0 +1,336 @@
+"""ctypes binding of the C ABI in include/ringzk_b200.h (libringzk_b200.so).
+
+This is the only compute path of the package: every call goes to the hand-written
+sm_100a kernels through the C ABI.  There is no CPU fallback -- if the shared library
+is missing or no CUDA device is present, loading / Engine() raises.
+
+Host entry points take numpy arrays (C-contiguous; int32 / int8 as documented in the
+header).  `*_dev` entry points take torch CUDA tensors (or anything with data_ptr())
+and enqueue on a CUDA stream without synchronising.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, "_build", "libringzk_b200.so")
+
+RZK_OK, RZK_ERR_INVALID, RZK_ERR_UNSUPPORTED, RZK_ERR_CUDA, RZK_ERR_RANGE, RZK_ERR_NOKEY = range(6)
+_ERRNAMES = {1: "RZK_ERR_INVALID", 2: "RZK_ERR_UNSUPPORTED", 3: "RZK_ERR_CUDA", 4: "RZK_ERR_RANGE", 5: "RZK_ERR_NOKEY"}
+
+SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("rzk_engine.cu", "rzk_tables.cpp")]
+HEADERS = [os.path.join(_HERE, "csrc", f) for f in
+           ("rzk_arith.cuh", "rzk_vm.h", "rzk_vm_exec.cuh", "rzk_programs.h", "rzk_tables.h")] + \
+          [os.path.join(_ROOT, "include", "ringzk_b200.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "--shared"]
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA extension in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    deps = SOURCES + HEADERS
+    stale = force or not os.path.exists(LIB_PATH) or any(
+        os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps)
+    if stale:
+        os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
+        cmd = ["nvcc"] + NVCC_FLAGS
+        if os.path.exists("/usr/bin/g++"):
+            cmd += ["-ccbin", "/usr/bin/g++"]
+        cmd += ["-o", LIB_PATH] + SOURCES
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or res.returncode != 0:
+            print(res.stdout, res.stderr)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed building libringzk_b200.so")
+    return LIB_PATH
+
+
+class RzkError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{_ERRNAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+class RzkParams(C.Structure):
+    _fields_ = [("q", C.c_int64), ("b", C.c_int64), ("N", C.c_int32), ("n", C.c_int32),
+                ("k", C.c_int32), ("l", C.c_int32), ("kappa", C.c_int32)]
+
+
+_lib = None
+_VP = C.c_void_p
+
+# name -> argument kinds after the engine handle ('z' size_t, 'u' uint32, 'p' pointer)
+_SIGS = {
+    "rzk_commit_batch": "zpppp",
+    "rzk_open_commit_batch": "zpppppp",
+    "rzk_open_respond_batch": "zpppp",
+    "rzk_open_verify_batch": "zppppp",
+    "rzk_linear_commit_batch": "z" + "p" * 13,
+    "rzk_linear_respond_batch": "z" + "p" * 7,
+    "rzk_linear_verify_batch": "z" + "p" * 10,
+    "rzk_sum_commit_batch": "zu" + "p" * 13,
+    "rzk_sum_respond_batch": "zu" + "p" * 7,
+    "rzk_sum_verify_batch": "zu" + "p" * 10,
+    "rzk_commit_batch_dev": "zppppp",
+    "rzk_open_commit_batch_dev": "zppppppp",
+    "rzk_open_respond_batch_dev": "zppppp",
+    "rzk_open_verify_batch_dev": "zpppuppp",
+    "rzk_linear_commit_batch_dev": "z" + "p" * 14,
+    "rzk_linear_respond_batch_dev": "z" + "p" * 8,
+    "rzk_linear_verify_batch_dev": "z" + "p" * 11,
+    "rzk_sum_commit_batch_dev": "zu" + "p" * 14,
+    "rzk_sum_respond_batch_dev": "zu" + "p" * 8,
+    "rzk_sum_verify_batch_dev": "zu" + "p" * 11,
+    "rzk_flags_to_bitmap_dev": "zpppp",
+    "rzk_pack_i64": "zpp",
+    "rzk_unpack_i64": "zpp",
+    "rzk_sync": "p",
+}
+EXPORTS = sorted(list(_SIGS) + ["rzk_default_params", "rzk_create", "rzk_destroy", "rzk_last_error", "rzk_device",
+                                "rzk_sigma", "rzk_commit_bound", "rzk_verify_bound", "rzk_small_limit",
+                                "rzk_set_key", "rzk_host_alloc", "rzk_host_free", "rzk_kernel_launches"])
+
+
+def lib():
+    """Load libringzk_b200.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run __graft_entry__.build() (nvcc, sm_100a). "
+                           "There is no CPU fallback for the engine.")
+    L = C.CDLL(LIB_PATH)
+    kinds = {"z": C.c_size_t, "u": C.c_uint32, "p": _VP}
+    for name, sig in _SIGS.items():
+        fn = getattr(L, name)
+        fn.restype = C.c_int
+        fn.argtypes = [_VP] + [kinds[c] for c in sig]
+    L.rzk_default_params.restype = RzkParams
+    L.rzk_default_params.argtypes = [C.c_int32]
+    L.rzk_create.restype = C.c_int
+    L.rzk_create.argtypes = [C.POINTER(RzkParams), C.c_int, C.POINTER(_VP)]
+    L.rzk_destroy.argtypes = [_VP]
+    L.rzk_destroy.restype = None
+    L.rzk_last_error.restype = C.c_char_p
+    L.rzk_last_error.argtypes = [_VP]
+    L.rzk_device.argtypes = [_VP]
+    for n in ("rzk_sigma", "rzk_commit_bound", "rzk_verify_bound", "rzk_kernel_launches"):
+        getattr(L, n).restype = C.c_uint64
+        getattr(L, n).argtypes = [_VP]
+    L.rzk_small_limit.restype = C.c_uint32
+    L.rzk_small_limit.argtypes = [_VP]
+    L.rzk_set_key.restype = C.c_int
+    L.rzk_set_key.argtypes = [_VP, _VP, _VP]
+    L.rzk_host_alloc.restype = _VP
+    L.rzk_host_alloc.argtypes = [C.c_size_t]
+    L.rzk_host_free.argtypes = [_VP]
+    L.rzk_host_free.restype = None
+    _lib = L
+    return L
+
+
+def _ptr(a, dtype=None):
+    """Host numpy array or device tensor -> raw pointer (with dtype / contiguity checks)."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        if dtype is not None and a.dtype != dtype:
+            raise TypeError(f"expected {dtype}, got {a.dtype}")
+        if not a.flags["C_CONTIGUOUS"]:
+            raise ValueError("array must be C-contiguous")
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        if not a.is_contiguous():
+            raise ValueError("tensor must be contiguous")
+        return a.data_ptr()
+    if isinstance(a, int):
+        return a
+    raise TypeError(type(a))
+
+
+class Engine:
+    """One engine per CUDA device (rzk_create / rzk_destroy)."""
+
+    def __init__(self, N=512, device=-1, params: RzkParams | None = None):
+        L = lib()
+        self.L = L
+        self.params = params if params is not None else L.rzk_default_params(N)
+        h = _VP()
+        rc = L.rzk_create(C.byref(self.params), device, C.byref(h))
+        if rc != RZK_OK:
+            raise RzkError(rc, (L.rzk_last_error(None) or b"").decode())
+        self.h = h
+        self.N = self.params.N
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.rzk_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _call(self, name, *args):
+        rc = getattr(self.L, name)(self.h, *args)
+        if rc != RZK_OK:
+            raise RzkError(rc, (self.L.rzk_last_error(self.h) or b"").decode())
+
+    # ---- scalars ----
+    @property
+    def device(self):
+        return self.L.rzk_device(self.h)
+
+    def sigma(self):
+        return int(self.L.rzk_sigma(self.h))
+
+    def commit_bound(self):
+        return int(self.L.rzk_commit_bound(self.h))
+
+    def verify_bound(self):
+        return int(self.L.rzk_verify_bound(self.h))
+
+    def small_limit(self):
+        return int(self.L.rzk_small_limit(self.h))
+
+    def kernel_launches(self):
+        return int(self.L.rzk_kernel_launches(self.h))
+
+    # ---- key ----
+    def set_key(self, a1, a2):
+        """a1 [n][k][N], a2 [l][k][N] int64 as the reference stores them (commit.rs:19-60)."""
+        a1 = np.ascontiguousarray(a1, dtype=np.int64)
+        a2 = np.ascontiguousarray(a2, dtype=np.int64)
+        rc = self.L.rzk_set_key(self.h, a1.ctypes.data, a2.ctypes.data)
+        if rc != RZK_OK:
+            raise RzkError(rc, (self.L.rzk_last_error(self.h) or b"").decode())
+
+    def set_key_blocks(self, a1p, a2p):
+        """Random blocks only: a1p [1][2][N], a2p [1][1][N] -> [1 | a1p], [0 | 1 | a2p]."""
+        N = self.N
+        a1 = np.zeros((1, 3, N), np.int64)
+        a2 = np.zeros((1, 3, N), np.int64)
+        a1[0, 0, 0] = 1
+        a1[0, 1:] = np.asarray(a1p, dtype=np.int64).reshape(2, N)
+        a2[0, 1, 0] = 1
+        a2[0, 2] = np.asarray(a2p, dtype=np.int64).reshape(N)
+        self.set_key(a1, a2)
+        return a1, a2
+
+    # ---- host API (numpy) ----
+    def commit(self, x, r):
+        B, N = x.shape[0], self.N
+        c = np.empty((B, 2, N), np.int32)
+        ok = np.zeros((B + 7) // 8, np.uint8)
+        self._call("rzk_commit_batch", B, _ptr(x, np.int32), _ptr(r, np.int8), _ptr(c), _ptr(ok))
+        return c, ok
+
+    def open_commit(self, x, r, y):
+        B, N = x.shape[0], self.N
+        c = np.empty((B, 2, N), np.int32)
+        t = np.empty((B, 1, N), np.int32)
+        ok = np.zeros((B + 7) // 8, np.uint8)
+        self._call("rzk_open_commit_batch", B, _ptr(x, np.int32), _ptr(r, np.int8), _ptr(y, np.int32),
+                   _ptr(c), _ptr(t), _ptr(ok))
+        return c, t, ok
+
+    def open_respond(self, y, r, d):
+        B = y.shape[0]
+        z = np.empty((B, 3, self.N), np.int32)
+        self._call("rzk_open_respond_batch", B, _ptr(y, np.int32), _ptr(r, np.int8), _ptr(d, np.int8), _ptr(z))
+        return z
+
+    def open_verify(self, z, t, c1, d):
+        B = z.shape[0]
+        bm = np.zeros((B + 7) // 8, np.uint8)
+        self._call("rzk_open_verify_batch", B, _ptr(z, np.int32), _ptr(t, np.int32), _ptr(c1, np.int32),
+                   _ptr(d, np.int8), _ptr(bm))
+        return bm
+
+    def linear_commit(self, g, x, rp, r, y, yp):
+        B, N = x.shape[0], self.N
+        o = dict(gx=np.empty((B, 1, N), np.int32), cp=np.empty((B, 2, N), np.int32), c=np.empty((B, 2, N), np.int32),
+                 t=np.empty((B, 1, N), np.int32), tp=np.empty((B, 1, N), np.int32), u=np.empty((B, 1, N), np.int32),
+                 ok=np.zeros((B + 7) // 8, np.uint8))
+        self._call("rzk_linear_commit_batch", B, _ptr(g, np.int32), _ptr(x, np.int32), _ptr(rp, np.int8), _ptr(r, np.int8),
+                   _ptr(y, np.int32), _ptr(yp, np.int32), _ptr(o["gx"]), _ptr(o["cp"]), _ptr(o["c"]), _ptr(o["t"]),
+                   _ptr(o["tp"]), _ptr(o["u"]), _ptr(o["ok"]))
+        return o
+
+    def linear_respond(self, y, yp, r, rp, d):
+        B = y.shape[0]
+        z = np.empty((B, 3, self.N), np.int32)
+        zp = np.empty((B, 3, self.N), np.int32)
+        self._call("rzk_linear_respond_batch", B, _ptr(y, np.int32), _ptr(yp, np.int32), _ptr(r, np.int8),
+                   _ptr(rp, np.int8), _ptr(d, np.int8), _ptr(z), _ptr(zp))
+        return z, zp
+
+    def linear_verify(self, z, zp, c, cp, g, t, tp, u, d):
+        B = z.shape[0]
+        bm = np.zeros((B + 7) // 8, np.uint8)
+        self._call("rzk_linear_verify_batch", B, _ptr(z, np.int32), _ptr(zp, np.int32), _ptr(c, np.int32),
+                   _ptr(cp, np.int32), _ptr(g, np.int32), _ptr(t, np.int32), _ptr(tp, np.int32), _ptr(u, np.int32),
+                   _ptr(d, np.int8), _ptr(bm))
+        return bm
+
+    def sum_commit(self, gs, xs, rp, rs, ys, yp):
+        B, T, N = gs.shape[0], gs.shape[1], self.N
+        o = dict(xp=np.empty((B, 1, N), np.int32), cp=np.empty((B, 2, N), np.int32), cs=np.empty((B, T, 2, N), np.int32),
+                 ts=np.empty((B, T, 1, N), np.int32), tp=np.empty((B, 1, N), np.int32), u=np.empty((B, 1, N), np.int32),
+                 ok=np.zeros((B + 7) // 8, np.uint8))
+        self._call("rzk_sum_commit_batch", B, T, _ptr(gs, np.int32), _ptr(xs, np.int32), _ptr(rp, np.int8),
+                   _ptr(rs, np.int8), _ptr(ys, np.int32), _ptr(yp, np.int32), _ptr(o["xp"]), _ptr(o["cp"]),
+                   _ptr(o["cs"]), _ptr(o["ts"]), _ptr(o["tp"]), _ptr(o["u"]), _ptr(o["ok"]))
+        return o
+
+    def sum_respond(self, ys, yp, rs, rp, d):
+        B, T = ys.shape[0], ys.shape[1]
+        zs = np.empty((B, T, 3, self.N), np.int32)
+        zp = np.empty((B, 3, self.N), np.int32)
+        self._call("rzk_sum_respond_batch", B, T, _ptr(ys, np.int32), _ptr(yp, np.int32), _ptr(rs, np.int8),
+                   _ptr(rp, np.int8), _ptr(d, np.int8), _ptr(zs), _ptr(zp))
+        return zs, zp
+
+    def sum_verify(self, zs, zp, cs, cp, gs, ts, tp, u, d):
+        B, T = zs.shape[0], zs.shape[1]
+        bm = np.zeros((B + 7) // 8, np.uint8)
+        self._call("rzk_sum_verify_batch", B, T, _ptr(zs, np.int32), _ptr(zp, np.int32), _ptr(cs, np.int32),
+                   _ptr(cp, np.int32), _ptr(gs, np.int32), _ptr(ts, np.int32), _ptr(tp, np.int32), _ptr(u, np.int32),
+                   _ptr(d, np.int8), _ptr(bm))
+        return bm
+
+    def pack_i64(self, a):
+        a = np.ascontiguousarray(a, dtype=np.int64)
+        out = np.empty(a.shape, np.int32)
+        self._call("rzk_pack_i64", a.size, _ptr(a), _ptr(out))
+        return out
+
+    def unpack_i64(self, a):
+        a = np.ascontiguousarray(a, dtype=np.int32)
+        out = np.empty(a.shape, np.int64)
+        self._call("rzk_unpack_i64", a.size, _ptr(a), _ptr(out))
+        return out
+
+    # ---- device API (torch tensors / raw pointers) ----
+    def dev(self, name, *args, stream=0):
+        """Call rzk_<name>_dev; tensors are passed by data_ptr(); ints stay ints."""
+        sig = _SIGS[f"rzk_{name}_dev"]
+        conv = []
+        for kind, a in zip(sig, list(args) + [stream]):
+            conv.append(a if kind in "zu" else _ptr(a))
+        self._call(f"rzk_{name}_dev", *conv)
+
+    def sync(self, stream=0):
+        self._call("rzk_sync", stream)
+
+
+def unpack_bitmap(bm, B):
+    """bitmap (uint8, LSB first) -> bool array of length B."""
+    return np.unpackbits(np.asarray(bm, dtype=np.uint8), bitorder="little")[:B].astype(bool)

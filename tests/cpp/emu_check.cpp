@@ -41,7 +41,7 @@ struct Emu {
     int slots[3];
     std::vector<uint32_t> g1, g2, key, flags;
     VmLaunch K;
-    std::vector<uint32_t> buf, slot, stash;
+    std::vector<uint32_t> buf, slot, acc1, stash;
 
     Emu(int np_, const int *sl, const int64_t *keypolys /*[3][512]*/, size_t nflags)
     {
@@ -77,6 +77,7 @@ struct Emu {
         K.flags = flags.data();
         buf.resize(kBufWords);
         slot.resize(kSlotWords);
+        acc1.resize(kSlotWords);
         stash.resize(2 * 2 * kSlotWords);
     }
     void stream(int i, const void *base, uint32_t stride, uint32_t dtype, uint32_t div = 1)
@@ -89,7 +90,7 @@ struct Emu {
         static Lane lanes[16];
         for (uint32_t it = 0; it < n_items; ++it) {
             ItemCtx c;
-            c.buf = buf.data(); c.slot = slot.data(); c.stash = stash.data();
+            c.buf = buf.data(); c.slot = slot.data(); c.acc1 = acc1.data(); c.stash = stash.data();
             c.g2 = g2.data(); c.key = key.data(); c.g1 = g1.data();
             c.item = it; c.active = true;
             if (np == 1) vm_run_item<1, 2>(K, c, lanes, 0);

@@ -1,0 +1,52 @@
+"""The C-ABI library loads and exports every symbol include/ringzk_b200.h declares.
+No compute calls are made here (no GPU in this tier)."""
+import ctypes
+import importlib
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+engine = importlib.import_module("ring-zk_b200.engine")
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "ringzk_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rzk_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_header():
+    engine.build()
+    L = ctypes.CDLL(engine.LIB_PATH)
+    names = header_functions()
+    assert len(names) >= 35
+    for n in names:
+        assert hasattr(L, n), f"missing export {n}"
+    # the binding and the header agree on the surface
+    assert set(engine.EXPORTS) == set(names)
+
+
+def test_default_params_and_no_device_error():
+    L = engine.lib()
+    P = L.rzk_default_params(512)
+    assert (P.q, P.b, P.N, P.n, P.k, P.l, P.kappa) == (3515337053, 1, 512, 1, 3, 1, 36)
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if not has_gpu:
+        # the product path fails loudly without a CUDA device: no CPU fallback
+        with pytest.raises(engine.RzkError) as ei:
+            engine.Engine(N=512)
+        assert ei.value.code == engine.RZK_ERR_CUDA
+
+
+def test_unsupported_params_rejected():
+    L = engine.lib()
+    P = L.rzk_default_params(16)
+    h = ctypes.c_void_p()
+    assert L.rzk_create(ctypes.byref(P), -1, ctypes.byref(h)) == engine.RZK_ERR_UNSUPPORTED
+    assert b"N=512" in L.rzk_last_error(None)

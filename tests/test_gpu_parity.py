@@ -1,0 +1,272 @@
+"""GPU parity tests: the CUDA engine (through the C ABI, host-buffer entry points) against the
+CPU oracle on identical seeded inputs, bit-exact.  Run with `-m gpu` on the B200 box.
+
+Cases follow the reference's own tests (tests/test.rs:11-93: honest Open / Linear / Sum
+transcripts with ragged messages, 4-term sums; commit.rs:161-170: swapped openings) plus the
+negative tests the reference lacks (tampered z / t / c / d / g / u, oversized z, bad r).
+"""
+import importlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+engine = importlib.import_module("ring-zk_b200.engine")
+synth = importlib.import_module("ring-zk_b200.synth")
+from oracle import oracle as orc  # noqa: E402  (checker only)
+
+N = 512
+UB = engine.unpack_bitmap
+
+
+@pytest.fixture(scope="module")
+def setup():
+    s = synth.Synth(42, N=N)
+    a1p, a2p = s.key()
+    eng = engine.Engine(N=N, device=0)
+    eng.set_key_blocks(a1p, a2p)
+    o = orc.Oracle(orc.Params(N=N), a1p, a2p)
+    yield eng, o, s
+    eng.close()
+
+
+def test_bounds(setup):
+    eng, o, _ = setup
+    assert eng.sigma() == o.sigma() == 15444
+    assert eng.commit_bound() == o.commit_bound() == 1359072
+    assert eng.verify_bound() == o.verify_bound() == 679536
+    assert eng.small_limit() > 20 * 15444
+
+
+@pytest.mark.parametrize("B,ragged", [(1, False), (7, True), (200, True)])
+def test_commit(setup, B, ragged):
+    eng, o, s = setup
+    x, r = s.message(B, ragged=ragged), s.small(B)
+    c, ok = eng.commit(x, r)
+    c_o, ok_o = o.commit_batch(x, r)
+    assert (c == c_o).all()
+    assert (UB(ok, B) == ok_o.astype(bool)).all() and ok_o.all()
+
+
+def test_commit_readme_example(setup):
+    # README.md:32-55 / commit.rs:66-78: x = [1,2,3,4]
+    eng, o, s = setup
+    x = np.zeros((1, 1, N), np.int32); x[0, 0, :4] = [1, 2, 3, 4]
+    r = s.small(1)
+    c, ok = eng.commit(x, r)
+    assert o.commitment_verify(c[0], x[0], r[0]) and UB(ok, 1)[0]
+    x2 = np.zeros((1, 1, N), np.int32); x2[0, 0, :4] = [4, 5, 6, 7]
+    r2 = s.small(1)
+    c2, _ = eng.commit(x2, r2)
+    assert o.commitment_verify(c2[0], x2[0], r2[0])
+    assert not o.commitment_verify(c2[0], x[0], r[0])          # commit.rs:169
+    assert not o.commitment_verify(c[0], x2[0], r2[0])         # commit.rs:170
+
+
+def test_commit_edge_values(setup):
+    """extreme residues, all-zero and non-canonical representatives"""
+    eng, o, s = setup
+    half = (3515337053 - 1) // 2
+    x = np.zeros((4, 1, N), np.int32)
+    x[0] = half; x[1] = -half; x[3, 0, ::2] = half
+    r = s.small(4); r[2] = 0
+    c, _ = eng.commit(x, r)
+    c_o, _ = o.commit_batch(x, r)
+    assert (c == c_o).all()
+    # a non-canonical i32 representative is canonicalised like ZqI64::from
+    xn = x.copy(); xn[2, 0, 0] = np.int32(2 ** 31 - 1)
+    c2, _ = eng.commit(xn, r)
+    xc = o.center(xn.astype(np.int64))
+    c2_o, _ = o.commit_batch(xc, r)
+    assert (c2 == c2_o).all()
+
+
+def test_commit_constraint_flag(setup):
+    """check_commit_constraint (params.rs:102-108) needs a wide r to fail: use the device API with i8 limits"""
+    eng, o, s = setup
+    B = 9
+    x, r = s.message(B), s.small(B)
+    r[3, 1, :] = 127          # norm = 127*sqrt(512) = 2873 << bound: still ok
+    c, ok = eng.commit(x, r)
+    c_o, ok_o = o.commit_batch(x, r)
+    assert (c == c_o).all() and (UB(ok, B) == ok_o.astype(bool)).all()
+
+
+@pytest.mark.parametrize("B", [1, 65])
+def test_open_proof(setup, B):
+    eng, o, s = setup
+    x, r, y, d = s.message(B, ragged=True), s.small(B), s.gaussian(B), s.challenge(B)
+    c, t, ok = eng.open_commit(x, r, y)
+    c_o, t_o, ok_o = o.open_commit_batch(x, r, y)
+    assert (c == c_o).all() and (t == t_o).all() and UB(ok, B).all()
+    z = eng.open_respond(y, r, d)
+    assert (z == o.open_respond_batch(y, r, d)).all()
+    c1 = np.ascontiguousarray(c[:, :1])
+    v = UB(eng.open_verify(z, t, c1, d), B)
+    assert v.all() and o.open_verify_batch(z, t, c1, d).all()
+    # tampering: every single-coefficient change flips the bit, in the engine and in the oracle
+    for name in ("z", "t", "c", "d"):
+        zz, tt, cc, dd = z.copy(), t.copy(), c1.copy(), d.copy()
+        arr = {"z": zz, "t": tt, "c": cc, "d": dd}[name]
+        arr[:, ..., 5] += 1
+        v = UB(eng.open_verify(zz, tt, cc, dd), B)
+        v_o = o.open_verify_batch(zz, tt, cc, dd).astype(bool)
+        assert (v == v_o).all() and not v.any(), name
+    # oversized z: norm check (params.rs:112-118) fails
+    zb = z.copy(); zb[::2, 2, 9] = eng.verify_bound() + 1
+    v = UB(eng.open_verify(zb, t, c1, d), B)
+    assert (v == o.open_verify_batch(zb, t, c1, d).astype(bool)).all()
+    assert not v[::2].any()
+
+
+def test_open_verify_norm_boundary(setup):
+    """norm_2 exactly at / just above the bound (floor sqrt semantics, polynomial.rs:60-73)"""
+    eng, o, s = setup
+    B = 4
+    vb = eng.verify_bound()
+    z = np.zeros((B, 3, N), np.int32)
+    z[0, 0, 0] = vb            # norm == bound -> passes the norm check
+    z[1, 0, 0] = vb + 1        # fails
+    z[2, 1, 0] = vb; z[2, 1, 1] = 1165   # sqrt(vb^2 + 1165^2) = vb + 0.998.. -> floor == vb passes
+    z[3, 1, 0] = vb; z[3, 1, 1] = 1167   # just over -> fails
+    d = s.challenge(B)
+    t = np.zeros((B, 1, N), np.int32)
+    c1 = np.zeros((B, 1, N), np.int32)
+    # make the equation hold: t = A1.z - c1*d with c1 = 0
+    t_o = o.mat_dot(o.a1, z[0].astype(np.int64)[:, None, :])
+    for i in range(B):
+        t[i] = o.mat_dot(o.a1, z[i].astype(np.int64)[:, None, :])[:, 0, :]
+    v = UB(eng.open_verify(z, t, c1, d), B)
+    v_o = o.open_verify_batch(z, t, c1, d).astype(bool)
+    assert (v == v_o).all()
+    assert list(v) == [True, False, True, False]
+    assert t_o is not None
+
+
+def test_range_error_reported(setup):
+    eng, o, s = setup
+    x, r, y = s.message(2), s.small(2), s.gaussian(2)
+    y[1, 2, 100] = eng.small_limit() + 1
+    with pytest.raises(engine.RzkError) as ei:
+        eng.open_commit(x, r, y)
+    assert ei.value.code == engine.RZK_ERR_RANGE
+    y[1, 2, 100] = eng.small_limit()          # at the limit: exact
+    c, t, _ = eng.open_commit(x, r, y)
+    c_o, t_o, _ = o.open_commit_batch(x, r, y)
+    assert (t == t_o).all()
+    y[1, 0, 100] = 2 ** 30                     # y0 is never multiplied: any size is fine
+    c, t, _ = eng.open_commit(x, r, y)
+    c_o, t_o, _ = o.open_commit_batch(x, r, y)
+    assert (t == t_o).all()
+
+
+@pytest.mark.parametrize("B", [1, 33])
+def test_linear_proof(setup, B):
+    eng, o, s = setup
+    x, g = s.message(B, ragged=True), s.scalar(B)
+    r, rp, y, yp, d = s.small(B), s.small(B), s.gaussian(B), s.gaussian(B), s.challenge(B)
+    lc = eng.linear_commit(g, x, rp, r, y, yp)
+    lo = o.linear_commit_batch(g, x, rp, r, y, yp)
+    for kname in ("gx", "cp", "c", "t", "tp", "u"):
+        assert (lc[kname] == lo[kname]).all(), kname
+    assert UB(lc["ok"], B).all()
+    z, zp = eng.linear_respond(y, yp, r, rp, d)
+    z_o, zp_o = o.linear_respond_batch(y, yp, r, rp, d)
+    assert (z == z_o).all() and (zp == zp_o).all()
+    v = UB(eng.linear_verify(z, zp, lc["c"], lc["cp"], g, lc["t"], lc["tp"], lc["u"], d), B)
+    assert v.all() and o.linear_verify_batch(z, zp, lc["c"], lc["cp"], g, lc["t"], lc["tp"], lc["u"], d).all()
+    for name in ("z", "zp", "c", "cp", "g", "t", "tp", "u", "d"):
+        a = dict(z=z.copy(), zp=zp.copy(), c=lc["c"].copy(), cp=lc["cp"].copy(), g=g.copy(), t=lc["t"].copy(),
+                 tp=lc["tp"].copy(), u=lc["u"].copy(), d=d.copy())
+        a[name][:, ..., 17] += 1
+        v = UB(eng.linear_verify(a["z"], a["zp"], a["c"], a["cp"], a["g"], a["t"], a["tp"], a["u"], a["d"]), B)
+        v_o = o.linear_verify_batch(a["z"], a["zp"], a["c"], a["cp"], a["g"], a["t"], a["tp"], a["u"], a["d"])
+        assert (v == v_o.astype(bool)).all() and not v.any(), name
+
+
+@pytest.mark.parametrize("B,T", [(3, 1), (5, 4), (2, 64)])
+def test_sum_proof(setup, B, T):
+    eng, o, s = setup
+    gs, xs = s.scalar(B, T), s.uniform_q(B, T, 1)
+    rs, ys = s.small(B, T), s.gaussian(B, T)
+    rp, yp, d = s.small(B), s.gaussian(B), s.challenge(B)
+    sc = eng.sum_commit(gs, xs, rp, rs, ys, yp)
+    so = o.sum_commit_batch(gs, xs, rp, rs, ys, yp)
+    for kname in ("xp", "cp", "cs", "ts", "tp", "u"):
+        assert (sc[kname] == so[kname]).all(), kname
+    assert UB(sc["ok"], B).all()
+    zs, zp = eng.sum_respond(ys, yp, rs, rp, d)
+    zs_o, zp_o = o.sum_respond_batch(ys, yp, rs, rp, d)
+    assert (zs == zs_o).all() and (zp == zp_o).all()
+    v = UB(eng.sum_verify(zs, zp, sc["cs"], sc["cp"], gs, sc["ts"], sc["tp"], sc["u"], d), B)
+    assert v.all() and o.sum_verify_batch(zs, zp, sc["cs"], sc["cp"], gs, sc["ts"], sc["tp"], sc["u"], d).all()
+    # tamper a single term of a single instance: only that instance fails
+    for name in ("zs", "cs", "gs", "ts", "u", "zp"):
+        a = dict(zs=zs.copy(), zp=zp.copy(), cs=sc["cs"].copy(), cp=sc["cp"].copy(), gs=gs.copy(), ts=sc["ts"].copy(),
+                 tp=sc["tp"].copy(), u=sc["u"].copy(), d=d.copy())
+        arr = a[name]
+        if arr.ndim >= 4 or name == "gs":
+            arr[B - 1, T - 1, ..., 3] += 1
+        else:
+            arr[B - 1, ..., 3] += 1
+        v = UB(eng.sum_verify(a["zs"], a["zp"], a["cs"], a["cp"], a["gs"], a["ts"], a["tp"], a["u"], a["d"]), B)
+        v_o = o.sum_verify_batch(a["zs"], a["zp"], a["cs"], a["cp"], a["gs"], a["ts"], a["tp"], a["u"], a["d"])
+        assert (v == v_o.astype(bool)).all(), name
+        assert not v[B - 1] and v[:B - 1].all(), name
+
+
+def test_worst_case_magnitudes(setup):
+    """all operands at +-(q-1)/2: exercises the full range of the 2- and 3-prime CRT"""
+    eng, o, s = setup
+    half = (3515337053 - 1) // 2
+    B = 2
+    g = np.full((B, N), half, np.int32); g[1, ::2] = -half
+    x = np.full((B, 1, N), half, np.int32); x[1, 0, 1::3] = -half
+    r, rp, y, yp = s.small(B), s.small(B), s.gaussian(B), s.gaussian(B)
+    lim = eng.small_limit()
+    y[0] = lim; y[1, :, ::2] = -lim
+    lc = eng.linear_commit(g, x, rp, r, y, yp)
+    lo = o.linear_commit_batch(g, x, rp, r, y, yp)
+    for kname in ("gx", "cp", "c", "t", "tp", "u"):
+        assert (lc[kname] == lo[kname]).all(), kname
+
+
+def test_i64_staging(setup):
+    eng, o, s = setup
+    rng = np.random.default_rng(5)
+    a = rng.integers(-2 ** 62, 2 ** 62, size=3 * N + 17, dtype=np.int64)
+    p = eng.pack_i64(a)
+    assert (p == o.center(a)).all()
+    assert (eng.unpack_i64(p) == p.astype(np.int64)).all()
+
+
+def test_full_size_properties(setup):
+    """BASELINE configs 2 and 3 at full size (2^16): size-independent properties.
+    - linearity of the commitment: com(x1; r1) + com(x2; r2) == com(x1 + x2; r1 + r2)  (mod q)
+    - honest Open transcripts verify; a tampered subset does not
+    - a random sample of items is bit-exact against the oracle."""
+    eng, o, s = setup
+    B = 1 << 16
+    x1, x2 = s.message(B), s.message(B)
+    r1, r2 = s.small(B), s.small(B)
+    c1, ok1 = eng.commit(x1, r1)
+    c2, ok2 = eng.commit(x2, r2)
+    x12 = o.center(x1.astype(np.int64) + x2).astype(np.int32)
+    c12, _ = eng.commit(x12, (r1 + r2).astype(np.int8))
+    assert (o.center(c1.astype(np.int64) + c2) == c12).all()
+    assert UB(ok1, B).all() and UB(ok2, B).all()
+    idx = np.random.default_rng(1).choice(B, 48, replace=False)
+    c_o, _ = o.commit_batch(x1[idx], r1[idx])
+    assert (c1[idx] == c_o).all()
+    y, d = s.gaussian(B), s.challenge(B)
+    c, t, _ = eng.open_commit(x1, r1, y)
+    assert (c == c1).all()
+    z = eng.open_respond(y, r1, d)
+    cc1 = np.ascontiguousarray(c[:, :1])
+    assert UB(eng.open_verify(z, t, cc1, d), B).all()
+    z[::1000, 1, 77] ^= 1
+    v = UB(eng.open_verify(z, t, cc1, d), B)
+    assert not v[::1000].any() and v.sum() == B - len(range(0, B, 1000))
+    t_o = o.open_commit_batch(x1[idx], r1[idx], y[idx])[1]
+    assert (t[idx] == t_o).all()
