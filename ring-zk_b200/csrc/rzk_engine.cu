@@ -19,9 +19,6 @@
 #include "../../include/ringzk_b200.h"
 #include "rzk_vm.h"
 
-namespace rzk {
-__constant__ uint32_t c_g1[kNumPrimeSlots][2][32][2];
-}
 #include "rzk_vm_exec.cuh"
 #include "rzk_programs.h"
 #include "rzk_tables.h"
@@ -30,49 +27,65 @@ using namespace rzk;
 
 // ------------------------------------------------------------------------------ kernels
 
-template <int NP, int NSTASH>
+// warps per CTA: SPLIT fits 16 warps in 128 registers; the SEQ kernels finish 32 coefficients per
+// lane in the epilogue and get a larger register budget.
+template <int NP, bool SPLIT>
+struct VmCfg { static constexpr int kMaxWarps = SPLIT ? 16 : (NP == 1 ? 12 : 8); };
+
+template <int NP>
 struct VmSmem {
+    static constexpr int kG1 = NP * 2 * kG1Words;
     static constexpr int kG2 = NP * 2 * kLanes * kG2Words;
     static constexpr int kKey = NP * kKeyPolys * 2 * kPadWords;
-    static constexpr int kPerHw = kBufWords + 2 * kSlotWords + NSTASH * (NP - 1) * kSlotWords;
-    static_assert(kPerHw % 32 == 16, "half-warp regions must be shifted by 16 banks");
-    static constexpr size_t bytes(int warps) { return sizeof(uint32_t) * (size_t)(kG2 + kKey + warps * 2 * kPerHw); }
+    static constexpr int kTables = (kG1 + kG2 + kKey + 3) / 4 * 4;
+    static size_t bytes(int warps, uint32_t hw_words) { return sizeof(uint32_t) * ((size_t)kTables + (size_t)warps * 2 * hw_words); }
 };
 
-template <int NP, int NSTASH, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 1) rzk_vm_kernel(const __grid_constant__ VmLaunch K)
+// Persistent kernel: blockDim.x / 32 warps per CTA (as many as the program's shared-memory needs
+// allow, up to 16), one CTA per SM, each warp loops over its items.
+template <int NP, bool SPLIT>
+__global__ void __launch_bounds__(VmCfg<NP, SPLIT>::kMaxWarps * 32, 1) rzk_vm_kernel(const __grid_constant__ VmLaunch K)
 {
     extern __shared__ __align__(16) uint32_t smem[];
-    using S = VmSmem<NP, NSTASH>;
-    uint32_t *s_g2 = smem;
+    using S = VmSmem<NP>;
+    uint32_t *s_g1 = smem;
+    uint32_t *s_g2 = s_g1 + S::kG1;
     uint32_t *s_key = s_g2 + S::kG2;
-    uint32_t *s_hw = s_key + S::kKey;
+    uint32_t *s_hw = smem + S::kTables;
+    const int nthreads = blockDim.x, warps = nthreads >> 5;
 
-    // stage the lane-specific twiddles and the key image of every prime of this launch
+    // stage the twiddles and the key image of every prime of this launch
     for (int i = 0; i < NP; ++i) {
         const uint32_t slot = K.pc[i].slot;
+        const uint32_t *g1src = K.g1tab + (size_t)slot * (2 * kG1Words);
+        for (int w = threadIdx.x; w < 2 * kG1Words; w += nthreads) s_g1[i * 2 * kG1Words + w] = g1src[w];
         const uint4 *g2src = reinterpret_cast<const uint4 *>(K.g2tab + (size_t)slot * (2 * kLanes * kG2Words));
         uint4 *g2dst = reinterpret_cast<uint4 *>(s_g2 + i * (2 * kLanes * kG2Words));
-        for (int w = threadIdx.x; w < 2 * kLanes * kG2Words / 4; w += WARPS * 32) g2dst[w] = g2src[w];
+        for (int w = threadIdx.x; w < 2 * kLanes * kG2Words / 4; w += nthreads) g2dst[w] = g2src[w];
         const uint4 *ksrc = reinterpret_cast<const uint4 *>(K.keytab + (size_t)slot * (kKeyPolys * 2 * kPadWords));
         uint4 *kdst = reinterpret_cast<uint4 *>(s_key + i * (kKeyPolys * 2 * kPadWords));
-        for (int w = threadIdx.x; w < kKeyPolys * 2 * kPadWords / 4; w += WARPS * 32) kdst[w] = ksrc[w];
+        for (int w = threadIdx.x; w < kKeyPolys * 2 * kPadWords / 4; w += nthreads) kdst[w] = ksrc[w];
     }
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, hw = lane >> 4, t = lane & 15;
-    uint32_t *mine = s_hw + (warp * 2 + hw) * S::kPerHw;
-    ItemCtx ctx;
+    uint32_t *mine = s_hw + (warp * 2 + hw) * K.hw_words;
+    LaneCtx ctx;
     ctx.buf = mine;
-    ctx.slot = mine + kBufWords;
-    ctx.acc1 = mine + kBufWords + kSlotWords;
-    ctx.stash = mine + kBufWords + 2 * kSlotWords;
+    ctx.slot = mine + K.off_slot;
+    ctx.acc1 = mine + K.off_acc1;
+    ctx.stash = mine + K.off_stash;
+    ctx.red = SPLIT ? s_hw + (warp * 2) * K.hw_words : mine;
+    ctx.ridx = SPLIT ? lane : t;
+    ctx.g1 = s_g1;
     ctx.g2 = s_g2;
     ctx.key = s_key;
-    ctx.g1 = nullptr;
+    ctx.t = t;
+    ctx.hw = hw;
 
-    const uint32_t per_grid = gridDim.x * WARPS * 2;
-    const uint32_t first = (blockIdx.x * WARPS + warp) * 2 + hw;
+    const uint32_t units = SPLIT ? 1u : 2u;                          // items per warp
+    const uint32_t per_grid = gridDim.x * warps * units;
+    const uint32_t first = (blockIdx.x * warps + warp) * units + (SPLIT ? 0u : (uint32_t)hw);
     const uint32_t iters = (K.n_items + per_grid - 1) / per_grid;
     Lane L;
 #pragma unroll 1
@@ -80,7 +93,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rzk_vm_kernel(const __grid_cons
         const uint32_t item = first + it * per_grid;
         ctx.active = item < K.n_items;
         ctx.item = ctx.active ? item : K.n_items - 1;
-        vm_run_item<NP, NSTASH>(K, ctx, &L, t);
+        vm_run_item<NP, SPLIT>(K, &L, &ctx);
     }
 }
 
@@ -129,7 +142,6 @@ __global__ void rzk_unpack_i64_kernel(size_t n, const int32_t *__restrict__ src,
 namespace {
 
 constexpr int kPipe = 3;
-constexpr int kWarps1 = 8, kWarps2 = 8, kWarps3 = 6;
 
 struct PipeSlot {
     cudaStream_t stream = nullptr;
@@ -146,6 +158,7 @@ struct rzk_engine {
     int device = 0;
     int num_sms = 0;
     std::string err;
+    uint32_t *d_g1tab = nullptr;
     uint32_t *d_g2tab = nullptr;
     uint32_t *d_keytab = nullptr;
     uint32_t *d_misc = nullptr;     // [0] range word, [1] dummy flags word
@@ -204,6 +217,7 @@ void fill_common(const rzk_engine *e, VmLaunch &K, int np, uint32_t n_items, uin
     K.np = (uint32_t)np;
     if (flags) { K.flags = flags; K.flag_div = flag_div; }
     else { K.flags = e->d_misc + 1; K.flag_div = 0xFFFFFFFFu; }
+    K.g1tab = e->d_g1tab;
     K.g2tab = e->d_g2tab;
     K.keytab = e->d_keytab;
 }
@@ -213,31 +227,39 @@ void set_stream(VmLaunch &K, int i, const void *base, uint32_t stride, uint32_t 
     K.st[i].base = base; K.st[i].stride = stride; K.st[i].dtype = dtype; K.st[i].div = div; K.st[i].pad_ = 0;
 }
 
-template <int NP, int NSTASH, int WARPS>
-int launch_vm(rzk_engine *e, const VmLaunch &K, cudaStream_t s)
+template <int NP, bool SPLIT>
+int launch_vm(rzk_engine *e, VmLaunch &K, cudaStream_t s)
 {
     if (K.n_items == 0) return RZK_OK;
-    auto kern = rzk_vm_kernel<NP, NSTASH, WARPS>;
-    const size_t smem = VmSmem<NP, NSTASH>::bytes(WARPS);
+    auto kern = rzk_vm_kernel<NP, SPLIT>;
+    layout_hw(K, SPLIT);
+    const size_t max_smem = 227 * 1024;
+    int warps = (int)((max_smem - VmSmem<NP>::bytes(0, 0)) / (sizeof(uint32_t) * 2 * K.hw_words));
+    if (warps > VmCfg<NP, SPLIT>::kMaxWarps) warps = VmCfg<NP, SPLIT>::kMaxWarps;
+    const uint32_t per_warp = SPLIT ? 1 : 2;
+    // do not launch more warps per CTA than the batch can use
+    const uint32_t want = (uint32_t)((K.n_items + (uint64_t)e->num_sms * per_warp - 1) / ((uint64_t)e->num_sms * per_warp));
+    if ((uint32_t)warps > want) warps = (int)(want ? want : 1);
+    const size_t smem = VmSmem<NP>::bytes(warps, K.hw_words);
     static bool configured[16] = {};   // per device
     if (!configured[e->device & 15]) {
-        RZK_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RZK_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
         configured[e->device & 15] = true;
     }
-    const uint32_t per_cta = WARPS * 2;
+    const uint32_t per_cta = (uint32_t)warps * per_warp;
     uint32_t grid = (K.n_items + per_cta - 1) / per_cta;
     if (grid > (uint32_t)e->num_sms) grid = (uint32_t)e->num_sms;
-    kern<<<grid, WARPS * 32, smem, s>>>(K);
+    kern<<<grid, warps * 32, smem, s>>>(K);
     RZK_CUDA(e, cudaGetLastError());
     e->launches++;
     return RZK_OK;
 }
 
-int launch_np(rzk_engine *e, int np, const VmLaunch &K, cudaStream_t s)
+int launch_np(rzk_engine *e, int np, VmLaunch &K, cudaStream_t s)
 {
-    if (np == 1) return launch_vm<1, 0, kWarps1>(e, K, s);
-    if (np == 2) return launch_vm<2, 2, kWarps2>(e, K, s);
-    return launch_vm<3, 1, kWarps3>(e, K, s);
+    if (np == 1) return launch_vm<1, false>(e, K, s);
+    if (np == 2) return launch_vm<2, true>(e, K, s);
+    return launch_vm<3, false>(e, K, s);
 }
 
 int check_ready(rzk_engine *e, bool need_key = true)
@@ -533,17 +555,18 @@ int rzk_create(const rzk_params *params, int device, rzk_engine **out)
         e->small_lim = (uint32_t)((c.P01half - (1ull << 33)) / ((uint64_t)(P.k - P.n) * (uint64_t)P.N * half));
     }
     // static tables
-    std::vector<uint32_t> g1((size_t)kNumPrimeSlots * 2 * 32 * 2), g2((size_t)kNumPrimeSlots * 2 * kLanes * kG2Words);
+    std::vector<uint32_t> g1((size_t)kNumPrimeSlots * 2 * kG1Words, 0), g2((size_t)kNumPrimeSlots * 2 * kLanes * kG2Words);
     for (int s = 0; s < kNumPrimeSlots; ++s) {
         const PrimeTables &T = prime_tables(s);
-        memcpy(&g1[(size_t)s * 2 * 32 * 2], T.g1, sizeof(T.g1));
+        for (int d = 0; d < 2; ++d) memcpy(&g1[((size_t)s * 2 + d) * kG1Words], T.g1[d], sizeof(T.g1[d]));
         memcpy(&g2[(size_t)s * 2 * kLanes * kG2Words], T.g2, sizeof(T.g2));
     }
     int rc = RZK_OK;
     auto cu = [&](cudaError_t err, const char *what) {
         if (err != cudaSuccess && rc == RZK_OK) rc = fail(nullptr, RZK_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(err));
     };
-    cu(cudaMemcpyToSymbol(c_g1, g1.data(), g1.size() * sizeof(uint32_t)), "cudaMemcpyToSymbol(c_g1)");
+    cu(cudaMalloc(&e->d_g1tab, g1.size() * sizeof(uint32_t)), "cudaMalloc(g1)");
+    if (rc == RZK_OK) cu(cudaMemcpy(e->d_g1tab, g1.data(), g1.size() * sizeof(uint32_t), cudaMemcpyHostToDevice), "cudaMemcpy(g1)");
     cu(cudaMalloc(&e->d_g2tab, g2.size() * sizeof(uint32_t)), "cudaMalloc(g2)");
     if (rc == RZK_OK) cu(cudaMemcpy(e->d_g2tab, g2.data(), g2.size() * sizeof(uint32_t), cudaMemcpyHostToDevice), "cudaMemcpy(g2)");
     cu(cudaMalloc(&e->d_keytab, (size_t)kNumPrimeSlots * kKeyPolys * 2 * kPadWords * sizeof(uint32_t)), "cudaMalloc(key)");
@@ -565,6 +588,7 @@ void rzk_destroy(rzk_engine *e)
         if (e->pipe[i].stream) cudaStreamDestroy(e->pipe[i].stream);
     }
     if (e->scratch) cudaFree(e->scratch);
+    if (e->d_g1tab) cudaFree(e->d_g1tab);
     if (e->d_g2tab) cudaFree(e->d_g2tab);
     if (e->d_keytab) cudaFree(e->d_keytab);
     if (e->d_misc) cudaFree(e->d_misc);

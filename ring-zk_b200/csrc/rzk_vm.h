@@ -26,6 +26,8 @@ constexpr int kPadWords = 576;     // 512 + 4 words of padding per 32 (conflict-
 constexpr int kBufWords = 592;     // transpose buffer per half-warp (+16: bank shift between halves)
 constexpr int kSlotWords = 512;    // lane-private slot (uint4 chunks interleaved over lanes)
 constexpr int kG2Words = 60;       // lane-specific twiddle words per (direction, prime, lane)
+constexpr int kG1Words = 66;       // lane-uniform twiddle words per (prime, direction): 32 (w, w') pairs + 2 pad
+                                   // (66 = 2 mod 32: the two half warps of a SPLIT warp hit different banks)
 constexpr int kKeyPolys = 3;       // non-trivial key polynomials a1'[0], a1'[1], a2'[0] at (n,k,l)=(1,3,1)
 constexpr int kMaxOps = 56;
 constexpr int kMaxStreams = 12;
@@ -102,9 +104,42 @@ struct VmLaunch {
     uint32_t np;               // primes in this launch
     uint32_t pad_;
     uint32_t *flags;           // device, one word per item group
+    const uint32_t *g1tab;     // device, [prime slot][dir][kG1Words]
     const uint32_t *g2tab;     // device, [prime slot][dir][16][60]
     const uint32_t *keytab;    // device, [prime slot][3][2][576]
+    // shared-memory layout of one half-warp region (words); sized from what the program uses
+    uint32_t hw_words;         // == 16 (mod 32): the two half warps of a warp sit 16 banks apart
+    uint32_t off_slot, off_acc1, off_stash;
 };
+
+// What a program needs per half warp (decides how many warps fit in shared memory).
+struct ProgNeeds {
+    bool slot = false, acc1 = false;
+    int nstash = 0;
+};
+
+inline ProgNeeds scan_needs(const Op *ops)
+{
+    ProgNeeds n;
+    for (int i = 0; i < kMaxOps && ops[i].code != OP_END; ++i) {
+        const Op &o = ops[i];
+        if (o.code == OP_ST || o.code == OP_MACV) n.slot = true;
+        if ((o.code == OP_MACK || o.code == OP_MACV || o.code == OP_INV) && o.a == 1) n.acc1 = true;
+        if (o.code == OP_INV && (int)o.b + 1 > n.nstash) n.nstash = (int)o.b + 1;
+    }
+    return n;
+}
+
+// Fills the half-warp layout fields; `split` programs keep no stash (residues are swapped by shuffles).
+inline void layout_hw(VmLaunch &K, bool split)
+{
+    const ProgNeeds n = scan_needs(K.ops);
+    uint32_t w = kBufWords;
+    K.off_slot = w;  if (n.slot) w += kSlotWords;
+    K.off_acc1 = w;  if (n.acc1) w += kSlotWords;
+    K.off_stash = w; if (!split && K.np > 1) w += (uint32_t)n.nstash * (K.np - 1) * kSlotWords;
+    K.hw_words = w;
+}
 
 // Host-side twiddle tables for one prime (built in rzk_tables.cpp).
 struct PrimeTables {

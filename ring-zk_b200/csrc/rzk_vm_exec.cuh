@@ -1,14 +1,20 @@
 // rzk_vm_exec.cuh -- per-lane implementation of the polynomial-op program (rzk_vm.h).
 //
 // The same source is compiled twice:
-//   * by nvcc for sm_100a, where RZK_NL == 1 and "each lane" is the calling thread
-//     (16 lanes = one half warp = one batch item, 32 coefficients per lane in registers);
-//   * by g++ for the host lane emulator (tests/cpp/emu_check.cpp), where RZK_NL == 16
-//     and the lane loop is explicit.  The emulator exists so that the exact kernel
-//     arithmetic and shared-memory layouts are checked against the CPU oracle without
-//     a GPU; it is test infrastructure, never a product fallback.
+//   * by nvcc for sm_100a, where RZK_NL == 1 and "each lane" is the calling thread;
+//   * by g++ for the host lane emulator (tests/cpp/emu_check.cpp), where RZK_NL == 32 and the
+//     lane loop over one warp is explicit.  The emulator exists so that the exact kernel
+//     arithmetic, shared-memory layouts and lane exchanges are checked against the CPU oracle
+//     without a GPU; it is test infrastructure, never a product fallback.
 //
-// Layouts (N = 512):
+// Execution modes (template parameter SPLIT):
+//   SPLIT (np == 2): one warp owns one batch item; half warp h works modulo prime h.  After the
+//       inverse transforms the two half warps swap half of their residues with warp shuffles, so
+//       every lane recombines 16 coefficients (Garner CRT) -- no residue ever leaves registers.
+//   SEQ (np == 1 or 3): one half warp owns one item and runs each segment once per prime; the
+//       residues of the earlier primes wait in a lane-private shared-memory stash.
+//
+// Layouts (N = 512, 16 lanes per polynomial, 32 coefficients per lane in registers):
 //   G1 (strided):    lane t holds coefficients i = t + 16*m,  m = 0..31   (stages 0..4: bits 8..4 are lane-local)
 //   G2 (contiguous): lane t holds positions   i = 32*t + e,   e = 0..31   (stages 5..8: bits 3..0 are lane-local)
 //   transpose buffer word of position i: i + 4*(i>>5)  (uint4 rows of 36 words -> conflict-free)
@@ -26,72 +32,66 @@
 #define RZK_SYNC() __syncwarp()
 #define RZK_UNROLL _Pragma("unroll")
 #define RZK_NOUNROLL _Pragma("unroll 1")
-#else
-#define RZK_VM inline
-#define RZK_NL 16
-#define RZK_SYNC() ((void)0)
-#define RZK_UNROLL
-#define RZK_NOUNROLL
-struct uint4 { uint32_t x, y, z, w; };
-#endif
-
-#if defined(__CUDACC__)
 // one lane per thread: no loop, no indexing, so the lane state stays in registers
 #define RZK_EACH_LANE if (constexpr int li_ = 0; true)
 #else
+#define RZK_VM inline
+#define RZK_NL 32
+#define RZK_SYNC() ((void)0)
+#define RZK_UNROLL
+#define RZK_NOUNROLL
 #define RZK_EACH_LANE for (int li_ = 0; li_ < RZK_NL; ++li_)
+struct uint4 { uint32_t x, y, z, w; };
+struct uint2 { uint32_t x, y; };
 #endif
-#define RZK_LANE Lane &L = lanes[li_]; const int t = t0 + li_; (void)t; (void)L
+
+#define RZK_LANE Lane &L = lanes[li_]; const LaneCtx &ctx = ctxs[li_]; const int t = ctx.t; (void)t; (void)L; (void)ctx
 
 namespace rzk {
 
 struct Lane {
     uint32_t cur[kElems];
     uint32_t acc0[kElems];   // accumulator 0 lives in registers; accumulator 1 in the lane-private smem slot ctx.acc1
+    PrimeC pc;               // constants of the prime this lane currently works with
+    int pi;                  // its index in the launch's prime list
     uint32_t fail;
     uint32_t rerr;
 };
 
-struct ItemCtx {
+struct LaneCtx {
     uint32_t *buf;         // [kBufWords]  transpose buffer of this half warp
     uint32_t *slot;        // [kSlotWords] operand slot of OP_ST / OP_MACV
     uint32_t *acc1;        // [kSlotWords] accumulator 1 (lane-private layout)
-    uint32_t *stash;       // [NSTASH][np-1][kSlotWords] residues of earlier primes
+    uint32_t *stash;       // SEQ: [nstash][np-1][kSlotWords] residues of earlier primes
+    uint32_t *red;         // reduction scratch shared by the lanes that own one item
+    const uint32_t *g1;    // staged [np][2][kG1Words]
     const uint32_t *g2;    // staged [np][2][16][60]
     const uint32_t *key;   // staged [np][3][2][576]
-    const uint32_t *g1;    // host emulator only: [slot][2][32][2]
-    uint32_t item;         // item index (clamped to n_items-1 for inactive half warps)
+    uint32_t item;         // item index (clamped to n_items-1 for idle lanes)
+    int t;                 // lane within the half warp, 0..15
+    int hw;                // half warp within the warp, 0..1
+    int ridx;              // index of this lane among the lanes that own the item
     bool active;
 };
-
-#if defined(__CUDA_ARCH__)
-#define RZK_G1(slot, dir, idx, j) c_g1[slot][dir][idx][j]
-#else
-#define RZK_G1(slot, dir, idx, j) ctx.g1[((((slot) * 2 + (dir)) * 32 + (idx)) * 2) + (j)]
-#endif
-
-RZK_VM int priv_index(int t, int e) { return (((e >> 2) * kLanes + t) << 2) + (e & 3); }
 
 // ---------------------------------------------------------------- transforms
 
 // One butterfly stage with compile-time geometry (all loops have constant trip counts so that
 // they unroll fully and the 32 coefficients stay in registers).
-//   G1 stages S = 0..4: distance 16>>S in the strided layout, lane-uniform twiddles (constant bank)
-//   G2 stages S = 5..8: distance 256>>S in the contiguous layout, lane-specific twiddles (shared memory)
+//   G1 stages S = 0..4: distance 16>>S in the strided layout, lane-uniform twiddles
+//   G2 stages S = 5..8: distance 256>>S in the contiguous layout, lane-specific twiddles
 template <int S, int DIR>
-RZK_VM void g1_stage(uint32_t (&a)[kElems], const ItemCtx &ctx, uint32_t slot, uint32_t p, uint32_t p2)
+RZK_VM void g1_stage(uint32_t (&a)[kElems], const uint2 *g1, uint32_t p, uint32_t p2)
 {
-    (void)ctx;
     constexpr int half = 16 >> S;
     RZK_UNROLL
     for (int b = 0; b < (1 << S); ++b) {
-        const uint32_t w = RZK_G1(slot, DIR, (1 << S) + b, 0);
-        const uint32_t wp = RZK_G1(slot, DIR, (1 << S) + b, 1);
+        const uint2 w = g1[(1 << S) + b];
         RZK_UNROLL
         for (int j = 0; j < half; ++j) {
             const int i0 = b * 2 * half + j;
-            if (DIR == 0) ct_bfly(a[i0], a[i0 + half], w, wp, p, p2);
-            else gs_bfly(a[i0], a[i0 + half], w, wp, p, p2);
+            if (DIR == 0) ct_bfly(a[i0], a[i0 + half], w.x, w.y, p, p2);
+            else gs_bfly(a[i0], a[i0 + half], w.x, w.y, p, p2);
         }
     }
 }
@@ -120,13 +120,14 @@ RZK_VM void g2_stage(uint32_t (&a)[kElems], const uint4 *tw4, uint32_t p, uint32
     }
 }
 
-RZK_VM void fwd_g1(uint32_t (&a)[kElems], const ItemCtx &ctx, uint32_t slot, uint32_t p, uint32_t p2)
+RZK_VM void fwd_g1(uint32_t (&a)[kElems], const uint32_t *g1tab, uint32_t p, uint32_t p2)
 {
-    g1_stage<0, 0>(a, ctx, slot, p, p2);
-    g1_stage<1, 0>(a, ctx, slot, p, p2);
-    g1_stage<2, 0>(a, ctx, slot, p, p2);
-    g1_stage<3, 0>(a, ctx, slot, p, p2);
-    g1_stage<4, 0>(a, ctx, slot, p, p2);
+    const uint2 *g1 = reinterpret_cast<const uint2 *>(g1tab);
+    g1_stage<0, 0>(a, g1, p, p2);
+    g1_stage<1, 0>(a, g1, p, p2);
+    g1_stage<2, 0>(a, g1, p, p2);
+    g1_stage<3, 0>(a, g1, p, p2);
+    g1_stage<4, 0>(a, g1, p, p2);
 }
 
 RZK_VM void fwd_g2(uint32_t (&a)[kElems], const uint32_t *tw, uint32_t p, uint32_t p2)
@@ -147,13 +148,14 @@ RZK_VM void inv_g2(uint32_t (&a)[kElems], const uint32_t *tw, uint32_t p, uint32
     g2_stage<5, 1>(a, tw4, p, p2);
 }
 
-RZK_VM void inv_g1(uint32_t (&a)[kElems], const ItemCtx &ctx, uint32_t slot, uint32_t p, uint32_t p2)
+RZK_VM void inv_g1(uint32_t (&a)[kElems], const uint32_t *g1tab, uint32_t p, uint32_t p2)
 {
-    g1_stage<4, 1>(a, ctx, slot, p, p2);
-    g1_stage<3, 1>(a, ctx, slot, p, p2);
-    g1_stage<2, 1>(a, ctx, slot, p, p2);
-    g1_stage<1, 1>(a, ctx, slot, p, p2);
-    g1_stage<0, 1>(a, ctx, slot, p, p2);
+    const uint2 *g1 = reinterpret_cast<const uint2 *>(g1tab);
+    g1_stage<4, 1>(a, g1, p, p2);
+    g1_stage<3, 1>(a, g1, p, p2);
+    g1_stage<2, 1>(a, g1, p, p2);
+    g1_stage<1, 1>(a, g1, p, p2);
+    g1_stage<0, 1>(a, g1, p, p2);
 }
 
 // ---------------------------------------------------------------- global memory
@@ -165,13 +167,13 @@ RZK_VM uint64_t stream_poly(const Stream &s, uint32_t item, uint32_t off)
 
 // ---------------------------------------------------------------- ops
 
-RZK_VM void op_fwd(const VmLaunch &K, const ItemCtx &ctx, Lane *lanes, int t0, const Op &op, int it, int pi)
+RZK_VM void op_fwd(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const Op &op, int it)
 {
-    const PrimeC pc = K.pc[pi];
     const Stream st = K.st[op.a];
-    const uint64_t poly = stream_poly(st, ctx.item, (uint32_t)op.off + (uint32_t)it * op.step);
     RZK_EACH_LANE {
         RZK_LANE;
+        const PrimeC &pc = L.pc;
+        const uint64_t poly = stream_poly(st, ctx.item, (uint32_t)op.off + (uint32_t)it * op.step);
         int32_t v[kElems];
         if (st.dtype == DT_I8) {
             const int8_t *src = reinterpret_cast<const int8_t *>(st.base) + poly * kN;
@@ -200,7 +202,7 @@ RZK_VM void op_fwd(const VmLaunch &K, const ItemCtx &ctx, Lane *lanes, int t0, c
             RZK_UNROLL
             for (int m = 0; m < kElems; ++m) L.cur[m] = (uint32_t)v[m] + pc.p2;
         }
-        fwd_g1(L.cur, ctx, pc.slot, pc.p, pc.p2);
+        fwd_g1(L.cur, ctx.g1 + (L.pi * 2 + 0) * kG1Words, pc.p, pc.p2);
         RZK_UNROLL
         for (int m = 0; m < kElems; ++m) {
             const int i = t + kLanes * m;
@@ -216,7 +218,7 @@ RZK_VM void op_fwd(const VmLaunch &K, const ItemCtx &ctx, Lane *lanes, int t0, c
             const uint4 q = row[j];
             L.cur[4 * j + 0] = q.x; L.cur[4 * j + 1] = q.y; L.cur[4 * j + 2] = q.z; L.cur[4 * j + 3] = q.w;
         }
-        fwd_g2(L.cur, ctx.g2 + ((pi * 2 + 0) * kLanes + t) * kG2Words, pc.p, pc.p2);
+        fwd_g2(L.cur, ctx.g2 + ((L.pi * 2 + 0) * kLanes + t) * kG2Words, L.pc.p, L.pc.p2);
     }
     RZK_SYNC();
 }
@@ -304,11 +306,11 @@ RZK_VM void mac_var_smem(uint32_t *acc1, const uint32_t (&cur)[kElems], const ui
     }
 }
 
-RZK_VM void op_st(const VmLaunch &K, const ItemCtx &ctx, Lane *lanes, int t0, int pi)
+RZK_VM void op_st(Lane *lanes, const LaneCtx *ctxs)
 {
-    const PrimeC pc = K.pc[pi];
     RZK_EACH_LANE {
         RZK_LANE;
+        const PrimeC &pc = L.pc;
         uint4 *s4 = reinterpret_cast<uint4 *>(ctx.slot);
         RZK_UNROLL
         for (int j = 0; j < 8; ++j) {
@@ -323,47 +325,62 @@ RZK_VM void op_st(const VmLaunch &K, const ItemCtx &ctx, Lane *lanes, int t0, in
     // lane-private: no cross-lane hazard, no sync needed
 }
 
-RZK_VM void op_addp(const VmLaunch &K, const ItemCtx &ctx, int64_t (&V)[RZK_NL][kElems], int t0, const Op &op, int it)
+// ---------------------------------------------------------------- epilogue (last prime only)
+
+// Number of coefficients a lane finishes: SPLIT lanes share an item between two half warps.
+template <bool SPLIT>
+struct Epi { static constexpr int kCount = SPLIT ? 16 : 32; };
+
+// coefficient index m (in the G1 layout, i = t + 16*m) of epilogue element j
+template <bool SPLIT>
+RZK_VM int epi_m(const LaneCtx &ctx, int j) { return SPLIT ? (16 * ctx.hw + j) : j; }
+
+template <bool SPLIT>
+RZK_VM void op_addp(const VmLaunch &K, const LaneCtx *ctxs, int64_t (&V)[RZK_NL][Epi<SPLIT>::kCount], const Op &op, int it)
 {
+    constexpr int CNT = Epi<SPLIT>::kCount;
     const Stream st = K.st[op.a];
-    const uint64_t poly = stream_poly(st, ctx.item, (uint32_t)op.off + (uint32_t)it * op.step);
     const bool neg = op.c & MAC_NEG;
     RZK_EACH_LANE {
-        const int t = t0 + li_;
-        int32_t v[kElems];
+        const LaneCtx &ctx = ctxs[li_];
+        const int t = ctx.t;
+        const uint64_t poly = stream_poly(st, ctx.item, (uint32_t)op.off + (uint32_t)it * op.step);
+        int32_t v[CNT];
         if (st.dtype == DT_I8) {
             const int8_t *src = reinterpret_cast<const int8_t *>(st.base) + poly * kN;
             RZK_UNROLL
-            for (int m = 0; m < kElems; ++m) v[m] = src[t + kLanes * m];
+            for (int j = 0; j < CNT; ++j) v[j] = src[t + kLanes * epi_m<SPLIT>(ctx, j)];
         } else {
             const int32_t *src = reinterpret_cast<const int32_t *>(st.base) + poly * kN;
             RZK_UNROLL
-            for (int m = 0; m < kElems; ++m) v[m] = canon_q(src[t + kLanes * m], K.q);
+            for (int j = 0; j < CNT; ++j) v[j] = canon_q(src[t + kLanes * epi_m<SPLIT>(ctx, j)], K.q);
         }
         RZK_UNROLL
-        for (int m = 0; m < kElems; ++m) V[li_][m] += neg ? -(int64_t)v[m] : (int64_t)v[m];
+        for (int j = 0; j < CNT; ++j) V[li_][j] += neg ? -(int64_t)v[j] : (int64_t)v[j];
     }
 }
 
-RZK_VM void op_fin(const VmLaunch &K, const ItemCtx &ctx, Lane *lanes, int64_t (&V)[RZK_NL][kElems], int t0, const Op &op, int it)
+template <bool SPLIT>
+RZK_VM void op_fin(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int64_t (&V)[RZK_NL][Epi<SPLIT>::kCount], const Op &op, int it)
 {
+    constexpr int CNT = Epi<SPLIT>::kCount;
     const Stream st = K.st[op.a];
-    const uint64_t poly = stream_poly(st, ctx.item, (uint32_t)op.off + (uint32_t)it * op.step);
     RZK_EACH_LANE {
         RZK_LANE;
-        int32_t res[kElems];
+        const uint64_t poly = stream_poly(st, ctx.item, (uint32_t)op.off + (uint32_t)it * op.step);
+        int32_t res[CNT];
         RZK_UNROLL
-        for (int m = 0; m < kElems; ++m) res[m] = reduce_q_centered(V[li_][m], K.q, K.bar, K.kq);
+        for (int j = 0; j < CNT; ++j) res[j] = reduce_q_centered(V[li_][j], K.q, K.bar, K.kq);
         if (op.b & FIN_CMPZ) {
             uint32_t nz = 0;
             RZK_UNROLL
-            for (int m = 0; m < kElems; ++m) nz |= (uint32_t)res[m];
+            for (int j = 0; j < CNT; ++j) nz |= (uint32_t)res[j];
             L.fail |= nz ? 1u : 0u;
         }
         if ((op.b & FIN_STORE) && ctx.active) {
             int32_t *dst = reinterpret_cast<int32_t *>(const_cast<void *>(st.base)) + poly * kN;
             RZK_UNROLL
-            for (int m = 0; m < kElems; ++m) dst[t + kLanes * m] = res[m];
+            for (int j = 0; j < CNT; ++j) dst[t + kLanes * epi_m<SPLIT>(ctx, j)] = res[j];
         }
     }
 }
@@ -406,14 +423,16 @@ RZK_VM int64_t crt_combine(const VmLaunch &K, const uint32_t (&r)[kMaxPrimes])
 // Inverse transform of acc[a].  On the last prime the residues of all primes are combined and
 // the epilogue ops that follow (OP_ADDP*, OP_FIN) are executed here, so that the 64-bit
 // values live only inside this function.  Returns the index of the first op after the epilogue.
-template <int NP, int NSTASH>
-RZK_VM int op_inv(const VmLaunch &K, const ItemCtx &ctx, Lane *lanes, int t0, int q, int it, int pi)
+template <int NP, bool SPLIT>
+RZK_VM int op_inv(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int q, int it, int prime_iter)
 {
+    constexpr int CNT = Epi<SPLIT>::kCount;
     const Op op = K.ops[q];
-    int64_t V[RZK_NL][kElems];
-    const PrimeC pc = K.pc[pi];
+    const bool last = SPLIT || (prime_iter == NP - 1);
+    int64_t V[RZK_NL][CNT];
     RZK_EACH_LANE {
         RZK_LANE;
+        const PrimeC &pc = L.pc;
         if (op.a == 0) {
             RZK_UNROLL
             for (int e = 0; e < kElems; ++e) L.cur[e] = L.acc0[e];
@@ -425,94 +444,130 @@ RZK_VM int op_inv(const VmLaunch &K, const ItemCtx &ctx, Lane *lanes, int t0, in
                 L.cur[4 * j + 0] = a.x; L.cur[4 * j + 1] = a.y; L.cur[4 * j + 2] = a.z; L.cur[4 * j + 3] = a.w;
             }
         }
-        inv_g2(L.cur, ctx.g2 + ((pi * 2 + 1) * kLanes + t) * kG2Words, pc.p, pc.p2);
+        inv_g2(L.cur, ctx.g2 + ((L.pi * 2 + 1) * kLanes + t) * kG2Words, pc.p, pc.p2);
         uint4 *row = reinterpret_cast<uint4 *>(ctx.buf + 36 * t);
         RZK_UNROLL
         for (int j = 0; j < 8; ++j) {
-            uint4 q;
-            q.x = L.cur[4 * j + 0]; q.y = L.cur[4 * j + 1]; q.z = L.cur[4 * j + 2]; q.w = L.cur[4 * j + 3];
-            row[j] = q;
+            uint4 w;
+            w.x = L.cur[4 * j + 0]; w.y = L.cur[4 * j + 1]; w.z = L.cur[4 * j + 2]; w.w = L.cur[4 * j + 3];
+            row[j] = w;
         }
     }
     RZK_SYNC();
     RZK_EACH_LANE {
         RZK_LANE;
+        const PrimeC &pc = L.pc;
         RZK_UNROLL
         for (int m = 0; m < kElems; ++m) {
             const int i = t + kLanes * m;
             L.cur[m] = ctx.buf[i + ((i >> 5) << 2)];
         }
-        inv_g1(L.cur, ctx, pc.slot, pc.p, pc.p2);
+        inv_g1(L.cur, ctx.g1 + (L.pi * 2 + 1) * kG1Words, pc.p, pc.p2);
         RZK_UNROLL
         for (int m = 0; m < kElems; ++m) L.cur[m] = csub(L.cur[m], pc.p);     // [0,2p) -> [0,p)
-        if (pi < NP - 1) {
-            uint4 *s4 = reinterpret_cast<uint4 *>(ctx.stash + ((int)op.b * (NP - 1) + pi) * kSlotWords);
-            RZK_UNROLL
-            for (int j = 0; j < 8; ++j) {
-                uint4 q;
-                q.x = L.cur[4 * j + 0]; q.y = L.cur[4 * j + 1]; q.z = L.cur[4 * j + 2]; q.w = L.cur[4 * j + 3];
-                s4[j * kLanes + t] = q;
+    }
+    RZK_SYNC();
+    if (SPLIT) {
+        // half warp 0 holds residues mod p0, half warp 1 mod p1, both for all 512 coefficients.
+        // Lane (h, t) finishes coefficients m in [16h, 16h+16): it keeps its own residue of those
+        // and receives the partner's; it sends its residues of the other half.
+        uint32_t recv[RZK_NL][16];
+#if defined(__CUDA_ARCH__)
+        RZK_UNROLL
+        for (int j = 0; j < 16; ++j) {
+            const uint32_t send = ctxs[0].hw ? lanes[0].cur[j] : lanes[0].cur[16 + j];
+            recv[0][j] = __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+#else
+        for (int li = 0; li < RZK_NL; ++li)
+            for (int j = 0; j < 16; ++j) {
+                const int partner = li ^ 16;
+                recv[li][j] = ctxs[partner].hw ? lanes[partner].cur[j] : lanes[partner].cur[16 + j];
             }
-        } else {
-            uint32_t prev[2][kElems];
+#endif
+        RZK_EACH_LANE {
+            RZK_LANE;
             RZK_UNROLL
-            for (int k = 0; k < NP - 1; ++k) {
-                const uint4 *s4 = reinterpret_cast<const uint4 *>(ctx.stash + ((int)op.b * (NP - 1) + k) * kSlotWords);
+            for (int j = 0; j < 16; ++j) {
+                const uint32_t own = ctx.hw ? L.cur[16 + j] : L.cur[j];
+                uint32_t r[kMaxPrimes] = {0, 0, 0};
+                r[0] = ctx.hw ? recv[li_][j] : own;
+                r[1] = ctx.hw ? own : recv[li_][j];
+                V[li_][j % CNT] = crt_combine<2>(K, r);
+            }
+        }
+    } else {
+        RZK_EACH_LANE {
+            RZK_LANE;
+            if (prime_iter < NP - 1) {
+                uint4 *s4 = reinterpret_cast<uint4 *>(ctx.stash + ((int)op.b * (NP - 1) + prime_iter) * kSlotWords);
                 RZK_UNROLL
                 for (int j = 0; j < 8; ++j) {
-                    const uint4 q = s4[j * kLanes + t];
-                    prev[k][4 * j + 0] = q.x; prev[k][4 * j + 1] = q.y; prev[k][4 * j + 2] = q.z; prev[k][4 * j + 3] = q.w;
+                    uint4 w;
+                    w.x = L.cur[4 * j + 0]; w.y = L.cur[4 * j + 1]; w.z = L.cur[4 * j + 2]; w.w = L.cur[4 * j + 3];
+                    s4[j * kLanes + t] = w;
                 }
-            }
-            RZK_UNROLL
-            for (int m = 0; m < kElems; ++m) {
-                uint32_t r[kMaxPrimes] = {0, 0, 0};
+            } else {
+                uint32_t prev[NP > 1 ? NP - 1 : 1][kElems];
                 RZK_UNROLL
-                for (int k = 0; k < NP - 1; ++k) r[k] = prev[k][m];
-                r[NP - 1] = L.cur[m];
-                V[li_][m] = crt_combine<NP>(K, r);
+                for (int k = 0; k < NP - 1; ++k) {
+                    const uint4 *s4 = reinterpret_cast<const uint4 *>(ctx.stash + ((int)op.b * (NP - 1) + k) * kSlotWords);
+                    RZK_UNROLL
+                    for (int j = 0; j < 8; ++j) {
+                        const uint4 w = s4[j * kLanes + t];
+                        prev[k][4 * j + 0] = w.x; prev[k][4 * j + 1] = w.y; prev[k][4 * j + 2] = w.z; prev[k][4 * j + 3] = w.w;
+                    }
+                }
+                RZK_UNROLL
+                for (int m = 0; m < kElems; ++m) {
+                    uint32_t r[kMaxPrimes] = {0, 0, 0};
+                    RZK_UNROLL
+                    for (int k = 0; k < NP - 1; ++k) r[k] = prev[k][m];
+                    r[NP - 1] = L.cur[m];
+                    V[li_][m % CNT] = crt_combine<NP>(K, r);
+                }
             }
         }
     }
-    RZK_SYNC();
-    (void)NSTASH;
-    const bool last = (pi == NP - 1);
     ++q;
     RZK_NOUNROLL
     for (;; ++q) {
         const Op e = K.ops[q];
-        if (e.code == OP_ADDP) { if (last) op_addp(K, ctx, V, t0, e, it); }
-        else if (e.code == OP_FIN) { if (last) op_fin(K, ctx, lanes, V, t0, e, it); }
+        if (e.code == OP_ADDP) { if (last) op_addp<SPLIT>(K, ctxs, V, e, it); }
+        else if (e.code == OP_FIN) { if (last) op_fin<SPLIT>(K, lanes, ctxs, V, e, it); }
         else break;
     }
     return q;
 }
 
 // params.rs:102-118 via polynomial.rs:60-73: floor(sqrt(sum c^2)) <= bound  <=>  sum c^2 < (bound+1)^2
-RZK_VM void op_norm(const VmLaunch &K, const ItemCtx &ctx, Lane *lanes, int t0, const Op &op)
+template <bool SPLIT>
+RZK_VM void op_norm(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const Op &op)
 {
+    constexpr int CNT = Epi<SPLIT>::kCount;
+    constexpr int RED_N = SPLIT ? 32 : 16;
     const Stream st = K.st[op.a];
     const uint32_t abs_lim = K.norm_abs_lim[op.b];
     const uint64_t sq_lim = K.norm_sq_lim[op.b];
     RZK_NOUNROLL
     for (int c = 0; c < (int)op.c; ++c) {
-        const uint64_t poly = stream_poly(st, ctx.item, (uint32_t)op.off + (uint32_t)c);
         RZK_EACH_LANE {
             RZK_LANE;
+            const uint64_t poly = stream_poly(st, ctx.item, (uint32_t)op.off + (uint32_t)c);
             uint64_t s = 0;
             uint32_t bad = 0;
             if (st.dtype == DT_I8) {
                 const int8_t *src = reinterpret_cast<const int8_t *>(st.base) + poly * kN;
                 RZK_UNROLL
-                for (int m = 0; m < kElems; ++m) {
-                    const int32_t v = src[t + kLanes * m];
+                for (int j = 0; j < CNT; ++j) {
+                    const int32_t v = src[t + kLanes * epi_m<SPLIT>(ctx, j)];
                     s += (uint64_t)(uint32_t)(v * v);
                 }
             } else {
                 const int32_t *src = reinterpret_cast<const int32_t *>(st.base) + poly * kN;
                 RZK_UNROLL
-                for (int m = 0; m < kElems; ++m) {
-                    const int32_t v = canon_q(src[t + kLanes * m], K.q);
+                for (int j = 0; j < CNT; ++j) {
+                    const int32_t v = canon_q(src[t + kLanes * epi_m<SPLIT>(ctx, j)], K.q);
                     const uint32_t av = (uint32_t)(v < 0 ? -v : v);
                     const bool big = av > abs_lim;
                     bad |= big ? 1u : 0u;
@@ -520,15 +575,15 @@ RZK_VM void op_norm(const VmLaunch &K, const ItemCtx &ctx, Lane *lanes, int t0, 
                 }
             }
             L.fail |= bad;
-            ctx.buf[2 * t] = (uint32_t)s;
-            ctx.buf[2 * t + 1] = (uint32_t)(s >> 32);
+            ctx.red[2 * ctx.ridx] = (uint32_t)s;
+            ctx.red[2 * ctx.ridx + 1] = (uint32_t)(s >> 32);
         }
         RZK_SYNC();
         RZK_EACH_LANE {
             RZK_LANE;
             uint64_t tot = 0;
             RZK_UNROLL
-            for (int j = 0; j < kLanes; ++j) tot += (uint64_t)ctx.buf[2 * j] | ((uint64_t)ctx.buf[2 * j + 1] << 32);
+            for (int j = 0; j < RED_N; ++j) tot += (uint64_t)ctx.red[2 * j] | ((uint64_t)ctx.red[2 * j + 1] << 32);
             L.fail |= (tot > sq_lim) ? 1u : 0u;
         }
         RZK_SYNC();
@@ -537,14 +592,18 @@ RZK_VM void op_norm(const VmLaunch &K, const ItemCtx &ctx, Lane *lanes, int t0, 
 
 // ---------------------------------------------------------------- interpreter
 
-template <int NP, int NSTASH>
-RZK_VM void vm_run_item(const VmLaunch &K, const ItemCtx &ctx, Lane *lanes, int t0)
+// Runs the whole program for the item(s) owned by this warp.
+template <int NP, bool SPLIT>
+RZK_VM void vm_run_item(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs)
 {
+    static_assert(!SPLIT || NP == 2, "SPLIT mode maps the two half warps to two primes");
+    constexpr int RED_N = SPLIT ? 32 : 16;
+    constexpr int PRIME_ITERS = SPLIT ? 1 : NP;
     RZK_EACH_LANE { RZK_LANE; L.fail = 0; L.rerr = 0; }
     int pc = 0;
     RZK_NOUNROLL
     while (K.ops[pc].code == OP_NORM) {
-        op_norm(K, ctx, lanes, t0, K.ops[pc]);
+        op_norm<SPLIT>(K, lanes, ctxs, K.ops[pc]);
         ++pc;
     }
     RZK_NOUNROLL
@@ -552,8 +611,12 @@ RZK_VM void vm_run_item(const VmLaunch &K, const ItemCtx &ctx, Lane *lanes, int 
         const int seg_begin = pc + 1;
         int seg_end = seg_begin;
         RZK_NOUNROLL
-        for (int pi = 0; pi < NP; ++pi) {
-            const PrimeC pcst = K.pc[pi];
+        for (int prime_iter = 0; prime_iter < PRIME_ITERS; ++prime_iter) {
+            RZK_EACH_LANE {
+                RZK_LANE;
+                L.pi = SPLIT ? ctx.hw : prime_iter;
+                L.pc = K.pc[L.pi];
+            }
             int q = seg_begin, loop_start = 0, loop_cnt = 0, it = 0;
             RZK_NOUNROLL
             for (;;) {
@@ -561,29 +624,28 @@ RZK_VM void vm_run_item(const VmLaunch &K, const ItemCtx &ctx, Lane *lanes, int 
                 if (op.code == OP_SEG || op.code == OP_END) break;
                 switch (op.code) {
                 case OP_FWD:
-                    op_fwd(K, ctx, lanes, t0, op, it, pi);
+                    op_fwd(K, lanes, ctxs, op, it);
                     break;
-                case OP_MACK: {
-                    const uint32_t *krow = ctx.key + ((pi * kKeyPolys + (int)op.b) * 2) * kPadWords;
+                case OP_MACK:
                     RZK_EACH_LANE {
                         RZK_LANE;
-                        if (op.a == 0) mac_key(L.acc0, L.cur, krow, t, op.c, pcst.p, pcst.p2);
-                        else mac_key_smem(ctx.acc1, L.cur, krow, t, op.c, pcst.p, pcst.p2);
+                        const uint32_t *krow = ctx.key + ((L.pi * kKeyPolys + (int)op.b) * 2) * kPadWords;
+                        if (op.a == 0) mac_key(L.acc0, L.cur, krow, t, op.c, L.pc.p, L.pc.p2);
+                        else mac_key_smem(ctx.acc1, L.cur, krow, t, op.c, L.pc.p, L.pc.p2);
                     }
                     break;
-                }
                 case OP_MACV:
                     RZK_EACH_LANE {
                         RZK_LANE;
-                        if (op.a == 0) mac_var(L.acc0, L.cur, ctx.slot, t, op.c, pcst.p, pcst.p2, pcst.pinv);
-                        else mac_var_smem(ctx.acc1, L.cur, ctx.slot, t, op.c, pcst.p, pcst.p2, pcst.pinv);
+                        if (op.a == 0) mac_var(L.acc0, L.cur, ctx.slot, t, op.c, L.pc.p, L.pc.p2, L.pc.pinv);
+                        else mac_var_smem(ctx.acc1, L.cur, ctx.slot, t, op.c, L.pc.p, L.pc.p2, L.pc.pinv);
                     }
                     break;
                 case OP_ST:
-                    op_st(K, ctx, lanes, t0, pi);
+                    op_st(lanes, ctxs);
                     break;
                 case OP_INV:
-                    q = op_inv<NP, NSTASH>(K, ctx, lanes, t0, q, it, pi);
+                    q = op_inv<NP, SPLIT>(K, lanes, ctxs, q, it, prime_iter);
                     continue;
                 case OP_LOOP:
                     loop_start = q + 1; loop_cnt = op.off; it = 0;
@@ -601,15 +663,15 @@ RZK_VM void vm_run_item(const VmLaunch &K, const ItemCtx &ctx, Lane *lanes, int 
         }
         pc = seg_end;
     }
-    // fold the 16 lanes' status words into the item-group flag word
-    RZK_EACH_LANE { RZK_LANE; ctx.buf[t] = L.fail | (L.rerr << 1); }
+    // fold the owning lanes' status words into the item-group flag word
+    RZK_EACH_LANE { RZK_LANE; ctx.red[ctx.ridx] = L.fail | (L.rerr << 1); }
     RZK_SYNC();
     RZK_EACH_LANE {
         RZK_LANE;
-        if (t == 0 && ctx.active) {
+        if (ctx.ridx == 0 && ctx.active) {
             uint32_t f = 0;
             RZK_UNROLL
-            for (int j = 0; j < kLanes; ++j) f |= ctx.buf[j];
+            for (int j = 0; j < RED_N; ++j) f |= ctx.red[j];
             if (f) {
 #if defined(__CUDA_ARCH__)
                 atomicOr(&K.flags[ctx.item / K.flag_div], f);

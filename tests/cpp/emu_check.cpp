@@ -41,22 +41,19 @@ struct Emu {
     int slots[3];
     std::vector<uint32_t> g1, g2, key, flags;
     VmLaunch K;
-    std::vector<uint32_t> buf, slot, acc1, stash;
+    std::vector<uint32_t> region;     // two half-warp regions
 
     Emu(int np_, const int *sl, const int64_t *keypolys /*[3][512]*/, size_t nflags)
     {
         np = np_;
         memset(&K, 0, sizeof(K));
-        g1.resize(kNumPrimeSlots * 2 * 32 * 2);
+        g1.assign((size_t)np * 2 * kG1Words, 0);
         g2.resize((size_t)np * 2 * kLanes * kG2Words);
         key.resize((size_t)np * kKeyPolys * 2 * kPadWords);
-        for (int s = 0; s < kNumPrimeSlots; ++s) {
-            const PrimeTables &T = prime_tables(s);
-            memcpy(&g1[(size_t)s * 2 * 32 * 2], T.g1, sizeof(T.g1));
-        }
         for (int i = 0; i < np; ++i) {
             slots[i] = sl[i];
             const PrimeTables &T = prime_tables(sl[i]);
+            for (int d = 0; d < 2; ++d) memcpy(&g1[((size_t)i * 2 + d) * kG1Words], T.g1[d], sizeof(T.g1[d]));
             memcpy(&g2[(size_t)i * 2 * kLanes * kG2Words], T.g2, sizeof(T.g2));
             for (int k = 0; k < kKeyPolys; ++k)
                 key_image(T, keypolys + (size_t)k * kN, &key[((size_t)i * kKeyPolys + k) * 2 * kPadWords]);
@@ -75,27 +72,40 @@ struct Emu {
         K.flag_div = 1;
         flags.assign(nflags, 0);
         K.flags = flags.data();
-        buf.resize(kBufWords);
-        slot.resize(kSlotWords);
-        acc1.resize(kSlotWords);
-        stash.resize(2 * 2 * kSlotWords);
     }
     void stream(int i, const void *base, uint32_t stride, uint32_t dtype, uint32_t div = 1)
     {
         K.st[i].base = base; K.st[i].stride = stride; K.st[i].dtype = dtype; K.st[i].div = div;
     }
+    // Emulates one warp at a time exactly as the kernel maps it: SPLIT (np == 2) gives the warp one
+    // item with half warp h on prime h; SEQ gives each half warp its own item.
     void run(uint32_t n_items)
     {
         K.n_items = n_items;
-        static Lane lanes[16];
-        for (uint32_t it = 0; it < n_items; ++it) {
-            ItemCtx c;
-            c.buf = buf.data(); c.slot = slot.data(); c.acc1 = acc1.data(); c.stash = stash.data();
-            c.g2 = g2.data(); c.key = key.data(); c.g1 = g1.data();
-            c.item = it; c.active = true;
-            if (np == 1) vm_run_item<1, 2>(K, c, lanes, 0);
-            else if (np == 2) vm_run_item<2, 2>(K, c, lanes, 0);
-            else vm_run_item<3, 2>(K, c, lanes, 0);
+        const bool split = (np == 2);
+        layout_hw(K, split);
+        if (K.hw_words % 32 != 16) { printf("FAIL: hw_words %u not 16 mod 32\n", K.hw_words); exit(1); }
+        region.assign((size_t)2 * K.hw_words, 0xDEADBEEFu);
+        static Lane lanes[32];
+        static LaneCtx ctxs[32];
+        const uint32_t per_warp = split ? 1 : 2;
+        for (uint32_t base = 0; base < n_items; base += per_warp) {
+            for (int li = 0; li < 32; ++li) {
+                LaneCtx &c = ctxs[li];
+                const int hw = li >> 4;
+                uint32_t *mine = region.data() + (size_t)hw * K.hw_words;
+                c.buf = mine; c.slot = mine + K.off_slot; c.acc1 = mine + K.off_acc1; c.stash = mine + K.off_stash;
+                c.red = split ? region.data() : mine;
+                c.ridx = split ? li : (li & 15);
+                c.g1 = g1.data(); c.g2 = g2.data(); c.key = key.data();
+                c.t = li & 15; c.hw = hw;
+                const uint32_t item = base + (split ? 0 : hw);
+                c.active = item < n_items;
+                c.item = c.active ? item : n_items - 1;
+            }
+            if (np == 1) vm_run_item<1, false>(K, lanes, ctxs);
+            else if (np == 2) vm_run_item<2, true>(K, lanes, ctxs);
+            else vm_run_item<3, false>(K, lanes, ctxs);
         }
     }
 };
