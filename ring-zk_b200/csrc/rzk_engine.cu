@@ -29,25 +29,27 @@ using namespace rzk;
 
 // warps per CTA: SPLIT fits 16 warps in 128 registers; the SEQ kernels finish 32 coefficients per
 // lane in the epilogue and get a larger register budget.
-template <int NP, bool SPLIT>
-struct VmCfg { static constexpr int kMaxWarps = SPLIT ? 16 : (NP == 1 ? 12 : 8); };
+template <int NP, int MODE>
+struct VmCfg { static constexpr int kMaxWarps = (MODE != MODE_SEQ) ? 16 : (NP == 1 ? 12 : 8); };
 
-template <int NP>
+template <int NP, int MODE>
 struct VmSmem {
+    static constexpr int kKP = (MODE == MODE_SPLITKEY) ? 2 * kKeyPolys : kKeyPolys;   // key images per prime
     static constexpr int kG1 = NP * 2 * kG1Words;
     static constexpr int kG2 = NP * 2 * kLanes * kG2Words;
-    static constexpr int kKey = NP * kKeyPolys * 2 * kPadWords;
+    static constexpr int kKey = NP * kKP * 2 * kPadWords;
     static constexpr int kTables = (kG1 + kG2 + kKey + 3) / 4 * 4;
     static size_t bytes(int warps, uint32_t hw_words) { return sizeof(uint32_t) * ((size_t)kTables + (size_t)warps * 2 * hw_words); }
 };
 
 // Persistent kernel: blockDim.x / 32 warps per CTA (as many as the program's shared-memory needs
 // allow, up to 16), one CTA per SM, each warp loops over its items.
-template <int NP, bool SPLIT>
-__global__ void __launch_bounds__(VmCfg<NP, SPLIT>::kMaxWarps * 32, 1) rzk_vm_kernel(const __grid_constant__ VmLaunch K)
+template <int NP, int MODE>
+__global__ void __launch_bounds__(VmCfg<NP, MODE>::kMaxWarps * 32, 1) rzk_vm_kernel(const __grid_constant__ VmLaunch K)
 {
+    constexpr bool SPLIT = (MODE != MODE_SEQ);      // one warp per item
     extern __shared__ __align__(16) uint32_t smem[];
-    using S = VmSmem<NP>;
+    using S = VmSmem<NP, MODE>;
     uint32_t *s_g1 = smem;
     uint32_t *s_g2 = s_g1 + S::kG1;
     uint32_t *s_key = s_g2 + S::kG2;
@@ -62,9 +64,9 @@ __global__ void __launch_bounds__(VmCfg<NP, SPLIT>::kMaxWarps * 32, 1) rzk_vm_ke
         const uint4 *g2src = reinterpret_cast<const uint4 *>(K.g2tab + (size_t)slot * (2 * kLanes * kG2Words));
         uint4 *g2dst = reinterpret_cast<uint4 *>(s_g2 + i * (2 * kLanes * kG2Words));
         for (int w = threadIdx.x; w < 2 * kLanes * kG2Words / 4; w += nthreads) g2dst[w] = g2src[w];
-        const uint4 *ksrc = reinterpret_cast<const uint4 *>(K.keytab + (size_t)slot * (kKeyPolys * 2 * kPadWords));
-        uint4 *kdst = reinterpret_cast<uint4 *>(s_key + i * (kKeyPolys * 2 * kPadWords));
-        for (int w = threadIdx.x; w < kKeyPolys * 2 * kPadWords / 4; w += nthreads) kdst[w] = ksrc[w];
+        const uint4 *ksrc = reinterpret_cast<const uint4 *>(K.keytab + (size_t)i * (S::kKP * 2 * kPadWords));
+        uint4 *kdst = reinterpret_cast<uint4 *>(s_key + i * (S::kKP * 2 * kPadWords));
+        for (int w = threadIdx.x; w < S::kKP * 2 * kPadWords / 4; w += nthreads) kdst[w] = ksrc[w];
     }
     __syncthreads();
 
@@ -73,6 +75,8 @@ __global__ void __launch_bounds__(VmCfg<NP, SPLIT>::kMaxWarps * 32, 1) rzk_vm_ke
     LaneCtx ctx;
     ctx.buf = mine;
     ctx.slot = mine + K.off_slot;
+    ctx.slot_hw[0] = s_hw + (warp * 2 + 0) * K.hw_words + K.off_slot;
+    ctx.slot_hw[1] = s_hw + (warp * 2 + 1) * K.hw_words + K.off_slot;
     ctx.acc1 = mine + K.off_acc1;
     ctx.stash = mine + K.off_stash;
     ctx.red = SPLIT ? s_hw + (warp * 2) * K.hw_words : mine;
@@ -93,7 +97,7 @@ __global__ void __launch_bounds__(VmCfg<NP, SPLIT>::kMaxWarps * 32, 1) rzk_vm_ke
         const uint32_t item = first + it * per_grid;
         ctx.active = item < K.n_items;
         ctx.item = ctx.active ? item : K.n_items - 1;
-        vm_run_item<NP, SPLIT>(K, &L, &ctx);
+        vm_run_item<NP, MODE>(K, &L, &ctx);
     }
 }
 
@@ -161,6 +165,7 @@ struct rzk_engine {
     uint32_t *d_g1tab = nullptr;
     uint32_t *d_g2tab = nullptr;
     uint32_t *d_keytab = nullptr;
+    uint32_t *d_keytab2 = nullptr;  // split-key images (lo/hi) for prime slot 0, [6][2][576]
     uint32_t *d_misc = nullptr;     // [0] range word, [1] dummy flags word
     bool has_key = false;
     uint64_t sigma = 0, cbound = 0, vbound = 0;
@@ -227,20 +232,21 @@ void set_stream(VmLaunch &K, int i, const void *base, uint32_t stride, uint32_t 
     K.st[i].base = base; K.st[i].stride = stride; K.st[i].dtype = dtype; K.st[i].div = div; K.st[i].pad_ = 0;
 }
 
-template <int NP, bool SPLIT>
+template <int NP, int MODE>
 int launch_vm(rzk_engine *e, VmLaunch &K, cudaStream_t s)
 {
     if (K.n_items == 0) return RZK_OK;
-    auto kern = rzk_vm_kernel<NP, SPLIT>;
+    constexpr bool SPLIT = (MODE != MODE_SEQ);
+    auto kern = rzk_vm_kernel<NP, MODE>;
     layout_hw(K, SPLIT);
     const size_t max_smem = 227 * 1024;
-    int warps = (int)((max_smem - VmSmem<NP>::bytes(0, 0)) / (sizeof(uint32_t) * 2 * K.hw_words));
-    if (warps > VmCfg<NP, SPLIT>::kMaxWarps) warps = VmCfg<NP, SPLIT>::kMaxWarps;
+    int warps = (int)((max_smem - VmSmem<NP, MODE>::bytes(0, 0)) / (sizeof(uint32_t) * 2 * K.hw_words));
+    if (warps > VmCfg<NP, MODE>::kMaxWarps) warps = VmCfg<NP, MODE>::kMaxWarps;
     const uint32_t per_warp = SPLIT ? 1 : 2;
     // do not launch more warps per CTA than the batch can use
     const uint32_t want = (uint32_t)((K.n_items + (uint64_t)e->num_sms * per_warp - 1) / ((uint64_t)e->num_sms * per_warp));
     if ((uint32_t)warps > want) warps = (int)(want ? want : 1);
-    const size_t smem = VmSmem<NP>::bytes(warps, K.hw_words);
+    const size_t smem = VmSmem<NP, MODE>::bytes(warps, K.hw_words);
     static bool configured[16] = {};   // per device
     if (!configured[e->device & 15]) {
         RZK_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
@@ -257,9 +263,9 @@ int launch_vm(rzk_engine *e, VmLaunch &K, cudaStream_t s)
 
 int launch_np(rzk_engine *e, int np, VmLaunch &K, cudaStream_t s)
 {
-    if (np == 1) return launch_vm<1, false>(e, K, s);
-    if (np == 2) return launch_vm<2, true>(e, K, s);
-    return launch_vm<3, false>(e, K, s);
+    if (np == 1) return launch_vm<1, MODE_SEQ>(e, K, s);
+    if (np == 2) return launch_vm<2, MODE_SPLIT>(e, K, s);
+    return launch_vm<3, MODE_SEQ>(e, K, s);
 }
 
 int check_ready(rzk_engine *e, bool need_key = true)
@@ -284,15 +290,24 @@ constexpr size_t kPolyBytes = (size_t)kN * sizeof(int32_t);
 
 // ---- phase lowering on device pointers (scratch supplied by the caller of these helpers) ----
 
-int dev_commit(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r, int32_t *c, uint32_t *flags, cudaStream_t s)
+constexpr uint32_t kSplitKeyLimit = 15;    // |r| bound of MODE_SPLITKEY: 2*512*2^15*15 < p/2
+
+// generic = true: two-prime program, exact for any int8 r.
+// generic = false: split-key program (|r| <= 15 on the transformed rows, else FLAG_RANGE).
+int dev_commit(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r, int32_t *c, uint32_t *flags, cudaStream_t s,
+               bool generic = false)
 {
     VmLaunch K; memset(&K, 0, sizeof(K));
     Prog p(&K);
-    prog_commit(p, 0, 1, 2);
+    if (generic) prog_commit(p, 0, 1, 2);
+    else prog_commit_splitkey(p, 0, 1, 2);
     p.end();
-    fill_common(e, K, 2, (uint32_t)B, 1, flags);
+    fill_common(e, K, generic ? 2 : 1, (uint32_t)B, 1, flags);
     set_stream(K, 0, x, 1, DT_I32); set_stream(K, 1, r, 3, DT_I8); set_stream(K, 2, c, 2, DT_I32);
-    return launch_np(e, 2, K, s);
+    if (generic) return launch_np(e, 2, K, s);
+    K.small_lim = kSplitKeyLimit;
+    K.keytab = e->d_keytab2;
+    return launch_vm<1, MODE_SPLITKEY>(e, K, s);
 }
 
 int dev_open_commit(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r, const int32_t *y,
@@ -570,6 +585,7 @@ int rzk_create(const rzk_params *params, int device, rzk_engine **out)
     cu(cudaMalloc(&e->d_g2tab, g2.size() * sizeof(uint32_t)), "cudaMalloc(g2)");
     if (rc == RZK_OK) cu(cudaMemcpy(e->d_g2tab, g2.data(), g2.size() * sizeof(uint32_t), cudaMemcpyHostToDevice), "cudaMemcpy(g2)");
     cu(cudaMalloc(&e->d_keytab, (size_t)kNumPrimeSlots * kKeyPolys * 2 * kPadWords * sizeof(uint32_t)), "cudaMalloc(key)");
+    cu(cudaMalloc(&e->d_keytab2, (size_t)2 * kKeyPolys * 2 * kPadWords * sizeof(uint32_t)), "cudaMalloc(key2)");
     cu(cudaMalloc(&e->d_misc, 64), "cudaMalloc(misc)");
     if (rc == RZK_OK) cu(cudaMemset(e->d_misc, 0, 64), "cudaMemset(misc)");
     for (int i = 0; i < kPipe && rc == RZK_OK; ++i) cu(cudaStreamCreateWithFlags(&e->pipe[i].stream, cudaStreamNonBlocking), "cudaStreamCreate");
@@ -591,6 +607,7 @@ void rzk_destroy(rzk_engine *e)
     if (e->d_g1tab) cudaFree(e->d_g1tab);
     if (e->d_g2tab) cudaFree(e->d_g2tab);
     if (e->d_keytab) cudaFree(e->d_keytab);
+    if (e->d_keytab2) cudaFree(e->d_keytab2);
     if (e->d_misc) cudaFree(e->d_misc);
     delete e;
 }
@@ -625,8 +642,18 @@ int rzk_set_key(rzk_engine *e, const int64_t *a1, const int64_t *a2)
             key_image(T, cen.data(), &img[((size_t)s * kKeyPolys + kk) * 2 * kPadWords]);
         }
     }
+    std::vector<uint32_t> img2((size_t)2 * kKeyPolys * 2 * kPadWords, 0);
+    for (int kk = 0; kk < kKeyPolys; ++kk) {
+        for (int i = 0; i < kN; ++i) {
+            int64_t r = polys[kk][i] % q;
+            if (r > half) r -= q; else if (r < -half) r += q;
+            cen[i] = r;
+        }
+        key_image_split(prime_tables(0), cen.data(), &img2[(size_t)kk * 4 * kPadWords]);
+    }
     RZK_CUDA(e, cudaDeviceSynchronize());
     RZK_CUDA(e, cudaMemcpy(e->d_keytab, img.data(), img.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    RZK_CUDA(e, cudaMemcpy(e->d_keytab2, img2.data(), img2.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     e->has_key = true;
     return RZK_OK;
 }
@@ -771,8 +798,13 @@ int rzk_commit_batch(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r,
     RZK_TRY(check_ready(e));
     if (any_null({x, r, c, ok})) return fail(e, RZK_ERR_INVALID, "null argument");
     std::vector<HArr> a = {{x, nullptr, kPolyBytes}, {r, nullptr, 3 * kN}, {nullptr, c, 2 * kPolyBytes}};
-    return run_chunked(e, B, a, 0, ok, [&](size_t n, void **d, char *, uint32_t *fl, cudaStream_t s) {
+    int rc = run_chunked(e, B, a, 0, ok, [&](size_t n, void **d, char *, uint32_t *fl, cudaStream_t s) {
         return dev_commit(e, n, (const int32_t *)d[0], (const int8_t *)d[1], (int32_t *)d[2], fl, s);
+    });
+    if (rc != RZK_ERR_RANGE) return rc;
+    // some |r| > 15: redo the batch with the two-prime program, which is exact for any int8 r
+    return run_chunked(e, B, a, 0, ok, [&](size_t n, void **d, char *, uint32_t *fl, cudaStream_t s) {
+        return dev_commit(e, n, (const int32_t *)d[0], (const int8_t *)d[1], (int32_t *)d[2], fl, s, true);
     });
 }
 

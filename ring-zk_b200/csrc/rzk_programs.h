@@ -48,6 +48,29 @@ inline void prog_commit(Prog &P, int sx = 0, int sr = 1, int sc = 2, bool with_n
     P.add(OP_FIN, sc, FIN_STORE, 0, 1);
 }
 
+// Same commitment for small randomness (|r| <= 15) in MODE_SPLITKEY: one prime, the key split
+// into 16-bit halves (half warp 0: lo images, half warp 1: hi images), the two forward
+// transforms shared between the half warps through their operand slots.
+inline void prog_commit_splitkey(Prog &P, int sx = 0, int sr = 1, int sc = 2, bool with_norm = true)
+{
+    if (with_norm) P.add(OP_NORM, sr, /*commit bound*/ 0, /*count*/ 3, 0);     // commit.rs:102
+    P.add(OP_SEG);
+    P.add(OP_FWD, sr, FWD_HWPOLY | FWD_CHECK_SMALL, 0, 1);    // half warp h transforms r[1 + h]
+    P.add(OP_ST, 0, ST_RAW);
+    P.add(OP_LD, 0);
+    P.add(OP_MACK, 0, 0, MAC_INIT);
+    P.add(OP_LD, 1);
+    P.add(OP_MACK, 0, 1, 0);
+    P.add(OP_MACK, 1, 2, MAC_INIT);
+    P.add(OP_INV, 0, 0);
+    P.add(OP_ADDP, sr, 0, 0, 0);
+    P.add(OP_FIN, sc, FIN_STORE, 0, 0);
+    P.add(OP_INV, 1, 1);
+    P.add(OP_ADDP, sr, 0, 0, 1);
+    P.add(OP_ADDP, sx, 0, 0, 0);
+    P.add(OP_FIN, sc, FIN_STORE, 0, 1);
+}
+
 // t = A1 . y  (open.rs:97, linear.rs:118-121, sum.rs:145-151) and optionally w = A2 . y
 // (the inner factor of u, linear.rs:124-129 / sum.rs:154-160).
 // sv = y stream (3 polys), st = t out (or -1), sw = w out (or -1)

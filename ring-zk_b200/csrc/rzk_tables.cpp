@@ -192,4 +192,16 @@ void key_image(const PrimeTables &T, const int64_t *poly, uint32_t *out)
     }
 }
 
+void key_image_split(const PrimeTables &T, const int64_t *poly, uint32_t *out)
+{
+    int64_t lo[kN], hi[kN];
+    for (int i = 0; i < kN; ++i) {
+        int64_t l = ((poly[i] + 32768) & 0xFFFF) - 32768;     // centred low 16 bits
+        lo[i] = l;
+        hi[i] = (poly[i] - l) / 65536;
+    }
+    key_image(T, lo, out);
+    key_image(T, hi, out + 2 * kPadWords);
+}
+
 }  // namespace rzk

@@ -32,6 +32,10 @@ CrtC make_crt_consts(const int *slots, int np, uint64_t q);
 // lane layout read by OP_MACK.  out: [2][kPadWords] (w row then w' row).
 void key_image(const PrimeTables &T, const int64_t *poly_centered, uint32_t *out);
 
+// Split-key images (MODE_SPLITKEY): poly = lo + 2^16 * hi with lo in [-2^15, 2^15); writes the image of
+// lo to out[0 .. 2*kPadWords) and of hi to out[2*kPadWords .. 4*kPadWords).
+void key_image_split(const PrimeTables &T, const int64_t *poly_centered, uint32_t *out);
+
 inline int pad_index(int i) { return i + ((i >> 5) << 2); }
 
 }  // namespace rzk

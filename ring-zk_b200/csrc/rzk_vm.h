@@ -38,7 +38,8 @@ enum OpCode : uint8_t {
     OP_FWD,      // cur = NTT_p(stream a, poly off [+ it*step]);  b: FWD_* flags
     OP_MACK,     // acc[a] (+)= key[b] (.) cur            c: MAC_* flags
     OP_MACV,     // acc[a] (+)= slot (.) cur (Montgomery)  c: MAC_* flags
-    OP_ST,       // slot = cur  (cur must come from a FWD_SCALED transform)
+    OP_ST,       // slot = cur  (b: ST_RAW keeps lazy values; default reduces to [0,p) for OP_MACV)
+    OP_LD,       // cur = operand slot of half warp a (warp-per-item modes)
     OP_INV,      // inverse NTT of acc[a]; stash b; on the last prime: CRT -> V
     OP_ADDP,     // (last prime only) V += +-stream a poly off      c: MAC_NEG
     OP_FIN,      // (last prime only) res = reduce_q(V);  b: FIN_* flags (store to stream a / compare with 0)
@@ -47,7 +48,8 @@ enum OpCode : uint8_t {
     OP_ENDLOOP,
 };
 
-enum : uint8_t { FWD_SCALED = 1, FWD_CHECK_SMALL = 2 };
+enum : uint8_t { FWD_SCALED = 1, FWD_CHECK_SMALL = 2, FWD_HWPOLY = 4 };   // HWPOLY: half warp h reads poly off + h
+enum : uint8_t { ST_RAW = 1 };
 enum : uint8_t { MAC_INIT = 1, MAC_NEG = 2 };
 enum : uint8_t { FIN_STORE = 1, FIN_CMPZ = 2 };
 enum : uint8_t { DT_I32 = 0, DT_I8 = 1 };
@@ -123,7 +125,7 @@ inline ProgNeeds scan_needs(const Op *ops)
     ProgNeeds n;
     for (int i = 0; i < kMaxOps && ops[i].code != OP_END; ++i) {
         const Op &o = ops[i];
-        if (o.code == OP_ST || o.code == OP_MACV) n.slot = true;
+        if (o.code == OP_ST || o.code == OP_MACV || o.code == OP_LD) n.slot = true;
         if ((o.code == OP_MACK || o.code == OP_MACV || o.code == OP_INV) && o.a == 1) n.acc1 = true;
         if (o.code == OP_INV && (int)o.b + 1 > n.nstash) n.nstash = (int)o.b + 1;
     }

@@ -7,12 +7,18 @@
 //     arithmetic, shared-memory layouts and lane exchanges are checked against the CPU oracle
 //     without a GPU; it is test infrastructure, never a product fallback.
 //
-// Execution modes (template parameter SPLIT):
-//   SPLIT (np == 2): one warp owns one batch item; half warp h works modulo prime h.  After the
+// Execution modes (template parameter MODE):
+//   MODE_SEQ (np == 1 or 3): one half warp owns one item and runs each segment once per prime; the
+//       residues of the earlier primes wait in a lane-private shared-memory stash.
+//   MODE_SPLIT (np == 2): one warp owns one batch item; half warp h works modulo prime h.  After the
 //       inverse transforms the two half warps swap half of their residues with warp shuffles, so
 //       every lane recombines 16 coefficients (Garner CRT) -- no residue ever leaves registers.
-//   SEQ (np == 1 or 3): one half warp owns one item and runs each segment once per prime; the
-//       residues of the earlier primes wait in a lane-private shared-memory stash.
+//   MODE_SPLITKEY (np == 1): one warp owns one item whose small operands (|r| <= 15) meet the key.
+//       The key coefficients are split a = a_lo + 2^16 a_hi (|a_lo|, |a_hi| <= 2^15), so each partial
+//       product stays below 2^29 and ONE prime is exact.  Half warp 0 accumulates the lo images,
+//       half warp 1 the hi images; the forward transforms are shared through shared memory (each
+//       half warp transforms one operand) and the result is lo + 2^16 hi.  6 transforms per
+//       commitment instead of 8, and no Garner step.
 //
 // Layouts (N = 512, 16 lanes per polynomial, 32 coefficients per lane in registers):
 //   G1 (strided):    lane t holds coefficients i = t + 16*m,  m = 0..31   (stages 0..4: bits 8..4 are lane-local)
@@ -49,6 +55,8 @@ struct uint2 { uint32_t x, y; };
 
 namespace rzk {
 
+enum { MODE_SEQ = 0, MODE_SPLIT = 1, MODE_SPLITKEY = 2 };
+
 struct Lane {
     uint32_t cur[kElems];
     uint32_t acc0[kElems];   // accumulator 0 lives in registers; accumulator 1 in the lane-private smem slot ctx.acc1
@@ -61,6 +69,7 @@ struct Lane {
 struct LaneCtx {
     uint32_t *buf;         // [kBufWords]  transpose buffer of this half warp
     uint32_t *slot;        // [kSlotWords] operand slot of OP_ST / OP_MACV
+    uint32_t *slot_hw[2];  // the operand slots of both half warps of this warp (OP_LD)
     uint32_t *acc1;        // [kSlotWords] accumulator 1 (lane-private layout)
     uint32_t *stash;       // SEQ: [nstash][np-1][kSlotWords] residues of earlier primes
     uint32_t *red;         // reduction scratch shared by the lanes that own one item
@@ -173,7 +182,8 @@ RZK_VM void op_fwd(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const Op
     RZK_EACH_LANE {
         RZK_LANE;
         const PrimeC &pc = L.pc;
-        const uint64_t poly = stream_poly(st, ctx.item, (uint32_t)op.off + (uint32_t)it * op.step);
+        const uint64_t poly = stream_poly(st, ctx.item, (uint32_t)op.off + (uint32_t)it * op.step +
+                                                            ((op.b & FWD_HWPOLY) ? (uint32_t)ctx.hw : 0u));
         int32_t v[kElems];
         if (st.dtype == DT_I8) {
             const int8_t *src = reinterpret_cast<const int8_t *>(st.base) + poly * kN;
@@ -306,39 +316,62 @@ RZK_VM void mac_var_smem(uint32_t *acc1, const uint32_t (&cur)[kElems], const ui
     }
 }
 
-RZK_VM void op_st(Lane *lanes, const LaneCtx *ctxs)
+RZK_VM void op_st(Lane *lanes, const LaneCtx *ctxs, const Op &op)
 {
     RZK_EACH_LANE {
         RZK_LANE;
         const PrimeC &pc = L.pc;
         uint4 *s4 = reinterpret_cast<uint4 *>(ctx.slot);
-        RZK_UNROLL
-        for (int j = 0; j < 8; ++j) {
-            uint4 q;
-            q.x = csub(csub(L.cur[4 * j + 0], pc.p2), pc.p);
-            q.y = csub(csub(L.cur[4 * j + 1], pc.p2), pc.p);
-            q.z = csub(csub(L.cur[4 * j + 2], pc.p2), pc.p);
-            q.w = csub(csub(L.cur[4 * j + 3], pc.p2), pc.p);
-            s4[j * kLanes + t] = q;
+        if (op.b & ST_RAW) {            // operand of a Shoup product with the key: any 32-bit value is valid
+            RZK_UNROLL
+            for (int j = 0; j < 8; ++j) {
+                uint4 q;
+                q.x = L.cur[4 * j + 0]; q.y = L.cur[4 * j + 1]; q.z = L.cur[4 * j + 2]; q.w = L.cur[4 * j + 3];
+                s4[j * kLanes + t] = q;
+            }
+        } else {                        // operand of a Montgomery product: fully reduced
+            RZK_UNROLL
+            for (int j = 0; j < 8; ++j) {
+                uint4 q;
+                q.x = csub(csub(L.cur[4 * j + 0], pc.p2), pc.p);
+                q.y = csub(csub(L.cur[4 * j + 1], pc.p2), pc.p);
+                q.z = csub(csub(L.cur[4 * j + 2], pc.p2), pc.p);
+                q.w = csub(csub(L.cur[4 * j + 3], pc.p2), pc.p);
+                s4[j * kLanes + t] = q;
+            }
         }
     }
-    // lane-private: no cross-lane hazard, no sync needed
+    RZK_SYNC();     // OP_LD may read the other half warp's slot
+}
+
+// cur = operand slot of half warp op.a (same lane, same positions)
+RZK_VM void op_ld(Lane *lanes, const LaneCtx *ctxs, const Op &op)
+{
+    RZK_EACH_LANE {
+        RZK_LANE;
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(ctx.slot_hw[op.a & 1]);
+        RZK_UNROLL
+        for (int j = 0; j < 8; ++j) {
+            const uint4 q = s4[j * kLanes + t];
+            L.cur[4 * j + 0] = q.x; L.cur[4 * j + 1] = q.y; L.cur[4 * j + 2] = q.z; L.cur[4 * j + 3] = q.w;
+        }
+    }
 }
 
 // ---------------------------------------------------------------- epilogue (last prime only)
 
-// Number of coefficients a lane finishes: SPLIT lanes share an item between two half warps.
-template <bool SPLIT>
-struct Epi { static constexpr int kCount = SPLIT ? 16 : 32; };
+// Number of coefficients a lane finishes: in the warp-per-item modes two half warps share an item.
+template <int MODE>
+struct Epi { static constexpr int kCount = (MODE != MODE_SEQ) ? 16 : 32; };
 
 // coefficient index m (in the G1 layout, i = t + 16*m) of epilogue element j
-template <bool SPLIT>
-RZK_VM int epi_m(const LaneCtx &ctx, int j) { return SPLIT ? (16 * ctx.hw + j) : j; }
+template <int MODE>
+RZK_VM int epi_m(const LaneCtx &ctx, int j) { return (MODE != MODE_SEQ) ? (16 * ctx.hw + j) : j; }
 
-template <bool SPLIT>
-RZK_VM void op_addp(const VmLaunch &K, const LaneCtx *ctxs, int64_t (&V)[RZK_NL][Epi<SPLIT>::kCount], const Op &op, int it)
+template <int MODE>
+RZK_VM void op_addp(const VmLaunch &K, const LaneCtx *ctxs, int64_t (&V)[RZK_NL][Epi<MODE>::kCount], const Op &op, int it)
 {
-    constexpr int CNT = Epi<SPLIT>::kCount;
+    constexpr int CNT = Epi<MODE>::kCount;
     const Stream st = K.st[op.a];
     const bool neg = op.c & MAC_NEG;
     RZK_EACH_LANE {
@@ -349,21 +382,21 @@ RZK_VM void op_addp(const VmLaunch &K, const LaneCtx *ctxs, int64_t (&V)[RZK_NL]
         if (st.dtype == DT_I8) {
             const int8_t *src = reinterpret_cast<const int8_t *>(st.base) + poly * kN;
             RZK_UNROLL
-            for (int j = 0; j < CNT; ++j) v[j] = src[t + kLanes * epi_m<SPLIT>(ctx, j)];
+            for (int j = 0; j < CNT; ++j) v[j] = src[t + kLanes * epi_m<MODE>(ctx, j)];
         } else {
             const int32_t *src = reinterpret_cast<const int32_t *>(st.base) + poly * kN;
             RZK_UNROLL
-            for (int j = 0; j < CNT; ++j) v[j] = canon_q(src[t + kLanes * epi_m<SPLIT>(ctx, j)], K.q);
+            for (int j = 0; j < CNT; ++j) v[j] = canon_q(src[t + kLanes * epi_m<MODE>(ctx, j)], K.q);
         }
         RZK_UNROLL
         for (int j = 0; j < CNT; ++j) V[li_][j] += neg ? -(int64_t)v[j] : (int64_t)v[j];
     }
 }
 
-template <bool SPLIT>
-RZK_VM void op_fin(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int64_t (&V)[RZK_NL][Epi<SPLIT>::kCount], const Op &op, int it)
+template <int MODE>
+RZK_VM void op_fin(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int64_t (&V)[RZK_NL][Epi<MODE>::kCount], const Op &op, int it)
 {
-    constexpr int CNT = Epi<SPLIT>::kCount;
+    constexpr int CNT = Epi<MODE>::kCount;
     const Stream st = K.st[op.a];
     RZK_EACH_LANE {
         RZK_LANE;
@@ -380,7 +413,7 @@ RZK_VM void op_fin(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int64_t 
         if ((op.b & FIN_STORE) && ctx.active) {
             int32_t *dst = reinterpret_cast<int32_t *>(const_cast<void *>(st.base)) + poly * kN;
             RZK_UNROLL
-            for (int j = 0; j < CNT; ++j) dst[t + kLanes * epi_m<SPLIT>(ctx, j)] = res[j];
+            for (int j = 0; j < CNT; ++j) dst[t + kLanes * epi_m<MODE>(ctx, j)] = res[j];
         }
     }
 }
@@ -423,12 +456,12 @@ RZK_VM int64_t crt_combine(const VmLaunch &K, const uint32_t (&r)[kMaxPrimes])
 // Inverse transform of acc[a].  On the last prime the residues of all primes are combined and
 // the epilogue ops that follow (OP_ADDP*, OP_FIN) are executed here, so that the 64-bit
 // values live only inside this function.  Returns the index of the first op after the epilogue.
-template <int NP, bool SPLIT>
+template <int NP, int MODE>
 RZK_VM int op_inv(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int q, int it, int prime_iter)
 {
-    constexpr int CNT = Epi<SPLIT>::kCount;
+    constexpr int CNT = Epi<MODE>::kCount;
     const Op op = K.ops[q];
-    const bool last = SPLIT || (prime_iter == NP - 1);
+    const bool last = (MODE != MODE_SEQ) || (prime_iter == NP - 1);
     int64_t V[RZK_NL][CNT];
     RZK_EACH_LANE {
         RZK_LANE;
@@ -467,10 +500,19 @@ RZK_VM int op_inv(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int q, in
         for (int m = 0; m < kElems; ++m) L.cur[m] = csub(L.cur[m], pc.p);     // [0,2p) -> [0,p)
     }
     RZK_SYNC();
-    if (SPLIT) {
-        // half warp 0 holds residues mod p0, half warp 1 mod p1, both for all 512 coefficients.
-        // Lane (h, t) finishes coefficients m in [16h, 16h+16): it keeps its own residue of those
-        // and receives the partner's; it sends its residues of the other half.
+    if (MODE != MODE_SEQ) {
+        // MODE_SPLIT: half warp 0 holds residues mod p0, half warp 1 mod p1, both for all 512
+        // coefficients.  MODE_SPLITKEY: half warp 0 holds the lo part, half warp 1 the hi part.
+        // Lane (h, t) finishes coefficients m in [16h, 16h+16): it keeps its own value of those
+        // and receives the partner's; it sends its values of the other half.
+        if (MODE == MODE_SPLITKEY) {
+            RZK_EACH_LANE {
+                RZK_LANE;
+                const uint32_t p = L.pc.p, half = L.pc.half;
+                RZK_UNROLL
+                for (int m = 0; m < kElems; ++m) L.cur[m] = L.cur[m] > half ? L.cur[m] - p : L.cur[m];   // centred lift
+            }
+        }
         uint32_t recv[RZK_NL][16];
 #if defined(__CUDA_ARCH__)
         RZK_UNROLL
@@ -490,10 +532,14 @@ RZK_VM int op_inv(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int q, in
             RZK_UNROLL
             for (int j = 0; j < 16; ++j) {
                 const uint32_t own = ctx.hw ? L.cur[16 + j] : L.cur[j];
-                uint32_t r[kMaxPrimes] = {0, 0, 0};
-                r[0] = ctx.hw ? recv[li_][j] : own;
-                r[1] = ctx.hw ? own : recv[li_][j];
-                V[li_][j % CNT] = crt_combine<2>(K, r);
+                const uint32_t v0 = ctx.hw ? recv[li_][j] : own;      // half warp 0's value
+                const uint32_t v1 = ctx.hw ? own : recv[li_][j];      // half warp 1's value
+                if (MODE == MODE_SPLITKEY) {
+                    V[li_][j % CNT] = (int64_t)(int32_t)v0 + (int64_t)(int32_t)v1 * 65536;
+                } else {
+                    uint32_t r[kMaxPrimes] = {v0, v1, 0};
+                    V[li_][j % CNT] = crt_combine<2>(K, r);
+                }
             }
         }
     } else {
@@ -533,19 +579,19 @@ RZK_VM int op_inv(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int q, in
     RZK_NOUNROLL
     for (;; ++q) {
         const Op e = K.ops[q];
-        if (e.code == OP_ADDP) { if (last) op_addp<SPLIT>(K, ctxs, V, e, it); }
-        else if (e.code == OP_FIN) { if (last) op_fin<SPLIT>(K, lanes, ctxs, V, e, it); }
+        if (e.code == OP_ADDP) { if (last) op_addp<MODE>(K, ctxs, V, e, it); }
+        else if (e.code == OP_FIN) { if (last) op_fin<MODE>(K, lanes, ctxs, V, e, it); }
         else break;
     }
     return q;
 }
 
 // params.rs:102-118 via polynomial.rs:60-73: floor(sqrt(sum c^2)) <= bound  <=>  sum c^2 < (bound+1)^2
-template <bool SPLIT>
+template <int MODE>
 RZK_VM void op_norm(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const Op &op)
 {
-    constexpr int CNT = Epi<SPLIT>::kCount;
-    constexpr int RED_N = SPLIT ? 32 : 16;
+    constexpr int CNT = Epi<MODE>::kCount;
+    constexpr int RED_N = (MODE != MODE_SEQ) ? 32 : 16;
     const Stream st = K.st[op.a];
     const uint32_t abs_lim = K.norm_abs_lim[op.b];
     const uint64_t sq_lim = K.norm_sq_lim[op.b];
@@ -560,14 +606,14 @@ RZK_VM void op_norm(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const O
                 const int8_t *src = reinterpret_cast<const int8_t *>(st.base) + poly * kN;
                 RZK_UNROLL
                 for (int j = 0; j < CNT; ++j) {
-                    const int32_t v = src[t + kLanes * epi_m<SPLIT>(ctx, j)];
+                    const int32_t v = src[t + kLanes * epi_m<MODE>(ctx, j)];
                     s += (uint64_t)(uint32_t)(v * v);
                 }
             } else {
                 const int32_t *src = reinterpret_cast<const int32_t *>(st.base) + poly * kN;
                 RZK_UNROLL
                 for (int j = 0; j < CNT; ++j) {
-                    const int32_t v = canon_q(src[t + kLanes * epi_m<SPLIT>(ctx, j)], K.q);
+                    const int32_t v = canon_q(src[t + kLanes * epi_m<MODE>(ctx, j)], K.q);
                     const uint32_t av = (uint32_t)(v < 0 ? -v : v);
                     const bool big = av > abs_lim;
                     bad |= big ? 1u : 0u;
@@ -593,17 +639,19 @@ RZK_VM void op_norm(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const O
 // ---------------------------------------------------------------- interpreter
 
 // Runs the whole program for the item(s) owned by this warp.
-template <int NP, bool SPLIT>
+template <int NP, int MODE>
 RZK_VM void vm_run_item(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs)
 {
-    static_assert(!SPLIT || NP == 2, "SPLIT mode maps the two half warps to two primes");
-    constexpr int RED_N = SPLIT ? 32 : 16;
-    constexpr int PRIME_ITERS = SPLIT ? 1 : NP;
+    static_assert(MODE != MODE_SPLIT || NP == 2, "MODE_SPLIT maps the two half warps to two primes");
+    static_assert(MODE != MODE_SPLITKEY || NP == 1, "MODE_SPLITKEY works modulo one prime");
+    constexpr int RED_N = (MODE != MODE_SEQ) ? 32 : 16;
+    constexpr int PRIME_ITERS = (MODE != MODE_SEQ) ? 1 : NP;
+    constexpr int KP = (MODE == MODE_SPLITKEY) ? 2 * kKeyPolys : kKeyPolys;     // key images per prime
     RZK_EACH_LANE { RZK_LANE; L.fail = 0; L.rerr = 0; }
     int pc = 0;
     RZK_NOUNROLL
     while (K.ops[pc].code == OP_NORM) {
-        op_norm<SPLIT>(K, lanes, ctxs, K.ops[pc]);
+        op_norm<MODE>(K, lanes, ctxs, K.ops[pc]);
         ++pc;
     }
     RZK_NOUNROLL
@@ -614,7 +662,7 @@ RZK_VM void vm_run_item(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs)
         for (int prime_iter = 0; prime_iter < PRIME_ITERS; ++prime_iter) {
             RZK_EACH_LANE {
                 RZK_LANE;
-                L.pi = SPLIT ? ctx.hw : prime_iter;
+                L.pi = (MODE == MODE_SPLIT) ? ctx.hw : (MODE == MODE_SPLITKEY ? 0 : prime_iter);
                 L.pc = K.pc[L.pi];
             }
             int q = seg_begin, loop_start = 0, loop_cnt = 0, it = 0;
@@ -629,7 +677,9 @@ RZK_VM void vm_run_item(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs)
                 case OP_MACK:
                     RZK_EACH_LANE {
                         RZK_LANE;
-                        const uint32_t *krow = ctx.key + ((L.pi * kKeyPolys + (int)op.b) * 2) * kPadWords;
+                        // MODE_SPLITKEY: half warp h uses the lo (h = 0) / hi (h = 1) image of key poly b
+                        const int kidx = (MODE == MODE_SPLITKEY) ? (2 * (int)op.b + ctx.hw) : (int)op.b;
+                        const uint32_t *krow = ctx.key + ((L.pi * KP + kidx) * 2) * kPadWords;
                         if (op.a == 0) mac_key(L.acc0, L.cur, krow, t, op.c, L.pc.p, L.pc.p2);
                         else mac_key_smem(ctx.acc1, L.cur, krow, t, op.c, L.pc.p, L.pc.p2);
                     }
@@ -642,10 +692,13 @@ RZK_VM void vm_run_item(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs)
                     }
                     break;
                 case OP_ST:
-                    op_st(lanes, ctxs);
+                    op_st(lanes, ctxs, op);
+                    break;
+                case OP_LD:
+                    op_ld(lanes, ctxs, op);
                     break;
                 case OP_INV:
-                    q = op_inv<NP, SPLIT>(K, lanes, ctxs, q, it, prime_iter);
+                    q = op_inv<NP, MODE>(K, lanes, ctxs, q, it, prime_iter);
                     continue;
                 case OP_LOOP:
                     loop_start = q + 1; loop_cnt = op.off; it = 0;

@@ -38,25 +38,29 @@ static int32_t rnd_gauss(double sigma)
 
 struct Emu {
     int np;
+    int mode;
     int slots[3];
     std::vector<uint32_t> g1, g2, key, flags;
     VmLaunch K;
     std::vector<uint32_t> region;     // two half-warp regions
 
-    Emu(int np_, const int *sl, const int64_t *keypolys /*[3][512]*/, size_t nflags)
+    Emu(int np_, const int *sl, const int64_t *keypolys /*[3][512]*/, size_t nflags, int mode_ = -1)
     {
         np = np_;
+        mode = mode_ >= 0 ? mode_ : (np == 2 ? MODE_SPLIT : MODE_SEQ);
         memset(&K, 0, sizeof(K));
         g1.assign((size_t)np * 2 * kG1Words, 0);
         g2.resize((size_t)np * 2 * kLanes * kG2Words);
-        key.resize((size_t)np * kKeyPolys * 2 * kPadWords);
+        key.resize((size_t)np * kKeyPolys * 2 * kPadWords * (mode == MODE_SPLITKEY ? 2 : 1));
         for (int i = 0; i < np; ++i) {
             slots[i] = sl[i];
             const PrimeTables &T = prime_tables(sl[i]);
             for (int d = 0; d < 2; ++d) memcpy(&g1[((size_t)i * 2 + d) * kG1Words], T.g1[d], sizeof(T.g1[d]));
             memcpy(&g2[(size_t)i * 2 * kLanes * kG2Words], T.g2, sizeof(T.g2));
-            for (int k = 0; k < kKeyPolys; ++k)
-                key_image(T, keypolys + (size_t)k * kN, &key[((size_t)i * kKeyPolys + k) * 2 * kPadWords]);
+            for (int k = 0; k < kKeyPolys; ++k) {
+                if (mode == MODE_SPLITKEY) key_image_split(T, keypolys + (size_t)k * kN, &key[(size_t)k * 4 * kPadWords]);
+                else key_image(T, keypolys + (size_t)k * kN, &key[((size_t)i * kKeyPolys + k) * 2 * kPadWords]);
+            }
             K.pc[i] = make_prime_consts(sl[i]);
         }
         K.crt = make_crt_consts(sl, np, (uint64_t)Q);
@@ -82,7 +86,7 @@ struct Emu {
     void run(uint32_t n_items)
     {
         K.n_items = n_items;
-        const bool split = (np == 2);
+        const bool split = (mode != MODE_SEQ);
         layout_hw(K, split);
         if (K.hw_words % 32 != 16) { printf("FAIL: hw_words %u not 16 mod 32\n", K.hw_words); exit(1); }
         region.assign((size_t)2 * K.hw_words, 0xDEADBEEFu);
@@ -94,6 +98,7 @@ struct Emu {
                 LaneCtx &c = ctxs[li];
                 const int hw = li >> 4;
                 uint32_t *mine = region.data() + (size_t)hw * K.hw_words;
+                c.slot_hw[0] = region.data() + K.off_slot; c.slot_hw[1] = region.data() + K.hw_words + K.off_slot;
                 c.buf = mine; c.slot = mine + K.off_slot; c.acc1 = mine + K.off_acc1; c.stash = mine + K.off_stash;
                 c.red = split ? region.data() : mine;
                 c.ridx = split ? li : (li & 15);
@@ -103,9 +108,10 @@ struct Emu {
                 c.active = item < n_items;
                 c.item = c.active ? item : n_items - 1;
             }
-            if (np == 1) vm_run_item<1, false>(K, lanes, ctxs);
-            else if (np == 2) vm_run_item<2, true>(K, lanes, ctxs);
-            else vm_run_item<3, false>(K, lanes, ctxs);
+            if (mode == MODE_SPLITKEY) vm_run_item<1, MODE_SPLITKEY>(K, lanes, ctxs);
+            else if (np == 1) vm_run_item<1, MODE_SEQ>(K, lanes, ctxs);
+            else if (np == 2) vm_run_item<2, MODE_SPLIT>(K, lanes, ctxs);
+            else vm_run_item<3, MODE_SEQ>(K, lanes, ctxs);
         }
     }
 };
@@ -205,6 +211,37 @@ int main(int argc, char **argv)
         rzko_commit_batch(&P, a1.data(), a2.data(), B, x64.data(), rb64.data(), c2.data(), ok2.data(), 1);
         CHECK(same(c_e, c2), "commit with large r mismatch");
         for (int b = 0; b < B; ++b) CHECK(ok2[b] == 0, "oracle ok");
+    }
+
+    // ---------------- split-key commit (1 prime, key halves) ----------------
+    {
+        const int L1[1] = {0};
+        std::vector<int8_t> r15(r);
+        for (size_t i = 0; i < r15.size(); ++i) r15[i] = (int8_t)((int)(rnd() % 31) - 15);      // |r| <= 15: worst case of the bound
+        for (size_t i = N; i < 3 * N; ++i) r15[i] = (i & 1) ? 15 : -15;
+        std::vector<int32_t> xw(x);
+        Emu E(1, L1, keyp.data(), B, MODE_SPLITKEY);
+        Prog pr(&E.K);
+        prog_commit_splitkey(pr, 0, 1, 2);
+        pr.end();
+        E.K.small_lim = 15;
+        E.stream(0, xw.data(), 1, DT_I32); E.stream(1, r15.data(), 3, DT_I8); E.stream(2, c_e.data(), 2, DT_I32);
+        E.run(B);
+        auto r15_64 = widen8(r15);
+        std::vector<int64_t> c2(B * 2 * N);
+        std::vector<uint8_t> ok2(B);
+        rzko_commit_batch(&P, a1.data(), a2.data(), B, x64.data(), r15_64.data(), c2.data(), ok2.data(), 1);
+        CHECK(same(c_e, c2), "split-key commit mismatch");
+        for (int b = 0; b < B; ++b) CHECK(E.flags[b] == 0, "split-key flags[%d]=%u", b, E.flags[b]);
+        // |r| = 16 on a transformed row must raise the range flag; on row 0 it must not
+        r15[2 * N + 3] = 16;
+        r15[(size_t)3 * N + 5] = 100;      // item 1, row 0 (never transformed)
+        std::vector<uint32_t> f0(B, 0);
+        E.flags.assign(B, 0); E.K.flags = E.flags.data();
+        E.run(B);
+        CHECK(E.flags[0] == FLAG_RANGE, "split-key range flag item 0: %u", E.flags[0]);
+        if (B > 1) CHECK(E.flags[1] == 0, "split-key range flag item 1: %u", E.flags[1]);
+        printf("split-key commit ok, ops=%d\n", pr.n);
     }
 
     // ---------------- respond (1 prime) ----------------
