@@ -91,19 +91,19 @@ RZK_HD int32_t canon_q(int32_t v, uint32_t q)
     return (int32_t)u;
 }
 
-// Signed 64-bit value w with -kq <= w < 2^64 - kq  ->  centred residue mod q.
-// bar = floor(2^64 / q), kq = q * 2^29 (offset that makes the operand non-negative;
-// Barrett with floor(2^64/q) under-estimates the quotient by at most 1 for any u64).
-RZK_HD int32_t reduce_q_centered(int64_t w, uint32_t q, uint64_t bar, uint64_t kq)
+// Signed 64-bit value w with |w| < 2^60  ->  centred residue mod q in [-(q-1)/2, (q-1)/2].
+//   kqh = q * 2^29 + (q-1)/2   (offset: makes the operand positive and pre-centres it)
+//   m30 = floor(2^62 / q)      (32-bit Barrett constant applied to the top 32 bits of the operand)
+// The quotient estimate from the top bits is short by at most 1, so one conditional subtraction
+// finishes the reduction; subtracting (q-1)/2 then yields the centred representative.
+RZK_HD int32_t reduce_q_centered(int64_t w, uint32_t q, uint32_t m30, uint64_t kqh)
 {
-    uint64_t wp = (uint64_t)w + kq;                 // in (0, 2^61.6)
-    uint64_t qh = mulhi64(wp, bar);                 // floor(wp/q) or one less
-    uint64_t rem = wp - qh * (uint64_t)q;           // [0, 2q)
+    const uint64_t wp = (uint64_t)w + kqh;                      // (0, 2^61.7)
+    const uint32_t x = (uint32_t)(wp >> 30);
+    const uint32_t qh = mulhi32(x, m30);                        // floor(wp/q) or one less
+    uint64_t rem = wp - (uint64_t)qh * (uint64_t)q;             // [0, 2q)
     if (rem >= (uint64_t)q) rem -= q;
-    const uint64_t half = (uint64_t)((q - 1u) >> 1);
-    int64_t r = (int64_t)rem;
-    if (rem > half) r -= (int64_t)q;
-    return (int32_t)r;
+    return (int32_t)((uint32_t)rem - ((q - 1u) >> 1));
 }
 
 }  // namespace rzk

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -97,6 +98,18 @@ __global__ void __launch_bounds__(VmCfg<NP, MODE>::kMaxWarps * 32, 1) rzk_vm_ker
         const uint32_t item = first + it * per_grid;
         ctx.active = item < K.n_items;
         ctx.item = ctx.active ? item : K.n_items - 1;
+        // prefetch the input rows of the item this warp handles next into L2
+        const uint32_t next = item + per_grid;
+        if (next < K.n_items) {
+            for (uint32_t k = 0; k < K.n_prefetch; ++k) {
+                const Stream st = K.st[K.prefetch[k]];
+                const uint32_t esz = (st.dtype == DT_I8) ? 1u : 4u;
+                const uint32_t bytes = st.stride * kN * esz;
+                const char *base = reinterpret_cast<const char *>(st.base) + (size_t)next * bytes;
+                for (uint32_t o = (uint32_t)ctx.ridx * 128u; o < bytes; o += (SPLIT ? 32u : 16u) * 128u)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + o));
+            }
+        }
         vm_run_item<NP, MODE>(K, &L, &ctx);
     }
 }
@@ -174,6 +187,7 @@ struct rzk_engine {
     char *scratch = nullptr;        // scratch of the `_dev` entry points
     size_t scratch_cap = 0;
     uint64_t launches = 0;
+    uint32_t cta_sync = 1;          // keep the warps of a CTA in step (instruction-cache locality); RZK_CTA_SYNC=0 disables
 };
 
 namespace {
@@ -213,8 +227,8 @@ void fill_common(const rzk_engine *e, VmLaunch &K, int np, uint32_t n_items, uin
     for (int i = 0; i < np; ++i) K.pc[i] = make_prime_consts(slots[i]);
     K.crt = make_crt_consts(slots, np, q);
     K.q = (uint32_t)q;
-    K.bar = (uint64_t)((((unsigned __int128)1) << 64) / q);
-    K.kq = q << 29;
+    K.kqh = (q << 29) + (q - 1) / 2;
+    K.m30 = (uint32_t)((1ull << 62) / q);
     K.norm_abs_lim[0] = (uint32_t)e->cbound; K.norm_sq_lim[0] = (e->cbound + 1) * (e->cbound + 1) - 1;
     K.norm_abs_lim[1] = (uint32_t)e->vbound; K.norm_sq_lim[1] = (e->vbound + 1) * (e->vbound + 1) - 1;
     K.small_lim = e->small_lim;
@@ -239,6 +253,8 @@ int launch_vm(rzk_engine *e, VmLaunch &K, cudaStream_t s)
     constexpr bool SPLIT = (MODE != MODE_SEQ);
     auto kern = rzk_vm_kernel<NP, MODE>;
     layout_hw(K, SPLIT);
+    list_prefetch(K);
+    K.cta_sync = e->cta_sync;
     const size_t max_smem = 227 * 1024;
     int warps = (int)((max_smem - VmSmem<NP, MODE>::bytes(0, 0)) / (sizeof(uint32_t) * 2 * K.hw_words));
     if (warps > VmCfg<NP, MODE>::kMaxWarps) warps = VmCfg<NP, MODE>::kMaxWarps;
@@ -552,6 +568,7 @@ int rzk_create(const rzk_params *params, int device, rzk_engine **out)
     rzk_engine *e = new rzk_engine();
     e->P = P;
     e->device = device;
+    if (const char *cs = getenv("RZK_CTA_SYNC")) e->cta_sync = (uint32_t)atoi(cs);
     Guard g(device);
     cudaDeviceProp prop;
     ce = cudaGetDeviceProperties(&prop, device);

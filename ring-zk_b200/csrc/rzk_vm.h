@@ -95,8 +95,8 @@ struct VmLaunch {
     Stream st[kMaxStreams];
     PrimeC pc[kMaxPrimes];
     CrtC crt;
-    uint64_t bar;              // floor(2^64 / q)
-    uint64_t kq;               // q * 2^29
+    uint64_t kqh;              // q * 2^29 + (q-1)/2   (reduce_q_centered offset)
+    uint64_t pad64_;
     uint64_t norm_sq_lim[2];   // (bound+1)^2 - 1 for [0]=commit, [1]=verify constraint
     uint32_t norm_abs_lim[2];  // bound
     uint32_t q;
@@ -104,7 +104,7 @@ struct VmLaunch {
     uint32_t n_items;
     uint32_t flag_div;         // flags index = item / flag_div
     uint32_t np;               // primes in this launch
-    uint32_t pad_;
+    uint32_t m30;              // floor(2^62 / q)         (reduce_q_centered Barrett constant)
     uint32_t *flags;           // device, one word per item group
     const uint32_t *g1tab;     // device, [prime slot][dir][kG1Words]
     const uint32_t *g2tab;     // device, [prime slot][dir][16][60]
@@ -112,6 +112,10 @@ struct VmLaunch {
     // shared-memory layout of one half-warp region (words); sized from what the program uses
     uint32_t hw_words;         // == 16 (mod 32): the two half warps of a warp sit 16 banks apart
     uint32_t off_slot, off_acc1, off_stash;
+    // input streams whose next-item rows are prefetched into L2 while the current item is computed
+    uint32_t n_prefetch;
+    uint8_t prefetch[8];
+    uint32_t cta_sync;         // experiment: keep the warps of a CTA in step (instruction-cache locality)
 };
 
 // What a program needs per half warp (decides how many warps fit in shared memory).
@@ -130,6 +134,20 @@ inline ProgNeeds scan_needs(const Op *ops)
         if (o.code == OP_INV && (int)o.b + 1 > n.nstash) n.nstash = (int)o.b + 1;
     }
     return n;
+}
+
+// Lists the input streams of a program (read by OP_FWD / OP_ADDP / OP_NORM) for prefetching.
+inline void list_prefetch(VmLaunch &K)
+{
+    bool is_out[kMaxStreams] = {}, is_in[kMaxStreams] = {};
+    for (int i = 0; i < kMaxOps && K.ops[i].code != OP_END; ++i) {
+        const Op &o = K.ops[i];
+        if (o.code == OP_FIN && (o.b & FIN_STORE)) is_out[o.a] = true;
+        if (o.code == OP_FWD || o.code == OP_ADDP || o.code == OP_NORM) is_in[o.a] = true;
+    }
+    K.n_prefetch = 0;
+    for (int s = 0; s < kMaxStreams && K.n_prefetch < 8; ++s)
+        if (is_in[s] && !is_out[s] && K.st[s].div == 1) K.prefetch[K.n_prefetch++] = (uint8_t)s;
 }
 
 // Fills the half-warp layout fields; `split` programs keep no stash (residues are swapped by shuffles).

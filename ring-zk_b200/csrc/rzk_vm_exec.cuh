@@ -171,7 +171,8 @@ RZK_VM void inv_g1(uint32_t (&a)[kElems], const uint32_t *g1tab, uint32_t p, uin
 
 RZK_VM uint64_t stream_poly(const Stream &s, uint32_t item, uint32_t off)
 {
-    return (uint64_t)(item / s.div) * s.stride + off;
+    const uint32_t grp = (s.div == 1) ? item : item / s.div;     // div > 1 only for per-instance streams of Sum proofs
+    return (uint64_t)grp * s.stride + off;
 }
 
 // ---------------------------------------------------------------- ops
@@ -349,7 +350,7 @@ RZK_VM void op_ld(Lane *lanes, const LaneCtx *ctxs, const Op &op)
 {
     RZK_EACH_LANE {
         RZK_LANE;
-        const uint4 *s4 = reinterpret_cast<const uint4 *>(ctx.slot_hw[op.a & 1]);
+        const uint4 *s4 = reinterpret_cast<const uint4 *>((op.a & 1) ? ctx.slot_hw[1] : ctx.slot_hw[0]);
         RZK_UNROLL
         for (int j = 0; j < 8; ++j) {
             const uint4 q = s4[j * kLanes + t];
@@ -403,7 +404,7 @@ RZK_VM void op_fin(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int64_t 
         const uint64_t poly = stream_poly(st, ctx.item, (uint32_t)op.off + (uint32_t)it * op.step);
         int32_t res[CNT];
         RZK_UNROLL
-        for (int j = 0; j < CNT; ++j) res[j] = reduce_q_centered(V[li_][j], K.q, K.bar, K.kq);
+        for (int j = 0; j < CNT; ++j) res[j] = reduce_q_centered(V[li_][j], K.q, K.m30, K.kqh);
         if (op.b & FIN_CMPZ) {
             uint32_t nz = 0;
             RZK_UNROLL
@@ -447,8 +448,11 @@ RZK_VM int64_t crt_combine(const VmLaunch &K, const uint32_t (&r)[kMaxPrimes])
     const uint64_t lo = lo_prod + v01;
     const uint64_t hi = hi_prod + (lo < lo_prod ? 1u : 0u);
     const bool negv = (hi > K.crt.Phalf_hi) || (hi == K.crt.Phalf_hi && lo > K.crt.Phalf_lo);
-    // a value congruent to V mod q that stays inside int64: v01 < 2^60, P01modq*h2 < 2^62
-    int64_t w = (int64_t)(v01 + K.crt.P01modq * (uint64_t)h2);
+    // a value congruent to V mod q with |w| < 2^60 + 2^33 (the range reduce_q_centered accepts):
+    // (P01 mod q) * h2 < 2^62 is first brought to [0, 2q) with the same top-bits Barrett step
+    uint64_t tq = K.crt.P01modq * (uint64_t)h2;
+    tq -= (uint64_t)mulhi32((uint32_t)(tq >> 30), K.m30) * (uint64_t)K.q;
+    int64_t w = (int64_t)(v01 + tq);
     if (negv) w -= (int64_t)K.crt.Pmodq;
     return w;
 }
@@ -621,18 +625,30 @@ RZK_VM void op_norm(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const O
                 }
             }
             L.fail |= bad;
+#if defined(__CUDA_ARCH__)
+            // sum over the lanes that own the item (half warp in MODE_SEQ, full warp otherwise)
+            uint32_t lo = (uint32_t)s, hi = (uint32_t)(s >> 32);
+            RZK_UNROLL
+            for (int d = RED_N / 2; d >= 1; d >>= 1) {
+                const uint32_t olo = __shfl_xor_sync(0xffffffffu, lo, d);
+                const uint32_t ohi = __shfl_xor_sync(0xffffffffu, hi, d);
+                const uint64_t sum = (((uint64_t)hi << 32) | lo) + (((uint64_t)ohi << 32) | olo);
+                lo = (uint32_t)sum; hi = (uint32_t)(sum >> 32);
+            }
+            const uint64_t tot = ((uint64_t)hi << 32) | lo;
+            L.fail |= (tot > sq_lim) ? 1u : 0u;
+        }
+#else
             ctx.red[2 * ctx.ridx] = (uint32_t)s;
             ctx.red[2 * ctx.ridx + 1] = (uint32_t)(s >> 32);
         }
-        RZK_SYNC();
         RZK_EACH_LANE {
             RZK_LANE;
             uint64_t tot = 0;
-            RZK_UNROLL
             for (int j = 0; j < RED_N; ++j) tot += (uint64_t)ctx.red[2 * j] | ((uint64_t)ctx.red[2 * j + 1] << 32);
             L.fail |= (tot > sq_lim) ? 1u : 0u;
         }
-        RZK_SYNC();
+#endif
     }
 }
 
@@ -672,6 +688,9 @@ RZK_VM void vm_run_item(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs)
                 if (op.code == OP_SEG || op.code == OP_END) break;
                 switch (op.code) {
                 case OP_FWD:
+#if defined(__CUDA_ARCH__)
+                    if (K.cta_sync) __syncthreads();
+#endif
                     op_fwd(K, lanes, ctxs, op, it);
                     break;
                 case OP_MACK:
@@ -698,6 +717,9 @@ RZK_VM void vm_run_item(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs)
                     op_ld(lanes, ctxs, op);
                     break;
                 case OP_INV:
+#if defined(__CUDA_ARCH__)
+                    if (K.cta_sync) __syncthreads();
+#endif
                     q = op_inv<NP, MODE>(K, lanes, ctxs, q, it, prime_iter);
                     continue;
                 case OP_LOOP:
@@ -717,24 +739,24 @@ RZK_VM void vm_run_item(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs)
         pc = seg_end;
     }
     // fold the owning lanes' status words into the item-group flag word
+#if defined(__CUDA_ARCH__)
+    {
+        uint32_t f = lanes[0].fail | (lanes[0].rerr << 1);
+        RZK_UNROLL
+        for (int d = RED_N / 2; d >= 1; d >>= 1) f |= __shfl_xor_sync(0xffffffffu, f, d);
+        if (ctxs[0].ridx == 0 && ctxs[0].active && f) atomicOr(&K.flags[ctxs[0].item / K.flag_div], f);
+    }
+#else
     RZK_EACH_LANE { RZK_LANE; ctx.red[ctx.ridx] = L.fail | (L.rerr << 1); }
-    RZK_SYNC();
     RZK_EACH_LANE {
         RZK_LANE;
         if (ctx.ridx == 0 && ctx.active) {
             uint32_t f = 0;
-            RZK_UNROLL
             for (int j = 0; j < RED_N; ++j) f |= ctx.red[j];
-            if (f) {
-#if defined(__CUDA_ARCH__)
-                atomicOr(&K.flags[ctx.item / K.flag_div], f);
-#else
-                K.flags[ctx.item / K.flag_div] |= f;
-#endif
-            }
+            if (f) K.flags[ctx.item / K.flag_div] |= f;
         }
     }
-    RZK_SYNC();
+#endif
 }
 
 }  // namespace rzk

@@ -65,8 +65,8 @@ struct Emu {
         }
         K.crt = make_crt_consts(sl, np, (uint64_t)Q);
         K.q = (uint32_t)Q;
-        K.bar = (uint64_t)((((unsigned __int128)1) << 64) / (uint64_t)Q);
-        K.kq = (uint64_t)Q << 29;
+        K.kqh = ((uint64_t)Q << 29) + (uint64_t)(Q - 1) / 2;
+        K.m30 = (uint32_t)((1ull << 62) / (uint64_t)Q);
         rzko_params P = rzko_default_params(kN);
         uint64_t cb = rzko_commit_bound(&P), vb = rzko_verify_bound(&P);
         K.norm_abs_lim[0] = (uint32_t)cb; K.norm_sq_lim[0] = (cb + 1) * (cb + 1) - 1;
