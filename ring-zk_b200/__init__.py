@@ -7,3 +7,5 @@ hyphen).  Sub-modules:
   api     host-side mirror of the reference's public Rust API on top of `engine`
 """
 from . import synth  # noqa: F401
+
+__all__ = ["synth", "engine", "api", "shard"]
