@@ -38,6 +38,17 @@ RZK_HD uint64_t mulhi64(uint64_t a, uint64_t b)
 #endif
 }
 
+// acc + sum of squares of the four int8 lanes of v
+RZK_HD uint32_t dot4_i8(int32_t v, uint32_t acc)
+{
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__dp4a(v, v, (int32_t)acc);
+#else
+    for (int k = 0; k < 4; ++k) { const int32_t b = (int8_t)(v >> (8 * k)); acc += (uint32_t)(b * b); }
+    return acc;
+#endif
+}
+
 RZK_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
 
 // x in [0, 2m) -> [0, m)  (unsigned wrap makes x - m huge when x < m)
@@ -89,6 +100,15 @@ RZK_HD int32_t canon_q(int32_t v, uint32_t q)
     if (v > half) u -= q;
     else if (v < -half) u += q;
     return (int32_t)u;
+}
+
+// Any int32 representative v of a class mod q -> a value congruent to v mod q that is >= -2*p_min for
+// every auxiliary prime (so that v + 2p is a valid lazy NTT input in [0, 4p)).  Only the 98,302 lowest
+// int32 values need fixing (v + q still fits int32); products only need the class mod q, because
+// the integer result is reduced mod q at the end and the CRT ranges are sized for |v| <= 2^31.
+RZK_HD int32_t lift_in(int32_t v, uint32_t q)
+{
+    return v < -2147000000 ? (int32_t)((uint32_t)v + q) : v;
 }
 
 // Signed 64-bit value w with |w| < 2^60  ->  centred residue mod q in [-(q-1)/2, (q-1)/2].

@@ -304,6 +304,8 @@ int ensure_scratch(rzk_engine *e, size_t bytes)
 
 constexpr size_t kPolyBytes = (size_t)kN * sizeof(int32_t);
 
+#define RZK_TRY(x) do { int rc__ = (x); if (rc__ != RZK_OK) return rc__; } while (0)
+
 // ---- phase lowering on device pointers (scratch supplied by the caller of these helpers) ----
 
 constexpr uint32_t kSplitKeyLimit = 15;    // |r| bound of MODE_SPLITKEY: 2*512*2^15*15 < p/2
@@ -311,14 +313,14 @@ constexpr uint32_t kSplitKeyLimit = 15;    // |r| bound of MODE_SPLITKEY: 2*512*
 // generic = true: two-prime program, exact for any int8 r.
 // generic = false: split-key program (|r| <= 15 on the transformed rows, else FLAG_RANGE).
 int dev_commit(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r, int32_t *c, uint32_t *flags, cudaStream_t s,
-               bool generic = false)
+               bool generic = false, uint32_t flag_div = 1)
 {
     VmLaunch K; memset(&K, 0, sizeof(K));
     Prog p(&K);
     if (generic) prog_commit(p, 0, 1, 2);
     else prog_commit_splitkey(p, 0, 1, 2);
     p.end();
-    fill_common(e, K, generic ? 2 : 1, (uint32_t)B, 1, flags);
+    fill_common(e, K, generic ? 2 : 1, (uint32_t)B, flag_div, flags);
     set_stream(K, 0, x, 1, DT_I32); set_stream(K, 1, r, 3, DT_I8); set_stream(K, 2, c, 2, DT_I32);
     if (generic) return launch_np(e, 2, K, s);
     K.small_lim = kSplitKeyLimit;
@@ -326,18 +328,26 @@ int dev_commit(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r, int32
     return launch_vm<1, MODE_SPLITKEY>(e, K, s);
 }
 
-int dev_open_commit(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r, const int32_t *y,
-                    int32_t *c, int32_t *t, uint32_t *flags, cudaStream_t s)
+// t = A1.y (and optionally w = A2.y) for `items` masking vectors: two-prime program
+int dev_keymatvec(rzk_engine *e, size_t items, const int32_t *y, int32_t *t, int32_t *w, uint32_t *flags, uint32_t flag_div,
+                  cudaStream_t s)
 {
     VmLaunch K; memset(&K, 0, sizeof(K));
     Prog p(&K);
-    prog_commit(p, 0, 1, 2);
-    prog_keymatvec(p, 3, 4, -1, true);
+    prog_keymatvec(p, 0, 1, w ? 2 : -1, true);
     p.end();
-    fill_common(e, K, 2, (uint32_t)B, 1, flags);
-    set_stream(K, 0, x, 1, DT_I32); set_stream(K, 1, r, 3, DT_I8); set_stream(K, 2, c, 2, DT_I32);
-    set_stream(K, 3, y, 3, DT_I32); set_stream(K, 4, t, 1, DT_I32);
+    fill_common(e, K, 2, (uint32_t)items, flag_div, flags);
+    set_stream(K, 0, y, 3, DT_I32); set_stream(K, 1, t, 1, DT_I32);
+    if (w) set_stream(K, 2, w, 1, DT_I32);
     return launch_np(e, 2, K, s);
+}
+
+// open.rs:80-103: the commitment (split-key program) and t = A1.y (two-prime program)
+int dev_open_commit(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r, const int32_t *y,
+                    int32_t *c, int32_t *t, uint32_t *flags, cudaStream_t s, bool generic = false)
+{
+    RZK_TRY(dev_commit(e, B, x, r, c, flags, s, generic));
+    return dev_keymatvec(e, B, y, t, nullptr, flags, 1, s);
 }
 
 int dev_respond(rzk_engine *e, size_t items, const int32_t *y, const int8_t *r, const int8_t *d, uint32_t d_div,
@@ -387,30 +397,21 @@ int dev_mulsum(rzk_engine *e, size_t B, uint32_t T, const int32_t *a, const int3
 
 // commit(x; r) -> c  and  t = A1.y, w = A2.y  for `items` (x, r, y) triples
 int dev_commit_matvec(rzk_engine *e, size_t items, const int32_t *x, const int8_t *r, const int32_t *y,
-                      int32_t *c, int32_t *t, int32_t *w, uint32_t *flags, uint32_t flag_div, cudaStream_t s)
+                      int32_t *c, int32_t *t, int32_t *w, uint32_t *flags, uint32_t flag_div, cudaStream_t s, bool generic = false)
 {
-    VmLaunch K; memset(&K, 0, sizeof(K));
-    Prog p(&K);
-    prog_commit(p, 0, 1, 2);
-    prog_keymatvec(p, 3, 4, 5, true);
-    p.end();
-    fill_common(e, K, 2, (uint32_t)items, flag_div, flags);
-    set_stream(K, 0, x, 1, DT_I32); set_stream(K, 1, r, 3, DT_I8); set_stream(K, 2, c, 2, DT_I32);
-    set_stream(K, 3, y, 3, DT_I32); set_stream(K, 4, t, 1, DT_I32); set_stream(K, 5, w, 1, DT_I32);
-    return launch_np(e, 2, K, s);
+    RZK_TRY(dev_commit(e, items, x, r, c, flags, s, generic, flag_div));
+    return dev_keymatvec(e, items, y, t, w, flags, flag_div, s);
 }
-
-#define RZK_TRY(x) do { int rc__ = (x); if (rc__ != RZK_OK) return rc__; } while (0)
 
 // scratch: 2*B polys
 int dev_linear_commit(rzk_engine *e, size_t B, const int32_t *g, const int32_t *x, const int8_t *rp, const int8_t *r,
                       const int32_t *y, const int32_t *yp, int32_t *gx, int32_t *cp, int32_t *c, int32_t *t,
-                      int32_t *tp, int32_t *u, uint32_t *flags, int32_t *scratch, cudaStream_t s)
+                      int32_t *tp, int32_t *u, uint32_t *flags, int32_t *scratch, cudaStream_t s, bool generic = false)
 {
     int32_t *w = scratch, *wp = scratch + B * kN;
     RZK_TRY(dev_mulsum(e, B, 1, g, x, nullptr, nullptr, gx, flags, s));                 // linear.rs:91-95
-    RZK_TRY(dev_commit_matvec(e, B, gx, rp, yp, cp, tp, wp, flags, 1, s));              // linear.rs:96,121,129
-    RZK_TRY(dev_commit_matvec(e, B, x, r, y, c, t, w, flags, 1, s));                    // linear.rs:97,118,124-127
+    RZK_TRY(dev_commit_matvec(e, B, gx, rp, yp, cp, tp, wp, flags, 1, s, generic));     // linear.rs:96,121,129
+    RZK_TRY(dev_commit_matvec(e, B, x, r, y, c, t, w, flags, 1, s, generic));           // linear.rs:97,118,124-127
     return dev_mulsum(e, B, 1, g, w, wp, nullptr, u, flags, s);                         // linear.rs:124-129
 }
 
@@ -427,12 +428,12 @@ int dev_linear_verify(rzk_engine *e, size_t B, const int32_t *z, const int32_t *
 // scratch: (B*T + B) polys
 int dev_sum_commit(rzk_engine *e, size_t B, uint32_t T, const int32_t *gs, const int32_t *xs, const int8_t *rp,
                    const int8_t *rs, const int32_t *ys, const int32_t *yp, int32_t *xp, int32_t *cp, int32_t *cs,
-                   int32_t *ts, int32_t *tp, int32_t *u, uint32_t *flags, int32_t *scratch, cudaStream_t s)
+                   int32_t *ts, int32_t *tp, int32_t *u, uint32_t *flags, int32_t *scratch, cudaStream_t s, bool generic = false)
 {
     int32_t *ws = scratch, *wp = scratch + B * T * kN;
     RZK_TRY(dev_mulsum(e, B, T, gs, xs, nullptr, nullptr, xp, flags, s));               // sum.rs:107-115
-    RZK_TRY(dev_commit_matvec(e, B, xp, rp, yp, cp, tp, wp, flags, 1, s));              // sum.rs:116,151,160
-    RZK_TRY(dev_commit_matvec(e, B * T, xs, rs, ys, cs, ts, ws, flags, T, s));          // sum.rs:117-120,145-148,157
+    RZK_TRY(dev_commit_matvec(e, B, xp, rp, yp, cp, tp, wp, flags, 1, s, generic));     // sum.rs:116,151,160
+    RZK_TRY(dev_commit_matvec(e, B * T, xs, rs, ys, cs, ts, ws, flags, T, s, generic)); // sum.rs:117-120,145-148,157
     return dev_mulsum(e, B, T, gs, ws, wp, nullptr, u, flags, s);                       // sum.rs:154-160
 }
 
@@ -832,9 +833,15 @@ int rzk_open_commit_batch(rzk_engine *e, size_t B, const int32_t *x, const int8_
     if (any_null({x, r, y, c, t, ok})) return fail(e, RZK_ERR_INVALID, "null argument");
     std::vector<HArr> a = {{x, nullptr, kPolyBytes}, {r, nullptr, 3 * kN}, {y, nullptr, 3 * kPolyBytes},
                            {nullptr, c, 2 * kPolyBytes}, {nullptr, t, kPolyBytes}};
-    return run_chunked(e, B, a, 0, ok, [&](size_t n, void **d, char *, uint32_t *fl, cudaStream_t s) {
+    int rc = run_chunked(e, B, a, 0, ok, [&](size_t n, void **d, char *, uint32_t *fl, cudaStream_t s) {
         return dev_open_commit(e, n, (const int32_t *)d[0], (const int8_t *)d[1], (const int32_t *)d[2],
                                (int32_t *)d[3], (int32_t *)d[4], fl, s);
+    });
+    if (rc != RZK_ERR_RANGE) return rc;
+    // some |r| > 15 (or y out of range): redo with the two-prime commitment program, exact for any int8 r
+    return run_chunked(e, B, a, 0, ok, [&](size_t n, void **d, char *, uint32_t *fl, cudaStream_t s) {
+        return dev_open_commit(e, n, (const int32_t *)d[0], (const int8_t *)d[1], (const int32_t *)d[2],
+                               (int32_t *)d[3], (int32_t *)d[4], fl, s, true);
     });
 }
 
@@ -869,10 +876,17 @@ int rzk_linear_commit_batch(rzk_engine *e, size_t B, const int32_t *g, const int
                            {y, nullptr, 3 * kPolyBytes}, {yp, nullptr, 3 * kPolyBytes},
                            {nullptr, gx, kPolyBytes}, {nullptr, cp, 2 * kPolyBytes}, {nullptr, c, 2 * kPolyBytes},
                            {nullptr, t, kPolyBytes}, {nullptr, tp, kPolyBytes}, {nullptr, u, kPolyBytes}};
-    return run_chunked(e, B, a, 2 * kPolyBytes, ok, [&](size_t n, void **d, char *sc, uint32_t *fl, cudaStream_t s) {
+    int rc = run_chunked(e, B, a, 2 * kPolyBytes, ok, [&](size_t n, void **d, char *sc, uint32_t *fl, cudaStream_t s) {
         return dev_linear_commit(e, n, (const int32_t *)d[0], (const int32_t *)d[1], (const int8_t *)d[2], (const int8_t *)d[3],
                                  (const int32_t *)d[4], (const int32_t *)d[5], (int32_t *)d[6], (int32_t *)d[7], (int32_t *)d[8],
                                  (int32_t *)d[9], (int32_t *)d[10], (int32_t *)d[11], fl, (int32_t *)sc, s);
+    });
+    if (rc != RZK_ERR_RANGE) return rc;
+    // some |r| > 15 (or y out of range): redo with the two-prime commitment program, exact for any int8 r
+    return run_chunked(e, B, a, 2 * kPolyBytes, ok, [&](size_t n, void **d, char *sc, uint32_t *fl, cudaStream_t s) {
+        return dev_linear_commit(e, n, (const int32_t *)d[0], (const int32_t *)d[1], (const int8_t *)d[2], (const int8_t *)d[3],
+                                 (const int32_t *)d[4], (const int32_t *)d[5], (int32_t *)d[6], (int32_t *)d[7], (int32_t *)d[8],
+                                 (int32_t *)d[9], (int32_t *)d[10], (int32_t *)d[11], fl, (int32_t *)sc, s, true);
     });
 }
 
@@ -915,10 +929,17 @@ int rzk_sum_commit_batch(rzk_engine *e, size_t B, uint32_t T, const int32_t *gs,
                            {rs, nullptr, (size_t)T * 3 * kN}, {ys, nullptr, T * 3 * kPolyBytes}, {yp, nullptr, 3 * kPolyBytes},
                            {nullptr, xp, kPolyBytes}, {nullptr, cp, 2 * kPolyBytes}, {nullptr, cs, T * 2 * kPolyBytes},
                            {nullptr, ts, T * kPolyBytes}, {nullptr, tp, kPolyBytes}, {nullptr, u, kPolyBytes}};
-    return run_chunked(e, B, a, (T + 1) * kPolyBytes, ok, [&](size_t n, void **d, char *sc, uint32_t *fl, cudaStream_t s) {
+    int rc = run_chunked(e, B, a, (T + 1) * kPolyBytes, ok, [&](size_t n, void **d, char *sc, uint32_t *fl, cudaStream_t s) {
         return dev_sum_commit(e, n, T, (const int32_t *)d[0], (const int32_t *)d[1], (const int8_t *)d[2], (const int8_t *)d[3],
                               (const int32_t *)d[4], (const int32_t *)d[5], (int32_t *)d[6], (int32_t *)d[7], (int32_t *)d[8],
                               (int32_t *)d[9], (int32_t *)d[10], (int32_t *)d[11], fl, (int32_t *)sc, s);
+    });
+    if (rc != RZK_ERR_RANGE) return rc;
+    // some |r| > 15 (or y out of range): redo with the two-prime commitment program, exact for any int8 r
+    return run_chunked(e, B, a, (T + 1) * kPolyBytes, ok, [&](size_t n, void **d, char *sc, uint32_t *fl, cudaStream_t s) {
+        return dev_sum_commit(e, n, T, (const int32_t *)d[0], (const int32_t *)d[1], (const int8_t *)d[2], (const int8_t *)d[3],
+                              (const int32_t *)d[4], (const int32_t *)d[5], (int32_t *)d[6], (int32_t *)d[7], (int32_t *)d[8],
+                              (int32_t *)d[9], (int32_t *)d[10], (int32_t *)d[11], fl, (int32_t *)sc, s, true);
     });
 }
 

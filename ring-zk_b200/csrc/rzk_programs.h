@@ -53,6 +53,7 @@ inline void prog_commit(Prog &P, int sx = 0, int sr = 1, int sc = 2, bool with_n
 // transforms shared between the half warps through their operand slots.
 inline void prog_commit_splitkey(Prog &P, int sx = 0, int sr = 1, int sc = 2, bool with_norm = true)
 {
+    P.K->alias_slot = 1;      // ST/LD finish before the first inverse transform touches the buffer
     if (with_norm) P.add(OP_NORM, sr, /*commit bound*/ 0, /*count*/ 3, 0);     // commit.rs:102
     P.add(OP_SEG);
     P.add(OP_FWD, sr, FWD_HWPOLY | FWD_CHECK_SMALL, 0, 1);    // half warp h transforms r[1 + h]

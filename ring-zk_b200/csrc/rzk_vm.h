@@ -115,7 +115,9 @@ struct VmLaunch {
     // input streams whose next-item rows are prefetched into L2 while the current item is computed
     uint32_t n_prefetch;
     uint8_t prefetch[8];
-    uint32_t cta_sync;         // experiment: keep the warps of a CTA in step (instruction-cache locality)
+    uint32_t cta_sync;         // keep the warps of a CTA in step (instruction-cache locality)
+    uint32_t alias_slot;       // the operand slot may overlay the transpose buffer (programs whose OP_LDs all
+                               // precede the inverse transforms and that never use OP_MACV)
 };
 
 // What a program needs per half warp (decides how many warps fit in shared memory).
@@ -155,7 +157,8 @@ inline void layout_hw(VmLaunch &K, bool split)
 {
     const ProgNeeds n = scan_needs(K.ops);
     uint32_t w = kBufWords;
-    K.off_slot = w;  if (n.slot) w += kSlotWords;
+    if (K.alias_slot && n.slot) K.off_slot = 0;
+    else { K.off_slot = w; if (n.slot) w += kSlotWords; }
     K.off_acc1 = w;  if (n.acc1) w += kSlotWords;
     K.off_stash = w; if (!split && K.np > 1) w += (uint32_t)n.nstash * (K.np - 1) * kSlotWords;
     K.hw_words = w;

@@ -193,7 +193,7 @@ RZK_VM void op_fwd(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const Op
         } else {
             const int32_t *src = reinterpret_cast<const int32_t *>(st.base) + poly * kN;
             RZK_UNROLL
-            for (int m = 0; m < kElems; ++m) v[m] = canon_q(src[t + kLanes * m], K.q);
+            for (int m = 0; m < kElems; ++m) v[m] = lift_in(src[t + kLanes * m], K.q);
         }
         if (op.b & FWD_CHECK_SMALL) {
             uint32_t bad = 0;
@@ -387,7 +387,7 @@ RZK_VM void op_addp(const VmLaunch &K, const LaneCtx *ctxs, int64_t (&V)[RZK_NL]
         } else {
             const int32_t *src = reinterpret_cast<const int32_t *>(st.base) + poly * kN;
             RZK_UNROLL
-            for (int j = 0; j < CNT; ++j) v[j] = canon_q(src[t + kLanes * epi_m<MODE>(ctx, j)], K.q);
+            for (int j = 0; j < CNT; ++j) v[j] = src[t + kLanes * epi_m<MODE>(ctx, j)];   // any representative: reduced in OP_FIN
         }
         RZK_UNROLL
         for (int j = 0; j < CNT; ++j) V[li_][j] += neg ? -(int64_t)v[j] : (int64_t)v[j];
@@ -467,6 +467,7 @@ RZK_VM int op_inv(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int q, in
     const Op op = K.ops[q];
     const bool last = (MODE != MODE_SEQ) || (prime_iter == NP - 1);
     int64_t V[RZK_NL][CNT];
+    RZK_SYNC();      // every OP_LD of the partner half warp has finished (the slot may overlay this buffer)
     RZK_EACH_LANE {
         RZK_LANE;
         const PrimeC &pc = L.pc;
@@ -607,12 +608,13 @@ RZK_VM void op_norm(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const O
             uint64_t s = 0;
             uint32_t bad = 0;
             if (st.dtype == DT_I8) {
-                const int8_t *src = reinterpret_cast<const int8_t *>(st.base) + poly * kN;
+                // any partition of the 512 coefficients works for a norm: CNT contiguous bytes per lane
+                const int32_t *src = reinterpret_cast<const int32_t *>(reinterpret_cast<const int8_t *>(st.base) + poly * kN) +
+                                     ctx.ridx * (CNT / 4);
+                uint32_t acc = 0;
                 RZK_UNROLL
-                for (int j = 0; j < CNT; ++j) {
-                    const int32_t v = src[t + kLanes * epi_m<MODE>(ctx, j)];
-                    s += (uint64_t)(uint32_t)(v * v);
-                }
+                for (int j = 0; j < CNT / 4; ++j) acc = dot4_i8(src[j], acc);
+                s = acc;
             } else {
                 const int32_t *src = reinterpret_cast<const int32_t *>(st.base) + poly * kN;
                 RZK_UNROLL

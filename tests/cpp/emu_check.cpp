@@ -9,6 +9,8 @@
 #include <string.h>
 #include <math.h>
 #include <vector>
+#include <limits.h>
+#include <stdint.h>
 
 #include "../../ring-zk_b200/csrc/rzk_vm_exec.cuh"
 #include "../../ring-zk_b200/csrc/rzk_programs.h"
@@ -397,6 +399,12 @@ int main(int argc, char **argv)
         for (auto &v : sub) v = rnd_q();
         // worst-case magnitudes on item 0 to exercise the 3-prime range
         for (size_t i = 0; i < T * N; ++i) { gs[i] = (i & 1) ? (int32_t)((Q - 1) / 2) : -(int32_t)((Q - 1) / 2); xs[i] = (int32_t)((Q - 1) / 2); }
+        // non-canonical int32 representatives (any representative of a class mod q is accepted)
+        if (B > 1) for (size_t i = 0; i < N; ++i) {
+            gs[(size_t)T * N + i] = (i % 3 == 0) ? INT32_MIN : (i % 3 == 1) ? INT32_MAX : (int32_t)(-2147000001 + (int)(i % 7));
+            xs[(size_t)T * N + i] = (i & 1) ? INT32_MAX : INT32_MIN;
+            sub[N + i] = (i & 2) ? INT32_MAX : INT32_MIN;
+        }
         Emu E(3, L2, keyp.data(), B);
         Prog pr(&E.K);
         prog_mulsum(pr, T, 0, 1, 2, -1, 3, FIN_STORE);
@@ -405,6 +413,7 @@ int main(int argc, char **argv)
         E.stream(3, out_e.data(), 1, DT_I32);
         E.run(B);
         auto gs64 = widen(gs), xs64 = widen(xs), sub64 = widen(sub);
+        for (auto *v : {&gs64, &xs64, &sub64}) for (auto &c : *v) c = rzko_center(c, Q);
         std::vector<int64_t> acc(N), tmp(N);
         for (int b = 0; b < B; ++b) {
             for (int i = 0; i < T; ++i) {
