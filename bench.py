@@ -33,6 +33,7 @@ BATCH = 1 << 16
 ALG_BYTES_COMMIT = 12288       # 4 polys in + 2 out at 4 B/coeff
 ALG_BYTES_VERIFY = 12288       # 6 polys in
 ALG_MULMODS_COMMIT = 21504
+MEASURED_MULMOD_TPS = 4.617     # T Shoup-mulmods/s, profiles/r1_imad_bench.jsonl
 METRIC = "commitments/s"
 UNIT = "commitments/s"
 WORKLOAD = "configs[1]: batched commitment generation, 2^16 messages/GPU at N=512, Params::default(), one shared key"
@@ -257,7 +258,7 @@ def main():
     peak, peak_src = measured_peaks()
     achieved = ALG_BYTES_COMMIT * B / (ms_k * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic("rzk_vm_kernel<2,2,8>:commit"), "kernel": "rzk_vm_kernel<2,2,8> (commit program)",
+                "traffic": ncu_traffic("commit"), "kernel": "rzk_vm_kernel<1, MODE_SPLITKEY, SPCommitSplitKey>",
                 "kernel_ms": ms_k, "algorithmic_bytes_per_launch": ALG_BYTES_COMMIT * B, "peak_source": peak_src,
                 "note": "integer-pipe bound path: 21504 modular multiplies per commitment; see DESIGN.md"}
 
@@ -335,7 +336,10 @@ def main():
             "clocks": clk.summary(),
             "int_roofline": {"mulmods_per_item": ALG_MULMODS_COMMIT,
                              "achieved_Tmulmod_s": ALG_MULMODS_COMMIT * B / (ms_k * 1e-3) / 1e12,
-                             "planning_peak_Tmulmod_s": 6.2, "frac_of_planning_peak": ALG_MULMODS_COMMIT * B / (ms_k * 1e-3) / 6.2e12},
+                             "peak_Tmulmod_s": MEASURED_MULMOD_TPS,
+                             "frac": ALG_MULMODS_COMMIT * B / (ms_k * 1e-3) / (MEASURED_MULMOD_TPS * 1e12),
+                             "peak_source": "measured Shoup mulmod rate on this pool's B200 (tools/imad_bench.cu, "
+                                            "profiles/r1_imad_bench.jsonl); algorithmic mulmods per SURVEY.md 8(d)"},
         }
         print(json.dumps(line), flush=True)
     eng.close()

@@ -13,24 +13,31 @@
 
 namespace rzk {
 
+// Program builder.  A literal type so that the same builders produce both the runtime programs the
+// generic interpreter decodes and the compile-time programs the specialised kernels are unrolled from.
 struct Prog {
-    VmLaunch *K;
+    Op ops[kMaxOps] = {};
     int n = 0;
-    explicit Prog(VmLaunch *k) : K(k) { memset(K->ops, 0, sizeof(K->ops)); }
-    void add(uint8_t code, int a = 0, int b = 0, int c = 0, int off = 0, int step = 0)
+    uint8_t alias_slot = 0;
+    constexpr void add(uint8_t code, int a = 0, int b = 0, int c = 0, int off = 0, int step = 0)
     {
-        Op &o = K->ops[n++];
+        Op &o = ops[n++];
         o.code = code; o.a = (uint8_t)a; o.b = (uint8_t)b; o.c = (uint8_t)c;
         o.off = (uint16_t)off; o.step = (uint16_t)step;
     }
-    void end() { add(OP_END); }
+    constexpr void end() { add(OP_END); }
+    void install(VmLaunch &K) const
+    {
+        for (int i = 0; i < kMaxOps; ++i) K.ops[i] = ops[i];
+        K.alias_slot = alias_slot;
+    }
 };
 
 // ---- 2-prime programs -------------------------------------------------------------
 
 // [c1; c2] = [a1; a2] . r + [0; x]                       commit.rs:88-128
 // streams: 0 = x (1 poly), 1 = r (3 polys), 2 = c out (2 polys)
-inline void prog_commit(Prog &P, int sx = 0, int sr = 1, int sc = 2, bool with_norm = true)
+constexpr inline void prog_commit(Prog &P, int sx = 0, int sr = 1, int sc = 2, bool with_norm = true)
 {
     if (with_norm) P.add(OP_NORM, sr, /*commit bound*/ 0, /*count*/ 3, 0);     // commit.rs:102
     P.add(OP_SEG);
@@ -51,9 +58,9 @@ inline void prog_commit(Prog &P, int sx = 0, int sr = 1, int sc = 2, bool with_n
 // Same commitment for small randomness (|r| <= 15) in MODE_SPLITKEY: one prime, the key split
 // into 16-bit halves (half warp 0: lo images, half warp 1: hi images), the two forward
 // transforms shared between the half warps through their operand slots.
-inline void prog_commit_splitkey(Prog &P, int sx = 0, int sr = 1, int sc = 2, bool with_norm = true)
+constexpr inline void prog_commit_splitkey(Prog &P, int sx = 0, int sr = 1, int sc = 2, bool with_norm = true)
 {
-    P.K->alias_slot = 1;      // ST/LD finish before the first inverse transform touches the buffer
+    P.alias_slot = 1;         // ST/LD finish before the first inverse transform touches the buffer
     if (with_norm) P.add(OP_NORM, sr, /*commit bound*/ 0, /*count*/ 3, 0);     // commit.rs:102
     P.add(OP_SEG);
     P.add(OP_FWD, sr, FWD_HWPOLY | FWD_CHECK_SMALL, 0, 1);    // half warp h transforms r[1 + h]
@@ -75,7 +82,7 @@ inline void prog_commit_splitkey(Prog &P, int sx = 0, int sr = 1, int sc = 2, bo
 // t = A1 . y  (open.rs:97, linear.rs:118-121, sum.rs:145-151) and optionally w = A2 . y
 // (the inner factor of u, linear.rs:124-129 / sum.rs:154-160).
 // sv = y stream (3 polys), st = t out (or -1), sw = w out (or -1)
-inline void prog_keymatvec(Prog &P, int sv, int st, int sw, bool check_small)
+constexpr inline void prog_keymatvec(Prog &P, int sv, int st, int sw, bool check_small)
 {
     const int fl = check_small ? FWD_CHECK_SMALL : 0;
     P.add(OP_SEG);
@@ -102,7 +109,7 @@ inline void prog_keymatvec(Prog &P, int sv, int st, int sw, bool check_small)
 // optionally also w = A2.z - c2*d  (left/right sides of the third equation folded
 // together, linear.rs:236-249 / sum.rs:300-319).
 // sz = z (3 polys), st = t, sc = commitment c (2 polys: c1, c2), sd = d, sw = w out or -1
-inline void prog_verify_first(Prog &P, int sz, int st, int sc, int sd, int sw)
+constexpr inline void prog_verify_first(Prog &P, int sz, int st, int sc, int sd, int sw)
 {
     P.add(OP_SEG);
     P.add(OP_FWD, sd, FWD_SCALED, 0, 0);
@@ -129,7 +136,7 @@ inline void prog_verify_first(Prog &P, int sz, int st, int sc, int sd, int sw)
     }
 }
 
-inline void prog_norm_verify(Prog &P, int sz)
+constexpr inline void prog_norm_verify(Prog &P, int sz)
 {
     P.add(OP_NORM, sz, /*verify bound*/ 1, 3, 0);      // params.rs:112-118
 }
@@ -138,7 +145,7 @@ inline void prog_norm_verify(Prog &P, int sz)
 
 // z = y + r.componentwise_mul(d)                          open.rs:113-115
 // streams: sy = y (3), sr = r (3), sd = d (1), sz = z out (3)
-inline void prog_respond(Prog &P, int sy, int sr, int sd, int sz)
+constexpr inline void prog_respond(Prog &P, int sy, int sr, int sd, int sz)
 {
     P.add(OP_SEG);
     P.add(OP_FWD, sd, FWD_SCALED, 0, 0);
@@ -169,7 +176,7 @@ inline void prog_respond(Prog &P, int sy, int sr, int sd, int sz)
 //   g*x (linear.rs:91-95), sum g_i*x_i (sum.rs:107-115), u (linear.rs:124-129, sum.rs:154-160),
 //   third-equation check (linear.rs:236-249, sum.rs:300-319) with mode = FIN_CMPZ.
 // sa, sb: streams holding T polys per item; ssub0/ssub1: single-poly streams or -1.
-inline void prog_mulsum(Prog &P, int T, int sa, int sb, int ssub0, int ssub1, int sout, int mode)
+constexpr inline void prog_mulsum(Prog &P, int T, int sa, int sb, int ssub0, int ssub1, int sout, int mode)
 {
     P.add(OP_SEG);
     P.add(OP_FWD, sb, FWD_SCALED, 0, 0);
@@ -189,5 +196,44 @@ inline void prog_mulsum(Prog &P, int T, int sa, int sb, int ssub0, int ssub1, in
     if (ssub1 >= 0) P.add(OP_ADDP, ssub1, 0, MAC_NEG, 0);
     P.add(OP_FIN, sout >= 0 ? sout : 0, mode, 0, 0);
 }
+
+// ---- compile-time program descriptors (vm_run_static) --------------------------------------
+// Stream numbering is the one the engine's dev_* helpers use for the same programs.
+
+struct SPCommitSplitKey {        // streams: 0 = x (i32), 1 = r (i8), 2 = c out
+    static constexpr int kNP = 1, kMode = 2 /* MODE_SPLITKEY */;
+    static constexpr Prog prog = [] { Prog p; prog_commit_splitkey(p, 0, 1, 2, false); p.end(); return p; }();
+    static constexpr uint8_t dtype[kMaxStreams] = {DT_I32, DT_I8, DT_I32};
+};
+
+struct SPKeyMatVecT {            // streams: 0 = y (i32), 1 = t out
+    static constexpr int kNP = 2, kMode = 1 /* MODE_SPLIT */;
+    static constexpr Prog prog = [] { Prog p; prog_keymatvec(p, 0, 1, -1, true); p.end(); return p; }();
+    static constexpr uint8_t dtype[kMaxStreams] = {DT_I32, DT_I32};
+};
+
+struct SPKeyMatVecTW {           // streams: 0 = y, 1 = t out, 2 = w out
+    static constexpr int kNP = 2, kMode = 1;
+    static constexpr Prog prog = [] { Prog p; prog_keymatvec(p, 0, 1, 2, true); p.end(); return p; }();
+    static constexpr uint8_t dtype[kMaxStreams] = {DT_I32, DT_I32, DT_I32};
+};
+
+struct SPVerifyFirst {           // streams: 0 = z, 1 = t, 2 = c, 3 = d (i8)
+    static constexpr int kNP = 2, kMode = 1;
+    static constexpr Prog prog = [] { Prog p; prog_norm_verify(p, 0); prog_verify_first(p, 0, 1, 2, 3, -1); p.end(); return p; }();
+    static constexpr uint8_t dtype[kMaxStreams] = {DT_I32, DT_I32, DT_I32, DT_I8};
+};
+
+struct SPVerifyFirstW {          // streams: 0 = z, 1 = t, 2 = c, 3 = d (i8), 4 = w out
+    static constexpr int kNP = 2, kMode = 1;
+    static constexpr Prog prog = [] { Prog p; prog_norm_verify(p, 0); prog_verify_first(p, 0, 1, 2, 3, 4); p.end(); return p; }();
+    static constexpr uint8_t dtype[kMaxStreams] = {DT_I32, DT_I32, DT_I32, DT_I8, DT_I32};
+};
+
+struct SPRespond {               // streams: 0 = y, 1 = r (i8), 2 = d (i8), 3 = z out
+    static constexpr int kNP = 1, kMode = 0 /* MODE_SEQ */;
+    static constexpr Prog prog = [] { Prog p; prog_respond(p, 0, 1, 2, 3); p.end(); return p; }();
+    static constexpr uint8_t dtype[kMaxStreams] = {DT_I32, DT_I8, DT_I8, DT_I32};
+};
 
 }  // namespace rzk

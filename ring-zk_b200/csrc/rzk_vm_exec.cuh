@@ -31,6 +31,7 @@
 #pragma once
 #include "rzk_arith.cuh"
 #include "rzk_vm.h"
+#include "rzk_programs.h"
 
 #if defined(__CUDACC__)
 #define RZK_VM __device__ __forceinline__
@@ -177,7 +178,7 @@ RZK_VM uint64_t stream_poly(const Stream &s, uint32_t item, uint32_t off)
 
 // ---------------------------------------------------------------- ops
 
-RZK_VM void op_fwd(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const Op &op, int it)
+RZK_VM void op_fwd(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const Op &op, int it, uint32_t dtype)
 {
     const Stream st = K.st[op.a];
     RZK_EACH_LANE {
@@ -186,7 +187,7 @@ RZK_VM void op_fwd(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const Op
         const uint64_t poly = stream_poly(st, ctx.item, (uint32_t)op.off + (uint32_t)it * op.step +
                                                             ((op.b & FWD_HWPOLY) ? (uint32_t)ctx.hw : 0u));
         int32_t v[kElems];
-        if (st.dtype == DT_I8) {
+        if (dtype == DT_I8) {
             const int8_t *src = reinterpret_cast<const int8_t *>(st.base) + poly * kN;
             RZK_UNROLL
             for (int m = 0; m < kElems; ++m) v[m] = src[t + kLanes * m];
@@ -370,7 +371,7 @@ template <int MODE>
 RZK_VM int epi_m(const LaneCtx &ctx, int j) { return (MODE != MODE_SEQ) ? (16 * ctx.hw + j) : j; }
 
 template <int MODE>
-RZK_VM void op_addp(const VmLaunch &K, const LaneCtx *ctxs, int64_t (&V)[RZK_NL][Epi<MODE>::kCount], const Op &op, int it)
+RZK_VM void op_addp(const VmLaunch &K, const LaneCtx *ctxs, int64_t (&V)[RZK_NL][Epi<MODE>::kCount], const Op &op, int it, uint32_t dtype)
 {
     constexpr int CNT = Epi<MODE>::kCount;
     const Stream st = K.st[op.a];
@@ -380,7 +381,7 @@ RZK_VM void op_addp(const VmLaunch &K, const LaneCtx *ctxs, int64_t (&V)[RZK_NL]
         const int t = ctx.t;
         const uint64_t poly = stream_poly(st, ctx.item, (uint32_t)op.off + (uint32_t)it * op.step);
         int32_t v[CNT];
-        if (st.dtype == DT_I8) {
+        if (dtype == DT_I8) {
             const int8_t *src = reinterpret_cast<const int8_t *>(st.base) + poly * kN;
             RZK_UNROLL
             for (int j = 0; j < CNT; ++j) v[j] = src[t + kLanes * epi_m<MODE>(ctx, j)];
@@ -461,12 +462,10 @@ RZK_VM int64_t crt_combine(const VmLaunch &K, const uint32_t (&r)[kMaxPrimes])
 // the epilogue ops that follow (OP_ADDP*, OP_FIN) are executed here, so that the 64-bit
 // values live only inside this function.  Returns the index of the first op after the epilogue.
 template <int NP, int MODE>
-RZK_VM int op_inv(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int q, int it, int prime_iter)
+RZK_VM void inv_core(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const Op &op, int prime_iter,
+                     int64_t (&V)[RZK_NL][Epi<MODE>::kCount])
 {
     constexpr int CNT = Epi<MODE>::kCount;
-    const Op op = K.ops[q];
-    const bool last = (MODE != MODE_SEQ) || (prime_iter == NP - 1);
-    int64_t V[RZK_NL][CNT];
     RZK_SYNC();      // every OP_LD of the partner half warp has finished (the slot may overlay this buffer)
     RZK_EACH_LANE {
         RZK_LANE;
@@ -580,11 +579,22 @@ RZK_VM int op_inv(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int q, in
             }
         }
     }
+}
+
+// Generic (runtime-decoded) form: inverse transform, then the epilogue ops that follow.
+// Returns the index of the first op after the epilogue.
+template <int NP, int MODE>
+RZK_VM int op_inv(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int q, int it, int prime_iter)
+{
+    const Op op = K.ops[q];
+    const bool last = (MODE != MODE_SEQ) || (prime_iter == NP - 1);
+    int64_t V[RZK_NL][Epi<MODE>::kCount];
+    inv_core<NP, MODE>(K, lanes, ctxs, op, prime_iter, V);
     ++q;
     RZK_NOUNROLL
     for (;; ++q) {
         const Op e = K.ops[q];
-        if (e.code == OP_ADDP) { if (last) op_addp<MODE>(K, ctxs, V, e, it); }
+        if (e.code == OP_ADDP) { if (last) op_addp<MODE>(K, ctxs, V, e, it, K.st[e.a].dtype); }
         else if (e.code == OP_FIN) { if (last) op_fin<MODE>(K, lanes, ctxs, V, e, it); }
         else break;
     }
@@ -593,7 +603,7 @@ RZK_VM int op_inv(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int q, in
 
 // params.rs:102-118 via polynomial.rs:60-73: floor(sqrt(sum c^2)) <= bound  <=>  sum c^2 < (bound+1)^2
 template <int MODE>
-RZK_VM void op_norm(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const Op &op)
+RZK_VM void op_norm(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const Op &op, uint32_t dtype)
 {
     constexpr int CNT = Epi<MODE>::kCount;
     constexpr int RED_N = (MODE != MODE_SEQ) ? 32 : 16;
@@ -607,7 +617,7 @@ RZK_VM void op_norm(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const O
             const uint64_t poly = stream_poly(st, ctx.item, (uint32_t)op.off + (uint32_t)c);
             uint64_t s = 0;
             uint32_t bad = 0;
-            if (st.dtype == DT_I8) {
+            if (dtype == DT_I8) {
                 // any partition of the 512 coefficients works for a norm: CNT contiguous bytes per lane
                 const int32_t *src = reinterpret_cast<const int32_t *>(reinterpret_cast<const int8_t *>(st.base) + poly * kN) +
                                      ctx.ridx * (CNT / 4);
@@ -669,7 +679,7 @@ RZK_VM void vm_run_item(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs)
     int pc = 0;
     RZK_NOUNROLL
     while (K.ops[pc].code == OP_NORM) {
-        op_norm<MODE>(K, lanes, ctxs, K.ops[pc]);
+        op_norm<MODE>(K, lanes, ctxs, K.ops[pc], K.st[K.ops[pc].a].dtype);
         ++pc;
     }
     RZK_NOUNROLL
@@ -693,7 +703,7 @@ RZK_VM void vm_run_item(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs)
 #if defined(__CUDA_ARCH__)
                     if (K.cta_sync) __syncthreads();
 #endif
-                    op_fwd(K, lanes, ctxs, op, it);
+                    op_fwd(K, lanes, ctxs, op, it, K.st[op.a].dtype);
                     break;
                 case OP_MACK:
                     RZK_EACH_LANE {
@@ -741,6 +751,162 @@ RZK_VM void vm_run_item(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs)
         pc = seg_end;
     }
     // fold the owning lanes' status words into the item-group flag word
+#if defined(__CUDA_ARCH__)
+    {
+        uint32_t f = lanes[0].fail | (lanes[0].rerr << 1);
+        RZK_UNROLL
+        for (int d = RED_N / 2; d >= 1; d >>= 1) f |= __shfl_xor_sync(0xffffffffu, f, d);
+        if (ctxs[0].ridx == 0 && ctxs[0].active && f) atomicOr(&K.flags[ctxs[0].item / K.flag_div], f);
+    }
+#else
+    RZK_EACH_LANE { RZK_LANE; ctx.red[ctx.ridx] = L.fail | (L.rerr << 1); }
+    RZK_EACH_LANE {
+        RZK_LANE;
+        if (ctx.ridx == 0 && ctx.active) {
+            uint32_t f = 0;
+            for (int j = 0; j < RED_N; ++j) f |= ctx.red[j];
+            if (f) K.flags[ctx.item / K.flag_div] |= f;
+        }
+    }
+#endif
+}
+
+// ---------------------------------------------------------------- compile-time programs
+//
+// The hot programs are also instantiated as templates: SP::prog is a constexpr program (built by the
+// same builders), so op decoding, flag tests, dtype branches and the epilogue op lists fold away at
+// compile time and the kernel body is straight-line code.  K.loop_count replaces the immediate of
+// OP_LOOP (the number of Sum-proof terms is only known at launch).
+
+constexpr int sp_find_endloop(const Prog &p, int pc)
+{
+    while (p.ops[pc].code != OP_ENDLOOP) ++pc;
+    return pc;
+}
+
+constexpr int sp_next_seg(const Prog &p, int pc)        // index of the next OP_SEG / OP_END at or after pc
+{
+    while (p.ops[pc].code != OP_SEG && p.ops[pc].code != OP_END) ++pc;
+    return pc;
+}
+
+template <class SP, int MODE, int PC>
+RZK_VM void sp_epilogue(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int64_t (&V)[RZK_NL][Epi<MODE>::kCount], int it)
+{
+    constexpr Op e = SP::prog.ops[PC];
+    if constexpr (e.code == OP_ADDP) {
+        constexpr uint32_t dt = SP::dtype[e.a];
+        op_addp<MODE>(K, ctxs, V, e, it, dt);
+        sp_epilogue<SP, MODE, PC + 1>(K, lanes, ctxs, V, it);
+    } else if constexpr (e.code == OP_FIN) {
+        op_fin<MODE>(K, lanes, ctxs, V, e, it);
+        sp_epilogue<SP, MODE, PC + 1>(K, lanes, ctxs, V, it);
+    }
+}
+
+constexpr int sp_skip_epilogue(const Prog &p, int pc)
+{
+    while (p.ops[pc].code == OP_ADDP || p.ops[pc].code == OP_FIN) ++pc;
+    return pc;
+}
+
+// executes ops from PC up to (not including) the next OP_SEG / OP_END / OP_ENDLOOP
+template <class SP, int NP, int MODE, int PC>
+RZK_VM void sp_exec(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int it, int prime_iter)
+{
+    constexpr Op op = SP::prog.ops[PC];
+    constexpr int KP = (MODE == MODE_SPLITKEY) ? 2 * kKeyPolys : kKeyPolys;
+    if constexpr (op.code == OP_SEG || op.code == OP_END || op.code == OP_ENDLOOP) {
+        return;
+    } else if constexpr (op.code == OP_LOOP) {
+        constexpr int end = sp_find_endloop(SP::prog, PC);
+        RZK_NOUNROLL
+        for (int i = 0; i < (int)K.loop_count; ++i) sp_exec<SP, NP, MODE, PC + 1>(K, lanes, ctxs, i, prime_iter);
+        sp_exec<SP, NP, MODE, end + 1>(K, lanes, ctxs, 0, prime_iter);
+    } else if constexpr (op.code == OP_INV) {
+        constexpr int next = sp_skip_epilogue(SP::prog, PC + 1);
+        {
+            int64_t V[RZK_NL][Epi<MODE>::kCount];
+            inv_core<NP, MODE>(K, lanes, ctxs, op, prime_iter, V);
+            if ((MODE != MODE_SEQ) || prime_iter == NP - 1) sp_epilogue<SP, MODE, PC + 1>(K, lanes, ctxs, V, it);
+        }
+        sp_exec<SP, NP, MODE, next>(K, lanes, ctxs, it, prime_iter);
+    } else {
+        if constexpr (op.code == OP_FWD) {
+#if defined(__CUDA_ARCH__)
+            if (K.cta_sync) __syncthreads();
+#endif
+            constexpr uint32_t dt = SP::dtype[op.a];
+            op_fwd(K, lanes, ctxs, op, it, dt);
+        } else if constexpr (op.code == OP_MACK) {
+            RZK_EACH_LANE {
+                RZK_LANE;
+                const int kidx = (MODE == MODE_SPLITKEY) ? (2 * (int)op.b + ctx.hw) : (int)op.b;
+                const uint32_t *krow = ctx.key + ((L.pi * KP + kidx) * 2) * kPadWords;
+                if constexpr (op.a == 0) mac_key(L.acc0, L.cur, krow, t, op.c, L.pc.p, L.pc.p2);
+                else mac_key_smem(ctx.acc1, L.cur, krow, t, op.c, L.pc.p, L.pc.p2);
+            }
+        } else if constexpr (op.code == OP_MACV) {
+            RZK_EACH_LANE {
+                RZK_LANE;
+                if constexpr (op.a == 0) mac_var(L.acc0, L.cur, ctx.slot, t, op.c, L.pc.p, L.pc.p2, L.pc.pinv);
+                else mac_var_smem(ctx.acc1, L.cur, ctx.slot, t, op.c, L.pc.p, L.pc.p2, L.pc.pinv);
+            }
+        } else if constexpr (op.code == OP_ST) {
+            op_st(lanes, ctxs, op);
+        } else if constexpr (op.code == OP_LD) {
+            op_ld(lanes, ctxs, op);
+        }
+        sp_exec<SP, NP, MODE, PC + 1>(K, lanes, ctxs, it, prime_iter);
+    }
+}
+
+template <class SP, int NP, int MODE, int PC>
+RZK_VM void sp_norms(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs)
+{
+    constexpr Op op = SP::prog.ops[PC];
+    if constexpr (op.code == OP_NORM) {
+        constexpr uint32_t dt = SP::dtype[op.a];
+        op_norm<MODE>(K, lanes, ctxs, op, dt);
+        sp_norms<SP, NP, MODE, PC + 1>(K, lanes, ctxs);
+    }
+}
+
+constexpr int sp_first_seg(const Prog &p)
+{
+    int pc = 0;
+    while (p.ops[pc].code == OP_NORM) ++pc;
+    return pc;
+}
+
+template <class SP, int NP, int MODE, int PC>
+RZK_VM void sp_segments(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs)
+{
+    constexpr Op op = SP::prog.ops[PC];
+    if constexpr (op.code == OP_SEG) {
+        constexpr int PRIME_ITERS = (MODE != MODE_SEQ) ? 1 : NP;
+        RZK_NOUNROLL
+        for (int prime_iter = 0; prime_iter < PRIME_ITERS; ++prime_iter) {
+            RZK_EACH_LANE {
+                RZK_LANE;
+                L.pi = (MODE == MODE_SPLIT) ? ctx.hw : (MODE == MODE_SPLITKEY ? 0 : prime_iter);
+                L.pc = K.pc[L.pi];
+            }
+            sp_exec<SP, NP, MODE, PC + 1>(K, lanes, ctxs, 0, prime_iter);
+        }
+        sp_segments<SP, NP, MODE, sp_next_seg(SP::prog, PC + 1)>(K, lanes, ctxs);
+    }
+}
+
+// Compile-time counterpart of vm_run_item.
+template <class SP>
+RZK_VM void vm_run_static(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs)
+{
+    constexpr int NP = SP::kNP, MODE = SP::kMode;
+    constexpr int RED_N = (MODE != MODE_SEQ) ? 32 : 16;
+    RZK_EACH_LANE { RZK_LANE; L.fail = 0; L.rerr = 0; }
+    sp_norms<SP, NP, MODE, 0>(K, lanes, ctxs);
+    sp_segments<SP, NP, MODE, sp_first_seg(SP::prog)>(K, lanes, ctxs);
 #if defined(__CUDA_ARCH__)
     {
         uint32_t f = lanes[0].fail | (lanes[0].rerr << 1);

@@ -27,7 +27,7 @@ SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("rzk_engine.cu", "rzk_tables
 HEADERS = [os.path.join(_HERE, "csrc", f) for f in
            ("rzk_arith.cuh", "rzk_vm.h", "rzk_vm_exec.cuh", "rzk_programs.h", "rzk_tables.h")] + \
           [os.path.join(_ROOT, "include", "ringzk_b200.h")]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
               "-Xcompiler", "-fPIC", "--shared"]
 
 

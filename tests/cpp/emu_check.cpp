@@ -9,6 +9,7 @@
 #include <string.h>
 #include <math.h>
 #include <vector>
+#include <type_traits>
 #include <limits.h>
 #include <stdint.h>
 
@@ -85,6 +86,7 @@ struct Emu {
     }
     // Emulates one warp at a time exactly as the kernel maps it: SPLIT (np == 2) gives the warp one
     // item with half warp h on prime h; SEQ gives each half warp its own item.
+    template <class SP = void>
     void run(uint32_t n_items)
     {
         K.n_items = n_items;
@@ -110,7 +112,8 @@ struct Emu {
                 c.active = item < n_items;
                 c.item = c.active ? item : n_items - 1;
             }
-            if (mode == MODE_SPLITKEY) vm_run_item<1, MODE_SPLITKEY>(K, lanes, ctxs);
+            if constexpr (!std::is_void<SP>::value) vm_run_static<SP>(K, lanes, ctxs);
+            else if (mode == MODE_SPLITKEY) vm_run_item<1, MODE_SPLITKEY>(K, lanes, ctxs);
             else if (np == 1) vm_run_item<1, MODE_SEQ>(K, lanes, ctxs);
             else if (np == 2) vm_run_item<2, MODE_SPLIT>(K, lanes, ctxs);
             else vm_run_item<3, MODE_SEQ>(K, lanes, ctxs);
@@ -173,10 +176,10 @@ int main(int argc, char **argv)
     std::vector<int32_t> c_e(B * 2 * N), t_e(B * N), w_e(B * N);
     {
         Emu E(2, L2, keyp.data(), B);
-        Prog pr(&E.K);
+        Prog pr;
         prog_commit(pr, 0, 1, 2);
         prog_keymatvec(pr, 3, 4, 5, true);
-        pr.end();
+        pr.end(); pr.install(E.K);
         E.stream(0, x.data(), 1, DT_I32); E.stream(1, r.data(), 3, DT_I8); E.stream(2, c_e.data(), 2, DT_I32);
         E.stream(3, y.data(), 3, DT_I32); E.stream(4, t_e.data(), 1, DT_I32); E.stream(5, w_e.data(), 1, DT_I32);
         E.run(B);
@@ -198,10 +201,10 @@ int main(int argc, char **argv)
         ybig[5] = (1 << 18) + 1;                                                 // item 0, poly 0: not transformed -> no flag
         ybig[N + 5] = (1 << 18) + 1;                                             // item 0, poly 1: flagged
         Emu E(2, L2, keyp.data(), B);
-        Prog pr(&E.K);
+        Prog pr;
         prog_commit(pr, 0, 1, 2);
         prog_keymatvec(pr, 3, 4, -1, true);
-        pr.end();
+        pr.end(); pr.install(E.K);
         E.stream(0, x.data(), 1, DT_I32); E.stream(1, rbig.data(), 3, DT_I32); E.stream(2, c_e.data(), 2, DT_I32);
         E.stream(3, ybig.data(), 3, DT_I32); E.stream(4, t_e.data(), 1, DT_I32);
         E.run(B);
@@ -223,9 +226,9 @@ int main(int argc, char **argv)
         for (size_t i = N; i < 3 * N; ++i) r15[i] = (i & 1) ? 15 : -15;
         std::vector<int32_t> xw(x);
         Emu E(1, L1, keyp.data(), B, MODE_SPLITKEY);
-        Prog pr(&E.K);
+        Prog pr;
         prog_commit_splitkey(pr, 0, 1, 2);
-        pr.end();
+        pr.end(); pr.install(E.K);
         E.K.small_lim = 15;
         E.stream(0, xw.data(), 1, DT_I32); E.stream(1, r15.data(), 3, DT_I8); E.stream(2, c_e.data(), 2, DT_I32);
         E.run(B);
@@ -253,10 +256,10 @@ int main(int argc, char **argv)
     {
         const int L1[1] = {0};
         Emu E(1, L1, keyp.data(), B);
-        Prog pr(&E.K);
+        Prog pr;
         prog_respond(pr, 0, 1, 2, 3);
         prog_respond(pr, 4, 5, 2, 6);
-        pr.end();
+        pr.end(); pr.install(E.K);
         E.stream(0, y.data(), 3, DT_I32); E.stream(1, r.data(), 3, DT_I8); E.stream(2, d.data(), 1, DT_I8);
         E.stream(3, z_e.data(), 3, DT_I32);
         E.stream(4, yp.data(), 3, DT_I32); E.stream(5, rp.data(), 3, DT_I8); E.stream(6, zp_e.data(), 3, DT_I32);
@@ -277,10 +280,10 @@ int main(int argc, char **argv)
             if (variant == 3) for (int b = 0; b < B; ++b) cc[(b * 2) * N + 1] += 1;
             if (variant == 4) for (int b = 0; b < B; ++b) zz[(b * 3) * N + 3] = 679537;   // norm check
             Emu E(2, L2, keyp.data(), B);
-            Prog pr(&E.K);
+            Prog pr;
             prog_norm_verify(pr, 0);
             prog_verify_first(pr, 0, 1, 2, 3, -1);
-            pr.end();
+            pr.end(); pr.install(E.K);
             E.stream(0, zz.data(), 3, DT_I32); E.stream(1, tt.data(), 1, DT_I32);
             E.stream(2, cc.data(), 2, DT_I32); E.stream(3, dd.data(), 1, DT_I8);
             E.run(B);
@@ -307,9 +310,9 @@ int main(int argc, char **argv)
         std::vector<int32_t> gx_e(B * N), cp_e(B * 2 * N), cl_e(B * 2 * N), tl_e(B * N), tp_e(B * N), w_l(B * N), wp_l(B * N), u_e(B * N);
         {
             Emu E(3, L2, keyp.data(), B);
-            Prog pr(&E.K);
+            Prog pr;
             prog_mulsum(pr, 1, 0, 1, -1, -1, 2, FIN_STORE);
-            pr.end();
+            pr.end(); pr.install(E.K);
             E.stream(0, g.data(), 1, DT_I32); E.stream(1, x.data(), 1, DT_I32); E.stream(2, gx_e.data(), 1, DT_I32);
             E.run(B);
             CHECK(same(gx_e, gx_o), "linear gx mismatch");
@@ -317,12 +320,12 @@ int main(int argc, char **argv)
         // launch B (2 primes): both commits, t, tp, w, wp
         {
             Emu E(2, L2, keyp.data(), B);
-            Prog pr(&E.K);
+            Prog pr;
             prog_commit(pr, 0, 1, 2);
             prog_commit(pr, 3, 4, 5);
             prog_keymatvec(pr, 6, 7, 8, true);
             prog_keymatvec(pr, 9, 10, 11, true);
-            pr.end();
+            pr.end(); pr.install(E.K);
             CHECK(pr.n <= kMaxOps, "too many ops %d", pr.n);
             E.stream(0, gx_e.data(), 1, DT_I32); E.stream(1, rp.data(), 3, DT_I8); E.stream(2, cp_e.data(), 2, DT_I32);
             E.stream(3, x.data(), 1, DT_I32); E.stream(4, r.data(), 3, DT_I8); E.stream(5, cl_e.data(), 2, DT_I32);
@@ -336,9 +339,9 @@ int main(int argc, char **argv)
         // launch C (3 primes): u = g*w - wp
         {
             Emu E(3, L2, keyp.data(), B);
-            Prog pr(&E.K);
+            Prog pr;
             prog_mulsum(pr, 1, 0, 1, 2, -1, 3, FIN_STORE);
-            pr.end();
+            pr.end(); pr.install(E.K);
             E.stream(0, g.data(), 1, DT_I32); E.stream(1, w_l.data(), 1, DT_I32); E.stream(2, wp_l.data(), 1, DT_I32);
             E.stream(3, u_e.data(), 1, DT_I32);
             E.run(B);
@@ -354,12 +357,12 @@ int main(int argc, char **argv)
             std::vector<int32_t> wv(B * N), wvp(B * N);
             {
                 Emu E(2, L2, keyp.data(), B);
-                Prog pr(&E.K);
+                Prog pr;
                 prog_norm_verify(pr, 0);
                 prog_norm_verify(pr, 4);
                 prog_verify_first(pr, 0, 1, 2, 3, 8);
                 prog_verify_first(pr, 4, 5, 6, 3, 9);
-                pr.end();
+                pr.end(); pr.install(E.K);
                 CHECK(pr.n <= kMaxOps, "too many ops %d", pr.n);
                 E.stream(0, zz.data(), 3, DT_I32); E.stream(1, tl_e.data(), 1, DT_I32); E.stream(2, cl_e.data(), 2, DT_I32);
                 E.stream(3, d.data(), 1, DT_I8);
@@ -371,9 +374,9 @@ int main(int argc, char **argv)
             }
             {
                 Emu E(3, L2, keyp.data(), B);
-                Prog pr(&E.K);
+                Prog pr;
                 prog_mulsum(pr, 1, 0, 1, 2, 3, -1, FIN_CMPZ);
-                pr.end();
+                pr.end(); pr.install(E.K);
                 E.stream(0, gg.data(), 1, DT_I32); E.stream(1, wv.data(), 1, DT_I32); E.stream(2, wvp.data(), 1, DT_I32);
                 E.stream(3, uu.data(), 1, DT_I32);
                 E.run(B);
@@ -406,9 +409,9 @@ int main(int argc, char **argv)
             sub[N + i] = (i & 2) ? INT32_MAX : INT32_MIN;
         }
         Emu E(3, L2, keyp.data(), B);
-        Prog pr(&E.K);
+        Prog pr;
         prog_mulsum(pr, T, 0, 1, 2, -1, 3, FIN_STORE);
-        pr.end();
+        pr.end(); pr.install(E.K);
         E.stream(0, gs.data(), T, DT_I32); E.stream(1, xs.data(), T, DT_I32); E.stream(2, sub.data(), 1, DT_I32);
         E.stream(3, out_e.data(), 1, DT_I32);
         E.run(B);
@@ -424,6 +427,83 @@ int main(int argc, char **argv)
             for (size_t i = 0; i < N; ++i) CHECK(acc[i] == out_e[b * N + i], "mulsum item %d coef %zu: %lld vs %d", b, i, (long long)acc[i], out_e[b * N + i]);
         }
         printf("mulsum T=%d ok, ops=%d\n", T, pr.n);
+    }
+
+    // ---------------- compile-time programs (vm_run_static) against the same oracle outputs ----------------
+    {
+        const int L1[1] = {0};
+        // split-key commit without the (vacuous) norm pass
+        {
+            std::vector<int32_t> c_s(B * 2 * N, 0);
+            Emu E(1, L1, keyp.data(), B, MODE_SPLITKEY);
+            SPCommitSplitKey::prog.install(E.K);
+            E.K.small_lim = 15;
+            E.stream(0, x.data(), 1, DT_I32); E.stream(1, r.data(), 3, DT_I8); E.stream(2, c_s.data(), 2, DT_I32);
+            E.run<SPCommitSplitKey>(B);
+            CHECK(same(c_s, c_o), "static split-key commit mismatch");
+            for (int b = 0; b < B; ++b) CHECK(E.flags[b] == 0, "static split-key flags");
+        }
+        // t = A1.y and (t, w)
+        {
+            std::vector<int32_t> t_s(B * N, 0), t_s2(B * N, 0), w_s(B * N, 0);
+            Emu E(2, L2, keyp.data(), B);
+            SPKeyMatVecT::prog.install(E.K);
+            E.stream(0, y.data(), 3, DT_I32); E.stream(1, t_s.data(), 1, DT_I32);
+            E.run<SPKeyMatVecT>(B);
+            CHECK(same(t_s, t_o), "static keymatvec t mismatch");
+            Emu E2(2, L2, keyp.data(), B);
+            SPKeyMatVecTW::prog.install(E2.K);
+            E2.stream(0, y.data(), 3, DT_I32); E2.stream(1, t_s2.data(), 1, DT_I32); E2.stream(2, w_s.data(), 1, DT_I32);
+            E2.run<SPKeyMatVecTW>(B);
+            CHECK(same(t_s2, t_o), "static keymatvec (t,w) t mismatch");
+            std::vector<int64_t> w_o(N);
+            for (int b = 0; b < B; ++b) {
+                rzko_mat_dot(&P, 1, 3, 1, a2.data(), y64.data() + (size_t)b * 3 * N, w_o.data());
+                for (size_t i = 0; i < N; ++i) CHECK(w_o[i] == w_s[b * N + i], "static w mismatch");
+            }
+        }
+        // respond
+        {
+            std::vector<int32_t> z_s(B * 3 * N, 0);
+            Emu E(1, L1, keyp.data(), B);
+            SPRespond::prog.install(E.K);
+            E.stream(0, y.data(), 3, DT_I32); E.stream(1, r.data(), 3, DT_I8); E.stream(2, d.data(), 1, DT_I8); E.stream(3, z_s.data(), 3, DT_I32);
+            E.run<SPRespond>(B);
+            CHECK(same(z_s, z_o), "static respond mismatch");
+        }
+        // verify (honest and tampered) with and without the w output
+        {
+            std::vector<int32_t> c32(c_o.begin(), c_o.end()), t32(t_o.begin(), t_o.end());
+            for (int variant = 0; variant < 3; ++variant) {
+                std::vector<int32_t> zz(z_e), w_s(B * N, 0);
+                if (variant == 1) for (int b = 0; b < B; ++b) zz[(b * 3 + 1) * N + 77] -= 1;
+                if (variant == 2) for (int b = 0; b < B; ++b) zz[(b * 3 + 2) * N] = 679537;
+                Emu E(2, L2, keyp.data(), B);
+                SPVerifyFirst::prog.install(E.K);
+                E.stream(0, zz.data(), 3, DT_I32); E.stream(1, t32.data(), 1, DT_I32); E.stream(2, c32.data(), 2, DT_I32); E.stream(3, d.data(), 1, DT_I8);
+                E.run<SPVerifyFirst>(B);
+                Emu E2(2, L2, keyp.data(), B);
+                SPVerifyFirstW::prog.install(E2.K);
+                E2.stream(0, zz.data(), 3, DT_I32); E2.stream(1, t32.data(), 1, DT_I32); E2.stream(2, c32.data(), 2, DT_I32); E2.stream(3, d.data(), 1, DT_I8);
+                E2.stream(4, w_s.data(), 1, DT_I32);
+                E2.run<SPVerifyFirstW>(B);
+                for (int b = 0; b < B; ++b) {
+                    CHECK((E.flags[b] == 0) == (variant == 0), "static verify variant %d item %d flags %u", variant, b, E.flags[b]);
+                    CHECK(E2.flags[b] == E.flags[b], "static verify W flags differ");
+                }
+                if (variant == 0) {        // w = A2.z - c2*d
+                    std::vector<int64_t> az(N), cd(N), wo(N);
+                    auto z64 = widen(zz);
+                    for (int b = 0; b < B; ++b) {
+                        rzko_mat_dot(&P, 1, 3, 1, a2.data(), z64.data() + (size_t)b * 3 * N, az.data());
+                        rzko_poly_mul(&P, c_o.data() + ((size_t)b * 2 + 1) * N, d64.data() + (size_t)b * N, cd.data());
+                        rzko_poly_sub(&P, az.data(), cd.data(), wo.data());
+                        for (size_t i = 0; i < N; ++i) CHECK(wo[i] == w_s[b * N + i], "static verify w mismatch");
+                    }
+                }
+            }
+        }
+        printf("static programs ok\n");
     }
 
     printf(nfail ? "EMU_CHECK FAILED (%d)\n" : "EMU_CHECK PASSED\n", nfail);
