@@ -73,19 +73,24 @@ RZK_HD uint32_t mont_mul(uint32_t a, uint32_t b, uint32_t p, uint32_t pinv)
     return hi - mh + p;
 }
 
+// `z` below is an operand that is always 0 but opaque to the compiler (it arrives as a kernel
+// parameter).  Writing the two-input adds of the butterflies as a + b + z keeps them three-input
+// IADD3 instructions on the ALU pipe; without it ptxas turns them into IMAD.IADD on the FMA-heavy
+// pipe, which is the pipe the 32-bit multiplies saturate (ncu: sm__pipe_fmaheavy_cycles_active).
+
 // Cooley-Tukey (forward) butterfly, Harvey lazy form: inputs in [0, 4p), outputs in [0, 4p).
-RZK_HD void ct_bfly(uint32_t &x, uint32_t &y, uint32_t w, uint32_t wp, uint32_t p, uint32_t p2)
+RZK_HD void ct_bfly(uint32_t &x, uint32_t &y, uint32_t w, uint32_t wp, uint32_t p, uint32_t p2, uint32_t z)
 {
     uint32_t xr = csub(x, p2);
     uint32_t t = shoup_mul(w, wp, y, p);
-    x = xr + t;
+    x = xr + t + z;
     y = xr - t + p2;
 }
 
 // Gentleman-Sande (inverse) butterfly: inputs in [0, 2p), outputs in [0, 2p).
-RZK_HD void gs_bfly(uint32_t &x, uint32_t &y, uint32_t w, uint32_t wp, uint32_t p, uint32_t p2)
+RZK_HD void gs_bfly(uint32_t &x, uint32_t &y, uint32_t w, uint32_t wp, uint32_t p, uint32_t p2, uint32_t z)
 {
-    uint32_t s = csub(x + y, p2);
+    uint32_t s = csub(x + y + z, p2);
     uint32_t d = x - y + p2;
     x = s;
     y = shoup_mul(w, wp, d, p);

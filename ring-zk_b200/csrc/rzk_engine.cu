@@ -193,7 +193,7 @@ struct rzk_engine {
     uint64_t launches = 0;
     uint32_t static_respond = 0;
     uint32_t no_static = 0;         // RZK_NO_STATIC=1 forces the generic interpreter (debugging / A-B timing)
-    uint32_t cta_sync = 1;          // keep the warps of a CTA in step (instruction-cache locality); RZK_CTA_SYNC=0 disables
+    uint32_t cta_sync = 8;          // lock-step barriers (rzk_vm_exec.cuh cta_lockstep): 8 = one per segment (measured best), 1 = per transform, 0 = off
 };
 
 namespace {
@@ -419,6 +419,10 @@ int dev_mulsum(rzk_engine *e, size_t B, uint32_t T, const int32_t *a, const int3
     if (sub0) set_stream(K, 2, sub0, 1, DT_I32);
     if (sub1) set_stream(K, 3, sub1, 1, DT_I32);
     if (out) set_stream(K, 4, out, 1, DT_I32);
+    K.loop_count = T - 1;
+    if (out && !sub0 && !sub1) return launch_sp<SPMulSum0>(e, K, s);
+    if (out && sub0 && !sub1) return launch_sp<SPMulSum1>(e, K, s);
+    if (!out && sub0 && sub1) return launch_sp<SPMulSumCmp>(e, K, s);
     return launch_np(e, 3, K, s);
 }
 

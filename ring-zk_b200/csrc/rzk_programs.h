@@ -236,4 +236,23 @@ struct SPRespond {               // streams: 0 = y, 1 = r (i8), 2 = d (i8), 3 = 
     static constexpr uint8_t dtype[kMaxStreams] = {DT_I32, DT_I8, DT_I8, DT_I32};
 };
 
+// 3-prime product sums; the loop trip count comes from K.loop_count (= T - 1) at launch.
+struct SPMulSum0 {               // streams: 0 = a, 1 = b, 4 = out            out = sum a_i*b_i
+    static constexpr int kNP = 3, kMode = 0;
+    static constexpr Prog prog = [] { Prog p; prog_mulsum(p, 2, 0, 1, -1, -1, 4, FIN_STORE); p.end(); return p; }();
+    static constexpr uint8_t dtype[kMaxStreams] = {DT_I32, DT_I32, DT_I32, DT_I32, DT_I32};
+};
+
+struct SPMulSum1 {               // streams: 0 = a, 1 = b, 2 = sub0, 4 = out  out = sum a_i*b_i - sub0
+    static constexpr int kNP = 3, kMode = 0;
+    static constexpr Prog prog = [] { Prog p; prog_mulsum(p, 2, 0, 1, 2, -1, 4, FIN_STORE); p.end(); return p; }();
+    static constexpr uint8_t dtype[kMaxStreams] = {DT_I32, DT_I32, DT_I32, DT_I32, DT_I32};
+};
+
+struct SPMulSumCmp {             // streams: 0 = a, 1 = b, 2 = sub0, 3 = sub1  sum a_i*b_i - sub0 - sub1 == 0
+    static constexpr int kNP = 3, kMode = 0;
+    static constexpr Prog prog = [] { Prog p; prog_mulsum(p, 2, 0, 1, 2, 3, -1, FIN_CMPZ); p.end(); return p; }();
+    static constexpr uint8_t dtype[kMaxStreams] = {DT_I32, DT_I32, DT_I32, DT_I32, DT_I32};
+};
+
 }  // namespace rzk

@@ -73,7 +73,7 @@ struct PrimeC {
     uint32_t rn, rnp;       // R * N^-1 mod p (R = 2^32) and its Shoup companion
     uint32_t slot;          // index into the global static prime list (selects G1 twiddles)
     uint32_t half;          // (p-1)/2
-    uint32_t pad_;
+    uint32_t pad_;          // always 0; used as the compiler-opaque zero operand `z` of the butterflies
 };
 
 struct CrtC {

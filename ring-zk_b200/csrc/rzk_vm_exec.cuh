@@ -84,6 +84,24 @@ struct LaneCtx {
     bool active;
 };
 
+#if defined(__CUDACC__)
+// Keeps warps in the same region of the (large, unrolled) program so that they share instruction
+// cache lines.  cta_sync = 1: the whole CTA; n >= 2: independent groups of 16/n... warps (named barriers),
+// which lets the groups drift apart and mix their pipe usage.
+__device__ __forceinline__ void cta_lockstep(const VmLaunch &K)
+{
+    if (K.cta_sync == 1 || K.cta_sync >= 8) {
+        __syncthreads();
+    } else if (K.cta_sync >= 2 && K.cta_sync < 8) {
+        const uint32_t warps = blockDim.x >> 5;
+        const uint32_t per = (warps + K.cta_sync - 1) / K.cta_sync;        // warps per group
+        const uint32_t grp = (threadIdx.x >> 5) / per;
+        const uint32_t cnt = min(per, warps - grp * per) * 32;
+        asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(cnt));
+    }
+}
+#endif
+
 // ---------------------------------------------------------------- transforms
 
 // One butterfly stage with compile-time geometry (all loops have constant trip counts so that
@@ -91,7 +109,7 @@ struct LaneCtx {
 //   G1 stages S = 0..4: distance 16>>S in the strided layout, lane-uniform twiddles
 //   G2 stages S = 5..8: distance 256>>S in the contiguous layout, lane-specific twiddles
 template <int S, int DIR>
-RZK_VM void g1_stage(uint32_t (&a)[kElems], const uint2 *g1, uint32_t p, uint32_t p2)
+RZK_VM void g1_stage(uint32_t (&a)[kElems], const uint2 *g1, uint32_t p, uint32_t p2, uint32_t z)
 {
     constexpr int half = 16 >> S;
     RZK_UNROLL
@@ -100,14 +118,14 @@ RZK_VM void g1_stage(uint32_t (&a)[kElems], const uint2 *g1, uint32_t p, uint32_
         RZK_UNROLL
         for (int j = 0; j < half; ++j) {
             const int i0 = b * 2 * half + j;
-            if (DIR == 0) ct_bfly(a[i0], a[i0 + half], w.x, w.y, p, p2);
-            else gs_bfly(a[i0], a[i0 + half], w.x, w.y, p, p2);
+            if (DIR == 0) ct_bfly(a[i0], a[i0 + half], w.x, w.y, p, p2, z);
+            else gs_bfly(a[i0], a[i0 + half], w.x, w.y, p, p2, z);
         }
     }
 }
 
 template <int S, int DIR>
-RZK_VM void g2_stage(uint32_t (&a)[kElems], const uint4 *tw4, uint32_t p, uint32_t p2)
+RZK_VM void g2_stage(uint32_t (&a)[kElems], const uint4 *tw4, uint32_t p, uint32_t p2, uint32_t z)
 {
     constexpr int half = 256 >> S;                // 8,4,2,1
     constexpr int nb = 1 << (S - 4);              // 2,4,8,16 blocks
@@ -118,54 +136,54 @@ RZK_VM void g2_stage(uint32_t (&a)[kElems], const uint4 *tw4, uint32_t p, uint32
         RZK_UNROLL
         for (int j = 0; j < half; ++j) {
             const int i0 = (2 * b2) * 2 * half + j;
-            if (DIR == 0) ct_bfly(a[i0], a[i0 + half], q.x, q.y, p, p2);
-            else gs_bfly(a[i0], a[i0 + half], q.x, q.y, p, p2);
+            if (DIR == 0) ct_bfly(a[i0], a[i0 + half], q.x, q.y, p, p2, z);
+            else gs_bfly(a[i0], a[i0 + half], q.x, q.y, p, p2, z);
         }
         RZK_UNROLL
         for (int j = 0; j < half; ++j) {
             const int i0 = (2 * b2 + 1) * 2 * half + j;
-            if (DIR == 0) ct_bfly(a[i0], a[i0 + half], q.z, q.w, p, p2);
-            else gs_bfly(a[i0], a[i0 + half], q.z, q.w, p, p2);
+            if (DIR == 0) ct_bfly(a[i0], a[i0 + half], q.z, q.w, p, p2, z);
+            else gs_bfly(a[i0], a[i0 + half], q.z, q.w, p, p2, z);
         }
     }
 }
 
-RZK_VM void fwd_g1(uint32_t (&a)[kElems], const uint32_t *g1tab, uint32_t p, uint32_t p2)
+RZK_VM void fwd_g1(uint32_t (&a)[kElems], const uint32_t *g1tab, uint32_t p, uint32_t p2, uint32_t z)
 {
     const uint2 *g1 = reinterpret_cast<const uint2 *>(g1tab);
-    g1_stage<0, 0>(a, g1, p, p2);
-    g1_stage<1, 0>(a, g1, p, p2);
-    g1_stage<2, 0>(a, g1, p, p2);
-    g1_stage<3, 0>(a, g1, p, p2);
-    g1_stage<4, 0>(a, g1, p, p2);
+    g1_stage<0, 0>(a, g1, p, p2, z);
+    g1_stage<1, 0>(a, g1, p, p2, z);
+    g1_stage<2, 0>(a, g1, p, p2, z);
+    g1_stage<3, 0>(a, g1, p, p2, z);
+    g1_stage<4, 0>(a, g1, p, p2, z);
 }
 
-RZK_VM void fwd_g2(uint32_t (&a)[kElems], const uint32_t *tw, uint32_t p, uint32_t p2)
+RZK_VM void fwd_g2(uint32_t (&a)[kElems], const uint32_t *tw, uint32_t p, uint32_t p2, uint32_t z)
 {
     const uint4 *tw4 = reinterpret_cast<const uint4 *>(tw);
-    g2_stage<5, 0>(a, tw4, p, p2);
-    g2_stage<6, 0>(a, tw4, p, p2);
-    g2_stage<7, 0>(a, tw4, p, p2);
-    g2_stage<8, 0>(a, tw4, p, p2);
+    g2_stage<5, 0>(a, tw4, p, p2, z);
+    g2_stage<6, 0>(a, tw4, p, p2, z);
+    g2_stage<7, 0>(a, tw4, p, p2, z);
+    g2_stage<8, 0>(a, tw4, p, p2, z);
 }
 
-RZK_VM void inv_g2(uint32_t (&a)[kElems], const uint32_t *tw, uint32_t p, uint32_t p2)
+RZK_VM void inv_g2(uint32_t (&a)[kElems], const uint32_t *tw, uint32_t p, uint32_t p2, uint32_t z)
 {
     const uint4 *tw4 = reinterpret_cast<const uint4 *>(tw);
-    g2_stage<8, 1>(a, tw4, p, p2);
-    g2_stage<7, 1>(a, tw4, p, p2);
-    g2_stage<6, 1>(a, tw4, p, p2);
-    g2_stage<5, 1>(a, tw4, p, p2);
+    g2_stage<8, 1>(a, tw4, p, p2, z);
+    g2_stage<7, 1>(a, tw4, p, p2, z);
+    g2_stage<6, 1>(a, tw4, p, p2, z);
+    g2_stage<5, 1>(a, tw4, p, p2, z);
 }
 
-RZK_VM void inv_g1(uint32_t (&a)[kElems], const uint32_t *g1tab, uint32_t p, uint32_t p2)
+RZK_VM void inv_g1(uint32_t (&a)[kElems], const uint32_t *g1tab, uint32_t p, uint32_t p2, uint32_t z)
 {
     const uint2 *g1 = reinterpret_cast<const uint2 *>(g1tab);
-    g1_stage<4, 1>(a, g1, p, p2);
-    g1_stage<3, 1>(a, g1, p, p2);
-    g1_stage<2, 1>(a, g1, p, p2);
-    g1_stage<1, 1>(a, g1, p, p2);
-    g1_stage<0, 1>(a, g1, p, p2);
+    g1_stage<4, 1>(a, g1, p, p2, z);
+    g1_stage<3, 1>(a, g1, p, p2, z);
+    g1_stage<2, 1>(a, g1, p, p2, z);
+    g1_stage<1, 1>(a, g1, p, p2, z);
+    g1_stage<0, 1>(a, g1, p, p2, z);
 }
 
 // ---------------------------------------------------------------- global memory
@@ -214,7 +232,7 @@ RZK_VM void op_fwd(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const Op
             RZK_UNROLL
             for (int m = 0; m < kElems; ++m) L.cur[m] = (uint32_t)v[m] + pc.p2;
         }
-        fwd_g1(L.cur, ctx.g1 + (L.pi * 2 + 0) * kG1Words, pc.p, pc.p2);
+        fwd_g1(L.cur, ctx.g1 + (L.pi * 2 + 0) * kG1Words, pc.p, pc.p2, pc.pad_);
         RZK_UNROLL
         for (int m = 0; m < kElems; ++m) {
             const int i = t + kLanes * m;
@@ -230,7 +248,7 @@ RZK_VM void op_fwd(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const Op
             const uint4 q = row[j];
             L.cur[4 * j + 0] = q.x; L.cur[4 * j + 1] = q.y; L.cur[4 * j + 2] = q.z; L.cur[4 * j + 3] = q.w;
         }
-        fwd_g2(L.cur, ctx.g2 + ((L.pi * 2 + 0) * kLanes + t) * kG2Words, L.pc.p, L.pc.p2);
+        fwd_g2(L.cur, ctx.g2 + ((L.pi * 2 + 0) * kLanes + t) * kG2Words, L.pc.p, L.pc.p2, L.pc.pad_);
     }
     RZK_SYNC();
 }
@@ -481,7 +499,7 @@ RZK_VM void inv_core(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const 
                 L.cur[4 * j + 0] = a.x; L.cur[4 * j + 1] = a.y; L.cur[4 * j + 2] = a.z; L.cur[4 * j + 3] = a.w;
             }
         }
-        inv_g2(L.cur, ctx.g2 + ((L.pi * 2 + 1) * kLanes + t) * kG2Words, pc.p, pc.p2);
+        inv_g2(L.cur, ctx.g2 + ((L.pi * 2 + 1) * kLanes + t) * kG2Words, pc.p, pc.p2, pc.pad_);
         uint4 *row = reinterpret_cast<uint4 *>(ctx.buf + 36 * t);
         RZK_UNROLL
         for (int j = 0; j < 8; ++j) {
@@ -499,7 +517,7 @@ RZK_VM void inv_core(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const 
             const int i = t + kLanes * m;
             L.cur[m] = ctx.buf[i + ((i >> 5) << 2)];
         }
-        inv_g1(L.cur, ctx.g1 + (L.pi * 2 + 1) * kG1Words, pc.p, pc.p2);
+        inv_g1(L.cur, ctx.g1 + (L.pi * 2 + 1) * kG1Words, pc.p, pc.p2, pc.pad_);
         RZK_UNROLL
         for (int m = 0; m < kElems; ++m) L.cur[m] = csub(L.cur[m], pc.p);     // [0,2p) -> [0,p)
     }
@@ -701,7 +719,7 @@ RZK_VM void vm_run_item(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs)
                 switch (op.code) {
                 case OP_FWD:
 #if defined(__CUDA_ARCH__)
-                    if (K.cta_sync) __syncthreads();
+                    cta_lockstep(K);
 #endif
                     op_fwd(K, lanes, ctxs, op, it, K.st[op.a].dtype);
                     break;
@@ -730,7 +748,7 @@ RZK_VM void vm_run_item(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs)
                     break;
                 case OP_INV:
 #if defined(__CUDA_ARCH__)
-                    if (K.cta_sync) __syncthreads();
+                    cta_lockstep(K);
 #endif
                     q = op_inv<NP, MODE>(K, lanes, ctxs, q, it, prime_iter);
                     continue;
@@ -834,7 +852,10 @@ RZK_VM void sp_exec(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int it,
     } else {
         if constexpr (op.code == OP_FWD) {
 #if defined(__CUDA_ARCH__)
-            if (K.cta_sync) __syncthreads();
+            // measured on B200: one barrier per forward transform (none before the inverses) is the best
+            // trade between instruction-cache locality and pipe mixing; cta_sync >= 8 keeps only the
+            // barrier at the start of each segment
+            if (K.cta_sync < 8 || SP::prog.ops[PC - 1].code == OP_SEG) cta_lockstep(K);
 #endif
             constexpr uint32_t dt = SP::dtype[op.a];
             op_fwd(K, lanes, ctxs, op, it, dt);

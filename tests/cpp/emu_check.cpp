@@ -426,6 +426,28 @@ int main(int argc, char **argv)
             rzko_poly_sub(&P, acc.data(), sub64.data() + (size_t)b * N, acc.data());
             for (size_t i = 0; i < N; ++i) CHECK(acc[i] == out_e[b * N + i], "mulsum item %d coef %zu: %lld vs %d", b, i, (long long)acc[i], out_e[b * N + i]);
         }
+        // the compile-time variant of the same program (loop count from K.loop_count)
+        {
+            std::vector<int32_t> out_s(B * N, 0);
+            Emu ES(3, L2, keyp.data(), B);
+            SPMulSum1::prog.install(ES.K);
+            ES.K.loop_count = T - 1;
+            ES.stream(0, gs.data(), T, DT_I32); ES.stream(1, xs.data(), T, DT_I32); ES.stream(2, sub.data(), 1, DT_I32);
+            ES.stream(4, out_s.data(), 1, DT_I32);
+            ES.run<SPMulSum1>(B);
+            CHECK(out_s == out_e, "static mulsum differs from the interpreted one");
+            // T = 1 through the same looped program (zero trips)
+            std::vector<int32_t> o1(B * N, 0), o2(B * N, 0);
+            Emu E1(3, L2, keyp.data(), B);
+            SPMulSum0::prog.install(E1.K);
+            E1.K.loop_count = 0;
+            E1.stream(0, gs.data(), T, DT_I32); E1.stream(1, xs.data(), T, DT_I32); E1.stream(4, o1.data(), 1, DT_I32);
+            E1.run<SPMulSum0>(B);
+            for (int b = 0; b < B; ++b) {
+                rzko_poly_mul(&P, xs64.data() + (size_t)b * T * N, gs64.data() + (size_t)b * T * N, tmp.data());
+                for (size_t i = 0; i < N; ++i) CHECK(tmp[i] == o1[b * N + i], "static mulsum T=1 mismatch");
+            }
+        }
         printf("mulsum T=%d ok, ops=%d\n", T, pr.n);
     }
 
