@@ -22,6 +22,7 @@
 #include "rzk_vm.h"
 
 #include "rzk_vm_exec.cuh"
+#include "rzk_f64.cuh"
 #include "rzk_programs.h"
 #include "rzk_tables.h"
 
@@ -32,7 +33,10 @@ using namespace rzk;
 // warps per CTA: SPLIT fits 16 warps in 128 registers; the SEQ kernels finish 32 coefficients per
 // lane in the epilogue and get a larger register budget.
 template <int NP, int MODE>
-struct VmCfg { static constexpr int kMaxWarps = (MODE != MODE_SEQ) ? 16 : (NP == 1 ? 12 : 8); };
+#ifndef RZK_SPLIT_WARPS
+#define RZK_SPLIT_WARPS 16
+#endif
+struct VmCfg { static constexpr int kMaxWarps = (MODE != MODE_SEQ) ? RZK_SPLIT_WARPS : (NP == 1 ? 12 : 8); };
 
 template <int NP, int MODE>
 struct VmSmem {
@@ -96,6 +100,13 @@ __global__ void __launch_bounds__(VmCfg<NP, MODE>::kMaxWarps * 32, 1) rzk_vm_ker
     const uint32_t first = (blockIdx.x * warps + warp) * units + (SPLIT ? 0u : (uint32_t)hw);
     const uint32_t iters = (K.n_items + per_grid - 1) / per_grid;
     Lane L;
+    uint32_t pp_count = 0;
+    ctx.pp_count = &pp_count;
+    if (K.pp_mode == 2) {
+        if (pp_group() == 1) asm volatile("bar.arrive 8, %0;" ::"r"(blockDim.x) : "memory");     // group 0 owns the first window
+    } else if (K.pp_mode != 0) {
+        if (pp_group() == 1) asm volatile("bar.sync 10, %0;" ::"r"(blockDim.x) : "memory");       // start offset
+    }
 #pragma unroll 1
     for (uint32_t it = 0; it < iters; ++it) {
         const uint32_t item = first + it * per_grid;
@@ -115,6 +126,178 @@ __global__ void __launch_bounds__(VmCfg<NP, MODE>::kMaxWarps * 32, 1) rzk_vm_ker
         }
         if constexpr (std::is_void<SP>::value) vm_run_item<NP, MODE>(K, &L, &ctx);
         else vm_run_static<SP>(K, &L, &ctx);
+    }
+    if (K.pp_mode == 2) {
+        if (pp_group() == 0) asm volatile("bar.sync 8, %0;" ::"r"(blockDim.x) : "memory");        // absorbs the last hand-over
+    } else if (K.pp_mode != 0) {
+        // a CTA whose group 0 never reached the hand-over point (no work) must still release group 1
+        if (pp_group() == 0 && pp_count < (K.pp_mode == 1 ? 1u : 2u)) asm volatile("bar.arrive 10, %0;" ::"r"(blockDim.x) : "memory");
+    }
+}
+
+// ---- commitments on the FP64 pipe (rzk_f64.cuh): one warp per item, 4 transforms modulo a 46-bit prime ----
+
+constexpr int kF64G1D = 2 * 32 * 2;                       // doubles
+constexpr int kF64G2D = 2 * kLanes * kF64G2Stride * 2;
+constexpr int kF64KeyD = kF64KeyImages * kN * 2;
+constexpr int kF64TabD = kF64G1D + kF64G2D + kF64KeyD;    // 6144 doubles = 48 KiB
+constexpr int kF64Warps = 16;
+
+static size_t f64_smem_bytes(int warps) { return sizeof(double) * ((size_t)kF64TabD + (size_t)warps * 2 * kF64BufD); }
+
+__device__ __forceinline__ void f64_stage_tables(const F64Launch &K, double *s_tab)
+{
+    const double2 *g1 = reinterpret_cast<const double2 *>(K.g1);
+    const double2 *g2 = reinterpret_cast<const double2 *>(K.g2);
+    const double2 *key = reinterpret_cast<const double2 *>(K.key);
+    double2 *d = reinterpret_cast<double2 *>(s_tab);
+    for (int w = threadIdx.x; w < kF64G1D / 2; w += blockDim.x) d[w] = g1[w];
+    d += kF64G1D / 2;
+    for (int w = threadIdx.x; w < kF64G2D / 2; w += blockDim.x) d[w] = g2[w];
+    d += kF64G2D / 2;
+    for (int w = threadIdx.x; w < kF64KeyD / 2; w += blockDim.x) d[w] = key[w];
+}
+
+__device__ __forceinline__ void f64_ctx_init(LaneCtxF &ctx, double *s_tab, double *s_buf, int warp_slot, int lane)
+{
+    const int hw = lane >> 4;
+    ctx.buf = s_buf + (size_t)(warp_slot * 2 + hw) * kF64BufD;
+    ctx.buf_partner = s_buf + (size_t)(warp_slot * 2 + (hw ^ 1)) * kF64BufD;
+    ctx.g1 = reinterpret_cast<const double2 *>(s_tab);
+    ctx.g2 = reinterpret_cast<const double2 *>(s_tab + kF64G1D);
+    ctx.key = reinterpret_cast<const double2 *>(s_tab + kF64G1D + kF64G2D);
+    ctx.t = lane & 15;
+    ctx.hw = hw;
+    ctx.ridx = lane;
+}
+
+__device__ __forceinline__ void f64_prefetch_item(const F64Launch &K, uint32_t next, int lane)
+{
+    if (next < K.n_items) {
+        const char *rb = reinterpret_cast<const char *>(K.r) + (size_t)next * 3 * kN;
+        const char *xb = reinterpret_cast<const char *>(K.x) + (size_t)next * kN * 4;
+        if (lane < 12) asm volatile("prefetch.global.L2 [%0];" ::"l"(rb + lane * 128));
+        else if (lane < 28) asm volatile("prefetch.global.L2 [%0];" ::"l"(xb + (lane - 12) * 128));
+    }
+}
+
+__global__ void __launch_bounds__(kF64Warps * 32, 1) rzk_commit_f64_kernel(const __grid_constant__ F64Launch K)
+{
+    extern __shared__ __align__(16) double smd[];
+    f64_stage_tables(K, smd);
+    __syncthreads();
+    const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    LaneCtxF ctx;
+    f64_ctx_init(ctx, smd, smd + kF64TabD, warp, lane);
+    const uint32_t per_grid = gridDim.x * warps;
+    const uint32_t first = blockIdx.x * warps + warp;
+    const uint32_t iters = (K.n_items + per_grid - 1) / per_grid;
+    LaneF L;
+#pragma unroll 1
+    for (uint32_t it = 0; it < iters; ++it) {
+        const uint32_t item = first + it * per_grid;
+        ctx.active = item < K.n_items;
+        ctx.item = ctx.active ? item : K.n_items - 1;
+        f64_prefetch_item(K, item + per_grid, lane);
+        if (K.pad_) __syncthreads();       // lock-step: one instruction-cache window per CTA (32 KB L1.5 vs ~70 KB of program)
+        f64_commit_item(K, &L, &ctx);
+    }
+}
+
+// ---- hybrid commitment kernel: both pipes at once -------------------------------------------------
+// Warps [0, wi) run the integer split-key program (FMA-heavy + ALU pipes), warps [wi, warps) run the
+// FP64 program (FP64 pipe) on different items of the same batch.  Each group claims `group size` items
+// at a time from a global counter, so the split adapts to the two paths' speeds; the group barrier of
+// the claim doubles as the lock-step barrier that keeps a group inside one instruction-cache window.
+struct HybridLaunch {
+    uint32_t *work;            // device counter, zeroed before the launch
+    uint32_t int_warps;
+    uint32_t disable;          // experiments: 1 = integer group idles, 2 = FP64 group idles
+};
+
+template <class SP>
+__global__ void __launch_bounds__(512, 1) rzk_commit_hybrid_kernel(const __grid_constant__ VmLaunch K, const __grid_constant__ F64Launch KF,
+                                                                   const __grid_constant__ HybridLaunch H)
+{
+    constexpr int NP = SP::kNP, MODE = SP::kMode;
+    extern __shared__ __align__(16) uint32_t smem[];
+    using S = VmSmem<NP, MODE>;
+    __shared__ uint32_t s_claim[2][3];     // claims are made one iteration ahead (slot it % 3) so that the next item can be prefetched
+    uint32_t *s_g1 = smem;
+    uint32_t *s_g2 = s_g1 + S::kG1;
+    uint32_t *s_key = s_g2 + S::kG2;
+    double *s_f64 = reinterpret_cast<double *>(smem + S::kTables);
+    const int nthreads = blockDim.x, warps = nthreads >> 5;
+    const int wi = (int)H.int_warps, wf = warps - wi;
+    uint32_t *s_hw = reinterpret_cast<uint32_t *>(s_f64 + kF64TabD);                       // wi int warps
+    double *s_fbuf = reinterpret_cast<double *>(s_hw + (size_t)wi * 2 * K.hw_words);       // wf FP64 warps
+
+    {   // stage the tables of both paths
+        const uint32_t slot = K.pc[0].slot;
+        const uint32_t *g1src = K.g1tab + (size_t)slot * (2 * kG1Words);
+        for (int w = threadIdx.x; w < 2 * kG1Words; w += nthreads) s_g1[w] = g1src[w];
+        const uint4 *g2src = reinterpret_cast<const uint4 *>(K.g2tab + (size_t)slot * (2 * kLanes * kG2Words));
+        uint4 *g2dst = reinterpret_cast<uint4 *>(s_g2);
+        for (int w = threadIdx.x; w < 2 * kLanes * kG2Words / 4; w += nthreads) g2dst[w] = g2src[w];
+        const uint4 *ksrc = reinterpret_cast<const uint4 *>(K.keytab);
+        uint4 *kdst = reinterpret_cast<uint4 *>(s_key);
+        for (int w = threadIdx.x; w < S::kKP * 2 * kPadWords / 4; w += nthreads) kdst[w] = ksrc[w];
+        f64_stage_tables(KF, s_f64);
+    }
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, hw = lane >> 4, t = lane & 15;
+    const uint32_t grp = warp >= wi ? 1u : 0u;
+    const uint32_t gw = grp ? (uint32_t)wf : (uint32_t)wi, wg = grp ? (uint32_t)(warp - wi) : (uint32_t)warp;
+    const bool leader = (wg == 0 && lane == 0);
+
+    if (H.disable == grp + 1) return;
+    if (grp == 0) {
+        uint32_t *mine = s_hw + (warp * 2 + hw) * K.hw_words;
+        LaneCtx ctx;
+        ctx.buf = mine;
+        ctx.slot = mine + K.off_slot;
+        ctx.slot_hw[0] = s_hw + (warp * 2 + 0) * K.hw_words + K.off_slot;
+        ctx.slot_hw[1] = s_hw + (warp * 2 + 1) * K.hw_words + K.off_slot;
+        ctx.acc1 = mine + K.off_acc1;
+        ctx.stash = mine + K.off_stash;
+        ctx.red = s_hw + (warp * 2) * K.hw_words;
+        ctx.ridx = lane;
+        ctx.g1 = s_g1; ctx.g2 = s_g2; ctx.key = s_key;
+        ctx.t = t; ctx.hw = hw;
+        uint32_t pp_count = 0;
+        ctx.pp_count = &pp_count;
+        Lane L;
+#pragma unroll 1
+        if (leader) s_claim[0][0] = atomicAdd(H.work, gw);
+        for (uint32_t it = 0;; ++it) {
+            if (leader) s_claim[0][(it + 1) % 3] = atomicAdd(H.work, gw);
+            asm volatile("bar.sync 1, %0;" ::"r"(gw * 32) : "memory");
+            const uint32_t base = s_claim[0][it % 3];
+            if (base >= K.n_items) break;
+            const uint32_t item = base + wg;
+            f64_prefetch_item(KF, s_claim[0][(it + 1) % 3] + wg, lane);
+            ctx.active = item < K.n_items;
+            ctx.item = ctx.active ? item : K.n_items - 1;
+            vm_run_static<SP>(K, &L, &ctx);
+        }
+    } else {
+        LaneCtxF ctx;
+        f64_ctx_init(ctx, s_f64, s_fbuf, (int)wg, lane);
+        LaneF L;
+#pragma unroll 1
+        if (leader) s_claim[1][0] = atomicAdd(H.work, gw);
+        for (uint32_t it = 0;; ++it) {
+            if (leader) s_claim[1][(it + 1) % 3] = atomicAdd(H.work, gw);
+            asm volatile("bar.sync 2, %0;" ::"r"(gw * 32) : "memory");
+            const uint32_t base = s_claim[1][it % 3];
+            if (base >= KF.n_items) break;
+            const uint32_t item = base + wg;
+            f64_prefetch_item(KF, s_claim[1][(it + 1) % 3] + wg, lane);
+            ctx.active = item < KF.n_items;
+            ctx.item = ctx.active ? item : KF.n_items - 1;
+            f64_commit_item(KF, &L, &ctx);
+        }
     }
 }
 
@@ -162,7 +345,7 @@ __global__ void rzk_unpack_i64_kernel(size_t n, const int32_t *__restrict__ src,
 
 namespace {
 
-constexpr int kPipe = 3;
+constexpr int kPipe = 4;
 
 struct PipeSlot {
     cudaStream_t stream = nullptr;
@@ -183,6 +366,11 @@ struct rzk_engine {
     uint32_t *d_g2tab = nullptr;
     uint32_t *d_keytab = nullptr;
     uint32_t *d_keytab2 = nullptr;  // split-key images (lo/hi) for prime slot 0, [6][2][576]
+    double *d_f64tab = nullptr;     // FP64 path: [g1 | g2 | key images] (rzk_f64.cuh)
+    uint32_t hyb_seq = 0;
+    uint32_t hyb_disable = 0;       // RZK_HYB_DISABLE (experiments)
+    uint32_t hyb_int_warps = 8;     // RZK_HYB_INT_WARPS: integer-path warps per CTA in the hybrid kernel (of 16)
+    uint32_t commit_mode = 2;       // RZK_COMMIT_MODE: 0 = integer split-key program, 1 = FP64 pipe, 2 = both pipes (hybrid; measured best)
     uint32_t *d_misc = nullptr;     // [0] range word, [1] dummy flags word
     bool has_key = false;
     uint64_t sigma = 0, cbound = 0, vbound = 0;
@@ -193,6 +381,8 @@ struct rzk_engine {
     uint64_t launches = 0;
     uint32_t static_respond = 0;
     uint32_t no_static = 0;         // RZK_NO_STATIC=1 forces the generic interpreter (debugging / A-B timing)
+    uint32_t pp_mode = 0;           // RZK_PP: phase mixing between CTA halves (rzk_vm_exec.cuh), static programs only
+    uint32_t chunk_items = 8192;    // host pipeline: items per chunk (RZK_CHUNK_ITEMS)
     uint32_t cta_sync = 8;          // lock-step barriers (rzk_vm_exec.cuh cta_lockstep): 8 = one per segment (measured best), 1 = per transform, 0 = off
 };
 
@@ -261,6 +451,7 @@ int launch_vm(rzk_engine *e, VmLaunch &K, cudaStream_t s)
     layout_hw(K, SPLIT);
     list_prefetch(K);
     K.cta_sync = e->cta_sync;
+    K.pp_mode = 0;
     const size_t max_smem = 227 * 1024;
     int warps = (int)((max_smem - VmSmem<NP, MODE>::bytes(0, 0)) / (sizeof(uint32_t) * 2 * K.hw_words));
     if (warps > VmCfg<NP, MODE>::kMaxWarps) warps = VmCfg<NP, MODE>::kMaxWarps;
@@ -268,6 +459,10 @@ int launch_vm(rzk_engine *e, VmLaunch &K, cudaStream_t s)
     // do not launch more warps per CTA than the batch can use
     const uint32_t want = (uint32_t)((K.n_items + (uint64_t)e->num_sms * per_warp - 1) / ((uint64_t)e->num_sms * per_warp));
     if ((uint32_t)warps > want) warps = (int)(want ? want : 1);
+    if (e->pp_mode && !std::is_void<SP>::value && warps >= 2 && (warps & 1) == 0) {
+        K.pp_mode = e->pp_mode;
+        K.cta_sync = (e->pp_mode == 2) ? 0u : 2u;     // strict alternation already keeps each group in step
+    }
     const size_t smem = VmSmem<NP, MODE>::bytes(warps, K.hw_words);
     static bool configured[16] = {};   // per device
     if (!configured[e->device & 15]) {
@@ -325,6 +520,81 @@ constexpr size_t kPolyBytes = (size_t)kN * sizeof(int32_t);
 
 // ---- phase lowering on device pointers (scratch supplied by the caller of these helpers) ----
 
+int launch_commit_f64(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r, int32_t *c, uint32_t *flags, uint32_t flag_div,
+                      cudaStream_t s)
+{
+    if (B == 0) return RZK_OK;
+    F64Launch K;
+    memset(&K, 0, sizeof(K));
+    K.x = x; K.r = r; K.c = c;
+    if (flags) { K.flags = flags; K.flag_div = flag_div; }
+    else { K.flags = e->d_misc + 1; K.flag_div = 0xFFFFFFFFu; }
+    K.g1 = e->d_f64tab; K.g2 = e->d_f64tab + kF64G1D; K.key = e->d_f64tab + kF64G1D + kF64G2D;
+    K.q = (double)e->P.q; K.qinv = 1.0 / (double)e->P.q; K.pinv = 1.0 / kF64P;
+    K.n_items = (uint32_t)B; K.small_lim = kF64SmallLimit;
+    K.pad_ = e->cta_sync ? 1u : 0u;      // lock-step barrier per item
+    int warps = kF64Warps;
+    const uint32_t want = (uint32_t)((B + (uint64_t)e->num_sms - 1) / (uint64_t)e->num_sms);
+    if ((uint32_t)warps > want) warps = (int)(want ? want : 1);
+    static bool configured[16] = {};
+    if (!configured[e->device & 15]) {
+        RZK_CUDA(e, cudaFuncSetAttribute(rzk_commit_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f64_smem_bytes(kF64Warps)));
+        configured[e->device & 15] = true;
+    }
+    uint32_t grid = (uint32_t)((B + warps - 1) / warps);
+    if (grid > (uint32_t)e->num_sms) grid = (uint32_t)e->num_sms;
+    rzk_commit_f64_kernel<<<grid, warps * 32, f64_smem_bytes(warps), s>>>(K);
+    RZK_CUDA(e, cudaGetLastError());
+    e->launches++;
+    return RZK_OK;
+}
+
+void fill_f64(rzk_engine *e, F64Launch &K, size_t B, const int32_t *x, const int8_t *r, int32_t *c, uint32_t *flags, uint32_t flag_div)
+{
+    memset(&K, 0, sizeof(K));
+    K.x = x; K.r = r; K.c = c;
+    if (flags) { K.flags = flags; K.flag_div = flag_div; }
+    else { K.flags = e->d_misc + 1; K.flag_div = 0xFFFFFFFFu; }
+    K.g1 = e->d_f64tab; K.g2 = e->d_f64tab + kF64G1D; K.key = e->d_f64tab + kF64G1D + kF64G2D;
+    K.q = (double)e->P.q; K.qinv = 1.0 / (double)e->P.q; K.pinv = 1.0 / kF64P;
+    K.n_items = (uint32_t)B; K.small_lim = kF64SmallLimit;
+    K.pad_ = e->cta_sync ? 1u : 0u;
+}
+
+// K: a filled launch of the split-key commit program (streams, constants, flags)
+int launch_commit_hybrid(rzk_engine *e, VmLaunch &K, size_t B, const int32_t *x, const int8_t *r, int32_t *c, uint32_t *flags,
+                         uint32_t flag_div, cudaStream_t s)
+{
+    using SP = SPCommitSplitKey;
+    auto kern = rzk_commit_hybrid_kernel<SP>;
+    layout_hw(K, true);
+    K.n_prefetch = 0;
+    K.cta_sync = 0;
+    K.pp_mode = 0;
+    F64Launch KF;
+    fill_f64(e, KF, B, x, r, c, flags, flag_div);
+    HybridLaunch H;
+    const int warps = 16;
+    H.int_warps = std::min<uint32_t>(std::max<uint32_t>(e->hyb_int_warps, 1), warps - 1);
+    // one counter per launch in flight on a stream: zeroed by a memset ordered before the kernel
+    H.work = e->d_misc + 2 + (e->hyb_seq++ & 7);
+    H.disable = e->hyb_disable;
+    RZK_CUDA(e, cudaMemsetAsync(H.work, 0, sizeof(uint32_t), s));
+    const size_t smem = sizeof(uint32_t) * (size_t)VmSmem<1, MODE_SPLITKEY>::kTables + sizeof(double) * kF64TabD +
+                        sizeof(uint32_t) * (size_t)H.int_warps * 2 * K.hw_words + sizeof(double) * (size_t)(warps - H.int_warps) * 2 * kF64BufD;
+    static bool configured[16] = {};
+    if (!configured[e->device & 15]) {
+        RZK_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));   // 16 B of static smem
+        configured[e->device & 15] = true;
+    }
+    uint32_t grid = (uint32_t)((B + 7) / 8);
+    if (grid > (uint32_t)e->num_sms) grid = (uint32_t)e->num_sms;
+    kern<<<grid, warps * 32, smem, s>>>(K, KF, H);
+    RZK_CUDA(e, cudaGetLastError());
+    e->launches++;
+    return RZK_OK;
+}
+
 constexpr uint32_t kSplitKeyLimit = 15;    // |r| bound of MODE_SPLITKEY: 2*512*2^15*15 < p/2
 
 // generic = true: two-prime program, exact for any int8 r.
@@ -344,8 +614,10 @@ int dev_commit(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r, int32
     fill_common(e, K, generic ? 2 : 1, (uint32_t)B, flag_div, flags);
     set_stream(K, 0, x, 1, DT_I32); set_stream(K, 1, r, 3, DT_I8); set_stream(K, 2, c, 2, DT_I32);
     if (generic) return launch_np(e, 2, K, s);
+    if (e->commit_mode == 1 && norm_vacuous) return launch_commit_f64(e, B, x, r, c, flags, flag_div, s);
     K.small_lim = kSplitKeyLimit;
     K.keytab = e->d_keytab2;
+    if (e->commit_mode == 2 && norm_vacuous && B >= 4096) return launch_commit_hybrid(e, K, B, x, r, c, flags, flag_div, s);
     if (norm_vacuous) return launch_sp<SPCommitSplitKey>(e, K, s);
     return launch_vm<1, MODE_SPLITKEY>(e, K, s);
 }
@@ -497,7 +769,7 @@ int run_chunked(rzk_engine *e, size_t B, std::vector<HArr> &arrs, size_t scratch
     size_t per_item = scratch_per_item + sizeof(uint32_t) + 1;
     for (auto &a : arrs) per_item += a.per_item;
     size_t chunk = (size_t)(96ull << 20) / per_item;
-    chunk = std::max<size_t>(8, std::min<size_t>(chunk, 16384)) / 8 * 8;
+    chunk = std::max<size_t>(8, std::min<size_t>(chunk, e->chunk_items)) / 8 * 8;
     if (chunk > B) chunk = align_up(B, 8);
     // arena layout for one pipeline slot
     std::vector<size_t> offs(arrs.size());
@@ -602,6 +874,11 @@ int rzk_create(const rzk_params *params, int device, rzk_engine **out)
     e->device = device;
     if (const char *cs = getenv("RZK_CTA_SYNC")) e->cta_sync = (uint32_t)atoi(cs);
     if (const char *cs = getenv("RZK_NO_STATIC")) e->no_static = (uint32_t)atoi(cs);
+    if (const char *cs = getenv("RZK_COMMIT_MODE")) e->commit_mode = (uint32_t)atoi(cs);
+    if (const char *cs = getenv("RZK_HYB_DISABLE")) e->hyb_disable = (uint32_t)atoi(cs);
+    if (const char *cs = getenv("RZK_HYB_INT_WARPS")) e->hyb_int_warps = (uint32_t)atoi(cs);
+    if (const char *cs = getenv("RZK_PP")) e->pp_mode = (uint32_t)atoi(cs);
+    if (const char *cs = getenv("RZK_CHUNK_ITEMS")) e->chunk_items = (uint32_t)std::max(8, atoi(cs));
     Guard g(device);
     cudaDeviceProp prop;
     ce = cudaGetDeviceProperties(&prop, device);
@@ -636,6 +913,14 @@ int rzk_create(const rzk_params *params, int device, rzk_engine **out)
     if (rc == RZK_OK) cu(cudaMemcpy(e->d_g2tab, g2.data(), g2.size() * sizeof(uint32_t), cudaMemcpyHostToDevice), "cudaMemcpy(g2)");
     cu(cudaMalloc(&e->d_keytab, (size_t)kNumPrimeSlots * kKeyPolys * 2 * kPadWords * sizeof(uint32_t)), "cudaMalloc(key)");
     cu(cudaMalloc(&e->d_keytab2, (size_t)2 * kKeyPolys * 2 * kPadWords * sizeof(uint32_t)), "cudaMalloc(key2)");
+    cu(cudaMalloc(&e->d_f64tab, sizeof(double) * kF64TabD), "cudaMalloc(f64tab)");
+    if (rc == RZK_OK) {
+        const F64Tables &FT = f64_tables();
+        std::vector<double> tab(kF64G1D + kF64G2D);
+        memcpy(tab.data(), FT.g1, sizeof(FT.g1));
+        memcpy(tab.data() + kF64G1D, FT.g2, sizeof(FT.g2));
+        cu(cudaMemcpy(e->d_f64tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice), "cudaMemcpy(f64tab)");
+    }
     cu(cudaMalloc(&e->d_misc, 64), "cudaMalloc(misc)");
     if (rc == RZK_OK) cu(cudaMemset(e->d_misc, 0, 64), "cudaMemset(misc)");
     for (int i = 0; i < kPipe && rc == RZK_OK; ++i) cu(cudaStreamCreateWithFlags(&e->pipe[i].stream, cudaStreamNonBlocking), "cudaStreamCreate");
@@ -658,6 +943,7 @@ void rzk_destroy(rzk_engine *e)
     if (e->d_g2tab) cudaFree(e->d_g2tab);
     if (e->d_keytab) cudaFree(e->d_keytab);
     if (e->d_keytab2) cudaFree(e->d_keytab2);
+    if (e->d_f64tab) cudaFree(e->d_f64tab);
     if (e->d_misc) cudaFree(e->d_misc);
     delete e;
 }
@@ -701,7 +987,18 @@ int rzk_set_key(rzk_engine *e, const int64_t *a1, const int64_t *a2)
         }
         key_image_split(prime_tables(0), cen.data(), &img2[(size_t)kk * 4 * kPadWords]);
     }
+    std::vector<double> img64((size_t)kF64KeyD);
+    for (int kk = 0; kk < kKeyPolys; ++kk) {
+        for (int i = 0; i < kN; ++i) {
+            int64_t r = polys[kk][i] % q;
+            if (r > half) r -= q; else if (r < -half) r += q;
+            cen[i] = r;
+        }
+        f64_key_image(cen.data(), &img64[(size_t)kk * kN * 2]);
+    }
+    f64_key_image(nullptr, &img64[(size_t)kKeyPolys * kN * 2]);
     RZK_CUDA(e, cudaDeviceSynchronize());
+    RZK_CUDA(e, cudaMemcpy(e->d_f64tab + kF64G1D + kF64G2D, img64.data(), img64.size() * sizeof(double), cudaMemcpyHostToDevice));
     RZK_CUDA(e, cudaMemcpy(e->d_keytab, img.data(), img.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     RZK_CUDA(e, cudaMemcpy(e->d_keytab2, img2.data(), img2.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     e->has_key = true;

@@ -117,6 +117,7 @@ struct VmLaunch {
     uint8_t prefetch[8];
     uint32_t cta_sync;         // keep the warps of a CTA in step (instruction-cache locality)
     uint32_t loop_count;       // trip count of OP_LOOP in compile-time programs (terms of a Sum proof - 1)
+    uint32_t pp_mode;          // phase mixing between the two halves of a CTA (rzk_vm_exec.cuh pp_acquire); 0 = off
     uint32_t alias_slot;       // the operand slot may overlay the transpose buffer (programs whose OP_LDs all
                                // precede the inverse transforms and that never use OP_MACV)
 };

@@ -82,6 +82,7 @@ struct LaneCtx {
     int hw;                // half warp within the warp, 0..1
     int ridx;              // index of this lane among the lanes that own the item
     bool active;
+    uint32_t *pp_count;    // device: releases of heavy windows executed so far by this warp (pp_mode 1 / 3)
 };
 
 #if defined(__CUDACC__)
@@ -98,6 +99,33 @@ __device__ __forceinline__ void cta_lockstep(const VmLaunch &K)
         const uint32_t grp = (threadIdx.x >> 5) / per;
         const uint32_t cnt = min(per, warps - grp * per) * 32;
         asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(cnt));
+    }
+}
+
+// Phase mixing between the two halves of a CTA ("ping-pong", K.pp_mode):
+// the multiply-heavy windows (forward transform; inverse transform) saturate the FMA-heavy pipe while
+// the windows between them (global loads, int8 conversion, CRT / reduction mod q, stores) leave it idle.
+// With all warps in the same window at the same time (lock-step, needed for instruction-cache
+// locality: 32 KB L1.5 vs ~80 KB of unrolled program) the pipe idles about a third of the time.
+// Two groups of warps, each internally in step, run half an item apart instead:
+//   pp_mode 2: strict alternation -- a group enters a heavy window only when the other group has left
+//              its own (named barriers 8 + g: 256 threads sync, the other 256 arrive);
+//   pp_mode 1 / 3: free running after an initial offset (group 1 starts when group 0 leaves its
+//              first / second heavy window).
+__device__ __forceinline__ uint32_t pp_group() { return (threadIdx.x >> 5) >= (blockDim.x >> 6) ? 1u : 0u; }
+
+__device__ __forceinline__ void pp_acquire(const VmLaunch &K)
+{
+    if (K.pp_mode == 2) asm volatile("bar.sync %0, %1;" ::"r"(8u + pp_group()), "r"(blockDim.x) : "memory");
+}
+
+__device__ __forceinline__ void pp_release(const VmLaunch &K, uint32_t &pp_count)
+{
+    if (K.pp_mode == 2) asm volatile("bar.arrive %0, %1;" ::"r"(8u + (pp_group() ^ 1u)), "r"(blockDim.x) : "memory");
+    else if (K.pp_mode != 0) {
+        ++pp_count;
+        if (pp_count == (K.pp_mode == 1 ? 1u : 2u) && pp_group() == 0)
+            asm volatile("bar.arrive 10, %0;" ::"r"(blockDim.x) : "memory");
     }
 }
 #endif
@@ -232,6 +260,9 @@ RZK_VM void op_fwd(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const Op
             RZK_UNROLL
             for (int m = 0; m < kElems; ++m) L.cur[m] = (uint32_t)v[m] + pc.p2;
         }
+#if defined(__CUDA_ARCH__)
+        pp_acquire(K);
+#endif
         fwd_g1(L.cur, ctx.g1 + (L.pi * 2 + 0) * kG1Words, pc.p, pc.p2, pc.pad_);
         RZK_UNROLL
         for (int m = 0; m < kElems; ++m) {
@@ -251,6 +282,9 @@ RZK_VM void op_fwd(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const Op
         fwd_g2(L.cur, ctx.g2 + ((L.pi * 2 + 0) * kLanes + t) * kG2Words, L.pc.p, L.pc.p2, L.pc.pad_);
     }
     RZK_SYNC();
+#if defined(__CUDA_ARCH__)
+    pp_release(K, *ctxs[0].pp_count);
+#endif
 }
 
 // acc (+)= key (.) cur ; key rows pre-scaled by N^-1, Shoup form
@@ -485,6 +519,9 @@ RZK_VM void inv_core(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const 
 {
     constexpr int CNT = Epi<MODE>::kCount;
     RZK_SYNC();      // every OP_LD of the partner half warp has finished (the slot may overlay this buffer)
+#if defined(__CUDA_ARCH__)
+    pp_acquire(K);
+#endif
     RZK_EACH_LANE {
         RZK_LANE;
         const PrimeC &pc = L.pc;
@@ -522,6 +559,9 @@ RZK_VM void inv_core(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const 
         for (int m = 0; m < kElems; ++m) L.cur[m] = csub(L.cur[m], pc.p);     // [0,2p) -> [0,p)
     }
     RZK_SYNC();
+#if defined(__CUDA_ARCH__)
+    pp_release(K, *ctxs[0].pp_count);
+#endif
     if (MODE != MODE_SEQ) {
         // MODE_SPLIT: half warp 0 holds residues mod p0, half warp 1 mod p1, both for all 512
         // coefficients.  MODE_SPLITKEY: half warp 0 holds the lo part, half warp 1 the hi part.

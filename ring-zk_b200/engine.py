@@ -18,7 +18,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "_build", "libringzk_b200.so")
+LIB_PATH = os.environ.get("RZK_LIB_PATH") or os.path.join(_HERE, "_build", "libringzk_b200.so")   # RZK_LIB_PATH: A/B builds during development
 
 RZK_OK, RZK_ERR_INVALID, RZK_ERR_UNSUPPORTED, RZK_ERR_CUDA, RZK_ERR_RANGE, RZK_ERR_NOKEY = range(6)
 _ERRNAMES = {1: "RZK_ERR_INVALID", 2: "RZK_ERR_UNSUPPORTED", 3: "RZK_ERR_CUDA", 4: "RZK_ERR_RANGE", 5: "RZK_ERR_NOKEY"}

@@ -15,6 +15,7 @@
 
 #include "../../ring-zk_b200/csrc/rzk_vm_exec.cuh"
 #include "../../ring-zk_b200/csrc/rzk_programs.h"
+#include "../../ring-zk_b200/csrc/rzk_f64.cuh"
 #include "../../ring-zk_b200/csrc/rzk_tables.h"
 extern "C" {
 #include "../../oracle/ringzk_oracle.h"
@@ -526,6 +527,61 @@ int main(int argc, char **argv)
             }
         }
         printf("static programs ok\n");
+    }
+
+    // ---------------- FP64-pipe commitment (rzk_f64.cuh): one 46-bit prime, 4 transforms ----------------
+    {
+        const F64Tables &FT = f64_tables();
+        std::vector<double> kimg((size_t)kF64KeyImages * kN * 2);
+        for (int k = 0; k < 3; ++k) f64_key_image(keyp.data() + (size_t)k * kN, &kimg[(size_t)k * kN * 2]);
+        f64_key_image(nullptr, &kimg[(size_t)3 * kN * 2]);
+        std::vector<double> bufs(2 * kF64BufD, -1.0);
+        for (int variant = 0; variant < 3; ++variant) {
+            std::vector<int8_t> rr(r);
+            std::vector<int32_t> xx(x);
+            if (variant >= 1) {          // worst case of the bound: |r| = 15 everywhere on the transformed rows
+                for (size_t i = 0; i < rr.size(); ++i) rr[i] = (int8_t)((int)(rnd() % 31) - 15);
+                for (size_t i = N; i < 3 * N; ++i) rr[i] = (i & 1) ? 15 : -15;
+                for (size_t i = 0; i < N; ++i) xx[i] = (i % 3 == 0) ? INT32_MIN : (i % 3 == 1) ? INT32_MAX : xx[i];   // any int32 representative
+            }
+            if (variant == 2) { rr[2 * N + 3] = 16; if (B > 1) rr[(size_t)3 * N + 5] = 100; }   // range flag on item 0 only
+            std::vector<int32_t> c_f(B * 2 * N, 0);
+            std::vector<uint32_t> fl(B, 0);
+            F64Launch K;
+            memset(&K, 0, sizeof(K));
+            K.x = xx.data(); K.r = rr.data(); K.c = c_f.data(); K.flags = fl.data();
+            K.q = (double)Q; K.qinv = 1.0 / (double)Q; K.pinv = 1.0 / kF64P;
+            K.n_items = B; K.flag_div = 1; K.small_lim = kF64SmallLimit;
+            static LaneF lanes[32];
+            static LaneCtxF ctxs[32];
+            for (int b = 0; b < B; ++b) {
+                for (int li = 0; li < 32; ++li) {
+                    LaneCtxF &c = ctxs[li];
+                    c.hw = li >> 4; c.t = li & 15; c.ridx = li;
+                    c.buf = bufs.data() + (size_t)c.hw * kF64BufD;
+                    c.buf_partner = bufs.data() + (size_t)(c.hw ^ 1) * kF64BufD;
+                    c.g1 = reinterpret_cast<const double2 *>(&FT.g1[0][0][0]);
+                    c.g2 = reinterpret_cast<const double2 *>(&FT.g2[0][0][0][0]);
+                    c.key = reinterpret_cast<const double2 *>(kimg.data());
+                    c.item = b; c.active = true;
+                }
+                f64_commit_item(K, lanes, ctxs);
+            }
+            auto rr64 = widen8(rr);
+            auto xx64 = widen(xx);
+            for (auto &v : xx64) v = rzko_center(v, Q);
+            std::vector<int64_t> c2(B * 2 * N);
+            std::vector<uint8_t> ok2(B);
+            rzko_commit_batch(&P, a1.data(), a2.data(), B, xx64.data(), rr64.data(), c2.data(), ok2.data(), 1);
+            if (variant < 2) {
+                CHECK(same(c_f, c2), "FP64 commit mismatch (variant %d)", variant);
+                for (int b = 0; b < B; ++b) CHECK(fl[b] == 0, "FP64 commit flags[%d]=%u", b, fl[b]);
+            } else {
+                CHECK(fl[0] == FLAG_RANGE, "FP64 range flag item 0: %u", fl[0]);
+                if (B > 1) CHECK(fl[1] == 0, "FP64 range flag item 1: %u", fl[1]);
+            }
+        }
+        printf("FP64 commit ok\n");
     }
 
     printf(nfail ? "EMU_CHECK FAILED (%d)\n" : "EMU_CHECK PASSED\n", nfail);

@@ -270,3 +270,33 @@ def test_full_size_properties(setup):
     assert not v[::1000].any() and v.sum() == B - len(range(0, B, 1000))
     t_o = o.open_commit_batch(x1[idx], r1[idx], y[idx])[1]
     assert (t[idx] == t_o).all()
+
+
+@pytest.mark.parametrize("mode,B", [(0, 300), (1, 300), (1, 5000), (2, 5000)])
+def test_commit_execution_modes(mode, B, monkeypatch):
+    """The three commitment kernels -- integer split-key program (0), FP64-pipe program (1), both pipes in
+    one launch (2, used from 4096 items) -- are bit-exact against the oracle, including the |r| = 15 edge of
+    their shared range and arbitrary int32 representatives of x; |r| = 16 falls back to the generic program."""
+    monkeypatch.setenv("RZK_COMMIT_MODE", str(mode))
+    s = synth.Synth(77 + mode, N=N)
+    a1p, a2p = s.key()
+    eng = engine.Engine(N=N, device=0)
+    try:
+        eng.set_key_blocks(a1p, a2p)
+        o = orc.Oracle(orc.Params(N=N), a1p, a2p)
+        rng = np.random.default_rng(5)
+        x, r = s.message(B, ragged=True), s.small(B)
+        r[1] = rng.integers(-15, 16, size=r[1].shape)
+        r[2, 1:] = 15; r[3, 1:] = -15
+        x[4, 0, ::3] = np.int32(2 ** 31 - 1); x[4, 0, 1::3] = np.int32(-2 ** 31)
+        c, ok = eng.commit(x, r)
+        c_o, ok_o = o.commit_batch(o.center(x.astype(np.int64)).astype(np.int32), r)
+        assert (c == c_o).all() and UB(ok, B).all()
+        launched = eng.kernel_launches()
+        r[7, 2, 100] = 16                       # outside the one-word range: redone by the two-prime program
+        c2, ok2 = eng.commit(x, r)
+        c2_o, _ = o.commit_batch(o.center(x.astype(np.int64)).astype(np.int32), r)
+        assert (c2 == c2_o).all() and UB(ok2, B).all()
+        assert eng.kernel_launches() > launched
+    finally:
+        eng.close()
