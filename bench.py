@@ -33,7 +33,8 @@ BATCH = 1 << 16
 ALG_BYTES_COMMIT = 12288       # 4 polys in + 2 out at 4 B/coeff
 ALG_BYTES_VERIFY = 12288       # 6 polys in
 ALG_MULMODS_COMMIT = 21504
-MEASURED_MULMOD_TPS = 4.617     # T Shoup-mulmods/s, profiles/r1_imad_bench.jsonl
+MEASURED_MULMOD_TPS = 4.617     # T Shoup-mulmods/s on the integer pipes, profiles/r1_imad_bench.jsonl
+MEASURED_F64_MULMOD_TPS = 3.057  # T FP64 mulmods/s (6 DP ops each) on the FP64 pipe, profiles/r1b_imad_fp64_bench.jsonl
 METRIC = "commitments/s"
 UNIT = "commitments/s"
 WORKLOAD = "configs[1]: batched commitment generation, 2^16 messages/GPU at N=512, Params::default(), one shared key"
@@ -278,9 +279,11 @@ def main():
     peak, peak_src = measured_peaks()
     achieved = ALG_BYTES_COMMIT * B / (ms_k * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic("commit"), "kernel": "rzk_vm_kernel<1, MODE_SPLITKEY, SPCommitSplitKey>",
+                "traffic": ncu_traffic("commit"),
+                "kernel": "rzk_commit_hybrid_kernel<SPCommitSplitKey> (per CTA: 8 warps integer split-key program + 8 warps FP64-pipe program)",
                 "kernel_ms": ms_k, "algorithmic_bytes_per_launch": ALG_BYTES_COMMIT * B, "peak_source": peak_src,
-                "note": "integer-pipe bound path: 21504 modular multiplies per commitment; see DESIGN.md"}
+                "note": "arithmetic-pipe bound path (21504 modular multiplies per commitment by SURVEY.md 8(d)): "
+                        "the kernel runs the FMA-heavy (integer) and the FP64 pipes side by side; see int_roofline and DESIGN.md"}
 
     # ---- second half of the metric: open-proof verifies/s (config 3) ----
     eng.dev("open_commit_batch", B, x, r, y, c, t, flags, stream=stream)
@@ -329,7 +332,7 @@ def main():
         assert bool((ch.to(dev) == c).all()), "host-path and device-path commitments differ"
         e2e = {"value": world * B * ksteps / dt, "unit": UNIT,
                "h2d_bytes_per_step": B * (N * 4 + 3 * N), "d2h_bytes_per_step": B * 2 * N * 4 + (B + 7) // 8,
-               "steps": ksteps, "api": "rzk_commit_batch (host pointers, pinned), chunked 3-stream pipeline"}
+               "steps": ksteps, "api": "rzk_commit_batch (host pointers, pinned), chunked 4-stream pipeline (8192 items per chunk)"}
 
     # ---- CPU baseline (rank 0, N=1 only) ----
     cpu = None
@@ -357,7 +360,10 @@ def main():
                              "peak_Tmulmod_s": MEASURED_MULMOD_TPS,
                              "frac": ALG_MULMODS_COMMIT * B / (ms_k * 1e-3) / (MEASURED_MULMOD_TPS * 1e12),
                              "peak_source": "measured Shoup mulmod rate on this pool's B200 (tools/imad_bench.cu, "
-                                            "profiles/r1_imad_bench.jsonl); algorithmic mulmods per SURVEY.md 8(d)"},
+                                            "profiles/r1_imad_bench.jsonl); algorithmic mulmods per SURVEY.md 8(d)",
+                             "fp64_pipe_peak_Tmulmod_s": MEASURED_F64_MULMOD_TPS,
+                             "frac_of_both_pipes": ALG_MULMODS_COMMIT * B / (ms_k * 1e-3) /
+                                                   ((MEASURED_MULMOD_TPS + MEASURED_F64_MULMOD_TPS) * 1e12)},
         }
         print(json.dumps(line), flush=True)
     eng.close()

@@ -89,6 +89,13 @@ int rzk_sync(rzk_engine *e, void *stream);
 int rzk_commit_batch(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r,
                      int32_t *c, uint8_t *ok_bitmap);
 
+/* Commitment::verify (commit.rs:173-210): check_commit_constraint(r), then
+ *   f == NULL (Opening.f = None):  [a1;a2].r + [0;x] == c
+ *   f != NULL (Some(f)):           f*c == [a1;a2].r + f*[0;x]          f [B][N] i8 (challenge-space polynomial)
+ *   c [B][2][N] i32, x [B][1][N] i32, r [B][3][N] i8; bit i of the bitmap = the reference's bool. */
+int rzk_commitment_verify_batch(rzk_engine *e, size_t B, const int32_t *c, const int32_t *x,
+                                const int8_t *r, const int8_t *f, uint8_t *verify_bitmap);
+
 /* ---------------------------------------------------------------- Open proof
  * OpenProofProver::commit (open.rs:80-103): commitment c plus t = A1.y.   y [B][3][N] i32, t [B][1][N] */
 int rzk_open_commit_batch(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r,
@@ -142,6 +149,8 @@ int rzk_sum_verify_batch(rzk_engine *e, size_t B, uint32_t T, const int32_t *zs,
  * polynomials per item in the commitment array handed to verify (1: c1 only, 2: full c). */
 int rzk_commit_batch_dev(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r,
                          int32_t *c, uint32_t *flags, void *stream);
+int rzk_commitment_verify_batch_dev(rzk_engine *e, size_t B, const int32_t *c, const int32_t *x,
+                                    const int8_t *r, const int8_t *f, uint32_t *flags, void *stream);
 int rzk_open_commit_batch_dev(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r,
                               const int32_t *y, int32_t *c, int32_t *t, uint32_t *flags, void *stream);
 int rzk_open_respond_batch_dev(rzk_engine *e, size_t B, const int32_t *y, const int8_t *r,

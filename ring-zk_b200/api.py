@@ -93,10 +93,18 @@ class Commitment:  # commit.rs:135-141
     c: np.ndarray          # [(n+l)][N]
 
     def verify(self, opening: Opening, ck: "CommitmentKey", params: Params) -> bool:  # commit.rs:173-210
-        if opening.f is not None:
-            raise NotImplementedError("randomised openings (Some(f)) are scope row f3 of SURVEY.md 8(f)")
-        c, ok = ck.engine.commit(opening.x[None].astype(np.int32), opening.r[None].astype(np.int8))
-        return bool(_engine.unpack_bitmap(ok, 1)[0]) and bool((c[0] == self.c).all())
+        f = None if opening.f is None else np.ascontiguousarray(opening.f, np.int8)[None]
+        bm = ck.engine.commitment_verify(np.ascontiguousarray(self.c, np.int32)[None], opening.x[None].astype(np.int32),
+                                         opening.r[None].astype(np.int8), f)
+        return bool(_engine.unpack_bitmap(bm, 1)[0])
+
+    @staticmethod
+    def verify_batch(C, X, R, ck: "CommitmentKey", F=None):
+        """Batched Commitment::verify: C [B][n+l][N], X [B][l][N], R [B][k][N] int8, F None or [B][N] int8."""
+        B = C.shape[0]
+        return _engine.unpack_bitmap(ck.engine.commitment_verify(np.ascontiguousarray(C, np.int32), np.ascontiguousarray(X, np.int32),
+                                                                 np.ascontiguousarray(R, np.int8),
+                                                                 None if F is None else np.ascontiguousarray(F, np.int8)), B)
 
     def c1_c2(self, params: Params):  # commit.rs:213-218
         m = self.c.shape[0]

@@ -677,6 +677,21 @@ int dev_verify_first(rzk_engine *e, size_t items, const int32_t *z, const int32_
     return w ? launch_sp<SPVerifyFirstW>(e, K, s) : launch_sp<SPVerifyFirst>(e, K, s);
 }
 
+// Commitment::verify (commit.rs:173-210); f == nullptr is the `None` branch
+int dev_commitment_verify(rzk_engine *e, size_t B, const int32_t *c, const int32_t *x, const int8_t *r, const int8_t *f,
+                          uint32_t *flags, cudaStream_t s)
+{
+    VmLaunch K; memset(&K, 0, sizeof(K));
+    Prog p;
+    prog_commitment_verify(p, 0, 1, 2, f ? 3 : -1);
+    p.end();
+    p.install(K);
+    fill_common(e, K, 2, (uint32_t)B, 1, flags);
+    set_stream(K, 0, c, 2, DT_I32); set_stream(K, 1, x, 1, DT_I32); set_stream(K, 2, r, 3, DT_I8);
+    if (f) set_stream(K, 3, f, 1, DT_I8);
+    return launch_np(e, 2, K, s);
+}
+
 // out = sum_{i<T} a_i*b_i - sub0 - sub1 (store) or == 0 (compare)
 int dev_mulsum(rzk_engine *e, size_t B, uint32_t T, const int32_t *a, const int32_t *b, const int32_t *sub0,
                const int32_t *sub1, int32_t *out, uint32_t *flags, cudaStream_t s)
@@ -1032,6 +1047,15 @@ int rzk_commit_batch_dev(rzk_engine *e, size_t B, const int32_t *x, const int8_t
     return dev_commit(e, B, x, r, c, flags, (cudaStream_t)stream);
 }
 
+int rzk_commitment_verify_batch_dev(rzk_engine *e, size_t B, const int32_t *c, const int32_t *x, const int8_t *r, const int8_t *f,
+                                    uint32_t *flags, void *stream)
+{
+    RZK_TRY(check_ready(e));
+    if (any_null({c, x, r, flags})) return fail(e, RZK_ERR_INVALID, "null argument");
+    Guard g(e->device);
+    return dev_commitment_verify(e, B, c, x, r, f, flags, (cudaStream_t)stream);
+}
+
 int rzk_open_commit_batch_dev(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r, const int32_t *y,
                               int32_t *c, int32_t *t, uint32_t *flags, void *stream)
 {
@@ -1181,6 +1205,18 @@ int rzk_open_respond_batch(rzk_engine *e, size_t B, const int32_t *y, const int8
     std::vector<HArr> a = {{y, nullptr, 3 * kPolyBytes}, {r, nullptr, 3 * kN}, {dch, nullptr, kN}, {nullptr, z, 3 * kPolyBytes}};
     return run_chunked(e, B, a, 0, nullptr, [&](size_t n, void **d, char *, uint32_t *, cudaStream_t s) {
         return dev_respond(e, n, (const int32_t *)d[0], (const int8_t *)d[1], (const int8_t *)d[2], 1, (int32_t *)d[3], s);
+    });
+}
+
+int rzk_commitment_verify_batch(rzk_engine *e, size_t B, const int32_t *c, const int32_t *x, const int8_t *r, const int8_t *f, uint8_t *bm)
+{
+    RZK_TRY(check_ready(e));
+    if (any_null({c, x, r, bm})) return fail(e, RZK_ERR_INVALID, "null argument");
+    std::vector<HArr> a = {{c, nullptr, 2 * kPolyBytes}, {x, nullptr, kPolyBytes}, {r, nullptr, 3 * kN}};
+    if (f) a.push_back({f, nullptr, kN});
+    return run_chunked(e, B, a, 0, bm, [&](size_t n, void **d, char *, uint32_t *fl, cudaStream_t s) {
+        return dev_commitment_verify(e, n, (const int32_t *)d[0], (const int32_t *)d[1], (const int8_t *)d[2],
+                                     f ? (const int8_t *)d[3] : nullptr, fl, s);
     });
 }
 

@@ -141,6 +141,45 @@ constexpr inline void prog_norm_verify(Prog &P, int sz)
     P.add(OP_NORM, sz, /*verify bound*/ 1, 3, 0);      // params.rs:112-118
 }
 
+// Commitment::verify (commit.rs:173-210) as a zero test, 2 primes (r is any int8 row, f any int8 polynomial):
+//   f = None:     c - ([a1;a2].r + [0;x]) == 0
+//   f = Some(f):  f*c - [a1;a2].r - f*[0;x] == 0      (commit.rs:203-207, rearranged by commutativity of R_q)
+// preceded by check_commit_constraint(r) (commit.rs:182).
+// streams: sc = c (2 polys), sx = x, sr = r (i8, 3 polys), sf = f (i8) or -1
+constexpr inline void prog_commitment_verify(Prog &P, int sc, int sx, int sr, int sf)
+{
+    P.add(OP_NORM, sr, /*commit bound*/ 0, 3, 0);
+    P.add(OP_SEG);
+    if (sf >= 0) {
+        P.add(OP_FWD, sf, FWD_SCALED, 0, 0);
+        P.add(OP_ST);
+    }
+    P.add(OP_FWD, sr, 0, 0, 1);
+    P.add(OP_MACK, 0, 0, MAC_INIT | MAC_NEG);
+    P.add(OP_FWD, sr, 0, 0, 2);
+    P.add(OP_MACK, 0, 1, MAC_NEG);
+    P.add(OP_MACK, 1, 2, MAC_INIT | MAC_NEG);
+    if (sf >= 0) {
+        P.add(OP_FWD, sc, 0, 0, 0);
+        P.add(OP_MACV, 0, 0, 0);
+        P.add(OP_FWD, sc, 0, 0, 1);
+        P.add(OP_MACV, 1, 0, 0);
+        P.add(OP_FWD, sx, 0, 0, 0);
+        P.add(OP_MACV, 1, 0, MAC_NEG);
+    }
+    P.add(OP_INV, 0, 0);
+    P.add(OP_ADDP, sr, 0, MAC_NEG, 0);
+    if (sf < 0) P.add(OP_ADDP, sc, 0, 0, 0);
+    P.add(OP_FIN, 0, FIN_CMPZ, 0, 0);
+    P.add(OP_INV, 1, 1);
+    P.add(OP_ADDP, sr, 0, MAC_NEG, 1);
+    if (sf < 0) {
+        P.add(OP_ADDP, sc, 0, 0, 1);
+        P.add(OP_ADDP, sx, 0, MAC_NEG, 0);
+    }
+    P.add(OP_FIN, 0, FIN_CMPZ, 0, 0);
+}
+
 // ---- 1-prime program ---------------------------------------------------------------
 
 // z = y + r.componentwise_mul(d)                          open.rs:113-115

@@ -67,6 +67,8 @@ _VP = C.c_void_p
 # name -> argument kinds after the engine handle ('z' size_t, 'u' uint32, 'p' pointer)
 _SIGS = {
     "rzk_commit_batch": "zpppp",
+    "rzk_commitment_verify_batch": "zppppp",
+    "rzk_commitment_verify_batch_dev": "zpppppp",
     "rzk_open_commit_batch": "zpppppp",
     "rzk_open_respond_batch": "zpppp",
     "rzk_open_verify_batch": "zppppp",
@@ -231,6 +233,14 @@ class Engine:
         ok = np.zeros((B + 7) // 8, np.uint8)
         self._call("rzk_commit_batch", B, _ptr(x, np.int32), _ptr(r, np.int8), _ptr(c), _ptr(ok))
         return c, ok
+
+    def commitment_verify(self, c, x, r, f=None):
+        """Commitment::verify (commit.rs:173-210) for a batch; f None or [B][N] int8."""
+        B = c.shape[0]
+        bm = np.zeros((B + 7) // 8, np.uint8)
+        self._call("rzk_commitment_verify_batch", B, _ptr(c, np.int32), _ptr(x, np.int32), _ptr(r, np.int8),
+                   _ptr(f, np.int8) if f is not None else None, _ptr(bm))
+        return bm
 
     def open_commit(self, x, r, y):
         B, N = x.shape[0], self.N

@@ -106,7 +106,11 @@ struct Params {
     }
 };
 
-template <int N> struct Opening { std::vector<Polynomial<N>> x; std::vector<int8_t> r; };   // src/commit.rs:223-235 (f = None)
+template <int N> struct Opening {                                                         // src/commit.rs:223-235
+    std::vector<Polynomial<N>> x;
+    std::vector<int8_t> r;
+    std::vector<int8_t> f;       // empty = None; else a challenge-space polynomial [N] (randomised opening)
+};
 
 template <int N>
 struct Commitment {                                                                       // src/commit.rs:135-141
@@ -174,10 +178,12 @@ template <int N>
 bool Commitment<N>::verify(const Opening<N> &o, const CommitmentKey<N> &ck, const Params &P) const
 {
     std::vector<int32_t> xf; for (auto &p : o.x) xf.insert(xf.end(), p.c.begin(), p.c.end());
-    std::vector<int32_t> c2((P.n + P.l) * N);
+    rzk_assert(o.f.empty() || (int)o.f.size() == N, "f is one polynomial");
+    (void)P;
     std::vector<uint8_t> ok(1);
-    ck.eng->check(rzk_commit_batch(ck.eng->h, 1, xf.data(), o.r.data(), c2.data(), ok.data()));
-    return (ok[0] & 1) && c2 == c;          // check_commit_constraint(r) && A.r + [0;x] == c
+    // check_commit_constraint(r), then A.r + [0;x] == c (None) or f*c == A.r + f*[0;x] (Some(f))
+    ck.eng->check(rzk_commitment_verify_batch(ck.eng->h, 1, c.data(), xf.data(), o.r.data(), o.f.empty() ? nullptr : o.f.data(), ok.data()));
+    return ok[0] & 1;
 }
 
 // ------------------------------------------------------------------ Open proof (src/prove/open.rs)

@@ -529,6 +529,41 @@ int main(int argc, char **argv)
         printf("static programs ok\n");
     }
 
+    // ---------------- Commitment::verify (commit.rs:173-210), None and Some(f) branches ----------------
+    {
+        std::vector<int32_t> c32(c_o.begin(), c_o.end());
+        // randomised opening: r' = f * r for a challenge-space f (36 entries +-1), so that f*c == A r' + f*[0;x]
+        std::vector<int8_t> rf(B * 3 * N);
+        std::vector<int64_t> tmp(N);
+        for (int b = 0; b < B; ++b)
+            for (int j = 0; j < 3; ++j) {
+                rzko_poly_mul(&P, r64.data() + ((size_t)b * 3 + j) * N, d64.data() + (size_t)b * N, tmp.data());
+                for (size_t i = 0; i < N; ++i) rf[((size_t)b * 3 + j) * N + i] = (int8_t)tmp[i];
+            }
+        for (int variant = 0; variant < 6; ++variant) {
+            const bool withf = variant >= 3;
+            std::vector<int32_t> cc(c32), xx(x);
+            std::vector<int8_t> rr(withf ? rf : r);
+            if (variant == 1 || variant == 4) for (int b = 0; b < B; ++b) cc[((size_t)b * 2 + 1) * N + 5] += 1;
+            if (variant == 2 || variant == 5) for (int b = 0; b < B; ++b) rr[((size_t)b * 3) * N + 9] += 1;
+            Emu E(2, L2, keyp.data(), B);
+            Prog pr;
+            prog_commitment_verify(pr, 0, 1, 2, withf ? 3 : -1);
+            pr.end(); pr.install(E.K);
+            E.stream(0, cc.data(), 2, DT_I32); E.stream(1, xx.data(), 1, DT_I32); E.stream(2, rr.data(), 3, DT_I8);
+            if (withf) E.stream(3, d.data(), 1, DT_I8);
+            E.run(B);
+            auto c64 = widen(cc), rr64 = widen8(rr);
+            for (int b = 0; b < B; ++b) {
+                const int okv = rzko_commitment_verify(&P, a1.data(), a2.data(), c64.data() + (size_t)b * 2 * N, x64.data() + (size_t)b * N,
+                                                       rr64.data() + (size_t)b * 3 * N, withf ? d64.data() + (size_t)b * N : nullptr);
+                CHECK((E.flags[b] == 0) == (okv == 1), "commitment verify variant %d item %d: emu %u oracle %d", variant, b, E.flags[b], okv);
+                CHECK((okv == 1) == (variant == 0 || variant == 3), "oracle commitment verdict variant %d", variant);
+            }
+        }
+        printf("commitment verify ok\n");
+    }
+
     // ---------------- FP64-pipe commitment (rzk_f64.cuh): one 46-bit prime, 4 transforms ----------------
     {
         const F64Tables &FT = f64_tables();

@@ -42,6 +42,20 @@ static void test_readme_and_doctests()
     ASSERT(com2.verify(open2, ck, params));
     ASSERT(!com2.verify(open1, ck, params));
     ASSERT(!com1.verify(open2, ck, params));
+    {   // randomised opening (commit.rs:203-207) with the unit f = -X^3: r' = f*r keeps the norm, f*c == A.r' + f*[0;x]
+        auto openf = open1;
+        openf.f.assign(N, 0); openf.f[3] = -1;
+        for (int j = 0; j < params.k; ++j)
+            for (int i = 0; i < N; ++i) {
+                const int src = (i - 3 + N) % N;
+                const int sign = (i >= 3) ? -1 : 1;            // X^N = -1
+                openf.r[(size_t)j * N + i] = (int8_t)(sign * open1.r[(size_t)j * N + src]);
+            }
+        ASSERT(com1.verify(openf, ck, params));
+        ASSERT(!com2.verify(openf, ck, params));
+        openf.r[5] = (int8_t)(openf.r[5] + 1);
+        ASSERT(!com1.verify(openf, ck, params));
+    }
     bool threw = false;
     try { params.prepare_value<N>({{1}, {2}}); } catch (const std::logic_error &) { threw = true; }   // params.rs:71
     ASSERT(threw);
