@@ -176,6 +176,7 @@ def main():
     ap.add_argument("--ref-seconds", type=float, default=8.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the Linear / Sum lines (configs[3], configs[4])")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -304,6 +305,56 @@ def main():
     ms_p = timed(prove_step, args.steps, args.warmup)
     proves = world * B * args.steps / (ms_p * 1e-3)
 
+    # ---- configs[3] and configs[4]: Linear proofs (2^14 instances) and Sum proofs with 64 terms (2^12 instances),
+    # device-resident, commit + respond + verify per instance.  Inputs are drawn on the device (same distributions
+    # as ring-zk_b200/synth.py); correctness inside the bench = every honest instance verifies (flags == 0).
+    extras = None
+    if not args.no_extras:
+        extras = {}
+        half = (3515337053 - 1) // 2
+        gen = torch.Generator(device=dev); gen.manual_seed(77 + rank)
+        U = lambda *sh: torch.randint(-half, half + 1, sh, device=dev, generator=gen, dtype=torch.int64).to(torch.int32)
+        S3 = lambda *sh: torch.randint(-1, 2, sh, device=dev, generator=gen, dtype=torch.int32).to(torch.int8)
+        G = lambda *sh: (torch.randn(sh, device=dev, generator=gen, dtype=torch.float64) * 15444.0).trunc().to(torch.int32)
+        E = lambda *sh: torch.empty(sh, dtype=torch.int32, device=dev)
+        ksteps = max(3, args.steps // 4)
+        # Linear
+        BL = 1 << 14
+        g_, x_, r_, rp_, y_, yp_, d_ = U(BL, N), U(BL, 1, N), S3(BL, 3, N), S3(BL, 3, N), G(BL, 3, N), G(BL, 3, N), d[:BL].contiguous()
+        gx, cp, cl, tl, tpl, u = E(BL, 1, N), E(BL, 2, N), E(BL, 2, N), E(BL, 1, N), E(BL, 1, N), E(BL, 1, N)
+        zl, zpl = E(BL, 3, N), E(BL, 3, N)
+        fl = torch.zeros(BL, dtype=torch.int32, device=dev)
+
+        def linear_step():
+            eng.dev("linear_commit_batch", BL, g_, x_, rp_, r_, y_, yp_, gx, cp, cl, tl, tpl, u, fl, stream=stream)
+            eng.dev("linear_respond_batch", BL, y_, yp_, r_, rp_, d_, zl, zpl, stream=stream)
+            eng.dev("linear_verify_batch", BL, zl, zpl, cl, cp, g_, tl, tpl, u, d_, fl, stream=stream)
+        ms_l = timed(linear_step, ksteps, 2) / ksteps
+        assert bool((fl == 0).all()), "honest Linear proofs failed to verify"
+        extras["linear"] = {"instances_per_gpu": BL, "instances_per_s": world * BL / (ms_l * 1e-3), "ms_per_step": ms_l,
+                            "mulmods_per_instance": 204288,
+                            "frac_of_int_mulmod_peak": 204288 * BL / (ms_l * 1e-3) / (MEASURED_MULMOD_TPS * 1e12)}
+        del g_, x_, r_, rp_, y_, yp_, gx, cp, cl, tl, tpl, u, zl, zpl
+        # Sum, T = 64
+        BS, TT = 1 << 12, 64
+        gs, xs, rs, ys = U(BS, TT, N), U(BS, TT, 1, N), S3(BS, TT, 3, N), G(BS, TT, 3, N)
+        rps, yps, ds = S3(BS, 3, N), G(BS, 3, N), d[:BS].contiguous()
+        xp, cps, css, tss, tps, us = E(BS, 1, N), E(BS, 2, N), E(BS, TT, 2, N), E(BS, TT, 1, N), E(BS, 1, N), E(BS, 1, N)
+        zs, zps = E(BS, TT, 3, N), E(BS, 3, N)
+        fs = torch.zeros(BS, dtype=torch.int32, device=dev)
+
+        def sum_step():
+            eng.dev("sum_commit_batch", BS, TT, gs, xs, rps, rs, ys, yps, xp, cps, css, tss, tps, us, fs, stream=stream)
+            eng.dev("sum_respond_batch", BS, TT, ys, yps, rs, rps, ds, zs, zps, stream=stream)
+            eng.dev("sum_verify_batch", BS, TT, zs, zps, css, cps, gs, tss, tps, us, ds, fs, stream=stream)
+        ms_s = timed(sum_step, ksteps, 1) / ksteps
+        assert bool((fs == 0).all()), "honest Sum proofs failed to verify"
+        extras["sum64"] = {"instances_per_gpu": BS, "terms": TT, "instances_per_s": world * BS / (ms_s * 1e-3), "ms_per_step": ms_s,
+                           "mulmods_per_instance": 7268352,
+                           "frac_of_int_mulmod_peak": 7268352 * BS / (ms_s * 1e-3) / (MEASURED_MULMOD_TPS * 1e12)}
+        del gs, xs, rs, ys, xp, cps, css, tss, tps, us, zs, zps
+        torch.cuda.empty_cache()
+
     # ---- end to end through the host C ABI (pinned host buffers, H2D + D2H inside the timed region) ----
     e2e = None
     if not args.no_e2e:
@@ -353,7 +404,7 @@ def main():
                        "seed": 1000},
             "open_verifies_per_s": verifies, "open_proves_per_s": proves,
             "ms_per_step_open_verify": ms_v / args.steps, "ms_per_step_open_prove": ms_p / args.steps,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "other_configs": extras, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clk.summary(),
             "int_roofline": {"mulmods_per_item": ALG_MULMODS_COMMIT,
                              "achieved_Tmulmod_s": ALG_MULMODS_COMMIT * B / (ms_k * 1e-3) / 1e12,

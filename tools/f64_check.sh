@@ -1,3 +1,4 @@
 set -x
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/bench_s2b_n2.json 2> gpurun_out/bench_s2b_n2.err; tail -c 400 gpurun_out/bench_s2b_n2.err; cat gpurun_out/bench_s2b_n2.json
+python bench.py --steps 20 --warmup 3 > gpurun_out/bench_s2c_n1.json 2> gpurun_out/bench_s2c_n1.err; tail -c 400 gpurun_out/bench_s2c_n1.err; cat gpurun_out/bench_s2c_n1.json
+python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/plain_r1b.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1b.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_r1b.log 2>&1
+tail -2 gpurun_out/ncu_r1b.log
