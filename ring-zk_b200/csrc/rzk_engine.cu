@@ -23,6 +23,7 @@
 
 #include "rzk_vm_exec.cuh"
 #include "rzk_f64.cuh"
+#include "rzk_sparse.cuh"
 #include "rzk_programs.h"
 #include "rzk_tables.h"
 
@@ -58,6 +59,7 @@ __global__ void __launch_bounds__(VmCfg<NP, MODE>::kMaxWarps * 32, 1) rzk_vm_ker
     constexpr bool SPLIT = (MODE != MODE_SEQ);      // one warp per item
     extern __shared__ __align__(16) uint32_t smem[];
     using S = VmSmem<NP, MODE>;
+    if (K.any_item && *K.any_item == 0) return;     // masked fallback launch with nothing to redo
     uint32_t *s_g1 = smem;
     uint32_t *s_g2 = s_g1 + S::kG1;
     uint32_t *s_key = s_g2 + S::kG2;
@@ -112,6 +114,10 @@ __global__ void __launch_bounds__(VmCfg<NP, MODE>::kMaxWarps * 32, 1) rzk_vm_ker
         const uint32_t item = first + it * per_grid;
         ctx.active = item < K.n_items;
         ctx.item = ctx.active ? item : K.n_items - 1;
+        if (K.item_mask) {                          // redo only the flagged items (warp-uniform skip)
+            ctx.active = ctx.active && K.item_mask[ctx.item] != 0;
+            if (!__any_sync(0xffffffffu, ctx.active)) continue;
+        }
         // prefetch the input rows of the item this warp handles next into L2
         const uint32_t next = item + per_grid;
         if (next < K.n_items) {
@@ -301,6 +307,35 @@ __global__ void __launch_bounds__(512, 1) rzk_commit_hybrid_kernel(const __grid_
     }
 }
 
+// ---- response z = y + d*r as signed rotations (rzk_sparse.cuh): one warp per item, byte accumulators ----
+__global__ void __launch_bounds__(512, 1) rzk_respond_sparse_kernel(const __grid_constant__ SparseLaunch K)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    LaneCtxS ctx;
+    ctx.sm = smem + (size_t)warp * kSpWarpWords;
+    ctx.lane = lane;
+    const uint32_t per_grid = gridDim.x * warps;
+    const uint32_t first = blockIdx.x * warps + warp;
+    const uint32_t iters = (K.n_items + per_grid - 1) / per_grid;
+#pragma unroll 1
+    for (uint32_t it = 0; it < iters; ++it) {
+        const uint32_t item = first + it * per_grid;
+        ctx.active = item < K.n_items;
+        ctx.item = ctx.active ? item : K.n_items - 1;
+        const uint32_t next = item + per_grid;
+        if (next < K.n_items) {                     // L2 prefetch of the next item's rows: y 6 KB, r 1.5 KB, d 0.5 KB
+            const char *yb = reinterpret_cast<const char *>(K.y) + (size_t)next * 3 * kN * 4;
+            const char *rb = reinterpret_cast<const char *>(K.r) + (size_t)next * 3 * kN;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(yb + lane * 128));
+            if (lane < 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(yb + 4096 + lane * 128));
+            else if (lane < 28) asm volatile("prefetch.global.L2 [%0];" ::"l"(rb + (lane - 16) * 128));
+            else asm volatile("prefetch.global.L2 [%0];" ::"l"(K.d + (size_t)(next / K.d_div) * kN + (lane - 28) * 128));
+        }
+        sparse_respond_item(K, &ctx);
+    }
+}
+
 // bitmap[i>>3] bit (i&7) = (flags[i] & FLAG_FAIL) == 0 ; range_any |= FLAG_RANGE bits
 __global__ void rzk_flags_to_bitmap_kernel(size_t n, const uint32_t *__restrict__ flags,
                                            uint8_t *__restrict__ bitmap, uint32_t *range_any)
@@ -367,6 +402,9 @@ struct rzk_engine {
     uint32_t *d_keytab = nullptr;
     uint32_t *d_keytab2 = nullptr;  // split-key images (lo/hi) for prime slot 0, [6][2][576]
     double *d_f64tab = nullptr;     // FP64 path: [g1 | g2 | key images] (rzk_f64.cuh)
+    uint32_t no_sparse = 0;         // RZK_NO_SPARSE=1: responses through the NTT program only (A/B timing)
+    uint32_t *d_need = nullptr;     // hand-over words of dev_respond for the `_dev` entry points
+    size_t need_cap = 0;
     uint32_t hyb_seq = 0;
     uint32_t hyb_disable = 0;       // RZK_HYB_DISABLE (experiments)
     uint32_t hyb_int_warps = 8;     // RZK_HYB_INT_WARPS: integer-path warps per CTA in the hybrid kernel (of 16)
@@ -450,7 +488,7 @@ int launch_vm(rzk_engine *e, VmLaunch &K, cudaStream_t s)
     auto kern = rzk_vm_kernel<NP, MODE, SP>;
     layout_hw(K, SPLIT);
     list_prefetch(K);
-    K.cta_sync = e->cta_sync;
+    K.cta_sync = K.item_mask ? 0u : e->cta_sync;      // masked launches skip items per warp: no CTA barriers
     K.pp_mode = 0;
     const size_t max_smem = 227 * 1024;
     int warps = (int)((max_smem - VmSmem<NP, MODE>::bytes(0, 0)) / (sizeof(uint32_t) * 2 * K.hw_words));
@@ -511,6 +549,17 @@ int ensure_scratch(rzk_engine *e, size_t bytes)
     e->scratch = nullptr; e->scratch_cap = 0;
     RZK_CUDA(e, cudaMalloc(&e->scratch, bytes));
     e->scratch_cap = bytes;
+    return RZK_OK;
+}
+
+int ensure_need(rzk_engine *e, size_t words)
+{
+    if (words <= e->need_cap) return RZK_OK;
+    RZK_CUDA(e, cudaDeviceSynchronize());
+    if (e->d_need) cudaFree(e->d_need);
+    e->d_need = nullptr; e->need_cap = 0;
+    RZK_CUDA(e, cudaMalloc(&e->d_need, words * sizeof(uint32_t)));
+    e->need_cap = words;
     return RZK_OK;
 }
 
@@ -645,9 +694,37 @@ int dev_open_commit(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r, 
     return dev_keymatvec(e, B, y, t, nullptr, flags, 1, s);
 }
 
+// z = y + d*r.  `need` ([items + 1] words of device scratch owned by the caller) carries the hand-over between the
+// two launches: the rotation kernel (rzk_sparse.cuh) answers every item whose operands fit its byte accumulators
+// -- all honest inputs -- and flags the rest; the one-prime NTT program then redoes exactly the flagged items
+// (it returns at once when there are none).  need == nullptr: NTT program for everything.
 int dev_respond(rzk_engine *e, size_t items, const int32_t *y, const int8_t *r, const int8_t *d, uint32_t d_div,
-                int32_t *z, cudaStream_t s)
+                int32_t *z, uint32_t *need, cudaStream_t s)
 {
+    if (items == 0) return RZK_OK;
+    const bool sparse = need && !e->no_sparse;
+    if (sparse) {
+        SparseLaunch SK;
+        memset(&SK, 0, sizeof(SK));
+        SK.y = y; SK.r = r; SK.d = d; SK.z = z; SK.need = need; SK.any_need = need + items;
+        SK.n_items = (uint32_t)items; SK.d_div = d_div; SK.q = (uint32_t)e->P.q;
+        RZK_CUDA(e, cudaMemsetAsync(need + items, 0, sizeof(uint32_t), s));
+        int warps = 16;
+        const uint32_t want = (uint32_t)((items + (uint64_t)e->num_sms - 1) / (uint64_t)e->num_sms);
+        if ((uint32_t)warps > want) warps = (int)(want ? want : 1);
+        const size_t smem = sizeof(uint32_t) * (size_t)warps * kSpWarpWords;
+        static bool configured[16] = {};
+        if (!configured[e->device & 15]) {
+            RZK_CUDA(e, cudaFuncSetAttribute(rzk_respond_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(sizeof(uint32_t) * 16 * kSpWarpWords)));
+            configured[e->device & 15] = true;
+        }
+        uint32_t grid = (uint32_t)((items + warps - 1) / warps);
+        if (grid > (uint32_t)e->num_sms) grid = (uint32_t)e->num_sms;
+        rzk_respond_sparse_kernel<<<grid, warps * 32, smem, s>>>(SK);
+        RZK_CUDA(e, cudaGetLastError());
+        e->launches++;
+    }
     VmLaunch K; memset(&K, 0, sizeof(K));
     Prog p;
     prog_respond(p, 0, 1, 2, 3);
@@ -656,8 +733,9 @@ int dev_respond(rzk_engine *e, size_t items, const int32_t *y, const int8_t *r, 
     fill_common(e, K, 1, (uint32_t)items, 1, nullptr);
     set_stream(K, 0, y, 3, DT_I32); set_stream(K, 1, r, 3, DT_I8); set_stream(K, 2, d, 1, DT_I8, d_div);
     set_stream(K, 3, z, 3, DT_I32);
+    if (sparse) { K.item_mask = need; K.any_item = need + items; }
     // measured: the runtime-decoded kernel is faster than the unrolled one for this program (77 vs 61 M/s)
-    return e->static_respond ? launch_sp<SPRespond>(e, K, s) : launch_np(e, 1, K, s);
+    return (e->static_respond && !sparse) ? launch_sp<SPRespond>(e, K, s) : launch_np(e, 1, K, s);
 }
 
 // norm check + first equation (+ optional w = A2.z - c2*d) for `items` responses
@@ -890,6 +968,7 @@ int rzk_create(const rzk_params *params, int device, rzk_engine **out)
     if (const char *cs = getenv("RZK_CTA_SYNC")) e->cta_sync = (uint32_t)atoi(cs);
     if (const char *cs = getenv("RZK_NO_STATIC")) e->no_static = (uint32_t)atoi(cs);
     if (const char *cs = getenv("RZK_COMMIT_MODE")) e->commit_mode = (uint32_t)atoi(cs);
+    if (const char *cs = getenv("RZK_NO_SPARSE")) e->no_sparse = (uint32_t)atoi(cs);
     if (const char *cs = getenv("RZK_HYB_DISABLE")) e->hyb_disable = (uint32_t)atoi(cs);
     if (const char *cs = getenv("RZK_HYB_INT_WARPS")) e->hyb_int_warps = (uint32_t)atoi(cs);
     if (const char *cs = getenv("RZK_PP")) e->pp_mode = (uint32_t)atoi(cs);
@@ -959,6 +1038,7 @@ void rzk_destroy(rzk_engine *e)
     if (e->d_keytab) cudaFree(e->d_keytab);
     if (e->d_keytab2) cudaFree(e->d_keytab2);
     if (e->d_f64tab) cudaFree(e->d_f64tab);
+    if (e->d_need) cudaFree(e->d_need);
     if (e->d_misc) cudaFree(e->d_misc);
     delete e;
 }
@@ -1070,7 +1150,8 @@ int rzk_open_respond_batch_dev(rzk_engine *e, size_t B, const int32_t *y, const 
     RZK_TRY(check_ready(e));
     if (any_null({y, r, d, z})) return fail(e, RZK_ERR_INVALID, "null argument");
     Guard g(e->device);
-    return dev_respond(e, B, y, r, d, 1, z, (cudaStream_t)stream);
+    RZK_TRY(ensure_need(e, B + 1));
+    return dev_respond(e, B, y, r, d, 1, z, e->d_need, (cudaStream_t)stream);
 }
 
 int rzk_open_verify_batch_dev(rzk_engine *e, size_t B, const int32_t *z, const int32_t *t, const int32_t *c, uint32_t c_stride,
@@ -1099,8 +1180,9 @@ int rzk_linear_respond_batch_dev(rzk_engine *e, size_t B, const int32_t *y, cons
     RZK_TRY(check_ready(e));
     if (any_null({y, yp, r, rp, d, z, zp})) return fail(e, RZK_ERR_INVALID, "null argument");
     Guard g(e->device);
-    RZK_TRY(dev_respond(e, B, y, r, d, 1, z, (cudaStream_t)stream));           // linear.rs:150-152
-    return dev_respond(e, B, yp, rp, d, 1, zp, (cudaStream_t)stream);          // linear.rs:154-156
+    RZK_TRY(ensure_need(e, 2 * (B + 1)));
+    RZK_TRY(dev_respond(e, B, y, r, d, 1, z, e->d_need, (cudaStream_t)stream));                  // linear.rs:150-152
+    return dev_respond(e, B, yp, rp, d, 1, zp, e->d_need + B + 1, (cudaStream_t)stream);         // linear.rs:154-156
 }
 
 int rzk_linear_verify_batch_dev(rzk_engine *e, size_t B, const int32_t *z, const int32_t *zp, const int32_t *c, const int32_t *cp,
@@ -1133,8 +1215,9 @@ int rzk_sum_respond_batch_dev(rzk_engine *e, size_t B, uint32_t T, const int32_t
     if (T == 0 || T > 65535) return fail(e, RZK_ERR_INVALID, "T must be in 1..65535");
     if (any_null({ys, yp, rs, rp, d, zs, zp})) return fail(e, RZK_ERR_INVALID, "null argument");
     Guard g(e->device);
-    RZK_TRY(dev_respond(e, B * T, ys, rs, d, T, zs, (cudaStream_t)stream));    // sum.rs:188-193
-    return dev_respond(e, B, yp, rp, d, 1, zp, (cudaStream_t)stream);          // sum.rs:195-197
+    RZK_TRY(ensure_need(e, B * T + 1 + B + 1));
+    RZK_TRY(dev_respond(e, B * T, ys, rs, d, T, zs, e->d_need, (cudaStream_t)stream));           // sum.rs:188-193
+    return dev_respond(e, B, yp, rp, d, 1, zp, e->d_need + B * T + 1, (cudaStream_t)stream);     // sum.rs:195-197
 }
 
 int rzk_sum_verify_batch_dev(rzk_engine *e, size_t B, uint32_t T, const int32_t *zs, const int32_t *zp, const int32_t *cs,
@@ -1203,8 +1286,8 @@ int rzk_open_respond_batch(rzk_engine *e, size_t B, const int32_t *y, const int8
     RZK_TRY(check_ready(e));
     if (any_null({y, r, dch, z})) return fail(e, RZK_ERR_INVALID, "null argument");
     std::vector<HArr> a = {{y, nullptr, 3 * kPolyBytes}, {r, nullptr, 3 * kN}, {dch, nullptr, kN}, {nullptr, z, 3 * kPolyBytes}};
-    return run_chunked(e, B, a, 0, nullptr, [&](size_t n, void **d, char *, uint32_t *, cudaStream_t s) {
-        return dev_respond(e, n, (const int32_t *)d[0], (const int8_t *)d[1], (const int8_t *)d[2], 1, (int32_t *)d[3], s);
+    return run_chunked(e, B, a, 2 * sizeof(uint32_t), nullptr, [&](size_t n, void **d, char *sc, uint32_t *, cudaStream_t s) {
+        return dev_respond(e, n, (const int32_t *)d[0], (const int8_t *)d[1], (const int8_t *)d[2], 1, (int32_t *)d[3], (uint32_t *)sc, s);
     });
 }
 
@@ -1262,9 +1345,10 @@ int rzk_linear_respond_batch(rzk_engine *e, size_t B, const int32_t *y, const in
     if (any_null({y, yp, r, rp, dch, z, zp})) return fail(e, RZK_ERR_INVALID, "null argument");
     std::vector<HArr> a = {{y, nullptr, 3 * kPolyBytes}, {yp, nullptr, 3 * kPolyBytes}, {r, nullptr, 3 * kN}, {rp, nullptr, 3 * kN},
                            {dch, nullptr, kN}, {nullptr, z, 3 * kPolyBytes}, {nullptr, zp, 3 * kPolyBytes}};
-    return run_chunked(e, B, a, 0, nullptr, [&](size_t n, void **d, char *, uint32_t *, cudaStream_t s) {
-        RZK_TRY(dev_respond(e, n, (const int32_t *)d[0], (const int8_t *)d[2], (const int8_t *)d[4], 1, (int32_t *)d[5], s));
-        return dev_respond(e, n, (const int32_t *)d[1], (const int8_t *)d[3], (const int8_t *)d[4], 1, (int32_t *)d[6], s);
+    return run_chunked(e, B, a, 4 * sizeof(uint32_t), nullptr, [&](size_t n, void **d, char *sc, uint32_t *, cudaStream_t s) {
+        uint32_t *need = (uint32_t *)sc;
+        RZK_TRY(dev_respond(e, n, (const int32_t *)d[0], (const int8_t *)d[2], (const int8_t *)d[4], 1, (int32_t *)d[5], need, s));
+        return dev_respond(e, n, (const int32_t *)d[1], (const int8_t *)d[3], (const int8_t *)d[4], 1, (int32_t *)d[6], need + n + 1, s);
     });
 }
 
@@ -1316,9 +1400,10 @@ int rzk_sum_respond_batch(rzk_engine *e, size_t B, uint32_t T, const int32_t *ys
     if (any_null({ys, yp, rs, rp, dch, zs, zp})) return fail(e, RZK_ERR_INVALID, "null argument");
     std::vector<HArr> a = {{ys, nullptr, T * 3 * kPolyBytes}, {yp, nullptr, 3 * kPolyBytes}, {rs, nullptr, (size_t)T * 3 * kN},
                            {rp, nullptr, 3 * kN}, {dch, nullptr, kN}, {nullptr, zs, T * 3 * kPolyBytes}, {nullptr, zp, 3 * kPolyBytes}};
-    return run_chunked(e, B, a, 0, nullptr, [&](size_t n, void **d, char *, uint32_t *, cudaStream_t s) {
-        RZK_TRY(dev_respond(e, n * T, (const int32_t *)d[0], (const int8_t *)d[2], (const int8_t *)d[4], T, (int32_t *)d[5], s));
-        return dev_respond(e, n, (const int32_t *)d[1], (const int8_t *)d[3], (const int8_t *)d[4], 1, (int32_t *)d[6], s);
+    return run_chunked(e, B, a, ((size_t)T + 3) * sizeof(uint32_t), nullptr, [&](size_t n, void **d, char *sc, uint32_t *, cudaStream_t s) {
+        uint32_t *need = (uint32_t *)sc;
+        RZK_TRY(dev_respond(e, n * T, (const int32_t *)d[0], (const int8_t *)d[2], (const int8_t *)d[4], T, (int32_t *)d[5], need, s));
+        return dev_respond(e, n, (const int32_t *)d[1], (const int8_t *)d[3], (const int8_t *)d[4], 1, (int32_t *)d[6], need + n * T + 1, s);
     });
 }
 

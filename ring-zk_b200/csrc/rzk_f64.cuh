@@ -165,6 +165,8 @@ RZK_VM void f64_g1_stage(double (&a)[kElems], const double2 *g1)
     constexpr int half = 16 >> S;
     RZK_UNROLL
     for (int b = 0; b < (1 << S); ++b) {
+        // (tried: these lane-uniform twiddles from constant memory -- LDC.64 instead of LDS.128: +8 % for this
+        //  program alone, -4 % inside the hybrid launch, where the integer group's parameter reads share the constant cache)
         const double2 w = g1[(1 << S) + b];
         RZK_UNROLL
         for (int j = 0; j < half; ++j) {

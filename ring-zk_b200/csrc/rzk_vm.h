@@ -117,6 +117,8 @@ struct VmLaunch {
     uint8_t prefetch[8];
     uint32_t cta_sync;         // keep the warps of a CTA in step (instruction-cache locality)
     uint32_t loop_count;       // trip count of OP_LOOP in compile-time programs (terms of a Sum proof - 1)
+    const uint32_t *item_mask; // optional: only items with item_mask[item] != 0 are processed (fallback launches)
+    const uint32_t *any_item;  // optional: the whole launch returns at once when *any_item == 0
     uint32_t pp_mode;          // phase mixing between the two halves of a CTA (rzk_vm_exec.cuh pp_acquire); 0 = off
     uint32_t alias_slot;       // the operand slot may overlay the transpose buffer (programs whose OP_LDs all
                                // precede the inverse transforms and that never use OP_MACV)

@@ -16,6 +16,7 @@
 #include "../../ring-zk_b200/csrc/rzk_vm_exec.cuh"
 #include "../../ring-zk_b200/csrc/rzk_programs.h"
 #include "../../ring-zk_b200/csrc/rzk_f64.cuh"
+#include "../../ring-zk_b200/csrc/rzk_sparse.cuh"
 #include "../../ring-zk_b200/csrc/rzk_tables.h"
 extern "C" {
 #include "../../oracle/ringzk_oracle.h"
@@ -527,6 +528,63 @@ int main(int argc, char **argv)
             }
         }
         printf("static programs ok\n");
+    }
+
+    // ---------------- sparse response z = y + d*r as signed rotations (rzk_sparse.cuh) ----------------
+    {
+        const int BB = B < 6 ? 6 : B;
+        std::vector<int32_t> ys(BB * 3 * N), zs(BB * 3 * N, 12345);
+        std::vector<int8_t> rsm(BB * 3 * N), dsm(BB * N, 0);
+        for (auto &v : ys) v = rnd_gauss(15444.0);
+        for (auto &v : rsm) v = (int8_t)((int)(rnd() % 3) - 1);
+        auto put_d = [&](int b, int cnt) {
+            for (int k = 0; k < cnt;) { int pos = (int)(rnd() % N); if (dsm[b * N + pos]) continue; dsm[b * N + pos] = (rnd() & 1) ? 1 : -1; ++k; }
+        };
+        put_d(0, 36); put_d(1, 36); put_d(2, 42); put_d(3, 127); put_d(4, 0); put_d(5, 36);
+        for (int b = 6; b < BB; ++b) put_d(b, 36);
+        dsm[0 * N + 0] = 1; dsm[0 * N + 511] = -1;                             // rotations by 0 and by N-1
+        for (size_t i = 0; i < 3 * N; ++i) rsm[1 * 3 * N + i] = (int8_t)((int)(rnd() % 7) - 3);      // |r| <= 3 with 36 terms
+        for (size_t i = 0; i < 3 * N; ++i) rsm[2 * 3 * N + i] = (i & 1) ? 3 : -3;                    // extreme bytes: 42 * 6 = 252
+        for (size_t i = 0; i < 3 * N; ++i) rsm[3 * 3 * N + i] = (i % 3) ? 1 : -1;                    // 127 terms, bias 1: 254
+        // any int32 representative of y, including the extremes and values next to +-(q-1)/2
+        for (size_t i = 0; i < N; ++i) {
+            ys[5 * 3 * N + i] = (i % 4 == 0) ? INT32_MAX : (i % 4 == 1) ? INT32_MIN : (i % 4 == 2) ? (int32_t)((Q - 1) / 2) : -(int32_t)((Q - 1) / 2);
+            ys[5 * 3 * N + N + i] = (int32_t)((Q - 1) / 2) - (int32_t)(i % 40);
+        }
+        std::vector<uint32_t> need(BB, 7), anyn(1, 0), smem(kSpWarpWords, 0xDEADBEEFu);
+        SparseLaunch K;
+        memset(&K, 0, sizeof(K));
+        K.y = ys.data(); K.r = rsm.data(); K.d = dsm.data(); K.z = zs.data(); K.need = need.data(); K.any_need = anyn.data();
+        K.n_items = BB; K.d_div = 1; K.q = (uint32_t)Q;
+        static LaneCtxS sctx[32];
+        auto run_all = [&]() {
+            for (int b = 0; b < BB; ++b) {
+                for (int li = 0; li < 32; ++li) { sctx[li].sm = smem.data(); sctx[li].item = b; sctx[li].lane = li; sctx[li].active = true; }
+                sparse_respond_item(K, sctx);
+            }
+        };
+        run_all();
+        auto ys64 = widen(ys), rs64 = widen8(rsm), ds64 = widen8(dsm);
+        for (auto &v : ys64) v = rzko_center(v, Q);
+        std::vector<int64_t> zo(BB * 3 * N);
+        rzko_open_respond_batch(&P, BB, ys64.data(), rs64.data(), ds64.data(), zo.data(), 1);
+        CHECK(same(zs, zo), "sparse respond mismatch");
+        for (int b = 0; b < BB; ++b) CHECK(need[b] == 0, "sparse respond need[%d]=%u", b, need[b]);
+        CHECK(anyn[0] == 0, "any_need set");
+        // items outside the byte range are left to the NTT program: |r| = 4; 43 terms with |r| = 2; d entry 2; 128 terms
+        rsm[0 * 3 * N + 700] = 4;
+        dsm[2 * N + 0] = dsm[2 * N + 0] ? dsm[2 * N + 0] : 1; { int extra = 0; for (size_t i = 0; i < N && !extra; ++i) if (!dsm[2 * N + i]) { dsm[2 * N + i] = 1; extra = 1; } }
+        for (size_t i = 0; i < 3 * N; ++i) rsm[2 * 3 * N + i] = 2;
+        dsm[1 * N + 9] = 2;
+        { int extra = 0; for (size_t i = 0; i < N && !extra; ++i) if (!dsm[3 * N + i]) { dsm[3 * N + i] = -1; extra = 1; } }
+        std::fill(zs.begin(), zs.end(), 777);
+        run_all();
+        for (int b = 0; b < 4; ++b) {
+            CHECK(need[b] == 1, "sparse respond fallback flag item %d: %u", b, need[b]);
+            for (size_t i = 0; i < 3 * N; ++i) CHECK(zs[(size_t)b * 3 * N + i] == 777, "fallback item %d was written", b);
+        }
+        CHECK(need[4] == 0 && need[5] == 0 && anyn[0] == 1, "need flags of in-range items");
+        printf("sparse respond ok\n");
     }
 
     // ---------------- Commitment::verify (commit.rs:173-210), None and Some(f) branches ----------------

@@ -350,3 +350,32 @@ def test_api_commitment_verify_with_f():
     assert com.verify(api.Opening(opening.x, rf, f), ck, params)
     assert not com.verify(api.Opening(opening.x, opening.r, f), ck, params)
     assert api.Commitment.verify_batch(com.c[None], opening.x[None], rf[None], ck, f[None]).all()
+
+
+def test_respond_rotation_kernel_and_fallback(setup):
+    """z = y + d*r: the rotation kernel (byte accumulators) answers the honest items, the NTT program redoes the
+    items it declines (|r| beyond the byte range, dense or non-{-1,0,1} d); any int32 representative of y."""
+    eng, o, s = setup
+    B = 40
+    y, r, d = s.gaussian(B), s.small(B), s.challenge(B)
+    rng = np.random.default_rng(11)
+    r[1] = rng.integers(-3, 4, size=r[1].shape)                 # still inside the byte range (36 * 6 < 256)
+    r[2] = rng.integers(-127, 128, size=r[2].shape)             # declined: |r| > 3
+    d[3] = rng.integers(-1, 2, size=d[3].shape)                 # declined: ~340 non-zeros
+    d[4, 5] = 2                                                 # declined: entry outside {-1, 0, 1}
+    d[5] = 0                                                    # d = 0: z = y
+    d[6] = 0; d[6, :127] = 1                                    # 127 terms: bias 1, sums up to 254
+    half = (3515337053 - 1) // 2
+    y[7, 0, ::2] = np.int32(2 ** 31 - 1); y[7, 0, 1::2] = np.int32(-2 ** 31)
+    y[7, 1, :] = half - (np.arange(N) % 40); y[7, 2, :] = -half + (np.arange(N) % 40)
+    z = eng.open_respond(y, r, d)
+    z_o = o.open_respond_batch(o.center(y.astype(np.int64)), r, d)
+    assert (z == z_o).all()
+    # Sum-proof shape: one challenge per instance shared by its T terms
+    T = 3
+    ys, rs = s.gaussian(B, T), s.small(B, T)
+    yp, rp = s.gaussian(B), s.small(B)
+    rs[2, 1] = 100
+    zs, zp = eng.sum_respond(ys, yp, rs, rp, d)
+    zs_o, zp_o = o.sum_respond_batch(ys, yp, rs, rp, d)
+    assert (zs == zs_o).all() and (zp == zp_o).all()

@@ -1,4 +1,4 @@
 set -x
-python bench.py --steps 20 --warmup 3 > gpurun_out/bench_s2c_n1.json 2> gpurun_out/bench_s2c_n1.err; tail -c 400 gpurun_out/bench_s2c_n1.err; cat gpurun_out/bench_s2c_n1.json
-python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/plain_r1b.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1b.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_r1b.log 2>&1
-tail -2 gpurun_out/ncu_r1b.log
+timeout 300 python tools/quick_time.py 2>&1 | grep -E "^(open_respond|linear_respond|sum_respond|.*Error)"
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -2
+python tools/profile_respond.py 4 > gpurun_out/plain_resp.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:sparse -s 2 -c 1 -o gpurun_out/prof_sparse2 -f python tools/profile_respond.py 4 > gpurun_out/ncu_resp.log 2>&1
