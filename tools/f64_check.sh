@@ -1,4 +1,4 @@
 set -x
-timeout 300 python tools/quick_time.py 2>&1 | grep -E "^(open_respond|linear_respond|sum_respond|.*Error)"
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -2
-python tools/profile_respond.py 4 > gpurun_out/plain_resp.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:sparse -s 2 -c 1 -o gpurun_out/prof_sparse2 -f python tools/profile_respond.py 4 > gpurun_out/ncu_resp.log 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py --steps 20 --warmup 3 > gpurun_out/bench_s2d_n1.json 2> gpurun_out/bench_s2d_n1.err; tail -c 300 gpurun_out/bench_s2d_n1.err; cat gpurun_out/bench_s2d_n1.json
+python -c "import __graft_entry__ as g; g.smoke()"
