@@ -308,6 +308,7 @@ __global__ void __launch_bounds__(512, 1) rzk_commit_hybrid_kernel(const __grid_
 }
 
 // ---- response z = y + d*r as signed rotations (rzk_sparse.cuh): one warp per item, byte accumulators ----
+// (tried: 64 registers, two CTAs per SM, y loaded after the loop: 178 M/s vs 186 M/s -- the shared-memory pipe is the limit)
 __global__ void __launch_bounds__(512, 1) rzk_respond_sparse_kernel(const __grid_constant__ SparseLaunch K)
 {
     extern __shared__ __align__(16) uint32_t smem[];

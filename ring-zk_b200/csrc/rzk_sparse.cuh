@@ -185,28 +185,15 @@ RZK_VM void sparse_respond_item(const SparseLaunch &K, const LaneCtxS *ctxs)
     // y is fetched now so that its latency hides behind the accumulation loop
     const int32_t corr = -(int32_t)(bias * nnz);
     uint4 yq[RZK_NL][3][4];
-    uint32_t wide_l[RZK_NL];
     RZK_EACH_LANE {
         const LaneCtxS &ctx = ctxs[li_];
-        uint32_t wide = 0;
         RZK_UNROLL
         for (int j = 0; j < 3; ++j) {
             const size_t row = ((size_t)ctx.item * 3 + j) * kN + 16 * ctx.lane;
             RZK_UNROLL
-            for (int c = 0; c < 4; ++c) {
-                const uint4 q = sp_ld128(K.y + row + 4 * c);
-                yq[li_][j][c] = q;
-                wide |= (q.x + 0x40000000u) | (q.y + 0x40000000u) | (q.z + 0x40000000u) | (q.w + 0x40000000u);   // bit 31 <=> y outside [-2^30, 2^30)
-            }
+            for (int c = 0; c < 4; ++c) yq[li_][j][c] = sp_ld128(K.y + row + 4 * c);      // first use is after the loop
         }
-        wide_l[li_] = wide >> 31;
     }
-    uint32_t wide_any = 0;
-#if defined(__CUDA_ARCH__)
-    wide_any = __any_sync(0xffffffffu, wide_l[0] != 0) ? 1u : 0u;
-#else
-    for (int li = 0; li < RZK_NL; ++li) wide_any |= wide_l[li];
-#endif
     // ---- accumulate the nnz signed rotations as packed biased bytes
     uint32_t acc[RZK_NL][3][4];
     RZK_EACH_LANE {
@@ -234,6 +221,27 @@ RZK_VM void sparse_respond_item(const SparseLaunch &K, const LaneCtxS *ctxs)
     // ---- z = y + (byte - bias * nnz), canonical centred residue mod q (what Polynomial + yields).
     // Honest y is tiny (|y| < 2^30): then y + delta is canonical as it stands; any other int32 representative
     // takes the exact 64-bit path below (warp-uniform choice).
+    uint32_t wide_any = 0;
+    {
+        uint32_t wide_l[RZK_NL];
+        RZK_EACH_LANE {
+            uint32_t wide = 0;
+            RZK_UNROLL
+            for (int j = 0; j < 3; ++j) {
+                RZK_UNROLL
+                for (int c = 0; c < 4; ++c) {
+                    const uint4 q = yq[li_][j][c];
+                    wide |= (q.x + 0x40000000u) | (q.y + 0x40000000u) | (q.z + 0x40000000u) | (q.w + 0x40000000u);   // bit 31 <=> y outside [-2^30, 2^30)
+                }
+            }
+            wide_l[li_] = wide >> 31;
+        }
+#if defined(__CUDA_ARCH__)
+        wide_any = __any_sync(0xffffffffu, wide_l[0] != 0) ? 1u : 0u;
+#else
+        for (int li = 0; li < RZK_NL; ++li) wide_any |= wide_l[li];
+#endif
+    }
     RZK_EACH_LANE {
         const LaneCtxS &ctx = ctxs[li_];
         RZK_UNROLL
