@@ -379,3 +379,42 @@ def test_respond_rotation_kernel_and_fallback(setup):
     zs, zp = eng.sum_respond(ys, yp, rs, rp, d)
     zs_o, zp_o = o.sum_respond_batch(ys, yp, rs, rp, d)
     assert (zs == zs_o).all() and (zp == zp_o).all()
+
+
+def test_device_outputs_stay_in_bounds(setup):
+    """Outputs of the device-resident entry points are carved out of larger buffers with canary words on both
+    sides (compute-sanitizer is not available on this pool): odd batch sizes, the hybrid commitment launch
+    (>= 4096 items), the rotation-kernel response and the masked fallback must leave every canary intact."""
+    import torch
+    eng, o, s = setup
+    dev = torch.device("cuda:0")
+    st = torch.cuda.current_stream().cuda_stream
+    CAN = 4096
+
+    def carve(shape, dtype=torch.int32):
+        n = int(np.prod(shape))
+        buf = torch.full((n + 2 * CAN,), -1234567, dtype=dtype, device=dev)
+        return buf, buf[CAN:CAN + n].view(*shape)
+
+    def intact(buf, n):
+        return bool((buf[:CAN] == -1234567).all()) and bool((buf[CAN + n:] == -1234567).all())
+
+    for B in (4099, 333):
+        x, r, y, d = (torch.from_numpy(a).to(dev) for a in (s.message(B), s.small(B), s.gaussian(B), s.challenge(B)))
+        r[5, 1, 7] = 100                                       # one item for the masked NTT fallback of the response
+        cb, c = carve((B, 2, N)); tb, t = carve((B, 1, N)); zb, z = carve((B, 3, N)); fb, flags = carve((B,))
+        flags.zero_()
+        eng.dev("open_commit_batch", B, x, r, y, c, t, flags, stream=st)
+        eng.dev("open_respond_batch", B, y, r, d, z, stream=st)
+        eng.dev("open_verify_batch", B, z, t, c, 2, d, flags, stream=st)
+        eng.dev("commitment_verify_batch", B, c, x, r, None, flags, stream=st)
+        torch.cuda.synchronize()
+        assert intact(cb, B * 2 * N) and intact(tb, B * N) and intact(zb, B * 3 * N) and intact(fb, B)
+        fl = flags.cpu().numpy()
+        assert (fl[np.arange(B) != 5] == 0).all() and (fl[5] & 2)     # item 5: range flag from the one-word commitment kernels
+        idx = [0, 5, B - 1]
+        xs, rs, ys, ds = (a[idx].cpu().numpy() for a in (x, r, y, d))
+        c_o, t_o, _ = o.open_commit_batch(xs, rs, ys)
+        z_o = o.open_respond_batch(ys, rs, ds)
+        assert (z[idx].cpu().numpy() == z_o).all() and (t[idx].cpu().numpy() == t_o).all()
+        assert (c[[0, B - 1]].cpu().numpy() == c_o[[0, 2]]).all()
