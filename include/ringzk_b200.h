@@ -194,6 +194,45 @@ int rzk_unpack_i64(rzk_engine *e, size_t count, const int32_t *src, int64_t *dst
 /* Counters for the benchmark harness: kernels launched by this engine since creation. */
 uint64_t rzk_kernel_launches(const rzk_engine *e);
 
+/* ---------------------------------------------------------------- several GPUs behind one handle
+ * For a single-process caller (the Rust crate): a group owns one engine per listed device and one host
+ * worker thread per engine.  Every host entry point has a group form with the same arguments; the batch
+ * is split into contiguous item ranges whose starts are multiples of 8 (so every range owns whole bytes
+ * of the result bitmap), each range runs on its device, and there is no exchange between devices
+ * (commit.rs:88-128 reads only self, params, x, r).  A device id may be listed more than once.
+ * Status: RZK_OK, or the first non-zero status of any device (message in rzk_group_last_error). */
+typedef struct rzk_group rzk_group;
+int rzk_group_create(const rzk_params *params, const int *device_ids, int n_devices, rzk_group **out);
+void rzk_group_destroy(rzk_group *g);
+int rzk_group_size(const rzk_group *g);
+const char *rzk_group_last_error(const rzk_group *g);
+int rzk_group_set_key(rzk_group *g, const int64_t *a1, const int64_t *a2);
+uint64_t rzk_group_kernel_launches(const rzk_group *g);
+int rzk_group_commit_batch(rzk_group *g, size_t B, const int32_t *x, const int8_t *r, int32_t *c, uint8_t *ok_bitmap);
+int rzk_group_commitment_verify_batch(rzk_group *g, size_t B, const int32_t *c, const int32_t *x, const int8_t *r,
+                                      const int8_t *f, uint8_t *verify_bitmap);
+int rzk_group_open_commit_batch(rzk_group *g, size_t B, const int32_t *x, const int8_t *r, const int32_t *y,
+                                int32_t *c, int32_t *t, uint8_t *ok_bitmap);
+int rzk_group_open_respond_batch(rzk_group *g, size_t B, const int32_t *y, const int8_t *r, const int8_t *d, int32_t *z);
+int rzk_group_open_verify_batch(rzk_group *g, size_t B, const int32_t *z, const int32_t *t, const int32_t *c1,
+                                const int8_t *d, uint8_t *verify_bitmap);
+int rzk_group_linear_commit_batch(rzk_group *g, size_t B, const int32_t *gg, const int32_t *x, const int8_t *rp, const int8_t *r,
+                                  const int32_t *y, const int32_t *yp, int32_t *gx, int32_t *cp, int32_t *c, int32_t *t,
+                                  int32_t *tp, int32_t *u, uint8_t *ok_bitmap);
+int rzk_group_linear_respond_batch(rzk_group *g, size_t B, const int32_t *y, const int32_t *yp, const int8_t *r, const int8_t *rp,
+                                   const int8_t *d, int32_t *z, int32_t *zp);
+int rzk_group_linear_verify_batch(rzk_group *g, size_t B, const int32_t *z, const int32_t *zp, const int32_t *c, const int32_t *cp,
+                                  const int32_t *gg, const int32_t *t, const int32_t *tp, const int32_t *u, const int8_t *d,
+                                  uint8_t *verify_bitmap);
+int rzk_group_sum_commit_batch(rzk_group *g, size_t B, uint32_t T, const int32_t *gs, const int32_t *xs, const int8_t *rp,
+                               const int8_t *rs, const int32_t *ys, const int32_t *yp, int32_t *xp, int32_t *cp, int32_t *cs,
+                               int32_t *ts, int32_t *tp, int32_t *u, uint8_t *ok_bitmap);
+int rzk_group_sum_respond_batch(rzk_group *g, size_t B, uint32_t T, const int32_t *ys, const int32_t *yp, const int8_t *rs,
+                                const int8_t *rp, const int8_t *d, int32_t *zs, int32_t *zp);
+int rzk_group_sum_verify_batch(rzk_group *g, size_t B, uint32_t T, const int32_t *zs, const int32_t *zp, const int32_t *cs,
+                               const int32_t *cp, const int32_t *gs, const int32_t *ts, const int32_t *tp, const int32_t *u,
+                               const int8_t *d, uint8_t *verify_bitmap);
+
 #ifdef __cplusplus
 }
 #endif

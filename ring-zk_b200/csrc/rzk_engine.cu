@@ -14,6 +14,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <string>
 #include <type_traits>
 #include <vector>
@@ -503,7 +505,7 @@ int launch_vm(rzk_engine *e, VmLaunch &K, cudaStream_t s)
         K.cta_sync = (e->pp_mode == 2) ? 0u : 2u;     // strict alternation already keeps each group in step
     }
     const size_t smem = VmSmem<NP, MODE>::bytes(warps, K.hw_words);
-    static bool configured[16] = {};   // per device
+    static std::atomic<bool> configured[16];   // per device; engines of a group run on separate threads   // per device
     if (!configured[e->device & 15]) {
         RZK_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
         configured[e->device & 15] = true;
@@ -586,7 +588,7 @@ int launch_commit_f64(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r
     int warps = kF64Warps;
     const uint32_t want = (uint32_t)((B + (uint64_t)e->num_sms - 1) / (uint64_t)e->num_sms);
     if ((uint32_t)warps > want) warps = (int)(want ? want : 1);
-    static bool configured[16] = {};
+    static std::atomic<bool> configured[16];   // per device; engines of a group run on separate threads
     if (!configured[e->device & 15]) {
         RZK_CUDA(e, cudaFuncSetAttribute(rzk_commit_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f64_smem_bytes(kF64Warps)));
         configured[e->device & 15] = true;
@@ -632,7 +634,7 @@ int launch_commit_hybrid(rzk_engine *e, VmLaunch &K, size_t B, const int32_t *x,
     RZK_CUDA(e, cudaMemsetAsync(H.work, 0, sizeof(uint32_t), s));
     const size_t smem = sizeof(uint32_t) * (size_t)VmSmem<1, MODE_SPLITKEY>::kTables + sizeof(double) * kF64TabD +
                         sizeof(uint32_t) * (size_t)H.int_warps * 2 * K.hw_words + sizeof(double) * (size_t)(warps - H.int_warps) * 2 * kF64BufD;
-    static bool configured[16] = {};
+    static std::atomic<bool> configured[16];   // per device; engines of a group run on separate threads
     if (!configured[e->device & 15]) {
         RZK_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));   // 16 B of static smem
         configured[e->device & 15] = true;
@@ -714,7 +716,7 @@ int dev_respond(rzk_engine *e, size_t items, const int32_t *y, const int8_t *r, 
         const uint32_t want = (uint32_t)((items + (uint64_t)e->num_sms - 1) / (uint64_t)e->num_sms);
         if ((uint32_t)warps > want) warps = (int)(want ? want : 1);
         const size_t smem = sizeof(uint32_t) * (size_t)warps * kSpWarpWords;
-        static bool configured[16] = {};
+        static std::atomic<bool> configured[16];   // per device; engines of a group run on separate threads
         if (!configured[e->device & 15]) {
             RZK_CUDA(e, cudaFuncSetAttribute(rzk_respond_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)(sizeof(uint32_t) * 16 * kSpWarpWords)));
@@ -1467,5 +1469,192 @@ int rzk_unpack_i64(rzk_engine *e, size_t count, const int32_t *src, int64_t *dst
     for (size_t i = whole * kN; i < count; ++i) dst[i] = src[i];
     return RZK_OK;
 }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------ several GPUs behind one handle
+
+struct rzk_group {
+    std::vector<rzk_engine *> eng;
+    std::string err;
+};
+
+namespace {
+
+// poly counts are in units of N coefficients per item; o(ptr, per_item, start) offsets a typed pointer
+template <class T>
+T *off(T *p, size_t per_item_elems, size_t start) { return p ? p + per_item_elems * start : nullptr; }
+
+// fn(engine, start, count) on one worker thread per engine over contiguous 8-aligned ranges
+template <class F>
+int group_run(rzk_group *g, size_t B, F &&fn)
+{
+    if (!g || g->eng.empty()) return RZK_ERR_INVALID;
+    const size_t n = g->eng.size();
+    size_t per = (B + n - 1) / n;
+    per = (per + 7) / 8 * 8;
+    std::vector<int> rc(n, RZK_OK);
+    std::vector<std::thread> th;
+    for (size_t i = 0; i < n; ++i) {
+        const size_t lo = std::min(B, i * per), hi = std::min(B, lo + per);
+        if (hi == lo) continue;
+        th.emplace_back([&, i, lo, hi] { rc[i] = fn(g->eng[i], lo, hi - lo); });
+    }
+    for (auto &t : th) t.join();
+    for (size_t i = 0; i < n; ++i)
+        if (rc[i] != RZK_OK) {
+            g->err = "device " + std::to_string(g->eng[i]->device) + ": " + g->eng[i]->err;
+            return rc[i];
+        }
+    return RZK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rzk_group_create(const rzk_params *params, const int *device_ids, int n_devices, rzk_group **out)
+{
+    if (!params || !device_ids || n_devices < 1 || !out) return fail(nullptr, RZK_ERR_INVALID, "null argument");
+    *out = nullptr;
+    rzk_group *g = new rzk_group();
+    for (int i = 0; i < n_devices; ++i) {
+        rzk_engine *e = nullptr;
+        const int rc = rzk_create(params, device_ids[i], &e);
+        if (rc != RZK_OK) { rzk_group_destroy(g); return rc; }
+        g->eng.push_back(e);
+    }
+    *out = g;
+    return RZK_OK;
+}
+
+void rzk_group_destroy(rzk_group *g)
+{
+    if (!g) return;
+    for (auto *e : g->eng) rzk_destroy(e);
+    delete g;
+}
+
+int rzk_group_size(const rzk_group *g) { return g ? (int)g->eng.size() : 0; }
+const char *rzk_group_last_error(const rzk_group *g) { return g ? g->err.c_str() : g_create_err.c_str(); }
+
+uint64_t rzk_group_kernel_launches(const rzk_group *g)
+{
+    uint64_t n = 0;
+    if (g) for (auto *e : g->eng) n += e->launches;
+    return n;
+}
+
+int rzk_group_set_key(rzk_group *g, const int64_t *a1, const int64_t *a2)
+{
+    if (!g) return RZK_ERR_INVALID;
+    for (auto *e : g->eng) {
+        const int rc = rzk_set_key(e, a1, a2);
+        if (rc != RZK_OK) { g->err = e->err; return rc; }
+    }
+    return RZK_OK;
+}
+
+#define POLY(p, polys, s) off(p, (size_t)(polys) * kN, s)
+#define BITS(p, s) ((p) ? (p) + (s) / 8 : nullptr)
+
+int rzk_group_commit_batch(rzk_group *g, size_t B, const int32_t *x, const int8_t *r, int32_t *c, uint8_t *ok)
+{
+    return group_run(g, B, [&](rzk_engine *e, size_t s, size_t n) {
+        return rzk_commit_batch(e, n, POLY(x, 1, s), POLY(r, 3, s), POLY(c, 2, s), BITS(ok, s));
+    });
+}
+
+int rzk_group_commitment_verify_batch(rzk_group *g, size_t B, const int32_t *c, const int32_t *x, const int8_t *r,
+                                      const int8_t *f, uint8_t *bm)
+{
+    return group_run(g, B, [&](rzk_engine *e, size_t s, size_t n) {
+        return rzk_commitment_verify_batch(e, n, POLY(c, 2, s), POLY(x, 1, s), POLY(r, 3, s), POLY(f, 1, s), BITS(bm, s));
+    });
+}
+
+int rzk_group_open_commit_batch(rzk_group *g, size_t B, const int32_t *x, const int8_t *r, const int32_t *y,
+                                int32_t *c, int32_t *t, uint8_t *ok)
+{
+    return group_run(g, B, [&](rzk_engine *e, size_t s, size_t n) {
+        return rzk_open_commit_batch(e, n, POLY(x, 1, s), POLY(r, 3, s), POLY(y, 3, s), POLY(c, 2, s), POLY(t, 1, s), BITS(ok, s));
+    });
+}
+
+int rzk_group_open_respond_batch(rzk_group *g, size_t B, const int32_t *y, const int8_t *r, const int8_t *d, int32_t *z)
+{
+    return group_run(g, B, [&](rzk_engine *e, size_t s, size_t n) {
+        return rzk_open_respond_batch(e, n, POLY(y, 3, s), POLY(r, 3, s), POLY(d, 1, s), POLY(z, 3, s));
+    });
+}
+
+int rzk_group_open_verify_batch(rzk_group *g, size_t B, const int32_t *z, const int32_t *t, const int32_t *c1,
+                                const int8_t *d, uint8_t *bm)
+{
+    return group_run(g, B, [&](rzk_engine *e, size_t s, size_t n) {
+        return rzk_open_verify_batch(e, n, POLY(z, 3, s), POLY(t, 1, s), POLY(c1, 1, s), POLY(d, 1, s), BITS(bm, s));
+    });
+}
+
+int rzk_group_linear_commit_batch(rzk_group *g, size_t B, const int32_t *gg, const int32_t *x, const int8_t *rp, const int8_t *r,
+                                  const int32_t *y, const int32_t *yp, int32_t *gx, int32_t *cp, int32_t *c, int32_t *t,
+                                  int32_t *tp, int32_t *u, uint8_t *ok)
+{
+    return group_run(g, B, [&](rzk_engine *e, size_t s, size_t n) {
+        return rzk_linear_commit_batch(e, n, POLY(gg, 1, s), POLY(x, 1, s), POLY(rp, 3, s), POLY(r, 3, s), POLY(y, 3, s), POLY(yp, 3, s),
+                                       POLY(gx, 1, s), POLY(cp, 2, s), POLY(c, 2, s), POLY(t, 1, s), POLY(tp, 1, s), POLY(u, 1, s), BITS(ok, s));
+    });
+}
+
+int rzk_group_linear_respond_batch(rzk_group *g, size_t B, const int32_t *y, const int32_t *yp, const int8_t *r, const int8_t *rp,
+                                   const int8_t *d, int32_t *z, int32_t *zp)
+{
+    return group_run(g, B, [&](rzk_engine *e, size_t s, size_t n) {
+        return rzk_linear_respond_batch(e, n, POLY(y, 3, s), POLY(yp, 3, s), POLY(r, 3, s), POLY(rp, 3, s), POLY(d, 1, s),
+                                        POLY(z, 3, s), POLY(zp, 3, s));
+    });
+}
+
+int rzk_group_linear_verify_batch(rzk_group *g, size_t B, const int32_t *z, const int32_t *zp, const int32_t *c, const int32_t *cp,
+                                  const int32_t *gg, const int32_t *t, const int32_t *tp, const int32_t *u, const int8_t *d, uint8_t *bm)
+{
+    return group_run(g, B, [&](rzk_engine *e, size_t s, size_t n) {
+        return rzk_linear_verify_batch(e, n, POLY(z, 3, s), POLY(zp, 3, s), POLY(c, 2, s), POLY(cp, 2, s), POLY(gg, 1, s), POLY(t, 1, s),
+                                       POLY(tp, 1, s), POLY(u, 1, s), POLY(d, 1, s), BITS(bm, s));
+    });
+}
+
+int rzk_group_sum_commit_batch(rzk_group *g, size_t B, uint32_t T, const int32_t *gs, const int32_t *xs, const int8_t *rp,
+                               const int8_t *rs, const int32_t *ys, const int32_t *yp, int32_t *xp, int32_t *cp, int32_t *cs,
+                               int32_t *ts, int32_t *tp, int32_t *u, uint8_t *ok)
+{
+    return group_run(g, B, [&](rzk_engine *e, size_t s, size_t n) {
+        return rzk_sum_commit_batch(e, n, T, POLY(gs, T, s), POLY(xs, T, s), POLY(rp, 3, s), POLY(rs, 3 * T, s), POLY(ys, 3 * T, s),
+                                    POLY(yp, 3, s), POLY(xp, 1, s), POLY(cp, 2, s), POLY(cs, 2 * T, s), POLY(ts, T, s), POLY(tp, 1, s),
+                                    POLY(u, 1, s), BITS(ok, s));
+    });
+}
+
+int rzk_group_sum_respond_batch(rzk_group *g, size_t B, uint32_t T, const int32_t *ys, const int32_t *yp, const int8_t *rs,
+                                const int8_t *rp, const int8_t *d, int32_t *zs, int32_t *zp)
+{
+    return group_run(g, B, [&](rzk_engine *e, size_t s, size_t n) {
+        return rzk_sum_respond_batch(e, n, T, POLY(ys, 3 * T, s), POLY(yp, 3, s), POLY(rs, 3 * T, s), POLY(rp, 3, s), POLY(d, 1, s),
+                                     POLY(zs, 3 * T, s), POLY(zp, 3, s));
+    });
+}
+
+int rzk_group_sum_verify_batch(rzk_group *g, size_t B, uint32_t T, const int32_t *zs, const int32_t *zp, const int32_t *cs,
+                               const int32_t *cp, const int32_t *gs, const int32_t *ts, const int32_t *tp, const int32_t *u,
+                               const int8_t *d, uint8_t *bm)
+{
+    return group_run(g, B, [&](rzk_engine *e, size_t s, size_t n) {
+        return rzk_sum_verify_batch(e, n, T, POLY(zs, 3 * T, s), POLY(zp, 3, s), POLY(cs, 2 * T, s), POLY(cp, 2, s), POLY(gs, T, s),
+                                    POLY(ts, T, s), POLY(tp, 1, s), POLY(u, 1, s), POLY(d, 1, s), BITS(bm, s));
+    });
+}
+
+#undef POLY
+#undef BITS
 
 }  // extern "C"

@@ -93,7 +93,12 @@ _SIGS = {
     "rzk_unpack_i64": "zpp",
     "rzk_sync": "p",
 }
-EXPORTS = sorted(list(_SIGS) + ["rzk_default_params", "rzk_create", "rzk_destroy", "rzk_last_error", "rzk_device",
+_GROUP_HOST = ["rzk_commit_batch", "rzk_commitment_verify_batch", "rzk_open_commit_batch", "rzk_open_respond_batch",
+               "rzk_open_verify_batch", "rzk_linear_commit_batch", "rzk_linear_respond_batch", "rzk_linear_verify_batch",
+               "rzk_sum_commit_batch", "rzk_sum_respond_batch", "rzk_sum_verify_batch"]
+_GROUP_SIGS = {n.replace("rzk_", "rzk_group_", 1): _SIGS[n] for n in _GROUP_HOST}
+EXPORTS = sorted(list(_SIGS) + list(_GROUP_SIGS) + ["rzk_group_create", "rzk_group_destroy", "rzk_group_size", "rzk_group_last_error",
+                                                    "rzk_group_set_key", "rzk_group_kernel_launches"] + ["rzk_default_params", "rzk_create", "rzk_destroy", "rzk_last_error", "rzk_device",
                                 "rzk_sigma", "rzk_commit_bound", "rzk_verify_bound", "rzk_small_limit",
                                 "rzk_set_key", "rzk_host_alloc", "rzk_host_free", "rzk_kernel_launches"])
 
@@ -132,6 +137,21 @@ def lib():
     L.rzk_host_alloc.argtypes = [C.c_size_t]
     L.rzk_host_free.argtypes = [_VP]
     L.rzk_host_free.restype = None
+    for name, sig in _GROUP_SIGS.items():
+        fn = getattr(L, name)
+        fn.restype = C.c_int
+        fn.argtypes = [_VP] + [kinds[c] for c in sig]
+    L.rzk_group_create.restype = C.c_int
+    L.rzk_group_create.argtypes = [C.POINTER(RzkParams), C.POINTER(C.c_int), C.c_int, C.POINTER(_VP)]
+    L.rzk_group_destroy.argtypes = [_VP]
+    L.rzk_group_destroy.restype = None
+    L.rzk_group_size.argtypes = [_VP]
+    L.rzk_group_last_error.restype = C.c_char_p
+    L.rzk_group_last_error.argtypes = [_VP]
+    L.rzk_group_set_key.restype = C.c_int
+    L.rzk_group_set_key.argtypes = [_VP, _VP, _VP]
+    L.rzk_group_kernel_launches.restype = C.c_uint64
+    L.rzk_group_kernel_launches.argtypes = [_VP]
     _lib = L
     return L
 
@@ -344,3 +364,48 @@ class Engine:
 def unpack_bitmap(bm, B):
     """bitmap (uint8, LSB first) -> bool array of length B."""
     return np.unpackbits(np.asarray(bm, dtype=np.uint8), bitorder="little")[:B].astype(bool)
+
+
+
+class Group(Engine):
+    """Several devices behind one handle (rzk_group_*): one engine and one host worker thread per listed device,
+    the batch split into contiguous 8-aligned item ranges.  Same host methods as Engine (commit, open_*, linear_*,
+    sum_*, commitment_verify); the `_dev` entry points belong to single engines."""
+
+    def __init__(self, device_ids, N=512, params: RzkParams | None = None):
+        self.L = lib()
+        self.params = params if params is not None else self.L.rzk_default_params(N)
+        self.N = self.params.N
+        ids = (C.c_int * len(device_ids))(*device_ids)
+        h = _VP()
+        rc = self.L.rzk_group_create(C.byref(self.params), ids, len(device_ids), C.byref(h))
+        if rc != RZK_OK:
+            raise RzkError(rc, (self.L.rzk_last_error(None) or b"").decode())
+        self.h = h
+        self.devices = list(device_ids)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.rzk_group_destroy(self.h)
+            self.h = None
+
+    def _call(self, name, *args):
+        gname = name.replace("rzk_", "rzk_group_", 1)
+        if gname not in _GROUP_SIGS:
+            raise AttributeError(f"{name} has no group form")
+        rc = getattr(self.L, gname)(self.h, *args)
+        if rc != RZK_OK:
+            raise RzkError(rc, (self.L.rzk_group_last_error(self.h) or b"").decode())
+
+    def size(self):
+        return int(self.L.rzk_group_size(self.h))
+
+    def kernel_launches(self):
+        return int(self.L.rzk_group_kernel_launches(self.h))
+
+    def set_key(self, a1, a2):
+        a1 = np.ascontiguousarray(a1, dtype=np.int64)
+        a2 = np.ascontiguousarray(a2, dtype=np.int64)
+        rc = self.L.rzk_group_set_key(self.h, a1.ctypes.data, a2.ctypes.data)
+        if rc != RZK_OK:
+            raise RzkError(rc, (self.L.rzk_group_last_error(self.h) or b"").decode())

@@ -418,3 +418,47 @@ def test_device_outputs_stay_in_bounds(setup):
         z_o = o.open_respond_batch(ys, rs, ds)
         assert (z[idx].cpu().numpy() == z_o).all() and (t[idx].cpu().numpy() == t_o).all()
         assert (c[[0, B - 1]].cpu().numpy() == c_o[[0, 2]]).all()
+
+
+def test_device_group_matches_single_engine(setup):
+    """rzk_group_*: one engine + one host thread per listed device, the batch split in 8-aligned contiguous ranges.
+    Results equal the single-engine ones bit for bit.  With one GPU the group lists device 0 three times (three
+    engines, three threads); with more GPUs it uses them."""
+    import torch
+    eng, o, s = setup
+    ndev = torch.cuda.device_count()
+    ids = list(range(ndev)) if ndev >= 2 else [0, 0, 0]
+    grp = engine.Group(ids, N=N)
+    try:
+        a1p, a2p = synth.Synth(42, N=N).key()
+        grp.set_key_blocks(a1p, a2p)
+        assert grp.size() == len(ids)
+        B = 5003                                           # ragged: ranges of 1672, 1672, 1659 items on three engines
+        x, r, y, d = s.message(B, ragged=True), s.small(B), s.gaussian(B), s.challenge(B)
+        c, t, ok = eng.open_commit(x, r, y)
+        cg, tg, okg = grp.open_commit(x, r, y)
+        assert (c == cg).all() and (t == tg).all() and (ok == okg).all()
+        z = eng.open_respond(y, r, d)
+        assert (z == grp.open_respond(y, r, d)).all()
+        zt = z.copy(); zt[::7, 2, 3] += 1
+        c1 = np.ascontiguousarray(c[:, :1])
+        v, vg = eng.open_verify(zt, t, c1, d), grp.open_verify(zt, t, c1, d)
+        assert (v == vg).all() and UB(vg, B).sum() == B - len(range(0, B, 7))
+        assert (grp.commitment_verify(c, x, r) == eng.commitment_verify(c, x, r)).all()
+        cc, okc = grp.commit(x, r)
+        assert (cc == c).all() and UB(okc, B).all()
+        # Linear and Sum through the group (small batches: more engines than 8-item ranges is fine)
+        Bl, T = 21, 3
+        g, rp, yp = s.scalar(Bl), s.small(Bl), s.gaussian(Bl)
+        L1 = eng.linear_commit(g, x[:Bl], rp, r[:Bl], y[:Bl], yp)
+        L2 = grp.linear_commit(g, x[:Bl], rp, r[:Bl], y[:Bl], yp)
+        assert all((L1[k] == L2[k]).all() for k in L1)
+        gs, xs, rs, ys = s.scalar(Bl, T), s.uniform_q(Bl, T, 1), s.small(Bl, T), s.gaussian(Bl, T)
+        S1 = eng.sum_commit(gs, xs, rp, rs, ys, yp)
+        S2 = grp.sum_commit(gs, xs, rp, rs, ys, yp)
+        assert all((S1[k] == S2[k]).all() for k in S1)
+        zs, zp = grp.sum_respond(ys, yp, rs, rp, d[:Bl])
+        assert UB(grp.sum_verify(zs, zp, S2["cs"], S2["cp"], gs, S2["ts"], S2["tp"], S2["u"], d[:Bl]), Bl).all()
+        assert grp.kernel_launches() > 0
+    finally:
+        grp.close()
