@@ -137,6 +137,54 @@ def cpu_commit_rate(target_s=12.0, seed=7):
     return n / dt, cores, n, dt
 
 
+def single_call_latency(eng, oracle_obj=None, reps=30):
+    """Median latency in microseconds of one call on ONE item through the host C ABI (pageable numpy buffers) for the
+    phases the reference's own Criterion benches time (benches/bench.rs:35-305: N = 512, Sum with 4 terms).
+    With oracle_obj the same calls are timed on the CPU restatement, one thread (cpu_baseline leg only)."""
+    pkg = importlib.import_module("ring-zk_b200")
+    s = pkg.synth.Synth(5, N=N)
+    B, T = 1, 4
+    x, r, y, d = s.message(B), s.small(B), s.gaussian(B), s.challenge(B)
+    g, rp, yp = s.scalar(B), s.small(B), s.gaussian(B)
+    gs, xs, rs, ys = s.scalar(B, T), s.uniform_q(B, T, 1), s.small(B, T), s.gaussian(B, T)
+    c, t, _ = eng.open_commit(x, r, y)
+    z = eng.open_respond(y, r, d)
+    c1 = np.ascontiguousarray(c[:, :1])
+    L = eng.linear_commit(g, x, rp, r, y, yp)
+    lz, lzp = eng.linear_respond(y, yp, r, rp, d)
+    S = eng.sum_commit(gs, xs, rp, rs, ys, yp)
+    zs, zp = eng.sum_respond(ys, yp, rs, rp, d)
+    o = oracle_obj
+    calls = {
+        "open_proof_commit": (lambda: eng.open_commit(x, r, y), lambda: o.open_commit_batch(x, r, y, 1)),
+        "open_proof_create_response": (lambda: eng.open_respond(y, r, d), lambda: o.open_respond_batch(y, r, d, 1)),
+        "open_proof_verify": (lambda: eng.open_verify(z, t, c1, d), lambda: o.open_verify_batch(z, t, c1, d, 1)),
+        "linear_proof_commit": (lambda: eng.linear_commit(g, x, rp, r, y, yp), lambda: o.linear_commit_batch(g, x, rp, r, y, yp, 1)),
+        "linear_proof_create_response": (lambda: eng.linear_respond(y, yp, r, rp, d), lambda: o.linear_respond_batch(y, yp, r, rp, d, 1)),
+        "linear_proof_verify": (lambda: eng.linear_verify(lz, lzp, L["c"], L["cp"], g, L["t"], L["tp"], L["u"], d),
+                                lambda: o.linear_verify_batch(lz, lzp, L["c"], L["cp"], g, L["t"], L["tp"], L["u"], d, 1)),
+        "sum_proof_commit": (lambda: eng.sum_commit(gs, xs, rp, rs, ys, yp), lambda: o.sum_commit_batch(gs, xs, rp, rs, ys, yp, 1)),
+        "sum_proof_create_response": (lambda: eng.sum_respond(ys, yp, rs, rp, d), lambda: o.sum_respond_batch(ys, yp, rs, rp, d, 1)),
+        "sum_proof_verify": (lambda: eng.sum_verify(zs, zp, S["cs"], S["cp"], gs, S["ts"], S["tp"], S["u"], d),
+                             lambda: o.sum_verify_batch(zs, zp, S["cs"], S["cp"], gs, S["ts"], S["tp"], S["u"], d, 1)),
+    }
+
+    def med(fn, n):
+        ts = []
+        for _ in range(n):
+            t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
+        return round(float(np.median(ts)) * 1e6, 1)
+    out = {}
+    for name, (gpu, cpu) in calls.items():
+        if o is None:
+            for _ in range(3):
+                gpu()
+            out[name] = med(gpu, reps)
+        else:
+            out[name] = med(cpu, 3)
+    return out
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path (C restatement; the Rust crate cannot be built here)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -354,6 +402,8 @@ def main():
                            "frac_of_int_mulmod_peak": 7268352 * BS / (ms_s * 1e-3) / (MEASURED_MULMOD_TPS * 1e12)}
         del gs, xs, rs, ys, xp, cps, css, tss, tps, us, zs, zps
         torch.cuda.empty_cache()
+        if world == 1:
+            extras["single_call_latency_us"] = single_call_latency(eng)
 
     # ---- end to end through the host C ABI (pinned host buffers, H2D + D2H inside the timed region) ----
     e2e = None
@@ -392,6 +442,9 @@ def main():
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{n} commitments in {dt:.1f} s, C restatement of the reference (schoolbook products, "
                          f"reference operation order), OpenMP over items"}
+        if not args.no_extras:
+            from oracle import oracle as orc
+            cpu["single_call_latency_us_1thread"] = single_call_latency(eng, orc.Oracle(orc.Params(N=N), *key))
 
     if rank == 0:
         line = {

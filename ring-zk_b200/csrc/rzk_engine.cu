@@ -413,6 +413,7 @@ struct rzk_engine {
     uint32_t hyb_int_warps = 8;     // RZK_HYB_INT_WARPS: integer-path warps per CTA in the hybrid kernel (of 16)
     uint32_t commit_mode = 2;       // RZK_COMMIT_MODE: 0 = integer split-key program, 1 = FP64 pipe, 2 = both pipes (hybrid; measured best)
     uint32_t *d_misc = nullptr;     // [0] range word, [1] dummy flags word
+    uint32_t *h_range = nullptr;    // pinned host copy of the range word (single-chunk calls)
     bool has_key = false;
     uint64_t sigma = 0, cbound = 0, vbound = 0;
     uint32_t small_lim = 0;
@@ -499,7 +500,8 @@ int launch_vm(rzk_engine *e, VmLaunch &K, cudaStream_t s)
     const uint32_t per_warp = SPLIT ? 1 : 2;
     // do not launch more warps per CTA than the batch can use
     const uint32_t want = (uint32_t)((K.n_items + (uint64_t)e->num_sms * per_warp - 1) / ((uint64_t)e->num_sms * per_warp));
-    if ((uint32_t)warps > want) warps = (int)(want ? want : 1);
+    // (but at least 4: the whole CTA stages the tables, which is what a single call on one item waits for)
+    if ((uint32_t)warps > want) warps = (int)std::max<uint32_t>(want, (uint32_t)std::min(4, warps));
     if (e->pp_mode && !std::is_void<SP>::value && warps >= 2 && (warps & 1) == 0) {
         K.pp_mode = e->pp_mode;
         K.cta_sync = (e->pp_mode == 2) ? 0u : 2u;     // strict alternation already keeps each group in step
@@ -885,8 +887,11 @@ int run_chunked(rzk_engine *e, size_t B, std::vector<HArr> &arrs, size_t scratch
             ps.cap = need;
         }
     }
+    // the range word is cleared on the first stream; the other streams are only used (and must wait) when the batch
+    // spans several chunks -- a single call on one item stays on one stream with one synchronisation at the end
+    const size_t nchunks = (B + chunk - 1) / chunk;
     RZK_CUDA(e, cudaMemsetAsync(e->d_misc, 0, sizeof(uint32_t), e->pipe[0].stream));
-    RZK_CUDA(e, cudaStreamSynchronize(e->pipe[0].stream));
+    if (nchunks > 1) RZK_CUDA(e, cudaStreamSynchronize(e->pipe[0].stream));
     std::vector<void *> dptr(arrs.size());
     int ci = 0;
     for (size_t c0 = 0; c0 < B; c0 += chunk, ++ci) {
@@ -915,9 +920,15 @@ int run_chunked(rzk_engine *e, size_t B, std::vector<HArr> &arrs, size_t scratch
                 RZK_CUDA(e, cudaMemcpyAsync((char *)arrs[i].out + c0 * arrs[i].per_item, dptr[i],
                                             n * arrs[i].per_item, cudaMemcpyDeviceToHost, s));
     }
-    for (int i = 0; i < kPipe; ++i) RZK_CUDA(e, cudaStreamSynchronize(e->pipe[i].stream));
     uint32_t range = 0;
-    RZK_CUDA(e, cudaMemcpy(&range, e->d_misc, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (nchunks == 1) {
+        RZK_CUDA(e, cudaMemcpyAsync(e->h_range, e->d_misc, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->pipe[0].stream));
+        RZK_CUDA(e, cudaStreamSynchronize(e->pipe[0].stream));
+        range = *e->h_range;
+    } else {
+        for (int i = 0; i < kPipe; ++i) RZK_CUDA(e, cudaStreamSynchronize(e->pipe[i].stream));
+        RZK_CUDA(e, cudaMemcpy(&range, e->d_misc, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    }
     if (range & FLAG_RANGE)
         return fail(e, RZK_ERR_RANGE, "a masking vector y exceeds rzk_small_limit(); affected outputs are not exact");
     return RZK_OK;
@@ -1019,6 +1030,7 @@ int rzk_create(const rzk_params *params, int device, rzk_engine **out)
         cu(cudaMemcpy(e->d_f64tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice), "cudaMemcpy(f64tab)");
     }
     cu(cudaMalloc(&e->d_misc, 64), "cudaMalloc(misc)");
+    cu(cudaMallocHost(&e->h_range, 64), "cudaMallocHost(range)");
     if (rc == RZK_OK) cu(cudaMemset(e->d_misc, 0, 64), "cudaMemset(misc)");
     for (int i = 0; i < kPipe && rc == RZK_OK; ++i) cu(cudaStreamCreateWithFlags(&e->pipe[i].stream, cudaStreamNonBlocking), "cudaStreamCreate");
     if (rc != RZK_OK) { rzk_destroy(e); return rc; }
@@ -1043,6 +1055,7 @@ void rzk_destroy(rzk_engine *e)
     if (e->d_f64tab) cudaFree(e->d_f64tab);
     if (e->d_need) cudaFree(e->d_need);
     if (e->d_misc) cudaFree(e->d_misc);
+    if (e->h_range) cudaFreeHost(e->h_range);
     delete e;
 }
 

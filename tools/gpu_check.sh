@@ -1,3 +1,4 @@
-# Development helper: GPU test suite (and whatever else is being checked) on the box.
+# Development helper: runs whatever is being checked on the GPU box.
 set -x
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
+python tools/latency.py
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
