@@ -966,6 +966,7 @@ int rzk_create(const rzk_params *params, int device, rzk_engine **out)
     if (!params || !out) return fail(nullptr, RZK_ERR_INVALID, "null argument");
     *out = nullptr;
     const rzk_params &P = *params;
+    if (kPrimeList[0] != kStaticPrime0) return fail(nullptr, RZK_ERR_INVALID, "prime slot 0 differs from kStaticPrime0");
     if (P.N != kN || P.n != 1 || P.k != 3 || P.l != 1)
         return fail(nullptr, RZK_ERR_UNSUPPORTED, "only N=512, (n,k,l)=(1,3,1) is accelerated");
     if (P.q != 3515337053LL || P.b < 1 || P.b > 127 || P.kappa < 1)

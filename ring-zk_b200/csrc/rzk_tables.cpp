@@ -7,7 +7,7 @@
 
 namespace rzk {
 
-const uint32_t kPrimeList[kNumPrimeSlots] = {
+const uint32_t kPrimeList[kNumPrimeSlots] = {      // slot 0 is also the compile-time prime of the split-key program (kStaticPrime0)
     1073692673u, 1073668097u, 1073655809u,   // < 2^30
     195198977u, 195186689u, 195162113u,      // < 2^32 / 22
 };

@@ -57,12 +57,14 @@ struct uint2 { uint32_t x, y; };
 namespace rzk {
 
 enum { MODE_SEQ = 0, MODE_SPLIT = 1, MODE_SPLITKEY = 2 };
+constexpr uint32_t kStaticPrime0 = 1073692673u;      // kPrimeList[0] (rzk_tables.cpp); 4p - 1 < 2^32
 
 struct Lane {
     uint32_t cur[kElems];
     uint32_t acc0[kElems];   // accumulator 0 lives in registers; accumulator 1 in the lane-private smem slot ctx.acc1
     PrimeC pc;               // constants of the prime this lane currently works with
     int pi;                  // its index in the launch's prime list
+    uint32_t cap;            // 4p - 1 when p is a compile-time constant (rzk_arith.cuh add_alu), else 0
     uint32_t fail;
     uint32_t rerr;
 };
@@ -137,7 +139,7 @@ __device__ __forceinline__ void pp_release(const VmLaunch &K, uint32_t &pp_count
 //   G1 stages S = 0..4: distance 16>>S in the strided layout, lane-uniform twiddles
 //   G2 stages S = 5..8: distance 256>>S in the contiguous layout, lane-specific twiddles
 template <int S, int DIR>
-RZK_VM void g1_stage(uint32_t (&a)[kElems], const uint2 *g1, uint32_t p, uint32_t p2, uint32_t z)
+RZK_VM void g1_stage(uint32_t (&a)[kElems], const uint2 *g1, uint32_t p, uint32_t p2, uint32_t z, uint32_t cap)
 {
     constexpr int half = 16 >> S;
     RZK_UNROLL
@@ -146,14 +148,14 @@ RZK_VM void g1_stage(uint32_t (&a)[kElems], const uint2 *g1, uint32_t p, uint32_
         RZK_UNROLL
         for (int j = 0; j < half; ++j) {
             const int i0 = b * 2 * half + j;
-            if (DIR == 0) ct_bfly(a[i0], a[i0 + half], w.x, w.y, p, p2, z);
-            else gs_bfly(a[i0], a[i0 + half], w.x, w.y, p, p2, z);
+            if (DIR == 0) ct_bfly(a[i0], a[i0 + half], w.x, w.y, p, p2, z, cap);
+            else gs_bfly(a[i0], a[i0 + half], w.x, w.y, p, p2, z, cap);
         }
     }
 }
 
 template <int S, int DIR>
-RZK_VM void g2_stage(uint32_t (&a)[kElems], const uint4 *tw4, uint32_t p, uint32_t p2, uint32_t z)
+RZK_VM void g2_stage(uint32_t (&a)[kElems], const uint4 *tw4, uint32_t p, uint32_t p2, uint32_t z, uint32_t cap)
 {
     constexpr int half = 256 >> S;                // 8,4,2,1
     constexpr int nb = 1 << (S - 4);              // 2,4,8,16 blocks
@@ -164,54 +166,54 @@ RZK_VM void g2_stage(uint32_t (&a)[kElems], const uint4 *tw4, uint32_t p, uint32
         RZK_UNROLL
         for (int j = 0; j < half; ++j) {
             const int i0 = (2 * b2) * 2 * half + j;
-            if (DIR == 0) ct_bfly(a[i0], a[i0 + half], q.x, q.y, p, p2, z);
-            else gs_bfly(a[i0], a[i0 + half], q.x, q.y, p, p2, z);
+            if (DIR == 0) ct_bfly(a[i0], a[i0 + half], q.x, q.y, p, p2, z, cap);
+            else gs_bfly(a[i0], a[i0 + half], q.x, q.y, p, p2, z, cap);
         }
         RZK_UNROLL
         for (int j = 0; j < half; ++j) {
             const int i0 = (2 * b2 + 1) * 2 * half + j;
-            if (DIR == 0) ct_bfly(a[i0], a[i0 + half], q.z, q.w, p, p2, z);
-            else gs_bfly(a[i0], a[i0 + half], q.z, q.w, p, p2, z);
+            if (DIR == 0) ct_bfly(a[i0], a[i0 + half], q.z, q.w, p, p2, z, cap);
+            else gs_bfly(a[i0], a[i0 + half], q.z, q.w, p, p2, z, cap);
         }
     }
 }
 
-RZK_VM void fwd_g1(uint32_t (&a)[kElems], const uint32_t *g1tab, uint32_t p, uint32_t p2, uint32_t z)
+RZK_VM void fwd_g1(uint32_t (&a)[kElems], const uint32_t *g1tab, uint32_t p, uint32_t p2, uint32_t z, uint32_t cap)
 {
     const uint2 *g1 = reinterpret_cast<const uint2 *>(g1tab);
-    g1_stage<0, 0>(a, g1, p, p2, z);
-    g1_stage<1, 0>(a, g1, p, p2, z);
-    g1_stage<2, 0>(a, g1, p, p2, z);
-    g1_stage<3, 0>(a, g1, p, p2, z);
-    g1_stage<4, 0>(a, g1, p, p2, z);
+    g1_stage<0, 0>(a, g1, p, p2, z, cap);
+    g1_stage<1, 0>(a, g1, p, p2, z, cap);
+    g1_stage<2, 0>(a, g1, p, p2, z, cap);
+    g1_stage<3, 0>(a, g1, p, p2, z, cap);
+    g1_stage<4, 0>(a, g1, p, p2, z, cap);
 }
 
-RZK_VM void fwd_g2(uint32_t (&a)[kElems], const uint32_t *tw, uint32_t p, uint32_t p2, uint32_t z)
+RZK_VM void fwd_g2(uint32_t (&a)[kElems], const uint32_t *tw, uint32_t p, uint32_t p2, uint32_t z, uint32_t cap)
 {
     const uint4 *tw4 = reinterpret_cast<const uint4 *>(tw);
-    g2_stage<5, 0>(a, tw4, p, p2, z);
-    g2_stage<6, 0>(a, tw4, p, p2, z);
-    g2_stage<7, 0>(a, tw4, p, p2, z);
-    g2_stage<8, 0>(a, tw4, p, p2, z);
+    g2_stage<5, 0>(a, tw4, p, p2, z, cap);
+    g2_stage<6, 0>(a, tw4, p, p2, z, cap);
+    g2_stage<7, 0>(a, tw4, p, p2, z, cap);
+    g2_stage<8, 0>(a, tw4, p, p2, z, cap);
 }
 
-RZK_VM void inv_g2(uint32_t (&a)[kElems], const uint32_t *tw, uint32_t p, uint32_t p2, uint32_t z)
+RZK_VM void inv_g2(uint32_t (&a)[kElems], const uint32_t *tw, uint32_t p, uint32_t p2, uint32_t z, uint32_t cap)
 {
     const uint4 *tw4 = reinterpret_cast<const uint4 *>(tw);
-    g2_stage<8, 1>(a, tw4, p, p2, z);
-    g2_stage<7, 1>(a, tw4, p, p2, z);
-    g2_stage<6, 1>(a, tw4, p, p2, z);
-    g2_stage<5, 1>(a, tw4, p, p2, z);
+    g2_stage<8, 1>(a, tw4, p, p2, z, cap);
+    g2_stage<7, 1>(a, tw4, p, p2, z, cap);
+    g2_stage<6, 1>(a, tw4, p, p2, z, cap);
+    g2_stage<5, 1>(a, tw4, p, p2, z, cap);
 }
 
-RZK_VM void inv_g1(uint32_t (&a)[kElems], const uint32_t *g1tab, uint32_t p, uint32_t p2, uint32_t z)
+RZK_VM void inv_g1(uint32_t (&a)[kElems], const uint32_t *g1tab, uint32_t p, uint32_t p2, uint32_t z, uint32_t cap)
 {
     const uint2 *g1 = reinterpret_cast<const uint2 *>(g1tab);
-    g1_stage<4, 1>(a, g1, p, p2, z);
-    g1_stage<3, 1>(a, g1, p, p2, z);
-    g1_stage<2, 1>(a, g1, p, p2, z);
-    g1_stage<1, 1>(a, g1, p, p2, z);
-    g1_stage<0, 1>(a, g1, p, p2, z);
+    g1_stage<4, 1>(a, g1, p, p2, z, cap);
+    g1_stage<3, 1>(a, g1, p, p2, z, cap);
+    g1_stage<2, 1>(a, g1, p, p2, z, cap);
+    g1_stage<1, 1>(a, g1, p, p2, z, cap);
+    g1_stage<0, 1>(a, g1, p, p2, z, cap);
 }
 
 // ---------------------------------------------------------------- global memory
@@ -263,7 +265,7 @@ RZK_VM void op_fwd(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const Op
 #if defined(__CUDA_ARCH__)
         pp_acquire(K);
 #endif
-        fwd_g1(L.cur, ctx.g1 + (L.pi * 2 + 0) * kG1Words, pc.p, pc.p2, pc.pad_);
+        fwd_g1(L.cur, ctx.g1 + (L.pi * 2 + 0) * kG1Words, pc.p, pc.p2, pc.pad_, L.cap);
         RZK_UNROLL
         for (int m = 0; m < kElems; ++m) {
             const int i = t + kLanes * m;
@@ -279,7 +281,7 @@ RZK_VM void op_fwd(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const Op
             const uint4 q = row[j];
             L.cur[4 * j + 0] = q.x; L.cur[4 * j + 1] = q.y; L.cur[4 * j + 2] = q.z; L.cur[4 * j + 3] = q.w;
         }
-        fwd_g2(L.cur, ctx.g2 + ((L.pi * 2 + 0) * kLanes + t) * kG2Words, L.pc.p, L.pc.p2, L.pc.pad_);
+        fwd_g2(L.cur, ctx.g2 + ((L.pi * 2 + 0) * kLanes + t) * kG2Words, L.pc.p, L.pc.p2, L.pc.pad_, L.cap);
     }
     RZK_SYNC();
 #if defined(__CUDA_ARCH__)
@@ -536,7 +538,7 @@ RZK_VM void inv_core(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const 
                 L.cur[4 * j + 0] = a.x; L.cur[4 * j + 1] = a.y; L.cur[4 * j + 2] = a.z; L.cur[4 * j + 3] = a.w;
             }
         }
-        inv_g2(L.cur, ctx.g2 + ((L.pi * 2 + 1) * kLanes + t) * kG2Words, pc.p, pc.p2, pc.pad_);
+        inv_g2(L.cur, ctx.g2 + ((L.pi * 2 + 1) * kLanes + t) * kG2Words, pc.p, pc.p2, pc.pad_, L.cap);
         uint4 *row = reinterpret_cast<uint4 *>(ctx.buf + 36 * t);
         RZK_UNROLL
         for (int j = 0; j < 8; ++j) {
@@ -554,7 +556,7 @@ RZK_VM void inv_core(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const 
             const int i = t + kLanes * m;
             L.cur[m] = ctx.buf[i + ((i >> 5) << 2)];
         }
-        inv_g1(L.cur, ctx.g1 + (L.pi * 2 + 1) * kG1Words, pc.p, pc.p2, pc.pad_);
+        inv_g1(L.cur, ctx.g1 + (L.pi * 2 + 1) * kG1Words, pc.p, pc.p2, pc.pad_, L.cap);
         RZK_UNROLL
         for (int m = 0; m < kElems; ++m) L.cur[m] = csub(L.cur[m], pc.p);     // [0,2p) -> [0,p)
     }
@@ -750,6 +752,7 @@ RZK_VM void vm_run_item(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs)
                 RZK_LANE;
                 L.pi = (MODE == MODE_SPLIT) ? ctx.hw : (MODE == MODE_SPLITKEY ? 0 : prime_iter);
                 L.pc = K.pc[L.pi];
+                L.cap = 0;
             }
             int q = seg_begin, loop_start = 0, loop_cnt = 0, it = 0;
             RZK_NOUNROLL
@@ -952,6 +955,12 @@ RZK_VM void sp_segments(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs)
                 RZK_LANE;
                 L.pi = (MODE == MODE_SPLIT) ? ctx.hw : (MODE == MODE_SPLITKEY ? 0 : prime_iter);
                 L.pc = K.pc[L.pi];
+                L.cap = 0;
+                if (MODE == MODE_SPLITKEY) {
+                    // one fixed prime (slot 0, checked at key setup): its constants become immediates
+                    L.pc.p = kStaticPrime0; L.pc.p2 = 2u * kStaticPrime0; L.pc.half = (kStaticPrime0 - 1u) / 2u;
+                    L.cap = 4u * kStaticPrime0 - 1u;
+                }
             }
             sp_exec<SP, NP, MODE, PC + 1>(K, lanes, ctxs, 0, prime_iter);
         }
