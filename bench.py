@@ -114,6 +114,16 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_commit_rate(target_s=12.0, seed=7):
     """Times the CPU restatement of the reference (oracle/, schoolbook products, the reference's own
     operation order incl. the identity/zero key blocks) on a bounded sample with all host threads."""
@@ -206,7 +216,7 @@ def run_reference(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample_items_per_step": n,
                    "note": "C restatement of the reference's CPU path (oracle/), not the Rust binary"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "cpu_model": cpu_model(),
                          "sample": f"{n} commitments per step, schoolbook O(N^2) products, OpenMP over items"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t_all0,
@@ -439,7 +449,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, cores, n, dt = cpu_commit_rate(target_s=12.0)
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "cpu_model": cpu_model(),
                "sample": f"{n} commitments in {dt:.1f} s, C restatement of the reference (schoolbook products, "
                          f"reference operation order), OpenMP over items"}
         if not args.no_extras:
