@@ -78,10 +78,10 @@ RZK_HD uint32_t mont_mul(uint32_t a, uint32_t b, uint32_t p, uint32_t pinv)
 // IADD3 instructions on the ALU pipe; without it ptxas turns them into IMAD.IADD on the FMA-heavy
 // pipe, which is the pipe the 32-bit multiplies saturate (ncu: sm__pipe_fmaheavy_cycles_active).
 
-// a + b for a, b in [0, 2p), kept on the ALU pipe.  z is the opaque zero described above; when the prime is a
-// compile-time constant (`cap` = 4p - 1 != 0) the add is written as min(a + b, 4p - 1) instead -- an identity
-// (a + b <= 4p - 2) the compiler cannot see through, which becomes one VIADDMNMX with an immediate: two register
-// operands instead of the three of IADD3 R, R, R (ncu: dispatch stalls on the three-register form).
+// a + b for a, b in [0, 2p), kept on the ALU pipe.  With `cap` != 0 the add is written as min(a + b, cap) for an
+// immediate cap >= 4p - 2 (0xFFFFFFFE covers every p < 2^30) -- an identity the compiler cannot see through, which
+// becomes one VIADDMNMX with an immediate: two register operands instead of the three of IADD3 R, R, R with the
+// opaque zero z described above (ncu: dispatch stalls on the three-register form).  cap == 0 keeps the z form.
 RZK_HD uint32_t add_alu(uint32_t a, uint32_t b, uint32_t z, uint32_t cap) { return cap ? umin32(a + b, cap) : a + b + z; }
 
 // Cooley-Tukey (forward) butterfly, Harvey lazy form: inputs in [0, 4p), outputs in [0, 4p).

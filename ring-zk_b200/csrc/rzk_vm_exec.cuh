@@ -58,13 +58,14 @@ namespace rzk {
 
 enum { MODE_SEQ = 0, MODE_SPLIT = 1, MODE_SPLITKEY = 2 };
 constexpr uint32_t kStaticPrime0 = 1073692673u;      // kPrimeList[0] (rzk_tables.cpp); 4p - 1 < 2^32
+constexpr uint32_t kAddCap = 0xFFFFFFFEu;            // >= 4p - 2 for every p < 2^30: min(a + b, kAddCap) == a + b in the butterflies
 
 struct Lane {
     uint32_t cur[kElems];
     uint32_t acc0[kElems];   // accumulator 0 lives in registers; accumulator 1 in the lane-private smem slot ctx.acc1
     PrimeC pc;               // constants of the prime this lane currently works with
     int pi;                  // its index in the launch's prime list
-    uint32_t cap;            // 4p - 1 when p is a compile-time constant (rzk_arith.cuh add_alu), else 0
+    uint32_t cap;            // immediate bound of the butterfly adds (rzk_arith.cuh add_alu): 4p - 1 for a compile-time p, else kAddCap
     uint32_t fail;
     uint32_t rerr;
 };
@@ -752,7 +753,7 @@ RZK_VM void vm_run_item(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs)
                 RZK_LANE;
                 L.pi = (MODE == MODE_SPLIT) ? ctx.hw : (MODE == MODE_SPLITKEY ? 0 : prime_iter);
                 L.pc = K.pc[L.pi];
-                L.cap = 0;
+                L.cap = kAddCap;
             }
             int q = seg_begin, loop_start = 0, loop_cnt = 0, it = 0;
             RZK_NOUNROLL
@@ -955,7 +956,7 @@ RZK_VM void sp_segments(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs)
                 RZK_LANE;
                 L.pi = (MODE == MODE_SPLIT) ? ctx.hw : (MODE == MODE_SPLITKEY ? 0 : prime_iter);
                 L.pc = K.pc[L.pi];
-                L.cap = 0;
+                L.cap = kAddCap;
                 if (MODE == MODE_SPLITKEY) {
                     // one fixed prime (slot 0, checked at key setup): its constants become immediates
                     L.pc.p = kStaticPrime0; L.pc.p2 = 2u * kStaticPrime0; L.pc.half = (kStaticPrime0 - 1u) / 2u;
