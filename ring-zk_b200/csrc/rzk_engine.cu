@@ -51,6 +51,57 @@ struct VmSmem {
     static size_t bytes(int warps, uint32_t hw_words) { return sizeof(uint32_t) * ((size_t)kTables + (size_t)warps * 2 * hw_words); }
 };
 
+// ------------------------------------------------------------------------------ TMA staging of the resident tables
+// Twiddle and key tiles are brought into shared memory with 1-D bulk copies (cp.async.bulk, SASS UBLKCP) issued by
+// one thread and tracked by an mbarrier; every thread then waits on the barrier's phase 0.  Sizes and addresses are
+// multiples of 16 bytes by construction (kG1Words, kG2Words, kPadWords; cudaMalloc bases).
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tma_init(uint64_t *bar)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void tma_expect(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void tma_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tma_wait(uint64_t *bar)
+{
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "WAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+                 "@!p bra WAIT_%=;\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// stages the twiddles and the key images of the NP primes of a launch
+template <int NP, int MODE>
+__device__ __forceinline__ void stage_int_tables(const VmLaunch &K, uint32_t *s_g1, uint32_t *s_g2, uint32_t *s_key, uint64_t *bar,
+                                                 bool issue)
+{
+    using S = VmSmem<NP, MODE>;
+    constexpr uint32_t g1b = 2 * kG1Words * 4, g2b = 2 * kLanes * kG2Words * 4, keyb = S::kKP * 2 * kPadWords * 4;
+    static_assert(g1b % 16 == 0 && g2b % 16 == 0 && keyb % 16 == 0, "bulk copies move multiples of 16 bytes");
+    if (issue) {
+        tma_expect(bar, NP * (g1b + g2b + keyb));
+        for (int i = 0; i < NP; ++i) {
+            const uint32_t slot = K.pc[i].slot;
+            tma_load(s_g1 + i * 2 * kG1Words, K.g1tab + (size_t)slot * (2 * kG1Words), g1b, bar);
+            tma_load(s_g2 + i * (2 * kLanes * kG2Words), K.g2tab + (size_t)slot * (2 * kLanes * kG2Words), g2b, bar);
+            tma_load(s_key + i * (S::kKP * 2 * kPadWords), K.keytab + (size_t)i * (S::kKP * 2 * kPadWords), keyb, bar);
+        }
+    }
+}
+
 // Persistent kernel: blockDim.x / 32 warps per CTA (as many as the program's shared-memory needs
 // allow, up to 16), one CTA per SM, each warp loops over its items.
 // SP = void: the generic kernel decodes K.ops at run time.  SP = a compile-time program descriptor
@@ -68,19 +119,12 @@ __global__ void __launch_bounds__(VmCfg<NP, MODE>::kMaxWarps * 32, 1) rzk_vm_ker
     uint32_t *s_hw = smem + S::kTables;
     const int nthreads = blockDim.x, warps = nthreads >> 5;
 
-    // stage the twiddles and the key image of every prime of this launch
-    for (int i = 0; i < NP; ++i) {
-        const uint32_t slot = K.pc[i].slot;
-        const uint32_t *g1src = K.g1tab + (size_t)slot * (2 * kG1Words);
-        for (int w = threadIdx.x; w < 2 * kG1Words; w += nthreads) s_g1[i * 2 * kG1Words + w] = g1src[w];
-        const uint4 *g2src = reinterpret_cast<const uint4 *>(K.g2tab + (size_t)slot * (2 * kLanes * kG2Words));
-        uint4 *g2dst = reinterpret_cast<uint4 *>(s_g2 + i * (2 * kLanes * kG2Words));
-        for (int w = threadIdx.x; w < 2 * kLanes * kG2Words / 4; w += nthreads) g2dst[w] = g2src[w];
-        const uint4 *ksrc = reinterpret_cast<const uint4 *>(K.keytab + (size_t)i * (S::kKP * 2 * kPadWords));
-        uint4 *kdst = reinterpret_cast<uint4 *>(s_key + i * (S::kKP * 2 * kPadWords));
-        for (int w = threadIdx.x; w < S::kKP * 2 * kPadWords / 4; w += nthreads) kdst[w] = ksrc[w];
-    }
+    // stage the twiddles and the key image of every prime of this launch (TMA bulk copies)
+    __shared__ __align__(8) uint64_t s_bar;
+    if (threadIdx.x == 0) tma_init(&s_bar);
     __syncthreads();
+    stage_int_tables<NP, MODE>(K, s_g1, s_g2, s_key, &s_bar, threadIdx.x == 0);
+    tma_wait(&s_bar);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, hw = lane >> 4, t = lane & 15;
     uint32_t *mine = s_hw + (warp * 2 + hw) * K.hw_words;
@@ -153,17 +197,14 @@ constexpr int kF64Warps = 16;
 
 static size_t f64_smem_bytes(int warps) { return sizeof(double) * ((size_t)kF64TabD + (size_t)warps * 2 * kF64BufD); }
 
-__device__ __forceinline__ void f64_stage_tables(const F64Launch &K, double *s_tab)
+// FP64 tables [g1 | g2 | key images] are contiguous on the device: one bulk copy
+__device__ __forceinline__ void f64_stage_tables(const F64Launch &K, double *s_tab, uint64_t *bar, bool issue)
 {
-    const double2 *g1 = reinterpret_cast<const double2 *>(K.g1);
-    const double2 *g2 = reinterpret_cast<const double2 *>(K.g2);
-    const double2 *key = reinterpret_cast<const double2 *>(K.key);
-    double2 *d = reinterpret_cast<double2 *>(s_tab);
-    for (int w = threadIdx.x; w < kF64G1D / 2; w += blockDim.x) d[w] = g1[w];
-    d += kF64G1D / 2;
-    for (int w = threadIdx.x; w < kF64G2D / 2; w += blockDim.x) d[w] = g2[w];
-    d += kF64G2D / 2;
-    for (int w = threadIdx.x; w < kF64KeyD / 2; w += blockDim.x) d[w] = key[w];
+    static_assert((kF64TabD * 8) % 16 == 0, "bulk copies move multiples of 16 bytes");
+    if (issue) {
+        tma_expect(bar, kF64TabD * 8);
+        tma_load(s_tab, K.g1, kF64TabD * 8, bar);
+    }
 }
 
 __device__ __forceinline__ void f64_ctx_init(LaneCtxF &ctx, double *s_tab, double *s_buf, int warp_slot, int lane)
@@ -192,8 +233,11 @@ __device__ __forceinline__ void f64_prefetch_item(const F64Launch &K, uint32_t n
 __global__ void __launch_bounds__(kF64Warps * 32, 1) rzk_commit_f64_kernel(const __grid_constant__ F64Launch K)
 {
     extern __shared__ __align__(16) double smd[];
-    f64_stage_tables(K, smd);
+    __shared__ __align__(8) uint64_t s_bar;
+    if (threadIdx.x == 0) tma_init(&s_bar);
     __syncthreads();
+    f64_stage_tables(K, smd, &s_bar, threadIdx.x == 0);
+    tma_wait(&s_bar);
     const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     LaneCtxF ctx;
     f64_ctx_init(ctx, smd, smd + kF64TabD, warp, lane);
@@ -240,19 +284,14 @@ __global__ void __launch_bounds__(512, 1) rzk_commit_hybrid_kernel(const __grid_
     uint32_t *s_hw = reinterpret_cast<uint32_t *>(s_f64 + kF64TabD);                       // wi int warps
     double *s_fbuf = reinterpret_cast<double *>(s_hw + (size_t)wi * 2 * K.hw_words);       // wf FP64 warps
 
-    {   // stage the tables of both paths
-        const uint32_t slot = K.pc[0].slot;
-        const uint32_t *g1src = K.g1tab + (size_t)slot * (2 * kG1Words);
-        for (int w = threadIdx.x; w < 2 * kG1Words; w += nthreads) s_g1[w] = g1src[w];
-        const uint4 *g2src = reinterpret_cast<const uint4 *>(K.g2tab + (size_t)slot * (2 * kLanes * kG2Words));
-        uint4 *g2dst = reinterpret_cast<uint4 *>(s_g2);
-        for (int w = threadIdx.x; w < 2 * kLanes * kG2Words / 4; w += nthreads) g2dst[w] = g2src[w];
-        const uint4 *ksrc = reinterpret_cast<const uint4 *>(K.keytab);
-        uint4 *kdst = reinterpret_cast<uint4 *>(s_key);
-        for (int w = threadIdx.x; w < S::kKP * 2 * kPadWords / 4; w += nthreads) kdst[w] = ksrc[w];
-        f64_stage_tables(KF, s_f64);
-    }
+    // stage the tables of both paths: TMA bulk copies issued by one thread, two mbarriers (one per table set)
+    __shared__ __align__(8) uint64_t s_bar[2];
+    if (threadIdx.x == 0) { tma_init(&s_bar[0]); tma_init(&s_bar[1]); }
     __syncthreads();
+    stage_int_tables<NP, MODE>(K, s_g1, s_g2, s_key, &s_bar[0], threadIdx.x == 0);
+    f64_stage_tables(KF, s_f64, &s_bar[1], threadIdx.x == 0);
+    tma_wait(&s_bar[0]);
+    tma_wait(&s_bar[1]);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, hw = lane >> 4, t = lane & 15;
     const uint32_t grp = warp >= wi ? 1u : 0u;
@@ -494,7 +533,7 @@ int launch_vm(rzk_engine *e, VmLaunch &K, cudaStream_t s)
     list_prefetch(K);
     K.cta_sync = K.item_mask ? 0u : e->cta_sync;      // masked launches skip items per warp: no CTA barriers
     K.pp_mode = 0;
-    const size_t max_smem = 227 * 1024;
+    const size_t max_smem = 227 * 1024 - 64;          // 8 bytes of static shared memory hold the TMA mbarrier
     int warps = (int)((max_smem - VmSmem<NP, MODE>::bytes(0, 0)) / (sizeof(uint32_t) * 2 * K.hw_words));
     if (warps > VmCfg<NP, MODE>::kMaxWarps) warps = VmCfg<NP, MODE>::kMaxWarps;
     const uint32_t per_warp = SPLIT ? 1 : 2;
