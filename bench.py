@@ -414,6 +414,43 @@ def main():
         torch.cuda.empty_cache()
         if world == 1:
             extras["single_call_latency_us"] = single_call_latency(eng)
+        # ---- row f1 (optional on-device samplers): Open prover end to end, host -> c, t, z on the host, with the
+        # randomness drawn on the host and copied up (the reference's flow) or sampled on the device (r, y never move).
+        # One stream, no chunk pipelining in either variant: the difference is the bytes that cross PCIe.
+        Bp = B
+        pin = lambda *sh, dt=torch.int32: torch.empty(sh, dtype=dt).pin_memory()
+        xh, rh, yh, dh = pin(Bp, 1, N), pin(Bp, 3, N, dt=torch.int8), pin(Bp, 3, N), pin(Bp, N, dt=torch.int8)
+        ch2, th2, zh2 = pin(Bp, 2, N), pin(Bp, 1, N), pin(Bp, 3, N)
+        xh.copy_(x.cpu()); rh.copy_(r.cpu()); yh.copy_(y.cpu()); dh.copy_(d.cpu())
+        xd, rd, yd, dd = torch.empty_like(x), torch.empty_like(r), torch.empty_like(y), torch.empty_like(d)
+        cE, tE, zE, fE = torch.empty_like(c), torch.empty_like(t), torch.empty_like(z), torch.zeros_like(flags)
+        sig = float(eng.sigma())
+
+        def prove_e2e(device_randomness, seed):
+            xd.copy_(xh, non_blocking=True)
+            if device_randomness:
+                eng.dev("sample_small", 3 * Bp, 1, seed, 1, rd, stream=stream)
+                eng.dev("sample_gaussian", 3 * Bp, sig, seed, 2, yd, stream=stream)
+            else:
+                rd.copy_(rh, non_blocking=True); yd.copy_(yh, non_blocking=True)
+            eng.dev("open_commit_batch", Bp, xd, rd, yd, cE, tE, fE, stream=stream)
+            ch2.copy_(cE, non_blocking=True); th2.copy_(tE, non_blocking=True)
+            dd.copy_(dh, non_blocking=True)                                   # the verifier's challenge arrives
+            eng.dev("open_respond_batch", Bp, yd, rd, dd, zE, stream=stream)
+            zh2.copy_(zE, non_blocking=True)
+            torch.cuda.synchronize()
+        res = {}
+        for name, devr in (("host_randomness", False), ("device_randomness", True)):
+            prove_e2e(devr, 1)
+            t0 = time.perf_counter()
+            for i in range(ksteps):
+                prove_e2e(devr, 2 + i)
+            res[name] = world * Bp * ksteps / (time.perf_counter() - t0)
+        assert int(fE.any()) == 0
+        del xd, rd, yd, dd, cE, tE, zE, xh, rh, yh, dh, ch2, th2, zh2
+        extras["open_prove_e2e"] = {"instances_per_s": res, "unit": "open proofs (commit + response)/s, host buffers in and out",
+                                    "h2d_bytes_per_item": {"host_randomness": 4 * N + 3 * N + 12 * N + N, "device_randomness": 4 * N + N},
+                                    "d2h_bytes_per_item": 8 * N + 4 * N + 12 * N}
 
     # ---- end to end through the host C ABI (pinned host buffers, H2D + D2H inside the timed region) ----
     e2e = None

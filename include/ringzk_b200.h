@@ -191,6 +191,18 @@ int rzk_flags_to_bitmap_dev(rzk_engine *e, size_t B, const uint32_t *flags, uint
 int rzk_pack_i64(rzk_engine *e, size_t count, const int64_t *src, int32_t *dst);
 int rzk_unpack_i64(rzk_engine *e, size_t count, const int32_t *src, int64_t *dst);
 
+/* ---------------------------------------------------------------- optional on-device samplers
+ * NOT part of the reference's flow, where r, y, d are drawn host side by the caller's RNG and passed in.  They keep the
+ * prover's r and y on the device between commit and create_response.  Counter-based (Philox4x32-10 keyed by `seed`;
+ * `tag` < 2^24 separates streams), so a value depends only on (seed, tag, polynomial index, coefficient index) and is
+ * reproducible on the host (tests/philox_ref.py); they do not reproduce the stream of Rust's `rand`.
+ *   small:     n_polys polynomials, coefficients exactly uniform in [-b, b]            (polynomial.rs:14-24)
+ *   gaussian:  coefficients trunc(N(0, sigma)) (Box-Muller in binary64)                 (polynomial.rs:28-44)
+ *   challenge: per item min(kappa, N) entries +-1 at distinct uniform positions         (challenge_space.rs:12-33) */
+int rzk_sample_small_dev(rzk_engine *e, size_t n_polys, int32_t b, uint64_t seed, uint32_t tag, int8_t *out, void *stream);
+int rzk_sample_gaussian_dev(rzk_engine *e, size_t n_polys, double sigma, uint64_t seed, uint32_t tag, int32_t *out, void *stream);
+int rzk_sample_challenge_dev(rzk_engine *e, size_t n_items, int32_t kappa, uint64_t seed, uint32_t tag, int8_t *out, void *stream);
+
 /* Counters for the benchmark harness: kernels launched by this engine since creation. */
 uint64_t rzk_kernel_launches(const rzk_engine *e);
 

@@ -26,6 +26,7 @@
 #include "rzk_vm_exec.cuh"
 #include "rzk_f64.cuh"
 #include "rzk_sparse.cuh"
+#include "rzk_sample.cuh"
 #include "rzk_programs.h"
 #include "rzk_tables.h"
 
@@ -375,6 +376,42 @@ __global__ void __launch_bounds__(512, 1) rzk_respond_sparse_kernel(const __grid
             else asm volatile("prefetch.global.L2 [%0];" ::"l"(K.d + (size_t)(next / K.d_div) * kN + (lane - 28) * 128));
         }
         sparse_respond_item(K, &ctx);
+    }
+}
+
+// ---- optional on-device samplers (rzk_sample.cuh): one thread per Philox block / per item ----
+__global__ void rzk_sample_small_kernel(size_t n_polys, uint32_t b, uint32_t tag, uint32_t k0, uint32_t k1, int8_t *__restrict__ out)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x, total = n_polys * (kN / 4);
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += stride) {
+        const uint64_t poly = g / (kN / 4);
+        const uint32_t i0 = (uint32_t)(g % (kN / 4)) * 4u;
+        char4 v;
+        v.x = (signed char)sample_small_coeff(poly, i0 + 0, b, tag, k0, k1);
+        v.y = (signed char)sample_small_coeff(poly, i0 + 1, b, tag, k0, k1);
+        v.z = (signed char)sample_small_coeff(poly, i0 + 2, b, tag, k0, k1);
+        v.w = (signed char)sample_small_coeff(poly, i0 + 3, b, tag, k0, k1);
+        reinterpret_cast<char4 *>(out)[g] = v;
+    }
+}
+
+__global__ void rzk_sample_gaussian_kernel(size_t n_polys, double sigma, uint32_t tag, uint32_t k0, uint32_t k1, int32_t *__restrict__ out)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x, total = n_polys * (kN / 2);
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += stride) {
+        int32_t v[2];
+        sample_gaussian_pair(g / (kN / 2), (uint32_t)(g % (kN / 2)), sigma, tag, k0, k1, v);
+        reinterpret_cast<int2 *>(out)[g] = make_int2(v[0], v[1]);
+    }
+}
+
+__global__ void rzk_sample_challenge_kernel(size_t n_items, uint32_t kappa, uint32_t tag, uint32_t k0, uint32_t k1, int8_t *__restrict__ out)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t it = (size_t)blockIdx.x * blockDim.x + threadIdx.x; it < n_items; it += stride) {
+        int8_t *d = out + it * kN;
+        for (int i = 0; i < kN / 16; ++i) reinterpret_cast<uint4 *>(d)[i] = make_uint4(0, 0, 0, 0);
+        sample_challenge_item(it, kN, kappa, tag, k0, k1, d);
     }
 }
 
@@ -1286,6 +1323,49 @@ int rzk_sum_verify_batch_dev(rzk_engine *e, size_t B, uint32_t T, const int32_t 
     Guard gd(e->device);
     RZK_TRY(ensure_scratch(e, (B * T + B) * kPolyBytes));
     return dev_sum_verify(e, B, T, zs, zp, cs, cp, gs, ts, tp, u, d, flags, (int32_t *)e->scratch, (cudaStream_t)stream);
+}
+
+// ---- optional on-device samplers (not part of the reference's flow: see rzk_sample.cuh) ----
+
+int rzk_sample_small_dev(rzk_engine *e, size_t n_polys, int32_t b, uint64_t seed, uint32_t tag, int8_t *out, void *stream)
+{
+    RZK_TRY(check_ready(e, false));
+    if (!out || b < 1 || b > 127 || tag >= (1u << 24)) return fail(e, RZK_ERR_INVALID, "bad sampler argument");
+    if (n_polys == 0) return RZK_OK;
+    Guard g(e->device);
+    const size_t total = n_polys * (kN / 4);
+    const unsigned grid = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)e->num_sms * 8);
+    rzk_sample_small_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n_polys, (uint32_t)b, tag, (uint32_t)seed, (uint32_t)(seed >> 32), out);
+    RZK_CUDA(e, cudaGetLastError());
+    e->launches++;
+    return RZK_OK;
+}
+
+int rzk_sample_gaussian_dev(rzk_engine *e, size_t n_polys, double sigma, uint64_t seed, uint32_t tag, int32_t *out, void *stream)
+{
+    RZK_TRY(check_ready(e, false));
+    if (!out || !(sigma > 0.0) || sigma > 1.0e8 || tag >= (1u << 24)) return fail(e, RZK_ERR_INVALID, "bad sampler argument");
+    if (n_polys == 0) return RZK_OK;
+    Guard g(e->device);
+    const size_t total = n_polys * (kN / 2);
+    const unsigned grid = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)e->num_sms * 8);
+    rzk_sample_gaussian_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n_polys, sigma, tag, (uint32_t)seed, (uint32_t)(seed >> 32), out);
+    RZK_CUDA(e, cudaGetLastError());
+    e->launches++;
+    return RZK_OK;
+}
+
+int rzk_sample_challenge_dev(rzk_engine *e, size_t n_items, int32_t kappa, uint64_t seed, uint32_t tag, int8_t *out, void *stream)
+{
+    RZK_TRY(check_ready(e, false));
+    if (!out || kappa < 1 || tag >= (1u << 24)) return fail(e, RZK_ERR_INVALID, "bad sampler argument");
+    if (n_items == 0) return RZK_OK;
+    Guard g(e->device);
+    const unsigned grid = (unsigned)std::min<size_t>((n_items + 127) / 128, (size_t)e->num_sms * 8);
+    rzk_sample_challenge_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(n_items, (uint32_t)kappa, tag, (uint32_t)seed, (uint32_t)(seed >> 32), out);
+    RZK_CUDA(e, cudaGetLastError());
+    e->launches++;
+    return RZK_OK;
 }
 
 int rzk_flags_to_bitmap_dev(rzk_engine *e, size_t B, const uint32_t *flags, uint8_t *bitmap, uint32_t *range_any, void *stream)

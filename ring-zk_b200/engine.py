@@ -25,7 +25,7 @@ _ERRNAMES = {1: "RZK_ERR_INVALID", 2: "RZK_ERR_UNSUPPORTED", 3: "RZK_ERR_CUDA", 
 
 SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("rzk_engine.cu", "rzk_tables.cpp")]
 HEADERS = [os.path.join(_HERE, "csrc", f) for f in
-           ("rzk_arith.cuh", "rzk_vm.h", "rzk_vm_exec.cuh", "rzk_programs.h", "rzk_tables.h", "rzk_f64.cuh", "rzk_sparse.cuh")] + \
+           ("rzk_arith.cuh", "rzk_vm.h", "rzk_vm_exec.cuh", "rzk_programs.h", "rzk_tables.h", "rzk_f64.cuh", "rzk_sparse.cuh", "rzk_sample.cuh")] + \
           [os.path.join(_ROOT, "include", "ringzk_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
               "-Xcompiler", "-fPIC", "--shared"]
@@ -89,6 +89,9 @@ _SIGS = {
     "rzk_sum_respond_batch_dev": "zu" + "p" * 8,
     "rzk_sum_verify_batch_dev": "zu" + "p" * 11,
     "rzk_flags_to_bitmap_dev": "zpppp",
+    "rzk_sample_small_dev": "ziqupp",
+    "rzk_sample_gaussian_dev": "zdqupp",
+    "rzk_sample_challenge_dev": "ziqupp",
     "rzk_pack_i64": "zpp",
     "rzk_unpack_i64": "zpp",
     "rzk_sync": "p",
@@ -112,7 +115,7 @@ def lib():
         raise RuntimeError(f"{LIB_PATH} is missing: run __graft_entry__.build() (nvcc, sm_100a). "
                            "There is no CPU fallback for the engine.")
     L = C.CDLL(LIB_PATH)
-    kinds = {"z": C.c_size_t, "u": C.c_uint32, "p": _VP}
+    kinds = {"z": C.c_size_t, "u": C.c_uint32, "p": _VP, "i": C.c_int32, "q": C.c_uint64, "d": C.c_double}
     for name, sig in _SIGS.items():
         fn = getattr(L, name)
         fn.restype = C.c_int
@@ -354,7 +357,7 @@ class Engine:
         sig = _SIGS[f"rzk_{name}_dev"]
         conv = []
         for kind, a in zip(sig, list(args) + [stream]):
-            conv.append(a if kind in "zu" else _ptr(a))
+            conv.append(a if kind in "zuiqd" else _ptr(a))
         self._call(f"rzk_{name}_dev", *conv)
 
     def sync(self, stream=0):

@@ -17,6 +17,7 @@
 #include "../../ring-zk_b200/csrc/rzk_programs.h"
 #include "../../ring-zk_b200/csrc/rzk_f64.cuh"
 #include "../../ring-zk_b200/csrc/rzk_sparse.cuh"
+#include "../../ring-zk_b200/csrc/rzk_sample.cuh"
 #include "../../ring-zk_b200/csrc/rzk_tables.h"
 extern "C" {
 #include "../../oracle/ringzk_oracle.h"
@@ -528,6 +529,24 @@ int main(int argc, char **argv)
             }
         }
         printf("static programs ok\n");
+    }
+
+    // ---------------- optional samplers (rzk_sample.cuh): Philox4x32-10 known answers (Random123) and draw ranges ----------------
+    {
+        Philox4 o = philox4x32_10(0, 0, 0, 0, 0, 0);
+        CHECK(o.x == 0x6627e8d5u && o.y == 0xe169c58du && o.z == 0xbc57ac4cu && o.w == 0x9b00dbd8u, "philox KAT 0");
+        o = philox4x32_10(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        CHECK(o.x == 0x408f276du && o.y == 0x41c83b0eu && o.z == 0xa20bc7c6u && o.w == 0x6d5451fdu, "philox KAT 1");
+        o = philox4x32_10(0x243f6a88u, 0x85a308d3u, 0x13198a2eu, 0x03707344u, 0xa4093822u, 0x299f31d0u);
+        CHECK(o.x == 0xd16cfe09u && o.y == 0x94fdccebu && o.z == 0x5001e420u && o.w == 0x24126ea1u, "philox KAT 2");
+        int hist[3] = {0, 0, 0};
+        for (uint32_t i = 0; i < 3000; ++i) { int v = sample_small_coeff(7, i, 1, 1, 123u, 456u); CHECK(v >= -1 && v <= 1, "small range"); hist[v + 1]++; }
+        for (int k = 0; k < 3; ++k) CHECK(hist[k] > 900 && hist[k] < 1100, "small histogram %d: %d", k, hist[k]);
+        std::vector<int8_t> dd(N, 0);
+        sample_challenge_item(3, (uint32_t)N, 36, 2, 123u, 456u, dd.data());
+        int nz = 0; for (auto v : dd) { CHECK(v >= -1 && v <= 1, "challenge entry"); nz += v != 0; }
+        CHECK(nz == 36, "challenge weight %d", nz);
+        printf("samplers ok\n");
     }
 
     // ---------------- sparse response z = y + d*r as signed rotations (rzk_sparse.cuh) ----------------
