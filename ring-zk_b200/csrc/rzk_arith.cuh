@@ -49,7 +49,27 @@ RZK_HD uint32_t dot4_i8(int32_t v, uint32_t acc)
 #endif
 }
 
+// exact int32 -> binary64 without the conversion pipe (bit pattern 2^52 + 2^31 + v, minus 2^52 + 2^31) and a fused
+// multiply-add that the host emulator evaluates with fma(): used for exact integer sums on the FP64 pipe
+RZK_HD double f64_exact_i32(int32_t v)
+{
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(__hiloint2double(0x43300000, (int)((uint32_t)v ^ 0x80000000u)), -4503601774854144.0);
+#else
+    return (double)v;
+#endif
+}
+RZK_HD double f64_exact_fma(double a, double b, double c)
+{
+#if defined(__CUDA_ARCH__)
+    return __fma_rn(a, b, c);
+#else
+    return __builtin_fma(a, b, c);
+#endif
+}
+
 RZK_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
+RZK_HD uint32_t umax32(uint32_t a, uint32_t b) { return a > b ? a : b; }
 
 // x in [0, 2m) -> [0, m)  (unsigned wrap makes x - m huge when x < m)
 RZK_HD uint32_t csub(uint32_t x, uint32_t m) { return umin32(x, x - m); }

@@ -246,13 +246,11 @@ RZK_VM void op_fwd(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const Op
             for (int m = 0; m < kElems; ++m) v[m] = lift_in(src[t + kLanes * m], K.q);
         }
         if (op.b & FWD_CHECK_SMALL) {
-            uint32_t bad = 0;
+            // |v| <= lim  <=>  (uint32)(v + lim) <= 2 lim: one add-and-max per coefficient (VIADDMNMX)
+            uint32_t mx = 0;
             RZK_UNROLL
-            for (int m = 0; m < kElems; ++m) {
-                const uint32_t av = (uint32_t)(v[m] < 0 ? -v[m] : v[m]);
-                bad |= (av > K.small_lim) ? 1u : 0u;
-            }
-            L.rerr |= bad;
+            for (int m = 0; m < kElems; ++m) mx = umax32(mx, (uint32_t)v[m] + K.small_lim);
+            L.rerr |= (mx > 2u * K.small_lim) ? 1u : 0u;
         }
         // centred value + 2p lies in (0, 4p): a valid lazy input of the forward butterflies
         if (op.b & FWD_SCALED) {
@@ -686,6 +684,23 @@ RZK_VM void op_norm(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const O
                 RZK_UNROLL
                 for (int j = 0; j < CNT / 4; ++j) acc = dot4_i8(src[j], acc);
                 s = acc;
+            } else if (abs_lim < (1u << 21)) {
+                // Bounds below 2^21 (the default parameters): a coefficient can only pass if its int32 value is
+                // already the small canonical residue (a non-canonical int32 representative is > 1.3e9 in magnitude
+                // once centred), so |v| < 2^21 is tested on the raw value and the squares are summed exactly in binary64
+                // (512 * 2^42 < 2^53) on the FP64 pipe, which these integer kernels leave idle.
+                const int32_t *src = reinterpret_cast<const int32_t *>(st.base) + poly * kN;
+                double acc = 0.0;
+                uint32_t rng = 0;
+                RZK_UNROLL
+                for (int j = 0; j < CNT; ++j) {
+                    const int32_t v = src[t + kLanes * epi_m<MODE>(ctx, j)];
+                    rng |= (uint32_t)v + (1u << 21);
+                    const double dv = f64_exact_i32(v);
+                    acc = f64_exact_fma(dv, dv, acc);
+                }
+                bad = (rng >> 22) ? 1u : 0u;
+                s = bad ? 0ull : (uint64_t)acc;
             } else {
                 const int32_t *src = reinterpret_cast<const int32_t *>(st.base) + poly * kN;
                 RZK_UNROLL
