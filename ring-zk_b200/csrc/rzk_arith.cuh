@@ -137,9 +137,12 @@ RZK_HD int32_t canon_q(int32_t v, uint32_t q)
 // every auxiliary prime (so that v + 2p is a valid lazy NTT input in [0, 4p)).  Only the 98,302 lowest
 // int32 values need fixing (v + q still fits int32); products only need the class mod q, because
 // the integer result is reduced mod q at the end and the CRT ranges are sized for |v| <= 2^31.
+// Written as max(v, v + q) on int32 (one add-and-max instruction): v + q wraps to a smaller value unless
+// v < q - 2^32 + ... , i.e. exactly when v is so negative that v + q is the representative in [1.36e9, 2^31).
 RZK_HD int32_t lift_in(int32_t v, uint32_t q)
 {
-    return v < -2147000000 ? (int32_t)((uint32_t)v + q) : v;
+    const int32_t w = (int32_t)((uint32_t)v + q);
+    return w > v ? w : v;
 }
 
 // Signed 64-bit value w with |w| < 2^60  ->  centred residue mod q in [-(q-1)/2, (q-1)/2].
