@@ -559,13 +559,15 @@ void fill_common(const rzk_engine *e, VmLaunch &K, int np, uint32_t n_items, uin
 
 void set_stream(VmLaunch &K, int i, const void *base, uint32_t stride, uint32_t dtype, uint32_t div = 1)
 {
-    K.st[i].base = base; K.st[i].stride = stride; K.st[i].dtype = dtype; K.st[i].div = div; K.st[i].pad_ = 0;
+    K.st[i].base = base; K.st[i].stride = stride; K.st[i].dtype = dtype; K.st[i].pad_ = 0;
+    set_stream_div(K.st[i], div);
 }
 
 template <int NP, int MODE, class SP = void>
 int launch_vm(rzk_engine *e, VmLaunch &K, cudaStream_t s)
 {
     if (K.n_items == 0) return RZK_OK;
+    if (K.n_items >= (1u << 28)) return fail(e, RZK_ERR_INVALID, "more than 2^28 items in one launch");
     constexpr bool SPLIT = (MODE != MODE_SEQ);
     auto kern = rzk_vm_kernel<NP, MODE, SP>;
     layout_hw(K, SPLIT);

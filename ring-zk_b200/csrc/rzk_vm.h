@@ -63,10 +63,23 @@ struct Op {
 struct Stream {
     const void *base;     // device pointer
     uint32_t stride;      // polynomials per item group
-    uint32_t div;         // item group = item / div
+    uint32_t div;         // item group = item / div  (div > 1 only for per-instance streams of Sum proofs)
     uint32_t dtype;       // DT_I32 / DT_I8
+    uint32_t magic;       // item / div == (item * magic) >> shift for item < 2^28 (set_stream_div)
+    uint32_t shift;
     uint32_t pad_;
 };
+
+// Exact division by the stream's (run-time) group size without a divide sequence: round-up multiplier
+// magic = ceil(2^shift / div), shift = 28 + ceil(log2 div); exact for item < 2^28, div < 2^16.
+inline void set_stream_div(Stream &s, uint32_t div)
+{
+    uint32_t c = 0;
+    while ((1u << c) < div) ++c;
+    s.div = div;
+    s.shift = 28 + c;
+    s.magic = (uint32_t)((((uint64_t)1 << s.shift) + div - 1) / div);
+}
 
 struct PrimeC {
     uint32_t p, p2, pinv;   // p, 2p, p^-1 mod 2^32

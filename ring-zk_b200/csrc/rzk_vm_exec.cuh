@@ -221,7 +221,7 @@ RZK_VM void inv_g1(uint32_t (&a)[kElems], const uint32_t *g1tab, uint32_t p, uin
 
 RZK_VM uint64_t stream_poly(const Stream &s, uint32_t item, uint32_t off)
 {
-    const uint32_t grp = (s.div == 1) ? item : item / s.div;     // div > 1 only for per-instance streams of Sum proofs
+    const uint32_t grp = (uint32_t)(((uint64_t)item * s.magic) >> s.shift);      // item / s.div (rzk_vm.h set_stream_div)
     return (uint64_t)grp * s.stride + off;
 }
 

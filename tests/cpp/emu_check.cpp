@@ -85,7 +85,7 @@ struct Emu {
     }
     void stream(int i, const void *base, uint32_t stride, uint32_t dtype, uint32_t div = 1)
     {
-        K.st[i].base = base; K.st[i].stride = stride; K.st[i].dtype = dtype; K.st[i].div = div;
+        K.st[i].base = base; K.st[i].stride = stride; K.st[i].dtype = dtype; set_stream_div(K.st[i], div);
     }
     // Emulates one warp at a time exactly as the kernel maps it: SPLIT (np == 2) gives the warp one
     // item with half warp h on prime h; SEQ gives each half warp its own item.
