@@ -37,6 +37,11 @@ MEASURED_MULMOD_TPS = 4.617     # T Shoup-mulmods/s on the integer pipes, profil
 MEASURED_F64_MULMOD_TPS = 3.057  # T FP64 mulmods/s (6 DP ops each) on the FP64 pipe, profiles/r1b_imad_fp64_bench.jsonl
 METRIC = "commitments/s"
 UNIT = "commitments/s"
+COMMIT_KERNELS = {      # RZK_COMMIT_MODE -> (kernel, key in profiles/traffic.json)
+    0: ("rzk_vm_kernel<1, MODE_SPLITKEY, SPCommitSplitKey> (integer split-key program, CTA halves phase-mixed)", "commit_int_splitkey"),
+    1: ("rzk_commit_f64_kernel (FP64-pipe program)", "commit_f64"),
+    2: ("rzk_commit_hybrid_kernel<SPCommitSplitKey> (per CTA: 8 warps integer split-key program + 8 warps FP64-pipe program)", "commit_hybrid"),
+}
 WORKLOAD = "configs[1]: batched commitment generation, 2^16 messages/GPU at N=512, Params::default(), one shared key"
 
 
@@ -332,17 +337,18 @@ def main():
     assert bool((flags == 0).all()), "commit constraint flags set on honest inputs"
 
     # ---- dominant kernel alone (roofline) ----
+    commit_mode = int(os.environ.get("RZK_COMMIT_MODE", "0"))
     def kern_only():
         eng.dev("commit_batch", B, x, r, c, flags, stream=stream)
     ms_k = timed(kern_only, args.steps, args.warmup) / args.steps
     peak, peak_src = measured_peaks()
     achieved = ALG_BYTES_COMMIT * B / (ms_k * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic("commit"),
-                "kernel": "rzk_commit_hybrid_kernel<SPCommitSplitKey> (per CTA: 8 warps integer split-key program + 8 warps FP64-pipe program)",
+                "traffic": ncu_traffic(COMMIT_KERNELS[commit_mode][1]),
+                "kernel": COMMIT_KERNELS[commit_mode][0],
                 "kernel_ms": ms_k, "algorithmic_bytes_per_launch": ALG_BYTES_COMMIT * B, "peak_source": peak_src,
-                "note": "arithmetic-pipe bound path (21504 modular multiplies per commitment by SURVEY.md 8(d)): "
-                        "the kernel runs the FMA-heavy (integer) and the FP64 pipes side by side; see int_roofline and DESIGN.md"}
+                "note": "arithmetic-issue bound path (21504 modular multiplies per commitment by SURVEY.md 8(d)); "
+                        "see int_roofline and DESIGN.md"}
 
     # ---- second half of the metric: open-proof verifies/s (config 3) ----
     eng.dev("open_commit_batch", B, x, r, y, c, t, flags, stream=stream)
@@ -512,9 +518,7 @@ def main():
                              "frac": ALG_MULMODS_COMMIT * B / (ms_k * 1e-3) / (MEASURED_MULMOD_TPS * 1e12),
                              "peak_source": "measured Shoup mulmod rate on this pool's B200 (tools/imad_bench.cu, "
                                             "profiles/r1_imad_bench.jsonl); algorithmic mulmods per SURVEY.md 8(d)",
-                             "fp64_pipe_peak_Tmulmod_s": MEASURED_F64_MULMOD_TPS,
-                             "frac_of_both_pipes": ALG_MULMODS_COMMIT * B / (ms_k * 1e-3) /
-                                                   ((MEASURED_MULMOD_TPS + MEASURED_F64_MULMOD_TPS) * 1e12)},
+                             "fp64_pipe_peak_Tmulmod_s": MEASURED_F64_MULMOD_TPS},
         }
         print(json.dumps(line), flush=True)
     eng.close()

@@ -489,7 +489,9 @@ struct rzk_engine {
     uint32_t hyb_seq = 0;
     uint32_t hyb_disable = 0;       // RZK_HYB_DISABLE (experiments)
     uint32_t hyb_int_warps = 8;     // RZK_HYB_INT_WARPS: integer-path warps per CTA in the hybrid kernel (of 16)
-    uint32_t commit_mode = 2;       // RZK_COMMIT_MODE: 0 = integer split-key program, 1 = FP64 pipe, 2 = both pipes (hybrid; measured best)
+    uint32_t commit_mode = 0;       // RZK_COMMIT_MODE: 0 = integer split-key program with phase mixing (measured best, 145 M/s),
+                                    // 1 = FP64-pipe program (123 M/s), 2 = both pipes in one launch (hybrid, 142 M/s)
+    uint32_t commit_pp = 2;         // RZK_COMMIT_PP: phase mixing of the split-key commitment program (0 / 9 = off)
     uint32_t *d_misc = nullptr;     // [0] range word, [1] dummy flags word
     uint32_t *h_range = nullptr;    // pinned host copy of the range word (single-chunk calls)
     bool has_key = false;
@@ -564,7 +566,7 @@ void set_stream(VmLaunch &K, int i, const void *base, uint32_t stride, uint32_t 
 }
 
 template <int NP, int MODE, class SP = void>
-int launch_vm(rzk_engine *e, VmLaunch &K, cudaStream_t s)
+int launch_vm(rzk_engine *e, VmLaunch &K, cudaStream_t s, uint32_t pp_program = 0)
 {
     if (K.n_items == 0) return RZK_OK;
     if (K.n_items >= (1u << 28)) return fail(e, RZK_ERR_INVALID, "more than 2^28 items in one launch");
@@ -582,9 +584,11 @@ int launch_vm(rzk_engine *e, VmLaunch &K, cudaStream_t s)
     const uint32_t want = (uint32_t)((K.n_items + (uint64_t)e->num_sms * per_warp - 1) / ((uint64_t)e->num_sms * per_warp));
     // (but at least 4: the whole CTA stages the tables, which is what a single call on one item waits for)
     if ((uint32_t)warps > want) warps = (int)std::max<uint32_t>(want, (uint32_t)std::min(4, warps));
-    if (e->pp_mode && !std::is_void<SP>::value && warps >= 2 && (warps & 1) == 0) {
-        K.pp_mode = e->pp_mode;
-        K.cta_sync = (e->pp_mode == 2) ? 0u : 2u;     // strict alternation already keeps each group in step
+    // phase mixing: RZK_PP for every static program (experiments), else the program's own setting
+    const uint32_t pp = e->pp_mode ? e->pp_mode : pp_program;
+    if (pp && pp != 9 && !std::is_void<SP>::value && warps >= 2 && (warps & 1) == 0) {
+        K.pp_mode = pp;
+        K.cta_sync = (pp == 2) ? 0u : 2u;             // strict alternation already keeps each group in step
     }
     const size_t smem = VmSmem<NP, MODE>::bytes(warps, K.hw_words);
     static std::atomic<bool> configured[16];   // per device; engines of a group run on separate threads   // per device
@@ -602,14 +606,14 @@ int launch_vm(rzk_engine *e, VmLaunch &K, cudaStream_t s)
 }
 
 template <class SP>
-int launch_sp(rzk_engine *e, VmLaunch &K, cudaStream_t s)
+int launch_sp(rzk_engine *e, VmLaunch &K, cudaStream_t s, uint32_t pp_program = 0)
 {
     if (e->no_static) {      // RZK_NO_STATIC=1: run the same program through the generic interpreter
         if (SP::kMode == MODE_SPLITKEY) return launch_vm<1, MODE_SPLITKEY>(e, K, s);
         if (SP::kMode == MODE_SPLIT) return launch_vm<2, MODE_SPLIT>(e, K, s);
         return SP::kNP == 1 ? launch_vm<1, MODE_SEQ>(e, K, s) : launch_vm<3, MODE_SEQ>(e, K, s);
     }
-    return launch_vm<SP::kNP, SP::kMode, SP>(e, K, s);
+    return launch_vm<SP::kNP, SP::kMode, SP>(e, K, s, pp_program);
 }
 
 int launch_np(rzk_engine *e, int np, VmLaunch &K, cudaStream_t s)
@@ -752,7 +756,8 @@ int dev_commit(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r, int32
     K.small_lim = kSplitKeyLimit;
     K.keytab = e->d_keytab2;
     if (e->commit_mode == 2 && norm_vacuous && B >= 4096) return launch_commit_hybrid(e, K, B, x, r, c, flags, flag_div, s);
-    if (norm_vacuous) return launch_sp<SPCommitSplitKey>(e, K, s);
+    // measured best for this program: the two halves of the CTA alternate their multiply-heavy windows (rzk_vm_exec.cuh pp_*)
+    if (norm_vacuous) return launch_sp<SPCommitSplitKey>(e, K, s, e->commit_pp);
     return launch_vm<1, MODE_SPLITKEY>(e, K, s);
 }
 
@@ -1067,6 +1072,7 @@ int rzk_create(const rzk_params *params, int device, rzk_engine **out)
     if (const char *cs = getenv("RZK_HYB_DISABLE")) e->hyb_disable = (uint32_t)atoi(cs);
     if (const char *cs = getenv("RZK_HYB_INT_WARPS")) e->hyb_int_warps = (uint32_t)atoi(cs);
     if (const char *cs = getenv("RZK_PP")) e->pp_mode = (uint32_t)atoi(cs);
+    if (const char *cs = getenv("RZK_COMMIT_PP")) e->commit_pp = (uint32_t)atoi(cs);
     if (const char *cs = getenv("RZK_CHUNK_ITEMS")) e->chunk_items = (uint32_t)std::max(8, atoi(cs));
     Guard g(device);
     cudaDeviceProp prop;

@@ -3,6 +3,6 @@ set -x
 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_final_n1.json 2> gpurun_out/bench_final_n1.err
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_final_ref.json 2>&1
 python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/plain_final.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_final.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_final.log 2>&1
-python tools/profile_commit.py > gpurun_out/plain_pc.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"hybrid|SPVerifyFirst|sparse" -c 6 -o gpurun_out/prof_final -f python tools/profile_commit.py > gpurun_out/ncu_pc.log 2>&1
+python tools/profile_commit.py > gpurun_out/plain_pc.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"rzk_vm_kernel|sparse|hybrid" -c 10 -o gpurun_out/prof_final -f python tools/profile_commit.py > gpurun_out/ncu_pc.log 2>&1
 tail -n 2 gpurun_out/ncu_pc.log
 cat gpurun_out/bench_final_n1.json | cut -c1-600
