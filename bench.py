@@ -205,6 +205,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to every rank; this arm is the one CPU job of the node and is
+    # meant to use every host core, so the variable is reset before the OpenMP runtime of the oracle library starts
+    os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
     rates = []
     t_all0 = time.perf_counter()
     info = None
