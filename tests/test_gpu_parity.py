@@ -462,3 +462,36 @@ def test_device_group_matches_single_engine(setup):
         assert grp.kernel_launches() > 0
     finally:
         grp.close()
+
+
+def test_other_randomness_bound_b4():
+    """Params with b = 4 (sigma, both norm bounds and the small operands scale by 4): the norm checks take their
+    general 64-bit path (bounds above 2^21), the commitment stays inside its one-word range, the rotation kernel declines
+    the responses (|r| = 4) and the NTT program answers them; every phase of the Open proof is bit-exact against the
+    oracle built with the same parameters."""
+    b = 4
+    s = synth.Synth(31, N=N, b=b)
+    a1p, a2p = s.key()
+    P = engine.lib().rzk_default_params(N)
+    P.b = b
+    eng = engine.Engine(N=N, device=0, params=P)
+    try:
+        eng.set_key_blocks(a1p, a2p)
+        o = orc.Oracle(orc.Params(N=N, b=b), a1p, a2p)
+        assert eng.sigma() == o.sigma() == b * 15444 and eng.verify_bound() == o.verify_bound() > (1 << 21)
+        B = 33
+        x, r, y, d = s.message(B, ragged=True), s.small(B), s.gaussian(B), s.challenge(B)
+        assert np.abs(r).max() == b
+        c, t, ok = eng.open_commit(x, r, y)
+        c_o, t_o, ok_o = o.open_commit_batch(x, r, y)
+        assert (c == c_o).all() and (t == t_o).all() and UB(ok, B).all() and ok_o.all()
+        z = eng.open_respond(y, r, d)
+        assert (z == o.open_respond_batch(y, r, d)).all()
+        c1 = np.ascontiguousarray(c[:, :1])
+        assert UB(eng.open_verify(z, t, c1, d), B).all()
+        zb = z.copy(); zb[0, 0, 0] = eng.verify_bound() + 1; zb[1, 2, 9] += 1
+        v = UB(eng.open_verify(zb, t, c1, d), B)
+        v_o = o.open_verify_batch(zb, t, c1, d).astype(bool)
+        assert (v == v_o).all() and not v[0] and not v[1] and v[2:].all()
+    finally:
+        eng.close()
