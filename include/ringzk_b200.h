@@ -24,8 +24,10 @@
  *     and pipeline H2D / kernels / D2H over chunks.  `_dev` entry points take device
  *     pointers, enqueue on the given cudaStream_t (as void*) and do not synchronise.
  *   - One engine is bound to one CUDA device and is externally synchronised.
- *   - The randomness r, y, d is drawn by the caller (host side, seeded RNG) and passed in;
- *     nothing is sampled on the device.
+ *   - The randomness r, y, d is drawn by the caller (host side, seeded RNG) and passed in; the
+ *     protocol entry points sample nothing.  (Optional, separate: rzk_sample_*_dev, below.)
+ *   - Execution knobs are environment variables read by rzk_create (RZK_COMMIT_MODE, RZK_COMMIT_PP, RZK_PP,
+ *     RZK_CTA_SYNC, RZK_NO_SPARSE, RZK_CHUNK_ITEMS, ...): A/B timing only, results are identical in every setting.
  *   - There is no CPU fallback: without a CUDA device rzk_create fails with RZK_ERR_CUDA.
  */
 #ifndef RINGZK_B200_H
