@@ -160,4 +160,21 @@ RZK_HD int32_t reduce_q_centered(int64_t w, uint32_t q, uint32_t m30, uint64_t k
     return (int32_t)((uint32_t)rem - ((q - 1u) >> 1));
 }
 
+// Integer-valued double with |v| < 2^51  ->  centred residue mod q.  k = rint(v / q) (magic-constant rounding), then
+// rem = v - k q exactly (one FMA); q is odd and the estimate of v / q is off by < 2^-38, so the rounding always picks the
+// nearest integer and |rem| <= (q-1)/2: the canonical representative, no correction step.
+RZK_HD int32_t reduce_q_centered_f64(double v, double q, double qinv)
+{
+    const double magic = 6755399441055744.0;                    // 1.5 * 2^52
+#if defined(__CUDA_ARCH__)
+    const double k = __dadd_rn(__fma_rn(v, qinv, magic), -magic);
+    const double rem = __fma_rn(-k, q, v);
+    return __double2loint(__dadd_rn(rem, magic));
+#else
+    const double k = (__builtin_fma(v, qinv, magic)) - magic;
+    const double rem = __builtin_fma(-k, q, v);
+    return (int32_t)(int64_t)rem;
+#endif
+}
+
 }  // namespace rzk

@@ -29,6 +29,7 @@
 // Replaces Polynomial `*`/`+`/`-`/`==` as composed by Mat::dot, add, sub and
 // componentwise_mul (/root/reference/src/mat.rs:95-178).
 #pragma once
+#include <type_traits>
 #include "rzk_arith.cuh"
 #include "rzk_vm.h"
 #include "rzk_programs.h"
@@ -417,14 +418,20 @@ RZK_VM void op_ld(Lane *lanes, const LaneCtx *ctxs, const Op &op)
 
 // Number of coefficients a lane finishes: in the warp-per-item modes two half warps share an item.
 template <int MODE>
-struct Epi { static constexpr int kCount = (MODE != MODE_SEQ) ? 16 : 32; };
+struct Epi {
+    static constexpr int kCount = (MODE != MODE_SEQ) ? 16 : 32;
+    // MODE_SPLITKEY: |lo + 2^16 hi + plain terms| < 2^47, so the epilogue value is an exact integer in a double and the
+    // reduction mod q runs on the FP64 pipe (three FMAs), which relieves the FMA-heavy pipe of two wide multiplies and
+    // a mulhi per coefficient; the other modes carry up to 2^60 and stay in int64
+    typedef typename std::conditional<MODE == MODE_SPLITKEY, double, int64_t>::type V_t;
+};
 
 // coefficient index m (in the G1 layout, i = t + 16*m) of epilogue element j
 template <int MODE>
 RZK_VM int epi_m(const LaneCtx &ctx, int j) { return (MODE != MODE_SEQ) ? (16 * ctx.hw + j) : j; }
 
 template <int MODE>
-RZK_VM void op_addp(const VmLaunch &K, const LaneCtx *ctxs, int64_t (&V)[RZK_NL][Epi<MODE>::kCount], const Op &op, int it, uint32_t dtype)
+RZK_VM void op_addp(const VmLaunch &K, const LaneCtx *ctxs, typename Epi<MODE>::V_t (&V)[RZK_NL][Epi<MODE>::kCount], const Op &op, int it, uint32_t dtype)
 {
     constexpr int CNT = Epi<MODE>::kCount;
     const Stream st = K.st[op.a];
@@ -443,13 +450,18 @@ RZK_VM void op_addp(const VmLaunch &K, const LaneCtx *ctxs, int64_t (&V)[RZK_NL]
             RZK_UNROLL
             for (int j = 0; j < CNT; ++j) v[j] = src[t + kLanes * epi_m<MODE>(ctx, j)];   // any representative: reduced in OP_FIN
         }
-        RZK_UNROLL
-        for (int j = 0; j < CNT; ++j) V[li_][j] += neg ? -(int64_t)v[j] : (int64_t)v[j];
+        if constexpr (MODE == MODE_SPLITKEY) {
+            RZK_UNROLL
+            for (int j = 0; j < CNT; ++j) V[li_][j] += neg ? -f64_exact_i32(v[j]) : f64_exact_i32(v[j]);
+        } else {
+            RZK_UNROLL
+            for (int j = 0; j < CNT; ++j) V[li_][j] += neg ? -(int64_t)v[j] : (int64_t)v[j];
+        }
     }
 }
 
 template <int MODE>
-RZK_VM void op_fin(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int64_t (&V)[RZK_NL][Epi<MODE>::kCount], const Op &op, int it)
+RZK_VM void op_fin(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, typename Epi<MODE>::V_t (&V)[RZK_NL][Epi<MODE>::kCount], const Op &op, int it)
 {
     constexpr int CNT = Epi<MODE>::kCount;
     const Stream st = K.st[op.a];
@@ -458,7 +470,10 @@ RZK_VM void op_fin(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int64_t 
         const uint64_t poly = stream_poly(st, ctx.item, (uint32_t)op.off + (uint32_t)it * op.step);
         int32_t res[CNT];
         RZK_UNROLL
-        for (int j = 0; j < CNT; ++j) res[j] = reduce_q_centered(V[li_][j], K.q, K.m30, K.kqh);
+        for (int j = 0; j < CNT; ++j) {
+            if constexpr (MODE == MODE_SPLITKEY) res[j] = reduce_q_centered_f64(V[li_][j], K.qd, K.qinvd);
+            else res[j] = reduce_q_centered(V[li_][j], K.q, K.m30, K.kqh);
+        }
         if (op.b & FIN_CMPZ) {
             uint32_t nz = 0;
             RZK_UNROLL
@@ -516,7 +531,7 @@ RZK_VM int64_t crt_combine(const VmLaunch &K, const uint32_t (&r)[kMaxPrimes])
 // values live only inside this function.  Returns the index of the first op after the epilogue.
 template <int NP, int MODE>
 RZK_VM void inv_core(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const Op &op, int prime_iter,
-                     int64_t (&V)[RZK_NL][Epi<MODE>::kCount])
+                     typename Epi<MODE>::V_t (&V)[RZK_NL][Epi<MODE>::kCount])
 {
     constexpr int CNT = Epi<MODE>::kCount;
     RZK_SYNC();      // every OP_LD of the partner half warp has finished (the slot may overlay this buffer)
@@ -598,7 +613,7 @@ RZK_VM void inv_core(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const 
                 const uint32_t v0 = ctx.hw ? recv[li_][j] : own;      // half warp 0's value
                 const uint32_t v1 = ctx.hw ? own : recv[li_][j];      // half warp 1's value
                 if (MODE == MODE_SPLITKEY) {
-                    V[li_][j % CNT] = (int64_t)(int32_t)v0 + (int64_t)(int32_t)v1 * 65536;
+                    V[li_][j % CNT] = f64_exact_fma(f64_exact_i32((int32_t)v1), 65536.0, f64_exact_i32((int32_t)v0));
                 } else {
                     uint32_t r[kMaxPrimes] = {v0, v1, 0};
                     V[li_][j % CNT] = crt_combine<2>(K, r);
@@ -647,7 +662,7 @@ RZK_VM int op_inv(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int q, in
 {
     const Op op = K.ops[q];
     const bool last = (MODE != MODE_SEQ) || (prime_iter == NP - 1);
-    int64_t V[RZK_NL][Epi<MODE>::kCount];
+    typename Epi<MODE>::V_t V[RZK_NL][Epi<MODE>::kCount];
     inv_core<NP, MODE>(K, lanes, ctxs, op, prime_iter, V);
     ++q;
     RZK_NOUNROLL
@@ -868,7 +883,7 @@ constexpr int sp_next_seg(const Prog &p, int pc)        // index of the next OP_
 }
 
 template <class SP, int MODE, int PC>
-RZK_VM void sp_epilogue(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int64_t (&V)[RZK_NL][Epi<MODE>::kCount], int it)
+RZK_VM void sp_epilogue(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, typename Epi<MODE>::V_t (&V)[RZK_NL][Epi<MODE>::kCount], int it)
 {
     constexpr Op e = SP::prog.ops[PC];
     if constexpr (e.code == OP_ADDP) {
@@ -903,7 +918,7 @@ RZK_VM void sp_exec(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int it,
     } else if constexpr (op.code == OP_INV) {
         constexpr int next = sp_skip_epilogue(SP::prog, PC + 1);
         {
-            int64_t V[RZK_NL][Epi<MODE>::kCount];
+            typename Epi<MODE>::V_t V[RZK_NL][Epi<MODE>::kCount];
             inv_core<NP, MODE>(K, lanes, ctxs, op, prime_iter, V);
             if ((MODE != MODE_SEQ) || prime_iter == NP - 1) sp_epilogue<SP, MODE, PC + 1>(K, lanes, ctxs, V, it);
         }
