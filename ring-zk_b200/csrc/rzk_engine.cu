@@ -547,6 +547,7 @@ void fill_common(const rzk_engine *e, VmLaunch &K, int np, uint32_t n_items, uin
     K.q = (uint32_t)q;
     K.kqh = (q << 29) + (q - 1) / 2;
     K.qd = (double)q; K.qinvd = 1.0 / (double)q;
+    K.p0d = (double)K.pc[0].p; K.p0qinvd = (double)K.pc[0].p / (double)q;
     K.m30 = (uint32_t)((1ull << 62) / q);
     K.norm_abs_lim[0] = (uint32_t)e->cbound; K.norm_sq_lim[0] = (e->cbound + 1) * (e->cbound + 1) - 1;
     K.norm_abs_lim[1] = (uint32_t)e->vbound; K.norm_sq_lim[1] = (e->vbound + 1) * (e->vbound + 1) - 1;

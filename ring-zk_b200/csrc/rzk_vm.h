@@ -110,6 +110,7 @@ struct VmLaunch {
     CrtC crt;
     uint64_t kqh;              // q * 2^29 + (q-1)/2   (reduce_q_centered offset)
     double qd, qinvd;          // q and 1/q as doubles (reduce_q_centered_f64)
+    double p0d, p0qinvd;       // prime 0 and p0 / q as doubles (crt2_mod_q_f64)
     uint64_t pad64_;
     uint64_t norm_sq_lim[2];   // (bound+1)^2 - 1 for [0]=commit, [1]=verify constraint
     uint32_t norm_abs_lim[2];  // bound

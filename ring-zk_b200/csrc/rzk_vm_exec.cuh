@@ -420,10 +420,13 @@ RZK_VM void op_ld(Lane *lanes, const LaneCtx *ctxs, const Op &op)
 template <int MODE>
 struct Epi {
     static constexpr int kCount = (MODE != MODE_SEQ) ? 16 : 32;
-    // MODE_SPLITKEY: |lo + 2^16 hi + plain terms| < 2^47, so the epilogue value is an exact integer in a double and the
-    // reduction mod q runs on the FP64 pipe (three FMAs), which relieves the FMA-heavy pipe of two wide multiplies and
-    // a mulhi per coefficient; the other modes carry up to 2^60 and stay in int64
-    typedef typename std::conditional<MODE == MODE_SPLITKEY, double, int64_t>::type V_t;
+    // Warp-per-item modes: the epilogue value is an exact integer in a double and the reduction mod q runs on the FP64
+    // pipe (three FMAs), which relieves the FMA-heavy pipe of the wide multiplies and the mulhi per coefficient.
+    //   MODE_SPLITKEY: |lo + 2^16 hi + plain terms| < 2^47.
+    //   MODE_SPLIT:    the Garner digit h1 (centred) enters as (p0 * h1) mod q through an exact FMA product
+    //                  (crt2_mod_q_f64), so the value is a0 + r + plain terms, < 2^35.
+    // MODE_SEQ (1 or 3 primes) stays in int64
+    typedef typename std::conditional<MODE != MODE_SEQ, double, int64_t>::type V_t;
 };
 
 // coefficient index m (in the G1 layout, i = t + 16*m) of epilogue element j
@@ -450,7 +453,7 @@ RZK_VM void op_addp(const VmLaunch &K, const LaneCtx *ctxs, typename Epi<MODE>::
             RZK_UNROLL
             for (int j = 0; j < CNT; ++j) v[j] = src[t + kLanes * epi_m<MODE>(ctx, j)];   // any representative: reduced in OP_FIN
         }
-        if constexpr (MODE == MODE_SPLITKEY) {
+        if constexpr (MODE != MODE_SEQ) {
             RZK_UNROLL
             for (int j = 0; j < CNT; ++j) V[li_][j] += neg ? -f64_exact_i32(v[j]) : f64_exact_i32(v[j]);
         } else {
@@ -471,7 +474,7 @@ RZK_VM void op_fin(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, typename
         int32_t res[CNT];
         RZK_UNROLL
         for (int j = 0; j < CNT; ++j) {
-            if constexpr (MODE == MODE_SPLITKEY) res[j] = reduce_q_centered_f64(V[li_][j], K.qd, K.qinvd);
+            if constexpr (MODE != MODE_SEQ) res[j] = reduce_q_centered_f64(V[li_][j], K.qd, K.qinvd);
             else res[j] = reduce_q_centered(V[li_][j], K.q, K.m30, K.kqh);
         }
         if (op.b & FIN_CMPZ) {
@@ -524,6 +527,32 @@ RZK_VM int64_t crt_combine(const VmLaunch &K, const uint32_t (&r)[kMaxPrimes])
     int64_t w = (int64_t)(v01 + tq);
     if (negv) w -= (int64_t)K.crt.Pmodq;
     return w;
+}
+
+// Two-prime Garner recombination straight to a value congruent to the exact integer result modulo q, as an exact
+// integer in a double: V = a0 + p0 * h1 with the digit h1 = (a1 - a0) * p0^-1 mod p1 taken centred.  For every result the
+// range checks admit (|V| <= P01/2 - 2^33) that IS the integer result (the centred digit cannot be off by p1: the
+// difference would exceed the range by P01); (p0 * h1) mod q is an error-free FMA product reduced by rint(. / q) * q.
+RZK_VM double crt2_mod_q_f64(const VmLaunch &K, uint32_t a0, uint32_t a1)
+{
+    const uint32_t p1 = K.pc[1].p;
+    uint32_t h1 = shoup_mul(K.crt.inv01, K.crt.inv01p, a1 - a0 + 2u * p1, p1);
+    h1 = csub(h1, p1);
+    const int32_t h1c = h1 > K.pc[1].half ? (int32_t)(h1 - p1) : (int32_t)h1;
+    const double x = f64_exact_i32(h1c);
+    const double magic = 6755399441055744.0;
+#if defined(__CUDA_ARCH__)
+    const double h = __dmul_rn(x, K.p0d);
+    const double l = __fma_rn(x, K.p0d, -h);
+    const double k = __dadd_rn(__fma_rn(x, K.p0qinvd, magic), -magic);
+    const double r = __dadd_rn(__fma_rn(-k, K.qd, h), l);
+#else
+    const double h = x * K.p0d;
+    const double l = __builtin_fma(x, K.p0d, -h);
+    const double k = __builtin_fma(x, K.p0qinvd, magic) - magic;
+    const double r = __builtin_fma(-k, K.qd, h) + l;
+#endif
+    return f64_exact_i32((int32_t)a0) + r;
 }
 
 // Inverse transform of acc[a].  On the last prime the residues of all primes are combined and
@@ -615,8 +644,7 @@ RZK_VM void inv_core(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const 
                 if (MODE == MODE_SPLITKEY) {
                     V[li_][j % CNT] = f64_exact_fma(f64_exact_i32((int32_t)v1), 65536.0, f64_exact_i32((int32_t)v0));
                 } else {
-                    uint32_t r[kMaxPrimes] = {v0, v1, 0};
-                    V[li_][j % CNT] = crt_combine<2>(K, r);
+                    V[li_][j % CNT] = crt2_mod_q_f64(K, v0, v1);
                 }
             }
         }

@@ -73,6 +73,7 @@ struct Emu {
         K.q = (uint32_t)Q;
         K.kqh = ((uint64_t)Q << 29) + (uint64_t)(Q - 1) / 2;
         K.qd = (double)Q; K.qinvd = 1.0 / (double)Q;
+        K.p0d = (double)K.pc[0].p; K.p0qinvd = (double)K.pc[0].p / (double)Q;
         K.m30 = (uint32_t)((1ull << 62) / (uint64_t)Q);
         rzko_params P = rzko_default_params(kN);
         uint64_t cb = rzko_commit_bound(&P), vb = rzko_verify_bound(&P);
