@@ -1,0 +1,16 @@
+"""GPU: differential soak (tools/soak.py) -- random batch sizes around every launch-shape boundary; the integer (with
+and without phase mixing), FP64 and hybrid commitment kernels must agree with each other, the rotation-kernel response
+with the NTT response, and honest proofs must verify."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_differential_soak():
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "soak.py"), "24", "11"], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "SOAK PASSED" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
