@@ -34,13 +34,16 @@ using namespace rzk;
 
 // ------------------------------------------------------------------------------ kernels
 
-// warps per CTA: SPLIT fits 16 warps in 128 registers; the SEQ kernels finish 32 coefficients per
-// lane in the epilogue and get a larger register budget.
+// warps per CTA: SPLIT fits 16 warps in 128 registers; the one-prime SEQ kernel finishes 32 coefficients per
+// lane in the epilogue and gets a larger register budget; the three-prime SEQ kernels finish them four at a time.
 template <int NP, int MODE>
 #ifndef RZK_SPLIT_WARPS
 #define RZK_SPLIT_WARPS 16
 #endif
-struct VmCfg { static constexpr int kMaxWarps = (MODE != MODE_SEQ) ? RZK_SPLIT_WARPS : (NP == 1 ? 12 : 8); };
+#ifndef RZK_SEQ3_WARPS
+#define RZK_SEQ3_WARPS 16      // three-prime programs: chunked epilogue + residue stash in global memory (rzk_vm_exec.cuh ChunkedEpi)
+#endif
+struct VmCfg { static constexpr int kMaxWarps = (MODE != MODE_SEQ) ? RZK_SPLIT_WARPS : (NP == 1 ? 12 : RZK_SEQ3_WARPS); };
 
 template <int NP, int MODE>
 struct VmSmem {
@@ -135,7 +138,7 @@ __global__ void __launch_bounds__(VmCfg<NP, MODE>::kMaxWarps * 32, 1) rzk_vm_ker
     ctx.slot_hw[0] = s_hw + (warp * 2 + 0) * K.hw_words + K.off_slot;
     ctx.slot_hw[1] = s_hw + (warp * 2 + 1) * K.hw_words + K.off_slot;
     ctx.acc1 = mine + K.off_acc1;
-    ctx.stash = mine + K.off_stash;
+    ctx.stash = K.gstash ? K.gstash + (size_t)((blockIdx.x * warps + warp) * 2 + hw) * K.stash_words : mine + K.off_stash;
     ctx.red = SPLIT ? s_hw + (warp * 2) * K.hw_words : mine;
     ctx.ridx = SPLIT ? lane : t;
     ctx.g1 = s_g1;
@@ -484,6 +487,8 @@ struct rzk_engine {
     uint32_t *d_keytab2 = nullptr;  // split-key images (lo/hi) for prime slot 0, [6][2][576]
     double *d_f64tab = nullptr;     // FP64 path: [g1 | g2 | key images] (rzk_f64.cuh)
     uint32_t no_sparse = 0;         // RZK_NO_SPARSE=1: responses through the NTT program only (A/B timing)
+    uint32_t *d_gstash[kPipe + 1] = {};   // residue stash of the three-prime programs, [SM][warp][half warp][kStashWordsMax]:
+                                    // one per pipeline stream (their kernels may overlap) + one for the `_dev` entry points
     uint32_t *d_need = nullptr;     // hand-over words of dev_respond for the `_dev` entry points
     size_t need_cap = 0;
     uint32_t hyb_seq = 0;
@@ -567,6 +572,8 @@ void set_stream(VmLaunch &K, int i, const void *base, uint32_t stride, uint32_t 
     set_stream_div(K.st[i], div);
 }
 
+constexpr uint32_t kStashWordsMax = (kMaxPrimes - 1) * kSlotWords;    // one stashed output per three-prime program (prog_mulsum)
+
 template <int NP, int MODE, class SP = void>
 int launch_vm(rzk_engine *e, VmLaunch &K, cudaStream_t s, uint32_t pp_program = 0)
 {
@@ -574,7 +581,16 @@ int launch_vm(rzk_engine *e, VmLaunch &K, cudaStream_t s, uint32_t pp_program = 
     if (K.n_items >= (1u << 28)) return fail(e, RZK_ERR_INVALID, "more than 2^28 items in one launch");
     constexpr bool SPLIT = (MODE != MODE_SEQ);
     auto kern = rzk_vm_kernel<NP, MODE, SP>;
+    if (!SPLIT && NP > 1) {
+        // residues of the earlier primes wait in global memory (one region per resident half warp, reused item after item)
+        int si = kPipe;
+        for (int i = 0; i < kPipe; ++i) if (e->pipe[i].stream == s) si = i;
+        if (!e->d_gstash[si])
+            RZK_CUDA(e, cudaMalloc(&e->d_gstash[si], sizeof(uint32_t) * (size_t)e->num_sms * VmCfg<NP, MODE>::kMaxWarps * 2 * kStashWordsMax));
+        K.gstash = e->d_gstash[si];
+    }
     layout_hw(K, SPLIT);
+    if (K.stash_words > kStashWordsMax) return fail(e, RZK_ERR_INVALID, "program needs more residue stash than the engine provides");
     list_prefetch(K);
     K.cta_sync = K.item_mask ? 0u : e->cta_sync;      // masked launches skip items per warp: no CTA barriers
     K.pp_mode = 0;
@@ -1143,6 +1159,7 @@ void rzk_destroy(rzk_engine *e)
     if (e->d_keytab2) cudaFree(e->d_keytab2);
     if (e->d_f64tab) cudaFree(e->d_f64tab);
     if (e->d_need) cudaFree(e->d_need);
+    for (auto p : e->d_gstash) if (p) cudaFree(p);
     if (e->d_misc) cudaFree(e->d_misc);
     if (e->h_range) cudaFreeHost(e->h_range);
     delete e;

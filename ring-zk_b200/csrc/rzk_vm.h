@@ -137,6 +137,9 @@ struct VmLaunch {
     uint32_t pp_mode;          // phase mixing between the two halves of a CTA (rzk_vm_exec.cuh pp_acquire); 0 = off
     uint32_t alias_slot;       // the operand slot may overlay the transpose buffer (programs whose OP_LDs all
                                // precede the inverse transforms and that never use OP_MACV)
+    uint32_t stash_words;      // words of residue stash per half warp: nstash * (np - 1) * kSlotWords (MODE_SEQ, np > 1)
+    uint32_t *gstash;          // device: the stash lives in global memory, [CTA][warp][half warp][stash_words]
+                               // (nullptr: in the half warp's shared-memory region, host emulator)
 };
 
 // What a program needs per half warp (decides how many warps fit in shared memory).
@@ -179,7 +182,8 @@ inline void layout_hw(VmLaunch &K, bool split)
     if (K.alias_slot && n.slot) K.off_slot = 0;
     else { K.off_slot = w; if (n.slot) w += kSlotWords; }
     K.off_acc1 = w;  if (n.acc1) w += kSlotWords;
-    K.off_stash = w; if (!split && K.np > 1) w += (uint32_t)n.nstash * (K.np - 1) * kSlotWords;
+    K.stash_words = (!split && K.np > 1) ? (uint32_t)n.nstash * (K.np - 1) * kSlotWords : 0u;
+    K.off_stash = w; if (!K.gstash) w += K.stash_words;
     K.hw_words = w;
 }
 

@@ -555,6 +555,76 @@ RZK_VM double crt2_mod_q_f64(const VmLaunch &K, uint32_t a0, uint32_t a1)
     return f64_exact_i32((int32_t)a0) + r;
 }
 
+// Three-prime MODE_SEQ programs finish an output in chunks of four coefficients per lane (one uint4 of the lane-private
+// layout): the residues of the earlier primes wait in a stash in GLOBAL memory (K.gstash, written and read back by the
+// same lane, L2-resident), and only four 64-bit values are live at a time.  That keeps the kernel within 128 registers
+// (16 warps per SM instead of the 8 that 223 registers allowed) and takes 4 KB per half warp out of shared memory.
+template <int NP, int MODE>
+struct ChunkedEpi { static constexpr bool value = (MODE == MODE_SEQ && NP == 3); };
+constexpr int kEpiChunk = 4;
+
+template <int NP>
+RZK_VM void seq_chunk_values(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const Op &op, int j, int64_t (&V)[RZK_NL][kEpiChunk])
+{
+    RZK_EACH_LANE {
+        RZK_LANE;
+        uint4 prev[NP > 1 ? NP - 1 : 1];
+        RZK_UNROLL
+        for (int k = 0; k < NP - 1; ++k)
+            prev[k] = reinterpret_cast<const uint4 *>(ctx.stash + ((int)op.b * (NP - 1) + k) * kSlotWords)[j * kLanes + t];
+        RZK_UNROLL
+        for (int c = 0; c < kEpiChunk; ++c) {
+            uint32_t r[kMaxPrimes] = {0, 0, 0};
+            RZK_UNROLL
+            for (int k = 0; k < NP - 1; ++k) r[k] = (c == 0) ? prev[k].x : (c == 1) ? prev[k].y : (c == 2) ? prev[k].z : prev[k].w;
+            r[NP - 1] = L.cur[kEpiChunk * j + c];
+            V[li_][c] = crt_combine<NP>(K, r);
+        }
+    }
+}
+
+// OP_ADDP / OP_FIN on the four coefficients m = 4j .. 4j+3 of every lane (MODE_SEQ; i = t + 16 m)
+RZK_VM void op_addp_chunk(const VmLaunch &K, const LaneCtx *ctxs, int64_t (&V)[RZK_NL][kEpiChunk], const Op &op, int it, uint32_t dtype, int j)
+{
+    const Stream st = K.st[op.a];
+    const bool neg = op.c & MAC_NEG;
+    RZK_EACH_LANE {
+        const LaneCtx &ctx = ctxs[li_];
+        const int t = ctx.t;
+        const uint64_t poly = stream_poly(st, ctx.item, (uint32_t)op.off + (uint32_t)it * op.step);
+        RZK_UNROLL
+        for (int c = 0; c < kEpiChunk; ++c) {
+            const int i = t + kLanes * (kEpiChunk * j + c);
+            const int32_t v = (dtype == DT_I8) ? (int32_t)(reinterpret_cast<const int8_t *>(st.base) + poly * kN)[i]
+                                               : (reinterpret_cast<const int32_t *>(st.base) + poly * kN)[i];
+            V[li_][c] += neg ? -(int64_t)v : (int64_t)v;
+        }
+    }
+}
+
+RZK_VM void op_fin_chunk(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int64_t (&V)[RZK_NL][kEpiChunk], const Op &op, int it, int j)
+{
+    const Stream st = K.st[op.a];
+    RZK_EACH_LANE {
+        RZK_LANE;
+        const uint64_t poly = stream_poly(st, ctx.item, (uint32_t)op.off + (uint32_t)it * op.step);
+        int32_t res[kEpiChunk];
+        RZK_UNROLL
+        for (int c = 0; c < kEpiChunk; ++c) res[c] = reduce_q_centered(V[li_][c], K.q, K.m30, K.kqh);
+        if (op.b & FIN_CMPZ) {
+            uint32_t nz = 0;
+            RZK_UNROLL
+            for (int c = 0; c < kEpiChunk; ++c) nz |= (uint32_t)res[c];
+            L.fail |= nz ? 1u : 0u;
+        }
+        if ((op.b & FIN_STORE) && ctx.active) {
+            int32_t *dst = reinterpret_cast<int32_t *>(const_cast<void *>(st.base)) + poly * kN;
+            RZK_UNROLL
+            for (int c = 0; c < kEpiChunk; ++c) dst[t + kLanes * (kEpiChunk * j + c)] = res[c];
+        }
+    }
+}
+
 // Inverse transform of acc[a].  On the last prime the residues of all primes are combined and
 // the epilogue ops that follow (OP_ADDP*, OP_FIN) are executed here, so that the 64-bit
 // values live only inside this function.  Returns the index of the first op after the epilogue.
@@ -659,7 +729,7 @@ RZK_VM void inv_core(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const 
                     w.x = L.cur[4 * j + 0]; w.y = L.cur[4 * j + 1]; w.z = L.cur[4 * j + 2]; w.w = L.cur[4 * j + 3];
                     s4[j * kLanes + t] = w;
                 }
-            } else {
+            } else if constexpr (!ChunkedEpi<NP, MODE>::value) {
                 uint32_t prev[NP > 1 ? NP - 1 : 1][kElems];
                 RZK_UNROLL
                 for (int k = 0; k < NP - 1; ++k) {
@@ -693,6 +763,24 @@ RZK_VM int op_inv(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int q, in
     typename Epi<MODE>::V_t V[RZK_NL][Epi<MODE>::kCount];
     inv_core<NP, MODE>(K, lanes, ctxs, op, prime_iter, V);
     ++q;
+    if constexpr (ChunkedEpi<NP, MODE>::value) {
+        int qe = q;
+        while (K.ops[qe].code == OP_ADDP || K.ops[qe].code == OP_FIN) ++qe;
+        if (last) {
+            RZK_UNROLL
+            for (int j = 0; j < kElems / kEpiChunk; ++j) {
+                int64_t V4[RZK_NL][kEpiChunk];
+                seq_chunk_values<NP>(K, lanes, ctxs, op, j, V4);
+                RZK_NOUNROLL
+                for (int qq = q; qq < qe; ++qq) {
+                    const Op e = K.ops[qq];
+                    if (e.code == OP_ADDP) op_addp_chunk(K, ctxs, V4, e, it, K.st[e.a].dtype, j);
+                    else op_fin_chunk(K, lanes, ctxs, V4, e, it, j);
+                }
+            }
+        }
+        return qe;
+    }
     RZK_NOUNROLL
     for (;; ++q) {
         const Op e = K.ops[q];
@@ -910,6 +998,20 @@ constexpr int sp_next_seg(const Prog &p, int pc)        // index of the next OP_
     return pc;
 }
 
+template <class SP, int PC>
+RZK_VM void sp_epilogue_chunk(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int64_t (&V)[RZK_NL][kEpiChunk], int it, int j)
+{
+    constexpr Op e = SP::prog.ops[PC];
+    if constexpr (e.code == OP_ADDP) {
+        constexpr uint32_t dt = SP::dtype[e.a];
+        op_addp_chunk(K, ctxs, V, e, it, dt, j);
+        sp_epilogue_chunk<SP, PC + 1>(K, lanes, ctxs, V, it, j);
+    } else if constexpr (e.code == OP_FIN) {
+        op_fin_chunk(K, lanes, ctxs, V, e, it, j);
+        sp_epilogue_chunk<SP, PC + 1>(K, lanes, ctxs, V, it, j);
+    }
+}
+
 template <class SP, int MODE, int PC>
 RZK_VM void sp_epilogue(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, typename Epi<MODE>::V_t (&V)[RZK_NL][Epi<MODE>::kCount], int it)
 {
@@ -948,7 +1050,16 @@ RZK_VM void sp_exec(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int it,
         {
             typename Epi<MODE>::V_t V[RZK_NL][Epi<MODE>::kCount];
             inv_core<NP, MODE>(K, lanes, ctxs, op, prime_iter, V);
-            if ((MODE != MODE_SEQ) || prime_iter == NP - 1) sp_epilogue<SP, MODE, PC + 1>(K, lanes, ctxs, V, it);
+            if constexpr (ChunkedEpi<NP, MODE>::value) {
+                if (prime_iter == NP - 1) {
+                    RZK_UNROLL
+                    for (int j = 0; j < kElems / kEpiChunk; ++j) {
+                        int64_t V4[RZK_NL][kEpiChunk];
+                        seq_chunk_values<NP>(K, lanes, ctxs, op, j, V4);
+                        sp_epilogue_chunk<SP, PC + 1>(K, lanes, ctxs, V4, it, j);
+                    }
+                }
+            } else if ((MODE != MODE_SEQ) || prime_iter == NP - 1) sp_epilogue<SP, MODE, PC + 1>(K, lanes, ctxs, V, it);
         }
         sp_exec<SP, NP, MODE, next>(K, lanes, ctxs, it, prime_iter);
     } else {
