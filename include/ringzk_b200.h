@@ -148,7 +148,10 @@ int rzk_sum_verify_batch(rzk_engine *e, size_t B, uint32_t T, const int32_t *zs,
  * Same semantics; every pointer is a device pointer on the engine's device.  `flags` is one
  * uint32_t per item (bit 0: check failed, bit 1: range error) and is OR-ed into, so the caller
  * zeroes it; rzk_flags_to_bitmap_dev packs "flags == 0" into a bitmap.  c_stride is the number of
- * polynomials per item in the commitment array handed to verify (1: c1 only, 2: full c). */
+ * polynomials per item in the commitment array handed to verify (1: c1 only, 2: full c).
+ * The Linear / Sum variants and the responses keep intermediates (w = A2.y, the residue stash of the
+ * three-prime products, the hand-over words of the response kernels) in scratch owned by the engine:
+ * enqueue the `_dev` calls of one engine on ONE stream at a time (use one engine per stream otherwise). */
 int rzk_commit_batch_dev(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r,
                          int32_t *c, uint32_t *flags, void *stream);
 int rzk_commitment_verify_batch_dev(rzk_engine *e, size_t B, const int32_t *c, const int32_t *x,

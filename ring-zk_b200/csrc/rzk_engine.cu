@@ -45,12 +45,25 @@ template <int NP, int MODE>
 #endif
 struct VmCfg { static constexpr int kMaxWarps = (MODE != MODE_SEQ) ? RZK_SPLIT_WARPS : (NP == 1 ? 12 : RZK_SEQ3_WARPS); };
 
-template <int NP, int MODE>
+// does a compile-time program multiply by the resident key (OP_MACK)?  Programs that do not (the three-prime product
+// sums) leave the key images out of shared memory, which is what lets their two-accumulator form keep 16 warps.
+template <class SP>
+constexpr bool sp_uses_key()
+{
+    if constexpr (std::is_void<SP>::value) return true;
+    else {
+        for (int i = 0; i < kMaxOps && SP::prog.ops[i].code != OP_END; ++i)
+            if (SP::prog.ops[i].code == OP_MACK) return true;
+        return false;
+    }
+}
+
+template <int NP, int MODE, bool KEY = true>
 struct VmSmem {
     static constexpr int kKP = (MODE == MODE_SPLITKEY) ? 2 * kKeyPolys : kKeyPolys;   // key images per prime
     static constexpr int kG1 = NP * 2 * kG1Words;
     static constexpr int kG2 = NP * 2 * kLanes * kG2Words;
-    static constexpr int kKey = NP * kKP * 2 * kPadWords;
+    static constexpr int kKey = KEY ? NP * kKP * 2 * kPadWords : 0;
     static constexpr int kTables = (kG1 + kG2 + kKey + 3) / 4 * 4;
     static size_t bytes(int warps, uint32_t hw_words) { return sizeof(uint32_t) * ((size_t)kTables + (size_t)warps * 2 * hw_words); }
 };
@@ -88,12 +101,12 @@ __device__ __forceinline__ void tma_wait(uint64_t *bar)
 }
 
 // stages the twiddles and the key images of the NP primes of a launch
-template <int NP, int MODE>
+template <int NP, int MODE, bool KEY = true>
 __device__ __forceinline__ void stage_int_tables(const VmLaunch &K, uint32_t *s_g1, uint32_t *s_g2, uint32_t *s_key, uint64_t *bar,
                                                  bool issue)
 {
-    using S = VmSmem<NP, MODE>;
-    constexpr uint32_t g1b = 2 * kG1Words * 4, g2b = 2 * kLanes * kG2Words * 4, keyb = S::kKP * 2 * kPadWords * 4;
+    using S = VmSmem<NP, MODE, KEY>;
+    constexpr uint32_t g1b = 2 * kG1Words * 4, g2b = 2 * kLanes * kG2Words * 4, keyb = KEY ? S::kKP * 2 * kPadWords * 4 : 0;
     static_assert(g1b % 16 == 0 && g2b % 16 == 0 && keyb % 16 == 0, "bulk copies move multiples of 16 bytes");
     if (issue) {
         tma_expect(bar, NP * (g1b + g2b + keyb));
@@ -101,7 +114,7 @@ __device__ __forceinline__ void stage_int_tables(const VmLaunch &K, uint32_t *s_
             const uint32_t slot = K.pc[i].slot;
             tma_load(s_g1 + i * 2 * kG1Words, K.g1tab + (size_t)slot * (2 * kG1Words), g1b, bar);
             tma_load(s_g2 + i * (2 * kLanes * kG2Words), K.g2tab + (size_t)slot * (2 * kLanes * kG2Words), g2b, bar);
-            tma_load(s_key + i * (S::kKP * 2 * kPadWords), K.keytab + (size_t)i * (S::kKP * 2 * kPadWords), keyb, bar);
+            if constexpr (KEY) tma_load(s_key + i * (S::kKP * 2 * kPadWords), K.keytab + (size_t)i * (S::kKP * 2 * kPadWords), keyb, bar);
         }
     }
 }
@@ -115,7 +128,8 @@ __global__ void __launch_bounds__(VmCfg<NP, MODE>::kMaxWarps * 32, 1) rzk_vm_ker
 {
     constexpr bool SPLIT = (MODE != MODE_SEQ);      // one warp per item
     extern __shared__ __align__(16) uint32_t smem[];
-    using S = VmSmem<NP, MODE>;
+    constexpr bool KEY = sp_uses_key<SP>();
+    using S = VmSmem<NP, MODE, KEY>;
     if (K.any_item && *K.any_item == 0) return;     // masked fallback launch with nothing to redo
     uint32_t *s_g1 = smem;
     uint32_t *s_g2 = s_g1 + S::kG1;
@@ -127,7 +141,7 @@ __global__ void __launch_bounds__(VmCfg<NP, MODE>::kMaxWarps * 32, 1) rzk_vm_ker
     __shared__ __align__(8) uint64_t s_bar;
     if (threadIdx.x == 0) tma_init(&s_bar);
     __syncthreads();
-    stage_int_tables<NP, MODE>(K, s_g1, s_g2, s_key, &s_bar, threadIdx.x == 0);
+    stage_int_tables<NP, MODE, KEY>(K, s_g1, s_g2, s_key, &s_bar, threadIdx.x == 0);
     tma_wait(&s_bar);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, hw = lane >> 4, t = lane & 15;
@@ -507,6 +521,8 @@ struct rzk_engine {
     size_t scratch_cap = 0;
     uint64_t launches = 0;
     uint32_t static_respond = 0;
+    uint32_t no_fuse = 0;           // RZK_NO_FUSE=1: the Sum prover's two product sums as two launches; 2: one launch for Linear too (A/B timing)
+    uint32_t no_dimg = 0;           // RZK_NO_DIMG=1: every verify item transforms its challenge itself (A/B timing)
     uint32_t no_static = 0;         // RZK_NO_STATIC=1 forces the generic interpreter (debugging / A-B timing)
     uint32_t pp_mode = 0;           // RZK_PP: phase mixing between CTA halves (rzk_vm_exec.cuh), static programs only
     uint32_t chunk_items = 8192;    // host pipeline: items per chunk (RZK_CHUNK_ITEMS)
@@ -572,7 +588,7 @@ void set_stream(VmLaunch &K, int i, const void *base, uint32_t stride, uint32_t 
     set_stream_div(K.st[i], div);
 }
 
-constexpr uint32_t kStashWordsMax = (kMaxPrimes - 1) * kSlotWords;    // one stashed output per three-prime program (prog_mulsum)
+constexpr uint32_t kStashWordsMax = 2 * (kMaxPrimes - 1) * kSlotWords;    // up to two stashed outputs per three-prime program (prog_mulsum2)
 
 template <int NP, int MODE, class SP = void>
 int launch_vm(rzk_engine *e, VmLaunch &K, cudaStream_t s, uint32_t pp_program = 0)
@@ -595,7 +611,8 @@ int launch_vm(rzk_engine *e, VmLaunch &K, cudaStream_t s, uint32_t pp_program = 
     K.cta_sync = K.item_mask ? 0u : e->cta_sync;      // masked launches skip items per warp: no CTA barriers
     K.pp_mode = 0;
     const size_t max_smem = 227 * 1024 - 64;          // 8 bytes of static shared memory hold the TMA mbarrier
-    int warps = (int)((max_smem - VmSmem<NP, MODE>::bytes(0, 0)) / (sizeof(uint32_t) * 2 * K.hw_words));
+    using S = VmSmem<NP, MODE, sp_uses_key<SP>()>;
+    int warps = (int)((max_smem - S::bytes(0, 0)) / (sizeof(uint32_t) * 2 * K.hw_words));
     if (warps > VmCfg<NP, MODE>::kMaxWarps) warps = VmCfg<NP, MODE>::kMaxWarps;
     const uint32_t per_warp = SPLIT ? 1 : 2;
     // do not launch more warps per CTA than the batch can use
@@ -608,8 +625,8 @@ int launch_vm(rzk_engine *e, VmLaunch &K, cudaStream_t s, uint32_t pp_program = 
         K.pp_mode = pp;
         K.cta_sync = (pp == 2) ? 0u : 2u;             // strict alternation already keeps each group in step
     }
-    const size_t smem = VmSmem<NP, MODE>::bytes(warps, K.hw_words);
-    static std::atomic<bool> configured[16];   // per device; engines of a group run on separate threads   // per device
+    const size_t smem = S::bytes(warps, K.hw_words);
+    static std::atomic<bool> configured[16];   // per device; engines of a group run on separate threads
     if (!configured[e->device & 15]) {
         RZK_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
         configured[e->device & 15] = true;
@@ -847,19 +864,32 @@ int dev_respond(rzk_engine *e, size_t items, const int32_t *y, const int8_t *r, 
 }
 
 // norm check + first equation (+ optional w = A2.z - c2*d) for `items` responses
+// NTT image (two primes) of `groups` challenges d, for dev_verify_first(..., dimg): 2 polys of words per group
+int dev_challenge_image(rzk_engine *e, size_t groups, const int8_t *d, uint32_t *dimg, cudaStream_t s)
+{
+    VmLaunch K; memset(&K, 0, sizeof(K));
+    SPChallengeImage::prog.install(K);
+    fill_common(e, K, 2, (uint32_t)groups, 1, nullptr);
+    set_stream(K, 0, d, 1, DT_I8); set_stream(K, 1, dimg, 2, DT_I32);
+    return launch_sp<SPChallengeImage>(e, K, s);
+}
+
+// dimg != nullptr (with w): the image of d comes from dev_challenge_image, one per d_div items
 int dev_verify_first(rzk_engine *e, size_t items, const int32_t *z, const int32_t *t, const int32_t *c, uint32_t c_stride,
-                     const int8_t *d, uint32_t d_div, int32_t *w, uint32_t *flags, uint32_t flag_div, cudaStream_t s)
+                     const int8_t *d, uint32_t d_div, int32_t *w, uint32_t *flags, uint32_t flag_div, cudaStream_t s,
+                     const uint32_t *dimg = nullptr)
 {
     VmLaunch K; memset(&K, 0, sizeof(K));
     Prog p;
     prog_norm_verify(p, 0);
-    prog_verify_first(p, 0, 1, 2, 3, w ? 4 : -1);
+    prog_verify_first(p, 0, 1, 2, 3, w ? 4 : -1, (w && dimg) ? 5 : -1);
     p.end();
     p.install(K);
     fill_common(e, K, 2, (uint32_t)items, flag_div, flags);
     set_stream(K, 0, z, 3, DT_I32); set_stream(K, 1, t, 1, DT_I32); set_stream(K, 2, c, c_stride, DT_I32);
     set_stream(K, 3, d, 1, DT_I8, d_div);
     if (w) set_stream(K, 4, w, 1, DT_I32);
+    if (w && dimg) { set_stream(K, 5, dimg, 2, DT_I32, d_div); return launch_sp<SPVerifyFirstWG>(e, K, s); }
     return w ? launch_sp<SPVerifyFirstW>(e, K, s) : launch_sp<SPVerifyFirst>(e, K, s);
 }
 
@@ -899,6 +929,22 @@ int dev_mulsum(rzk_engine *e, size_t B, uint32_t T, const int32_t *a, const int3
     return launch_np(e, 3, K, s);
 }
 
+// out0 = sum_{i<T} a_i*b_i,  out1 = sum_{i<T} a_i*c_i - sub   (every a_i transformed once; prog_mulsum2)
+int dev_mulsum2(rzk_engine *e, size_t B, uint32_t T, const int32_t *a, const int32_t *b, const int32_t *c, const int32_t *sub,
+                int32_t *out0, int32_t *out1, uint32_t *flags, cudaStream_t s)
+{
+    VmLaunch K; memset(&K, 0, sizeof(K));
+    Prog p;
+    prog_mulsum2(p, (int)T, 0, 1, 2, 3, 4, 5);
+    p.end();
+    p.install(K);
+    fill_common(e, K, 3, (uint32_t)B, 1, flags);
+    set_stream(K, 0, a, T, DT_I32); set_stream(K, 1, b, T, DT_I32); set_stream(K, 2, c, T, DT_I32);
+    set_stream(K, 3, sub, 1, DT_I32); set_stream(K, 4, out0, 1, DT_I32); set_stream(K, 5, out1, 1, DT_I32);
+    K.loop_count = T - 1;
+    return launch_sp<SPMulSum2>(e, K, s);
+}
+
 // commit(x; r) -> c  and  t = A1.y, w = A2.y  for `items` (x, r, y) triples
 int dev_commit_matvec(rzk_engine *e, size_t items, const int32_t *x, const int8_t *r, const int32_t *y,
                       int32_t *c, int32_t *t, int32_t *w, uint32_t *flags, uint32_t flag_div, cudaStream_t s, bool generic = false)
@@ -913,10 +959,18 @@ int dev_linear_commit(rzk_engine *e, size_t B, const int32_t *g, const int32_t *
                       int32_t *tp, int32_t *u, uint32_t *flags, int32_t *scratch, cudaStream_t s, bool generic = false)
 {
     int32_t *w = scratch, *wp = scratch + B * kN;
-    RZK_TRY(dev_mulsum(e, B, 1, g, x, nullptr, nullptr, gx, flags, s));                 // linear.rs:91-95
-    RZK_TRY(dev_commit_matvec(e, B, gx, rp, yp, cp, tp, wp, flags, 1, s, generic));     // linear.rs:96,121,129
+    if (e->no_fuse != 2) {
+        // (the one-launch form of g*x and u below was measured 5 % slower for a single term: its second accumulator lives
+        // in shared memory and nothing is amortised over a loop; RZK_NO_FUSE=2 selects it for A/B timing)
+        RZK_TRY(dev_mulsum(e, B, 1, g, x, nullptr, nullptr, gx, flags, s));                 // linear.rs:91-95
+        RZK_TRY(dev_commit_matvec(e, B, gx, rp, yp, cp, tp, wp, flags, 1, s, generic));     // linear.rs:96,121,129
+        RZK_TRY(dev_commit_matvec(e, B, x, r, y, c, t, w, flags, 1, s, generic));           // linear.rs:97,118,124-127
+        return dev_mulsum(e, B, 1, g, w, wp, nullptr, u, flags, s);                         // linear.rs:124-129
+    }
+    RZK_TRY(dev_keymatvec(e, B, yp, tp, wp, flags, 1, s));                              // linear.rs:121,129
     RZK_TRY(dev_commit_matvec(e, B, x, r, y, c, t, w, flags, 1, s, generic));           // linear.rs:97,118,124-127
-    return dev_mulsum(e, B, 1, g, w, wp, nullptr, u, flags, s);                         // linear.rs:124-129
+    RZK_TRY(dev_mulsum2(e, B, 1, g, x, w, wp, gx, u, flags, s));                        // linear.rs:91-95,124-129
+    return dev_commit(e, B, gx, rp, cp, flags, s, generic);                             // linear.rs:96
 }
 
 int dev_linear_verify(rzk_engine *e, size_t B, const int32_t *z, const int32_t *zp, const int32_t *c, const int32_t *cp,
@@ -924,6 +978,7 @@ int dev_linear_verify(rzk_engine *e, size_t B, const int32_t *z, const int32_t *
                       uint32_t *flags, int32_t *scratch, cudaStream_t s)
 {
     int32_t *w = scratch, *wp = scratch + B * kN;
+    // (a shared NTT image of d, as in dev_sum_verify, was measured 1 % slower here: two users per image do not pay for the launch)
     RZK_TRY(dev_verify_first(e, B, z, t, c, 2, d, 1, w, flags, 1, s));                  // linear.rs:218,225-229
     RZK_TRY(dev_verify_first(e, B, zp, tp, cp, 2, d, 1, wp, flags, 1, s));              // linear.rs:221,231-235
     return dev_mulsum(e, B, 1, g, w, wp, u, nullptr, flags, s);                         // linear.rs:236-249
@@ -935,10 +990,18 @@ int dev_sum_commit(rzk_engine *e, size_t B, uint32_t T, const int32_t *gs, const
                    int32_t *ts, int32_t *tp, int32_t *u, uint32_t *flags, int32_t *scratch, cudaStream_t s, bool generic = false)
 {
     int32_t *ws = scratch, *wp = scratch + B * T * kN;
-    RZK_TRY(dev_mulsum(e, B, T, gs, xs, nullptr, nullptr, xp, flags, s));               // sum.rs:107-115
-    RZK_TRY(dev_commit_matvec(e, B, xp, rp, yp, cp, tp, wp, flags, 1, s, generic));     // sum.rs:116,151,160
+    if (e->no_fuse == 1 || T == 1) {
+        RZK_TRY(dev_mulsum(e, B, T, gs, xs, nullptr, nullptr, xp, flags, s));               // sum.rs:107-115
+        RZK_TRY(dev_commit_matvec(e, B, xp, rp, yp, cp, tp, wp, flags, 1, s, generic));     // sum.rs:116,151,160
+        RZK_TRY(dev_commit_matvec(e, B * T, xs, rs, ys, cs, ts, ws, flags, T, s, generic)); // sum.rs:117-120,145-148,157
+        return dev_mulsum(e, B, T, gs, ws, wp, nullptr, u, flags, s);                       // sum.rs:154-160
+    }
+    // same results in an order that lets every g_i be transformed once for both of its products: the masking products
+    // first (they do not depend on x'), then x' = sum g_i x_i and u in one launch, then the commitment to x'
+    RZK_TRY(dev_keymatvec(e, B, yp, tp, wp, flags, 1, s));                              // sum.rs:151,160
     RZK_TRY(dev_commit_matvec(e, B * T, xs, rs, ys, cs, ts, ws, flags, T, s, generic)); // sum.rs:117-120,145-148,157
-    return dev_mulsum(e, B, T, gs, ws, wp, nullptr, u, flags, s);                       // sum.rs:154-160
+    RZK_TRY(dev_mulsum2(e, B, T, gs, xs, ws, wp, xp, u, flags, s));                     // sum.rs:107-115,154-160
+    return dev_commit(e, B, xp, rp, cp, flags, s, generic);                             // sum.rs:116
 }
 
 int dev_sum_verify(rzk_engine *e, size_t B, uint32_t T, const int32_t *zs, const int32_t *zp, const int32_t *cs,
@@ -946,8 +1009,10 @@ int dev_sum_verify(rzk_engine *e, size_t B, uint32_t T, const int32_t *zs, const
                    const int8_t *d, uint32_t *flags, int32_t *scratch, cudaStream_t s)
 {
     int32_t *ws = scratch, *wp = scratch + B * T * kN;
-    RZK_TRY(dev_verify_first(e, B * T, zs, ts, cs, 2, d, T, ws, flags, T, s));          // sum.rs:262-268,277-291
-    RZK_TRY(dev_verify_first(e, B, zp, tp, cp, 2, d, 1, wp, flags, 1, s));              // sum.rs:269,293-298
+    uint32_t *dimg = e->no_dimg ? nullptr : reinterpret_cast<uint32_t *>(scratch + (B * T + B) * kN);   // T + 1 equations share d
+    if (dimg) RZK_TRY(dev_challenge_image(e, B, d, dimg, s));
+    RZK_TRY(dev_verify_first(e, B * T, zs, ts, cs, 2, d, T, ws, flags, T, s, dimg));    // sum.rs:262-268,277-291
+    RZK_TRY(dev_verify_first(e, B, zp, tp, cp, 2, d, 1, wp, flags, 1, s, dimg));        // sum.rs:269,293-298
     return dev_mulsum(e, B, T, gs, ws, wp, u, nullptr, flags, s);                       // sum.rs:300-319
 }
 
@@ -1085,6 +1150,8 @@ int rzk_create(const rzk_params *params, int device, rzk_engine **out)
     e->device = device;
     if (const char *cs = getenv("RZK_CTA_SYNC")) e->cta_sync = (uint32_t)atoi(cs);
     if (const char *cs = getenv("RZK_NO_STATIC")) e->no_static = (uint32_t)atoi(cs);
+    if (const char *cs = getenv("RZK_NO_DIMG")) e->no_dimg = (uint32_t)atoi(cs);
+    if (const char *cs = getenv("RZK_NO_FUSE")) e->no_fuse = (uint32_t)atoi(cs);
     if (const char *cs = getenv("RZK_COMMIT_MODE")) e->commit_mode = (uint32_t)atoi(cs);
     if (const char *cs = getenv("RZK_NO_SPARSE")) e->no_sparse = (uint32_t)atoi(cs);
     if (const char *cs = getenv("RZK_HYB_DISABLE")) e->hyb_disable = (uint32_t)atoi(cs);
@@ -1350,7 +1417,7 @@ int rzk_sum_verify_batch_dev(rzk_engine *e, size_t B, uint32_t T, const int32_t 
     if (T == 0 || T > 65535) return fail(e, RZK_ERR_INVALID, "T must be in 1..65535");
     if (any_null({zs, zp, cs, cp, gs, ts, tp, u, d, flags})) return fail(e, RZK_ERR_INVALID, "null argument");
     Guard gd(e->device);
-    RZK_TRY(ensure_scratch(e, (B * T + B) * kPolyBytes));
+    RZK_TRY(ensure_scratch(e, (B * T + 3 * B) * kPolyBytes));
     return dev_sum_verify(e, B, T, zs, zp, cs, cp, gs, ts, tp, u, d, flags, (int32_t *)e->scratch, (cudaStream_t)stream);
 }
 
@@ -1582,7 +1649,7 @@ int rzk_sum_verify_batch(rzk_engine *e, size_t B, uint32_t T, const int32_t *zs,
     std::vector<HArr> a = {{zs, nullptr, T * 3 * kPolyBytes}, {zp, nullptr, 3 * kPolyBytes}, {cs, nullptr, T * 2 * kPolyBytes},
                            {cp, nullptr, 2 * kPolyBytes}, {gs, nullptr, T * kPolyBytes}, {ts, nullptr, T * kPolyBytes},
                            {tp, nullptr, kPolyBytes}, {u, nullptr, kPolyBytes}, {dch, nullptr, kN}};
-    return run_chunked(e, B, a, (T + 1) * kPolyBytes, bm, [&](size_t n, void **d, char *sc, uint32_t *fl, cudaStream_t s) {
+    return run_chunked(e, B, a, (T + 3) * kPolyBytes, bm, [&](size_t n, void **d, char *sc, uint32_t *fl, cudaStream_t s) {
         return dev_sum_verify(e, n, T, (const int32_t *)d[0], (const int32_t *)d[1], (const int32_t *)d[2], (const int32_t *)d[3],
                               (const int32_t *)d[4], (const int32_t *)d[5], (const int32_t *)d[6], (const int32_t *)d[7],
                               (const int8_t *)d[8], fl, (int32_t *)sc, s);

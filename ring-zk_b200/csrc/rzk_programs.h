@@ -109,21 +109,28 @@ constexpr inline void prog_keymatvec(Prog &P, int sv, int st, int sw, bool check
 // optionally also w = A2.z - c2*d  (left/right sides of the third equation folded
 // together, linear.rs:236-249 / sum.rs:300-319).
 // sz = z (3 polys), st = t, sc = commitment c (2 polys: c1, c2), sd = d, sw = w out or -1
-constexpr inline void prog_verify_first(Prog &P, int sz, int st, int sc, int sd, int sw)
+// With sdh >= 0 the NTT image of d comes from stream sdh (written by prog_challenge_image for the group the item
+// belongs to) instead of being transformed per item: the T terms of a Sum proof and the two first equations of a
+// Linear proof share one challenge.
+constexpr inline void prog_verify_first(Prog &P, int sz, int st, int sc, int sd, int sw, int sdh = -1)
 {
     P.add(OP_SEG);
-    P.add(OP_FWD, sd, FWD_SCALED, 0, 0);
-    P.add(OP_ST);
+    if (sdh < 0) {
+        P.add(OP_FWD, sd, FWD_SCALED, 0, 0);
+        P.add(OP_ST);
+    }
     P.add(OP_FWD, sz, 0, 0, 1);
     P.add(OP_MACK, 0, 0, MAC_INIT);
     P.add(OP_FWD, sz, 0, 0, 2);
     P.add(OP_MACK, 0, 1, 0);
     if (sw >= 0) P.add(OP_MACK, 1, 2, MAC_INIT);
     P.add(OP_FWD, sc, 0, 0, 0);
-    P.add(OP_MACV, 0, 0, MAC_NEG);
+    if (sdh < 0) P.add(OP_MACV, 0, 0, MAC_NEG);
+    else P.add(OP_MACG, 0, sdh, MAC_NEG);
     if (sw >= 0) {
         P.add(OP_FWD, sc, 0, 0, 1);
-        P.add(OP_MACV, 1, 0, MAC_NEG);
+        if (sdh < 0) P.add(OP_MACV, 1, 0, MAC_NEG);
+        else P.add(OP_MACG, 1, sdh, MAC_NEG);
     }
     P.add(OP_INV, 0, 0);
     P.add(OP_ADDP, sz, 0, 0, 0);
@@ -134,6 +141,15 @@ constexpr inline void prog_verify_first(Prog &P, int sz, int st, int sc, int sd,
         P.add(OP_ADDP, sz, 0, 0, 1);
         P.add(OP_FIN, sw, FIN_STORE, 0, 0);
     }
+}
+
+// NTT image of the challenge d (two primes, Montgomery-operand form) for prog_verify_first(..., sdh)
+// streams: sd = d (i8, 1 poly per group), sdh = image out
+constexpr inline void prog_challenge_image(Prog &P, int sd, int sdh)
+{
+    P.add(OP_SEG);
+    P.add(OP_FWD, sd, FWD_SCALED, 0, 0);
+    P.add(OP_STG, sdh);
 }
 
 constexpr inline void prog_norm_verify(Prog &P, int sz)
@@ -236,6 +252,38 @@ constexpr inline void prog_mulsum(Prog &P, int T, int sa, int sb, int ssub0, int
     P.add(OP_FIN, sout >= 0 ? sout : 0, mode, 0, 0);
 }
 
+// Two product sums over the same scalars in one pass (the prover's commit phase, linear.rs:91-95 + 124-129,
+// sum.rs:107-115 + 154-160):
+//     out0 = sum_{i<T} a_i * b_i            (x' = sum g_i x_i)
+//     out1 = sum_{i<T} a_i * c_i  -  sub    (u  = sum g_i (A2.y_i) - A2.y')
+// Every a_i is transformed once instead of twice: 3 transforms per term and prime instead of 4.
+// sa, sb, sc: streams with T polys per item; ssub: single-poly stream.
+constexpr inline void prog_mulsum2(Prog &P, int T, int sa, int sb, int sc, int ssub, int sout0, int sout1)
+{
+    P.add(OP_SEG);
+    P.add(OP_FWD, sa, FWD_SCALED, 0, 0);
+    P.add(OP_ST);
+    P.add(OP_FWD, sb, 0, 0, 0);
+    P.add(OP_MACV, 0, 0, MAC_INIT);
+    P.add(OP_FWD, sc, 0, 0, 0);
+    P.add(OP_MACV, 1, 0, MAC_INIT);
+    if (T > 1) {
+        P.add(OP_LOOP, 0, 0, 0, T - 1);
+        P.add(OP_FWD, sa, FWD_SCALED, 0, 1, 1);
+        P.add(OP_ST);
+        P.add(OP_FWD, sb, 0, 0, 1, 1);
+        P.add(OP_MACV, 0, 0, 0);
+        P.add(OP_FWD, sc, 0, 0, 1, 1);
+        P.add(OP_MACV, 1, 0, 0);
+        P.add(OP_ENDLOOP);
+    }
+    P.add(OP_INV, 0, 0);
+    P.add(OP_FIN, sout0, FIN_STORE, 0, 0);
+    P.add(OP_INV, 1, 1);
+    P.add(OP_ADDP, ssub, 0, MAC_NEG, 0);
+    P.add(OP_FIN, sout1, FIN_STORE, 0, 0);
+}
+
 // ---- compile-time program descriptors (vm_run_static) --------------------------------------
 // Stream numbering is the one the engine's dev_* helpers use for the same programs.
 
@@ -269,6 +317,18 @@ struct SPVerifyFirstW {          // streams: 0 = z, 1 = t, 2 = c, 3 = d (i8), 4 
     static constexpr uint8_t dtype[kMaxStreams] = {DT_I32, DT_I32, DT_I32, DT_I8, DT_I32};
 };
 
+struct SPVerifyFirstWG {         // streams: 0 = z, 1 = t, 2 = c, 4 = w out, 5 = NTT image of d (per group)
+    static constexpr int kNP = 2, kMode = 1;
+    static constexpr Prog prog = [] { Prog p; prog_norm_verify(p, 0); prog_verify_first(p, 0, 1, 2, 3, 4, 5); p.end(); return p; }();
+    static constexpr uint8_t dtype[kMaxStreams] = {DT_I32, DT_I32, DT_I32, DT_I8, DT_I32, DT_I32};
+};
+
+struct SPChallengeImage {        // streams: 0 = d (i8), 1 = image out
+    static constexpr int kNP = 2, kMode = 1;
+    static constexpr Prog prog = [] { Prog p; prog_challenge_image(p, 0, 1); p.end(); return p; }();
+    static constexpr uint8_t dtype[kMaxStreams] = {DT_I8, DT_I32};
+};
+
 struct SPRespond {               // streams: 0 = y, 1 = r (i8), 2 = d (i8), 3 = z out
     static constexpr int kNP = 1, kMode = 0 /* MODE_SEQ */;
     static constexpr Prog prog = [] { Prog p; prog_respond(p, 0, 1, 2, 3); p.end(); return p; }();
@@ -286,6 +346,12 @@ struct SPMulSum1 {               // streams: 0 = a, 1 = b, 2 = sub0, 4 = out  ou
     static constexpr int kNP = 3, kMode = 0;
     static constexpr Prog prog = [] { Prog p; prog_mulsum(p, 2, 0, 1, 2, -1, 4, FIN_STORE); p.end(); return p; }();
     static constexpr uint8_t dtype[kMaxStreams] = {DT_I32, DT_I32, DT_I32, DT_I32, DT_I32};
+};
+
+struct SPMulSum2 {               // streams: 0 = a, 1 = b, 2 = c, 3 = sub, 4 = out0, 5 = out1   (prog_mulsum2)
+    static constexpr int kNP = 3, kMode = 0;
+    static constexpr Prog prog = [] { Prog p; prog_mulsum2(p, 2, 0, 1, 2, 3, 4, 5); p.end(); return p; }();
+    static constexpr uint8_t dtype[kMaxStreams] = {DT_I32, DT_I32, DT_I32, DT_I32, DT_I32, DT_I32};
 };
 
 struct SPMulSumCmp {             // streams: 0 = a, 1 = b, 2 = sub0, 3 = sub1  sum a_i*b_i - sub0 - sub1 == 0

@@ -46,6 +46,9 @@ enum OpCode : uint8_t {
     OP_NORM,     // (once) squared 2-norm check of c consecutive polys of stream a from off; b = bound select
     OP_LOOP,     // repeat the ops up to OP_ENDLOOP `off` times (iteration index scales `step`)
     OP_ENDLOOP,
+    OP_STG,      // NTT image out: stream a [group][prime][512 words, lane-private order] = cur reduced to [0,p)
+                 // (the Montgomery operand a later launch consumes with OP_MACG; cur comes from a FWD_SCALED transform)
+    OP_MACG,     // acc[a] (+)= image stream b (.) cur (Montgomery), the image read from global memory     c: MAC_* flags
 };
 
 enum : uint8_t { FWD_SCALED = 1, FWD_CHECK_SMALL = 2, FWD_HWPOLY = 4 };   // HWPOLY: half warp h reads poly off + h
@@ -154,7 +157,7 @@ inline ProgNeeds scan_needs(const Op *ops)
     for (int i = 0; i < kMaxOps && ops[i].code != OP_END; ++i) {
         const Op &o = ops[i];
         if (o.code == OP_ST || o.code == OP_MACV || o.code == OP_LD) n.slot = true;
-        if ((o.code == OP_MACK || o.code == OP_MACV || o.code == OP_INV) && o.a == 1) n.acc1 = true;
+        if ((o.code == OP_MACK || o.code == OP_MACV || o.code == OP_MACG || o.code == OP_INV) && o.a == 1) n.acc1 = true;
         if (o.code == OP_INV && (int)o.b + 1 > n.nstash) n.nstash = (int)o.b + 1;
     }
     return n;

@@ -414,6 +414,35 @@ RZK_VM void op_ld(Lane *lanes, const LaneCtx *ctxs, const Op &op)
     }
 }
 
+// NTT images in global memory (OP_STG / OP_MACG): one image = np rows of 512 words in the lane-private order of the
+// operand slot; a transform that several items share (the challenge d of the T terms of a Sum proof, of both first
+// equations of a Linear proof) is computed once per group by one launch and read by the items of the next.
+RZK_VM uint32_t *image_row(const VmLaunch &K, const Stream &st, const LaneCtx &ctx, const Lane &L)
+{
+    return reinterpret_cast<uint32_t *>(const_cast<void *>(st.base)) + stream_poly(st, ctx.item, (uint32_t)L.pi) * kN;
+}
+
+RZK_VM void op_stg(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const Op &op)
+{
+    const Stream st = K.st[op.a];
+    RZK_EACH_LANE {
+        RZK_LANE;
+        const PrimeC &pc = L.pc;
+        if (ctx.active) {
+            uint4 *s4 = reinterpret_cast<uint4 *>(image_row(K, st, ctx, L));
+            RZK_UNROLL
+            for (int j = 0; j < 8; ++j) {
+                uint4 q;
+                q.x = csub(csub(L.cur[4 * j + 0], pc.p2), pc.p);
+                q.y = csub(csub(L.cur[4 * j + 1], pc.p2), pc.p);
+                q.z = csub(csub(L.cur[4 * j + 2], pc.p2), pc.p);
+                q.w = csub(csub(L.cur[4 * j + 3], pc.p2), pc.p);
+                s4[j * kLanes + t] = q;
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------- epilogue (last prime only)
 
 // Number of coefficients a lane finishes: in the warp-per-item modes two half warps share an item.
@@ -780,15 +809,16 @@ RZK_VM int op_inv(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int q, in
             }
         }
         return qe;
+    } else {
+        RZK_NOUNROLL
+        for (;; ++q) {
+            const Op e = K.ops[q];
+            if (e.code == OP_ADDP) { if (last) op_addp<MODE>(K, ctxs, V, e, it, K.st[e.a].dtype); }
+            else if (e.code == OP_FIN) { if (last) op_fin<MODE>(K, lanes, ctxs, V, e, it); }
+            else break;
+        }
+        return q;
     }
-    RZK_NOUNROLL
-    for (;; ++q) {
-        const Op e = K.ops[q];
-        if (e.code == OP_ADDP) { if (last) op_addp<MODE>(K, ctxs, V, e, it, K.st[e.a].dtype); }
-        else if (e.code == OP_FIN) { if (last) op_fin<MODE>(K, lanes, ctxs, V, e, it); }
-        else break;
-    }
-    return q;
 }
 
 // params.rs:102-118 via polynomial.rs:60-73: floor(sqrt(sum c^2)) <= bound  <=>  sum c^2 < (bound+1)^2
@@ -932,6 +962,17 @@ RZK_VM void vm_run_item(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs)
                     break;
                 case OP_ST:
                     op_st(lanes, ctxs, op);
+                    break;
+                case OP_STG:
+                    op_stg(K, lanes, ctxs, op);
+                    break;
+                case OP_MACG:
+                    RZK_EACH_LANE {
+                        RZK_LANE;
+                        const uint32_t *img = image_row(K, K.st[op.b], ctx, L);
+                        if (op.a == 0) mac_var(L.acc0, L.cur, img, t, op.c, L.pc.p, L.pc.p2, L.pc.pinv);
+                        else mac_var_smem(ctx.acc1, L.cur, img, t, op.c, L.pc.p, L.pc.p2, L.pc.pinv);
+                    }
                     break;
                 case OP_LD:
                     op_ld(lanes, ctxs, op);
@@ -1088,6 +1129,15 @@ RZK_VM void sp_exec(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int it,
             }
         } else if constexpr (op.code == OP_ST) {
             op_st(lanes, ctxs, op);
+        } else if constexpr (op.code == OP_STG) {
+            op_stg(K, lanes, ctxs, op);
+        } else if constexpr (op.code == OP_MACG) {
+            RZK_EACH_LANE {
+                RZK_LANE;
+                const uint32_t *img = image_row(K, K.st[op.b], ctx, L);
+                if constexpr (op.a == 0) mac_var(L.acc0, L.cur, img, t, op.c, L.pc.p, L.pc.p2, L.pc.pinv);
+                else mac_var_smem(ctx.acc1, L.cur, img, t, op.c, L.pc.p, L.pc.p2, L.pc.pinv);
+            }
         } else if constexpr (op.code == OP_LD) {
             op_ld(lanes, ctxs, op);
         }

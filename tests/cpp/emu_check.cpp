@@ -453,6 +453,35 @@ int main(int argc, char **argv)
                 for (size_t i = 0; i < N; ++i) CHECK(tmp[i] == o1[b * N + i], "static mulsum T=1 mismatch");
             }
         }
+        // two product sums over the same scalars in one pass (prog_mulsum2): out0 = sum g_i*x_i, out1 = sum g_i*c_i - sub,
+        // static and interpreted, against the single-output program run twice; T = 3 and T = 1
+        for (int TT : {T, 1}) {
+            std::vector<int32_t> cs2(xs.size());
+            for (size_t i = 0; i < cs2.size(); ++i) cs2[i] = xs[(i * 7 + 3) % xs.size()];
+            std::vector<int32_t> r0(B * N, 0), r1(B * N, 0);
+            {
+                Emu EA(3, L2, keyp.data(), B);
+                Prog pa; prog_mulsum(pa, TT, 0, 1, -1, -1, 2, FIN_STORE); pa.end(); pa.install(EA.K);
+                EA.stream(0, gs.data(), T, DT_I32); EA.stream(1, xs.data(), T, DT_I32); EA.stream(2, r0.data(), 1, DT_I32);
+                EA.run(B);
+                Emu EB(3, L2, keyp.data(), B);
+                Prog pb; prog_mulsum(pb, TT, 0, 1, 2, -1, 3, FIN_STORE); pb.end(); pb.install(EB.K);
+                EB.stream(0, gs.data(), T, DT_I32); EB.stream(1, cs2.data(), T, DT_I32); EB.stream(2, sub.data(), 1, DT_I32);
+                EB.stream(3, r1.data(), 1, DT_I32);
+                EB.run(B);
+            }
+            for (int pass = 0; pass < 2; ++pass) {
+                std::vector<int32_t> o0(B * N, 0), o1(B * N, 0);
+                Emu E2(3, L2, keyp.data(), B);
+                if (pass == 0) { Prog p2; prog_mulsum2(p2, TT, 0, 1, 2, 3, 4, 5); p2.end(); p2.install(E2.K); }
+                else { SPMulSum2::prog.install(E2.K); E2.K.loop_count = TT - 1; }
+                E2.stream(0, gs.data(), T, DT_I32); E2.stream(1, xs.data(), T, DT_I32); E2.stream(2, cs2.data(), T, DT_I32);
+                E2.stream(3, sub.data(), 1, DT_I32); E2.stream(4, o0.data(), 1, DT_I32); E2.stream(5, o1.data(), 1, DT_I32);
+                if (pass == 0) E2.run(B); else E2.run<SPMulSum2>(B);
+                CHECK(o0 == r0, "mulsum2 out0 differs (T=%d pass %d)", TT, pass);
+                CHECK(o1 == r1, "mulsum2 out1 differs (T=%d pass %d)", TT, pass);
+            }
+        }
         printf("mulsum T=%d ok, ops=%d\n", T, pr.n);
     }
 
@@ -517,6 +546,30 @@ int main(int argc, char **argv)
                 for (int b = 0; b < B; ++b) {
                     CHECK((E.flags[b] == 0) == (variant == 0), "static verify variant %d item %d flags %u", variant, b, E.flags[b]);
                     CHECK(E2.flags[b] == E.flags[b], "static verify W flags differ");
+                }
+                // the same launch with the challenge's NTT image computed once per group by a launch of its own
+                // (OP_STG / OP_MACG), static and interpreted; group size 1 here, shared images are checked on the GPU
+                {
+                    std::vector<uint32_t> img(B * 2 * N, 0xDEADBEEFu), img_i(B * 2 * N, 0xDEADBEEFu);
+                    Emu EI(2, L2, keyp.data(), B);
+                    SPChallengeImage::prog.install(EI.K);
+                    EI.stream(0, d.data(), 1, DT_I8); EI.stream(1, img.data(), 2, DT_I32);
+                    EI.run<SPChallengeImage>(B);
+                    Emu EJ(2, L2, keyp.data(), B);
+                    SPChallengeImage::prog.install(EJ.K);
+                    EJ.stream(0, d.data(), 1, DT_I8); EJ.stream(1, img_i.data(), 2, DT_I32);
+                    EJ.run(B);
+                    CHECK(img == img_i, "challenge image: static and interpreted differ");
+                    for (int pass = 0; pass < 2; ++pass) {
+                        std::vector<int32_t> w_g(B * N, 0);
+                        Emu E3(2, L2, keyp.data(), B);
+                        SPVerifyFirstWG::prog.install(E3.K);
+                        E3.stream(0, zz.data(), 3, DT_I32); E3.stream(1, t32.data(), 1, DT_I32); E3.stream(2, c32.data(), 2, DT_I32);
+                        E3.stream(3, d.data(), 1, DT_I8); E3.stream(4, w_g.data(), 1, DT_I32); E3.stream(5, img.data(), 2, DT_I32);
+                        if (pass == 0) E3.run<SPVerifyFirstWG>(B); else E3.run(B);
+                        for (int b = 0; b < B; ++b) CHECK(E3.flags[b] == E.flags[b], "verify with challenge image: flags differ (pass %d)", pass);
+                        CHECK(w_g == w_s, "verify with challenge image: w differs (pass %d)", pass);
+                    }
                 }
                 if (variant == 0) {        // w = A2.z - c2*d
                     std::vector<int64_t> az(N), cd(N), wo(N);

@@ -69,7 +69,7 @@ def main():
     print(f"linear_respond B={BL} {mn:8.3f} ms {BL / mn * 1e3 / 1e6:8.3f} M/s")
     mn, _ = timeit(lambda: eng.dev("linear_verify_batch", BL, zl, zpl, cl, cp, g, tl, tpl, u, dl, fl, stream=st))
     print(f"linear_verify  B={BL} {mn:8.3f} ms {BL / mn * 1e3 / 1e6:8.3f} M/s   flags any: {int(fl.any())}")
-    BS, TT = min(B, 1 << 10), 64
+    BS, TT = min(B, 1 << 12), 64
     gs, xs = T(s.scalar(BS, TT)), T(s.uniform_q(BS, TT, 1))
     rs, ys = T(s.small(BS, TT)), T(s.gaussian(BS, TT))
     rps, yps, ds = T(s.small(BS)), T(s.gaussian(BS)), T(s.challenge(BS))
