@@ -272,6 +272,61 @@ def test_full_size_properties(setup):
     assert (t[idx] == t_o).all()
 
 
+def test_full_size_linear(setup):
+    """BASELINE config 4 at full size (2^14 instances) through the host entry points (several pipeline chunks on
+    several streams): honest transcripts verify, a tampered subset fails and nothing else does, and a random sample of
+    instances is bit-exact against the oracle in every output of the prover's commit phase."""
+    eng, o, s = setup
+    B = 1 << 14
+    x, g = s.message(B), s.scalar(B)
+    r, rp, y, yp, d = s.small(B), s.small(B), s.gaussian(B), s.gaussian(B), s.challenge(B)
+    lc = eng.linear_commit(g, x, rp, r, y, yp)
+    assert UB(lc["ok"], B).all()
+    idx = np.random.default_rng(2).choice(B, 24, replace=False)
+    idx[0], idx[1] = 0, B - 1
+    lo = o.linear_commit_batch(g[idx], x[idx], rp[idx], r[idx], y[idx], yp[idx])
+    for kname in ("gx", "cp", "c", "t", "tp", "u"):
+        assert (lc[kname][idx] == lo[kname]).all(), kname
+    z, zp = eng.linear_respond(y, yp, r, rp, d)
+    z_o, zp_o = o.linear_respond_batch(y[idx], yp[idx], r[idx], rp[idx], d[idx])
+    assert (z[idx] == z_o).all() and (zp[idx] == zp_o).all()
+    assert UB(eng.linear_verify(z, zp, lc["c"], lc["cp"], g, lc["t"], lc["tp"], lc["u"], d), B).all()
+    u = lc["u"].copy()
+    u[::997, ..., 5] += 1                                   # third equation only
+    zp2 = zp.copy()
+    zp2[3::1999, 2, 500] -= 1                               # second first-type equation and the third
+    v = UB(eng.linear_verify(z, zp2, lc["c"], lc["cp"], g, lc["t"], lc["tp"], u, d), B)
+    bad = np.zeros(B, bool); bad[::997] = True; bad[3::1999] = True
+    assert (v == ~bad).all()
+
+
+def test_full_size_sum(setup):
+    """BASELINE config 5 at full size (2^12 instances of 64 terms) through the host entry points: honest transcripts
+    verify, single tampered terms fail exactly their instance, sampled instances are bit-exact against the oracle."""
+    eng, o, s = setup
+    B, T = 1 << 12, 64
+    gs, xs = s.scalar(B, T), s.uniform_q(B, T, 1)
+    rs, ys = s.small(B, T), s.gaussian(B, T)
+    rp, yp, d = s.small(B), s.gaussian(B), s.challenge(B)
+    sc = eng.sum_commit(gs, xs, rp, rs, ys, yp)
+    assert UB(sc["ok"], B).all()
+    idx = np.array([0, 1777, B - 1])
+    so = o.sum_commit_batch(gs[idx], xs[idx], rp[idx], rs[idx], ys[idx], yp[idx])
+    for kname in ("xp", "cp", "cs", "ts", "tp", "u"):
+        assert (sc[kname][idx] == so[kname]).all(), kname
+    zs, zp = eng.sum_respond(ys, yp, rs, rp, d)
+    zs_o, zp_o = o.sum_respond_batch(ys[idx], yp[idx], rs[idx], rp[idx], d[idx])
+    assert (zs[idx] == zs_o).all() and (zp[idx] == zp_o).all()
+    assert UB(eng.sum_verify(zs, zp, sc["cs"], sc["cp"], gs, sc["ts"], sc["tp"], sc["u"], d), B).all()
+    ts = sc["ts"].copy()
+    ts[5::501, 63, ..., 0] += 1                             # first equation of the last term
+    gs2 = gs.copy()
+    gs2[7::1013, 31, 9] ^= 1                                # third equation through one scalar
+    v = UB(eng.sum_verify(zs, zp, sc["cs"], sc["cp"], gs2, ts, sc["tp"], sc["u"], d), B)
+    bad = np.zeros(B, bool); bad[5::501] = True; bad[7::1013] = True
+    assert (v == ~bad).all()
+
+
 @pytest.mark.parametrize("mode,B", [(0, 300), (1, 300), (1, 5000), (2, 5000)])
 def test_commit_execution_modes(mode, B, monkeypatch):
     """The three commitment kernels -- integer split-key program (0), FP64-pipe program (1), both pipes in
