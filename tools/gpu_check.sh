@@ -1,6 +1,6 @@
 # Development helper: what was run on the GPU box while iterating (edit freely).
 #   gpurun --timeout 900 -- 'bash tools/gpu_check.sh > gpurun_out/gpu_check.log 2>&1; cat gpurun_out/gpu_check.log'
 set -x
-timeout 300 python tools/quick_time.py 16384 2>&1 | grep -E "^(commit|open_|linear|sum|flags|.*Error)"
-RZK_NO_FUSE=1 RZK_NO_DIMG=1 timeout 300 python tools/quick_time.py 16384 2>&1 | grep -E "^(linear_|sum_|.*Error)"
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+for lib in lib_w12 lib_w14; do
+RZK_LIB_PATH=$PWD/ring-zk_b200/_build/$lib.so timeout 300 python tools/quick_time.py 65536 2>&1 | grep -E "^(commit|open_|linear|sum|flags|.*Error)"
+done
