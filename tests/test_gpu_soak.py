@@ -1,6 +1,7 @@
 """GPU: differential soak (tools/soak.py) -- random batch sizes around every launch-shape boundary; the integer (with
 and without phase mixing), FP64 and hybrid commitment kernels must agree with each other, the rotation-kernel response
-with the NTT response, and honest proofs must verify."""
+with the NTT response, honest proofs must verify, and Sum / Linear proofs in their default lowering (chunked three-prime
+epilogue, shared challenge image, one-launch product sums) must agree with the plain lowering run by the generic interpreter."""
 import os
 import subprocess
 import sys

@@ -1,5 +1,6 @@
 """Differential soak test on the GPU: random batch sizes, the commitment kernels (integer with / without phase mixing,
-FP64, hybrid) against each other, the rotation-kernel response against the NTT response, honest proofs verify.
+FP64, hybrid) against each other, the rotation-kernel response against the NTT response, honest proofs verify; Sum /
+Linear proofs in their default lowering against the plain lowering run by the generic interpreter.
 usage: python tools/soak.py [rounds] [seed]"""
 import importlib, os, sys
 import numpy as np
@@ -58,6 +59,38 @@ def main():
         assert v.all(), ("verify", B, it)
         assert UB(e0.commitment_verify(c, x, r), B).all()
         print(f"round {it:3d} B={B:6d} ok", flush=True)
+    # Linear / Sum proofs: the default lowering (three-prime kernels with the chunked epilogue, shared challenge image,
+    # one-launch product sums) against the plain one (every item transforms its own challenge, one launch per product
+    # sum) run through the generic interpreter, at instance counts around the launch-shape boundaries of the
+    # half-warp-per-item kernels (148 SMs x 2 x warps)
+    plain = make({"RZK_NO_FUSE": "1", "RZK_NO_DIMG": "1", "RZK_NO_STATIC": "1"})
+    plain.set_key_blocks(a1p, a2p)
+    e0 = engines["int+pp"]
+    for it in range(max(4, rounds // 3)):
+        B = int(rng.choice([1, 2, 3, 147, 149, 295, 297, 591, 593, 1185, int(rng.integers(1, 1500))]))
+        T = int(rng.choice([1, 2, 3, 5, 8]))
+        gs, xs = s.scalar(B, T), s.uniform_q(B, T, 1)
+        rs, ys = s.small(B, T), s.gaussian(B, T)
+        rp, yp, d = s.small(B), s.gaussian(B), s.challenge(B)
+        a, b = e0.sum_commit(gs, xs, rp, rs, ys, yp), plain.sum_commit(gs, xs, rp, rs, ys, yp)
+        for k in ("xp", "cp", "cs", "ts", "tp", "u"):
+            assert (a[k] == b[k]).all(), ("sum_commit", k, B, T)
+        zs, zp = e0.sum_respond(ys, yp, rs, rp, d)
+        args = [zs, zp, a["cs"], a["cp"], gs, a["ts"], a["tp"], a["u"], d]
+        assert UB(e0.sum_verify(*args), B).all() and UB(plain.sum_verify(*args), B).all(), ("sum_verify", B, T)
+        bad = rng.random(B) < 0.3
+        u2 = a["u"].copy(); u2[bad, ..., 11] += 1
+        ts2 = a["ts"].copy(); ts2[bad, T - 1, ..., 3] -= 1
+        for args2 in ([zs, zp, a["cs"], a["cp"], gs, a["ts"], a["tp"], u2, d], [zs, zp, a["cs"], a["cp"], gs, ts2, a["tp"], a["u"], d]):
+            v1, v2 = UB(e0.sum_verify(*args2), B), UB(plain.sum_verify(*args2), B)
+            assert (v1 == ~bad).all() and (v2 == ~bad).all(), ("sum_verify tampered", B, T)
+        if T == 1:
+            g, x = gs[:, 0], xs[:, 0]
+            la, lb = e0.linear_commit(g, x, rp, rs[:, 0], ys[:, 0], yp), plain.linear_commit(g, x, rp, rs[:, 0], ys[:, 0], yp)
+            for k in ("gx", "cp", "c", "t", "tp", "u"):
+                assert (la[k] == lb[k]).all(), ("linear_commit", k, B)
+        print(f"sum round {it:3d} B={B:6d} T={T} ok", flush=True)
+    plain.close()
     for e in engines.values():
         e.close()
     print("SOAK PASSED")
