@@ -15,6 +15,7 @@ __global__ void __launch_bounds__(256) k(uint32_t *out, uint32_t a, uint32_t b)
 #pragma unroll
     for (int i = 0; i < ILP; ++i) v[i] = threadIdx.x + i * 7 + blockIdx.x;
     uint32_t w = a | 1u, p = b | 3u;
+    const double wq = (double)w * 2.3283064365386963e-10, Cq = 4503599627370496.0 - (double)w * 1048576.0;
 #pragma unroll 1
     for (int it = 0; it < ITERS; ++it) {
 #pragma unroll
@@ -34,7 +35,18 @@ __global__ void __launch_bounds__(256) k(uint32_t *out, uint32_t a, uint32_t b)
                 uint32_t t = a * v[i] - q * p;
                 uint32_t x = t - p;
                 v[i] = (min(t, x) + w) ^ p;
-            } else if (MODE == 5) {                                          // Harvey CT butterfly on a pair
+            } else if (MODE == 8 || (MODE == 9 && (i & 1)) || (MODE == 10 && (i % 3) == 0)) {
+                // Harvey CT butterfly whose Shoup quotient floor(y * w' / 2^32) is computed on the FP64 pipe:
+                // y enters as the exact double 2^52 + y (bit pattern), wq = w' * 2^-32 and C = 2^52 - w' * 2^20 are
+                // per-twiddle constants, so fma_rd(D, wq, C) = 2^52 + floor(y * w' / 2^32) exactly: same q as IMAD.HI
+                uint32_t x = v[i], y = v[(i + 1) % ILP];
+                uint32_t xr = min(x, x - 2 * p);
+                double D = __hiloint2double(0x43300000, (int)y);
+                uint32_t q = (uint32_t)__double2loint(__fma_rd(D, wq, Cq));
+                uint32_t t = a * y - q * p;
+                v[i] = xr + t;
+                v[(i + 1) % ILP] = xr - t + 2 * p;
+            } else if (MODE == 5 || MODE == 9 || MODE == 10) {               // Harvey CT butterfly on a pair
                 uint32_t x = v[i], y = v[(i + 1) % ILP];
                 uint32_t xr = min(x, x - 2 * p);
                 uint32_t q = __umulhi(w, y);
@@ -150,6 +162,9 @@ int main()
     run<5>("harvey_ct_butterfly (1 per iter)", 1, d, prop.multiProcessorCount);
     run<6>("imad_wide_u32", 1, d, prop.multiProcessorCount);
     run<7>("shoup_mulmod + 3 alu (1 per iter)", 1, d, prop.multiProcessorCount);
+    run<8>("harvey_ct_butterfly, quotient on the FP64 pipe (1 per iter)", 1, d, prop.multiProcessorCount);
+    run<9>("harvey_ct_butterfly, alternating IMAD.HI / FP64 quotient (1 per iter)", 1, d, prop.multiProcessorCount);
+    run<10>("harvey_ct_butterfly, one in three on the FP64 pipe (1 per iter)", 1, d, prop.multiProcessorCount);
     double *dd;
     cudaMalloc(&dd, (size_t)prop.multiProcessorCount * 8 * 256 * 8);
     rund<0>("dfma", 1, dd, prop.multiProcessorCount);
