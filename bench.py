@@ -229,7 +229,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t_all0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -259,8 +259,6 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL's own log lines (e.g. "NCCL version ...") go to stderr: stdout carries exactly one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     B = args.batch
@@ -525,11 +523,22 @@ def main():
                                             "profiles/r1_imad_bench.jsonl); algorithmic mulmods per SURVEY.md 8(d)",
                              "fp64_pipe_peak_Tmulmod_s": MEASURED_F64_MULMOD_TPS},
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+def emit(line):
+    """The one JSON line of this run, on the process's real stdout."""
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 if __name__ == "__main__":
+    # stdout carries exactly one JSON line: whatever a library prints to file descriptor 1 (NCCL's "NCCL version ..."
+    # line under torchrun) is routed to stderr, and the JSON line is written to a duplicate of the original stdout
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     main()

@@ -12,7 +12,8 @@ def test_reference_arm_prints_contract_line():
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
                           "--ref-seconds", "0.5"], capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert res.returncode == 0, res.stderr
-    line = json.loads(res.stdout.strip().splitlines()[-1])
+    assert len(res.stdout.strip().splitlines()) == 1, "stdout must carry exactly one JSON line"
+    line = json.loads(res.stdout.strip())
     assert line["impl"] == "reference" and line["metric"] == "commitments/s" and line["unit"] == "commitments/s"
     assert line["value"] > 0 and line["higher_is_better"] is True and line["n_gpus"] == 1
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
