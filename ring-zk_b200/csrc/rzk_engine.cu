@@ -455,6 +455,27 @@ __global__ void rzk_flags_to_bitmap_kernel(size_t n, const uint32_t *__restrict_
     if (rng && range_any) atomicOr(range_any, rng);
 }
 
+// Last step of a product sum that was cut into `segs` segments per instance (dev_mulsum, small batches): the segment
+// results are canonical residues; out = centred(sum of the segments - sub0 - sub1), stored or compared with zero.
+__global__ void rzk_partial_reduce_kernel(size_t n_coeffs, uint32_t segs, const int32_t *__restrict__ part,
+                                          const int32_t *__restrict__ sub0, const int32_t *__restrict__ sub1,
+                                          int32_t *__restrict__ out, uint32_t *__restrict__ flags, uint32_t one_flag_word, int64_t q)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_coeffs) return;
+    const size_t inst = i / kN, n = i % kN;
+    int64_t acc = 0;
+    for (uint32_t sgm = 0; sgm < segs; ++sgm) acc += part[(inst * segs + sgm) * kN + n];
+    if (sub0) acc -= sub0[i];
+    if (sub1) acc -= sub1[i];
+    const int64_t half = (q - 1) / 2;
+    int64_t r = acc % q;
+    if (r > half) r -= q;
+    else if (r < -half) r += q;
+    if (out) out[i] = (int32_t)r;
+    else if (r != 0) atomicOr(&flags[one_flag_word ? 0 : inst], FLAG_FAIL);
+}
+
 // ZqI64::from(i64) for whole arrays: any representative -> canonical centred i32
 __global__ void rzk_pack_i64_kernel(size_t n, const int64_t *__restrict__ src, int32_t *__restrict__ dst, int64_t q)
 {
@@ -503,6 +524,8 @@ struct rzk_engine {
     uint32_t no_sparse = 0;         // RZK_NO_SPARSE=1: responses through the NTT program only (A/B timing)
     uint32_t *d_gstash[kPipe + 1] = {};   // residue stash of the three-prime programs, [SM][warp][half warp][kStashWordsMax]:
                                     // one per pipeline stream (their kernels may overlap) + one for the `_dev` entry points
+    int32_t *d_partial[kPipe + 1] = {};   // segment results of product sums cut into segments (small batches), per stream as above
+    uint32_t no_segments = 0;       // RZK_NO_SEGMENTS=1: never cut a product sum into segments (A/B timing)
     uint32_t *d_need = nullptr;     // hand-over words of dev_respond for the `_dev` entry points
     size_t need_cap = 0;
     uint32_t hyb_seq = 0;
@@ -521,7 +544,7 @@ struct rzk_engine {
     size_t scratch_cap = 0;
     uint64_t launches = 0;
     uint32_t static_respond = 0;
-    uint32_t no_fuse = 0;           // RZK_NO_FUSE=1: the Sum prover's two product sums as two launches; 2: one launch for Linear too (A/B timing)
+    uint32_t no_fuse = 0;           // RZK_NO_FUSE=1: the Sum prover's two product sums as two launches (A/B timing)
     uint32_t no_dimg = 0;           // RZK_NO_DIMG=1: every verify item transforms its challenge itself (A/B timing)
     uint32_t no_static = 0;         // RZK_NO_STATIC=1 forces the generic interpreter (debugging / A-B timing)
     uint32_t pp_mode = 0;           // RZK_PP: phase mixing between CTA halves (rzk_vm_exec.cuh), static programs only
@@ -908,10 +931,48 @@ int dev_commitment_verify(rzk_engine *e, size_t B, const int32_t *c, const int32
     return launch_np(e, 2, K, s);
 }
 
+// A product sum is one item per instance: a half warp walks its T terms.  A batch too small to fill the SMs (single
+// calls, the tail shard of a multi-GPU job) is cut into `segs` segments per instance, segs | T, that run as separate
+// items and are summed by rzk_partial_reduce_kernel: [B][T] is [B * segs][T / segs] in memory, so no data moves.
+uint32_t mulsum_segments(const rzk_engine *e, size_t B, uint32_t T)
+{
+    const size_t slots = (size_t)e->num_sms * RZK_SEQ3_WARPS * 2;        // half-warp items of one resident wave
+    if (e->no_segments || T < 2 || B * 2 > slots) return 1;
+    uint32_t best = 1;
+    for (uint32_t sg = 2; sg <= T; ++sg)
+        if (T % sg == 0 && B * sg <= slots) best = sg;
+    return best;
+}
+
+int dev_mulsum(rzk_engine *e, size_t B, uint32_t T, const int32_t *a, const int32_t *b, const int32_t *sub0,
+               const int32_t *sub1, int32_t *out, uint32_t *flags, cudaStream_t s);
+
+int dev_mulsum_segmented(rzk_engine *e, size_t B, uint32_t T, uint32_t segs, const int32_t *a, const int32_t *b, const int32_t *sub0,
+                         const int32_t *sub1, int32_t *out, uint32_t *flags, cudaStream_t s)
+{
+    int si = kPipe;
+    for (int i = 0; i < kPipe; ++i) if (e->pipe[i].stream == s) si = i;
+    if (!e->d_partial[si])
+        RZK_CUDA(e, cudaMalloc(&e->d_partial[si], kPolyBytes * (size_t)e->num_sms * RZK_SEQ3_WARPS * 2));
+    int32_t *part = e->d_partial[si];
+    e->no_segments |= 2u;                                                     // the segment launch itself is not cut again
+    const int rc = dev_mulsum(e, B * segs, T / segs, a, b, nullptr, nullptr, part, nullptr, s);
+    e->no_segments &= ~2u;
+    RZK_TRY(rc);
+    const size_t n = B * kN;
+    rzk_partial_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, segs, part, sub0, sub1, out, flags ? flags : e->d_misc + 1,
+                                                                           flags ? 0u : 1u, (int64_t)e->P.q);
+    RZK_CUDA(e, cudaGetLastError());
+    e->launches++;
+    return RZK_OK;
+}
+
 // out = sum_{i<T} a_i*b_i - sub0 - sub1 (store) or == 0 (compare)
 int dev_mulsum(rzk_engine *e, size_t B, uint32_t T, const int32_t *a, const int32_t *b, const int32_t *sub0,
                const int32_t *sub1, int32_t *out, uint32_t *flags, cudaStream_t s)
 {
+    if (const uint32_t segs = mulsum_segments(e, B, T); segs > 1)
+        return dev_mulsum_segmented(e, B, T, segs, a, b, sub0, sub1, out, flags, s);
     VmLaunch K; memset(&K, 0, sizeof(K));
     Prog p;
     prog_mulsum(p, (int)T, 0, 1, sub0 ? 2 : -1, sub1 ? 3 : -1, out ? 4 : -1, out ? FIN_STORE : FIN_CMPZ);
@@ -959,18 +1020,13 @@ int dev_linear_commit(rzk_engine *e, size_t B, const int32_t *g, const int32_t *
                       int32_t *tp, int32_t *u, uint32_t *flags, int32_t *scratch, cudaStream_t s, bool generic = false)
 {
     int32_t *w = scratch, *wp = scratch + B * kN;
-    if (e->no_fuse != 2) {
-        // (the one-launch form of g*x and u below was measured 5 % slower for a single term: its second accumulator lives
-        // in shared memory and nothing is amortised over a loop; RZK_NO_FUSE=2 selects it for A/B timing)
-        RZK_TRY(dev_mulsum(e, B, 1, g, x, nullptr, nullptr, gx, flags, s));                 // linear.rs:91-95
-        RZK_TRY(dev_commit_matvec(e, B, gx, rp, yp, cp, tp, wp, flags, 1, s, generic));     // linear.rs:96,121,129
-        RZK_TRY(dev_commit_matvec(e, B, x, r, y, c, t, w, flags, 1, s, generic));           // linear.rs:97,118,124-127
-        return dev_mulsum(e, B, 1, g, w, wp, nullptr, u, flags, s);                         // linear.rs:124-129
-    }
-    RZK_TRY(dev_keymatvec(e, B, yp, tp, wp, flags, 1, s));                              // linear.rs:121,129
+    // One launch per product here.  Sharing the transform of g between g*x and u (prog_mulsum2, or a single-term program
+    // that inverts one product after the other) was measured 5 % SLOWER for single terms: the longer straight-line
+    // program loses more in the instruction cache than the saved transform gains.
+    RZK_TRY(dev_mulsum(e, B, 1, g, x, nullptr, nullptr, gx, flags, s));                 // linear.rs:91-95
+    RZK_TRY(dev_commit_matvec(e, B, gx, rp, yp, cp, tp, wp, flags, 1, s, generic));     // linear.rs:96,121,129
     RZK_TRY(dev_commit_matvec(e, B, x, r, y, c, t, w, flags, 1, s, generic));           // linear.rs:97,118,124-127
-    RZK_TRY(dev_mulsum2(e, B, 1, g, x, w, wp, gx, u, flags, s));                        // linear.rs:91-95,124-129
-    return dev_commit(e, B, gx, rp, cp, flags, s, generic);                             // linear.rs:96
+    return dev_mulsum(e, B, 1, g, w, wp, nullptr, u, flags, s);                         // linear.rs:124-129
 }
 
 int dev_linear_verify(rzk_engine *e, size_t B, const int32_t *z, const int32_t *zp, const int32_t *c, const int32_t *cp,
@@ -978,7 +1034,8 @@ int dev_linear_verify(rzk_engine *e, size_t B, const int32_t *z, const int32_t *
                       uint32_t *flags, int32_t *scratch, cudaStream_t s)
 {
     int32_t *w = scratch, *wp = scratch + B * kN;
-    // (a shared NTT image of d, as in dev_sum_verify, was measured 1 % slower here: two users per image do not pay for the launch)
+    // (sharing the transform of d between the two equations was measured slower both ways: as an image from a launch of its
+    // own, as in dev_sum_verify, by 1 %; as one program for both equations by 49 % -- twice the straight-line code)
     RZK_TRY(dev_verify_first(e, B, z, t, c, 2, d, 1, w, flags, 1, s));                  // linear.rs:218,225-229
     RZK_TRY(dev_verify_first(e, B, zp, tp, cp, 2, d, 1, wp, flags, 1, s));              // linear.rs:221,231-235
     return dev_mulsum(e, B, 1, g, w, wp, u, nullptr, flags, s);                         // linear.rs:236-249
@@ -990,7 +1047,7 @@ int dev_sum_commit(rzk_engine *e, size_t B, uint32_t T, const int32_t *gs, const
                    int32_t *ts, int32_t *tp, int32_t *u, uint32_t *flags, int32_t *scratch, cudaStream_t s, bool generic = false)
 {
     int32_t *ws = scratch, *wp = scratch + B * T * kN;
-    if (e->no_fuse == 1 || T == 1) {
+    if (e->no_fuse == 1 || T == 1 || mulsum_segments(e, B, T) > 1) {      // (small batches: each product sum is cut into segments)
         RZK_TRY(dev_mulsum(e, B, T, gs, xs, nullptr, nullptr, xp, flags, s));               // sum.rs:107-115
         RZK_TRY(dev_commit_matvec(e, B, xp, rp, yp, cp, tp, wp, flags, 1, s, generic));     // sum.rs:116,151,160
         RZK_TRY(dev_commit_matvec(e, B * T, xs, rs, ys, cs, ts, ws, flags, T, s, generic)); // sum.rs:117-120,145-148,157
@@ -1152,6 +1209,7 @@ int rzk_create(const rzk_params *params, int device, rzk_engine **out)
     if (const char *cs = getenv("RZK_NO_STATIC")) e->no_static = (uint32_t)atoi(cs);
     if (const char *cs = getenv("RZK_NO_DIMG")) e->no_dimg = (uint32_t)atoi(cs);
     if (const char *cs = getenv("RZK_NO_FUSE")) e->no_fuse = (uint32_t)atoi(cs);
+    if (const char *cs = getenv("RZK_NO_SEGMENTS")) e->no_segments = (uint32_t)atoi(cs) ? 1u : 0u;
     if (const char *cs = getenv("RZK_COMMIT_MODE")) e->commit_mode = (uint32_t)atoi(cs);
     if (const char *cs = getenv("RZK_NO_SPARSE")) e->no_sparse = (uint32_t)atoi(cs);
     if (const char *cs = getenv("RZK_HYB_DISABLE")) e->hyb_disable = (uint32_t)atoi(cs);
@@ -1227,6 +1285,7 @@ void rzk_destroy(rzk_engine *e)
     if (e->d_f64tab) cudaFree(e->d_f64tab);
     if (e->d_need) cudaFree(e->d_need);
     for (auto p : e->d_gstash) if (p) cudaFree(p);
+    for (auto p : e->d_partial) if (p) cudaFree(p);
     if (e->d_misc) cudaFree(e->d_misc);
     if (e->h_range) cudaFreeHost(e->h_range);
     delete e;

@@ -61,9 +61,9 @@ def main():
         print(f"round {it:3d} B={B:6d} ok", flush=True)
     # Linear / Sum proofs: the default lowering (three-prime kernels with the chunked epilogue, shared challenge image,
     # one-launch product sums) against the plain one (every item transforms its own challenge, one launch per product
-    # sum) run through the generic interpreter, at instance counts around the launch-shape boundaries of the
+    # sum, no cutting of small batches into segments) run through the generic interpreter, at instance counts around the launch-shape boundaries of the
     # half-warp-per-item kernels (148 SMs x 2 x warps)
-    plain = make({"RZK_NO_FUSE": "1", "RZK_NO_DIMG": "1", "RZK_NO_STATIC": "1"})
+    plain = make({"RZK_NO_FUSE": "1", "RZK_NO_DIMG": "1", "RZK_NO_STATIC": "1", "RZK_NO_SEGMENTS": "1"})
     plain.set_key_blocks(a1p, a2p)
     e0 = engines["int+pp"]
     for it in range(max(4, rounds // 3)):
