@@ -27,7 +27,8 @@
  *   - The randomness r, y, d is drawn by the caller (host side, seeded RNG) and passed in; the
  *     protocol entry points sample nothing.  (Optional, separate: rzk_sample_*_dev, below.)
  *   - Execution knobs are environment variables read by rzk_create (RZK_COMMIT_MODE, RZK_COMMIT_PP, RZK_PP,
- *     RZK_CTA_SYNC, RZK_NO_SPARSE, RZK_CHUNK_ITEMS, ...): A/B timing only, results are identical in every setting.
+ *     RZK_CTA_SYNC, RZK_NO_SPARSE, RZK_NO_DIMG, RZK_NO_FUSE, RZK_NO_SEGMENTS, RZK_NO_STATIC, RZK_CHUNK_ITEMS, ...):
+ *     A/B timing only, results are identical in every setting.
  *   - There is no CPU fallback: without a CUDA device rzk_create fails with RZK_ERR_CUDA.
  */
 #ifndef RINGZK_B200_H
