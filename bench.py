@@ -491,6 +491,31 @@ def main():
                "h2d_bytes_per_step": B * (N * 4 + 3 * N), "d2h_bytes_per_step": B * 2 * N * 4 + (B + 7) // 8,
                "steps": ksteps, "api": "rzk_commit_batch (host pointers, pinned), chunked 4-stream pipeline (8192 items per chunk)"}
 
+        # the second half of BASELINE.json's metric, same way: Open-proof verifies/s through rzk_open_verify_batch
+        pin = lambda tdev: tdev.cpu().pin_memory()
+        zh, th, c1h, dh = pin(z), pin(t), pin(c[:, :1].contiguous()), pin(d)
+        vbm = torch.zeros((B + 7) // 8, dtype=torch.uint8).pin_memory()
+        zn, tn, c1n, dn, vn = zh.numpy(), th.numpy(), c1h.numpy(), dh.numpy(), vbm.numpy()
+
+        def host_verify():
+            eng._call("rzk_open_verify_batch", B, zn.ctypes.data, tn.ctypes.data, c1n.ctypes.data, dn.ctypes.data, vn.ctypes.data)
+        for _ in range(max(1, args.warmup)):
+            host_verify()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            host_verify()
+        torch.cuda.synchronize()
+        dtv = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([dtv], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dtv = float(tt.item())
+        assert bool((vbm == 0xFF).all()), "honest Open proofs must verify through the host path"
+        e2e["open_verify"] = {"value": world * B * ksteps / dtv, "unit": "open-proof verifies/s",
+                              "h2d_bytes_per_step": B * (3 * N * 4 + N * 4 + N * 4 + N), "d2h_bytes_per_step": (B + 7) // 8,
+                              "api": "rzk_open_verify_batch (host pointers, pinned)"}
+
     # ---- CPU baseline (rank 0, N=1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
