@@ -327,6 +327,59 @@ def test_full_size_sum(setup):
     assert (v == ~bad).all()
 
 
+@pytest.mark.parametrize("B,T", [(3, 4), (700, 4), (40, 64), (2500, 1)])
+def test_device_resident_linear_sum_match_host_entry_points(setup, B, T):
+    """The `_dev` Linear / Sum entry points (device pointers, caller's stream; what bench.py times) against the host
+    entry points on the same inputs: identical outputs and verdicts, at instance counts where small product sums are
+    cut into segments (3, 40, 700) and where they are not (2500)."""
+    import torch
+    eng, o, s = setup
+    dev = torch.device("cuda:0")
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    E = lambda *sh: torch.empty(sh, dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    gs, xs = s.scalar(B, T), s.uniform_q(B, T, 1)
+    rs, ys = s.small(B, T), s.gaussian(B, T)
+    rp, yp, d = s.small(B), s.gaussian(B), s.challenge(B)
+    h = eng.sum_commit(gs, xs, rp, rs, ys, yp)
+    xp, cp, cs, ts, tp, u = E(B, 1, N), E(B, 2, N), E(B, T, 2, N), E(B, T, 1, N), E(B, 1, N), E(B, 1, N)
+    fl = torch.zeros(B, dtype=torch.int32, device=dev)
+    eng.dev("sum_commit_batch", B, T, up(gs), up(xs), up(rp), up(rs), up(ys), up(yp), xp, cp, cs, ts, tp, u, fl, stream=st)
+    torch.cuda.synchronize()
+    for name, t_dev in (("xp", xp), ("cp", cp), ("cs", cs), ("ts", ts), ("tp", tp), ("u", u)):
+        assert (t_dev.cpu().numpy() == h[name]).all(), name
+    assert not fl.any()
+    zs_h, zp_h = eng.sum_respond(ys, yp, rs, rp, d)
+    zs, zp = E(B, T, 3, N), E(B, 3, N)
+    eng.dev("sum_respond_batch", B, T, up(ys), up(yp), up(rs), up(rp), up(d), zs, zp, stream=st)
+    torch.cuda.synchronize()
+    assert (zs.cpu().numpy() == zs_h).all() and (zp.cpu().numpy() == zp_h).all()
+    u_bad = u.clone(); u_bad[::3, ..., 9] += 1
+    for u_t, expect in ((u, np.ones(B, bool)), (u_bad, np.arange(B) % 3 != 0)):
+        fl.zero_()
+        eng.dev("sum_verify_batch", B, T, zs, zp, cs, cp, up(gs), ts, tp, u_t, up(d), fl, stream=st)
+        torch.cuda.synchronize()
+        assert ((fl.cpu().numpy() == 0) == expect).all()
+        v_h = UB(eng.sum_verify(zs_h, zp_h, h["cs"], h["cp"], gs, h["ts"], h["tp"], u_t.cpu().numpy(), d), B)
+        assert (v_h == expect).all()
+    if T == 1:
+        g, x, r, y = gs[:, 0], xs[:, 0], rs[:, 0], ys[:, 0]
+        hl = eng.linear_commit(g, x, rp, r, y, yp)
+        gx, cpl, cl, tl, tpl, ul = E(B, 1, N), E(B, 2, N), E(B, 2, N), E(B, 1, N), E(B, 1, N), E(B, 1, N)
+        fl.zero_()
+        eng.dev("linear_commit_batch", B, up(g), up(x), up(rp), up(r), up(y), up(yp), gx, cpl, cl, tl, tpl, ul, fl, stream=st)
+        torch.cuda.synchronize()
+        for name, t_dev in (("gx", gx), ("cp", cpl), ("c", cl), ("t", tl), ("tp", tpl), ("u", ul)):
+            assert (t_dev.cpu().numpy() == hl[name]).all(), name
+        zl, zpl = E(B, 3, N), E(B, 3, N)
+        eng.dev("linear_respond_batch", B, up(y), up(yp), up(r), up(rp), up(d), zl, zpl, stream=st)
+        fl.zero_()
+        eng.dev("linear_verify_batch", B, zl, zpl, cl, cpl, up(g), tl, tpl, ul, up(d), fl, stream=st)
+        torch.cuda.synchronize()
+        assert not fl.any()
+        assert UB(eng.linear_verify(zl.cpu().numpy(), zpl.cpu().numpy(), hl["c"], hl["cp"], g, hl["t"], hl["tp"], hl["u"], d), B).all()
+
+
 @pytest.mark.parametrize("mode,B", [(0, 300), (1, 300), (1, 5000), (2, 5000)])
 def test_commit_execution_modes(mode, B, monkeypatch):
     """The three commitment kernels -- integer split-key program (0), FP64-pipe program (1), both pipes in
