@@ -1021,8 +1021,7 @@ int dev_linear_commit(rzk_engine *e, size_t B, const int32_t *g, const int32_t *
 {
     int32_t *w = scratch, *wp = scratch + B * kN;
     // One launch per product here.  Sharing the transform of g between g*x and u (prog_mulsum2, or a single-term program
-    // that inverts one product after the other) was measured 5 % SLOWER for single terms: the longer straight-line
-    // program loses more in the instruction cache than the saved transform gains.
+    // that inverts one product after the other) was measured 5 % SLOWER for single terms.
     RZK_TRY(dev_mulsum(e, B, 1, g, x, nullptr, nullptr, gx, flags, s));                 // linear.rs:91-95
     RZK_TRY(dev_commit_matvec(e, B, gx, rp, yp, cp, tp, wp, flags, 1, s, generic));     // linear.rs:96,121,129
     RZK_TRY(dev_commit_matvec(e, B, x, r, y, c, t, w, flags, 1, s, generic));           // linear.rs:97,118,124-127
