@@ -533,6 +533,7 @@ struct rzk_engine {
     uint32_t hyb_int_warps = 8;     // RZK_HYB_INT_WARPS: integer-path warps per CTA in the hybrid kernel (of 16)
     uint32_t commit_mode = 0;       // RZK_COMMIT_MODE: 0 = integer split-key program with phase mixing (measured best, 145 M/s),
                                     // 1 = FP64-pipe program (123 M/s), 2 = both pipes in one launch (hybrid, 142 M/s)
+    uint32_t mulsum2_pp = 2;        // RZK_MULSUM2_PP: phase mixing of the two-accumulator product-sum program (0 / 9 = off)
     uint32_t commit_pp = 2;         // RZK_COMMIT_PP: phase mixing of the split-key commitment program (0 / 9 = off)
     uint32_t *d_misc = nullptr;     // [0] range word, [1] dummy flags word
     uint32_t *h_range = nullptr;    // pinned host copy of the range word (single-chunk calls)
@@ -1003,7 +1004,9 @@ int dev_mulsum2(rzk_engine *e, size_t B, uint32_t T, const int32_t *a, const int
     set_stream(K, 0, a, T, DT_I32); set_stream(K, 1, b, T, DT_I32); set_stream(K, 2, c, T, DT_I32);
     set_stream(K, 3, sub, 1, DT_I32); set_stream(K, 4, out0, 1, DT_I32); set_stream(K, 5, out1, 1, DT_I32);
     K.loop_count = T - 1;
-    return launch_sp<SPMulSum2>(e, K, s);
+    // phase mixing between the CTA halves (as for the commitment program) measured +3.4 % on this kernel at 2^12 x 64 terms;
+    // on the single-accumulator product sums, A.y and the verify programs it measured within +-1 % or slower and stays off
+    return launch_sp<SPMulSum2>(e, K, s, e->mulsum2_pp);
 }
 
 // commit(x; r) -> c  and  t = A1.y, w = A2.y  for `items` (x, r, y) triples
@@ -1215,6 +1218,7 @@ int rzk_create(const rzk_params *params, int device, rzk_engine **out)
     if (const char *cs = getenv("RZK_HYB_INT_WARPS")) e->hyb_int_warps = (uint32_t)atoi(cs);
     if (const char *cs = getenv("RZK_PP")) e->pp_mode = (uint32_t)atoi(cs);
     if (const char *cs = getenv("RZK_COMMIT_PP")) e->commit_pp = (uint32_t)atoi(cs);
+    if (const char *cs = getenv("RZK_MULSUM2_PP")) e->mulsum2_pp = (uint32_t)atoi(cs);
     if (const char *cs = getenv("RZK_CHUNK_ITEMS")) e->chunk_items = (uint32_t)std::max(8, atoi(cs));
     Guard g(device);
     cudaDeviceProp prop;

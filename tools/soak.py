@@ -63,7 +63,7 @@ def main():
     # one-launch product sums) against the plain one (every item transforms its own challenge, one launch per product
     # sum, no cutting of small batches into segments) run through the generic interpreter, at instance counts around the launch-shape boundaries of the
     # half-warp-per-item kernels (148 SMs x 2 x warps)
-    plain = make({"RZK_NO_FUSE": "1", "RZK_NO_DIMG": "1", "RZK_NO_STATIC": "1", "RZK_NO_SEGMENTS": "1"})
+    plain = make({"RZK_NO_FUSE": "1", "RZK_NO_DIMG": "1", "RZK_NO_STATIC": "1", "RZK_NO_SEGMENTS": "1", "RZK_MULSUM2_PP": "0"})
     plain.set_key_blocks(a1p, a2p)
     e0 = engines["int+pp"]
     for it in range(max(4, rounds // 3)):
