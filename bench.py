@@ -152,6 +152,47 @@ def cpu_commit_rate(target_s=12.0, seed=7):
     return n / dt, cores, n, dt
 
 
+def cpu_other_configs(seed=11):
+    """The CPU restatement on the other configurations, all host threads, on stated sub-batches (Linear and
+    Sum are timed on a sub-batch and scale linearly in the instance count): Open verify, one Linear instance
+    (commit + respond + verify) and one Sum-64 instance."""
+    from oracle import oracle as orc
+    pkg = importlib.import_module("ring-zk_b200")
+    s = pkg.synth.Synth(seed, N=N)
+    o = orc.Oracle(orc.Params(N=N), *s.key())
+    cores = orc.max_threads()
+    out = {}
+    B = 2048 * cores
+    x, r, y, d = s.message(B), s.small(B), s.gaussian(B), s.challenge(B)
+    c, t, _ = o.open_commit_batch(x, r, y)
+    z = o.open_respond_batch(y, r, d)
+    c1 = np.ascontiguousarray(c[:, :1])
+    t0 = time.perf_counter(); ok = o.open_verify_batch(z, t, c1, d); dt = time.perf_counter() - t0
+    assert ok.all()
+    out["open_verify"] = {"value": B / dt, "unit": "open-proof verifies/s", "sample": f"{B} verifies in {dt:.2f} s"}
+    B = 512 * cores
+    g, x, r, rp, y, yp, d = s.scalar(B), s.message(B), s.small(B), s.small(B), s.gaussian(B), s.gaussian(B), s.challenge(B)
+    t0 = time.perf_counter()
+    lc = o.linear_commit_batch(g, x, rp, r, y, yp)
+    z, zp = o.linear_respond_batch(y, yp, r, rp, d)
+    ok = o.linear_verify_batch(z, zp, lc["c"], lc["cp"], g, lc["t"], lc["tp"], lc["u"], d)
+    dt = time.perf_counter() - t0
+    assert ok.all()
+    out["linear"] = {"value": B / dt, "unit": "Linear proofs (commit + respond + verify)/s", "sample": f"{B} instances in {dt:.2f} s"}
+    B, T = 16 * cores, 64
+    gs, xs, rs, ys = s.scalar(B, T), s.uniform_q(B, T, 1), s.small(B, T), s.gaussian(B, T)
+    rp, yp, d = s.small(B), s.gaussian(B), s.challenge(B)
+    t0 = time.perf_counter()
+    sc = o.sum_commit_batch(gs, xs, rp, rs, ys, yp)
+    zs, zp = o.sum_respond_batch(ys, yp, rs, rp, d)
+    ok = o.sum_verify_batch(zs, zp, sc["cs"], sc["cp"], gs, sc["ts"], sc["tp"], sc["u"], d)
+    dt = time.perf_counter() - t0
+    assert ok.all()
+    out["sum64"] = {"value": B / dt, "unit": "Sum proofs with 64 terms (commit + respond + verify)/s",
+                    "sample": f"{B} instances in {dt:.2f} s"}
+    return out
+
+
 def single_call_latency(eng, oracle_obj=None, reps=30):
     """Median latency in microseconds of one call on ONE item through the host C ABI (pageable numpy buffers) for the
     phases the reference's own Criterion benches time (benches/bench.rs:35-305: N = 512, Sum with 4 terms).
@@ -526,6 +567,7 @@ def main():
         if not args.no_extras:
             from oracle import oracle as orc
             cpu["single_call_latency_us_1thread"] = single_call_latency(eng, orc.Oracle(orc.Params(N=N), *key))
+            cpu["other_configs"] = cpu_other_configs()
 
     if rank == 0:
         line = {
