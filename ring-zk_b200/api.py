@@ -114,7 +114,10 @@ class Commitment:  # commit.rs:135-141
 class CommitmentKey:  # commit.rs:19-60
     def __init__(self, a1, a2, params: Params, N: int, device: int = -1):
         self.a1, self.a2, self.N = np.asarray(a1, np.int64), np.asarray(a2, np.int64), N
-        self.engine = _engine.Engine(N=N, device=device)
+        # the engine's sigma / norm bounds / exactness limits come from THESE parameters (not from Params::default())
+        rp = _engine.RzkParams(params.Q, params.b, N, params.n, params.k, params.l, params.kappa)
+        self.engine = _engine.Engine(N=N, device=device, params=rp)
+        assert self.engine.sigma() == params.standard_deviation(N)
         self.engine.set_key(self.a1, self.a2)
 
     @staticmethod

@@ -24,7 +24,6 @@
 #include "rzk_vm.h"
 
 #include "rzk_vm_exec.cuh"
-#include "rzk_f64.cuh"
 #include "rzk_sparse.cuh"
 #include "rzk_sample.cuh"
 #include "rzk_programs.h"
@@ -179,7 +178,7 @@ __global__ void __launch_bounds__(VmCfg<NP, MODE>::kMaxWarps * 32, 1) rzk_vm_ker
         ctx.active = item < K.n_items;
         ctx.item = ctx.active ? item : K.n_items - 1;
         if (K.item_mask) {                          // redo only the flagged items (warp-uniform skip)
-            ctx.active = ctx.active && K.item_mask[ctx.item] != 0;
+            ctx.active = ctx.active && K.item_mask[K.mask_div > 1 ? ctx.item / K.mask_div : ctx.item] != 0;
             if (!__any_sync(0xffffffffu, ctx.active)) continue;
         }
         // prefetch the input rows of the item this warp handles next into L2: lane k issues one bulk prefetch
@@ -199,171 +198,6 @@ __global__ void __launch_bounds__(VmCfg<NP, MODE>::kMaxWarps * 32, 1) rzk_vm_ker
     } else if (K.pp_mode != 0) {
         // a CTA whose group 0 never reached the hand-over point (no work) must still release group 1
         if (pp_group() == 0 && pp_count < (K.pp_mode == 1 ? 1u : 2u)) asm volatile("bar.arrive 10, %0;" ::"r"(blockDim.x) : "memory");
-    }
-}
-
-// ---- commitments on the FP64 pipe (rzk_f64.cuh): one warp per item, 4 transforms modulo a 46-bit prime ----
-
-constexpr int kF64G1D = 2 * 32 * 2;                       // doubles
-constexpr int kF64G2D = 2 * kLanes * kF64G2Stride * 2;
-constexpr int kF64KeyD = kF64KeyImages * kN * 2;
-constexpr int kF64TabD = kF64G1D + kF64G2D + kF64KeyD;    // 6144 doubles = 48 KiB
-constexpr int kF64Warps = 16;
-
-static size_t f64_smem_bytes(int warps) { return sizeof(double) * ((size_t)kF64TabD + (size_t)warps * 2 * kF64BufD); }
-
-// FP64 tables [g1 | g2 | key images] are contiguous on the device: one bulk copy
-__device__ __forceinline__ void f64_stage_tables(const F64Launch &K, double *s_tab, uint64_t *bar, bool issue)
-{
-    static_assert((kF64TabD * 8) % 16 == 0, "bulk copies move multiples of 16 bytes");
-    if (issue) {
-        tma_expect(bar, kF64TabD * 8);
-        tma_load(s_tab, K.g1, kF64TabD * 8, bar);
-    }
-}
-
-__device__ __forceinline__ void f64_ctx_init(LaneCtxF &ctx, double *s_tab, double *s_buf, int warp_slot, int lane)
-{
-    const int hw = lane >> 4;
-    ctx.buf = s_buf + (size_t)(warp_slot * 2 + hw) * kF64BufD;
-    ctx.buf_partner = s_buf + (size_t)(warp_slot * 2 + (hw ^ 1)) * kF64BufD;
-    ctx.g1 = reinterpret_cast<const double2 *>(s_tab);
-    ctx.g2 = reinterpret_cast<const double2 *>(s_tab + kF64G1D);
-    ctx.key = reinterpret_cast<const double2 *>(s_tab + kF64G1D + kF64G2D);
-    ctx.t = lane & 15;
-    ctx.hw = hw;
-    ctx.ridx = lane;
-}
-
-__device__ __forceinline__ void bulk_prefetch_l2(const void *p, uint32_t bytes)
-{
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-
-// next item's rows into L2: r (3 x 512 B) by lane 0, x (2 KB) by lane 1
-__device__ __forceinline__ void f64_prefetch_item(const F64Launch &K, uint32_t next, int lane)
-{
-    if (next < K.n_items) {
-        if (lane == 0) bulk_prefetch_l2(reinterpret_cast<const char *>(K.r) + (size_t)next * 3 * kN, 3 * kN);
-        else if (lane == 1) bulk_prefetch_l2(reinterpret_cast<const char *>(K.x) + (size_t)next * kN * 4, kN * 4);
-    }
-}
-
-__global__ void __launch_bounds__(kF64Warps * 32, 1) rzk_commit_f64_kernel(const __grid_constant__ F64Launch K)
-{
-    extern __shared__ __align__(16) double smd[];
-    __shared__ __align__(8) uint64_t s_bar;
-    if (threadIdx.x == 0) tma_init(&s_bar);
-    __syncthreads();
-    f64_stage_tables(K, smd, &s_bar, threadIdx.x == 0);
-    tma_wait(&s_bar);
-    const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    LaneCtxF ctx;
-    f64_ctx_init(ctx, smd, smd + kF64TabD, warp, lane);
-    const uint32_t per_grid = gridDim.x * warps;
-    const uint32_t first = blockIdx.x * warps + warp;
-    const uint32_t iters = (K.n_items + per_grid - 1) / per_grid;
-    LaneF L;
-#pragma unroll 1
-    for (uint32_t it = 0; it < iters; ++it) {
-        const uint32_t item = first + it * per_grid;
-        ctx.active = item < K.n_items;
-        ctx.item = ctx.active ? item : K.n_items - 1;
-        f64_prefetch_item(K, item + per_grid, lane);
-        if (K.pad_) __syncthreads();       // lock-step: one instruction-cache window per CTA (32 KB L1.5 vs ~70 KB of program)
-        f64_commit_item(K, &L, &ctx);
-    }
-}
-
-// ---- hybrid commitment kernel: both pipes at once -------------------------------------------------
-// Warps [0, wi) run the integer split-key program (FMA-heavy + ALU pipes), warps [wi, warps) run the
-// FP64 program (FP64 pipe) on different items of the same batch.  Each group claims `group size` items
-// at a time from a global counter, so the split adapts to the two paths' speeds; the group barrier of
-// the claim doubles as the lock-step barrier that keeps a group inside one instruction-cache window.
-struct HybridLaunch {
-    uint32_t *work;            // device counter, zeroed before the launch
-    uint32_t int_warps;
-    uint32_t disable;          // experiments: 1 = integer group idles, 2 = FP64 group idles
-};
-
-template <class SP>
-__global__ void __launch_bounds__(512, 1) rzk_commit_hybrid_kernel(const __grid_constant__ VmLaunch K, const __grid_constant__ F64Launch KF,
-                                                                   const __grid_constant__ HybridLaunch H)
-{
-    constexpr int NP = SP::kNP, MODE = SP::kMode;
-    extern __shared__ __align__(16) uint32_t smem[];
-    using S = VmSmem<NP, MODE>;
-    __shared__ uint32_t s_claim[2][3];     // claims are made one iteration ahead (slot it % 3) so that the next item can be prefetched
-    uint32_t *s_g1 = smem;
-    uint32_t *s_g2 = s_g1 + S::kG1;
-    uint32_t *s_key = s_g2 + S::kG2;
-    double *s_f64 = reinterpret_cast<double *>(smem + S::kTables);
-    const int nthreads = blockDim.x, warps = nthreads >> 5;
-    const int wi = (int)H.int_warps, wf = warps - wi;
-    uint32_t *s_hw = reinterpret_cast<uint32_t *>(s_f64 + kF64TabD);                       // wi int warps
-    double *s_fbuf = reinterpret_cast<double *>(s_hw + (size_t)wi * 2 * K.hw_words);       // wf FP64 warps
-
-    // stage the tables of both paths: TMA bulk copies issued by one thread, two mbarriers (one per table set)
-    __shared__ __align__(8) uint64_t s_bar[2];
-    if (threadIdx.x == 0) { tma_init(&s_bar[0]); tma_init(&s_bar[1]); }
-    __syncthreads();
-    stage_int_tables<NP, MODE>(K, s_g1, s_g2, s_key, &s_bar[0], threadIdx.x == 0);
-    f64_stage_tables(KF, s_f64, &s_bar[1], threadIdx.x == 0);
-    tma_wait(&s_bar[0]);
-    tma_wait(&s_bar[1]);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, hw = lane >> 4, t = lane & 15;
-    const uint32_t grp = warp >= wi ? 1u : 0u;
-    const uint32_t gw = grp ? (uint32_t)wf : (uint32_t)wi, wg = grp ? (uint32_t)(warp - wi) : (uint32_t)warp;
-    const bool leader = (wg == 0 && lane == 0);
-
-    if (H.disable == grp + 1) return;
-    if (grp == 0) {
-        uint32_t *mine = s_hw + (warp * 2 + hw) * K.hw_words;
-        LaneCtx ctx;
-        ctx.buf = mine;
-        ctx.slot = mine + K.off_slot;
-        ctx.slot_hw[0] = s_hw + (warp * 2 + 0) * K.hw_words + K.off_slot;
-        ctx.slot_hw[1] = s_hw + (warp * 2 + 1) * K.hw_words + K.off_slot;
-        ctx.acc1 = mine + K.off_acc1;
-        ctx.stash = mine + K.off_stash;
-        ctx.red = s_hw + (warp * 2) * K.hw_words;
-        ctx.ridx = lane;
-        ctx.g1 = s_g1; ctx.g2 = s_g2; ctx.key = s_key;
-        ctx.t = t; ctx.hw = hw;
-        uint32_t pp_count = 0;
-        ctx.pp_count = &pp_count;
-        Lane L;
-#pragma unroll 1
-        if (leader) s_claim[0][0] = atomicAdd(H.work, gw);
-        for (uint32_t it = 0;; ++it) {
-            if (leader) s_claim[0][(it + 1) % 3] = atomicAdd(H.work, gw);
-            asm volatile("bar.sync 1, %0;" ::"r"(gw * 32) : "memory");
-            const uint32_t base = s_claim[0][it % 3];
-            if (base >= K.n_items) break;
-            const uint32_t item = base + wg;
-            f64_prefetch_item(KF, s_claim[0][(it + 1) % 3] + wg, lane);
-            ctx.active = item < K.n_items;
-            ctx.item = ctx.active ? item : K.n_items - 1;
-            vm_run_static<SP>(K, &L, &ctx);
-        }
-    } else {
-        LaneCtxF ctx;
-        f64_ctx_init(ctx, s_f64, s_fbuf, (int)wg, lane);
-        LaneF L;
-#pragma unroll 1
-        if (leader) s_claim[1][0] = atomicAdd(H.work, gw);
-        for (uint32_t it = 0;; ++it) {
-            if (leader) s_claim[1][(it + 1) % 3] = atomicAdd(H.work, gw);
-            asm volatile("bar.sync 2, %0;" ::"r"(gw * 32) : "memory");
-            const uint32_t base = s_claim[1][it % 3];
-            if (base >= KF.n_items) break;
-            const uint32_t item = base + wg;
-            f64_prefetch_item(KF, s_claim[1][(it + 1) % 3] + wg, lane);
-            ctx.active = item < KF.n_items;
-            ctx.item = ctx.active ? item : KF.n_items - 1;
-            f64_commit_item(KF, &L, &ctx);
-        }
     }
 }
 
@@ -520,37 +354,36 @@ struct rzk_engine {
     uint32_t *d_g2tab = nullptr;
     uint32_t *d_keytab = nullptr;
     uint32_t *d_keytab2 = nullptr;  // split-key images (lo/hi) for prime slot 0, [6][2][576]
-    double *d_f64tab = nullptr;     // FP64 path: [g1 | g2 | key images] (rzk_f64.cuh)
-    uint32_t no_sparse = 0;         // RZK_NO_SPARSE=1: responses through the NTT program only (A/B timing)
     uint32_t *d_gstash[kPipe + 1] = {};   // residue stash of the three-prime programs, [SM][warp][half warp][kStashWordsMax]:
                                     // one per pipeline stream (their kernels may overlap) + one for the `_dev` entry points
     int32_t *d_partial[kPipe + 1] = {};   // segment results of product sums cut into segments (small batches), per stream as above
-    uint32_t no_segments = 0;       // RZK_NO_SEGMENTS=1: never cut a product sum into segments (A/B timing)
     uint32_t *d_need = nullptr;     // hand-over words of dev_respond for the `_dev` entry points
     size_t need_cap = 0;
-    uint32_t hyb_seq = 0;
-    uint32_t hyb_disable = 0;       // RZK_HYB_DISABLE (experiments)
-    uint32_t hyb_int_warps = 8;     // RZK_HYB_INT_WARPS: integer-path warps per CTA in the hybrid kernel (of 16)
-    uint32_t commit_mode = 0;       // RZK_COMMIT_MODE: 0 = integer split-key program with phase mixing (measured best, 145 M/s),
-                                    // 1 = FP64-pipe program (123 M/s), 2 = both pipes in one launch (hybrid, 142 M/s)
-    uint32_t mulsum2_pp = 2;        // RZK_MULSUM2_PP: phase mixing of the two-accumulator product-sum program (0 / 9 = off)
-    uint32_t commit_pp = 2;         // RZK_COMMIT_PP: phase mixing of the split-key commitment program (0 / 9 = off)
     uint32_t *d_misc = nullptr;     // [0] range word, [1] dummy flags word
     uint32_t *h_range = nullptr;    // pinned host copy of the range word (single-chunk calls)
     bool has_key = false;
+    bool generic_commit = false;    // b > kSplitKeyLimit: every commitment runs the two-prime program (exact for any int8 r)
     uint64_t sigma = 0, cbound = 0, vbound = 0;
     uint32_t small_lim = 0;
     PipeSlot pipe[kPipe];
     char *scratch = nullptr;        // scratch of the `_dev` entry points
     size_t scratch_cap = 0;
     uint64_t launches = 0;
-    uint32_t static_respond = 0;
-    uint32_t no_fuse = 0;           // RZK_NO_FUSE=1: the Sum prover's two product sums as two launches (A/B timing)
-    uint32_t no_dimg = 0;           // RZK_NO_DIMG=1: every verify item transforms its challenge itself (A/B timing)
-    uint32_t no_static = 0;         // RZK_NO_STATIC=1 forces the generic interpreter (debugging / A-B timing)
-    uint32_t pp_mode = 0;           // RZK_PP: phase mixing between CTA halves (rzk_vm_exec.cuh), static programs only
     uint32_t chunk_items = 8192;    // host pipeline: items per chunk (RZK_CHUNK_ITEMS)
-    uint32_t cta_sync = 8;          // lock-step barriers (rzk_vm_exec.cuh cta_lockstep): 8 = one per segment (measured best), 1 = per transform, 0 = off
+    // RZK_TEST_LOWERING: alternative lowerings of the same phases, for the differential tests (tools/soak.py) -- results are
+    // identical in every setting.  Comma-separated tokens:
+    uint32_t no_static = 0;         //   generic    the runtime-decoded interpreter instead of the compile-time programs
+    uint32_t no_sparse = 0;         //   nosparse   responses through the one-prime NTT program only (no rotation kernel)
+    uint32_t no_segments = 0;       //   nosegments never cut a small product sum into segments
+    uint32_t no_dimg = 0;           //   nodimg     every Sum verify item transforms its challenge itself
+    uint32_t no_fuse = 0;           //   nofuse     the Sum prover's two product sums as two launches
+    uint32_t no_rot = 0;            //   norot      Open verify multiplies c1*d in the NTT domain (no rotation sum)
+    // RZK_TUNE (developer A/B timing, "name=value,..."): the settings below are the measured best
+    uint32_t static_respond = 0;
+    uint32_t mulsum2_pp = 2;        //   mulsum2_pp phase mixing of the two-accumulator product-sum program (0 / 9 = off)
+    uint32_t commit_pp = 2;         //   commit_pp  phase mixing of the split-key commitment program (0 / 9 = off)
+    uint32_t pp_mode = 0;           //   pp         phase mixing between CTA halves for every static program
+    uint32_t cta_sync = 8;          //   cta_sync   lock-step barriers (rzk_vm_exec.cuh cta_lockstep): 8 = one per segment, 1 = per transform, 0 = off
 };
 
 namespace {
@@ -630,6 +463,7 @@ int launch_vm(rzk_engine *e, VmLaunch &K, cudaStream_t s, uint32_t pp_program = 
         K.gstash = e->d_gstash[si];
     }
     layout_hw(K, SPLIT);
+    if (!rot_layout_ok(K.ops, SPLIT)) return fail(e, RZK_ERR_INVALID, "OP_ROT needs a warp-per-item program without operand slot / second accumulator");
     if (K.stash_words > kStashWordsMax) return fail(e, RZK_ERR_INVALID, "program needs more residue stash than the engine provides");
     list_prefetch(K);
     K.cta_sync = K.item_mask ? 0u : e->cta_sync;      // masked launches skip items per warp: no CTA barriers
@@ -717,107 +551,51 @@ constexpr size_t kPolyBytes = (size_t)kN * sizeof(int32_t);
 
 // ---- phase lowering on device pointers (scratch supplied by the caller of these helpers) ----
 
-int launch_commit_f64(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r, int32_t *c, uint32_t *flags, uint32_t flag_div,
-                      cudaStream_t s)
-{
-    if (B == 0) return RZK_OK;
-    F64Launch K;
-    memset(&K, 0, sizeof(K));
-    K.x = x; K.r = r; K.c = c;
-    if (flags) { K.flags = flags; K.flag_div = flag_div; }
-    else { K.flags = e->d_misc + 1; K.flag_div = 0xFFFFFFFFu; }
-    K.g1 = e->d_f64tab; K.g2 = e->d_f64tab + kF64G1D; K.key = e->d_f64tab + kF64G1D + kF64G2D;
-    K.q = (double)e->P.q; K.qinv = 1.0 / (double)e->P.q; K.pinv = 1.0 / kF64P;
-    K.n_items = (uint32_t)B; K.small_lim = kF64SmallLimit;
-    K.pad_ = e->cta_sync ? 1u : 0u;      // lock-step barrier per item
-    int warps = kF64Warps;
-    const uint32_t want = (uint32_t)((B + (uint64_t)e->num_sms - 1) / (uint64_t)e->num_sms);
-    if ((uint32_t)warps > want) warps = (int)(want ? want : 1);
-    static std::atomic<bool> configured[16];   // per device; engines of a group run on separate threads
-    if (!configured[e->device & 15]) {
-        RZK_CUDA(e, cudaFuncSetAttribute(rzk_commit_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f64_smem_bytes(kF64Warps)));
-        configured[e->device & 15] = true;
-    }
-    uint32_t grid = (uint32_t)((B + warps - 1) / warps);
-    if (grid > (uint32_t)e->num_sms) grid = (uint32_t)e->num_sms;
-    rzk_commit_f64_kernel<<<grid, warps * 32, f64_smem_bytes(warps), s>>>(K);
-    RZK_CUDA(e, cudaGetLastError());
-    e->launches++;
-    return RZK_OK;
-}
-
-void fill_f64(rzk_engine *e, F64Launch &K, size_t B, const int32_t *x, const int8_t *r, int32_t *c, uint32_t *flags, uint32_t flag_div)
-{
-    memset(&K, 0, sizeof(K));
-    K.x = x; K.r = r; K.c = c;
-    if (flags) { K.flags = flags; K.flag_div = flag_div; }
-    else { K.flags = e->d_misc + 1; K.flag_div = 0xFFFFFFFFu; }
-    K.g1 = e->d_f64tab; K.g2 = e->d_f64tab + kF64G1D; K.key = e->d_f64tab + kF64G1D + kF64G2D;
-    K.q = (double)e->P.q; K.qinv = 1.0 / (double)e->P.q; K.pinv = 1.0 / kF64P;
-    K.n_items = (uint32_t)B; K.small_lim = kF64SmallLimit;
-    K.pad_ = e->cta_sync ? 1u : 0u;
-}
-
-// K: a filled launch of the split-key commit program (streams, constants, flags)
-int launch_commit_hybrid(rzk_engine *e, VmLaunch &K, size_t B, const int32_t *x, const int8_t *r, int32_t *c, uint32_t *flags,
-                         uint32_t flag_div, cudaStream_t s)
-{
-    using SP = SPCommitSplitKey;
-    auto kern = rzk_commit_hybrid_kernel<SP>;
-    layout_hw(K, true);
-    K.n_prefetch = 0;
-    K.cta_sync = 0;
-    K.pp_mode = 0;
-    F64Launch KF;
-    fill_f64(e, KF, B, x, r, c, flags, flag_div);
-    HybridLaunch H;
-    const int warps = 16;
-    H.int_warps = std::min<uint32_t>(std::max<uint32_t>(e->hyb_int_warps, 1), warps - 1);
-    // one counter per launch in flight on a stream: zeroed by a memset ordered before the kernel
-    H.work = e->d_misc + 2 + (e->hyb_seq++ & 7);
-    H.disable = e->hyb_disable;
-    RZK_CUDA(e, cudaMemsetAsync(H.work, 0, sizeof(uint32_t), s));
-    const size_t smem = sizeof(uint32_t) * (size_t)VmSmem<1, MODE_SPLITKEY>::kTables + sizeof(double) * kF64TabD +
-                        sizeof(uint32_t) * (size_t)H.int_warps * 2 * K.hw_words + sizeof(double) * (size_t)(warps - H.int_warps) * 2 * kF64BufD;
-    static std::atomic<bool> configured[16];   // per device; engines of a group run on separate threads
-    if (!configured[e->device & 15]) {
-        RZK_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));   // 16 B of static smem
-        configured[e->device & 15] = true;
-    }
-    uint32_t grid = (uint32_t)((B + 7) / 8);
-    if (grid > (uint32_t)e->num_sms) grid = (uint32_t)e->num_sms;
-    kern<<<grid, warps * 32, smem, s>>>(K, KF, H);
-    RZK_CUDA(e, cudaGetLastError());
-    e->launches++;
-    return RZK_OK;
-}
-
 constexpr uint32_t kSplitKeyLimit = 15;    // |r| bound of MODE_SPLITKEY: 2*512*2^15*15 < p/2
 
-// generic = true: two-prime program, exact for any int8 r.
-// generic = false: split-key program (|r| <= 15 on the transformed rows, else FLAG_RANGE).
+// c = [a1;a2].r + [0;x]  (commit.rs:88-128).
+// Default: the split-key program, exact for |r| <= 15 on the transformed rows.  An item outside that range is marked
+//   * in rmark[item / flag_div] (+ the any-word that follows the marks; rmark holds groups + 1 words) when the caller
+//     supplies rmark -- the host entry points do, and
+//     then redo exactly the marked item groups with the two-prime program in a second, masked launch on the same stream
+//     (it returns at once when nothing is marked), so they are exact for any int8 r without a host round trip;
+//   * else by FLAG_RANGE in its flags word (`_dev` entry points: documented in the header).
+// Engines created with b > 15 (generic_commit) always run the two-prime program, which is exact for any int8 r.
 int dev_commit(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r, int32_t *c, uint32_t *flags, cudaStream_t s,
-               bool generic = false, uint32_t flag_div = 1)
+               uint32_t *rmark = nullptr, uint32_t flag_div = 1)
 {
-    VmLaunch K; memset(&K, 0, sizeof(K));
+    uint32_t *rmark_any = rmark ? rmark + (B + flag_div - 1) / flag_div : nullptr;       // the any-word follows the marks
     // check_commit_constraint (params.rs:102-108) cannot fail for int8 rows when the bound is at least
     // 127*sqrt(N) (it is 1,359,072 at the default parameters): then the norm pass is skipped.
     const bool norm_vacuous = e->cbound >= 127ull * 23ull;
-    Prog p;
-    if (generic) prog_commit(p, 0, 1, 2, !norm_vacuous);
-    else prog_commit_splitkey(p, 0, 1, 2, !norm_vacuous);
-    p.end();
-    p.install(K);
-    fill_common(e, K, generic ? 2 : 1, (uint32_t)B, flag_div, flags);
-    set_stream(K, 0, x, 1, DT_I32); set_stream(K, 1, r, 3, DT_I8); set_stream(K, 2, c, 2, DT_I32);
-    if (generic) return launch_np(e, 2, K, s);
-    if (e->commit_mode == 1 && norm_vacuous) return launch_commit_f64(e, B, x, r, c, flags, flag_div, s);
-    K.small_lim = kSplitKeyLimit;
-    K.keytab = e->d_keytab2;
-    if (e->commit_mode == 2 && norm_vacuous && B >= 4096) return launch_commit_hybrid(e, K, B, x, r, c, flags, flag_div, s);
-    // measured best for this program: the two halves of the CTA alternate their multiply-heavy windows (rzk_vm_exec.cuh pp_*)
-    if (norm_vacuous) return launch_sp<SPCommitSplitKey>(e, K, s, e->commit_pp);
-    return launch_vm<1, MODE_SPLITKEY>(e, K, s);
+    auto launch = [&](bool generic, bool masked) -> int {
+        VmLaunch K; memset(&K, 0, sizeof(K));
+        Prog p;
+        if (generic) prog_commit(p, 0, 1, 2, !norm_vacuous);
+        else prog_commit_splitkey(p, 0, 1, 2, !norm_vacuous);
+        p.end();
+        p.install(K);
+        fill_common(e, K, generic ? 2 : 1, (uint32_t)B, flag_div, flags);
+        set_stream(K, 0, x, 1, DT_I32); set_stream(K, 1, r, 3, DT_I8); set_stream(K, 2, c, 2, DT_I32);
+        if (generic) {
+            if (masked) { K.item_mask = rmark; K.mask_div = flag_div; K.any_item = rmark_any; }
+            return launch_np(e, 2, K, s);
+        }
+        K.small_lim = kSplitKeyLimit;
+        K.keytab = e->d_keytab2;
+        K.rmark = rmark; K.rmark_any = rmark_any;
+        // measured best for this program: the two halves of the CTA alternate their multiply-heavy windows (rzk_vm_exec.cuh pp_*)
+        if (norm_vacuous) return launch_sp<SPCommitSplitKey>(e, K, s, e->commit_pp);
+        return launch_vm<1, MODE_SPLITKEY>(e, K, s);
+    };
+    if (B == 0) return RZK_OK;
+    if (e->generic_commit) return launch(true, false);
+    if (rmark) {
+        const size_t groups = (B + flag_div - 1) / flag_div;
+        RZK_CUDA(e, cudaMemsetAsync(rmark, 0, sizeof(uint32_t) * (groups + 1), s));
+    }
+    RZK_TRY(launch(false, false));
+    return rmark ? launch(true, true) : RZK_OK;
 }
 
 // t = A1.y (and optionally w = A2.y) for `items` masking vectors: two-prime program
@@ -837,9 +615,9 @@ int dev_keymatvec(rzk_engine *e, size_t items, const int32_t *y, int32_t *t, int
 
 // open.rs:80-103: the commitment (split-key program) and t = A1.y (two-prime program)
 int dev_open_commit(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r, const int32_t *y,
-                    int32_t *c, int32_t *t, uint32_t *flags, cudaStream_t s, bool generic = false)
+                    int32_t *c, int32_t *t, uint32_t *flags, cudaStream_t s, uint32_t *rmark = nullptr)
 {
-    RZK_TRY(dev_commit(e, B, x, r, c, flags, s, generic));
+    RZK_TRY(dev_commit(e, B, x, r, c, flags, s, rmark));
     return dev_keymatvec(e, B, y, t, nullptr, flags, 1, s);
 }
 
@@ -906,7 +684,8 @@ int dev_verify_first(rzk_engine *e, size_t items, const int32_t *z, const int32_
     VmLaunch K; memset(&K, 0, sizeof(K));
     Prog p;
     prog_norm_verify(p, 0);
-    prog_verify_first(p, 0, 1, 2, 3, w ? 4 : -1, (w && dimg) ? 5 : -1);
+    const bool rot = !w && !e->no_rot;       // Open verify: c1*d as signed rotations in the epilogue (OP_ROT)
+    prog_verify_first(p, 0, 1, 2, 3, w ? 4 : -1, (w && dimg) ? 5 : -1, rot);
     p.end();
     p.install(K);
     fill_common(e, K, 2, (uint32_t)items, flag_div, flags);
@@ -914,6 +693,7 @@ int dev_verify_first(rzk_engine *e, size_t items, const int32_t *z, const int32_
     set_stream(K, 3, d, 1, DT_I8, d_div);
     if (w) set_stream(K, 4, w, 1, DT_I32);
     if (w && dimg) { set_stream(K, 5, dimg, 2, DT_I32, d_div); return launch_sp<SPVerifyFirstWG>(e, K, s); }
+    if (rot) return launch_sp<SPVerifyFirstRot>(e, K, s);
     return w ? launch_sp<SPVerifyFirstW>(e, K, s) : launch_sp<SPVerifyFirst>(e, K, s);
 }
 
@@ -1011,23 +791,23 @@ int dev_mulsum2(rzk_engine *e, size_t B, uint32_t T, const int32_t *a, const int
 
 // commit(x; r) -> c  and  t = A1.y, w = A2.y  for `items` (x, r, y) triples
 int dev_commit_matvec(rzk_engine *e, size_t items, const int32_t *x, const int8_t *r, const int32_t *y,
-                      int32_t *c, int32_t *t, int32_t *w, uint32_t *flags, uint32_t flag_div, cudaStream_t s, bool generic = false)
+                      int32_t *c, int32_t *t, int32_t *w, uint32_t *flags, uint32_t flag_div, cudaStream_t s, uint32_t *rmark = nullptr)
 {
-    RZK_TRY(dev_commit(e, items, x, r, c, flags, s, generic, flag_div));
+    RZK_TRY(dev_commit(e, items, x, r, c, flags, s, rmark, flag_div));
     return dev_keymatvec(e, items, y, t, w, flags, flag_div, s);
 }
 
 // scratch: 2*B polys
 int dev_linear_commit(rzk_engine *e, size_t B, const int32_t *g, const int32_t *x, const int8_t *rp, const int8_t *r,
                       const int32_t *y, const int32_t *yp, int32_t *gx, int32_t *cp, int32_t *c, int32_t *t,
-                      int32_t *tp, int32_t *u, uint32_t *flags, int32_t *scratch, cudaStream_t s, bool generic = false)
+                      int32_t *tp, int32_t *u, uint32_t *flags, int32_t *scratch, cudaStream_t s, uint32_t *rmark = nullptr)
 {
     int32_t *w = scratch, *wp = scratch + B * kN;
     // One launch per product here.  Sharing the transform of g between g*x and u (prog_mulsum2, or a single-term program
     // that inverts one product after the other) was measured 5 % SLOWER for single terms.
     RZK_TRY(dev_mulsum(e, B, 1, g, x, nullptr, nullptr, gx, flags, s));                 // linear.rs:91-95
-    RZK_TRY(dev_commit_matvec(e, B, gx, rp, yp, cp, tp, wp, flags, 1, s, generic));     // linear.rs:96,121,129
-    RZK_TRY(dev_commit_matvec(e, B, x, r, y, c, t, w, flags, 1, s, generic));           // linear.rs:97,118,124-127
+    RZK_TRY(dev_commit_matvec(e, B, gx, rp, yp, cp, tp, wp, flags, 1, s, rmark));     // linear.rs:96,121,129
+    RZK_TRY(dev_commit_matvec(e, B, x, r, y, c, t, w, flags, 1, s, rmark));           // linear.rs:97,118,124-127
     return dev_mulsum(e, B, 1, g, w, wp, nullptr, u, flags, s);                         // linear.rs:124-129
 }
 
@@ -1046,21 +826,21 @@ int dev_linear_verify(rzk_engine *e, size_t B, const int32_t *z, const int32_t *
 // scratch: (B*T + B) polys
 int dev_sum_commit(rzk_engine *e, size_t B, uint32_t T, const int32_t *gs, const int32_t *xs, const int8_t *rp,
                    const int8_t *rs, const int32_t *ys, const int32_t *yp, int32_t *xp, int32_t *cp, int32_t *cs,
-                   int32_t *ts, int32_t *tp, int32_t *u, uint32_t *flags, int32_t *scratch, cudaStream_t s, bool generic = false)
+                   int32_t *ts, int32_t *tp, int32_t *u, uint32_t *flags, int32_t *scratch, cudaStream_t s, uint32_t *rmark = nullptr)
 {
     int32_t *ws = scratch, *wp = scratch + B * T * kN;
     if (e->no_fuse == 1 || T == 1 || mulsum_segments(e, B, T) > 1) {      // (small batches: each product sum is cut into segments)
         RZK_TRY(dev_mulsum(e, B, T, gs, xs, nullptr, nullptr, xp, flags, s));               // sum.rs:107-115
-        RZK_TRY(dev_commit_matvec(e, B, xp, rp, yp, cp, tp, wp, flags, 1, s, generic));     // sum.rs:116,151,160
-        RZK_TRY(dev_commit_matvec(e, B * T, xs, rs, ys, cs, ts, ws, flags, T, s, generic)); // sum.rs:117-120,145-148,157
+        RZK_TRY(dev_commit_matvec(e, B, xp, rp, yp, cp, tp, wp, flags, 1, s, rmark));     // sum.rs:116,151,160
+        RZK_TRY(dev_commit_matvec(e, B * T, xs, rs, ys, cs, ts, ws, flags, T, s, rmark)); // sum.rs:117-120,145-148,157
         return dev_mulsum(e, B, T, gs, ws, wp, nullptr, u, flags, s);                       // sum.rs:154-160
     }
     // same results in an order that lets every g_i be transformed once for both of its products: the masking products
     // first (they do not depend on x'), then x' = sum g_i x_i and u in one launch, then the commitment to x'
     RZK_TRY(dev_keymatvec(e, B, yp, tp, wp, flags, 1, s));                              // sum.rs:151,160
-    RZK_TRY(dev_commit_matvec(e, B * T, xs, rs, ys, cs, ts, ws, flags, T, s, generic)); // sum.rs:117-120,145-148,157
+    RZK_TRY(dev_commit_matvec(e, B * T, xs, rs, ys, cs, ts, ws, flags, T, s, rmark)); // sum.rs:117-120,145-148,157
     RZK_TRY(dev_mulsum2(e, B, T, gs, xs, ws, wp, xp, u, flags, s));                     // sum.rs:107-115,154-160
-    return dev_commit(e, B, xp, rp, cp, flags, s, generic);                             // sum.rs:116
+    return dev_commit(e, B, xp, rp, cp, flags, s, rmark);                               // sum.rs:116
 }
 
 int dev_sum_verify(rzk_engine *e, size_t B, uint32_t T, const int32_t *zs, const int32_t *zp, const int32_t *cs,
@@ -1085,14 +865,21 @@ struct HArr {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// fn(chunk_items, dptr[], scratch, flags, stream)
+constexpr size_t kArenaCap = (size_t)1 << 30;     // one pipeline slot never holds more than 1 GiB
+
+// fn(chunk_items, dptr[], scratch, flags, stream, rmark): rmark = (chunk + 1) words for dev_commit's masked redo
 template <class F>
 int run_chunked(rzk_engine *e, size_t B, std::vector<HArr> &arrs, size_t scratch_per_item, uint8_t *bitmap, F &&fn)
 {
     if (B == 0) return RZK_OK;
     Guard g(e->device);
-    size_t per_item = scratch_per_item + sizeof(uint32_t) + 1;
+    e->err.clear();
+    size_t per_item = scratch_per_item + 2 * sizeof(uint32_t) + 1;
     for (auto &a : arrs) per_item += a.per_item;
+    // (a Sum proof with tens of thousands of terms is hundreds of MB per instance: refuse instead of allocating four
+    // multi-GB arenas -- such an instance belongs to the `_dev` entry points with caller-owned buffers)
+    if (8 * per_item > kArenaCap)
+        return fail(e, RZK_ERR_INVALID, "one item group needs more than the host pipeline's 1 GiB arena: use the _dev entry points");
     size_t chunk = (size_t)(96ull << 20) / per_item;
     chunk = std::max<size_t>(8, std::min<size_t>(chunk, e->chunk_items)) / 8 * 8;
     if (chunk > B) chunk = align_up(B, 8);
@@ -1102,6 +889,7 @@ int run_chunked(rzk_engine *e, size_t B, std::vector<HArr> &arrs, size_t scratch
     for (size_t i = 0; i < arrs.size(); ++i) { offs[i] = off; off += align_up(arrs[i].per_item * chunk, 256); }
     const size_t off_scratch = off; off += align_up(scratch_per_item * chunk, 256);
     const size_t off_flags = off; off += align_up(sizeof(uint32_t) * chunk, 256);
+    const size_t off_rmark = off; off += align_up(sizeof(uint32_t) * (chunk + 1), 256);
     const size_t off_bitmap = off; off += align_up(chunk / 8 + 1, 256);
     const size_t need = off;
     for (int i = 0; i < kPipe; ++i) {
@@ -1120,32 +908,42 @@ int run_chunked(rzk_engine *e, size_t B, std::vector<HArr> &arrs, size_t scratch
     RZK_CUDA(e, cudaMemsetAsync(e->d_misc, 0, sizeof(uint32_t), e->pipe[0].stream));
     if (nchunks > 1) RZK_CUDA(e, cudaStreamSynchronize(e->pipe[0].stream));
     std::vector<void *> dptr(arrs.size());
-    int ci = 0;
-    for (size_t c0 = 0; c0 < B; c0 += chunk, ++ci) {
-        const size_t n = std::min(chunk, B - c0);
-        PipeSlot &ps = e->pipe[ci % kPipe];
-        cudaStream_t s = ps.stream;
-        for (size_t i = 0; i < arrs.size(); ++i) {
-            dptr[i] = ps.arena + offs[i];
-            if (arrs[i].in)
-                RZK_CUDA(e, cudaMemcpyAsync(dptr[i], (const char *)arrs[i].in + c0 * arrs[i].per_item,
-                                            n * arrs[i].per_item, cudaMemcpyHostToDevice, s));
+    // a failure in any chunk must not return while other streams still copy into the caller's buffers or run kernels on
+    // the arenas: every stream is drained first
+    auto body = [&]() -> int {
+        int ci = 0;
+        for (size_t c0 = 0; c0 < B; c0 += chunk, ++ci) {
+            const size_t n = std::min(chunk, B - c0);
+            PipeSlot &ps = e->pipe[ci % kPipe];
+            cudaStream_t s = ps.stream;
+            for (size_t i = 0; i < arrs.size(); ++i) {
+                dptr[i] = ps.arena + offs[i];
+                if (arrs[i].in)
+                    RZK_CUDA(e, cudaMemcpyAsync(dptr[i], (const char *)arrs[i].in + c0 * arrs[i].per_item,
+                                                n * arrs[i].per_item, cudaMemcpyHostToDevice, s));
+            }
+            uint32_t *dflags = reinterpret_cast<uint32_t *>(ps.arena + off_flags);
+            RZK_CUDA(e, cudaMemsetAsync(dflags, 0, sizeof(uint32_t) * n, s));
+            RZK_TRY(fn(n, dptr.data(), ps.arena + off_scratch, dflags, s, reinterpret_cast<uint32_t *>(ps.arena + off_rmark)));
+            if (bitmap) {
+                uint8_t *dbm = reinterpret_cast<uint8_t *>(ps.arena + off_bitmap);
+                const size_t nbytes = (n + 7) / 8;
+                rzk_flags_to_bitmap_kernel<<<(unsigned)((nbytes + 127) / 128), 128, 0, s>>>(n, dflags, dbm, e->d_misc);
+                RZK_CUDA(e, cudaGetLastError());
+                e->launches++;
+                RZK_CUDA(e, cudaMemcpyAsync(bitmap + c0 / 8, dbm, nbytes, cudaMemcpyDeviceToHost, s));
+            }
+            for (size_t i = 0; i < arrs.size(); ++i)
+                if (arrs[i].out)
+                    RZK_CUDA(e, cudaMemcpyAsync((char *)arrs[i].out + c0 * arrs[i].per_item, dptr[i],
+                                                n * arrs[i].per_item, cudaMemcpyDeviceToHost, s));
         }
-        uint32_t *dflags = reinterpret_cast<uint32_t *>(ps.arena + off_flags);
-        RZK_CUDA(e, cudaMemsetAsync(dflags, 0, sizeof(uint32_t) * n, s));
-        RZK_TRY(fn(n, dptr.data(), ps.arena + off_scratch, dflags, s));
-        if (bitmap) {
-            uint8_t *dbm = reinterpret_cast<uint8_t *>(ps.arena + off_bitmap);
-            const size_t nbytes = (n + 7) / 8;
-            rzk_flags_to_bitmap_kernel<<<(unsigned)((nbytes + 127) / 128), 128, 0, s>>>(n, dflags, dbm, e->d_misc);
-            RZK_CUDA(e, cudaGetLastError());
-            e->launches++;
-            RZK_CUDA(e, cudaMemcpyAsync(bitmap + c0 / 8, dbm, nbytes, cudaMemcpyDeviceToHost, s));
-        }
-        for (size_t i = 0; i < arrs.size(); ++i)
-            if (arrs[i].out)
-                RZK_CUDA(e, cudaMemcpyAsync((char *)arrs[i].out + c0 * arrs[i].per_item, dptr[i],
-                                            n * arrs[i].per_item, cudaMemcpyDeviceToHost, s));
+        return RZK_OK;
+    };
+    const int rc = body();
+    if (rc != RZK_OK) {
+        for (int i = 0; i < kPipe; ++i) cudaStreamSynchronize(e->pipe[i].stream);
+        return rc;
     }
     uint32_t range = 0;
     if (nchunks == 1) {
@@ -1153,7 +951,12 @@ int run_chunked(rzk_engine *e, size_t B, std::vector<HArr> &arrs, size_t scratch
         RZK_CUDA(e, cudaStreamSynchronize(e->pipe[0].stream));
         range = *e->h_range;
     } else {
-        for (int i = 0; i < kPipe; ++i) RZK_CUDA(e, cudaStreamSynchronize(e->pipe[i].stream));
+        cudaError_t first = cudaSuccess;
+        for (int i = 0; i < kPipe; ++i) {
+            const cudaError_t ce = cudaStreamSynchronize(e->pipe[i].stream);
+            if (ce != cudaSuccess && first == cudaSuccess) first = ce;
+        }
+        RZK_CUDA(e, first);
         RZK_CUDA(e, cudaMemcpy(&range, e->d_misc, sizeof(uint32_t), cudaMemcpyDeviceToHost));
     }
     if (range & FLAG_RANGE)
@@ -1198,6 +1001,30 @@ int rzk_create(const rzk_params *params, int device, rzk_engine **out)
         return fail(nullptr, RZK_ERR_UNSUPPORTED, "only N=512, (n,k,l)=(1,3,1) is accelerated");
     if (P.q != 3515337053LL || P.b < 1 || P.b > 127 || P.kappa < 1)
         return fail(nullptr, RZK_ERR_UNSUPPORTED, "only q=3515337053 with 1 <= b <= 127 is accelerated");
+    // params.rs:94-98, 104, 114
+    const uint64_t sigma = (uint64_t)P.b * (uint64_t)(11 * (int64_t)P.kappa) * isqrt64((uint64_t)P.k * (uint64_t)P.N);
+    const uint64_t cbound = 4 * sigma * isqrt64((uint64_t)P.N), vbound = 2 * sigma * isqrt64((uint64_t)P.N);
+    uint32_t small_lim = 0;
+    {
+        // Exactness of the two-prime products (small x large), from the actual bounds of this parameter set:
+        static const int slots[2] = {0, 1};
+        const CrtC c = make_crt_consts(slots, 2, (uint64_t)P.q);
+        const uint64_t half = (uint64_t)(P.q - 1) / 2, room = c.P01half - (1ull << 33);
+        // (a) prover: |y| <= small_lim keeps y0 + a11*y1 + a12*y2 inside the centred CRT range; the masking vectors are
+        //     N(0, sigma) samples, so the limit must sit far in the tail (10 sigma: < 2^-75 per coefficient) or honest
+        //     batches would be rejected with RZK_ERR_RANGE
+        small_lim = (uint32_t)std::min<uint64_t>(room / ((uint64_t)(P.k - P.n) * (uint64_t)P.N * half), 0x7fffffffu);
+        if ((uint64_t)small_lim < 10 * sigma)
+            return fail(nullptr, RZK_ERR_UNSUPPORTED, "b*kappa too large: masking vectors N(0, sigma) would leave the exact range of "
+                                                        "the two-prime products (needs rzk_small_limit() >= 10 sigma, i.e. b*kappa <= 74)");
+        // (b) verifier: a response that passes check_verify_constraint has ||z_i||_1 <= sqrt(N) * vbound, so
+        //     |a1j * z_j| <= half * sqrt(N) * vbound per coefficient; c*d with any int8 d and any int32 c adds < 2^47
+        const uint64_t sqrtN_up = isqrt64((uint64_t)P.N) + 1;
+        const unsigned __int128 worst = (unsigned __int128)(P.k - P.n) * half * sqrtN_up * vbound + ((unsigned __int128)1 << 47) + (1ull << 34);
+        if (worst > (unsigned __int128)room)
+            return fail(nullptr, RZK_ERR_UNSUPPORTED, "b*kappa too large: A1.z of a response at the norm bound would leave the exact "
+                                                        "range of the two-prime products");
+    }
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
     if (ce != cudaSuccess || ndev == 0)
@@ -1207,36 +1034,39 @@ int rzk_create(const rzk_params *params, int device, rzk_engine **out)
     rzk_engine *e = new rzk_engine();
     e->P = P;
     e->device = device;
-    if (const char *cs = getenv("RZK_CTA_SYNC")) e->cta_sync = (uint32_t)atoi(cs);
-    if (const char *cs = getenv("RZK_NO_STATIC")) e->no_static = (uint32_t)atoi(cs);
-    if (const char *cs = getenv("RZK_NO_DIMG")) e->no_dimg = (uint32_t)atoi(cs);
-    if (const char *cs = getenv("RZK_NO_FUSE")) e->no_fuse = (uint32_t)atoi(cs);
-    if (const char *cs = getenv("RZK_NO_SEGMENTS")) e->no_segments = (uint32_t)atoi(cs) ? 1u : 0u;
-    if (const char *cs = getenv("RZK_COMMIT_MODE")) e->commit_mode = (uint32_t)atoi(cs);
-    if (const char *cs = getenv("RZK_NO_SPARSE")) e->no_sparse = (uint32_t)atoi(cs);
-    if (const char *cs = getenv("RZK_HYB_DISABLE")) e->hyb_disable = (uint32_t)atoi(cs);
-    if (const char *cs = getenv("RZK_HYB_INT_WARPS")) e->hyb_int_warps = (uint32_t)atoi(cs);
-    if (const char *cs = getenv("RZK_PP")) e->pp_mode = (uint32_t)atoi(cs);
-    if (const char *cs = getenv("RZK_COMMIT_PP")) e->commit_pp = (uint32_t)atoi(cs);
-    if (const char *cs = getenv("RZK_MULSUM2_PP")) e->mulsum2_pp = (uint32_t)atoi(cs);
+    e->sigma = sigma; e->cbound = cbound; e->vbound = vbound; e->small_lim = small_lim;
+    e->generic_commit = (uint64_t)P.b > kSplitKeyLimit;
     if (const char *cs = getenv("RZK_CHUNK_ITEMS")) e->chunk_items = (uint32_t)std::max(8, atoi(cs));
+    auto has_token = [](const char *list, const char *tok) {
+        const size_t n = strlen(tok);
+        for (const char *p = list; p && *p;) {
+            const char *q = strchr(p, ',');
+            const size_t len = q ? (size_t)(q - p) : strlen(p);
+            if (len == n && strncmp(p, tok, n) == 0) return true;
+            p = q ? q + 1 : nullptr;
+        }
+        return false;
+    };
+    if (const char *tl = getenv("RZK_TEST_LOWERING")) {
+        e->no_static = has_token(tl, "generic"); e->no_sparse = has_token(tl, "nosparse");
+        e->no_segments = has_token(tl, "nosegments"); e->no_dimg = has_token(tl, "nodimg");
+        e->no_fuse = has_token(tl, "nofuse"); e->no_rot = has_token(tl, "norot");
+    }
+    if (const char *tu = getenv("RZK_TUNE")) {
+        auto val = [&](const char *name, uint32_t &dst) {
+            const std::string key = std::string(name) + "=";
+            const char *p = strstr(tu, key.c_str());
+            if (p && (p == tu || p[-1] == ',')) dst = (uint32_t)atoi(p + key.size());
+        };
+        val("cta_sync", e->cta_sync); val("pp", e->pp_mode); val("commit_pp", e->commit_pp);
+        val("mulsum2_pp", e->mulsum2_pp); val("static_respond", e->static_respond);
+    }
     Guard g(device);
     cudaDeviceProp prop;
     ce = cudaGetDeviceProperties(&prop, device);
     if (ce != cudaSuccess) { delete e; return fail(nullptr, RZK_ERR_CUDA, cudaGetErrorString(ce)); }
     if (prop.major < 10) { delete e; return fail(nullptr, RZK_ERR_CUDA, "an sm_100a (Blackwell) device is required"); }
     e->num_sms = prop.multiProcessorCount;
-    // params.rs:94-98, 104, 114
-    e->sigma = (uint64_t)P.b * (uint64_t)(11 * P.kappa) * isqrt64((uint64_t)P.k * (uint64_t)P.N);
-    e->cbound = 4 * e->sigma * isqrt64((uint64_t)P.N);
-    e->vbound = 2 * e->sigma * isqrt64((uint64_t)P.N);
-    {
-        // |y| bound keeping  y0 + a11*y1 + a12*y2  inside the centred range of the two-prime CRT
-        static const int slots[2] = {0, 1};
-        CrtC c = make_crt_consts(slots, 2, (uint64_t)P.q);
-        const uint64_t half = (uint64_t)(P.q - 1) / 2;
-        e->small_lim = (uint32_t)((c.P01half - (1ull << 33)) / ((uint64_t)(P.k - P.n) * (uint64_t)P.N * half));
-    }
     // static tables
     std::vector<uint32_t> g1((size_t)kNumPrimeSlots * 2 * kG1Words, 0), g2((size_t)kNumPrimeSlots * 2 * kLanes * kG2Words);
     for (int s = 0; s < kNumPrimeSlots; ++s) {
@@ -1254,14 +1084,6 @@ int rzk_create(const rzk_params *params, int device, rzk_engine **out)
     if (rc == RZK_OK) cu(cudaMemcpy(e->d_g2tab, g2.data(), g2.size() * sizeof(uint32_t), cudaMemcpyHostToDevice), "cudaMemcpy(g2)");
     cu(cudaMalloc(&e->d_keytab, (size_t)kNumPrimeSlots * kKeyPolys * 2 * kPadWords * sizeof(uint32_t)), "cudaMalloc(key)");
     cu(cudaMalloc(&e->d_keytab2, (size_t)2 * kKeyPolys * 2 * kPadWords * sizeof(uint32_t)), "cudaMalloc(key2)");
-    cu(cudaMalloc(&e->d_f64tab, sizeof(double) * kF64TabD), "cudaMalloc(f64tab)");
-    if (rc == RZK_OK) {
-        const F64Tables &FT = f64_tables();
-        std::vector<double> tab(kF64G1D + kF64G2D);
-        memcpy(tab.data(), FT.g1, sizeof(FT.g1));
-        memcpy(tab.data() + kF64G1D, FT.g2, sizeof(FT.g2));
-        cu(cudaMemcpy(e->d_f64tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice), "cudaMemcpy(f64tab)");
-    }
     cu(cudaMalloc(&e->d_misc, 64), "cudaMalloc(misc)");
     cu(cudaMallocHost(&e->h_range, 64), "cudaMallocHost(range)");
     if (rc == RZK_OK) cu(cudaMemset(e->d_misc, 0, 64), "cudaMemset(misc)");
@@ -1285,7 +1107,6 @@ void rzk_destroy(rzk_engine *e)
     if (e->d_g2tab) cudaFree(e->d_g2tab);
     if (e->d_keytab) cudaFree(e->d_keytab);
     if (e->d_keytab2) cudaFree(e->d_keytab2);
-    if (e->d_f64tab) cudaFree(e->d_f64tab);
     if (e->d_need) cudaFree(e->d_need);
     for (auto p : e->d_gstash) if (p) cudaFree(p);
     for (auto p : e->d_partial) if (p) cudaFree(p);
@@ -1333,18 +1154,7 @@ int rzk_set_key(rzk_engine *e, const int64_t *a1, const int64_t *a2)
         }
         key_image_split(prime_tables(0), cen.data(), &img2[(size_t)kk * 4 * kPadWords]);
     }
-    std::vector<double> img64((size_t)kF64KeyD);
-    for (int kk = 0; kk < kKeyPolys; ++kk) {
-        for (int i = 0; i < kN; ++i) {
-            int64_t r = polys[kk][i] % q;
-            if (r > half) r -= q; else if (r < -half) r += q;
-            cen[i] = r;
-        }
-        f64_key_image(cen.data(), &img64[(size_t)kk * kN * 2]);
-    }
-    f64_key_image(nullptr, &img64[(size_t)kKeyPolys * kN * 2]);
     RZK_CUDA(e, cudaDeviceSynchronize());
-    RZK_CUDA(e, cudaMemcpy(e->d_f64tab + kF64G1D + kF64G2D, img64.data(), img64.size() * sizeof(double), cudaMemcpyHostToDevice));
     RZK_CUDA(e, cudaMemcpy(e->d_keytab, img.data(), img.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     RZK_CUDA(e, cudaMemcpy(e->d_keytab2, img2.data(), img2.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     e->has_key = true;
@@ -1546,13 +1356,9 @@ int rzk_commit_batch(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r,
     RZK_TRY(check_ready(e));
     if (any_null({x, r, c, ok})) return fail(e, RZK_ERR_INVALID, "null argument");
     std::vector<HArr> a = {{x, nullptr, kPolyBytes}, {r, nullptr, 3 * kN}, {nullptr, c, 2 * kPolyBytes}};
-    int rc = run_chunked(e, B, a, 0, ok, [&](size_t n, void **d, char *, uint32_t *fl, cudaStream_t s) {
-        return dev_commit(e, n, (const int32_t *)d[0], (const int8_t *)d[1], (int32_t *)d[2], fl, s);
-    });
-    if (rc != RZK_ERR_RANGE) return rc;
-    // some |r| > 15: redo the batch with the two-prime program, which is exact for any int8 r
-    return run_chunked(e, B, a, 0, ok, [&](size_t n, void **d, char *, uint32_t *fl, cudaStream_t s) {
-        return dev_commit(e, n, (const int32_t *)d[0], (const int8_t *)d[1], (int32_t *)d[2], fl, s, true);
+    // items with some |r| > 15 are redone by the two-prime program inside dev_commit (masked launch, same stream)
+    return run_chunked(e, B, a, 0, ok, [&](size_t n, void **d, char *, uint32_t *fl, cudaStream_t s, uint32_t *rm) {
+        return dev_commit(e, n, (const int32_t *)d[0], (const int8_t *)d[1], (int32_t *)d[2], fl, s, rm);
     });
 }
 
@@ -1563,15 +1369,9 @@ int rzk_open_commit_batch(rzk_engine *e, size_t B, const int32_t *x, const int8_
     if (any_null({x, r, y, c, t, ok})) return fail(e, RZK_ERR_INVALID, "null argument");
     std::vector<HArr> a = {{x, nullptr, kPolyBytes}, {r, nullptr, 3 * kN}, {y, nullptr, 3 * kPolyBytes},
                            {nullptr, c, 2 * kPolyBytes}, {nullptr, t, kPolyBytes}};
-    int rc = run_chunked(e, B, a, 0, ok, [&](size_t n, void **d, char *, uint32_t *fl, cudaStream_t s) {
+    return run_chunked(e, B, a, 0, ok, [&](size_t n, void **d, char *, uint32_t *fl, cudaStream_t s, uint32_t *rm) {
         return dev_open_commit(e, n, (const int32_t *)d[0], (const int8_t *)d[1], (const int32_t *)d[2],
-                               (int32_t *)d[3], (int32_t *)d[4], fl, s);
-    });
-    if (rc != RZK_ERR_RANGE) return rc;
-    // some |r| > 15 (or y out of range): redo with the two-prime commitment program, exact for any int8 r
-    return run_chunked(e, B, a, 0, ok, [&](size_t n, void **d, char *, uint32_t *fl, cudaStream_t s) {
-        return dev_open_commit(e, n, (const int32_t *)d[0], (const int8_t *)d[1], (const int32_t *)d[2],
-                               (int32_t *)d[3], (int32_t *)d[4], fl, s, true);
+                               (int32_t *)d[3], (int32_t *)d[4], fl, s, rm);
     });
 }
 
@@ -1580,7 +1380,7 @@ int rzk_open_respond_batch(rzk_engine *e, size_t B, const int32_t *y, const int8
     RZK_TRY(check_ready(e));
     if (any_null({y, r, dch, z})) return fail(e, RZK_ERR_INVALID, "null argument");
     std::vector<HArr> a = {{y, nullptr, 3 * kPolyBytes}, {r, nullptr, 3 * kN}, {dch, nullptr, kN}, {nullptr, z, 3 * kPolyBytes}};
-    return run_chunked(e, B, a, 2 * sizeof(uint32_t), nullptr, [&](size_t n, void **d, char *sc, uint32_t *, cudaStream_t s) {
+    return run_chunked(e, B, a, 2 * sizeof(uint32_t), nullptr, [&](size_t n, void **d, char *sc, uint32_t *, cudaStream_t s, uint32_t *) {
         return dev_respond(e, n, (const int32_t *)d[0], (const int8_t *)d[1], (const int8_t *)d[2], 1, (int32_t *)d[3], (uint32_t *)sc, s);
     });
 }
@@ -1591,7 +1391,7 @@ int rzk_commitment_verify_batch(rzk_engine *e, size_t B, const int32_t *c, const
     if (any_null({c, x, r, bm})) return fail(e, RZK_ERR_INVALID, "null argument");
     std::vector<HArr> a = {{c, nullptr, 2 * kPolyBytes}, {x, nullptr, kPolyBytes}, {r, nullptr, 3 * kN}};
     if (f) a.push_back({f, nullptr, kN});
-    return run_chunked(e, B, a, 0, bm, [&](size_t n, void **d, char *, uint32_t *fl, cudaStream_t s) {
+    return run_chunked(e, B, a, 0, bm, [&](size_t n, void **d, char *, uint32_t *fl, cudaStream_t s, uint32_t *rm) {
         return dev_commitment_verify(e, n, (const int32_t *)d[0], (const int32_t *)d[1], (const int8_t *)d[2],
                                      f ? (const int8_t *)d[3] : nullptr, fl, s);
     });
@@ -1602,7 +1402,7 @@ int rzk_open_verify_batch(rzk_engine *e, size_t B, const int32_t *z, const int32
     RZK_TRY(check_ready(e));
     if (any_null({z, t, c1, dch, bm})) return fail(e, RZK_ERR_INVALID, "null argument");
     std::vector<HArr> a = {{z, nullptr, 3 * kPolyBytes}, {t, nullptr, kPolyBytes}, {c1, nullptr, kPolyBytes}, {dch, nullptr, kN}};
-    return run_chunked(e, B, a, 0, bm, [&](size_t n, void **d, char *, uint32_t *fl, cudaStream_t s) {
+    return run_chunked(e, B, a, 0, bm, [&](size_t n, void **d, char *, uint32_t *fl, cudaStream_t s, uint32_t *rm) {
         return dev_verify_first(e, n, (const int32_t *)d[0], (const int32_t *)d[1], (const int32_t *)d[2], 1,
                                 (const int8_t *)d[3], 1, nullptr, fl, 1, s);
     });
@@ -1618,17 +1418,10 @@ int rzk_linear_commit_batch(rzk_engine *e, size_t B, const int32_t *g, const int
                            {y, nullptr, 3 * kPolyBytes}, {yp, nullptr, 3 * kPolyBytes},
                            {nullptr, gx, kPolyBytes}, {nullptr, cp, 2 * kPolyBytes}, {nullptr, c, 2 * kPolyBytes},
                            {nullptr, t, kPolyBytes}, {nullptr, tp, kPolyBytes}, {nullptr, u, kPolyBytes}};
-    int rc = run_chunked(e, B, a, 2 * kPolyBytes, ok, [&](size_t n, void **d, char *sc, uint32_t *fl, cudaStream_t s) {
+    return run_chunked(e, B, a, 2 * kPolyBytes, ok, [&](size_t n, void **d, char *sc, uint32_t *fl, cudaStream_t s, uint32_t *rm) {
         return dev_linear_commit(e, n, (const int32_t *)d[0], (const int32_t *)d[1], (const int8_t *)d[2], (const int8_t *)d[3],
                                  (const int32_t *)d[4], (const int32_t *)d[5], (int32_t *)d[6], (int32_t *)d[7], (int32_t *)d[8],
-                                 (int32_t *)d[9], (int32_t *)d[10], (int32_t *)d[11], fl, (int32_t *)sc, s);
-    });
-    if (rc != RZK_ERR_RANGE) return rc;
-    // some |r| > 15 (or y out of range): redo with the two-prime commitment program, exact for any int8 r
-    return run_chunked(e, B, a, 2 * kPolyBytes, ok, [&](size_t n, void **d, char *sc, uint32_t *fl, cudaStream_t s) {
-        return dev_linear_commit(e, n, (const int32_t *)d[0], (const int32_t *)d[1], (const int8_t *)d[2], (const int8_t *)d[3],
-                                 (const int32_t *)d[4], (const int32_t *)d[5], (int32_t *)d[6], (int32_t *)d[7], (int32_t *)d[8],
-                                 (int32_t *)d[9], (int32_t *)d[10], (int32_t *)d[11], fl, (int32_t *)sc, s, true);
+                                 (int32_t *)d[9], (int32_t *)d[10], (int32_t *)d[11], fl, (int32_t *)sc, s, rm);
     });
 }
 
@@ -1639,7 +1432,7 @@ int rzk_linear_respond_batch(rzk_engine *e, size_t B, const int32_t *y, const in
     if (any_null({y, yp, r, rp, dch, z, zp})) return fail(e, RZK_ERR_INVALID, "null argument");
     std::vector<HArr> a = {{y, nullptr, 3 * kPolyBytes}, {yp, nullptr, 3 * kPolyBytes}, {r, nullptr, 3 * kN}, {rp, nullptr, 3 * kN},
                            {dch, nullptr, kN}, {nullptr, z, 3 * kPolyBytes}, {nullptr, zp, 3 * kPolyBytes}};
-    return run_chunked(e, B, a, 4 * sizeof(uint32_t), nullptr, [&](size_t n, void **d, char *sc, uint32_t *, cudaStream_t s) {
+    return run_chunked(e, B, a, 4 * sizeof(uint32_t), nullptr, [&](size_t n, void **d, char *sc, uint32_t *, cudaStream_t s, uint32_t *) {
         uint32_t *need = (uint32_t *)sc;
         RZK_TRY(dev_respond(e, n, (const int32_t *)d[0], (const int8_t *)d[2], (const int8_t *)d[4], 1, (int32_t *)d[5], need, s));
         return dev_respond(e, n, (const int32_t *)d[1], (const int8_t *)d[3], (const int8_t *)d[4], 1, (int32_t *)d[6], need + n + 1, s);
@@ -1654,7 +1447,7 @@ int rzk_linear_verify_batch(rzk_engine *e, size_t B, const int32_t *z, const int
     std::vector<HArr> a = {{z, nullptr, 3 * kPolyBytes}, {zp, nullptr, 3 * kPolyBytes}, {c, nullptr, 2 * kPolyBytes},
                            {cp, nullptr, 2 * kPolyBytes}, {g, nullptr, kPolyBytes}, {t, nullptr, kPolyBytes},
                            {tp, nullptr, kPolyBytes}, {u, nullptr, kPolyBytes}, {dch, nullptr, kN}};
-    return run_chunked(e, B, a, 2 * kPolyBytes, bm, [&](size_t n, void **d, char *sc, uint32_t *fl, cudaStream_t s) {
+    return run_chunked(e, B, a, 2 * kPolyBytes, bm, [&](size_t n, void **d, char *sc, uint32_t *fl, cudaStream_t s, uint32_t *rm) {
         return dev_linear_verify(e, n, (const int32_t *)d[0], (const int32_t *)d[1], (const int32_t *)d[2], (const int32_t *)d[3],
                                  (const int32_t *)d[4], (const int32_t *)d[5], (const int32_t *)d[6], (const int32_t *)d[7],
                                  (const int8_t *)d[8], fl, (int32_t *)sc, s);
@@ -1672,17 +1465,10 @@ int rzk_sum_commit_batch(rzk_engine *e, size_t B, uint32_t T, const int32_t *gs,
                            {rs, nullptr, (size_t)T * 3 * kN}, {ys, nullptr, T * 3 * kPolyBytes}, {yp, nullptr, 3 * kPolyBytes},
                            {nullptr, xp, kPolyBytes}, {nullptr, cp, 2 * kPolyBytes}, {nullptr, cs, T * 2 * kPolyBytes},
                            {nullptr, ts, T * kPolyBytes}, {nullptr, tp, kPolyBytes}, {nullptr, u, kPolyBytes}};
-    int rc = run_chunked(e, B, a, (T + 1) * kPolyBytes, ok, [&](size_t n, void **d, char *sc, uint32_t *fl, cudaStream_t s) {
+    return run_chunked(e, B, a, (T + 1) * kPolyBytes, ok, [&](size_t n, void **d, char *sc, uint32_t *fl, cudaStream_t s, uint32_t *rm) {
         return dev_sum_commit(e, n, T, (const int32_t *)d[0], (const int32_t *)d[1], (const int8_t *)d[2], (const int8_t *)d[3],
                               (const int32_t *)d[4], (const int32_t *)d[5], (int32_t *)d[6], (int32_t *)d[7], (int32_t *)d[8],
-                              (int32_t *)d[9], (int32_t *)d[10], (int32_t *)d[11], fl, (int32_t *)sc, s);
-    });
-    if (rc != RZK_ERR_RANGE) return rc;
-    // some |r| > 15 (or y out of range): redo with the two-prime commitment program, exact for any int8 r
-    return run_chunked(e, B, a, (T + 1) * kPolyBytes, ok, [&](size_t n, void **d, char *sc, uint32_t *fl, cudaStream_t s) {
-        return dev_sum_commit(e, n, T, (const int32_t *)d[0], (const int32_t *)d[1], (const int8_t *)d[2], (const int8_t *)d[3],
-                              (const int32_t *)d[4], (const int32_t *)d[5], (int32_t *)d[6], (int32_t *)d[7], (int32_t *)d[8],
-                              (int32_t *)d[9], (int32_t *)d[10], (int32_t *)d[11], fl, (int32_t *)sc, s, true);
+                              (int32_t *)d[9], (int32_t *)d[10], (int32_t *)d[11], fl, (int32_t *)sc, s, rm);
     });
 }
 
@@ -1694,7 +1480,7 @@ int rzk_sum_respond_batch(rzk_engine *e, size_t B, uint32_t T, const int32_t *ys
     if (any_null({ys, yp, rs, rp, dch, zs, zp})) return fail(e, RZK_ERR_INVALID, "null argument");
     std::vector<HArr> a = {{ys, nullptr, T * 3 * kPolyBytes}, {yp, nullptr, 3 * kPolyBytes}, {rs, nullptr, (size_t)T * 3 * kN},
                            {rp, nullptr, 3 * kN}, {dch, nullptr, kN}, {nullptr, zs, T * 3 * kPolyBytes}, {nullptr, zp, 3 * kPolyBytes}};
-    return run_chunked(e, B, a, ((size_t)T + 3) * sizeof(uint32_t), nullptr, [&](size_t n, void **d, char *sc, uint32_t *, cudaStream_t s) {
+    return run_chunked(e, B, a, ((size_t)T + 3) * sizeof(uint32_t), nullptr, [&](size_t n, void **d, char *sc, uint32_t *, cudaStream_t s, uint32_t *) {
         uint32_t *need = (uint32_t *)sc;
         RZK_TRY(dev_respond(e, n * T, (const int32_t *)d[0], (const int8_t *)d[2], (const int8_t *)d[4], T, (int32_t *)d[5], need, s));
         return dev_respond(e, n, (const int32_t *)d[1], (const int8_t *)d[3], (const int8_t *)d[4], 1, (int32_t *)d[6], need + n * T + 1, s);
@@ -1711,7 +1497,7 @@ int rzk_sum_verify_batch(rzk_engine *e, size_t B, uint32_t T, const int32_t *zs,
     std::vector<HArr> a = {{zs, nullptr, T * 3 * kPolyBytes}, {zp, nullptr, 3 * kPolyBytes}, {cs, nullptr, T * 2 * kPolyBytes},
                            {cp, nullptr, 2 * kPolyBytes}, {gs, nullptr, T * kPolyBytes}, {ts, nullptr, T * kPolyBytes},
                            {tp, nullptr, kPolyBytes}, {u, nullptr, kPolyBytes}, {dch, nullptr, kN}};
-    return run_chunked(e, B, a, (T + 3) * kPolyBytes, bm, [&](size_t n, void **d, char *sc, uint32_t *fl, cudaStream_t s) {
+    return run_chunked(e, B, a, (T + 3) * kPolyBytes, bm, [&](size_t n, void **d, char *sc, uint32_t *fl, cudaStream_t s, uint32_t *rm) {
         return dev_sum_verify(e, n, T, (const int32_t *)d[0], (const int32_t *)d[1], (const int32_t *)d[2], (const int32_t *)d[3],
                               (const int32_t *)d[4], (const int32_t *)d[5], (const int32_t *)d[6], (const int32_t *)d[7],
                               (const int8_t *)d[8], fl, (int32_t *)sc, s);
@@ -1729,7 +1515,7 @@ int rzk_pack_i64(rzk_engine *e, size_t count, const int64_t *src, int32_t *dst)
     std::vector<HArr> a = {{src, nullptr, kN * sizeof(int64_t)}, {nullptr, dst, kN * sizeof(int32_t)}};
     // whole polynomials per "item"; a ragged tail is handled by a final short call
     size_t whole = count / kN;
-    int rc = run_chunked(e, whole, a, 0, nullptr, [&](size_t n, void **d, char *, uint32_t *, cudaStream_t s) {
+    int rc = run_chunked(e, whole, a, 0, nullptr, [&](size_t n, void **d, char *, uint32_t *, cudaStream_t s, uint32_t *) {
         rzk_pack_i64_kernel<<<e->num_sms * 4, 256, 0, s>>>(n * kN, (const int64_t *)d[0], (int32_t *)d[1], q);
         e->launches++;
         return cudaGetLastError() == cudaSuccess ? RZK_OK : RZK_ERR_CUDA;
@@ -1751,7 +1537,7 @@ int rzk_unpack_i64(rzk_engine *e, size_t count, const int32_t *src, int64_t *dst
     if (any_null({src, dst})) return fail(e, RZK_ERR_INVALID, "null argument");
     std::vector<HArr> a = {{src, nullptr, kN * sizeof(int32_t)}, {nullptr, dst, kN * sizeof(int64_t)}};
     size_t whole = count / kN;
-    int rc = run_chunked(e, whole, a, 0, nullptr, [&](size_t n, void **d, char *, uint32_t *, cudaStream_t s) {
+    int rc = run_chunked(e, whole, a, 0, nullptr, [&](size_t n, void **d, char *, uint32_t *, cudaStream_t s, uint32_t *) {
         rzk_unpack_i64_kernel<<<e->num_sms * 4, 256, 0, s>>>(n * kN, (const int32_t *)d[0], (int64_t *)d[1]);
         e->launches++;
         return cudaGetLastError() == cudaSuccess ? RZK_OK : RZK_ERR_CUDA;

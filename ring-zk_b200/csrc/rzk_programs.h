@@ -112,9 +112,23 @@ constexpr inline void prog_keymatvec(Prog &P, int sv, int st, int sw, bool check
 // With sdh >= 0 the NTT image of d comes from stream sdh (written by prog_challenge_image for the group the item
 // belongs to) instead of being transformed per item: the T terms of a Sum proof and the two first equations of a
 // Linear proof share one challenge.
-constexpr inline void prog_verify_first(Prog &P, int sz, int st, int sc, int sd, int sw, int sdh = -1)
+// rot = true (sw < 0 only): c1*d is not multiplied in the NTT domain but added in the epilogue as signed rotations of the row
+// c1 (OP_ROT, SURVEY kernel K4): two transforms per item (z1, z2) instead of four (d, z1, z2, c1).
+constexpr inline void prog_verify_first(Prog &P, int sz, int st, int sc, int sd, int sw, int sdh = -1, bool rot = false)
 {
     P.add(OP_SEG);
+    if (rot && sw < 0) {
+        P.add(OP_FWD, sz, 0, 0, 1);
+        P.add(OP_MACK, 0, 0, MAC_INIT);
+        P.add(OP_FWD, sz, 0, 0, 2);
+        P.add(OP_MACK, 0, 1, 0);
+        P.add(OP_INV, 0, 0);
+        P.add(OP_ADDP, sz, 0, 0, 0);
+        P.add(OP_ADDP, st, 0, MAC_NEG, 0);
+        P.add(OP_ROT, sc, sd, MAC_NEG, 0);
+        P.add(OP_FIN, 0, FIN_CMPZ, 0, 0);
+        return;
+    }
     if (sdh < 0) {
         P.add(OP_FWD, sd, FWD_SCALED, 0, 0);
         P.add(OP_ST);
@@ -308,6 +322,12 @@ struct SPKeyMatVecTW {           // streams: 0 = y, 1 = t out, 2 = w out
 struct SPVerifyFirst {           // streams: 0 = z, 1 = t, 2 = c, 3 = d (i8)
     static constexpr int kNP = 2, kMode = 1;
     static constexpr Prog prog = [] { Prog p; prog_norm_verify(p, 0); prog_verify_first(p, 0, 1, 2, 3, -1); p.end(); return p; }();
+    static constexpr uint8_t dtype[kMaxStreams] = {DT_I32, DT_I32, DT_I32, DT_I8};
+};
+
+struct SPVerifyFirstRot {        // streams: 0 = z, 1 = t, 2 = c, 3 = d (i8); c1*d as signed rotations (OP_ROT)
+    static constexpr int kNP = 2, kMode = 1;
+    static constexpr Prog prog = [] { Prog p; prog_norm_verify(p, 0); prog_verify_first(p, 0, 1, 2, 3, -1, -1, true); p.end(); return p; }();
     static constexpr uint8_t dtype[kMaxStreams] = {DT_I32, DT_I32, DT_I32, DT_I8};
 };
 

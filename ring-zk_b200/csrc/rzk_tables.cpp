@@ -192,88 +192,6 @@ void key_image(const PrimeTables &T, const int64_t *poly, uint32_t *out)
     }
 }
 
-// ---------------------------------------------------------------- FP64 path tables
-
-static const int64_t kP64 = 70368744137729LL;      // rzk_f64.cuh kF64Prime
-
-static int64_t mulmod64(int64_t a, int64_t b) { return (int64_t)((__int128)a * b % kP64); }
-static int64_t powmod64(int64_t b, uint64_t e)
-{
-    int64_t r = 1, x = b % kP64;
-    while (e) {
-        if (e & 1) r = mulmod64(r, x);
-        x = mulmod64(x, x);
-        e >>= 1;
-    }
-    return r;
-}
-static int64_t centre64(int64_t v) { return v > (kP64 - 1) / 2 ? v - kP64 : v; }
-
-const F64Tables &f64_tables()
-{
-    static F64Tables T;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        memset(&T, 0, sizeof(T));
-        int64_t psi = 0;
-        for (int64_t x = 2; x < 1000; ++x) {
-            int64_t g = powmod64(x, (uint64_t)(kP64 - 1) / (2 * kN));
-            if (powmod64(g, kN) == kP64 - 1) { psi = g; break; }
-        }
-        if (!psi) throw std::runtime_error("no 2N-th root of unity mod the FP64 prime");
-        T.psi = psi;
-        T.psi_inv = powmod64(psi, (uint64_t)kP64 - 2);
-        T.ninv = powmod64(kN, (uint64_t)kP64 - 2);
-        for (int idx = 0; idx < kN; ++idx) {
-            T.tw[0][idx] = centre64(powmod64(psi, (uint64_t)brv9(idx)));
-            T.tw[1][idx] = centre64(powmod64(T.psi_inv, (uint64_t)brv9(idx)));
-        }
-        auto pair = [](int64_t w, double *o) { o[0] = (double)w; o[1] = (double)w / (double)kP64; };
-        for (int d = 0; d < 2; ++d) {
-            for (int idx = 0; idx < 32; ++idx) pair(T.tw[d][idx], T.g1[d][idx]);
-            for (int t = 0; t < kLanes; ++t) {
-                int w = 0;
-                for (int s = 5; s <= 8; ++s) {
-                    const int cnt = 1 << (s - 4);
-                    for (int a = 0; a < cnt; ++a) pair(T.tw[d][(1 << s) + cnt * t + a], T.g2[d][t][w++]);
-                }
-            }
-        }
-    });
-    return T;
-}
-
-void f64_key_image(const int64_t *poly, double *out)
-{
-    const F64Tables &T = f64_tables();
-    int64_t a[kN];
-    for (int i = 0; i < kN; ++i) {
-        int64_t v = poly ? poly[i] % kP64 : 0;
-        if (v < 0) v += kP64;
-        a[i] = v;
-    }
-    int t = kN;
-    for (int m = 1; m < kN; m <<= 1) {           // same butterfly order as ntt_forward_ref
-        t >>= 1;
-        for (int i = 0; i < m; ++i) {
-            int64_t S = T.tw[0][m + i];
-            if (S < 0) S += kP64;
-            const int j1 = 2 * i * t;
-            for (int j = j1; j < j1 + t; ++j) {
-                const int64_t U = a[j], V = mulmod64(a[j + t], S);
-                a[j] = (U + V) % kP64;
-                a[j + t] = (U + kP64 - V) % kP64;
-            }
-        }
-    }
-    for (int i = 0; i < kN; ++i) {
-        const int64_t k = centre64(mulmod64(a[i], T.ninv));
-        const int tl = i >> 5, e = i & 31;
-        out[(e * kLanes + tl) * 2 + 0] = (double)k;
-        out[(e * kLanes + tl) * 2 + 1] = (double)k / (double)kP64;
-    }
-}
-
 void key_image_split(const PrimeTables &T, const int64_t *poly, uint32_t *out)
 {
     int64_t lo[kN], hi[kN];

@@ -36,18 +36,6 @@ void key_image(const PrimeTables &T, const int64_t *poly_centered, uint32_t *out
 // lo to out[0 .. 2*kPadWords) and of hi to out[2*kPadWords .. 4*kPadWords).
 void key_image_split(const PrimeTables &T, const int64_t *poly_centered, uint32_t *out);
 
-// ---- FP64 path (rzk_f64.cuh): one 46-bit prime, twiddles as (w, w/p) pairs of doubles, w centred ----
-struct F64Tables {
-    double g1[2][32][2];                   // [dir][twiddle index][w, w/p]   (indices 1..31 used)
-    double g2[2][kLanes][31][2];           // [dir][lane][stage 5: 2, 6: 4, 7: 8, 8: 16, pad][w, w/p]
-    int64_t tw[2][kN];                     // full centred tables (key setup, reference transform)
-    int64_t psi, psi_inv, ninv;
-};
-const F64Tables &f64_tables();
-// N^-1 * NTT_p(poly) as (k, k/p) pairs, k centred, in the lane-private order read by f64_commit_item:
-// out[(e * 16 + t) * 2 + {0, 1}] for transform position 32 t + e.  poly == nullptr writes the zero image.
-void f64_key_image(const int64_t *poly_centered, double *out);
-
 inline int pad_index(int i) { return i + ((i >> 5) << 2); }
 
 }  // namespace rzk

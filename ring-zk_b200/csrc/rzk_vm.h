@@ -30,6 +30,9 @@ constexpr int kG1Words = 66;       // lane-uniform twiddle words per (prime, dir
                                    // (66 = 2 mod 32: the two half warps of a SPLIT warp hit different banks)
 constexpr int kKeyPolys = 3;       // non-trivial key polynomials a1'[0], a1'[1], a2'[0] at (n,k,l)=(1,3,1)
 constexpr int kMaxOps = 56;
+constexpr int kRotHwWords = 1296;  // half-warp region of a program with OP_ROT: the warp's two regions (2592 words) hold the
+                                   // extended row E = [-c | +c] as 1024 doubles and the (position, value) list of d (512 words)
+constexpr int kRotListOff = 2048;  // word offset of the list in the warp region
 constexpr int kMaxStreams = 12;
 
 enum OpCode : uint8_t {
@@ -49,6 +52,9 @@ enum OpCode : uint8_t {
     OP_STG,      // NTT image out: stream a [group][prime][512 words, lane-private order] = cur reduced to [0,p)
                  // (the Montgomery operand a later launch consumes with OP_MACG; cur comes from a FWD_SCALED transform)
     OP_MACG,     // acc[a] (+)= image stream b (.) cur (Montgomery), the image read from global memory     c: MAC_* flags
+    OP_ROT,      // (epilogue, warp-per-item modes) V += +-(stream a poly off) * (sparse int8 polynomial of stream b) as signed
+                 // rotations of the int32 row: sum_k d[pos_k] * X^pos_k * c, no multiplication by a transform (SURVEY kernel K4);
+                 // c: MAC_NEG.  Exact for any int8 d and any int32 c (512 * 127 * 2^31 < 2^53, summed in binary64).
 };
 
 enum : uint8_t { FWD_SCALED = 1, FWD_CHECK_SMALL = 2, FWD_HWPOLY = 4 };   // HWPOLY: half warp h reads poly off + h
@@ -135,8 +141,12 @@ struct VmLaunch {
     uint8_t prefetch[8];
     uint32_t cta_sync;         // keep the warps of a CTA in step (instruction-cache locality)
     uint32_t loop_count;       // trip count of OP_LOOP in compile-time programs (terms of a Sum proof - 1)
-    const uint32_t *item_mask; // optional: only items with item_mask[item] != 0 are processed (fallback launches)
+    const uint32_t *item_mask; // optional: only items with item_mask[item / mask_div] != 0 are processed (fallback launches)
     const uint32_t *any_item;  // optional: the whole launch returns at once when *any_item == 0
+    uint32_t mask_div;         // item groups per mask word (0 is read as 1)
+    uint32_t pad_mask_;
+    uint32_t *rmark;           // optional: a range error (FWD_CHECK_SMALL) marks rmark[item / flag_div] = 1 and *rmark_any = 1
+    uint32_t *rmark_any;       // instead of setting FLAG_RANGE -- the hand-over to a masked fallback launch (dev_commit)
     uint32_t pp_mode;          // phase mixing between the two halves of a CTA (rzk_vm_exec.cuh pp_acquire); 0 = off
     uint32_t alias_slot;       // the operand slot may overlay the transpose buffer (programs whose OP_LDs all
                                // precede the inverse transforms and that never use OP_MACV)
@@ -147,7 +157,7 @@ struct VmLaunch {
 
 // What a program needs per half warp (decides how many warps fit in shared memory).
 struct ProgNeeds {
-    bool slot = false, acc1 = false;
+    bool slot = false, acc1 = false, rot = false;
     int nstash = 0;
 };
 
@@ -159,6 +169,7 @@ inline ProgNeeds scan_needs(const Op *ops)
         if (o.code == OP_ST || o.code == OP_MACV || o.code == OP_LD) n.slot = true;
         if ((o.code == OP_MACK || o.code == OP_MACV || o.code == OP_MACG || o.code == OP_INV) && o.a == 1) n.acc1 = true;
         if (o.code == OP_INV && (int)o.b + 1 > n.nstash) n.nstash = (int)o.b + 1;
+        if (o.code == OP_ROT) n.rot = true;
     }
     return n;
 }
@@ -170,7 +181,8 @@ inline void list_prefetch(VmLaunch &K)
     for (int i = 0; i < kMaxOps && K.ops[i].code != OP_END; ++i) {
         const Op &o = K.ops[i];
         if (o.code == OP_FIN && (o.b & FIN_STORE)) is_out[o.a] = true;
-        if (o.code == OP_FWD || o.code == OP_ADDP || o.code == OP_NORM) is_in[o.a] = true;
+        if (o.code == OP_FWD || o.code == OP_ADDP || o.code == OP_NORM || o.code == OP_ROT) is_in[o.a] = true;
+        if (o.code == OP_ROT) is_in[o.b] = true;
     }
     K.n_prefetch = 0;
     for (int s = 0; s < kMaxStreams && K.n_prefetch < 8; ++s)
@@ -187,7 +199,17 @@ inline void layout_hw(VmLaunch &K, bool split)
     K.off_acc1 = w;  if (n.acc1) w += kSlotWords;
     K.stash_words = (!split && K.np > 1) ? (uint32_t)n.nstash * (K.np - 1) * kSlotWords : 0u;
     K.off_stash = w; if (!K.gstash) w += K.stash_words;
+    // OP_ROT overlays the whole warp region (transpose buffers included: they are dead in the epilogue); programs that keep
+    // an operand slot or a second accumulator in the region cannot use it (rot_layout_ok)
+    if (n.rot && w < (uint32_t)kRotHwWords) w = kRotHwWords;
     K.hw_words = w;
+}
+
+// OP_ROT needs the warp region to itself during the epilogue: warp-per-item programs without slot / second accumulator.
+inline bool rot_layout_ok(const Op *ops, bool split)
+{
+    const ProgNeeds n = scan_needs(ops);
+    return !n.rot || (split && !n.slot && !n.acc1);
 }
 
 // Host-side twiddle tables for one prime (built in rzk_tables.cpp).

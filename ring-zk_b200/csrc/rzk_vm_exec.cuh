@@ -520,6 +520,122 @@ RZK_VM void op_fin(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, typename
     }
 }
 
+// OP_ROT -- SURVEY kernel K4 for full-size rows: V += +-(c * d) where d is a sparse small polynomial (the challenge:
+// kappa entries +-1, challenge_space.rs:12-33) and c an int32 row (a commitment row), as in `c1.componentwise_mul(&d)`
+// of the verification equations (open.rs:172, linear.rs:226,232, sum.rs:287,295).  c * d = sum_k d[pos_k] * X^pos_k * c, and
+// X^pos * c is c rotated by pos with the wrapped part negated: the warp writes the extended row E = [-c | +c] to shared
+// memory as doubles (index 512 + i - pos reads the rotated, sign-corrected coefficient), lists the non-zero entries of
+// d, and every lane adds its 16 epilogue coefficients of every term with one LDS.64 + one DFMA -- on the FP64 pipe, which
+// the integer transforms leave idle -- instead of two forward transforms and a pointwise product per prime.
+// Any int8 d and any int32 representative of c are exact: |sum| <= 512 * 127 * 2^31 < 2^53.  Warp-per-item modes only.
+RZK_VM uint4 rot_ld128(const void *p)
+{
+#if defined(__CUDA_ARCH__)
+    return __ldg(reinterpret_cast<const uint4 *>(p));
+#else
+    return *reinterpret_cast<const uint4 *>(p);
+#endif
+}
+
+RZK_VM void rot_ld_pair(const int32_t *p, int32_t &a, int32_t &b)      // 8-byte aligned pair
+{
+#if defined(__CUDA_ARCH__)
+    const int2 v = __ldg(reinterpret_cast<const int2 *>(p));
+    a = v.x; b = v.y;
+#else
+    a = p[0]; b = p[1];
+#endif
+}
+
+RZK_VM void rot_st_pair(double *p, double a, double b)                  // 16-byte aligned pair
+{
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<double2 *>(p) = make_double2(a, b);
+#else
+    p[0] = a; p[1] = b;
+#endif
+}
+
+template <int MODE>
+RZK_VM void op_rot(const VmLaunch &K, const LaneCtx *ctxs, typename Epi<MODE>::V_t (&V)[RZK_NL][Epi<MODE>::kCount], const Op &op, int it)
+{
+    if constexpr (MODE != MODE_SEQ) {
+        const Stream sc = K.st[op.a], sd = K.st[op.b];
+        RZK_SYNC();          // the transpose buffers this overlays are no longer read
+        // ---- E = [-c | +c] as doubles: lane l converts the coefficient pairs 2l + 64e, e = 0..7 (8-byte loads, 16-byte stores)
+        RZK_EACH_LANE {
+            const LaneCtx &ctx = ctxs[li_];
+            double *E = reinterpret_cast<double *>(ctx.red);
+            const uint64_t poly = stream_poly(sc, ctx.item, (uint32_t)op.off + (uint32_t)it * op.step);
+            const int32_t *src = reinterpret_cast<const int32_t *>(sc.base) + poly * kN + 2 * ctx.ridx;
+            RZK_UNROLL
+            for (int e = 0; e < 8; ++e) {
+                int32_t v0, v1;
+                rot_ld_pair(src + 64 * e, v0, v1);
+                const double d0 = f64_exact_i32(v0), d1 = f64_exact_i32(v1);
+                rot_st_pair(E + 512 + 2 * ctx.ridx + 64 * e, d0, d1);
+                rot_st_pair(E + 2 * ctx.ridx + 64 * e, -d0, -d1);
+            }
+        }
+        // ---- (position, value) list of the non-zero entries of d: lane l scans the 16 bytes d[16l .. 16l+16)
+        uint32_t dw[RZK_NL][4], cnt_l[RZK_NL], pre_l[RZK_NL];
+        RZK_EACH_LANE {
+            const LaneCtx &ctx = ctxs[li_];
+            const uint64_t poly = stream_poly(sd, ctx.item, 0u);
+            const uint4 q = rot_ld128(reinterpret_cast<const int8_t *>(sd.base) + poly * kN + 16 * ctx.ridx);
+            dw[li_][0] = q.x; dw[li_][1] = q.y; dw[li_][2] = q.z; dw[li_][3] = q.w;
+            uint32_t cnt = 0;
+            RZK_UNROLL
+            for (int c = 0; c < 4; ++c) {
+                const uint32_t nz = (((dw[li_][c] & 0x7f7f7f7fu) + 0x7f7f7f7fu) | dw[li_][c]) & 0x80808080u;   // bit 7: byte != 0
+#if defined(__CUDA_ARCH__)
+                cnt += (uint32_t)__popc(nz);
+#else
+                cnt += (uint32_t)__builtin_popcount(nz);
+#endif
+            }
+            cnt_l[li_] = cnt;
+        }
+        uint32_t nnz = 0;
+#if defined(__CUDA_ARCH__)
+        {
+            uint32_t v = cnt_l[0];
+            RZK_UNROLL
+            for (int s = 1; s < 32; s <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, v, s); if (ctxs[0].ridx >= s) v += o; }
+            pre_l[0] = v - cnt_l[0];
+            nnz = __shfl_sync(0xffffffffu, v, 31);
+        }
+#else
+        for (int li = 0; li < RZK_NL; ++li) { pre_l[li] = nnz; nnz += cnt_l[li]; }
+#endif
+        RZK_EACH_LANE {
+            const LaneCtx &ctx = ctxs[li_];
+            uint32_t *list = ctx.red + kRotListOff;
+            uint32_t idx = pre_l[li_];
+            RZK_UNROLL
+            for (int b = 0; b < 16; ++b) {
+                const uint32_t byte = (dw[li_][b >> 2] >> (8 * (b & 3))) & 0xffu;
+                if (byte != 0) { list[idx] = (uint32_t)(16 * ctx.ridx + b) | (byte << 16); ++idx; }
+            }
+        }
+        RZK_SYNC();
+        // ---- V[j] += +-d[pos] * E[512 - pos + i_j], i_j = t + 256 hw + 16 j (the epilogue coefficients of this lane)
+        const double sgn = (op.c & MAC_NEG) ? -1.0 : 1.0;
+        RZK_NOUNROLL
+        for (uint32_t k = 0; k < nnz; ++k) {
+            RZK_EACH_LANE {
+                const LaneCtx &ctx = ctxs[li_];
+                const uint32_t e = (ctx.red + kRotListOff)[k];
+                const double s = sgn * f64_exact_i32((int32_t)(int8_t)(e >> 16));
+                const double *row = reinterpret_cast<const double *>(ctx.red) + (512u - (e & 511u)) + (uint32_t)(ctx.t + 256 * ctx.hw);
+                RZK_UNROLL
+                for (int j = 0; j < Epi<MODE>::kCount; ++j) V[li_][j] = f64_exact_fma(s, row[16 * j], V[li_][j]);
+            }
+        }
+        RZK_SYNC();          // the region is free again (next item's transposes)
+    }
+}
+
 // Garner recombination of the residues of one coefficient into a signed 64-bit value
 // congruent to the exact integer result modulo q (exact integer itself for np <= 2).
 template <int NP>
@@ -814,6 +930,7 @@ RZK_VM int op_inv(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int q, in
         for (;; ++q) {
             const Op e = K.ops[q];
             if (e.code == OP_ADDP) { if (last) op_addp<MODE>(K, ctxs, V, e, it, K.st[e.a].dtype); }
+            else if (e.code == OP_ROT) { if (last) op_rot<MODE>(K, ctxs, V, e, it); }
             else if (e.code == OP_FIN) { if (last) op_fin<MODE>(K, lanes, ctxs, V, e, it); }
             else break;
         }
@@ -902,6 +1019,35 @@ RZK_VM void op_norm(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const O
 }
 
 // ---------------------------------------------------------------- interpreter
+
+// Folds the status words of the lanes that own an item into the item group's flag word.  A range error goes to the
+// launch's mark array instead when there is one (K.rmark: the masked fallback launch of dev_commit redoes the group).
+template <int RED_N>
+RZK_VM void fold_flags(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs)
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t f = lanes[0].fail | (lanes[0].rerr << 1);
+    RZK_UNROLL
+    for (int d = RED_N / 2; d >= 1; d >>= 1) f |= __shfl_xor_sync(0xffffffffu, f, d);
+    if (ctxs[0].ridx == 0 && ctxs[0].active && f) {
+        const uint32_t grp = ctxs[0].item / K.flag_div;
+        if ((f & FLAG_RANGE) && K.rmark) { atomicOr(&K.rmark[grp], 1u); atomicOr(K.rmark_any, 1u); f &= ~(uint32_t)FLAG_RANGE; }
+        if (f) atomicOr(&K.flags[grp], f);
+    }
+#else
+    RZK_EACH_LANE { RZK_LANE; ctx.red[ctx.ridx] = L.fail | (L.rerr << 1); }
+    RZK_EACH_LANE {
+        RZK_LANE;
+        if (ctx.ridx == 0 && ctx.active) {
+            uint32_t f = 0;
+            for (int j = 0; j < RED_N; ++j) f |= ctx.red[j];
+            const uint32_t grp = ctx.item / K.flag_div;
+            if ((f & FLAG_RANGE) && K.rmark) { K.rmark[grp] |= 1u; *K.rmark_any |= 1u; f &= ~(uint32_t)FLAG_RANGE; }
+            if (f) K.flags[grp] |= f;
+        }
+    }
+#endif
+}
 
 // Runs the whole program for the item(s) owned by this warp.
 template <int NP, int MODE>
@@ -999,25 +1145,7 @@ RZK_VM void vm_run_item(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs)
         }
         pc = seg_end;
     }
-    // fold the owning lanes' status words into the item-group flag word
-#if defined(__CUDA_ARCH__)
-    {
-        uint32_t f = lanes[0].fail | (lanes[0].rerr << 1);
-        RZK_UNROLL
-        for (int d = RED_N / 2; d >= 1; d >>= 1) f |= __shfl_xor_sync(0xffffffffu, f, d);
-        if (ctxs[0].ridx == 0 && ctxs[0].active && f) atomicOr(&K.flags[ctxs[0].item / K.flag_div], f);
-    }
-#else
-    RZK_EACH_LANE { RZK_LANE; ctx.red[ctx.ridx] = L.fail | (L.rerr << 1); }
-    RZK_EACH_LANE {
-        RZK_LANE;
-        if (ctx.ridx == 0 && ctx.active) {
-            uint32_t f = 0;
-            for (int j = 0; j < RED_N; ++j) f |= ctx.red[j];
-            if (f) K.flags[ctx.item / K.flag_div] |= f;
-        }
-    }
-#endif
+    fold_flags<RED_N>(K, lanes, ctxs);
 }
 
 // ---------------------------------------------------------------- compile-time programs
@@ -1061,6 +1189,9 @@ RZK_VM void sp_epilogue(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, typ
         constexpr uint32_t dt = SP::dtype[e.a];
         op_addp<MODE>(K, ctxs, V, e, it, dt);
         sp_epilogue<SP, MODE, PC + 1>(K, lanes, ctxs, V, it);
+    } else if constexpr (e.code == OP_ROT) {
+        op_rot<MODE>(K, ctxs, V, e, it);
+        sp_epilogue<SP, MODE, PC + 1>(K, lanes, ctxs, V, it);
     } else if constexpr (e.code == OP_FIN) {
         op_fin<MODE>(K, lanes, ctxs, V, e, it);
         sp_epilogue<SP, MODE, PC + 1>(K, lanes, ctxs, V, it);
@@ -1069,7 +1200,7 @@ RZK_VM void sp_epilogue(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, typ
 
 constexpr int sp_skip_epilogue(const Prog &p, int pc)
 {
-    while (p.ops[pc].code == OP_ADDP || p.ops[pc].code == OP_FIN) ++pc;
+    while (p.ops[pc].code == OP_ADDP || p.ops[pc].code == OP_FIN || p.ops[pc].code == OP_ROT) ++pc;
     return pc;
 }
 
@@ -1197,24 +1328,7 @@ RZK_VM void vm_run_static(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs)
     RZK_EACH_LANE { RZK_LANE; L.fail = 0; L.rerr = 0; }
     sp_norms<SP, NP, MODE, 0>(K, lanes, ctxs);
     sp_segments<SP, NP, MODE, sp_first_seg(SP::prog)>(K, lanes, ctxs);
-#if defined(__CUDA_ARCH__)
-    {
-        uint32_t f = lanes[0].fail | (lanes[0].rerr << 1);
-        RZK_UNROLL
-        for (int d = RED_N / 2; d >= 1; d >>= 1) f |= __shfl_xor_sync(0xffffffffu, f, d);
-        if (ctxs[0].ridx == 0 && ctxs[0].active && f) atomicOr(&K.flags[ctxs[0].item / K.flag_div], f);
-    }
-#else
-    RZK_EACH_LANE { RZK_LANE; ctx.red[ctx.ridx] = L.fail | (L.rerr << 1); }
-    RZK_EACH_LANE {
-        RZK_LANE;
-        if (ctx.ridx == 0 && ctx.active) {
-            uint32_t f = 0;
-            for (int j = 0; j < RED_N; ++j) f |= ctx.red[j];
-            if (f) K.flags[ctx.item / K.flag_div] |= f;
-        }
-    }
-#endif
+    fold_flags<RED_N>(K, lanes, ctxs);
 }
 
 }  // namespace rzk

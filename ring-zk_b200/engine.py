@@ -25,7 +25,7 @@ _ERRNAMES = {1: "RZK_ERR_INVALID", 2: "RZK_ERR_UNSUPPORTED", 3: "RZK_ERR_CUDA", 
 
 SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("rzk_engine.cu", "rzk_tables.cpp")]
 HEADERS = [os.path.join(_HERE, "csrc", f) for f in
-           ("rzk_arith.cuh", "rzk_vm.h", "rzk_vm_exec.cuh", "rzk_programs.h", "rzk_tables.h", "rzk_f64.cuh", "rzk_sparse.cuh", "rzk_sample.cuh")] + \
+           ("rzk_arith.cuh", "rzk_vm.h", "rzk_vm_exec.cuh", "rzk_programs.h", "rzk_tables.h", "rzk_sparse.cuh", "rzk_sample.cuh")] + \
           [os.path.join(_ROOT, "include", "ringzk_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
               "-Xcompiler", "-fPIC", "--shared"]

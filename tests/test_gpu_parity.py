@@ -242,10 +242,10 @@ def test_i64_staging(setup):
 
 
 def test_full_size_properties(setup):
-    """BASELINE configs 2 and 3 at full size (2^16): size-independent properties.
+    """BASELINE configs 2 and 3 at full size (2^16): EVERY item bit-exact against the oracle (commitment c, t = A1.y,
+    response z, verify verdicts of a batch with a tampered subset), plus the size-independent properties
     - linearity of the commitment: com(x1; r1) + com(x2; r2) == com(x1 + x2; r1 + r2)  (mod q)
-    - honest Open transcripts verify; a tampered subset does not
-    - a random sample of items is bit-exact against the oracle."""
+    - honest Open transcripts verify; a tampered subset does not."""
     eng, o, s = setup
     B = 1 << 16
     x1, x2 = s.message(B), s.message(B)
@@ -256,40 +256,39 @@ def test_full_size_properties(setup):
     c12, _ = eng.commit(x12, (r1 + r2).astype(np.int8))
     assert (o.center(c1.astype(np.int64) + c2) == c12).all()
     assert UB(ok1, B).all() and UB(ok2, B).all()
-    idx = np.random.default_rng(1).choice(B, 48, replace=False)
-    c_o, _ = o.commit_batch(x1[idx], r1[idx])
-    assert (c1[idx] == c_o).all()
     y, d = s.gaussian(B), s.challenge(B)
     c, t, _ = eng.open_commit(x1, r1, y)
     assert (c == c1).all()
+    c_o, t_o, ok_o = o.open_commit_batch(x1, r1, y)          # the whole batch, every coefficient
+    assert (c == c_o).all() and (t == t_o).all() and ok_o.all()
     z = eng.open_respond(y, r1, d)
+    assert (z == o.open_respond_batch(y, r1, d)).all()
     cc1 = np.ascontiguousarray(c[:, :1])
     assert UB(eng.open_verify(z, t, cc1, d), B).all()
     z[::1000, 1, 77] ^= 1
-    v = UB(eng.open_verify(z, t, cc1, d), B)
-    assert not v[::1000].any() and v.sum() == B - len(range(0, B, 1000))
-    t_o = o.open_commit_batch(x1[idx], r1[idx], y[idx])[1]
-    assert (t[idx] == t_o).all()
+    t2 = t.copy(); t2[7::1777, 0, 300] += 1
+    v = UB(eng.open_verify(z, t2, cc1, d), B)
+    bad = np.zeros(B, bool); bad[::1000] = True; bad[7::1777] = True
+    assert (v == ~bad).all()
+    assert (v == o.open_verify_batch(z, t2, cc1, d).astype(bool)).all()
 
 
 def test_full_size_linear(setup):
     """BASELINE config 4 at full size (2^14 instances) through the host entry points (several pipeline chunks on
-    several streams): honest transcripts verify, a tampered subset fails and nothing else does, and a random sample of
-    instances is bit-exact against the oracle in every output of the prover's commit phase."""
+    several streams): EVERY instance bit-exact against the oracle in every output of the prover's commit phase and in
+    the responses; honest transcripts verify, a tampered subset fails and nothing else does, verdicts equal the oracle's."""
     eng, o, s = setup
     B = 1 << 14
     x, g = s.message(B), s.scalar(B)
     r, rp, y, yp, d = s.small(B), s.small(B), s.gaussian(B), s.gaussian(B), s.challenge(B)
     lc = eng.linear_commit(g, x, rp, r, y, yp)
     assert UB(lc["ok"], B).all()
-    idx = np.random.default_rng(2).choice(B, 24, replace=False)
-    idx[0], idx[1] = 0, B - 1
-    lo = o.linear_commit_batch(g[idx], x[idx], rp[idx], r[idx], y[idx], yp[idx])
+    lo = o.linear_commit_batch(g, x, rp, r, y, yp)
     for kname in ("gx", "cp", "c", "t", "tp", "u"):
-        assert (lc[kname][idx] == lo[kname]).all(), kname
+        assert (lc[kname] == lo[kname]).all(), kname
     z, zp = eng.linear_respond(y, yp, r, rp, d)
-    z_o, zp_o = o.linear_respond_batch(y[idx], yp[idx], r[idx], rp[idx], d[idx])
-    assert (z[idx] == z_o).all() and (zp[idx] == zp_o).all()
+    z_o, zp_o = o.linear_respond_batch(y, yp, r, rp, d)
+    assert (z == z_o).all() and (zp == zp_o).all()
     assert UB(eng.linear_verify(z, zp, lc["c"], lc["cp"], g, lc["t"], lc["tp"], lc["u"], d), B).all()
     u = lc["u"].copy()
     u[::997, ..., 5] += 1                                   # third equation only
@@ -298,11 +297,13 @@ def test_full_size_linear(setup):
     v = UB(eng.linear_verify(z, zp2, lc["c"], lc["cp"], g, lc["t"], lc["tp"], u, d), B)
     bad = np.zeros(B, bool); bad[::997] = True; bad[3::1999] = True
     assert (v == ~bad).all()
+    assert (v == o.linear_verify_batch(z, zp2, lc["c"], lc["cp"], g, lc["t"], lc["tp"], u, d).astype(bool)).all()
 
 
 def test_full_size_sum(setup):
-    """BASELINE config 5 at full size (2^12 instances of 64 terms) through the host entry points: honest transcripts
-    verify, single tampered terms fail exactly their instance, sampled instances are bit-exact against the oracle."""
+    """BASELINE config 5 at full size (2^12 instances of 64 terms) through the host entry points: EVERY instance
+    bit-exact against the oracle (x', c', c_i, t_i, t', u, z_i, z'); honest transcripts verify, single tampered terms
+    fail exactly their instance, verdicts equal the oracle's."""
     eng, o, s = setup
     B, T = 1 << 12, 64
     gs, xs = s.scalar(B, T), s.uniform_q(B, T, 1)
@@ -310,13 +311,13 @@ def test_full_size_sum(setup):
     rp, yp, d = s.small(B), s.gaussian(B), s.challenge(B)
     sc = eng.sum_commit(gs, xs, rp, rs, ys, yp)
     assert UB(sc["ok"], B).all()
-    idx = np.array([0, 1777, B - 1])
-    so = o.sum_commit_batch(gs[idx], xs[idx], rp[idx], rs[idx], ys[idx], yp[idx])
+    so = o.sum_commit_batch(gs, xs, rp, rs, ys, yp)
     for kname in ("xp", "cp", "cs", "ts", "tp", "u"):
-        assert (sc[kname][idx] == so[kname]).all(), kname
+        assert (sc[kname] == so[kname]).all(), kname
     zs, zp = eng.sum_respond(ys, yp, rs, rp, d)
-    zs_o, zp_o = o.sum_respond_batch(ys[idx], yp[idx], rs[idx], rp[idx], d[idx])
-    assert (zs[idx] == zs_o).all() and (zp[idx] == zp_o).all()
+    zs_o, zp_o = o.sum_respond_batch(ys, yp, rs, rp, d)
+    assert (zs == zs_o).all() and (zp == zp_o).all()
+    del so, zs_o, zp_o
     assert UB(eng.sum_verify(zs, zp, sc["cs"], sc["cp"], gs, sc["ts"], sc["tp"], sc["u"], d), B).all()
     ts = sc["ts"].copy()
     ts[5::501, 63, ..., 0] += 1                             # first equation of the last term
@@ -325,6 +326,7 @@ def test_full_size_sum(setup):
     v = UB(eng.sum_verify(zs, zp, sc["cs"], sc["cp"], gs2, ts, sc["tp"], sc["u"], d), B)
     bad = np.zeros(B, bool); bad[5::501] = True; bad[7::1013] = True
     assert (v == ~bad).all()
+    assert (v == o.sum_verify_batch(zs, zp, sc["cs"], sc["cp"], gs2, ts, sc["tp"], sc["u"], d).astype(bool)).all()
 
 
 @pytest.mark.parametrize("B,T", [(3, 4), (700, 4), (40, 64), (2500, 1)])
@@ -380,32 +382,88 @@ def test_device_resident_linear_sum_match_host_entry_points(setup, B, T):
         assert UB(eng.linear_verify(zl.cpu().numpy(), zpl.cpu().numpy(), hl["c"], hl["cp"], g, hl["t"], hl["tp"], hl["u"], d), B).all()
 
 
-@pytest.mark.parametrize("mode,B", [(0, 300), (1, 300), (1, 5000), (2, 5000)])
-def test_commit_execution_modes(mode, B, monkeypatch):
-    """The three commitment kernels -- integer split-key program (0), FP64-pipe program (1), both pipes in
-    one launch (2, used from 4096 items) -- are bit-exact against the oracle, including the |r| = 15 edge of
-    their shared range and arbitrary int32 representatives of x; |r| = 16 falls back to the generic program."""
-    monkeypatch.setenv("RZK_COMMIT_MODE", str(mode))
-    s = synth.Synth(77 + mode, N=N)
+@pytest.mark.parametrize("B", [300, 5000])
+def test_commit_split_key_range_and_masked_redo(setup, B):
+    """The split-key commitment program is bit-exact against the oracle up to the |r| = 15 edge of its range and for arbitrary
+    int32 representatives of x; items with |r| = 16 or more are redone by the two-prime program in a masked launch on the
+    same stream (no host round trip, no second pass over the batch)."""
+    eng, o, s = setup
+    rng = np.random.default_rng(5)
+    x, r = s.message(B, ragged=True), s.small(B)
+    r[1] = rng.integers(-15, 16, size=r[1].shape)
+    r[2, 1:] = 15; r[3, 1:] = -15
+    x[4, 0, ::3] = np.int32(2 ** 31 - 1); x[4, 0, 1::3] = np.int32(-2 ** 31)
+    launches0 = eng.kernel_launches()
+    c, ok = eng.commit(x, r)
+    clean = eng.kernel_launches() - launches0
+    c_o, ok_o = o.commit_batch(o.center(x.astype(np.int64)).astype(np.int32), r)
+    assert (c == c_o).all() and UB(ok, B).all()
+    r[7, 2, 100] = 16                       # outside the one-word range
+    r[B - 1, 1] = rng.integers(-127, 128, size=N)
+    launches0 = eng.kernel_launches()
+    c2, ok2 = eng.commit(x, r)
+    assert eng.kernel_launches() - launches0 == clean       # same launches as a clean batch: the redo is the masked launch
+    c2_o, _ = o.commit_batch(o.center(x.astype(np.int64)).astype(np.int32), r)
+    assert (c2 == c2_o).all() and UB(ok2, B).all()
+
+
+def test_masked_redo_full_batch_one_bad_item(setup):
+    """2^16 commitments with ONE |r| = 16 item: every commitment equals the oracle's, and the call costs the launches
+    and the PCIe bytes of a clean batch (no whole-batch redo on a range error)."""
+    eng, o, s = setup
+    B = 1 << 16
+    x, r = s.message(B), s.small(B)
+    launches0 = eng.kernel_launches()
+    c0, _ = eng.commit(x, r)
+    clean = eng.kernel_launches() - launches0
+    r[40000, 2, 9] = 16
+    launches0 = eng.kernel_launches()
+    c, ok = eng.commit(x, r)
+    assert eng.kernel_launches() - launches0 == clean
+    assert UB(ok, B).all()
+    same = np.ones(B, bool); same[40000] = False
+    assert (c[same] == c0[same]).all()
+    c_o, _ = o.commit_batch(x[39990:40010], r[39990:40010])
+    assert (c[39990:40010] == c_o).all()
+    # the Open / Linear / Sum provers share the path: one bad item among 300 instances of 3 terms
+    Bs, T = 300, 3
+    gs, xs = s.scalar(Bs, T), s.uniform_q(Bs, T, 1)
+    rs, ys = s.small(Bs, T), s.gaussian(Bs, T)
+    rp, yp = s.small(Bs), s.gaussian(Bs)
+    rs[123, 1, 2, 500] = -77; rp[7, 1, 0] = 16
+    sc = eng.sum_commit(gs, xs, rp, rs, ys, yp)
+    so = o.sum_commit_batch(gs, xs, rp, rs, ys, yp)
+    for kname in ("xp", "cp", "cs", "ts", "tp", "u"):
+        assert (sc[kname] == so[kname]).all(), kname
+    assert UB(sc["ok"], Bs).all()
+
+
+def test_large_b_runs_generic_commit():
+    """b > 15 (accepted while b * kappa <= 74): every commitment runs the two-prime program, exact for any int8 r, on the host
+    AND on the `_dev` entry points (no garbage c behind a FLAG_RANGE bit)."""
+    import torch
+    s = synth.Synth(91, N=N)
     a1p, a2p = s.key()
-    eng = engine.Engine(N=N, device=0)
+    P = engine.lib().rzk_default_params(N)
+    P.b, P.kappa = 24, 3
+    eng = engine.Engine(N=N, device=0, params=P)
     try:
         eng.set_key_blocks(a1p, a2p)
-        o = orc.Oracle(orc.Params(N=N), a1p, a2p)
-        rng = np.random.default_rng(5)
-        x, r = s.message(B, ragged=True), s.small(B)
-        r[1] = rng.integers(-15, 16, size=r[1].shape)
-        r[2, 1:] = 15; r[3, 1:] = -15
-        x[4, 0, ::3] = np.int32(2 ** 31 - 1); x[4, 0, 1::3] = np.int32(-2 ** 31)
+        o = orc.Oracle(orc.Params(N=N, b=24, kappa=3), a1p, a2p)
+        B = 70
+        rng = np.random.default_rng(3)
+        x = s.message(B)
+        r = rng.integers(-24, 25, size=(B, 3, N)).astype(np.int8)
         c, ok = eng.commit(x, r)
-        c_o, ok_o = o.commit_batch(o.center(x.astype(np.int64)).astype(np.int32), r)
-        assert (c == c_o).all() and UB(ok, B).all()
-        launched = eng.kernel_launches()
-        r[7, 2, 100] = 16                       # outside the one-word range: redone by the two-prime program
-        c2, ok2 = eng.commit(x, r)
-        c2_o, _ = o.commit_batch(o.center(x.astype(np.int64)).astype(np.int32), r)
-        assert (c2 == c2_o).all() and UB(ok2, B).all()
-        assert eng.kernel_launches() > launched
+        c_o, ok_o = o.commit_batch(x, r)
+        assert (c == c_o).all() and (UB(ok, B) == ok_o.astype(bool)).all()
+        dev = torch.device("cuda:0")
+        cd = torch.empty((B, 2, N), dtype=torch.int32, device=dev)
+        fl = torch.zeros(B, dtype=torch.int32, device=dev)
+        eng.dev("commit_batch", B, torch.from_numpy(x).to(dev), torch.from_numpy(r).to(dev), cd, fl,
+                stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert (cd.cpu().numpy() == c_o).all() and not fl.any()
     finally:
         eng.close()
 
@@ -491,8 +549,8 @@ def test_respond_rotation_kernel_and_fallback(setup):
 
 def test_device_outputs_stay_in_bounds(setup):
     """Outputs of the device-resident entry points are carved out of larger buffers with canary words on both
-    sides (compute-sanitizer is not available on this pool): odd batch sizes, the hybrid commitment launch
-    (>= 4096 items), the rotation-kernel response and the masked fallback must leave every canary intact."""
+    sides (compute-sanitizer is not available on this pool): odd batch sizes, the rotation-kernel response with its
+    masked fallback and Open verify by rotations must leave every canary intact."""
     import torch
     eng, o, s = setup
     dev = torch.device("cuda:0")

@@ -1,7 +1,8 @@
-"""GPU: differential soak (tools/soak.py) -- random batch sizes around every launch-shape boundary; the integer (with
-and without phase mixing), FP64 and hybrid commitment kernels must agree with each other, the rotation-kernel response
-with the NTT response, honest proofs must verify, and Sum / Linear proofs in their default lowering (chunked three-prime
-epilogue, shared challenge image, one-launch product sums) must agree with the plain lowering run by the generic interpreter."""
+"""GPU: differential soak (tools/soak.py) -- random batch sizes around every launch-shape boundary; the split-key
+commitment program (with and without phase mixing) and the generic two-prime program must agree with each other, the
+rotation-kernel response with the NTT response, Open verify by signed rotations with the NTT-domain product (honest and
+tampered), and Sum / Linear proofs in their default lowering (chunked three-prime epilogue, shared challenge image,
+one-launch product sums) must agree with the plain lowering run by the generic interpreter (RZK_TEST_LOWERING)."""
 import os
 import subprocess
 import sys

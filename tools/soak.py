@@ -1,6 +1,7 @@
-"""Differential soak test on the GPU: random batch sizes, the commitment kernels (integer with / without phase mixing,
-FP64, hybrid) against each other, the rotation-kernel response against the NTT response, honest proofs verify; Sum /
-Linear proofs in their default lowering against the plain lowering run by the generic interpreter.
+"""Differential soak test on the GPU: random batch sizes; the split-key commitment program with / without phase mixing and the
+two-prime program run by the generic interpreter against each other; the rotation-kernel response against the NTT response;
+Open verify with c1*d as signed rotations against the NTT-domain product (honest and tampered transcripts); Sum / Linear proofs
+in their default lowering against the plain lowering run by the generic interpreter.
 usage: python tools/soak.py [rounds] [seed]"""
 import importlib, os, sys
 import numpy as np
@@ -31,8 +32,8 @@ def main():
     rng = np.random.default_rng(seed)
     s = pkg.synth.Synth(seed, N=N)
     a1p, a2p = s.key()
-    engines = {"int+pp": make({"RZK_COMMIT_MODE": "0", "RZK_COMMIT_PP": "2"}), "int": make({"RZK_COMMIT_MODE": "0", "RZK_COMMIT_PP": "9"}),
-               "f64": make({"RZK_COMMIT_MODE": "1"}), "hybrid": make({"RZK_COMMIT_MODE": "2"}), "ntt-respond": make({"RZK_NO_SPARSE": "1"})}
+    engines = {"int+pp": make({}), "int": make({"RZK_TUNE": "commit_pp=9"}), "generic": make({"RZK_TEST_LOWERING": "generic"}),
+               "ntt": make({"RZK_TEST_LOWERING": "nosparse,norot"})}
     for e in engines.values():
         e.set_key_blocks(a1p, a2p)
     UB = engine.unpack_bitmap
@@ -42,7 +43,7 @@ def main():
         if it % 3 == 0:
             r = rng.integers(-3, 4, size=r.shape).astype(np.int8)
         ref = None
-        for name in ("int+pp", "int", "f64", "hybrid"):
+        for name in ("int+pp", "int", "generic"):
             c, ok = engines[name].commit(x, r)
             assert UB(ok, B).all(), (name, B)
             if ref is None:
@@ -53,17 +54,24 @@ def main():
         c, t, _ = e0.open_commit(x, r, y)
         assert (c == ref).all()
         z = e0.open_respond(y, r, d)
-        z2 = engines["ntt-respond"].open_respond(y, r, d)
+        z2 = engines["ntt"].open_respond(y, r, d)
         assert (z == z2).all(), ("respond", B, it)
-        v = UB(e0.open_verify(z, t, np.ascontiguousarray(c[:, :1]), d), B)
+        c1 = np.ascontiguousarray(c[:, :1])
+        v = UB(e0.open_verify(z, t, c1, d), B)
         assert v.all(), ("verify", B, it)
+        bad = rng.random(B) < 0.25
+        zt = z.copy(); zt[bad, int(rng.integers(0, 3)), int(rng.integers(0, N))] += 1
+        dt = d.copy(); dt[bad, int(rng.integers(0, N))] ^= 1                   # one rotation more / fewer / a sign flipped
+        for args in ((zt, t, c1, d), (z, t, c1, dt)):
+            v1, v2 = UB(e0.open_verify(*args), B), UB(engines["ntt"].open_verify(*args), B)
+            assert (v1 == ~bad).all() and (v2 == ~bad).all(), ("verify tampered", B, it)
         assert UB(e0.commitment_verify(c, x, r), B).all()
         print(f"round {it:3d} B={B:6d} ok", flush=True)
     # Linear / Sum proofs: the default lowering (three-prime kernels with the chunked epilogue, shared challenge image,
     # one-launch product sums) against the plain one (every item transforms its own challenge, one launch per product
     # sum, no cutting of small batches into segments) run through the generic interpreter, at instance counts around the launch-shape boundaries of the
     # half-warp-per-item kernels (148 SMs x 2 x warps)
-    plain = make({"RZK_NO_FUSE": "1", "RZK_NO_DIMG": "1", "RZK_NO_STATIC": "1", "RZK_NO_SEGMENTS": "1", "RZK_MULSUM2_PP": "0"})
+    plain = make({"RZK_TEST_LOWERING": "generic,nofuse,nodimg,nosegments,norot,nosparse"})
     plain.set_key_blocks(a1p, a2p)
     e0 = engines["int+pp"]
     for it in range(max(4, rounds // 3)):
