@@ -30,19 +30,43 @@ if ROOT not in sys.path:
 
 N = 512
 BATCH = 1 << 16
-ALG_BYTES_COMMIT = 12288       # 4 polys in + 2 out at 4 B/coeff
-ALG_BYTES_VERIFY = 12288       # 6 polys in
-ALG_MULMODS_COMMIT = 21504
-MEASURED_MULMOD_TPS = 4.617     # T Shoup-mulmods/s on the integer pipes, profiles/r1_imad_bench.jsonl
-MEASURED_F64_MULMOD_TPS = 3.057  # T FP64 mulmods/s (6 DP ops each) on the FP64 pipe, profiles/r1b_imad_fp64_bench.jsonl
+# algorithmic bytes (4 B per coefficient of every polynomial that must cross HBM) and modular multiplies
+# per unit of work
+ALG = {
+    "commit": {"bytes": 12288, "mulmods": 21504},            # 4 polys in + 2 out
+    "open_verify": {"bytes": 12288, "mulmods": 15872},       # 6 polys in
+    "open_instance": {"bytes": 53248, "mulmods": 53248},     # commit + respond + verify
+    "linear": {"bytes": 112640, "mulmods": 204288},
+    "sum64": {"bytes": 3596288, "mulmods": 7268352},
+}
+ALG_BYTES_COMMIT = ALG["commit"]["bytes"]
+ALG_MULMODS_COMMIT = ALG["commit"]["mulmods"]
+# Integer denominators, measured by the builder on this pool's B200s with tools/imad_bench.cu (MEASURED_PEAKS.json carries
+# no integer peak): the plain 32-bit multiply rate R_IMAD of SURVEY 8(d)'s formula frac = 3 * mulmods * rate / R_IMAD,
+# and the rate of a complete Shoup modular multiplication (IMAD.HI + 2 IMAD: IMAD.HI issues at 24 /clk/SM, 2.6 x an IMAD)
+MEASURED_IMAD_TPS = 18.1        # T IMAD/s, profiles/r1_imad_bench.jsonl
+MEASURED_MULMOD_TPS = 4.617     # T Shoup-mulmods/s, same file
 METRIC = "commitments/s"
 UNIT = "commitments/s"
-COMMIT_KERNELS = {      # RZK_COMMIT_MODE -> (kernel, key in profiles/traffic.json)
-    0: ("rzk_vm_kernel<1, MODE_SPLITKEY, SPCommitSplitKey> (integer split-key program, CTA halves phase-mixed)", "commit_int_splitkey"),
-    1: ("rzk_commit_f64_kernel (FP64-pipe program)", "commit_f64"),
-    2: ("rzk_commit_hybrid_kernel<SPCommitSplitKey> (per CTA: 8 warps integer split-key program + 8 warps FP64-pipe program)", "commit_hybrid"),
-}
+COMMIT_KERNEL = ("rzk_vm_kernel<1, MODE_SPLITKEY, SPCommitSplitKey> (integer split-key program, CTA halves phase-mixed)", "commit_int_splitkey")
 WORKLOAD = "configs[1]: batched commitment generation, 2^16 messages/GPU at N=512, Params::default(), one shared key"
+
+
+def bench_config():
+    """`config` of the JSON line: the same object for both arms (ours and --impl reference)."""
+    return {"workload": WORKLOAD, "items_per_gpu_per_step": BATCH, "N": N, "q": 3515337053, "params": "Params::default()",
+            "seed": 1000}
+
+
+def int_roofline(name, rate_per_s):
+    """Fraction of the integer-multiply roofline for `name` at `rate_per_s` units/s on ONE GPU, both ways:
+    frac_contract = 3 * mulmods * rate / R_IMAD (R_IMAD builder-measured, 18.1 T/s) and
+    frac_shoup = mulmods * rate / (measured rate of a whole Shoup mulmod, 4.617 T/s)."""
+    mm = ALG[name]["mulmods"]
+    return {"mulmods_per_unit": mm, "units_per_s_per_gpu": rate_per_s,
+            "frac_contract": 3.0 * mm * rate_per_s / (MEASURED_IMAD_TPS * 1e12),
+            "frac_shoup": mm * rate_per_s / (MEASURED_MULMOD_TPS * 1e12),
+            "hbm_frac": ALG[name]["bytes"] * rate_per_s / 1e9 / measured_peaks()[0]}
 
 
 def measured_peaks():
@@ -119,6 +143,11 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+CPU_LABEL = ("C restatement of the reference: schoolbook O(N^2) negacyclic products in the reference's operation order incl. the "
+             "identity / zero key blocks, zero coefficients of the left operand skipped (so r in {-1,0,1} costs 2/3 of the dense "
+             "MAC count of BASELINE.md section 3 -- the CPU figure is the faster, conservative one), OpenMP over items")
+
+
 def cpu_model():
     try:
         for line in open("/proc/cpuinfo"):
@@ -127,6 +156,37 @@ def cpu_model():
     except OSError:
         pass
     return "unknown"
+
+
+def bind_to_gpu_numa(index):
+    """Runs this rank's host threads and places its pinned buffers on the NUMA node the GPU hangs off (end-to-end leg:
+    with 8 ranks on one socket every copy crosses the inter-socket link).  Best effort: reports what it could do."""
+    info = {"gpu": index, "node": None, "cpus_bound": False, "mem_bound": False}
+    try:
+        import ctypes
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        node = int(open(f"/sys/bus/pci/devices/{bus[-12:].lower()}/numa_node").read())
+        info["node"] = node
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["cpus_bound"] = True
+        # set_mempolicy(MPOL_PREFERRED, {node}): later page faults (pinned allocations included) prefer the GPU's node
+        mask = ctypes.c_ulong(1 << node)
+        rc = ctypes.CDLL(None, use_errno=True).syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(64))
+        info["mem_bound"] = (rc == 0)
+    except Exception as ex:      # no NVML / sysfs / permission: keep the default placement
+        info["error"] = type(ex).__name__
+    return info
 
 
 def cpu_commit_rate(target_s=12.0, seed=7):
@@ -249,26 +309,36 @@ def run_reference(args):
     # torch.distributed.run exports OMP_NUM_THREADS=1 to every rank; this arm is the one CPU job of the node and is
     # meant to use every host core, so the variable is reset before the OpenMP runtime of the oracle library starts
     os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
-    rates = []
+    from oracle import oracle as orc
+    pkg = importlib.import_module("ring-zk_b200")
+    s = pkg.synth.Synth(999, N=N)
+    o = orc.Oracle(orc.Params(N=N), *s.key())
+    cores = orc.max_threads()
+    # one step = the same 2^16 commitments our arm's step computes (bounded sample: a few seconds of CPU per step)
+    n = BATCH
+    x, r = pkg.synth.Synth(1000, N=N).message(n), pkg.synth.Synth(1000, N=N).small(n)
     t_all0 = time.perf_counter()
-    info = None
+    times = []
     for i in range(args.warmup + args.steps):
-        rate, cores, n, dt = cpu_commit_rate(target_s=args.ref_seconds, seed=100 + i)
+        t0 = time.perf_counter()
+        o.commit_batch(x, r)
+        dt = time.perf_counter() - t0
         if i >= args.warmup:
-            rates.append(rate)
-        info = (cores, n, dt)
-    value = float(np.mean(rates))
-    cores, n, dt = info
+            times.append(dt)
+        if time.perf_counter() - t_all0 > 240 and len(times) >= 3:       # keep the whole run within a few minutes
+            break
+    dt = float(np.mean(times))
+    value = n / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "steps": len(times), "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample_items_per_step": n,
-                   "note": "C restatement of the reference's CPU path (oracle/), not the Rust binary"},
+        "config": bench_config(),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "cpu_model": cpu_model(),
-                         "sample": f"{n} commitments per step, schoolbook O(N^2) products, OpenMP over items"},
+                         "sample": f"{n} commitments per step ({CPU_LABEL})"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t_all0,
+        "notes": "C restatement of the reference's CPU path (oracle/), not the Rust binary: poly-ring-xnp1 is not in the tree and there is no Rust toolchain",
     }
     emit(line)
 
@@ -297,6 +367,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = bind_to_gpu_numa(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -318,8 +389,6 @@ def main():
     t = torch.empty((B, 1, N), dtype=torch.int32, device=dev)
     z = torch.empty((B, 3, N), dtype=torch.int32, device=dev)
     flags = torch.zeros(B, dtype=torch.int32, device=dev)
-    bitmap = torch.zeros((B + 7) // 8, dtype=torch.uint8, device=dev)
-    gathered = torch.zeros(world * bitmap.numel(), dtype=torch.uint8, device=dev) if world > 1 else None
     rng_word = torch.zeros(1, dtype=torch.int32, device=dev)
 
     def barrier():
@@ -327,41 +396,43 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # The only collective of the path: the all-gather of the per-shard ok / verify bitmaps (8 KiB per rank).
-    # It is issued asynchronously (NCCL stream) on double-buffered bitmaps so that it overlaps the next
-    # step's kernel; all handles are waited for before the timed region closes.
-    bitmaps = [bitmap, torch.zeros_like(bitmap)]
-    gathers = [gathered, torch.zeros_like(gathered)] if world > 1 else [None, None]
-    pending = []
+    # The only collective of the path: the all-gather of the per-shard ok / verify bitmaps (8 KiB per rank and step).
+    # The bitmaps of a job's steps are packed on the device into one [steps][bytes] buffer by the bitmap kernel (same
+    # stream as the commit / verify kernel) and gathered with ONE NCCL all-gather per job, inside the timed region:
+    # the per-step gather of round 1 cost 17 us of a 0.45 ms step at 8 GPUs (latency-bound plain NCCL, 4 % of the step).
+    nbm = (B + 7) // 8
+    max_steps = max(args.steps, args.warmup, 8) + 1
+    bitmaps = torch.zeros((max_steps, nbm), dtype=torch.uint8, device=dev)
+    gathered = torch.zeros((world, max_steps, nbm), dtype=torch.uint8, device=dev) if world > 1 else None
     step_no = [0]
 
-    def gather_async():
-        k = step_no[0] & 1
+    def pack_bitmap():
+        k = step_no[0] % max_steps
         step_no[0] += 1
         eng.dev("flags_to_bitmap", B, flags, bitmaps[k], rng_word, stream=stream)
-        if world > 1:
-            if len(pending) >= 2:
-                pending.pop(0).wait()
-            pending.append(dist.all_gather_into_tensor(gathers[k], bitmaps[k], async_op=True))
 
-    def drain():
-        while pending:
-            pending.pop(0).wait()
+    def gather_job():
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, bitmaps)
 
     def commit_step():
         flags.zero_()
         eng.dev("commit_batch", B, x, r, c, flags, stream=stream)
-        gather_async()
+        pack_bitmap()
 
-    def timed(step_fn, steps, warmup, kernel_events=False):
+    def timed(step_fn, steps, warmup, gather=True):
         for _ in range(warmup):
             step_fn()
+        if gather:
+            gather_job()                      # warms the communicator up
         barrier()
+        step_no[0] = 0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             step_fn()
-        drain()
+        if gather:
+            gather_job()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -380,19 +451,24 @@ def main():
     value = world * B * args.steps / (ms_total * 1e-3)
     assert bool((flags == 0).all()), "commit constraint flags set on honest inputs"
 
+    if world > 1:
+        # every rank's ok bitmap of every timed step arrived on every rank
+        assert bool((gathered[:, :args.steps] == 0xFF).all()), "gathered ok bitmaps are not all-ones"
+
     # ---- dominant kernel alone (roofline) ----
-    commit_mode = int(os.environ.get("RZK_COMMIT_MODE", "0"))
     def kern_only():
         eng.dev("commit_batch", B, x, r, c, flags, stream=stream)
-    ms_k = timed(kern_only, args.steps, args.warmup) / args.steps
+    ms_k = timed(kern_only, args.steps, args.warmup, gather=False) / args.steps
     peak, peak_src = measured_peaks()
     achieved = ALG_BYTES_COMMIT * B / (ms_k * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(COMMIT_KERNELS[commit_mode][1]),
-                "kernel": COMMIT_KERNELS[commit_mode][0],
+                "traffic": ncu_traffic(COMMIT_KERNEL[1]),
+                "traffic_source": "ncu --set full capture of this kernel (dram__bytes_read.sum + dram__bytes_write.sum per launch), "
+                                  "committed as profiles/traffic.json -- a constant of the committed build, not an in-run counter",
+                "kernel": COMMIT_KERNEL[0],
                 "kernel_ms": ms_k, "algorithmic_bytes_per_launch": ALG_BYTES_COMMIT * B, "peak_source": peak_src,
-                "note": "arithmetic-issue bound path (21504 modular multiplies per commitment by SURVEY.md 8(d)); "
-                        "see int_roofline and DESIGN.md"}
+                "note": "integer-multiply bound path (21504 modular multiplies per commitment by SURVEY.md 8(d)): the binding "
+                        "roofline is int_roofline.commit; HBM is second"}
 
     # ---- second half of the metric: open-proof verifies/s (config 3) ----
     eng.dev("open_commit_batch", B, x, r, y, c, t, flags, stream=stream)
@@ -402,15 +478,23 @@ def main():
     def verify_step():
         flags.zero_()
         eng.dev("open_verify_batch", B, z, t, c, 2, d, flags, stream=stream)
-        gather_async()
+        pack_bitmap()
     ms_v = timed(verify_step, args.steps, args.warmup)
     verifies = world * B * args.steps / (ms_v * 1e-3)
     assert bool((flags == 0).all()), "honest Open proofs failed to verify"
 
+    def verify_only():
+        eng.dev("open_verify_batch", B, z, t, c, 2, d, flags, stream=stream)
+    ms_vk = timed(verify_only, args.steps, args.warmup, gather=False) / args.steps
+    roofline["open_verify"] = {"kernel": "rzk_vm_kernel<2, MODE_SPLIT, SPVerifyFirstRot> (two-prime program; c1*d as signed rotations, OP_ROT)",
+                               "kernel_ms": ms_vk, "achieved": ALG["open_verify"]["bytes"] * B / (ms_vk * 1e-3) / 1e9, "unit": "GB/s",
+                               "frac": ALG["open_verify"]["bytes"] * B / (ms_vk * 1e-3) / 1e9 / peak,
+                               "verifies_per_s_per_gpu": B / (ms_vk * 1e-3), "traffic": ncu_traffic("open_verify_rot")}
+
     def prove_step():
         eng.dev("open_commit_batch", B, x, r, y, c, t, flags, stream=stream)
         eng.dev("open_respond_batch", B, y, r, d, z, stream=stream)
-    ms_p = timed(prove_step, args.steps, args.warmup)
+    ms_p = timed(prove_step, args.steps, args.warmup, gather=False)
     proves = world * B * args.steps / (ms_p * 1e-3)
 
     # ---- configs[3] and configs[4]: Linear proofs (2^14 instances) and Sum proofs with 64 terms (2^12 instances),
@@ -437,11 +521,10 @@ def main():
             eng.dev("linear_commit_batch", BL, g_, x_, rp_, r_, y_, yp_, gx, cp, cl, tl, tpl, u, fl, stream=stream)
             eng.dev("linear_respond_batch", BL, y_, yp_, r_, rp_, d_, zl, zpl, stream=stream)
             eng.dev("linear_verify_batch", BL, zl, zpl, cl, cp, g_, tl, tpl, u, d_, fl, stream=stream)
-        ms_l = timed(linear_step, ksteps, 2) / ksteps
+        ms_l = timed(linear_step, ksteps, 2, gather=False) / ksteps
         assert bool((fl == 0).all()), "honest Linear proofs failed to verify"
         extras["linear"] = {"instances_per_gpu": BL, "instances_per_s": world * BL / (ms_l * 1e-3), "ms_per_step": ms_l,
-                            "mulmods_per_instance": 204288,
-                            "frac_of_int_mulmod_peak": 204288 * BL / (ms_l * 1e-3) / (MEASURED_MULMOD_TPS * 1e12)}
+                            "int_roofline": int_roofline("linear", BL / (ms_l * 1e-3))}
         del g_, x_, r_, rp_, y_, yp_, gx, cp, cl, tl, tpl, u, zl, zpl
         # Sum, T = 64
         BS, TT = 1 << 12, 64
@@ -455,11 +538,10 @@ def main():
             eng.dev("sum_commit_batch", BS, TT, gs, xs, rps, rs, ys, yps, xp, cps, css, tss, tps, us, fs, stream=stream)
             eng.dev("sum_respond_batch", BS, TT, ys, yps, rs, rps, ds, zs, zps, stream=stream)
             eng.dev("sum_verify_batch", BS, TT, zs, zps, css, cps, gs, tss, tps, us, ds, fs, stream=stream)
-        ms_s = timed(sum_step, ksteps, 1) / ksteps
+        ms_s = timed(sum_step, ksteps, 1, gather=False) / ksteps
         assert bool((fs == 0).all()), "honest Sum proofs failed to verify"
         extras["sum64"] = {"instances_per_gpu": BS, "terms": TT, "instances_per_s": world * BS / (ms_s * 1e-3), "ms_per_step": ms_s,
-                           "mulmods_per_instance": 7268352,
-                           "frac_of_int_mulmod_peak": 7268352 * BS / (ms_s * 1e-3) / (MEASURED_MULMOD_TPS * 1e12)}
+                           "int_roofline": int_roofline("sum64", BS / (ms_s * 1e-3))}
         del gs, xs, rs, ys, xp, cps, css, tss, tps, us, zs, zps
         torch.cuda.empty_cache()
         if world == 1:
@@ -562,8 +644,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, cores, n, dt = cpu_commit_rate(target_s=12.0)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "cpu_model": cpu_model(),
-               "sample": f"{n} commitments in {dt:.1f} s, C restatement of the reference (schoolbook products, "
-                         f"reference operation order), OpenMP over items"}
+               "sample": f"{n} commitments in {dt:.1f} s ({CPU_LABEL})"}
         if not args.no_extras:
             from oracle import oracle as orc
             cpu["single_call_latency_us_1thread"] = single_call_latency(eng, orc.Oracle(orc.Params(N=N), *key))
@@ -573,22 +654,30 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u32 modular (int32 coefficients, exact integer arithmetic)", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "items_per_gpu_per_step": B, "N": N, "q": 3515337053,
-                       "l2": "inputs_larger_than_l2 (480 MB touched per step vs 126 MB L2)",
-                       "collective": "NCCL all_gather of ok bitmaps (8 KiB/rank), async, double-buffered" if world > 1 else "none",
-                       "seed": 1000},
+            "dtype": "u32", "data": "synthetic",
+            "config": bench_config(),
+            "numa": numa,
+            "notes": {"l2": "inputs_larger_than_l2 (480 MB touched per step vs 126 MB L2)",
+                      "collective": "one NCCL all_gather of the job's ok bitmaps (steps x 8 KiB per rank), inside the timed region" if world > 1 else "none",
+                      "items_per_gpu_per_step": B},
             "open_verifies_per_s": verifies, "open_proves_per_s": proves,
             "ms_per_step_open_verify": ms_v / args.steps, "ms_per_step_open_prove": ms_p / args.steps,
             "other_configs": extras, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clk.summary(),
-            "int_roofline": {"mulmods_per_item": ALG_MULMODS_COMMIT,
-                             "achieved_Tmulmod_s": ALG_MULMODS_COMMIT * B / (ms_k * 1e-3) / 1e12,
-                             "peak_Tmulmod_s": MEASURED_MULMOD_TPS,
-                             "frac": ALG_MULMODS_COMMIT * B / (ms_k * 1e-3) / (MEASURED_MULMOD_TPS * 1e12),
-                             "peak_source": "measured Shoup mulmod rate on this pool's B200 (tools/imad_bench.cu, "
-                                            "profiles/r1_imad_bench.jsonl); algorithmic mulmods per SURVEY.md 8(d)",
-                             "fp64_pipe_peak_Tmulmod_s": MEASURED_F64_MULMOD_TPS},
+            # integer-multiply roofline of every configuration, per GPU (step rates divided by the number of ranks)
+            "int_roofline": {
+                "R_IMAD_T_per_s": MEASURED_IMAD_TPS, "shoup_mulmod_T_per_s": MEASURED_MULMOD_TPS,
+                "peak_source": "builder-measured on this pool's B200s (tools/imad_bench.cu, profiles/r1_imad_bench.jsonl); "
+                               "MEASURED_PEAKS.json has no integer peak.  frac_contract = 3 * mulmods * rate / R_IMAD is "
+                               "SURVEY.md 8(d)'s formula; frac_shoup divides by the measured rate of a whole Shoup mulmod",
+                "commit": int_roofline("commit", B / (ms_k * 1e-3)),
+                "open_verify": int_roofline("open_verify", B / (ms_vk * 1e-3)),
+                "open_instance": int_roofline("open_instance", 1.0 / (ms_p / args.steps * 1e-3 / B + ms_vk * 1e-3 / B)),
+                "linear": extras["linear"]["int_roofline"] if extras else None,
+                "sum64": extras["sum64"]["int_roofline"] if extras else None,
+                # kept for continuity with round 1's line
+                "mulmods_per_item": ALG_MULMODS_COMMIT, "frac": ALG_MULMODS_COMMIT * B / (ms_k * 1e-3) / (MEASURED_MULMOD_TPS * 1e12),
+                "frac_contract": 3.0 * ALG_MULMODS_COMMIT * B / (ms_k * 1e-3) / (MEASURED_IMAD_TPS * 1e12)},
         }
         emit(line)
     eng.close()

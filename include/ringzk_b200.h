@@ -18,7 +18,10 @@
  *     and canonicalised.  Compact types: int32_t for full-size values, int8_t for the
  *     small randomness r in [-b, b] and the challenge d in {-1, 0, 1}.
  *   - Shapes are the reference's default (n, k, l) = (1, 3, 1), N = 512,
- *     q = 3515337053 (params.rs:121-138); other sets return RZK_ERR_UNSUPPORTED.
+ *     q = 3515337053 (params.rs:121-138), with b * kappa <= 74 (Params::default(): 1 * 36): rzk_create derives the
+ *     exactness limits of the two-prime products from the actual (b, kappa) -- the masking vectors N(0, sigma) must sit
+ *     10 sigma inside rzk_small_limit(), and A1.z of a response at the norm bound inside the CRT range -- and returns
+ *     RZK_ERR_UNSUPPORTED for every other set (the shim keeps the reference's CPU path for those).
  *   - "ok"/verify results are bitmaps: bit (i & 7) of byte (i >> 3) is item i.
  *   - Host entry points take host pointers (pinned memory recommended: rzk_host_alloc)
  *     and pipeline H2D / kernels / D2H over chunks.  `_dev` entry points take device
@@ -26,9 +29,9 @@
  *   - One engine is bound to one CUDA device and is externally synchronised.
  *   - The randomness r, y, d is drawn by the caller (host side, seeded RNG) and passed in; the
  *     protocol entry points sample nothing.  (Optional, separate: rzk_sample_*_dev, below.)
- *   - Execution knobs are environment variables read by rzk_create (RZK_COMMIT_MODE, RZK_COMMIT_PP, RZK_PP,
- *     RZK_CTA_SYNC, RZK_NO_SPARSE, RZK_NO_DIMG, RZK_NO_FUSE, RZK_NO_SEGMENTS, RZK_NO_STATIC, RZK_CHUNK_ITEMS, ...):
- *     A/B timing only, results are identical in every setting.
+ *   - Environment variables read by rzk_create: RZK_CHUNK_ITEMS (items per chunk of the host pipeline, default 8192);
+ *     RZK_TEST_LOWERING (comma-separated: generic, nosparse, norot, nodimg, nofuse, nosegments -- alternative lowerings of
+ *     the same phases for the differential tests, results are identical in every setting); RZK_TUNE (developer A/B timing).
  *   - There is no CPU fallback: without a CUDA device rzk_create fails with RZK_ERR_CUDA.
  */
 #ifndef RINGZK_B200_H
@@ -45,7 +48,8 @@ extern "C" {
 #define RZK_ERR_INVALID 1       /* null pointer / bad shape / T == 0 */
 #define RZK_ERR_UNSUPPORTED 2   /* parameter set or key structure outside the accelerated instantiation */
 #define RZK_ERR_CUDA 3          /* CUDA runtime failure (message in rzk_last_error) */
-#define RZK_ERR_RANGE 4         /* a masking vector y exceeded the exactness bound rzk_small_limit() */
+#define RZK_ERR_RANGE 4         /* a masking vector y exceeded the exactness bound rzk_small_limit(): the outputs of the call
+                                   that depend on it are not exact (honest samples never get there: the limit is >= 10 sigma) */
 #define RZK_ERR_NOKEY 5         /* rzk_set_key has not been called */
 
 typedef struct rzk_engine rzk_engine;
@@ -88,7 +92,10 @@ int rzk_sync(rzk_engine *e, void *stream);
 /* ---------------------------------------------------------------- commitment
  * CommitmentKey::commit (commit.rs:88-128) with r supplied:  c = [a1;a2].r + [0;x].
  *   x [B][1][N] i32, r [B][3][N] i8, c [B][2][N] i32,
- *   ok bitmap: check_commit_constraint(r) (commit.rs:102; the reference redraws r on 0). */
+ *   ok bitmap: check_commit_constraint(r) (commit.rs:102; the reference redraws r on 0).
+ * Exact for ANY int8 r: the fast program covers |r| <= 15 (one word per product), and the items outside that range
+ * are redone by the two-prime program in a masked launch on the same stream (no second pass over the batch).  Engines
+ * created with b > 15 run the two-prime program for every item. */
 int rzk_commit_batch(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r,
                      int32_t *c, uint8_t *ok_bitmap);
 
@@ -147,8 +154,14 @@ int rzk_sum_verify_batch(rzk_engine *e, size_t B, uint32_t T, const int32_t *zs,
 
 /* ---------------------------------------------------------------- device-resident variants
  * Same semantics; every pointer is a device pointer on the engine's device.  `flags` is one
- * uint32_t per item (bit 0: check failed, bit 1: range error) and is OR-ed into, so the caller
- * zeroes it; rzk_flags_to_bitmap_dev packs "flags == 0" into a bitmap.  c_stride is the number of
+ * uint32_t per item and is OR-ed into, so the caller zeroes it:
+ *   bit 0 (check failed): the commit / verify constraint or a verification equation does not hold -- the reference's `false`;
+ *   bit 1 (range error): an operand left the range in which the item's products are exact, and the item's OUTPUTS ARE NOT
+ *     VALID: a masking coefficient |y| > rzk_small_limit(), or -- `_dev` commit entry points of an engine with b <= 15 only --
+ *     a randomness coefficient |r| > 15, which is outside the reference's own contract |r| <= b (polynomial.rs:14-24; the
+ *     host entry points redo such items exactly, the `_dev` ones report them).  A caller must test bit 1, per item or
+ *     through the range_any word of rzk_flags_to_bitmap_dev: the bitmap alone carries bit 0 only.
+ * rzk_flags_to_bitmap_dev packs "(flags & 1) == 0" into a bitmap.  c_stride is the number of
  * polynomials per item in the commitment array handed to verify (1: c1 only, 2: full c).
  * The Linear / Sum variants and the responses keep intermediates (w = A2.y, the residue stash of the
  * three-prime products, the hand-over words of the response kernels) in scratch owned by the engine:
@@ -198,6 +211,10 @@ int rzk_pack_i64(rzk_engine *e, size_t count, const int64_t *src, int32_t *dst);
 int rzk_unpack_i64(rzk_engine *e, size_t count, const int32_t *src, int64_t *dst);
 
 /* ---------------------------------------------------------------- optional on-device samplers
+ * TEST AND BENCHMARK USE ONLY -- NOT CRYPTOGRAPHICALLY SECURE.  Philox4x32-10 is a statistical generator keyed by a 64-bit
+ * seed, not a CSPRNG: in this protocol y hides r and the unpredictability of d carries soundness, so production callers draw
+ * r, y, d from their own CSPRNG (the reference: rand::rng(), ChaCha-based) and pass them in, as every protocol entry point
+ * expects.  The samplers exist to measure the flow with r and y resident on the device.
  * NOT part of the reference's flow, where r, y, d are drawn host side by the caller's RNG and passed in.  They keep the
  * prover's r and y on the device between commit and create_response.  Counter-based (Philox4x32-10 keyed by `seed`;
  * `tag` < 2^24 separates streams), so a value depends only on (seed, tag, polynomial index, coefficient index) and is

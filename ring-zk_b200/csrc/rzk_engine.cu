@@ -186,9 +186,9 @@ __global__ void __launch_bounds__(VmCfg<NP, MODE>::kMaxWarps * 32, 1) rzk_vm_ker
         const uint32_t next = item + per_grid;
         if (next < K.n_items && (uint32_t)ctx.ridx < K.n_prefetch) {
             const Stream st = K.st[K.prefetch[ctx.ridx]];
-            const uint32_t bytes = st.stride * kN * ((st.dtype == DT_I8) ? 1u : 4u);
-            const char *base = reinterpret_cast<const char *>(st.base) + (size_t)next * bytes;
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base), "r"(bytes) : "memory");
+            const uint32_t esz = (st.dtype == DT_I8) ? 1u : 4u;
+            const char *base = reinterpret_cast<const char *>(st.base) + (size_t)next * (st.stride * kN * esz);
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base), "r"(K.prefetch_polys[ctx.ridx] * kN * esz) : "memory");
         }
         if constexpr (std::is_void<SP>::value) vm_run_item<NP, MODE>(K, &L, &ctx);
         else vm_run_static<SP>(K, &L, &ctx);

@@ -139,6 +139,8 @@ struct VmLaunch {
     // input streams whose next-item rows are prefetched into L2 while the current item is computed
     uint32_t n_prefetch;
     uint8_t prefetch[8];
+    uint32_t prefetch_polys[8]; // leading polynomials of the row group that the program reads (a verify launch handed the full
+                               // commitment with c_stride 2 reads c1 only: the unused row is not pulled through DRAM)
     uint32_t cta_sync;         // keep the warps of a CTA in step (instruction-cache locality)
     uint32_t loop_count;       // trip count of OP_LOOP in compile-time programs (terms of a Sum proof - 1)
     const uint32_t *item_mask; // optional: only items with item_mask[item / mask_div] != 0 are processed (fallback launches)
@@ -174,19 +176,34 @@ inline ProgNeeds scan_needs(const Op *ops)
     return n;
 }
 
-// Lists the input streams of a program (read by OP_FWD / OP_ADDP / OP_NORM) for prefetching.
+// Lists the input streams of a program (read by OP_FWD / OP_ADDP / OP_NORM / OP_ROT) for prefetching, with the number of
+// leading polynomials of each row group that are actually read.
 inline void list_prefetch(VmLaunch &K)
 {
     bool is_out[kMaxStreams] = {}, is_in[kMaxStreams] = {};
+    uint32_t used[kMaxStreams] = {};
+    bool in_loop = false;
+    auto touch = [&](int s, uint32_t off, uint32_t cnt, bool whole) {
+        is_in[s] = true;
+        const uint32_t hi = whole ? K.st[s].stride : off + cnt;
+        if (hi > used[s]) used[s] = hi;
+    };
     for (int i = 0; i < kMaxOps && K.ops[i].code != OP_END; ++i) {
         const Op &o = K.ops[i];
+        if (o.code == OP_LOOP) in_loop = true;
+        if (o.code == OP_ENDLOOP) in_loop = false;
         if (o.code == OP_FIN && (o.b & FIN_STORE)) is_out[o.a] = true;
-        if (o.code == OP_FWD || o.code == OP_ADDP || o.code == OP_NORM || o.code == OP_ROT) is_in[o.a] = true;
-        if (o.code == OP_ROT) is_in[o.b] = true;
+        if (o.code == OP_FWD) touch(o.a, o.off, (o.b & FWD_HWPOLY) ? 2u : 1u, in_loop && o.step);
+        if (o.code == OP_ADDP) touch(o.a, o.off, 1u, in_loop && o.step);
+        if (o.code == OP_NORM) touch(o.a, o.off, o.c, false);
+        if (o.code == OP_ROT) { touch(o.a, o.off, 1u, in_loop && o.step); touch(o.b, 0u, 1u, false); }
     }
     K.n_prefetch = 0;
     for (int s = 0; s < kMaxStreams && K.n_prefetch < 8; ++s)
-        if (is_in[s] && !is_out[s] && K.st[s].div == 1) K.prefetch[K.n_prefetch++] = (uint8_t)s;
+        if (is_in[s] && !is_out[s] && K.st[s].div == 1) {
+            K.prefetch_polys[K.n_prefetch] = used[s] < K.st[s].stride ? used[s] : K.st[s].stride;
+            K.prefetch[K.n_prefetch++] = (uint8_t)s;
+        }
 }
 
 // Fills the half-warp layout fields; `split` programs keep no stash (residues are swapped by shuffles).

@@ -50,3 +50,24 @@ def test_unsupported_params_rejected():
     h = ctypes.c_void_p()
     assert L.rzk_create(ctypes.byref(P), -1, ctypes.byref(h)) == engine.RZK_ERR_UNSUPPORTED
     assert b"N=512" in L.rzk_last_error(None)
+
+
+@pytest.mark.parametrize("b,kappa,admissible", [(1, 36, True), (2, 36, True), (2, 37, True), (3, 36, False), (5, 36, False),
+                                                 (11, 36, False), (127, 1, False), (74, 1, True), (75, 1, False), (24, 3, True)])
+def test_parameter_admissibility(b, kappa, admissible):
+    """rzk_create derives the exactness limits from the actual (b, kappa): sigma = 429 b kappa / 36 must leave
+    rzk_small_limit() = 320,245 at least 10 sigma away (b * kappa <= 74), and A1.z of a response at the norm bound must
+    stay inside the two-prime CRT range.  Anything else is RZK_ERR_UNSUPPORTED (the shim then keeps the CPU path),
+    never a silently wrapped result.  The check precedes the device query, so it is testable without a GPU."""
+    L = engine.lib()
+    P = L.rzk_default_params(512)
+    P.b, P.kappa = b, kappa
+    h = ctypes.c_void_p()
+    rc = L.rzk_create(ctypes.byref(P), -1, ctypes.byref(h))
+    if h:
+        L.rzk_destroy(h)
+    if admissible:
+        assert rc in (engine.RZK_OK, engine.RZK_ERR_CUDA), L.rzk_last_error(None)
+    else:
+        assert rc == engine.RZK_ERR_UNSUPPORTED
+        assert b"b*kappa" in L.rzk_last_error(None) or b"<= 127" in L.rzk_last_error(None)
