@@ -167,11 +167,7 @@ __global__ void __launch_bounds__(VmCfg<NP, MODE>::kMaxWarps * 32, 1) rzk_vm_ker
     Lane L;
     uint32_t pp_count = 0;
     ctx.pp_count = &pp_count;
-    if (K.pp_mode == 2) {
-        if (pp_group() == 1) asm volatile("bar.arrive 8, %0;" ::"r"(blockDim.x) : "memory");     // group 0 owns the first window
-    } else if (K.pp_mode != 0) {
-        if (pp_group() == 1) asm volatile("bar.sync 10, %0;" ::"r"(blockDim.x) : "memory");       // start offset
-    }
+    pp_start(K);
 #pragma unroll 1
     for (uint32_t it = 0; it < iters; ++it) {
         const uint32_t item = first + it * per_grid;
@@ -193,12 +189,7 @@ __global__ void __launch_bounds__(VmCfg<NP, MODE>::kMaxWarps * 32, 1) rzk_vm_ker
         if constexpr (std::is_void<SP>::value) vm_run_item<NP, MODE>(K, &L, &ctx);
         else vm_run_static<SP>(K, &L, &ctx);
     }
-    if (K.pp_mode == 2) {
-        if (pp_group() == 0) asm volatile("bar.sync 8, %0;" ::"r"(blockDim.x) : "memory");        // absorbs the last hand-over
-    } else if (K.pp_mode != 0) {
-        // a CTA whose group 0 never reached the hand-over point (no work) must still release group 1
-        if (pp_group() == 0 && pp_count < (K.pp_mode == 1 ? 1u : 2u)) asm volatile("bar.arrive 10, %0;" ::"r"(blockDim.x) : "memory");
-    }
+    pp_finish(K, pp_count);
 }
 
 // ---- response z = y + d*r as signed rotations (rzk_sparse.cuh): one warp per item, byte accumulators ----
@@ -382,6 +373,7 @@ struct rzk_engine {
     uint32_t static_respond = 0;
     uint32_t mulsum2_pp = 2;        //   mulsum2_pp phase mixing of the two-accumulator product-sum program (0 / 9 = off)
     uint32_t commit_pp = 2;         //   commit_pp  phase mixing of the split-key commitment program (0 / 9 = off)
+    uint32_t verify_pp = 22;        //   verify_pp  phase mixing of the Open verify program with the rotation sum (two staggered groups)
     uint32_t pp_mode = 0;           //   pp         phase mixing between CTA halves for every static program
     uint32_t cta_sync = 8;          //   cta_sync   lock-step barriers (rzk_vm_exec.cuh cta_lockstep): 8 = one per segment, 1 = per transform, 0 = off
 };
@@ -479,9 +471,13 @@ int launch_vm(rzk_engine *e, VmLaunch &K, cudaStream_t s, uint32_t pp_program = 
     if ((uint32_t)warps > want) warps = (int)std::max<uint32_t>(want, (uint32_t)std::min(4, warps));
     // phase mixing: RZK_PP for every static program (experiments), else the program's own setting
     const uint32_t pp = e->pp_mode ? e->pp_mode : pp_program;
-    if (pp && pp != 9 && !std::is_void<SP>::value && warps >= 2 && (warps & 1) == 0) {
+    const uint32_t pp_groups = pp >= 10 ? pp / 10 : 2u;
+    if (pp && pp != 9 && !std::is_void<SP>::value && pp_groups >= 2 && pp_groups <= 8 && (pp < 10 || pp % 10 >= 1) &&
+        (uint32_t)warps >= pp_groups && (uint32_t)warps % pp_groups == 0) {
         K.pp_mode = pp;
-        K.cta_sync = (pp == 2) ? 0u : 2u;             // strict alternation already keeps each group in step
+        // strict alternation already keeps each group in step; staggered groups (pp >= 10) lock-step per segment inside each
+        // group (cta_lockstep); the two-group offset modes 1 / 3 per transform
+        K.cta_sync = (pp == 2) ? 0u : (pp >= 10 ? e->cta_sync : 2u);
     }
     const size_t smem = S::bytes(warps, K.hw_words);
     static std::atomic<bool> configured[16];   // per device; engines of a group run on separate threads
@@ -693,7 +689,10 @@ int dev_verify_first(rzk_engine *e, size_t items, const int32_t *z, const int32_
     set_stream(K, 3, d, 1, DT_I8, d_div);
     if (w) set_stream(K, 4, w, 1, DT_I32);
     if (w && dimg) { set_stream(K, 5, dimg, 2, DT_I32, d_div); return launch_sp<SPVerifyFirstWG>(e, K, s); }
-    if (rot) return launch_sp<SPVerifyFirstRot>(e, K, s);
+    // measured (tools/ab_time.py, 2^16 items): lock-step over the whole CTA 86 M/s, two staggered groups (the second starts when
+    // the first has left its second heavy window, so one group's rotation sum -- shared memory + FP64 pipe -- runs beside the
+    // other group's transforms -- FMA-heavy pipe) 98.7 M/s; four / eight groups 96 / 88 M/s (instruction-cache streams)
+    if (rot) return launch_sp<SPVerifyFirstRot>(e, K, s, e->verify_pp);
     return w ? launch_sp<SPVerifyFirstW>(e, K, s) : launch_sp<SPVerifyFirst>(e, K, s);
 }
 
@@ -1059,7 +1058,7 @@ int rzk_create(const rzk_params *params, int device, rzk_engine **out)
             if (p && (p == tu || p[-1] == ',')) dst = (uint32_t)atoi(p + key.size());
         };
         val("cta_sync", e->cta_sync); val("pp", e->pp_mode); val("commit_pp", e->commit_pp);
-        val("mulsum2_pp", e->mulsum2_pp); val("static_respond", e->static_respond);
+        val("mulsum2_pp", e->mulsum2_pp); val("static_respond", e->static_respond); val("verify_pp", e->verify_pp);
     }
     Guard g(device);
     cudaDeviceProp prop;

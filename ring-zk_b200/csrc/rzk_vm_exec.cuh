@@ -95,7 +95,10 @@ struct LaneCtx {
 // which lets the groups drift apart and mix their pipe usage.
 __device__ __forceinline__ void cta_lockstep(const VmLaunch &K)
 {
-    if (K.cta_sync == 1 || K.cta_sync >= 8) {
+    if (K.pp_mode >= 10) {          // staggered groups (pp_start): lock-step inside each group only, barriers 1 .. G
+        const uint32_t G = K.pp_mode / 10, per = (blockDim.x >> 5) / G;
+        asm volatile("bar.sync %0, %1;" ::"r"((threadIdx.x >> 5) / per + 1u), "r"(per * 32u));
+    } else if (K.cta_sync == 1 || K.cta_sync >= 8) {
         __syncthreads();
     } else if (K.cta_sync >= 2 && K.cta_sync < 8) {
         const uint32_t warps = blockDim.x >> 5;
@@ -118,6 +121,12 @@ __device__ __forceinline__ void cta_lockstep(const VmLaunch &K)
 //              first / second heavy window).
 __device__ __forceinline__ uint32_t pp_group() { return (threadIdx.x >> 5) >= (blockDim.x >> 6) ? 1u : 0u; }
 
+// pp_mode >= 10 encodes G * 10 + n: G groups of consecutive warps (a group of 4 consecutive warps has one warp on every
+// scheduler), each in lock-step internally, started in a staggered way -- group g + 1 starts when group g has left its
+// n-th heavy window -- and free running afterwards.  Named barriers 8 + g (g = 1 .. G - 1) carry the start signal.
+__device__ __forceinline__ uint32_t pp_stagger_groups(const VmLaunch &K) { return K.pp_mode >= 10 ? K.pp_mode / 10 : 0u; }
+__device__ __forceinline__ uint32_t pp_stagger_group(const VmLaunch &K) { return (threadIdx.x >> 5) / ((blockDim.x >> 5) / pp_stagger_groups(K)); }
+
 __device__ __forceinline__ void pp_acquire(const VmLaunch &K)
 {
     if (K.pp_mode == 2) asm volatile("bar.sync %0, %1;" ::"r"(8u + pp_group()), "r"(blockDim.x) : "memory");
@@ -126,10 +135,42 @@ __device__ __forceinline__ void pp_acquire(const VmLaunch &K)
 __device__ __forceinline__ void pp_release(const VmLaunch &K, uint32_t &pp_count)
 {
     if (K.pp_mode == 2) asm volatile("bar.arrive %0, %1;" ::"r"(8u + (pp_group() ^ 1u)), "r"(blockDim.x) : "memory");
-    else if (K.pp_mode != 0) {
+    else if (K.pp_mode >= 10) {
+        ++pp_count;
+        const uint32_t G = pp_stagger_groups(K), g = pp_stagger_group(K);
+        if (pp_count == K.pp_mode % 10 && g + 1 < G)
+            asm volatile("bar.arrive %0, %1;" ::"r"(8u + g + 1u), "r"(2u * (blockDim.x / G)) : "memory");
+    } else if (K.pp_mode != 0) {
         ++pp_count;
         if (pp_count == (K.pp_mode == 1 ? 1u : 2u) && pp_group() == 0)
             asm volatile("bar.arrive 10, %0;" ::"r"(blockDim.x) : "memory");
+    }
+}
+
+// start of the kernel: every group but the first waits for its predecessor's signal
+__device__ __forceinline__ void pp_start(const VmLaunch &K)
+{
+    if (K.pp_mode == 2) {
+        if (pp_group() == 1) asm volatile("bar.arrive 8, %0;" ::"r"(blockDim.x) : "memory");     // group 0 owns the first window
+    } else if (K.pp_mode >= 10) {
+        const uint32_t G = pp_stagger_groups(K), g = pp_stagger_group(K);
+        if (g > 0) asm volatile("bar.sync %0, %1;" ::"r"(8u + g), "r"(2u * (blockDim.x / G)) : "memory");
+    } else if (K.pp_mode != 0) {
+        if (pp_group() == 1) asm volatile("bar.sync 10, %0;" ::"r"(blockDim.x) : "memory");       // start offset
+    }
+}
+
+// end of the kernel: a group that never reached the hand-over point (no work) must still release its successor
+__device__ __forceinline__ void pp_finish(const VmLaunch &K, uint32_t pp_count)
+{
+    if (K.pp_mode == 2) {
+        if (pp_group() == 0) asm volatile("bar.sync 8, %0;" ::"r"(blockDim.x) : "memory");        // absorbs the last hand-over
+    } else if (K.pp_mode >= 10) {
+        const uint32_t G = pp_stagger_groups(K), g = pp_stagger_group(K);
+        if (g + 1 < G && pp_count < K.pp_mode % 10)
+            asm volatile("bar.arrive %0, %1;" ::"r"(8u + g + 1u), "r"(2u * (blockDim.x / G)) : "memory");
+    } else if (K.pp_mode != 0) {
+        if (pp_group() == 0 && pp_count < (K.pp_mode == 1 ? 1u : 2u)) asm volatile("bar.arrive 10, %0;" ::"r"(blockDim.x) : "memory");
     }
 }
 #endif

@@ -71,3 +71,37 @@ def test_parameter_admissibility(b, kappa, admissible):
     else:
         assert rc == engine.RZK_ERR_UNSUPPORTED
         assert b"b*kappa" in L.rzk_last_error(None) or b"<= 127" in L.rzk_last_error(None)
+
+
+def test_rust_ffi_block_is_generated_from_the_header_and_complete():
+    """shim/src/b200/ffi.rs declares exactly the header's functions (it is regenerated here and compared byte for byte), and every
+    `ffi::rzk_*` call in the hand-written shim modules names a declared function with the right number of arguments."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_rust_ffi", os.path.join(ROOT, "tools", "gen_rust_ffi.py"))
+    gen = importlib.util.module_from_spec(spec); spec.loader.exec_module(gen)
+    text, names = gen.generate()
+    assert open(os.path.join(ROOT, "shim", "src", "b200", "ffi.rs")).read() == text, "run python tools/gen_rust_ffi.py"
+    assert sorted(names) == header_functions() and len(names) == len(set(names))
+    arity = {m.group(1): (0 if not m.group(2).strip() else m.group(2).count(":")) for m in re.finditer(r"pub fn (rzk_\w+)\((.*?)\)", text)}
+    used = set()
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "shim")):
+        for f in files:
+            if f.endswith(".rs") and f != "ffi.rs":
+                src = open(os.path.join(dirpath, f)).read()
+                for m in re.finditer(r"ffi::(rzk_\w+)\(", src):
+                    name = m.group(1)
+                    assert name in arity, f"{f}: {name} is not in the header"
+                    # count top-level commas of the call
+                    depth, i, commas = 1, m.end(), 0
+                    while depth:
+                        ch = src[i]
+                        depth += ch in "([{"
+                        depth -= ch in ")]}"
+                        commas += (ch == "," and depth == 1)
+                        i += 1
+                    nargs = commas + (1 if src[m.end():i - 1].strip() else 0)
+                    assert nargs == arity[name], f"{f}: {name} called with {nargs} arguments, declared with {arity[name]}"
+                    used.add(name)
+    # the shim drives every host protocol entry point, single engine and group
+    host = [n for n in names if n.endswith("_batch")]
+    assert set(host) <= used, sorted(set(host) - used)

@@ -630,23 +630,30 @@ def test_device_group_matches_single_engine(setup):
         grp.close()
 
 
-def test_other_randomness_bound_b4():
-    """Params with b = 4 (sigma, both norm bounds and the small operands scale by 4): the norm checks take their
-    general 64-bit path (bounds above 2^21), the commitment stays inside its one-word range, the rotation kernel declines
-    the responses (|r| = 4) and the NTT program answers them; every phase of the Open proof is bit-exact against the
-    oracle built with the same parameters."""
-    b = 4
+@pytest.mark.parametrize("b,kappa,B", [(4, 18, 33), (2, 37, 1 << 16)])
+def test_other_admissible_parameters(b, kappa, B):
+    """Parameter sets at the edge of what rzk_create admits (b * kappa <= 74; sigma, both norm bounds and the small
+    operands scale with b * kappa): (4, 18) makes the rotation kernel decline the responses (|r| = 4 > its bias) so the
+    NTT program answers them; (2, 37) is the accepted extreme -- rzk_small_limit() = 10.09 sigma -- run at the full 2^16
+    batch: honest N(0, sigma) masking vectors never raise RZK_ERR_RANGE and every output is bit-exact against the oracle
+    built with the same parameters (test the accepted extremes at full size)."""
     s = synth.Synth(31, N=N, b=b)
     a1p, a2p = s.key()
     P = engine.lib().rzk_default_params(N)
-    P.b = b
+    P.b, P.kappa = b, kappa
     eng = engine.Engine(N=N, device=0, params=P)
     try:
         eng.set_key_blocks(a1p, a2p)
-        o = orc.Oracle(orc.Params(N=N, b=b), a1p, a2p)
-        assert eng.sigma() == o.sigma() == b * 15444 and eng.verify_bound() == o.verify_bound() > (1 << 21)
-        B = 33
-        x, r, y, d = s.message(B, ragged=True), s.small(B), s.gaussian(B), s.challenge(B)
+        o = orc.Oracle(orc.Params(N=N, b=b, kappa=kappa), a1p, a2p)
+        sigma = b * 11 * kappa * 39
+        assert eng.sigma() == o.sigma() == sigma and eng.verify_bound() == o.verify_bound() == 2 * sigma * 22
+        assert eng.small_limit() >= 10 * sigma
+        rng = np.random.default_rng(b * 100 + kappa)
+        x, r = s.message(B, ragged=True), s.small(B)
+        y = np.trunc(rng.normal(0.0, float(sigma), size=(B, 3, N))).astype(np.int32)
+        d = np.zeros((B, N), np.int8)
+        pos = np.argsort(rng.random((B, N)), axis=1)[:, :kappa]
+        np.put_along_axis(d, pos, (rng.integers(0, 2, size=(B, kappa)) * 2 - 1).astype(np.int8), axis=1)
         assert np.abs(r).max() == b
         c, t, ok = eng.open_commit(x, r, y)
         c_o, t_o, ok_o = o.open_commit_batch(x, r, y)
