@@ -373,6 +373,7 @@ struct rzk_engine {
     uint32_t static_respond = 0;
     uint32_t mulsum2_pp = 2;        //   mulsum2_pp phase mixing of the two-accumulator product-sum program (0 / 9 = off)
     uint32_t commit_pp = 2;         //   commit_pp  phase mixing of the split-key commitment program (0 / 9 = off)
+    uint32_t ld128 = 0;             //   ld128      OP_FWD fetches int32 rows with 128-bit loads + a shared-memory redistribution (A/B)
     uint32_t verify_pp = 22;        //   verify_pp  phase mixing of the Open verify program with the rotation sum (two staggered groups)
     uint32_t pp_mode = 0;           //   pp         phase mixing between CTA halves for every static program
     uint32_t cta_sync = 8;          //   cta_sync   lock-step barriers (rzk_vm_exec.cuh cta_lockstep): 8 = one per segment, 1 = per transform, 0 = off
@@ -422,6 +423,7 @@ void fill_common(const rzk_engine *e, VmLaunch &K, int np, uint32_t n_items, uin
     K.norm_abs_lim[0] = (uint32_t)e->cbound; K.norm_sq_lim[0] = (e->cbound + 1) * (e->cbound + 1) - 1;
     K.norm_abs_lim[1] = (uint32_t)e->vbound; K.norm_sq_lim[1] = (e->vbound + 1) * (e->vbound + 1) - 1;
     K.small_lim = e->small_lim;
+    K.ld128 = e->ld128;
     K.n_items = n_items;
     K.np = (uint32_t)np;
     if (flags) { K.flags = flags; K.flag_div = flag_div; }
@@ -1058,7 +1060,7 @@ int rzk_create(const rzk_params *params, int device, rzk_engine **out)
             if (p && (p == tu || p[-1] == ',')) dst = (uint32_t)atoi(p + key.size());
         };
         val("cta_sync", e->cta_sync); val("pp", e->pp_mode); val("commit_pp", e->commit_pp);
-        val("mulsum2_pp", e->mulsum2_pp); val("static_respond", e->static_respond); val("verify_pp", e->verify_pp);
+        val("mulsum2_pp", e->mulsum2_pp); val("static_respond", e->static_respond); val("verify_pp", e->verify_pp); val("ld128", e->ld128);
     }
     Guard g(device);
     cudaDeviceProp prop;

@@ -146,7 +146,7 @@ struct VmLaunch {
     const uint32_t *item_mask; // optional: only items with item_mask[item / mask_div] != 0 are processed (fallback launches)
     const uint32_t *any_item;  // optional: the whole launch returns at once when *any_item == 0
     uint32_t mask_div;         // item groups per mask word (0 is read as 1)
-    uint32_t pad_mask_;
+    uint32_t ld128;            // A/B variant of OP_FWD's int32 loads (rzk_vm_exec.cuh op_fwd); 0 = 32-bit strided loads
     uint32_t *rmark;           // optional: a range error (FWD_CHECK_SMALL) marks rmark[item / flag_div] = 1 and *rmark_any = 1
     uint32_t *rmark_any;       // instead of setting FLAG_RANGE -- the hand-over to a masked fallback launch (dev_commit)
     uint32_t pp_mode;          // phase mixing between the two halves of a CTA (rzk_vm_exec.cuh pp_acquire); 0 = off

@@ -269,9 +269,35 @@ RZK_VM uint64_t stream_poly(const Stream &s, uint32_t item, uint32_t off)
 
 // ---------------------------------------------------------------- ops
 
+RZK_VM uint4 rot_ld128(const void *p)
+{
+#if defined(__CUDA_ARCH__)
+    return __ldg(reinterpret_cast<const uint4 *>(p));
+#else
+    return *reinterpret_cast<const uint4 *>(p);
+#endif
+}
+
+
 RZK_VM void op_fwd(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const Op &op, int it, uint32_t dtype)
 {
     const Stream st = K.st[op.a];
+    if (K.ld128 && dtype != DT_I8) {
+        // A/B variant (RZK_TUNE=ld128=1): the row arrives as 128-bit loads -- lane t fetches the 32 contiguous coefficients
+        // [32 t, 32 t + 32) -- and is redistributed to the strided layout through the transpose buffer (8 LDG.128 +
+        // 8 STS.128 + 32 LDS instead of 32 LDG.32).  Measured 9-16 % slower on every kernel: the loads
+        // are not what limits these kernels, and the extra shared-memory round trip costs issue slots and LSU wavefronts.
+        RZK_EACH_LANE {
+            RZK_LANE;
+            const uint64_t poly = stream_poly(st, ctx.item, (uint32_t)op.off + (uint32_t)it * op.step +
+                                                                ((op.b & FWD_HWPOLY) ? (uint32_t)ctx.hw : 0u));
+            const uint4 *src4 = reinterpret_cast<const uint4 *>(reinterpret_cast<const int32_t *>(st.base) + poly * kN) + 8 * t;
+            uint4 *row = reinterpret_cast<uint4 *>(ctx.buf + 36 * t);
+            RZK_UNROLL
+            for (int j = 0; j < 8; ++j) row[j] = rot_ld128(src4 + j);
+        }
+        RZK_SYNC();
+    }
     RZK_EACH_LANE {
         RZK_LANE;
         const PrimeC &pc = L.pc;
@@ -282,6 +308,13 @@ RZK_VM void op_fwd(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const Op
             const int8_t *src = reinterpret_cast<const int8_t *>(st.base) + poly * kN;
             RZK_UNROLL
             for (int m = 0; m < kElems; ++m) v[m] = src[t + kLanes * m];
+        } else if (K.ld128) {
+            // staged by the 128-bit loads above: every lane reads exactly the words its own transpose will overwrite
+            RZK_UNROLL
+            for (int m = 0; m < kElems; ++m) {
+                const int i = t + kLanes * m;
+                v[m] = lift_in((int32_t)ctx.buf[i + ((i >> 5) << 2)], K.q);
+            }
         } else {
             const int32_t *src = reinterpret_cast<const int32_t *>(st.base) + poly * kN;
             RZK_UNROLL
@@ -569,15 +602,6 @@ RZK_VM void op_fin(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, typename
 // d, and every lane adds its 16 epilogue coefficients of every term with one LDS.64 + one DFMA -- on the FP64 pipe, which
 // the integer transforms leave idle -- instead of two forward transforms and a pointwise product per prime.
 // Any int8 d and any int32 representative of c are exact: |sum| <= 512 * 127 * 2^31 < 2^53.  Warp-per-item modes only.
-RZK_VM uint4 rot_ld128(const void *p)
-{
-#if defined(__CUDA_ARCH__)
-    return __ldg(reinterpret_cast<const uint4 *>(p));
-#else
-    return *reinterpret_cast<const uint4 *>(p);
-#endif
-}
-
 RZK_VM void rot_ld_pair(const int32_t *p, int32_t &a, int32_t &b)      // 8-byte aligned pair
 {
 #if defined(__CUDA_ARCH__)

@@ -178,8 +178,9 @@ int main(int argc, char **argv)
     std::vector<uint8_t> ok_o(B);
     rzko_open_commit_batch(&P, a1.data(), a2.data(), B, x64.data(), r64.data(), y64.data(), c_o.data(), t_o.data(), ok_o.data(), 1);
     std::vector<int32_t> c_e(B * 2 * N), t_e(B * N), w_e(B * N);
-    {
+    for (int ld128 = 1; ld128 >= 0; --ld128) {       // both forms of OP_FWD's int32 loads (the default last: its outputs are reused below)
         Emu E(2, L2, keyp.data(), B);
+        E.K.ld128 = (uint32_t)ld128;
         Prog pr;
         prog_commit(pr, 0, 1, 2);
         prog_keymatvec(pr, 3, 4, 5, true);
