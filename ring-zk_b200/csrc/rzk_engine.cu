@@ -674,15 +674,16 @@ int dev_challenge_image(rzk_engine *e, size_t groups, const int8_t *d, uint32_t 
     return launch_sp<SPChallengeImage>(e, K, s);
 }
 
-// dimg != nullptr (with w): the image of d comes from dev_challenge_image, one per d_div items
+// dimg != nullptr (with w): the image of d comes from dev_challenge_image, one per d_div items.
+// Without w (Open verify) the product c1*d is a rotation sum in the epilogue (OP_ROT) instead of two transforms per prime.
 int dev_verify_first(rzk_engine *e, size_t items, const int32_t *z, const int32_t *t, const int32_t *c, uint32_t c_stride,
                      const int8_t *d, uint32_t d_div, int32_t *w, uint32_t *flags, uint32_t flag_div, cudaStream_t s,
                      const uint32_t *dimg = nullptr)
 {
     VmLaunch K; memset(&K, 0, sizeof(K));
     Prog p;
-    prog_norm_verify(p, 0);
     const bool rot = !w && !e->no_rot;       // Open verify: c1*d as signed rotations in the epilogue (OP_ROT)
+    prog_norm_verify(p, 0);
     prog_verify_first(p, 0, 1, 2, 3, w ? 4 : -1, (w && dimg) ? 5 : -1, rot);
     p.end();
     p.install(K);
@@ -691,9 +692,8 @@ int dev_verify_first(rzk_engine *e, size_t items, const int32_t *z, const int32_
     set_stream(K, 3, d, 1, DT_I8, d_div);
     if (w) set_stream(K, 4, w, 1, DT_I32);
     if (w && dimg) { set_stream(K, 5, dimg, 2, DT_I32, d_div); return launch_sp<SPVerifyFirstWG>(e, K, s); }
-    // measured (tools/ab_time.py, 2^16 items): lock-step over the whole CTA 86 M/s, two staggered groups (the second starts when
-    // the first has left its second heavy window, so one group's rotation sum -- shared memory + FP64 pipe -- runs beside the
-    // other group's transforms -- FMA-heavy pipe) 98.7 M/s; four / eight groups 96 / 88 M/s (instruction-cache streams)
+    // (tools/ab_time.py, profiles/r2_ab_timings.log: the staggered two-group start decides for the first rotation kernel --
+    // 86 -> 98.7 M/s -- and is neutral for the final one)
     if (rot) return launch_sp<SPVerifyFirstRot>(e, K, s, e->verify_pp);
     return w ? launch_sp<SPVerifyFirstW>(e, K, s) : launch_sp<SPVerifyFirst>(e, K, s);
 }

@@ -30,9 +30,12 @@ constexpr int kG1Words = 66;       // lane-uniform twiddle words per (prime, dir
                                    // (66 = 2 mod 32: the two half warps of a SPLIT warp hit different banks)
 constexpr int kKeyPolys = 3;       // non-trivial key polynomials a1'[0], a1'[1], a2'[0] at (n,k,l)=(1,3,1)
 constexpr int kMaxOps = 56;
-constexpr int kRotHwWords = 1296;  // half-warp region of a program with OP_ROT: the warp's two regions (2592 words) hold the
-                                   // extended row E = [-c | +c] as 1024 doubles and the (position, value) list of d (512 words)
-constexpr int kRotListOff = 2048;  // word offset of the list in the warp region
+constexpr int kRotHwWords = 1040;  // half-warp region of a program with OP_ROT: the warp's two regions (2080 words) hold the
+                                   // extended row E = [2^31 - c | 2^31 + c] (1024 words), the row-offset lists of the +1 and
+                                   // -1 entries of d (2 x 512 uint16 = 512 words) and a row of biased zeros (512 words) that
+                                   // partners the unpaired terms; 1040 = 16 (mod 32)
+constexpr int kRotListOff = 1024;  // word offset of the lists in the warp region
+constexpr int kRotZeroOff = 1536;  // word offset of the zero row
 constexpr int kMaxStreams = 12;
 
 enum OpCode : uint8_t {
@@ -54,7 +57,7 @@ enum OpCode : uint8_t {
     OP_MACG,     // acc[a] (+)= image stream b (.) cur (Montgomery), the image read from global memory     c: MAC_* flags
     OP_ROT,      // (epilogue, warp-per-item modes) V += +-(stream a poly off) * (sparse int8 polynomial of stream b) as signed
                  // rotations of the int32 row: sum_k d[pos_k] * X^pos_k * c, no multiplication by a transform (SURVEY kernel K4);
-                 // c: MAC_NEG.  Exact for any int8 d and any int32 c (512 * 127 * 2^31 < 2^53, summed in binary64).
+                 // c: MAC_NEG.  Exact for any int8 d and any int32 c (d in {-1, 0, 1}^N takes the fast paired form).
 };
 
 enum : uint8_t { FWD_SCALED = 1, FWD_CHECK_SMALL = 2, FWD_HWPOLY = 4 };   // HWPOLY: half warp h reads poly off + h

@@ -534,7 +534,10 @@ struct Epi {
 
 // coefficient index m (in the G1 layout, i = t + 16*m) of epilogue element j
 template <int MODE>
-RZK_VM int epi_m(const LaneCtx &ctx, int j) { return (MODE != MODE_SEQ) ? (16 * ctx.hw + j) : j; }
+// Warp-per-item modes: half warp h finishes the rows m = 2j + h, so the two half warps of a warp touch ADJACENT 64-byte
+// segments of every row they read or write in the epilogue (coefficients t + 32j and t + 16 + 32j: one 128-byte line per
+// warp instruction) and 32 consecutive words of the rotation sum's extended row (OP_ROT: one conflict-free wavefront).
+RZK_VM int epi_m(const LaneCtx &ctx, int j) { return (MODE != MODE_SEQ) ? (2 * j + ctx.hw) : j; }
 
 template <int MODE>
 RZK_VM void op_addp(const VmLaunch &K, const LaneCtx *ctxs, typename Epi<MODE>::V_t (&V)[RZK_NL][Epi<MODE>::kCount], const Op &op, int it, uint32_t dtype)
@@ -594,14 +597,31 @@ RZK_VM void op_fin(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, typename
     }
 }
 
-// OP_ROT -- SURVEY kernel K4 for full-size rows: V += +-(c * d) where d is a sparse small polynomial (the challenge:
-// kappa entries +-1, challenge_space.rs:12-33) and c an int32 row (a commitment row), as in `c1.componentwise_mul(&d)`
-// of the verification equations (open.rs:172, linear.rs:226,232, sum.rs:287,295).  c * d = sum_k d[pos_k] * X^pos_k * c, and
-// X^pos * c is c rotated by pos with the wrapped part negated: the warp writes the extended row E = [-c | +c] to shared
-// memory as doubles (index 512 + i - pos reads the rotated, sign-corrected coefficient), lists the non-zero entries of
-// d, and every lane adds its 16 epilogue coefficients of every term with one LDS.64 + one DFMA -- on the FP64 pipe, which
-// the integer transforms leave idle -- instead of two forward transforms and a pointwise product per prime.
-// Any int8 d and any int32 representative of c are exact: |sum| <= 512 * 127 * 2^31 < 2^53.  Warp-per-item modes only.
+// OP_ROT -- SURVEY kernel K4 for full-size rows: V += +-(c * d) where d is a challenge (kappa entries +-1,
+// challenge_space.rs:12-33) and c an int32 row (a commitment row), as in `c1.componentwise_mul(&d)` of the verification
+// equations (open.rs:172, linear.rs:226,232, sum.rs:287,295).  c * d = sum_k d[pos_k] * X^pos_k * c, and X^pos * c is c
+// rotated by pos with the wrapped part negated, so the product needs no multiplication at all:
+//   * the warp writes the extended row E = [2^31 - c | 2^31 + c] to shared memory as 1024 biased uint32 words (index
+//     512 + i - pos reads the rotated, sign-corrected coefficient of term pos; c is canonicalised first, |c| < 2^31);
+//   * it lists the positions of the +1 and of the -1 entries of d;
+//   * every lane adds its 16 epilogue coefficients (rows m = 2j + hw: the warp reads 32 consecutive words, one conflict-free
+//     wavefront) of every term with ONE 32-bit shared-memory load and ONE DADD, on the FP64 pipe the integer transforms
+//     leave idle: the loaded word u becomes the low half of the double D = 2^52 + u (high word 0x43300000, no conversion
+//     instruction), and the terms are taken in (+, -) pairs, V = (V + D+) - D-, so the 2^52 cancels at once and every
+//     intermediate is an exact integer below 2^53 (|V| < 2^38 between pairs).  When d has more +1 than -1 entries (or
+//     the reverse) the shorter list is padded with a row of biased zeros, so the biases 2^31 cancel pair by pair as well.
+// instead of two forward transforms and a pointwise product per prime.  An item whose d has an entry outside {-1, 0, 1}
+// takes a general loop (one scaled rotation per non-zero entry, DFMA), so the op is exact for every int8 d and every
+// int32 representative of c.  Warp-per-item modes only.
+RZK_VM double rot_biased(uint32_t u)      // the exact double 2^52 + u
+{
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(0x43300000, (int)u);
+#else
+    return 4503599627370496.0 + (double)u;
+#endif
+}
+
 RZK_VM void rot_ld_pair(const int32_t *p, int32_t &a, int32_t &b)      // 8-byte aligned pair
 {
 #if defined(__CUDA_ARCH__)
@@ -612,90 +632,139 @@ RZK_VM void rot_ld_pair(const int32_t *p, int32_t &a, int32_t &b)      // 8-byte
 #endif
 }
 
-RZK_VM void rot_st_pair(double *p, double a, double b)                  // 16-byte aligned pair
+RZK_VM void rot_st_pair(uint32_t *p, uint32_t a, uint32_t b)           // 8-byte aligned pair
 {
 #if defined(__CUDA_ARCH__)
-    *reinterpret_cast<double2 *>(p) = make_double2(a, b);
+    *reinterpret_cast<uint2 *>(p) = make_uint2(a, b);
 #else
     p[0] = a; p[1] = b;
 #endif
 }
 
 template <int MODE>
-RZK_VM void op_rot(const VmLaunch &K, const LaneCtx *ctxs, typename Epi<MODE>::V_t (&V)[RZK_NL][Epi<MODE>::kCount], const Op &op, int it)
+RZK_VM void op_rot(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, typename Epi<MODE>::V_t (&V)[RZK_NL][Epi<MODE>::kCount], const Op &op, int it)
 {
     if constexpr (MODE != MODE_SEQ) {
+        constexpr int CNT = Epi<MODE>::kCount;
         const Stream sc = K.st[op.a], sd = K.st[op.b];
         RZK_SYNC();          // the transpose buffers this overlays are no longer read
-        // ---- E = [-c | +c] as doubles: lane l converts the coefficient pairs 2l + 64e, e = 0..7 (8-byte loads, 16-byte stores)
+        // ---- E = [2^31 - c | 2^31 + c]: lane l handles the coefficient pairs 2l + 64e, e = 0..7 (8-byte loads and stores)
         RZK_EACH_LANE {
             const LaneCtx &ctx = ctxs[li_];
-            double *E = reinterpret_cast<double *>(ctx.red);
+            uint32_t *E = ctx.red;
             const uint64_t poly = stream_poly(sc, ctx.item, (uint32_t)op.off + (uint32_t)it * op.step);
             const int32_t *src = reinterpret_cast<const int32_t *>(sc.base) + poly * kN + 2 * ctx.ridx;
             RZK_UNROLL
             for (int e = 0; e < 8; ++e) {
                 int32_t v0, v1;
                 rot_ld_pair(src + 64 * e, v0, v1);
-                const double d0 = f64_exact_i32(v0), d1 = f64_exact_i32(v1);
-                rot_st_pair(E + 512 + 2 * ctx.ridx + 64 * e, d0, d1);
-                rot_st_pair(E + 2 * ctx.ridx + 64 * e, -d0, -d1);
+                // any int32 representative works (the sum is reduced mod q at the end); only the lowest values move up by q so
+                // that 2^31 - c fits a word (lift_in: one add-and-max)
+                const uint32_t c0 = (uint32_t)lift_in(v0, K.q), c1 = (uint32_t)lift_in(v1, K.q);
+                rot_st_pair(E + 512 + 2 * ctx.ridx + 64 * e, 0x80000000u + c0, 0x80000000u + c1);
+                rot_st_pair(E + 2 * ctx.ridx + 64 * e, 0x80000000u - c0, 0x80000000u - c1);
             }
         }
-        // ---- (position, value) list of the non-zero entries of d: lane l scans the 16 bytes d[16l .. 16l+16)
-        uint32_t dw[RZK_NL][4], cnt_l[RZK_NL], pre_l[RZK_NL];
+        // ---- positions of the +1 / -1 entries of d: lane l scans the 16 bytes d[16l .. 16l+16)
+        uint32_t dw[RZK_NL][4], np_l[RZK_NL], nm_l[RZK_NL], pp_l[RZK_NL], pm_l[RZK_NL], bad_l[RZK_NL];
         RZK_EACH_LANE {
             const LaneCtx &ctx = ctxs[li_];
             const uint64_t poly = stream_poly(sd, ctx.item, 0u);
             const uint4 q = rot_ld128(reinterpret_cast<const int8_t *>(sd.base) + poly * kN + 16 * ctx.ridx);
             dw[li_][0] = q.x; dw[li_][1] = q.y; dw[li_][2] = q.z; dw[li_][3] = q.w;
-            uint32_t cnt = 0;
+            uint32_t np = 0, nm = 0, bad = 0;
             RZK_UNROLL
             for (int c = 0; c < 4; ++c) {
-                const uint32_t nz = (((dw[li_][c] & 0x7f7f7f7fu) + 0x7f7f7f7fu) | dw[li_][c]) & 0x80808080u;   // bit 7: byte != 0
+                const uint32_t w = dw[li_][c];
+                const uint32_t nz = (((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u;            // bit 7: byte != 0
+                const uint32_t neg = w & 0x80808080u;                                                   // bit 7: byte < 0
+                const uint32_t t1 = ((w & 0x7f7f7f7fu) + 0x01010101u) ^ ((w ^ 0x01010101u) & 0x80808080u);   // byte + 1 (mod 256): 0, 1, 2
+                bad |= (((t1 & 0x7f7f7f7fu) + 0x7d7d7d7du) | t1) & 0x80808080u;                         // bit 7: byte + 1 > 2
 #if defined(__CUDA_ARCH__)
-                cnt += (uint32_t)__popc(nz);
+                nm += (uint32_t)__popc(neg); np += (uint32_t)__popc(nz & ~neg);
 #else
-                cnt += (uint32_t)__builtin_popcount(nz);
+                nm += (uint32_t)__builtin_popcount(neg); np += (uint32_t)__builtin_popcount(nz & ~neg);
 #endif
             }
-            cnt_l[li_] = cnt;
+            np_l[li_] = np; nm_l[li_] = nm; bad_l[li_] = bad;
         }
-        uint32_t nnz = 0;
+        uint32_t np = 0, nm = 0, bad_any = 0;
 #if defined(__CUDA_ARCH__)
         {
-            uint32_t v = cnt_l[0];
+            // one inclusive scan for both counts (16-bit fields: at most 512 entries each)
+            uint32_t v = np_l[0] | (nm_l[0] << 16);
             RZK_UNROLL
             for (int s = 1; s < 32; s <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, v, s); if (ctxs[0].ridx >= s) v += o; }
-            pre_l[0] = v - cnt_l[0];
-            nnz = __shfl_sync(0xffffffffu, v, 31);
+            pp_l[0] = (v & 0xffffu) - np_l[0]; pm_l[0] = (v >> 16) - nm_l[0];
+            const uint32_t tot = __shfl_sync(0xffffffffu, v, 31);
+            np = tot & 0xffffu; nm = tot >> 16;
+            bad_any = __any_sync(0xffffffffu, bad_l[0] != 0) ? 1u : 0u;
         }
 #else
-        for (int li = 0; li < RZK_NL; ++li) { pre_l[li] = nnz; nnz += cnt_l[li]; }
+        for (int li = 0; li < RZK_NL; ++li) { pp_l[li] = np; pm_l[li] = nm; np += np_l[li]; nm += nm_l[li]; bad_any |= bad_l[li] ? 1u : 0u; }
 #endif
+        // lists of ROW OFFSETS (512 - pos; the row of term pos starts at E + 512 - pos); the shorter list is padded with the
+        // offset of a row of biased zeros, so that every term has a partner and one loop shape serves all of them
+        const uint32_t n_max = np > nm ? np : nm;
         RZK_EACH_LANE {
             const LaneCtx &ctx = ctxs[li_];
-            uint32_t *list = ctx.red + kRotListOff;
-            uint32_t idx = pre_l[li_];
+            uint16_t *plist = reinterpret_cast<uint16_t *>(ctx.red + kRotListOff), *mlist = plist + kN;
+            uint32_t ip = pp_l[li_], im = pm_l[li_];
             RZK_UNROLL
             for (int b = 0; b < 16; ++b) {
                 const uint32_t byte = (dw[li_][b >> 2] >> (8 * (b & 3))) & 0xffu;
-                if (byte != 0) { list[idx] = (uint32_t)(16 * ctx.ridx + b) | (byte << 16); ++idx; }
+                if (byte == 1u) plist[ip++] = (uint16_t)(512 - (16 * ctx.ridx + b));
+                else if (byte == 0xffu) mlist[im++] = (uint16_t)(512 - (16 * ctx.ridx + b));
             }
+            uint16_t *shorter = np < nm ? plist : mlist;
+            RZK_NOUNROLL
+            for (uint32_t k = (np < nm ? np : nm) + (uint32_t)ctx.ridx; k < n_max; k += 32u) shorter[k] = (uint16_t)kRotZeroOff;
+            uint32_t *zero = ctx.red + kRotZeroOff;
+            RZK_UNROLL
+            for (int e = 0; e < 16; ++e) zero[ctx.ridx + 32 * e] = 0x80000000u;
         }
         RZK_SYNC();
-        // ---- V[j] += +-d[pos] * E[512 - pos + i_j], i_j = t + 256 hw + 16 j (the epilogue coefficients of this lane)
-        const double sgn = (op.c & MAC_NEG) ? -1.0 : 1.0;
-        RZK_NOUNROLL
-        for (uint32_t k = 0; k < nnz; ++k) {
+        if (bad_any) {
+            // Not a challenge-space polynomial (an entry outside {-1, 0, 1}): the general form, still exact for any int8 d
+            // (|sum| <= 512 * 128 * 2^31 < 2^53) -- every non-zero entry is one rotation scaled by its value, the biased word
+            // un-biased first.  Three instructions per coefficient and term instead of two; honest verifiers never get here.
             RZK_EACH_LANE {
                 const LaneCtx &ctx = ctxs[li_];
-                const uint32_t e = (ctx.red + kRotListOff)[k];
-                const double s = sgn * f64_exact_i32((int32_t)(int8_t)(e >> 16));
-                const double *row = reinterpret_cast<const double *>(ctx.red) + (512u - (e & 511u)) + (uint32_t)(ctx.t + 256 * ctx.hw);
-                RZK_UNROLL
-                for (int j = 0; j < Epi<MODE>::kCount; ++j) V[li_][j] = f64_exact_fma(s, row[16 * j], V[li_][j]);
+                uint4 q;
+                q.x = dw[li_][0]; q.y = dw[li_][1]; q.z = dw[li_][2]; q.w = dw[li_][3];
+                reinterpret_cast<uint4 *>(ctx.red + kRotListOff)[ctx.ridx] = q;        // d as 512 bytes over the (unused) lists
             }
+            RZK_SYNC();
+            const double unbias = 4503599627370496.0 + 2147483648.0;
+            const double sgn = (op.c & MAC_NEG) ? -1.0 : 1.0;
+            RZK_NOUNROLL
+            for (uint32_t k = 0; k < (uint32_t)kN; ++k) {
+                const int32_t dv = (int32_t)reinterpret_cast<const int8_t *>(ctxs[0].red + kRotListOff)[k];
+                if (dv == 0) continue;
+                RZK_EACH_LANE {
+                    const LaneCtx &ctx = ctxs[li_];
+                    const double sv = sgn * f64_exact_i32(dv);
+                    const uint32_t *row = ctx.red + (512u - k) + (uint32_t)(ctx.t + 16 * ctx.hw);
+                    RZK_UNROLL
+                    for (int j = 0; j < CNT; ++j) V[li_][j] = f64_exact_fma(sv, rot_biased(row[32 * j]) - unbias, V[li_][j]);
+                }
+            }
+        } else {
+            // V -= c*d (MAC_NEG): the roles of the +1 and -1 terms swap
+            const bool neg = op.c & MAC_NEG;
+            const uint32_t off_add = neg ? (uint32_t)kN : 0u, off_sub = neg ? 0u : (uint32_t)kN;       // list offsets in uint16 entries
+            RZK_NOUNROLL
+            for (uint32_t k = 0; k < n_max; ++k) {
+                RZK_EACH_LANE {
+                    const LaneCtx &ctx = ctxs[li_];
+                    const uint16_t *list = reinterpret_cast<const uint16_t *>(ctx.red + kRotListOff);
+                    const uint32_t *ra = ctx.red + list[off_add + k] + (uint32_t)(ctx.t + 16 * ctx.hw);
+                    const uint32_t *rs = ctx.red + list[off_sub + k] + (uint32_t)(ctx.t + 16 * ctx.hw);
+                    RZK_UNROLL
+                    for (int j = 0; j < CNT; ++j) V[li_][j] = (V[li_][j] + rot_biased(ra[32 * j])) - rot_biased(rs[32 * j]);
+                }
+            }
+            // (every added word carried the bias 2^31 and every subtracted one too -- the padding rows included -- so the biases cancel)
         }
         RZK_SYNC();          // the region is free again (next item's transposes)
     }
@@ -890,8 +959,8 @@ RZK_VM void inv_core(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const 
     if (MODE != MODE_SEQ) {
         // MODE_SPLIT: half warp 0 holds residues mod p0, half warp 1 mod p1, both for all 512
         // coefficients.  MODE_SPLITKEY: half warp 0 holds the lo part, half warp 1 the hi part.
-        // Lane (h, t) finishes coefficients m in [16h, 16h+16): it keeps its own value of those
-        // and receives the partner's; it sends its values of the other half.
+        // Lane (h, t) finishes the rows m = 2j + h (epi_m): it keeps its own value of those
+        // and receives the partner's; it sends its values of the other rows.
         if (MODE == MODE_SPLITKEY) {
             RZK_EACH_LANE {
                 RZK_LANE;
@@ -904,21 +973,21 @@ RZK_VM void inv_core(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const 
 #if defined(__CUDA_ARCH__)
         RZK_UNROLL
         for (int j = 0; j < 16; ++j) {
-            const uint32_t send = ctxs[0].hw ? lanes[0].cur[j] : lanes[0].cur[16 + j];
+            const uint32_t send = ctxs[0].hw ? lanes[0].cur[2 * j] : lanes[0].cur[2 * j + 1];
             recv[0][j] = __shfl_xor_sync(0xffffffffu, send, 16);
         }
 #else
         for (int li = 0; li < RZK_NL; ++li)
             for (int j = 0; j < 16; ++j) {
                 const int partner = li ^ 16;
-                recv[li][j] = ctxs[partner].hw ? lanes[partner].cur[j] : lanes[partner].cur[16 + j];
+                recv[li][j] = ctxs[partner].hw ? lanes[partner].cur[2 * j] : lanes[partner].cur[2 * j + 1];
             }
 #endif
         RZK_EACH_LANE {
             RZK_LANE;
             RZK_UNROLL
             for (int j = 0; j < 16; ++j) {
-                const uint32_t own = ctx.hw ? L.cur[16 + j] : L.cur[j];
+                const uint32_t own = ctx.hw ? L.cur[2 * j + 1] : L.cur[2 * j];
                 const uint32_t v0 = ctx.hw ? recv[li_][j] : own;      // half warp 0's value
                 const uint32_t v1 = ctx.hw ? own : recv[li_][j];      // half warp 1's value
                 if (MODE == MODE_SPLITKEY) {
@@ -995,7 +1064,7 @@ RZK_VM int op_inv(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int q, in
         for (;; ++q) {
             const Op e = K.ops[q];
             if (e.code == OP_ADDP) { if (last) op_addp<MODE>(K, ctxs, V, e, it, K.st[e.a].dtype); }
-            else if (e.code == OP_ROT) { if (last) op_rot<MODE>(K, ctxs, V, e, it); }
+            else if (e.code == OP_ROT) { if (last) op_rot<MODE>(K, lanes, ctxs, V, e, it); }
             else if (e.code == OP_FIN) { if (last) op_fin<MODE>(K, lanes, ctxs, V, e, it); }
             else break;
         }
@@ -1255,7 +1324,7 @@ RZK_VM void sp_epilogue(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, typ
         op_addp<MODE>(K, ctxs, V, e, it, dt);
         sp_epilogue<SP, MODE, PC + 1>(K, lanes, ctxs, V, it);
     } else if constexpr (e.code == OP_ROT) {
-        op_rot<MODE>(K, ctxs, V, e, it);
+        op_rot<MODE>(K, lanes, ctxs, V, e, it);
         sp_epilogue<SP, MODE, PC + 1>(K, lanes, ctxs, V, it);
     } else if constexpr (e.code == OP_FIN) {
         op_fin<MODE>(K, lanes, ctxs, V, e, it);

@@ -307,7 +307,7 @@ int main(int argc, char **argv)
             E.stream(0, zz.data(), 3, DT_I32); E.stream(1, tt.data(), 1, DT_I32);
             E.stream(2, cc.data(), 2, DT_I32); E.stream(3, dd.data(), 1, DT_I8);
             CHECK(rot_layout_ok(E.K.ops, true), "rot layout");
-            if (rot) E.run<SPVerifyFirstRot>(B); else E.run(B);
+            if (rot) E.run<SPVerifyFirstRot>(B); else E.run(B);      // variants 6, 7: the general (DFMA) form of the rotation sum
             auto z64 = widen(zz), t64 = widen(tt), c64 = widen(cc), dd64 = widen8(dd);
             std::vector<int64_t> c1(B * N);
             for (int b = 0; b < B; ++b) for (size_t i = 0; i < N; ++i) c1[b * N + i] = rzko_center(c64[(size_t)b * 2 * N + i], Q);
@@ -318,13 +318,16 @@ int main(int argc, char **argv)
                 CHECK((okv[b] == 1) == (variant == 0), "oracle verdict variant %d", variant);
             }
         }
-        // the rotation sum itself, bit for bit: with z = 0 and t = 0 the program compares -c1*d with zero, so feed t = -c1*d
-        // (from the oracle's product) and expect "verified" for a dense int8 d, and "failed" after a one-unit change of t
+        // the rotation sum itself, bit for bit: with z = 0 the program compares -t - c1*d with zero, so feed t = -c1*d
+        // (from the oracle's product) and expect "verified" for a dense ternary d, and "failed" after a one-unit change of t
         if (rot) {
             std::vector<int32_t> zz(B * 3 * N, 0), cc(c32);
             std::vector<int8_t> dd(B * N);
-            for (auto &v : dd) v = (int8_t)((int)(rnd() % 255) - 127);
+            for (auto &v : dd) v = (int8_t)((int)(rnd() % 3) - 1);              // dense challenge: ~340 rotations, unbalanced signs
+            for (size_t i = 0; i < N; ++i) dd[i] = (i < 300) ? 1 : (i < 310 ? -1 : 0);    // item 0: 300 additions, 10 subtractions
+            for (size_t i = 0; i < N; ++i) cc[i] = (i % 3 == 0) ? INT32_MIN : (i % 3 == 1) ? INT32_MAX : (int32_t)((Q - 1) / 2);   // extreme representatives
             auto c64 = widen(cc), dd64 = widen8(dd);
+            for (auto &v : c64) v = rzko_center(v, Q);
             std::vector<int32_t> tt(B * N);
             std::vector<int64_t> prod(N);
             for (int b = 0; b < B; ++b) {
@@ -340,7 +343,7 @@ int main(int argc, char **argv)
                 pr.end(); pr.install(E.K);
                 E.stream(0, zz.data(), 3, DT_I32); E.stream(1, tt.data(), 1, DT_I32);
                 E.stream(2, cc.data(), 2, DT_I32); E.stream(3, dd.data(), 1, DT_I8);
-                E.run(B);
+                E.run<SPVerifyFirstRot>(B);
                 for (int b = 0; b < B; ++b) CHECK((E.flags[b] == 0) == (bad == 0), "rotation sum vs oracle product: item %d bad %d flags %u", b, bad, E.flags[b]);
             }
         }
