@@ -57,6 +57,12 @@ constexpr bool sp_uses_key()
     }
 }
 
+// does a compile-time program keep accumulator 1 in the global stash region (SP::kAcc1Global, rzk_programs.h)?
+template <class SP, class = void>
+struct SpAcc1Global { static constexpr bool value = false; };
+template <class SP>
+struct SpAcc1Global<SP, std::enable_if_t<!std::is_void<SP>::value && SP::kAcc1Global>> { static constexpr bool value = true; };
+
 template <int NP, int MODE, bool KEY = true>
 struct VmSmem {
     static constexpr int kKP = (MODE == MODE_SPLITKEY) ? 2 * kKeyPolys : kKeyPolys;   // key images per prime
@@ -150,8 +156,11 @@ __global__ void __launch_bounds__(VmCfg<NP, MODE>::kMaxWarps * 32, 1) rzk_vm_ker
     ctx.slot = mine + K.off_slot;
     ctx.slot_hw[0] = s_hw + (warp * 2 + 0) * K.hw_words + K.off_slot;
     ctx.slot_hw[1] = s_hw + (warp * 2 + 1) * K.hw_words + K.off_slot;
-    ctx.acc1 = mine + K.off_acc1;
     ctx.stash = K.gstash ? K.gstash + (size_t)((blockIdx.x * warps + warp) * 2 + hw) * K.stash_words : mine + K.off_stash;
+    // (decided at compile time for the unrolled programs, so that their accumulator accesses stay LDS / STS or LDG / STG)
+    if constexpr (SpAcc1Global<SP>::value) ctx.acc1 = ctx.stash;
+    else if constexpr (std::is_void<SP>::value) ctx.acc1 = K.acc1_global ? ctx.stash : mine + K.off_acc1;
+    else ctx.acc1 = mine + K.off_acc1;
     ctx.red = SPLIT ? s_hw + (warp * 2) * K.hw_words : mine;
     ctx.ridx = SPLIT ? lane : t;
     ctx.g1 = s_g1;
@@ -368,13 +377,15 @@ struct rzk_engine {
     uint32_t no_segments = 0;       //   nosegments never cut a small product sum into segments
     uint32_t no_dimg = 0;           //   nodimg     every Sum verify item transforms its challenge itself
     uint32_t no_fuse = 0;           //   nofuse     the Sum prover's two product sums as two launches
-    uint32_t no_rot = 0;            //   norot      Open verify multiplies c1*d in the NTT domain (no rotation sum)
+    uint32_t no_rot = 0;            //   norot      the verify programs multiply c1*d, c2*d in the NTT domain (no rotation sums)
+    uint32_t no_rot_w = 0;          //   norotw     only Open verify uses the rotation sum; Linear / Sum first equations multiply in the NTT domain
     // RZK_TUNE (developer A/B timing, "name=value,..."): the settings below are the measured best
     uint32_t static_respond = 0;
     uint32_t mulsum2_pp = 2;        //   mulsum2_pp phase mixing of the two-accumulator product-sum program (0 / 9 = off)
     uint32_t commit_pp = 2;         //   commit_pp  phase mixing of the split-key commitment program (0 / 9 = off)
     uint32_t ld128 = 0;             //   ld128      OP_FWD fetches int32 rows with 128-bit loads + a shared-memory redistribution (A/B)
     uint32_t verify_pp = 22;        //   verify_pp  phase mixing of the Open verify program with the rotation sum (two staggered groups)
+    uint32_t verify_w_pp = 21;      //   verify_w_pp  the same for the Linear / Sum first-equation program with two rotation sums (+2 % on Linear verify)
     uint32_t pp_mode = 0;           //   pp         phase mixing between CTA halves for every static program
     uint32_t cta_sync = 8;          //   cta_sync   lock-step barriers (rzk_vm_exec.cuh cta_lockstep): 8 = one per segment, 1 = per transform, 0 = off
 };
@@ -448,8 +459,11 @@ int launch_vm(rzk_engine *e, VmLaunch &K, cudaStream_t s, uint32_t pp_program = 
     if (K.n_items >= (1u << 28)) return fail(e, RZK_ERR_INVALID, "more than 2^28 items in one launch");
     constexpr bool SPLIT = (MODE != MODE_SEQ);
     auto kern = rzk_vm_kernel<NP, MODE, SP>;
-    if (!SPLIT && NP > 1) {
-        // residues of the earlier primes wait in global memory (one region per resident half warp, reused item after item)
+    if (SpAcc1Global<SP>::value != (K.acc1_global != 0) && !std::is_void<SP>::value)
+        return fail(e, RZK_ERR_INVALID, "program and kernel disagree on where accumulator 1 lives");
+    if ((!SPLIT && NP > 1) || K.acc1_global) {
+        // residues of the earlier primes (or the second accumulator of a program with a rotation sum) wait in global memory
+        // (one region per resident half warp, reused item after item)
         int si = kPipe;
         for (int i = 0; i < kPipe; ++i) if (e->pipe[i].stream == s) si = i;
         if (!e->d_gstash[si])
@@ -457,7 +471,8 @@ int launch_vm(rzk_engine *e, VmLaunch &K, cudaStream_t s, uint32_t pp_program = 
         K.gstash = e->d_gstash[si];
     }
     layout_hw(K, SPLIT);
-    if (!rot_layout_ok(K.ops, SPLIT)) return fail(e, RZK_ERR_INVALID, "OP_ROT needs a warp-per-item program without operand slot / second accumulator");
+    if (!rot_layout_ok(K.ops, SPLIT, K.acc1_global != 0))
+        return fail(e, RZK_ERR_INVALID, "OP_ROT needs a warp-per-item program without operand slot and without a second accumulator in shared memory");
     if (K.stash_words > kStashWordsMax) return fail(e, RZK_ERR_INVALID, "program needs more residue stash than the engine provides");
     list_prefetch(K);
     K.cta_sync = K.item_mask ? 0u : e->cta_sync;      // masked launches skip items per warp: no CTA barriers
@@ -682,7 +697,8 @@ int dev_verify_first(rzk_engine *e, size_t items, const int32_t *z, const int32_
 {
     VmLaunch K; memset(&K, 0, sizeof(K));
     Prog p;
-    const bool rot = !w && !e->no_rot;       // Open verify: c1*d as signed rotations in the epilogue (OP_ROT)
+    const bool rot = !e->no_rot && (!w || !e->no_rot_w);   // c1*d (and c2*d) as signed rotations in the epilogues (OP_ROT)
+    if (rot) dimg = nullptr;
     prog_norm_verify(p, 0);
     prog_verify_first(p, 0, 1, 2, 3, w ? 4 : -1, (w && dimg) ? 5 : -1, rot);
     p.end();
@@ -694,6 +710,7 @@ int dev_verify_first(rzk_engine *e, size_t items, const int32_t *z, const int32_
     if (w && dimg) { set_stream(K, 5, dimg, 2, DT_I32, d_div); return launch_sp<SPVerifyFirstWG>(e, K, s); }
     // (tools/ab_time.py, profiles/r2_ab_timings.log: the staggered two-group start decides for the first rotation kernel --
     // 86 -> 98.7 M/s -- and is neutral for the final one)
+    if (rot && w) return launch_sp<SPVerifyFirstWRot>(e, K, s, e->verify_w_pp);
     if (rot) return launch_sp<SPVerifyFirstRot>(e, K, s, e->verify_pp);
     return w ? launch_sp<SPVerifyFirstW>(e, K, s) : launch_sp<SPVerifyFirst>(e, K, s);
 }
@@ -849,7 +866,9 @@ int dev_sum_verify(rzk_engine *e, size_t B, uint32_t T, const int32_t *zs, const
                    const int8_t *d, uint32_t *flags, int32_t *scratch, cudaStream_t s)
 {
     int32_t *ws = scratch, *wp = scratch + B * T * kN;
-    uint32_t *dimg = e->no_dimg ? nullptr : reinterpret_cast<uint32_t *>(scratch + (B * T + B) * kN);   // T + 1 equations share d
+    // (only the NTT-domain lowering of c*d needs the challenge's image; the default adds c1*d, c2*d as rotation sums)
+    const bool ntt_cd = e->no_rot || e->no_rot_w;
+    uint32_t *dimg = (e->no_dimg || !ntt_cd) ? nullptr : reinterpret_cast<uint32_t *>(scratch + (B * T + B) * kN);   // T + 1 equations share d
     if (dimg) RZK_TRY(dev_challenge_image(e, B, d, dimg, s));
     RZK_TRY(dev_verify_first(e, B * T, zs, ts, cs, 2, d, T, ws, flags, T, s, dimg));    // sum.rs:262-268,277-291
     RZK_TRY(dev_verify_first(e, B, zp, tp, cp, 2, d, 1, wp, flags, 1, s, dimg));        // sum.rs:269,293-298
@@ -1051,7 +1070,7 @@ int rzk_create(const rzk_params *params, int device, rzk_engine **out)
     if (const char *tl = getenv("RZK_TEST_LOWERING")) {
         e->no_static = has_token(tl, "generic"); e->no_sparse = has_token(tl, "nosparse");
         e->no_segments = has_token(tl, "nosegments"); e->no_dimg = has_token(tl, "nodimg");
-        e->no_fuse = has_token(tl, "nofuse"); e->no_rot = has_token(tl, "norot");
+        e->no_fuse = has_token(tl, "nofuse"); e->no_rot = has_token(tl, "norot"); e->no_rot_w = has_token(tl, "norotw");
     }
     if (const char *tu = getenv("RZK_TUNE")) {
         auto val = [&](const char *name, uint32_t &dst) {
@@ -1060,7 +1079,7 @@ int rzk_create(const rzk_params *params, int device, rzk_engine **out)
             if (p && (p == tu || p[-1] == ',')) dst = (uint32_t)atoi(p + key.size());
         };
         val("cta_sync", e->cta_sync); val("pp", e->pp_mode); val("commit_pp", e->commit_pp);
-        val("mulsum2_pp", e->mulsum2_pp); val("static_respond", e->static_respond); val("verify_pp", e->verify_pp); val("ld128", e->ld128);
+        val("mulsum2_pp", e->mulsum2_pp); val("static_respond", e->static_respond); val("verify_pp", e->verify_pp); val("verify_w_pp", e->verify_w_pp); val("ld128", e->ld128);
     }
     Guard g(device);
     cudaDeviceProp prop;

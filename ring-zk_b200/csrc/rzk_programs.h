@@ -19,6 +19,7 @@ struct Prog {
     Op ops[kMaxOps] = {};
     int n = 0;
     uint8_t alias_slot = 0;
+    uint8_t acc1_global = 0;
     constexpr void add(uint8_t code, int a = 0, int b = 0, int c = 0, int off = 0, int step = 0)
     {
         Op &o = ops[n++];
@@ -30,6 +31,7 @@ struct Prog {
     {
         for (int i = 0; i < kMaxOps; ++i) K.ops[i] = ops[i];
         K.alias_slot = alias_slot;
+        K.acc1_global = acc1_global;
     }
 };
 
@@ -112,21 +114,31 @@ constexpr inline void prog_keymatvec(Prog &P, int sv, int st, int sw, bool check
 // With sdh >= 0 the NTT image of d comes from stream sdh (written by prog_challenge_image for the group the item
 // belongs to) instead of being transformed per item: the T terms of a Sum proof and the two first equations of a
 // Linear proof share one challenge.
-// rot = true (sw < 0 only): c1*d is not multiplied in the NTT domain but added in the epilogue as signed rotations of the row
-// c1 (OP_ROT, SURVEY kernel K4): two transforms per item (z1, z2) instead of four (d, z1, z2, c1).
+// rot = true: c1*d (and c2*d) are not multiplied in the NTT domain but added in the epilogues as signed rotations of the rows
+// c1, c2 (OP_ROT, SURVEY kernel K4): two forward transforms per item (z1, z2) instead of four / five (d, z1, z2, c1, c2).
+// With w the second accumulator waits in the half warp's global stash region (acc1_global) while the first epilogue's
+// rotation sum overlays the warp's shared-memory region.
 constexpr inline void prog_verify_first(Prog &P, int sz, int st, int sc, int sd, int sw, int sdh = -1, bool rot = false)
 {
     P.add(OP_SEG);
-    if (rot && sw < 0) {
+    if (rot) {
+        if (sw >= 0) P.acc1_global = 1;
         P.add(OP_FWD, sz, 0, 0, 1);
         P.add(OP_MACK, 0, 0, MAC_INIT);
         P.add(OP_FWD, sz, 0, 0, 2);
         P.add(OP_MACK, 0, 1, 0);
+        if (sw >= 0) P.add(OP_MACK, 1, 2, MAC_INIT);
         P.add(OP_INV, 0, 0);
         P.add(OP_ADDP, sz, 0, 0, 0);
         P.add(OP_ADDP, st, 0, MAC_NEG, 0);
         P.add(OP_ROT, sc, sd, MAC_NEG, 0);
         P.add(OP_FIN, 0, FIN_CMPZ, 0, 0);
+        if (sw >= 0) {
+            P.add(OP_INV, 1, 1);
+            P.add(OP_ADDP, sz, 0, 0, 1);
+            P.add(OP_ROT, sc, sd, MAC_NEG, 1);
+            P.add(OP_FIN, sw, FIN_STORE, 0, 0);
+        }
         return;
     }
     if (sdh < 0) {
@@ -329,6 +341,13 @@ struct SPVerifyFirstRot {        // streams: 0 = z, 1 = t, 2 = c, 3 = d (i8); c1
     static constexpr int kNP = 2, kMode = 1;
     static constexpr Prog prog = [] { Prog p; prog_norm_verify(p, 0); prog_verify_first(p, 0, 1, 2, 3, -1, -1, true); p.end(); return p; }();
     static constexpr uint8_t dtype[kMaxStreams] = {DT_I32, DT_I32, DT_I32, DT_I8};
+};
+
+struct SPVerifyFirstWRot {       // streams: 0 = z, 1 = t, 2 = c, 3 = d (i8), 4 = w out; c1*d and c2*d as signed rotations
+    static constexpr int kNP = 2, kMode = 1;
+    static constexpr bool kAcc1Global = true;
+    static constexpr Prog prog = [] { Prog p; prog_norm_verify(p, 0); prog_verify_first(p, 0, 1, 2, 3, 4, -1, true); p.end(); return p; }();
+    static constexpr uint8_t dtype[kMaxStreams] = {DT_I32, DT_I32, DT_I32, DT_I8, DT_I32};
 };
 
 struct SPVerifyFirstW {          // streams: 0 = z, 1 = t, 2 = c, 3 = d (i8), 4 = w out

@@ -158,6 +158,10 @@ struct VmLaunch {
     uint32_t stash_words;      // words of residue stash per half warp: nstash * (np - 1) * kSlotWords (MODE_SEQ, np > 1)
     uint32_t *gstash;          // device: the stash lives in global memory, [CTA][warp][half warp][stash_words]
                                // (nullptr: in the half warp's shared-memory region, host emulator)
+    uint32_t acc1_global;      // warp-per-item programs with OP_ROT and a second accumulator: accumulator 1 lives in the half
+                               // warp's global stash region (written and read back by the same lane, L2-resident) so that
+                               // the rotation sum may overlay the whole shared-memory region of the warp
+    uint32_t pad32_;
 };
 
 // What a program needs per half warp (decides how many warps fit in shared memory).
@@ -216,20 +220,21 @@ inline void layout_hw(VmLaunch &K, bool split)
     uint32_t w = kBufWords;
     if (K.alias_slot && n.slot) K.off_slot = 0;
     else { K.off_slot = w; if (n.slot) w += kSlotWords; }
-    K.off_acc1 = w;  if (n.acc1) w += kSlotWords;
-    K.stash_words = (!split && K.np > 1) ? (uint32_t)n.nstash * (K.np - 1) * kSlotWords : 0u;
+    K.off_acc1 = w;  if (n.acc1 && !K.acc1_global) w += kSlotWords;
+    K.stash_words = (!split && K.np > 1) ? (uint32_t)n.nstash * (K.np - 1) * kSlotWords : ((K.acc1_global && n.acc1) ? (uint32_t)kSlotWords : 0u);
     K.off_stash = w; if (!K.gstash) w += K.stash_words;
     // OP_ROT overlays the whole warp region (transpose buffers included: they are dead in the epilogue); programs that keep
-    // an operand slot or a second accumulator in the region cannot use it (rot_layout_ok)
+    // an operand slot or a second accumulator in the region cannot use it (rot_layout_ok; acc1_global moves the accumulator out)
     if (n.rot && w < (uint32_t)kRotHwWords) w = kRotHwWords;
     K.hw_words = w;
 }
 
-// OP_ROT needs the warp region to itself during the epilogue: warp-per-item programs without slot / second accumulator.
-inline bool rot_layout_ok(const Op *ops, bool split)
+// OP_ROT needs the warp region to itself during the epilogue: warp-per-item programs without an operand slot, and with the
+// second accumulator (if any) in the global stash region.
+inline bool rot_layout_ok(const Op *ops, bool split, bool acc1_global = false)
 {
     const ProgNeeds n = scan_needs(ops);
-    return !n.rot || (split && !n.slot && !n.acc1);
+    return !n.rot || (split && !n.slot && (!n.acc1 || acc1_global));
 }
 
 // Host-side twiddle tables for one prime (built in rzk_tables.cpp).

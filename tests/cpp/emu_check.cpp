@@ -95,6 +95,8 @@ struct Emu {
     {
         K.n_items = n_items;
         const bool split = (mode != MODE_SEQ);
+        static std::vector<uint32_t> gst;
+        if (K.acc1_global) { gst.assign((size_t)2 * kSlotWords, 0xDEADBEEFu); K.gstash = gst.data(); }   // as the kernel: accumulator 1 outside the region
         layout_hw(K, split);
         if (K.hw_words % 32 != 16) { printf("FAIL: hw_words %u not 16 mod 32\n", K.hw_words); exit(1); }
         region.assign((size_t)2 * K.hw_words, 0xDEADBEEFu);
@@ -107,7 +109,8 @@ struct Emu {
                 const int hw = li >> 4;
                 uint32_t *mine = region.data() + (size_t)hw * K.hw_words;
                 c.slot_hw[0] = region.data() + K.off_slot; c.slot_hw[1] = region.data() + K.hw_words + K.off_slot;
-                c.buf = mine; c.slot = mine + K.off_slot; c.acc1 = mine + K.off_acc1; c.stash = mine + K.off_stash;
+                c.buf = mine; c.slot = mine + K.off_slot; c.stash = K.gstash ? K.gstash + (size_t)hw * K.stash_words : mine + K.off_stash;
+                c.acc1 = K.acc1_global ? c.stash : mine + K.off_acc1;
                 c.red = split ? region.data() : mine;
                 c.ridx = split ? li : (li & 15);
                 c.g1 = g1.data(); c.g2 = g2.data(); c.key = key.data();
@@ -421,6 +424,28 @@ int main(int argc, char **argv)
                 E.run(B);
                 flags = E.flags;
                 if (variant == 0) printf("linear verify launch A: ops=%d\n", pr.n);
+            }
+            // the same first equations with c1*d, c2*d as rotation sums (OP_ROT, accumulator 1 in the global stash region):
+            // the unrolled program for (z, t, c) and the runtime-decoded one for (z', t', c'); identical flags and w, w'
+            {
+                std::vector<int32_t> wr(B * N), wrp(B * N);
+                Emu E(2, L2, keyp.data(), B);
+                SPVerifyFirstWRot::prog.install(E.K);
+                E.stream(0, zz.data(), 3, DT_I32); E.stream(1, tl_e.data(), 1, DT_I32); E.stream(2, cl_e.data(), 2, DT_I32);
+                E.stream(3, d.data(), 1, DT_I8); E.stream(4, wr.data(), 1, DT_I32);
+                CHECK(E.K.acc1_global == 1 && rot_layout_ok(E.K.ops, true, true) && !rot_layout_ok(E.K.ops, true, false), "rot layout (w)");
+                E.run<SPVerifyFirstWRot>(B);
+                Emu E2(2, L2, keyp.data(), B);
+                Prog pr;
+                prog_norm_verify(pr, 0);
+                prog_verify_first(pr, 0, 1, 2, 3, 4, -1, true);
+                pr.end(); pr.install(E2.K);
+                E2.stream(0, zzp.data(), 3, DT_I32); E2.stream(1, tp_e.data(), 1, DT_I32); E2.stream(2, cp_e.data(), 2, DT_I32);
+                E2.stream(3, d.data(), 1, DT_I8); E2.stream(4, wrp.data(), 1, DT_I32);
+                E2.run(B);
+                for (int b = 0; b < B; ++b)
+                    CHECK((E.flags[b] | E2.flags[b]) == flags[b], "linear verify, rotation sums: variant %d item %d flags %u|%u vs %u", variant, b, E.flags[b], E2.flags[b], flags[b]);
+                CHECK(wr == wv && wrp == wvp, "linear verify, rotation sums: w / w' differ from the NTT-domain lowering (variant %d)", variant);
             }
             {
                 Emu E(3, L2, keyp.data(), B);

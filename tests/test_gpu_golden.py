@@ -47,9 +47,10 @@ class EngineAdapter:
         return UB(self.e.sum_verify(*a), self.B)
 
 
-@pytest.mark.parametrize("lowering", ["", "generic,nosparse,norot,nodimg,nofuse,nosegments"])
+@pytest.mark.parametrize("lowering", ["", "generic", "norotw", "generic,nosparse,norot,nodimg,nofuse,nosegments"])
 def test_engine_matches_golden_vectors(lowering, monkeypatch):
-    """default lowering (compile-time programs, rotation kernels) and the plain one (generic interpreter, NTT products only)"""
+    """default lowering (compile-time programs, rotation kernels and rotation sums), the same programs through the generic
+    interpreter, Linear / Sum first equations without rotation sums, and the plain one (generic interpreter, NTT products only)"""
     monkeypatch.setenv("RZK_TEST_LOWERING", lowering)
     G = gc.load()
     e = engine.Engine(N=512, device=0)
