@@ -30,12 +30,12 @@ constexpr int kG1Words = 66;       // lane-uniform twiddle words per (prime, dir
                                    // (66 = 2 mod 32: the two half warps of a SPLIT warp hit different banks)
 constexpr int kKeyPolys = 3;       // non-trivial key polynomials a1'[0], a1'[1], a2'[0] at (n,k,l)=(1,3,1)
 constexpr int kMaxOps = 56;
-constexpr int kRotHwWords = 1040;  // half-warp region of a program with OP_ROT: the warp's two regions (2080 words) hold the
-                                   // extended row E = [2^31 - c | 2^31 + c] (1024 words), the row-offset lists of the +1 and
-                                   // -1 entries of d (2 x 512 uint16 = 512 words) and a row of biased zeros (512 words) that
-                                   // partners the unpaired terms; 1040 = 16 (mod 32)
-constexpr int kRotListOff = 1024;  // word offset of the lists in the warp region
-constexpr int kRotZeroOff = 1536;  // word offset of the zero row
+constexpr int kRotHwWords = 1168;  // half-warp region of a program with OP_ROT: the warp's two regions (2336 words) hold the
+                                   // extended row E = [B - c | B + c | B - c] (1536 words, B = 2^31), a row of biased zeros (512
+                                   // words) that partners the last term of an odd count, and the list of row offsets, one
+                                   // uint16 per term (256 words); 1168 = 16 (mod 32)
+constexpr int kRotZeroOff = 1536;  // word offset of the zero row in the warp region
+constexpr int kRotListOff = 2048;  // word offset of the list
 constexpr int kMaxStreams = 12;
 
 enum OpCode : uint8_t {

@@ -601,15 +601,17 @@ RZK_VM void op_fin(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, typename
 // challenge_space.rs:12-33) and c an int32 row (a commitment row), as in `c1.componentwise_mul(&d)` of the verification
 // equations (open.rs:172, linear.rs:226,232, sum.rs:287,295).  c * d = sum_k d[pos_k] * X^pos_k * c, and X^pos * c is c
 // rotated by pos with the wrapped part negated, so the product needs no multiplication at all:
-//   * the warp writes the extended row E = [2^31 - c | 2^31 + c] to shared memory as 1024 biased uint32 words (index
-//     512 + i - pos reads the rotated, sign-corrected coefficient of term pos; c is canonicalised first, |c| < 2^31);
-//   * it lists the positions of the +1 and of the -1 entries of d;
+//   * the warp writes the extended row E = [B - c | B + c | B - c] (B = 2^31) to shared memory as 1536 biased uint32 words:
+//     the 512 words from offset 512 - pos are B + (X^pos c), the 512 words from offset 1024 - pos are B - (X^pos c)
+//     (c is canonicalised first, |c| < 2^31);
+//   * it lists one row offset per non-zero entry of d, in pairs: the first term of a pair will be ADDED, so it lists the
+//     row holding B + (its contribution); the second will be SUBTRACTED, so it lists the row holding B - (its contribution).
+//     Any two terms can be partners whatever their signs; an odd count is completed by a row of biased zeros;
 //   * every lane adds its 16 epilogue coefficients (rows m = 2j + hw: the warp reads 32 consecutive words, one conflict-free
 //     wavefront) of every term with ONE 32-bit shared-memory load and ONE DADD, on the FP64 pipe the integer transforms
 //     leave idle: the loaded word u becomes the low half of the double D = 2^52 + u (high word 0x43300000, no conversion
-//     instruction), and the terms are taken in (+, -) pairs, V = (V + D+) - D-, so the 2^52 cancels at once and every
-//     intermediate is an exact integer below 2^53 (|V| < 2^38 between pairs).  When d has more +1 than -1 entries (or
-//     the reverse) the shorter list is padded with a row of biased zeros, so the biases 2^31 cancel pair by pair as well.
+//     instruction; the high words sit in registers that are written once, before the loop), and V = (V + D1) - D2 cancels
+//     2^52 and B at once, so every intermediate is an exact integer below 2^53 (|V| < 2^39 between pairs);
 // instead of two forward transforms and a pointwise product per prime.  An item whose d has an entry outside {-1, 0, 1}
 // takes a general loop (one scaled rotation per non-zero entry, DFMA), so the op is exact for every int8 d and every
 // int32 representative of c.  Warp-per-item modes only.
@@ -618,6 +620,16 @@ RZK_VM double rot_biased(uint32_t u)      // the exact double 2^52 + u
 #if defined(__CUDA_ARCH__)
     return __hiloint2double(0x43300000, (int)u);
 #else
+    return 4503599627370496.0 + (double)u;
+#endif
+}
+
+RZK_VM double rot_biased_hi(uint32_t hi, uint32_t u)      // the same with the high word 0x43300000 supplied in a register
+{
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double((int)hi, (int)u);
+#else
+    (void)hi;
     return 4503599627370496.0 + (double)u;
 #endif
 }
@@ -641,14 +653,33 @@ RZK_VM void rot_st_pair(uint32_t *p, uint32_t a, uint32_t b)           // 8-byte
 #endif
 }
 
+RZK_VM uint32_t rot_popc(uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__popc(v);
+#else
+    return (uint32_t)__builtin_popcount(v);
+#endif
+}
+
+RZK_VM uint32_t rot_ctz(uint32_t v)       // v != 0
+{
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)(__ffs((int)v) - 1);
+#else
+    return (uint32_t)__builtin_ctz(v);
+#endif
+}
+
 template <int MODE>
 RZK_VM void op_rot(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, typename Epi<MODE>::V_t (&V)[RZK_NL][Epi<MODE>::kCount], const Op &op, int it)
 {
     if constexpr (MODE != MODE_SEQ) {
         constexpr int CNT = Epi<MODE>::kCount;
         const Stream sc = K.st[op.a], sd = K.st[op.b];
+        const bool neg = op.c & MAC_NEG;          // V -= c*d: every term's sign flips
         RZK_SYNC();          // the transpose buffers this overlays are no longer read
-        // ---- E = [2^31 - c | 2^31 + c]: lane l handles the coefficient pairs 2l + 64e, e = 0..7 (8-byte loads and stores)
+        // ---- E = [B - c | B + c | B - c]: lane l handles the coefficient pairs 2l + 64e, e = 0..7 (8-byte loads and stores)
         RZK_EACH_LANE {
             const LaneCtx &ctx = ctxs[li_];
             uint32_t *E = ctx.red;
@@ -663,62 +694,64 @@ RZK_VM void op_rot(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, typename
                 const uint32_t c0 = (uint32_t)lift_in(v0, K.q), c1 = (uint32_t)lift_in(v1, K.q);
                 rot_st_pair(E + 512 + 2 * ctx.ridx + 64 * e, 0x80000000u + c0, 0x80000000u + c1);
                 rot_st_pair(E + 2 * ctx.ridx + 64 * e, 0x80000000u - c0, 0x80000000u - c1);
+                rot_st_pair(E + 1024 + 2 * ctx.ridx + 64 * e, 0x80000000u - c0, 0x80000000u - c1);
             }
         }
-        // ---- positions of the +1 / -1 entries of d: lane l scans the 16 bytes d[16l .. 16l+16)
-        uint32_t dw[RZK_NL][4], np_l[RZK_NL], nm_l[RZK_NL], pp_l[RZK_NL], pm_l[RZK_NL], bad_l[RZK_NL];
+        // ---- the non-zero entries of d: lane l scans the 16 bytes d[16l .. 16l+16) with word-parallel byte tests
+        uint32_t dw[RZK_NL][4], nzw[RZK_NL][4], cnt_l[RZK_NL], pre_l[RZK_NL], bad_l[RZK_NL];
         RZK_EACH_LANE {
             const LaneCtx &ctx = ctxs[li_];
             const uint64_t poly = stream_poly(sd, ctx.item, 0u);
             const uint4 q = rot_ld128(reinterpret_cast<const int8_t *>(sd.base) + poly * kN + 16 * ctx.ridx);
             dw[li_][0] = q.x; dw[li_][1] = q.y; dw[li_][2] = q.z; dw[li_][3] = q.w;
-            uint32_t np = 0, nm = 0, bad = 0;
+            uint32_t cnt = 0, bad = 0;
             RZK_UNROLL
             for (int c = 0; c < 4; ++c) {
                 const uint32_t w = dw[li_][c];
                 const uint32_t nz = (((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u;            // bit 7: byte != 0
-                const uint32_t neg = w & 0x80808080u;                                                   // bit 7: byte < 0
                 const uint32_t t1 = ((w & 0x7f7f7f7fu) + 0x01010101u) ^ ((w ^ 0x01010101u) & 0x80808080u);   // byte + 1 (mod 256): 0, 1, 2
                 bad |= (((t1 & 0x7f7f7f7fu) + 0x7d7d7d7du) | t1) & 0x80808080u;                         // bit 7: byte + 1 > 2
-#if defined(__CUDA_ARCH__)
-                nm += (uint32_t)__popc(neg); np += (uint32_t)__popc(nz & ~neg);
-#else
-                nm += (uint32_t)__builtin_popcount(neg); np += (uint32_t)__builtin_popcount(nz & ~neg);
-#endif
+                nzw[li_][c] = nz;
+                cnt += rot_popc(nz);
             }
-            np_l[li_] = np; nm_l[li_] = nm; bad_l[li_] = bad;
+            cnt_l[li_] = cnt; bad_l[li_] = bad;
         }
-        uint32_t np = 0, nm = 0, bad_any = 0;
+        uint32_t n_terms = 0, bad_any = 0;
 #if defined(__CUDA_ARCH__)
         {
-            // one inclusive scan for both counts (16-bit fields: at most 512 entries each)
-            uint32_t v = np_l[0] | (nm_l[0] << 16);
+            uint32_t v = cnt_l[0];          // inclusive scan over the warp
             RZK_UNROLL
             for (int s = 1; s < 32; s <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, v, s); if (ctxs[0].ridx >= s) v += o; }
-            pp_l[0] = (v & 0xffffu) - np_l[0]; pm_l[0] = (v >> 16) - nm_l[0];
-            const uint32_t tot = __shfl_sync(0xffffffffu, v, 31);
-            np = tot & 0xffffu; nm = tot >> 16;
+            pre_l[0] = v - cnt_l[0];
+            n_terms = __shfl_sync(0xffffffffu, v, 31);
             bad_any = __any_sync(0xffffffffu, bad_l[0] != 0) ? 1u : 0u;
         }
 #else
-        for (int li = 0; li < RZK_NL; ++li) { pp_l[li] = np; pm_l[li] = nm; np += np_l[li]; nm += nm_l[li]; bad_any |= bad_l[li] ? 1u : 0u; }
+        for (int li = 0; li < RZK_NL; ++li) { pre_l[li] = n_terms; n_terms += cnt_l[li]; bad_any |= bad_l[li] ? 1u : 0u; }
 #endif
-        // lists of ROW OFFSETS (512 - pos; the row of term pos starts at E + 512 - pos); the shorter list is padded with the
-        // offset of a row of biased zeros, so that every term has a partner and one loop shape serves all of them
-        const uint32_t n_max = np > nm ? np : nm;
+        const uint32_t n_pairs = (n_terms + 1u) >> 1;
+        // ---- the list: slot k holds the row offset of term k -- an even slot is added (row B + contribution), an odd slot is
+        //      subtracted (row B - contribution); the contribution of an entry s at position pos is +-s X^pos c
         RZK_EACH_LANE {
             const LaneCtx &ctx = ctxs[li_];
-            uint16_t *plist = reinterpret_cast<uint16_t *>(ctx.red + kRotListOff), *mlist = plist + kN;
-            uint32_t ip = pp_l[li_], im = pm_l[li_];
+            uint16_t *list = reinterpret_cast<uint16_t *>(ctx.red + kRotListOff);
+            uint32_t slot = pre_l[li_];
             RZK_UNROLL
-            for (int b = 0; b < 16; ++b) {
-                const uint32_t byte = (dw[li_][b >> 2] >> (8 * (b & 3))) & 0xffu;
-                if (byte == 1u) plist[ip++] = (uint16_t)(512 - (16 * ctx.ridx + b));
-                else if (byte == 0xffu) mlist[im++] = (uint16_t)(512 - (16 * ctx.ridx + b));
+            for (int c = 0; c < 4; ++c) {
+                uint32_t m = nzw[li_][c];
+                RZK_NOUNROLL
+                while (m) {
+                    const uint32_t bit = rot_ctz(m);                        // 7, 15, 23 or 31
+                    m &= m - 1u;
+                    const uint32_t pos = 16u * (uint32_t)ctx.ridx + 4u * (uint32_t)c + (bit >> 3);
+                    const uint32_t minus = ((dw[li_][c] >> bit) & 1u) ^ (neg ? 1u : 0u);    // 1: the contribution is -X^pos c
+                    // added slot: contribution row; subtracted slot: the opposite row
+                    const uint32_t far = minus ^ (slot & 1u);               // 1: the row from offset 1024 - pos (B - X^pos c)
+                    list[slot] = (uint16_t)((far ? 1024u : 512u) - pos);
+                    ++slot;
+                }
             }
-            uint16_t *shorter = np < nm ? plist : mlist;
-            RZK_NOUNROLL
-            for (uint32_t k = (np < nm ? np : nm) + (uint32_t)ctx.ridx; k < n_max; k += 32u) shorter[k] = (uint16_t)kRotZeroOff;
+            if (ctx.ridx == 0) list[n_terms] = (uint16_t)kRotZeroOff;      // partner of the last term of an odd count
             uint32_t *zero = ctx.red + kRotZeroOff;
             RZK_UNROLL
             for (int e = 0; e < 16; ++e) zero[ctx.ridx + 32 * e] = 0x80000000u;
@@ -732,11 +765,11 @@ RZK_VM void op_rot(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, typename
                 const LaneCtx &ctx = ctxs[li_];
                 uint4 q;
                 q.x = dw[li_][0]; q.y = dw[li_][1]; q.z = dw[li_][2]; q.w = dw[li_][3];
-                reinterpret_cast<uint4 *>(ctx.red + kRotListOff)[ctx.ridx] = q;        // d as 512 bytes over the (unused) lists
+                reinterpret_cast<uint4 *>(ctx.red + kRotListOff)[ctx.ridx] = q;        // d as 512 bytes over the (unused) list
             }
             RZK_SYNC();
             const double unbias = 4503599627370496.0 + 2147483648.0;
-            const double sgn = (op.c & MAC_NEG) ? -1.0 : 1.0;
+            const double sgn = neg ? -1.0 : 1.0;
             RZK_NOUNROLL
             for (uint32_t k = 0; k < (uint32_t)kN; ++k) {
                 const int32_t dv = (int32_t)reinterpret_cast<const int8_t *>(ctxs[0].red + kRotListOff)[k];
@@ -750,21 +783,33 @@ RZK_VM void op_rot(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, typename
                 }
             }
         } else {
-            // V -= c*d (MAC_NEG): the roles of the +1 and -1 terms swap
-            const bool neg = op.c & MAC_NEG;
-            const uint32_t off_add = neg ? (uint32_t)kN : 0u, off_sub = neg ? 0u : (uint32_t)kN;       // list offsets in uint16 entries
+            // the high words of the doubles 2^52 + u: one register per load slot, written once (the `volatile` keeps the
+            // compiler from re-materialising the constant next to every load inside the loop)
+            uint32_t hi_a[CNT], hi_s[CNT];
+            RZK_UNROLL
+            for (int j = 0; j < CNT; ++j) {
+#if defined(__CUDA_ARCH__)
+                // (item < 2^28, so the shifted term is 0 -- but only at run time: a plain constant would be re-materialised
+                // by a move in front of every load, which is what this avoids)
+                hi_a[j] = 0x43300000u | ((ctxs[0].item + (uint32_t)j) >> 31);
+                hi_s[j] = 0x43300000u | ((ctxs[0].item + (uint32_t)(CNT + j)) >> 31);
+#else
+                hi_a[j] = hi_s[j] = 0x43300000u;
+#endif
+            }
             RZK_NOUNROLL
-            for (uint32_t k = 0; k < n_max; ++k) {
+            for (uint32_t k = 0; k < n_pairs; ++k) {
                 RZK_EACH_LANE {
                     const LaneCtx &ctx = ctxs[li_];
-                    const uint16_t *list = reinterpret_cast<const uint16_t *>(ctx.red + kRotListOff);
-                    const uint32_t *ra = ctx.red + list[off_add + k] + (uint32_t)(ctx.t + 16 * ctx.hw);
-                    const uint32_t *rs = ctx.red + list[off_sub + k] + (uint32_t)(ctx.t + 16 * ctx.hw);
+                    const uint32_t both = (ctx.red + kRotListOff)[k];       // slots 2k (added) and 2k + 1 (subtracted)
+                    const uint32_t *ra = ctx.red + (both & 0xffffu) + (uint32_t)(ctx.t + 16 * ctx.hw);
+                    const uint32_t *rs = ctx.red + (both >> 16) + (uint32_t)(ctx.t + 16 * ctx.hw);
                     RZK_UNROLL
-                    for (int j = 0; j < CNT; ++j) V[li_][j] = (V[li_][j] + rot_biased(ra[32 * j])) - rot_biased(rs[32 * j]);
+                    for (int j = 0; j < CNT; ++j)
+                        V[li_][j] = (V[li_][j] + rot_biased_hi(hi_a[j], ra[32 * j])) - rot_biased_hi(hi_s[j], rs[32 * j]);
                 }
             }
-            // (every added word carried the bias 2^31 and every subtracted one too -- the padding rows included -- so the biases cancel)
+            // (every added word carried the bias 2^31 and every subtracted one too -- the zero row included -- so the biases cancel)
         }
         RZK_SYNC();          // the region is free again (next item's transposes)
     }
