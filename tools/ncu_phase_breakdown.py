@@ -1,8 +1,15 @@
-import csv, subprocess, re, sys, json
+"""Where a kernel's instructions and stall samples go along its (straight-line) program, phase by phase (read without a GPU).
+usage: python tools/ncu_phase_breakdown.py <report.ncu-rep> [annotated_sass.txt]
+Walks the SASS in address order (the compile-time programs are straight-line code, so address order is program order),
+labels every instruction with the program phase of the source function ncu maps it to (forward transform, key product,
+inverse transform, plain terms, rotation sum, ...; leaf helpers such as shoup_mul inherit the phase they are inlined into)
+and prints executed warp instructions and stall samples per segment and per phase.  Needs -lineinfo and --import-source on."""
+import csv, subprocess, re, sys, json, os
 from collections import defaultdict, OrderedDict
-sys.path.insert(0, "/root/repo/tools")
-from ncu_source_breakdown import function_ranges
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from ncu_source_breakdown import function_ranges, load_report_sources
 rep = sys.argv[1]
+load_report_sources(rep)
 raw = subprocess.run(["ncu","-i",rep,"--page","source","--csv","--print-source","cuda,sass"],capture_output=True,text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 addr = {}

@@ -11,13 +11,33 @@ import sys
 from collections import defaultdict
 
 
+_REPORT_SOURCES = {}
+
+
+def load_report_sources(rep):
+    """The CUDA sources as imported into the report (--import-source on), so that line numbers match the profiled build."""
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda"], capture_output=True, text=True).stdout
+    cur = None
+    for r in csv.reader(raw.splitlines()):
+        if not r:
+            continue
+        if r[0] in ("File Name", "File Path"):
+            cur = r[1]; _REPORT_SOURCES[cur] = {}
+        elif cur is not None and len(r) >= 2 and r[0].isdigit():
+            _REPORT_SOURCES[cur][int(r[0])] = r[1]
+
+
 def function_ranges(path):
     """[(first_line, name)] of function definitions in a source file (good enough for this code base's style)."""
     out = []
-    try:
-        lines = open(path).read().splitlines()
-    except OSError:
-        return out
+    if path in _REPORT_SOURCES and _REPORT_SOURCES[path]:
+        src = _REPORT_SOURCES[path]
+        lines = [src.get(i, "") for i in range(1, max(src) + 1)]
+    else:
+        try:
+            lines = open(path).read().splitlines()
+        except OSError:
+            return out
     pat = re.compile(r'^\s*(?:RZK_VM|RZK_HD|RZK_D|__device__|__global__|static|inline|constexpr)\b.*?\b([A-Za-z_][A-Za-z0-9_]*)\s*\(')
     for i, ln in enumerate(lines, 1):
         if ln.startswith((' ', '\t')) and not ln.lstrip().startswith(('RZK_', '__device__', '__global__')):
@@ -30,6 +50,7 @@ def function_ranges(path):
 
 def main():
     rep = sys.argv[1]
+    load_report_sources(rep)
     raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
