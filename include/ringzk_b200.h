@@ -226,6 +226,65 @@ int rzk_sample_small_dev(rzk_engine *e, size_t n_polys, int32_t b, uint64_t seed
 int rzk_sample_gaussian_dev(rzk_engine *e, size_t n_polys, double sigma, uint64_t seed, uint32_t tag, int32_t *out, void *stream);
 int rzk_sample_challenge_dev(rzk_engine *e, size_t n_items, int32_t kappa, uint64_t seed, uint32_t tag, int8_t *out, void *stream);
 
+/* ---------------------------------------------------------------- wire format of the messages
+ * The reference's own encoding of a batch of messages, packed and parsed on the device: bincode 1.3 (the crate's serde test,
+ * mat.rs:424-438: little endian, fixed-width integers, u64 sequence lengths, one tag byte per Option, struct fields in
+ * declaration order) of the derive(Serialize) layouts of commit.rs:134-141,222-235, prove/open.rs:180-228,
+ * prove/linear.rs:256-315 and prove/sum.rs:327-391.  Mat = Vec<Vec<Polynomial>> (mat.rs:11-17); a Polynomial is the
+ * length-prefixed sequence of its coefficients -- mat.rs:434 pins 8 + 8 + (8 + 3*4) = 36 bytes for the 1 x 1 matrix
+ * [1 + 2X + 3X^2] over i32.  The serde impls of Polynomial / ZqI64 live in the absent dependency poly-ring-xnp1, so two facts
+ * are parameters, not assumptions: `trim` (1: trailing zero coefficients are not stored -- the reading that reproduces the
+ * 36 bytes; 0: always N coefficients) and `elem_bytes` (8: ZqI64's i64; 4: i32 as in the pinned test).
+ *
+ * A message kind is a list of tokens (rzk_wire_layout); its polynomials come from / go to numbered streams, which are the
+ * arrays of the protocol entry points above (device pointers, [B][polys_per_item][N]):
+ *   RZK_MSG_COMMITMENT         0 = c [2]
+ *   RZK_MSG_OPENING            0 = x [1], 1 = r [3] (i8)                  f = None      RZK_MSG_OPENING_F: + 2 = f [1] (i8)
+ *   RZK_MSG_OPEN_COMMITMENT    0 = c [2], 1 = t [1]
+ *   RZK_MSG_CHALLENGE          0 = d [1] (i8)                            (Open, Linear and Sum challenges are the same struct)
+ *   RZK_MSG_OPEN_RESPONSE      0 = z [3]
+ *   RZK_MSG_LINEAR_COMMITMENT  0 = c [2], 1 = cp [2], 2 = g [1], 3 = t [1], 4 = tp [1], 5 = u [1]
+ *   RZK_MSG_LINEAR_RESPONSE    0 = z [3], 1 = zp [3]     (linear.rs:318 lacks the derive: the layout it WOULD have -- an extension)
+ *   RZK_MSG_SUM_COMMITMENT     0 = cp [2], 1 = cs [T*2], 2 = gs [T], 3 = tp [1], 4 = ts [T], 5 = u [1]
+ *   RZK_MSG_SUM_RESPONSE       0 = zp [3], 1 = zs [T*3]
+ * The contexts (ResponseContext / VerificationContext) never cross the wire in the protocol and are not offered.
+ * Pack: item i occupies bytes [offsets[i], offsets[i+1]) of `out`; offsets is a device array of B + 1 words that the call
+ * fills, *total_bytes (host) = offsets[B].  out == NULL only computes offsets and the total.  Unpack: offsets is an input
+ * (the transport knows the message boundaries); every literal is checked and flags[i] |= 1 marks a malformed item
+ * (wrong length or tag, a polynomial longer than N, a coefficient that does not fit an int8 stream, bytes missing or left
+ * over); coefficients are canonicalised like ZqI64::from.  Both calls synchronise `stream` before they return. */
+enum { RZK_WIRE_END = 0, RZK_WIRE_LEN = 1 /* u64 `value` */, RZK_WIRE_POLY = 2 /* polynomial `poly` of `stream` */, RZK_WIRE_TAG = 3 /* byte `value` */ };
+typedef struct { uint32_t kind, stream, poly, value; } rzk_wire_tok;
+typedef struct { const void *base; uint32_t polys_per_item; uint32_t dtype; /* 0 = int32, 1 = int8 */ } rzk_wire_stream;
+enum { RZK_MSG_COMMITMENT = 1, RZK_MSG_OPENING, RZK_MSG_OPENING_F, RZK_MSG_OPEN_COMMITMENT, RZK_MSG_CHALLENGE, RZK_MSG_OPEN_RESPONSE,
+       RZK_MSG_LINEAR_COMMITMENT, RZK_MSG_LINEAR_RESPONSE, RZK_MSG_SUM_COMMITMENT, RZK_MSG_SUM_RESPONSE };
+/* Token list of a message kind (T: terms of a Sum proof, ignored otherwise).  toks == NULL: *ntoks = the length needed.  No GPU involved. */
+int rzk_wire_layout(int message_kind, uint32_t T, rzk_wire_tok *toks, size_t cap, size_t *ntoks);
+int rzk_wire_pack_dev(rzk_engine *e, size_t B, const rzk_wire_tok *toks, size_t ntoks, const rzk_wire_stream *streams, int nstreams,
+                      int elem_bytes, int trim, uint8_t *out, size_t out_capacity, uint64_t *offsets, uint64_t *total_bytes, void *stream);
+int rzk_wire_unpack_dev(rzk_engine *e, size_t B, const rzk_wire_tok *toks, size_t ntoks, const rzk_wire_stream *streams, int nstreams,
+                        int elem_bytes, const uint8_t *in, const uint64_t *offsets, uint32_t *flags, void *stream);
+
+/* ---------------------------------------------------------------- Fiat-Shamir challenges on the device
+ * NOT in the reference, which is interactive (open.rs:143-158 draws d from the verifier's RNG; README.md:16 names the
+ * transform as a possibility).  docs/FIAT_SHAMIR.md specifies the transcript:
+ *     d_i = SampleInBall_kappa( SHAKE128( prefix || polynomials of item i's first message ) )
+ * every polynomial absorbed as N little-endian int32 canonical centred coefficients (int8 streams are widened), the segments
+ * in the order given -- for the three protocols, the field order of the commitment struct (open.rs:190-198: c, t;
+ * linear.rs:271-285: c, cp, g, t, tp, u; sum.rs:342-355: cp, cs, gs, tp, ts, u).  `prefix` (host pointer, a multiple of
+ * 8 bytes: domain tag, key digest, shape words -- built by the caller, see the document) separates protocols, keys and shapes.
+ * kappa <= 64.  Bit-reproducible on the host with any SHAKE128 (oracle/fs_ref.py uses hashlib).
+ *   rzk_fs_challenge_dev          d [B][N] i8 from the transcript segments (device arrays [B][polys_per_item][N])
+ *   rzk_open_prove_fs_batch_dev   commit (open.rs:80-103) -> challenge -> response (open.rs:107-117) on one stream without a host
+ *                                 round trip: outputs c [B][2][N], t [B][N], d [B][N] i8, z [B][3][N]; flags as for the `_dev` calls
+ *   rzk_open_verify_fs_batch_dev  recomputes d from (c, t) into the caller's buffer, then open.rs:162-174 */
+int rzk_fs_challenge_dev(rzk_engine *e, size_t B, const uint8_t *prefix, size_t prefix_len, const rzk_wire_stream *segs, int nsegs,
+                         int8_t *d, void *stream);
+int rzk_open_prove_fs_batch_dev(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r, const int32_t *y, const uint8_t *prefix,
+                                size_t prefix_len, int32_t *c, int32_t *t, int8_t *d, int32_t *z, uint32_t *flags, void *stream);
+int rzk_open_verify_fs_batch_dev(rzk_engine *e, size_t B, const int32_t *c, const int32_t *t, const int32_t *z, const uint8_t *prefix,
+                                 size_t prefix_len, int8_t *d, uint32_t *flags, void *stream);
+
 /* Counters for the benchmark harness: kernels launched by this engine since creation. */
 uint64_t rzk_kernel_launches(const rzk_engine *e);
 

@@ -155,6 +155,31 @@ class CommitmentKey:  # commit.rs:19-60
         return Opening(np.stack(x), r[0], None), Commitment(c[0])
 
 
+# --------------------------------------------------------------------------- Fiat-Shamir transcript prefix (docs/FIAT_SHAMIR.md)
+
+def fs_key_digest(ck: "CommitmentKey") -> bytes:
+    """SHAKE128-256 of the key's random blocks a11 || a12 || a22 as int32 LE canonical centred coefficients"""
+    import hashlib
+    h = hashlib.shake_128()
+    half = (Q_DEFAULT - 1) // 2
+    for p in (ck.a1[0, 1], ck.a1[0, 2], ck.a2[0, 2]):
+        c = np.fmod(np.asarray(p, np.int64), Q_DEFAULT)
+        c = np.where(c > half, c - Q_DEFAULT, np.where(c < -half, c + Q_DEFAULT, c))
+        h.update(c.astype("<i4").tobytes())
+    return h.digest(32)
+
+
+def fs_prefix(tag: str, ck: "CommitmentKey", params: Params, T: int = 0, session: bytes = b"") -> bytes:
+    """tag (32 bytes, zero padded) || key digest (32) || q u64 || N u32 || kappa u32 || T u32 || b u32 || session (8-byte aligned)"""
+    import struct
+    t = tag.encode()
+    assert len(t) <= 32 and len(session) % 8 == 0
+    return t.ljust(32, b"\0") + fs_key_digest(ck) + struct.pack("<QIIII", params.Q, ck.N, params.kappa, T, params.b) + session
+
+
+FS_TAG_OPEN, FS_TAG_LINEAR, FS_TAG_SUM = "ring-zk/fs/open/v1", "ring-zk/fs/linear/v1", "ring-zk/fs/sum/v1"
+
+
 # --------------------------------------------------------------------------- Open proof (prove/open.rs)
 
 @dataclass
@@ -206,6 +231,27 @@ class OpenProofProver:
         """open.rs:107-117"""
         return self.ck.engine.open_respond(np.ascontiguousarray(y), np.ascontiguousarray(r), np.ascontiguousarray(d))
 
+    def prove_batch_fs(self, rng, X, session: bytes = b""):
+        """Non-interactive Open proofs (docs/FIAT_SHAMIR.md; NOT in the reference): commit -> challenge from the transcript ->
+        response, chained on the device without a host round trip.  Returns dict(x, r, y) (the openings, host) and the
+        proofs dict(c, t, z) as device tensors (d is recomputed by the verifier)."""
+        import torch
+        P, N, e = self.params, self.ck.N, self.ck.engine
+        X = np.ascontiguousarray(X, dtype=np.int32)
+        assert X.shape[1] == P.l
+        B = X.shape[0]
+        r = P.sample_small(rng, (B,), N)
+        y = P.sample_gaussian(rng, (B,), N)
+        dev = torch.device("cuda", e.device)
+        T = lambda a: torch.from_numpy(a).to(dev)
+        E = lambda *sh, dt=torch.int32: torch.empty(sh, dtype=dt, device=dev)
+        c, t, z, d = E(B, 2, N), E(B, 1, N), E(B, 3, N), E(B, N, dt=torch.int8)
+        flags = torch.zeros(B, dtype=torch.int32, device=dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        e.open_prove_fs(T(X), T(r), T(y), fs_prefix(FS_TAG_OPEN, self.ck, P, session=session), c, t, d, z, flags, stream=st)
+        assert not flags.any(), "commit constraint / range check failed (redraw r, y)"
+        return dict(x=X, r=r, y=y), dict(c=c, t=t, z=z)
+
     def commit(self, rng, x):
         s = self.commit_batch(rng, np.stack(x)[None])
         return (OpenProofResponseContext(Opening(s["x"][0], s["r"][0]), s["y"][0]),
@@ -229,6 +275,18 @@ class OpenProofVerifier:
         bm = self.ck.engine.open_verify(np.ascontiguousarray(z), np.ascontiguousarray(t),
                                         np.ascontiguousarray(c1), np.ascontiguousarray(d))
         return _engine.unpack_bitmap(bm, B)
+
+    def verify_batch_fs(self, proofs, session: bytes = b""):
+        """Verifies non-interactive Open proofs dict(c, t, z) (device tensors): d from the transcript, then open.rs:162-174."""
+        import torch
+        e = self.ck.engine
+        c, t, z = proofs["c"], proofs["t"], proofs["z"]
+        B = c.shape[0]
+        d = torch.empty((B, self.ck.N), dtype=torch.int8, device=c.device)
+        flags = torch.zeros(B, dtype=torch.int32, device=c.device)
+        e.open_verify_fs(c, t, z, fs_prefix(FS_TAG_OPEN, self.ck, self.params, session=session), d, flags,
+                         stream=torch.cuda.current_stream(c.device).cuda_stream)
+        return (flags & 1).eq(0).cpu().numpy()
 
     def generate_challenge(self, rng, commitment: OpenProofCommitment):
         d = self.generate_challenge_batch(rng, 1)[0]

@@ -25,7 +25,7 @@ _ERRNAMES = {1: "RZK_ERR_INVALID", 2: "RZK_ERR_UNSUPPORTED", 3: "RZK_ERR_CUDA", 
 
 SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("rzk_engine.cu", "rzk_tables.cpp")]
 HEADERS = [os.path.join(_HERE, "csrc", f) for f in
-           ("rzk_arith.cuh", "rzk_vm.h", "rzk_vm_exec.cuh", "rzk_programs.h", "rzk_tables.h", "rzk_sparse.cuh", "rzk_sample.cuh")] + \
+           ("rzk_arith.cuh", "rzk_vm.h", "rzk_vm_exec.cuh", "rzk_programs.h", "rzk_tables.h", "rzk_sparse.cuh", "rzk_sample.cuh", "rzk_wire.cuh")] + \
           [os.path.join(_ROOT, "include", "ringzk_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
               "-Xcompiler", "-fPIC", "--shared"]
@@ -103,7 +103,9 @@ _GROUP_SIGS = {n.replace("rzk_", "rzk_group_", 1): _SIGS[n] for n in _GROUP_HOST
 EXPORTS = sorted(list(_SIGS) + list(_GROUP_SIGS) + ["rzk_group_create", "rzk_group_destroy", "rzk_group_size", "rzk_group_last_error",
                                                     "rzk_group_set_key", "rzk_group_kernel_launches"] + ["rzk_default_params", "rzk_create", "rzk_destroy", "rzk_last_error", "rzk_device",
                                 "rzk_sigma", "rzk_commit_bound", "rzk_verify_bound", "rzk_small_limit",
-                                "rzk_set_key", "rzk_host_alloc", "rzk_host_free", "rzk_kernel_launches"])
+                                "rzk_set_key", "rzk_host_alloc", "rzk_host_free", "rzk_kernel_launches",
+                                "rzk_wire_layout", "rzk_wire_pack_dev", "rzk_wire_unpack_dev",
+                                "rzk_fs_challenge_dev", "rzk_open_prove_fs_batch_dev", "rzk_open_verify_fs_batch_dev"])
 
 
 def lib():
@@ -155,8 +157,49 @@ def lib():
     L.rzk_group_set_key.argtypes = [_VP, _VP, _VP]
     L.rzk_group_kernel_launches.restype = C.c_uint64
     L.rzk_group_kernel_launches.argtypes = [_VP]
+    L.rzk_wire_layout.restype = C.c_int
+    L.rzk_wire_layout.argtypes = [C.c_int, C.c_uint32, _VP, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.rzk_wire_pack_dev.restype = C.c_int
+    L.rzk_wire_pack_dev.argtypes = [_VP, C.c_size_t, _VP, C.c_size_t, _VP, C.c_int, C.c_int, C.c_int, _VP, C.c_size_t, _VP,
+                                    C.POINTER(C.c_uint64), _VP]
+    L.rzk_wire_unpack_dev.restype = C.c_int
+    L.rzk_wire_unpack_dev.argtypes = [_VP, C.c_size_t, _VP, C.c_size_t, _VP, C.c_int, C.c_int, _VP, _VP, _VP, _VP]
+    L.rzk_fs_challenge_dev.restype = C.c_int
+    L.rzk_fs_challenge_dev.argtypes = [_VP, C.c_size_t, C.c_char_p, C.c_size_t, _VP, C.c_int, _VP, _VP]
+    L.rzk_open_prove_fs_batch_dev.restype = C.c_int
+    L.rzk_open_prove_fs_batch_dev.argtypes = [_VP, C.c_size_t, _VP, _VP, _VP, C.c_char_p, C.c_size_t, _VP, _VP, _VP, _VP, _VP, _VP]
+    L.rzk_open_verify_fs_batch_dev.restype = C.c_int
+    L.rzk_open_verify_fs_batch_dev.argtypes = [_VP, C.c_size_t, _VP, _VP, _VP, C.c_char_p, C.c_size_t, _VP, _VP, _VP]
     _lib = L
     return L
+
+
+# ---- wire format (include/ringzk_b200.h, "wire format of the messages") ----
+class WireTok(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("stream", C.c_uint32), ("poly", C.c_uint32), ("value", C.c_uint32)]
+
+
+class WireStream(C.Structure):
+    _fields_ = [("base", _VP), ("polys_per_item", C.c_uint32), ("dtype", C.c_uint32)]
+
+
+WIRE_END, WIRE_LEN, WIRE_POLY, WIRE_TAG = range(4)
+(MSG_COMMITMENT, MSG_OPENING, MSG_OPENING_F, MSG_OPEN_COMMITMENT, MSG_CHALLENGE, MSG_OPEN_RESPONSE, MSG_LINEAR_COMMITMENT,
+ MSG_LINEAR_RESPONSE, MSG_SUM_COMMITMENT, MSG_SUM_RESPONSE) = range(1, 11)
+
+
+def wire_layout(kind: int, T: int = 0):
+    """Token list of a message kind (rzk_wire_layout; host logic only, no GPU): list of (kind, stream, poly, value)."""
+    L = lib()
+    n = C.c_size_t(0)
+    rc = L.rzk_wire_layout(kind, T, None, 0, C.byref(n))
+    if rc != RZK_OK:
+        raise RzkError(rc, "rzk_wire_layout: unknown message kind or T out of range")
+    toks = (WireTok * n.value)()
+    rc = L.rzk_wire_layout(kind, T, toks, n.value, C.byref(n))
+    if rc != RZK_OK:
+        raise RzkError(rc, "rzk_wire_layout")
+    return [(t.kind, t.stream, t.poly, t.value) for t in toks]
 
 
 def _ptr(a, dtype=None):
@@ -206,7 +249,10 @@ class Engine:
     def _call(self, name, *args):
         rc = getattr(self.L, name)(self.h, *args)
         if rc != RZK_OK:
-            raise RzkError(rc, (self.L.rzk_last_error(self.h) or b"").decode())
+            raise RzkError(rc, self.last_error())
+
+    def last_error(self):
+        return (self.L.rzk_last_error(self.h) or b"").decode()
 
     # ---- scalars ----
     @property
@@ -362,6 +408,72 @@ class Engine:
 
     def sync(self, stream=0):
         self._call("rzk_sync", stream)
+
+    # ---- Fiat-Shamir challenges on the device (docs/FIAT_SHAMIR.md) ----
+    def fs_challenge(self, prefix: bytes, segs, d, stream=0):
+        """d [B][N] int8 (device) = SampleInBall(SHAKE128(prefix || segs...)), one hash per item."""
+        import torch
+        cs = (WireStream * len(segs))()
+        for i, a in enumerate(segs):
+            cs[i] = WireStream(a.data_ptr(), int(np.prod(a.shape[1:-1])) if a.dim() > 2 else 1, 1 if a.dtype == torch.int8 else 0)
+        rc = self.L.rzk_fs_challenge_dev(self.h, segs[0].shape[0], prefix, len(prefix), cs, len(cs), d.data_ptr(), stream)
+        if rc != RZK_OK:
+            raise RzkError(rc, self.last_error())
+
+    def open_prove_fs(self, x, r, y, prefix: bytes, c, t, d, z, flags, stream=0):
+        rc = self.L.rzk_open_prove_fs_batch_dev(self.h, x.shape[0], _ptr(x), _ptr(r), _ptr(y), prefix, len(prefix), _ptr(c), _ptr(t),
+                                                _ptr(d), _ptr(z), _ptr(flags), stream)
+        if rc != RZK_OK:
+            raise RzkError(rc, self.last_error())
+
+    def open_verify_fs(self, c, t, z, prefix: bytes, d, flags, stream=0):
+        rc = self.L.rzk_open_verify_fs_batch_dev(self.h, c.shape[0], _ptr(c), _ptr(t), _ptr(z), prefix, len(prefix), _ptr(d), _ptr(flags), stream)
+        if rc != RZK_OK:
+            raise RzkError(rc, self.last_error())
+
+    # ---- wire format: device tensors in, device bytes out (and back) ----
+    @staticmethod
+    def _wire_args(kind, T, streams):
+        toks = wire_layout(kind, T)
+        ctoks = (WireTok * len(toks))(*[WireTok(*t) for t in toks])
+        cs = (WireStream * len(streams))()
+        for i, a in enumerate(streams):
+            import torch
+            if a.dtype not in (torch.int32, torch.int8) or not a.is_contiguous():
+                raise TypeError("wire streams are contiguous int32 / int8 device tensors [B][polys][N]")
+            cs[i] = WireStream(a.data_ptr(), int(np.prod(a.shape[1:-1])) if a.dim() > 2 else 1, 1 if a.dtype == torch.int8 else 0)
+        return ctoks, cs
+
+    def wire_pack(self, kind, streams, T=0, elem_bytes=8, trim=True, stream=0):
+        """Messages of `kind` for the B items of `streams` (device tensors, numbered as in the header) in the reference's
+        bincode layout: returns (bytes: uint8 device tensor, offsets: int64 device tensor of B + 1 entries)."""
+        import torch
+        B = streams[0].shape[0]
+        ctoks, cs = self._wire_args(kind, T, streams)
+        offsets = torch.empty(B + 1, dtype=torch.int64, device=streams[0].device)
+        total = C.c_uint64(0)
+        args = (self.h, B, ctoks, len(ctoks), cs, len(cs), elem_bytes, 1 if trim else 0)
+        rc = self.L.rzk_wire_pack_dev(*args, None, 0, offsets.data_ptr(), C.byref(total), stream)
+        if rc != RZK_OK:
+            raise RzkError(rc, self.last_error())
+        out = torch.empty(max(int(total.value), 1), dtype=torch.uint8, device=streams[0].device)
+        rc = self.L.rzk_wire_pack_dev(*args, out.data_ptr(), int(total.value), offsets.data_ptr(), C.byref(total), stream)
+        if rc != RZK_OK:
+            raise RzkError(rc, self.last_error())
+        return out[: int(total.value)], offsets
+
+    def wire_unpack(self, kind, data, offsets, streams, T=0, elem_bytes=8, stream=0):
+        """Parses B messages (uint8 device tensor + int64 offsets [B + 1]) into the preallocated `streams`;
+        returns the per-item flags (bit 0: malformed)."""
+        import torch
+        B = offsets.numel() - 1
+        ctoks, cs = self._wire_args(kind, T, streams)
+        flags = torch.zeros(max(B, 1), dtype=torch.int32, device=data.device)
+        rc = self.L.rzk_wire_unpack_dev(self.h, B, ctoks, len(ctoks), cs, len(cs), elem_bytes, data.data_ptr(), offsets.data_ptr(),
+                                        flags.data_ptr(), stream)
+        if rc != RZK_OK:
+            raise RzkError(rc, self.last_error())
+        return flags[:B]
 
 
 def unpack_bitmap(bm, B):
