@@ -579,7 +579,38 @@ def main():
                 prove_e2e(devr, 2 + i)
             res[name] = world * Bp * ksteps / (time.perf_counter() - t0)
         assert int(fE.any()) == 0
-        del xd, rd, yd, dd, cE, tE, zE, xh, rh, yh, dh, ch2, th2, zh2
+        # ---- rows f1 + f2 chained: messages arrive from the host (2 KB per item), r and y are drawn on the device, the proof
+        # (commit -> Fiat-Shamir challenge -> response, docs/FIAT_SHAMIR.md) and its verification run back to back on one
+        # stream, and only the verdict bitmap (1 bit per item) goes back: nothing but x and the bitmap crosses PCIe
+        api = importlib.import_module("ring-zk_b200.api")
+        pre = b"ring-zk/fs/open/v1".ljust(32, b"\0") + bytes(32) + bytes(24)          # tag || (benchmark: zero key digest) || shape words
+        d8, d8v = torch.empty((Bp, N), dtype=torch.int8, device=dev), torch.empty((Bp, N), dtype=torch.int8, device=dev)
+        fV = torch.zeros_like(flags)
+        bmd = torch.zeros((Bp + 7) // 8, dtype=torch.uint8, device=dev)
+        bmh = torch.zeros((Bp + 7) // 8, dtype=torch.uint8).pin_memory()
+
+        def chain_step(seed):
+            xd.copy_(xh, non_blocking=True)
+            eng.dev("sample_small", 3 * Bp, 1, seed, 1, rd, stream=stream)
+            eng.dev("sample_gaussian", 3 * Bp, sig, seed, 2, yd, stream=stream)
+            fE.zero_(); fV.zero_()
+            eng.open_prove_fs(xd, rd, yd, pre, cE, tE, d8, zE, fE, stream=stream)
+            eng.open_verify_fs(cE, tE, zE, pre, d8v, fV, stream=stream)
+            eng.dev("flags_to_bitmap", Bp, fV, bmd, rng_word, stream=stream)
+            bmh.copy_(bmd, non_blocking=True)
+            torch.cuda.synchronize()
+        chain_step(1)
+        l0 = eng.kernel_launches()
+        t0 = time.perf_counter()
+        for i in range(ksteps):
+            chain_step(100 + i)
+        dt_chain = time.perf_counter() - t0
+        assert int(fE.any()) == 0 and bool((bmh == 0xFF).all()) and bool((d8 == d8v).all()), "chained non-interactive proofs must verify"
+        extras["open_fs_chain_e2e"] = {
+            "instances_per_s": world * Bp * ksteps / dt_chain, "unit": "non-interactive open proofs proved AND verified/s, host messages in, verdict bitmap out",
+            "h2d_bytes_per_item": 4 * N, "d2h_bytes_per_item": 0.125, "kernel_launches_per_step": (eng.kernel_launches() - l0) / ksteps,
+            "note": "rzk_sample_*_dev (test-only samplers) + rzk_open_prove_fs_batch_dev + rzk_open_verify_fs_batch_dev on one stream"}
+        del xd, rd, yd, dd, cE, tE, zE, xh, rh, yh, dh, ch2, th2, zh2, d8, d8v
         extras["open_prove_e2e"] = {"instances_per_s": res, "unit": "open proofs (commit + response)/s, host buffers in and out",
                                     "h2d_bytes_per_item": {"host_randomness": 4 * N + 3 * N + 12 * N + N, "device_randomness": 4 * N + N},
                                     "d2h_bytes_per_item": 8 * N + 4 * N + 12 * N}

@@ -310,22 +310,30 @@ constexpr inline void prog_mulsum2(Prog &P, int T, int sa, int sb, int sc, int s
     P.add(OP_FIN, sout1, FIN_STORE, 0, 0);
 }
 
+#ifndef RZK_PRELOAD
+#define RZK_PRELOAD 0      // plain-term rows fetched ahead of each inverse transform by the warp-per-item programs: measured NO gain
+                           // (profiles/r2_ab_timings.log: 150.6 M commitments/s with 0, 1 and 2 rows; the verify kernels spill with 2), so off
+#endif
+
 // ---- compile-time program descriptors (vm_run_static) --------------------------------------
 // Stream numbering is the one the engine's dev_* helpers use for the same programs.
 
 struct SPCommitSplitKey {        // streams: 0 = x (i32), 1 = r (i8), 2 = c out
+    static constexpr int kPreload = RZK_PRELOAD;
     static constexpr int kNP = 1, kMode = 2 /* MODE_SPLITKEY */;
     static constexpr Prog prog = [] { Prog p; prog_commit_splitkey(p, 0, 1, 2, false); p.end(); return p; }();
     static constexpr uint8_t dtype[kMaxStreams] = {DT_I32, DT_I8, DT_I32};
 };
 
 struct SPKeyMatVecT {            // streams: 0 = y (i32), 1 = t out
+    static constexpr int kPreload = RZK_PRELOAD;
     static constexpr int kNP = 2, kMode = 1 /* MODE_SPLIT */;
     static constexpr Prog prog = [] { Prog p; prog_keymatvec(p, 0, 1, -1, true); p.end(); return p; }();
     static constexpr uint8_t dtype[kMaxStreams] = {DT_I32, DT_I32};
 };
 
 struct SPKeyMatVecTW {           // streams: 0 = y, 1 = t out, 2 = w out
+    static constexpr int kPreload = RZK_PRELOAD;
     static constexpr int kNP = 2, kMode = 1;
     static constexpr Prog prog = [] { Prog p; prog_keymatvec(p, 0, 1, 2, true); p.end(); return p; }();
     static constexpr uint8_t dtype[kMaxStreams] = {DT_I32, DT_I32, DT_I32};
@@ -338,12 +346,14 @@ struct SPVerifyFirst {           // streams: 0 = z, 1 = t, 2 = c, 3 = d (i8)
 };
 
 struct SPVerifyFirstRot {        // streams: 0 = z, 1 = t, 2 = c, 3 = d (i8); c1*d as signed rotations (OP_ROT)
+    static constexpr int kPreload = RZK_PRELOAD;
     static constexpr int kNP = 2, kMode = 1;
     static constexpr Prog prog = [] { Prog p; prog_norm_verify(p, 0); prog_verify_first(p, 0, 1, 2, 3, -1, -1, true); p.end(); return p; }();
     static constexpr uint8_t dtype[kMaxStreams] = {DT_I32, DT_I32, DT_I32, DT_I8};
 };
 
 struct SPVerifyFirstWRot {       // streams: 0 = z, 1 = t, 2 = c, 3 = d (i8), 4 = w out; c1*d and c2*d as signed rotations
+    static constexpr int kPreload = RZK_PRELOAD;
     static constexpr int kNP = 2, kMode = 1;
     static constexpr bool kAcc1Global = true;
     static constexpr Prog prog = [] { Prog p; prog_norm_verify(p, 0); prog_verify_first(p, 0, 1, 2, 3, 4, -1, true); p.end(); return p; }();

@@ -539,34 +539,51 @@ template <int MODE>
 // warp instruction) and 32 consecutive words of the rotation sum's extended row (OP_ROT: one conflict-free wavefront).
 RZK_VM int epi_m(const LaneCtx &ctx, int j) { return (MODE != MODE_SEQ) ? (2 * j + ctx.hw) : j; }
 
+// OP_ADDP in two halves: the loads (issued BEFORE the inverse transform by the compile-time programs, so that their latency
+// -- an L2 hit, ~300 cycles -- is covered by the butterflies instead of stalling the epilogue) and the accumulation.
 template <int MODE>
-RZK_VM void op_addp(const VmLaunch &K, const LaneCtx *ctxs, typename Epi<MODE>::V_t (&V)[RZK_NL][Epi<MODE>::kCount], const Op &op, int it, uint32_t dtype)
+RZK_VM void op_addp_load(const VmLaunch &K, const LaneCtx *ctxs, int32_t (&v)[RZK_NL][Epi<MODE>::kCount], const Op &op, int it, uint32_t dtype)
 {
     constexpr int CNT = Epi<MODE>::kCount;
     const Stream st = K.st[op.a];
-    const bool neg = op.c & MAC_NEG;
     RZK_EACH_LANE {
         const LaneCtx &ctx = ctxs[li_];
         const int t = ctx.t;
         const uint64_t poly = stream_poly(st, ctx.item, (uint32_t)op.off + (uint32_t)it * op.step);
-        int32_t v[CNT];
         if (dtype == DT_I8) {
             const int8_t *src = reinterpret_cast<const int8_t *>(st.base) + poly * kN;
             RZK_UNROLL
-            for (int j = 0; j < CNT; ++j) v[j] = src[t + kLanes * epi_m<MODE>(ctx, j)];
+            for (int j = 0; j < CNT; ++j) v[li_][j] = src[t + kLanes * epi_m<MODE>(ctx, j)];
         } else {
             const int32_t *src = reinterpret_cast<const int32_t *>(st.base) + poly * kN;
             RZK_UNROLL
-            for (int j = 0; j < CNT; ++j) v[j] = src[t + kLanes * epi_m<MODE>(ctx, j)];   // any representative: reduced in OP_FIN
-        }
-        if constexpr (MODE != MODE_SEQ) {
-            RZK_UNROLL
-            for (int j = 0; j < CNT; ++j) V[li_][j] += neg ? -f64_exact_i32(v[j]) : f64_exact_i32(v[j]);
-        } else {
-            RZK_UNROLL
-            for (int j = 0; j < CNT; ++j) V[li_][j] += neg ? -(int64_t)v[j] : (int64_t)v[j];
+            for (int j = 0; j < CNT; ++j) v[li_][j] = src[t + kLanes * epi_m<MODE>(ctx, j)];   // any representative: reduced in OP_FIN
         }
     }
+}
+
+template <int MODE>
+RZK_VM void op_addp_apply(typename Epi<MODE>::V_t (&V)[RZK_NL][Epi<MODE>::kCount], const int32_t (&v)[RZK_NL][Epi<MODE>::kCount], const Op &op)
+{
+    constexpr int CNT = Epi<MODE>::kCount;
+    const bool neg = op.c & MAC_NEG;
+    RZK_EACH_LANE {
+        if constexpr (MODE != MODE_SEQ) {
+            RZK_UNROLL
+            for (int j = 0; j < CNT; ++j) V[li_][j] += neg ? -f64_exact_i32(v[li_][j]) : f64_exact_i32(v[li_][j]);
+        } else {
+            RZK_UNROLL
+            for (int j = 0; j < CNT; ++j) V[li_][j] += neg ? -(int64_t)v[li_][j] : (int64_t)v[li_][j];
+        }
+    }
+}
+
+template <int MODE>
+RZK_VM void op_addp(const VmLaunch &K, const LaneCtx *ctxs, typename Epi<MODE>::V_t (&V)[RZK_NL][Epi<MODE>::kCount], const Op &op, int it, uint32_t dtype)
+{
+    int32_t v[RZK_NL][Epi<MODE>::kCount];
+    op_addp_load<MODE>(K, ctxs, v, op, it, dtype);
+    op_addp_apply<MODE>(V, v, op);
 }
 
 template <int MODE>
@@ -1334,6 +1351,12 @@ RZK_VM void vm_run_item(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs)
 // compile time and the kernel body is straight-line code.  K.loop_count replaces the immediate of
 // OP_LOOP (the number of Sum-proof terms is only known at launch).
 
+// how many plain-term rows a compile-time program fetches ahead of each inverse transform (SP::kPreload, default 0)
+template <class SP, class = void>
+struct SpPreload { static constexpr int value = 0; };
+template <class SP>
+struct SpPreload<SP, std::void_t<decltype(SP::kPreload)>> { static constexpr int value = SP::kPreload; };
+
 constexpr int sp_find_endloop(const Prog &p, int pc)
 {
     while (p.ops[pc].code != OP_ENDLOOP) ++pc;
@@ -1377,6 +1400,49 @@ RZK_VM void sp_epilogue(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, typ
     }
 }
 
+// Plain terms of an epilogue, fetched before the inverse transform that precedes it (warp-per-item modes): at most kMaxPre
+// OP_ADDP rows are held in registers across the transform, the others are loaded in place as before.
+constexpr int kMaxPre = 2;
+
+constexpr int sp_count_addp(const Prog &p, int pc)
+{
+    int n = 0;
+    while (p.ops[pc].code == OP_ADDP || p.ops[pc].code == OP_FIN || p.ops[pc].code == OP_ROT) { if (p.ops[pc].code == OP_ADDP) ++n; ++pc; }
+    return n;
+}
+
+template <class SP, int MODE, int PC, int IDX, int NPRE>
+RZK_VM void sp_preload(const VmLaunch &K, const LaneCtx *ctxs, int32_t (&pre)[NPRE > 0 ? NPRE : 1][RZK_NL][Epi<MODE>::kCount], int it)
+{
+    constexpr Op e = SP::prog.ops[PC];
+    if constexpr (e.code == OP_ADDP) {
+        constexpr uint32_t dt = SP::dtype[e.a];
+        if constexpr (IDX < NPRE) op_addp_load<MODE>(K, ctxs, pre[IDX], e, it, dt);
+        sp_preload<SP, MODE, PC + 1, IDX + 1, NPRE>(K, ctxs, pre, it);
+    } else if constexpr (e.code == OP_ROT || e.code == OP_FIN) {
+        sp_preload<SP, MODE, PC + 1, IDX, NPRE>(K, ctxs, pre, it);
+    }
+}
+
+template <class SP, int MODE, int PC, int IDX, int NPRE>
+RZK_VM void sp_epilogue_pre(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, typename Epi<MODE>::V_t (&V)[RZK_NL][Epi<MODE>::kCount],
+                            const int32_t (&pre)[NPRE > 0 ? NPRE : 1][RZK_NL][Epi<MODE>::kCount], int it)
+{
+    constexpr Op e = SP::prog.ops[PC];
+    if constexpr (e.code == OP_ADDP) {
+        constexpr uint32_t dt = SP::dtype[e.a];
+        if constexpr (IDX < NPRE) op_addp_apply<MODE>(V, pre[IDX], e);
+        else op_addp<MODE>(K, ctxs, V, e, it, dt);
+        sp_epilogue_pre<SP, MODE, PC + 1, IDX + 1, NPRE>(K, lanes, ctxs, V, pre, it);
+    } else if constexpr (e.code == OP_ROT) {
+        op_rot<MODE>(K, lanes, ctxs, V, e, it);
+        sp_epilogue_pre<SP, MODE, PC + 1, IDX, NPRE>(K, lanes, ctxs, V, pre, it);
+    } else if constexpr (e.code == OP_FIN) {
+        op_fin<MODE>(K, lanes, ctxs, V, e, it);
+        sp_epilogue_pre<SP, MODE, PC + 1, IDX, NPRE>(K, lanes, ctxs, V, pre, it);
+    }
+}
+
 constexpr int sp_skip_epilogue(const Prog &p, int pc)
 {
     while (p.ops[pc].code == OP_ADDP || p.ops[pc].code == OP_FIN || p.ops[pc].code == OP_ROT) ++pc;
@@ -1400,6 +1466,13 @@ RZK_VM void sp_exec(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int it,
         constexpr int next = sp_skip_epilogue(SP::prog, PC + 1);
         {
             typename Epi<MODE>::V_t V[RZK_NL][Epi<MODE>::kCount];
+            if constexpr (MODE != MODE_SEQ && SpPreload<SP>::value > 0) {
+                constexpr int NPRE = sp_count_addp(SP::prog, PC + 1) < SpPreload<SP>::value ? sp_count_addp(SP::prog, PC + 1) : SpPreload<SP>::value;
+                int32_t pre[NPRE > 0 ? NPRE : 1][RZK_NL][Epi<MODE>::kCount];
+                sp_preload<SP, MODE, PC + 1, 0, NPRE>(K, ctxs, pre, it);
+                inv_core<NP, MODE>(K, lanes, ctxs, op, prime_iter, V);
+                sp_epilogue_pre<SP, MODE, PC + 1, 0, NPRE>(K, lanes, ctxs, V, pre, it);
+            } else {
             inv_core<NP, MODE>(K, lanes, ctxs, op, prime_iter, V);
             if constexpr (ChunkedEpi<NP, MODE>::value) {
                 if (prime_iter == NP - 1) {
@@ -1411,6 +1484,7 @@ RZK_VM void sp_exec(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int it,
                     }
                 }
             } else if ((MODE != MODE_SEQ) || prime_iter == NP - 1) sp_epilogue<SP, MODE, PC + 1>(K, lanes, ctxs, V, it);
+            }
         }
         sp_exec<SP, NP, MODE, next>(K, lanes, ctxs, it, prime_iter);
     } else {
