@@ -4,7 +4,7 @@ else going on?  Pinned buffers, one stream per direction per GPU: the ceiling of
     python tools/pcie_duplex.py                                            # one GPU
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 tools/pcie_duplex.py
                                                                             # all GPUs copying at the same time
-    ... tools/pcie_duplex.py --numa                                        # ranks bound to their GPU's NUMA node (as bench.py)
+    RZK_BIND_NUMA=1 ... tools/pcie_duplex.py                               # ranks bound to their GPU's NUMA node (as bench.py)
 
 Prints one JSON line (rank 0): per-GPU and aggregate GB/s, and the commitments/s ceiling they imply."""
 import json
@@ -20,7 +20,7 @@ world = int(os.environ.get("WORLD_SIZE", "1"))
 rank = int(os.environ.get("RANK", "0"))
 local = int(os.environ.get("LOCAL_RANK", "0"))
 numa = None
-if "--numa" in sys.argv:
+if os.environ.get("RZK_BIND_NUMA"):
     import bench
     numa = bench.bind_to_gpu_numa(local)
 torch.cuda.set_device(local)
