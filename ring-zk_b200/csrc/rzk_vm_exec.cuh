@@ -379,8 +379,8 @@ RZK_VM void mac_key(uint32_t (&acc)[kElems], const uint32_t (&cur)[kElems], cons
             const int e = 4 * j + c;
             uint32_t tt = shoup_mul(ww[c], wwp[c], cur[e], p);
             if (neg) tt = p2 - tt;
-            const uint32_t base = init ? 0u : acc[e];
-            acc[e] = csub(base + tt, p2);
+            // (a first, positive term is already in [0, 2p): no correction)
+            acc[e] = (init && !neg) ? tt : csub((init ? 0u : acc[e]) + tt, p2);
         }
     }
 }
@@ -400,8 +400,7 @@ RZK_VM void mac_var(uint32_t (&acc)[kElems], const uint32_t (&cur)[kElems], cons
             const int e = 4 * j + c;
             uint32_t tt = mont_mul(csub(cur[e], p2), ss[c], p, pinv);
             if (neg) tt = p2 - tt;
-            const uint32_t base = init ? 0u : acc[e];
-            acc[e] = csub(base + tt, p2);
+            acc[e] = (init && !neg) ? tt : csub((init ? 0u : acc[e]) + tt, p2);
         }
     }
 }
@@ -419,10 +418,10 @@ RZK_VM void mac_key_smem(uint32_t *acc1, const uint32_t (&cur)[kElems], const ui
         const uint4 w = w4[j], wp = wp4[j];
         uint4 a = a4[j * kLanes + t];
         uint32_t tt;
-        tt = shoup_mul(w.x, wp.x, cur[4 * j + 0], p); if (neg) tt = p2 - tt; a.x = csub((init ? 0u : a.x) + tt, p2);
-        tt = shoup_mul(w.y, wp.y, cur[4 * j + 1], p); if (neg) tt = p2 - tt; a.y = csub((init ? 0u : a.y) + tt, p2);
-        tt = shoup_mul(w.z, wp.z, cur[4 * j + 2], p); if (neg) tt = p2 - tt; a.z = csub((init ? 0u : a.z) + tt, p2);
-        tt = shoup_mul(w.w, wp.w, cur[4 * j + 3], p); if (neg) tt = p2 - tt; a.w = csub((init ? 0u : a.w) + tt, p2);
+        tt = shoup_mul(w.x, wp.x, cur[4 * j + 0], p); if (neg) tt = p2 - tt; a.x = (init && !neg) ? tt : csub((init ? 0u : a.x) + tt, p2);
+        tt = shoup_mul(w.y, wp.y, cur[4 * j + 1], p); if (neg) tt = p2 - tt; a.y = (init && !neg) ? tt : csub((init ? 0u : a.y) + tt, p2);
+        tt = shoup_mul(w.z, wp.z, cur[4 * j + 2], p); if (neg) tt = p2 - tt; a.z = (init && !neg) ? tt : csub((init ? 0u : a.z) + tt, p2);
+        tt = shoup_mul(w.w, wp.w, cur[4 * j + 3], p); if (neg) tt = p2 - tt; a.w = (init && !neg) ? tt : csub((init ? 0u : a.w) + tt, p2);
         a4[j * kLanes + t] = a;
     }
 }
@@ -438,10 +437,10 @@ RZK_VM void mac_var_smem(uint32_t *acc1, const uint32_t (&cur)[kElems], const ui
         const uint4 s = s4[j * kLanes + t];
         uint4 a = a4[j * kLanes + t];
         uint32_t tt;
-        tt = mont_mul(csub(cur[4 * j + 0], p2), s.x, p, pinv); if (neg) tt = p2 - tt; a.x = csub((init ? 0u : a.x) + tt, p2);
-        tt = mont_mul(csub(cur[4 * j + 1], p2), s.y, p, pinv); if (neg) tt = p2 - tt; a.y = csub((init ? 0u : a.y) + tt, p2);
-        tt = mont_mul(csub(cur[4 * j + 2], p2), s.z, p, pinv); if (neg) tt = p2 - tt; a.z = csub((init ? 0u : a.z) + tt, p2);
-        tt = mont_mul(csub(cur[4 * j + 3], p2), s.w, p, pinv); if (neg) tt = p2 - tt; a.w = csub((init ? 0u : a.w) + tt, p2);
+        tt = mont_mul(csub(cur[4 * j + 0], p2), s.x, p, pinv); if (neg) tt = p2 - tt; a.x = (init && !neg) ? tt : csub((init ? 0u : a.x) + tt, p2);
+        tt = mont_mul(csub(cur[4 * j + 1], p2), s.y, p, pinv); if (neg) tt = p2 - tt; a.y = (init && !neg) ? tt : csub((init ? 0u : a.y) + tt, p2);
+        tt = mont_mul(csub(cur[4 * j + 2], p2), s.z, p, pinv); if (neg) tt = p2 - tt; a.z = (init && !neg) ? tt : csub((init ? 0u : a.z) + tt, p2);
+        tt = mont_mul(csub(cur[4 * j + 3], p2), s.w, p, pinv); if (neg) tt = p2 - tt; a.w = (init && !neg) ? tt : csub((init ? 0u : a.w) + tt, p2);
         a4[j * kLanes + t] = a;
     }
 }
