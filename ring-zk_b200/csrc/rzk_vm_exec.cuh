@@ -970,7 +970,8 @@ RZK_VM void op_fin_chunk(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, in
 // values live only inside this function.  Returns the index of the first op after the epilogue.
 template <int NP, int MODE>
 RZK_VM void inv_core(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const Op &op, int prime_iter,
-                     typename Epi<MODE>::V_t (&V)[RZK_NL][Epi<MODE>::kCount])
+                     typename Epi<MODE>::V_t (&V)[RZK_NL][Epi<MODE>::kCount],
+                     const int32_t (*small)[Epi<MODE>::kCount] = nullptr)
 {
     constexpr int CNT = Epi<MODE>::kCount;
     RZK_SYNC();      // every OP_LD of the partner half warp has finished (the slot may overlay this buffer)
@@ -1052,7 +1053,10 @@ RZK_VM void inv_core(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const 
                 const uint32_t v0 = ctx.hw ? recv[li_][j] : own;      // half warp 0's value
                 const uint32_t v1 = ctx.hw ? own : recv[li_][j];      // half warp 1's value
                 if (MODE == MODE_SPLITKEY) {
-                    V[li_][j % CNT] = f64_exact_fma(f64_exact_i32((int32_t)v1), 65536.0, f64_exact_i32((int32_t)v0));
+                    // `small`: an int8 plain term of the epilogue (the r0 / r1 row of a commitment) joins the lo part as an
+                    // integer (|lo| < 2^29, |small| < 2^7): one add instead of a conversion and a DADD
+                    const int32_t lo = small ? (int32_t)v0 + small[li_][j % CNT] : (int32_t)v0;
+                    V[li_][j % CNT] = f64_exact_fma(f64_exact_i32((int32_t)v1), 65536.0, f64_exact_i32(lo));
                 } else {
                     V[li_][j % CNT] = crt2_mod_q_f64(K, v0, v1);
                 }
@@ -1465,7 +1469,14 @@ RZK_VM void sp_exec(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int it,
         constexpr int next = sp_skip_epilogue(SP::prog, PC + 1);
         {
             typename Epi<MODE>::V_t V[RZK_NL][Epi<MODE>::kCount];
-            if constexpr (MODE != MODE_SEQ && SpPreload<SP>::value > 0) {
+            if constexpr (MODE == MODE_SPLITKEY && SP::prog.ops[PC + 1].code == OP_ADDP && SP::dtype[SP::prog.ops[PC + 1].a] == DT_I8 &&
+                          !(SP::prog.ops[PC + 1].c & MAC_NEG)) {
+                constexpr Op e0 = SP::prog.ops[PC + 1];
+                int32_t small[RZK_NL][Epi<MODE>::kCount];
+                op_addp_load<MODE>(K, ctxs, small, e0, it, DT_I8);
+                inv_core<NP, MODE>(K, lanes, ctxs, op, prime_iter, V, small);
+                sp_epilogue<SP, MODE, PC + 2>(K, lanes, ctxs, V, it);
+            } else if constexpr (MODE != MODE_SEQ && SpPreload<SP>::value > 0) {
                 constexpr int NPRE = sp_count_addp(SP::prog, PC + 1) < SpPreload<SP>::value ? sp_count_addp(SP::prog, PC + 1) : SpPreload<SP>::value;
                 int32_t pre[NPRE > 0 ? NPRE : 1][RZK_NL][Epi<MODE>::kCount];
                 sp_preload<SP, MODE, PC + 1, 0, NPRE>(K, ctxs, pre, it);
