@@ -89,7 +89,13 @@ def main():
         bad = rng.random(B) < 0.3
         u2 = a["u"].copy(); u2[bad, ..., 11] += 1
         ts2 = a["ts"].copy(); ts2[bad, T - 1, ..., 3] -= 1
-        for args2 in ([zs, zp, a["cs"], a["cp"], gs, a["ts"], a["tp"], u2, d], [zs, zp, a["cs"], a["cp"], gs, ts2, a["tp"], a["u"], d]):
+        # (a changed c1 / c2 row and a changed challenge go through the rotation sums of the first equations)
+        cs2 = a["cs"].copy(); cs2[bad, int(rng.integers(0, T)), int(rng.integers(0, 2)), int(rng.integers(0, N))] += 1
+        cp2 = a["cp"].copy(); cp2[bad, 1, int(rng.integers(0, N))] -= 1
+        d2 = d.copy(); d2[bad, int(rng.integers(0, N))] ^= 1
+        for args2 in ([zs, zp, a["cs"], a["cp"], gs, a["ts"], a["tp"], u2, d], [zs, zp, a["cs"], a["cp"], gs, ts2, a["tp"], a["u"], d],
+                      [zs, zp, cs2, a["cp"], gs, a["ts"], a["tp"], a["u"], d], [zs, zp, a["cs"], cp2, gs, a["ts"], a["tp"], a["u"], d],
+                      [zs, zp, a["cs"], a["cp"], gs, a["ts"], a["tp"], a["u"], d2]):
             v1, v2 = UB(e0.sum_verify(*args2), B), UB(plain.sum_verify(*args2), B)
             assert (v1 == ~bad).all() and (v2 == ~bad).all(), ("sum_verify tampered", B, T)
         if T == 1:
@@ -97,6 +103,12 @@ def main():
             la, lb = e0.linear_commit(g, x, rp, rs[:, 0], ys[:, 0], yp), plain.linear_commit(g, x, rp, rs[:, 0], ys[:, 0], yp)
             for k in ("gx", "cp", "c", "t", "tp", "u"):
                 assert (la[k] == lb[k]).all(), ("linear_commit", k, B)
+            z, zq = e0.linear_respond(ys[:, 0], yp, rs[:, 0], rp, d)
+            c2t = la["c"].copy(); c2t[bad, 1, int(rng.integers(0, N))] += 1
+            for cc, dd, want in ((la["c"], d, np.ones(B, bool)), (c2t, d, ~bad), (la["c"], d2, ~bad)):
+                largs = [z, zq, cc, la["cp"], g, la["t"], la["tp"], la["u"], dd]
+                v1, v2 = UB(e0.linear_verify(*largs), B), UB(plain.linear_verify(*largs), B)
+                assert (v1 == want).all() and (v2 == want).all(), ("linear_verify", B)
         print(f"sum round {it:3d} B={B:6d} T={T} ok", flush=True)
     plain.close()
     for e in engines.values():
