@@ -250,8 +250,8 @@ int rzk_sample_challenge_dev(rzk_engine *e, size_t n_items, int32_t kappa, uint6
  * The contexts (ResponseContext / VerificationContext) never cross the wire in the protocol and are not offered.
  * Pack: item i occupies bytes [offsets[i], offsets[i+1]) of `out`; offsets is a device array of B + 1 words that the call
  * fills, *total_bytes (host) = offsets[B].  out == NULL only computes offsets and the total.  Unpack: offsets is an input
- * (the transport knows the message boundaries); every literal is checked and flags[i] |= 1 marks a malformed item
- * (wrong length or tag, a polynomial longer than N, a coefficient that does not fit an int8 stream, bytes missing or left
+ * (the transport knows the message boundaries; an item whose offsets leave the `in_bytes` of the buffer or run backwards is
+ * malformed and is not read); every literal is checked and flags[i] |= 1 marks a malformed item (wrong length or tag, a polynomial longer than N, a coefficient that does not fit an int8 stream, bytes missing or left
  * over); coefficients are canonicalised like ZqI64::from.  Both calls synchronise `stream` before they return. */
 enum { RZK_WIRE_END = 0, RZK_WIRE_LEN = 1 /* u64 `value` */, RZK_WIRE_POLY = 2 /* polynomial `poly` of `stream` */, RZK_WIRE_TAG = 3 /* byte `value` */ };
 typedef struct { uint32_t kind, stream, poly, value; } rzk_wire_tok;
@@ -263,7 +263,7 @@ int rzk_wire_layout(int message_kind, uint32_t T, rzk_wire_tok *toks, size_t cap
 int rzk_wire_pack_dev(rzk_engine *e, size_t B, const rzk_wire_tok *toks, size_t ntoks, const rzk_wire_stream *streams, int nstreams,
                       int elem_bytes, int trim, uint8_t *out, size_t out_capacity, uint64_t *offsets, uint64_t *total_bytes, void *stream);
 int rzk_wire_unpack_dev(rzk_engine *e, size_t B, const rzk_wire_tok *toks, size_t ntoks, const rzk_wire_stream *streams, int nstreams,
-                        int elem_bytes, const uint8_t *in, const uint64_t *offsets, uint32_t *flags, void *stream);
+                        int elem_bytes, const uint8_t *in, size_t in_bytes, const uint64_t *offsets, uint32_t *flags, void *stream);
 
 /* ---------------------------------------------------------------- Fiat-Shamir challenges on the device
  * NOT in the reference, which is interactive (open.rs:143-158 draws d from the verifier's RNG; README.md:16 names the

@@ -359,6 +359,8 @@ struct rzk_engine {
     int32_t *d_partial[kPipe + 1] = {};   // segment results of product sums cut into segments (small batches), per stream as above
     uint32_t *d_need = nullptr;     // hand-over words of dev_respond for the `_dev` entry points
     size_t need_cap = 0;
+    void *d_wire_toks = nullptr;    // token list of the wire-format calls (rzk_wire.cuh)
+    size_t wire_toks_cap = 0;
     uint8_t *d_fs_prefix = nullptr; // transcript prefix of the Fiat-Shamir entry points (rzk_fs.cuh)
     size_t fs_prefix_cap = 0;
     uint32_t *d_misc = nullptr;     // [0] range word, [1] dummy flags word
@@ -1131,6 +1133,7 @@ void rzk_destroy(rzk_engine *e)
     if (e->d_keytab2) cudaFree(e->d_keytab2);
     if (e->d_need) cudaFree(e->d_need);
     if (e->d_fs_prefix) cudaFree(e->d_fs_prefix);
+    if (e->d_wire_toks) cudaFree(e->d_wire_toks);
     for (auto p : e->d_gstash) if (p) cudaFree(p);
     for (auto p : e->d_partial) if (p) cudaFree(p);
     if (e->d_misc) cudaFree(e->d_misc);

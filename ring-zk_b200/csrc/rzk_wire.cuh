@@ -31,6 +31,7 @@ struct WireLaunch {
     uint8_t *bytes;                         // packed messages
     uint64_t *sizes;                        // pack pass 1: bytes of every item
     const uint64_t *offsets;                // [n_items + 1]
+    uint64_t in_bytes;                      // unpack: length of `bytes`
     uint32_t *flags;                        // unpack: FLAG_FAIL = malformed item
     int64_t q;
 };
@@ -143,10 +144,11 @@ __global__ void __launch_bounds__(256) rzk_wire_unpack_kernel(const __grid_const
     const uint32_t lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
     const int64_t half = (K.q - 1) / 2;
     for (uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < K.n_items; item += warps) {
-        const uint8_t *in = K.bytes + K.offsets[item];
-        const uint64_t size = K.offsets[item + 1] - K.offsets[item];
+        const uint64_t o0 = K.offsets[item], o1 = K.offsets[item + 1];
+        uint32_t bad = (o1 < o0 || o1 > K.in_bytes) ? 1u : 0u;          // offsets that leave the buffer: nothing of the item is read
+        const uint8_t *in = K.bytes + (bad ? 0 : o0);
+        const uint64_t size = bad ? 0 : o1 - o0;
         uint64_t pos = 0;
-        uint32_t bad = 0;
         for (uint32_t q = 0; q < K.ntoks && !bad; ++q) {
             const rzk_wire_tok t = K.toks[q];
             if (t.kind == RZK_WIRE_LEN) {
@@ -217,7 +219,15 @@ int wire_fill(rzk_engine *e, WireLaunch &K, size_t B, const rzk_wire_tok *toks, 
         if (streams[s].dtype > DT_I8) return fail(e, RZK_ERR_INVALID, "wire: stream dtype is 0 (int32) or 1 (int8)");
         K.base[s] = streams[s].base; K.polys[s] = streams[s].polys_per_item; K.dtype[s] = streams[s].dtype;
     }
-    RZK_CUDA(e, cudaMalloc(d_toks, ntoks * sizeof(rzk_wire_tok)));
+    if (ntoks * sizeof(rzk_wire_tok) > e->wire_toks_cap) {            // token list staged in a buffer the engine keeps
+        RZK_CUDA(e, cudaDeviceSynchronize());
+        if (e->d_wire_toks) cudaFree(e->d_wire_toks);
+        e->d_wire_toks = nullptr; e->wire_toks_cap = 0;
+        const size_t cap = std::max<size_t>(ntoks * sizeof(rzk_wire_tok), 16384);
+        RZK_CUDA(e, cudaMalloc(&e->d_wire_toks, cap));
+        e->wire_toks_cap = cap;
+    }
+    *d_toks = reinterpret_cast<rzk_wire_tok *>(e->d_wire_toks);
     K.toks = *d_toks; K.ntoks = (uint32_t)ntoks; K.n_items = (uint32_t)B;
     K.elem_bytes = (uint32_t)elem_bytes; K.trim = trim ? 1u : 0u; K.q = e->P.q;
     return RZK_OK;
@@ -293,16 +303,14 @@ int rzk_wire_pack_dev(rzk_engine *e, size_t B, const rzk_wire_tok *toks, size_t 
         if (*total_bytes > out_capacity) return fail(e, RZK_ERR_INVALID, "wire: output buffer too small (total_bytes holds the size needed)");
         K.bytes = out; K.offsets = offsets;
         if (B) { rzk_wire_pack_kernel<true><<<grid, 256, 0, s>>>(K); RZK_CUDA(e, cudaGetLastError()); e->launches++; }
-        RZK_CUDA(e, cudaStreamSynchronize(s));                 // the token list is freed below
+        RZK_CUDA(e, cudaStreamSynchronize(s));
         return RZK_OK;
     };
-    const int rc = body();
-    cudaFree(d_toks);
-    return rc;
+    return body();
 }
 
 int rzk_wire_unpack_dev(rzk_engine *e, size_t B, const rzk_wire_tok *toks, size_t ntoks, const rzk_wire_stream *streams, int nstreams,
-                        int elem_bytes, const uint8_t *in, const uint64_t *offsets, uint32_t *flags, void *stream)
+                        int elem_bytes, const uint8_t *in, size_t in_bytes, const uint64_t *offsets, uint32_t *flags, void *stream)
 {
     RZK_TRY(check_ready(e, false));
     if (!in || !offsets || !flags) return fail(e, RZK_ERR_INVALID, "wire: null argument");
@@ -313,15 +321,13 @@ int rzk_wire_unpack_dev(rzk_engine *e, size_t B, const rzk_wire_tok *toks, size_
     RZK_TRY(wire_fill(e, K, B, toks, ntoks, streams, nstreams, elem_bytes, 0, &d_toks));
     auto body = [&]() -> int {
         RZK_CUDA(e, cudaMemcpyAsync(d_toks, toks, ntoks * sizeof(rzk_wire_tok), cudaMemcpyHostToDevice, s));
-        K.bytes = const_cast<uint8_t *>(in); K.offsets = offsets; K.flags = flags;
+        K.bytes = const_cast<uint8_t *>(in); K.offsets = offsets; K.flags = flags; K.in_bytes = in_bytes;
         const unsigned grid = (unsigned)std::min<size_t>((B + 7) / 8 + 1, (size_t)e->num_sms * 8);
         if (B) { rzk_wire_unpack_kernel<<<grid, 256, 0, s>>>(K); RZK_CUDA(e, cudaGetLastError()); e->launches++; }
         RZK_CUDA(e, cudaStreamSynchronize(s));
         return RZK_OK;
     };
-    const int rc = body();
-    cudaFree(d_toks);
-    return rc;
+    return body();
 }
 
 }  // extern "C"

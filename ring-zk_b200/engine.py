@@ -163,7 +163,7 @@ def lib():
     L.rzk_wire_pack_dev.argtypes = [_VP, C.c_size_t, _VP, C.c_size_t, _VP, C.c_int, C.c_int, C.c_int, _VP, C.c_size_t, _VP,
                                     C.POINTER(C.c_uint64), _VP]
     L.rzk_wire_unpack_dev.restype = C.c_int
-    L.rzk_wire_unpack_dev.argtypes = [_VP, C.c_size_t, _VP, C.c_size_t, _VP, C.c_int, C.c_int, _VP, _VP, _VP, _VP]
+    L.rzk_wire_unpack_dev.argtypes = [_VP, C.c_size_t, _VP, C.c_size_t, _VP, C.c_int, C.c_int, _VP, C.c_size_t, _VP, _VP, _VP]
     L.rzk_fs_challenge_dev.restype = C.c_int
     L.rzk_fs_challenge_dev.argtypes = [_VP, C.c_size_t, C.c_char_p, C.c_size_t, _VP, C.c_int, _VP, _VP]
     L.rzk_open_prove_fs_batch_dev.restype = C.c_int
@@ -469,8 +469,8 @@ class Engine:
         B = offsets.numel() - 1
         ctoks, cs = self._wire_args(kind, T, streams)
         flags = torch.zeros(max(B, 1), dtype=torch.int32, device=data.device)
-        rc = self.L.rzk_wire_unpack_dev(self.h, B, ctoks, len(ctoks), cs, len(cs), elem_bytes, data.data_ptr(), offsets.data_ptr(),
-                                        flags.data_ptr(), stream)
+        rc = self.L.rzk_wire_unpack_dev(self.h, B, ctoks, len(ctoks), cs, len(cs), elem_bytes, data.data_ptr(), data.numel(),
+                                        offsets.data_ptr(), flags.data_ptr(), stream)
         if rc != RZK_OK:
             raise RzkError(rc, self.last_error())
         return flags[:B]

@@ -102,6 +102,11 @@ def test_device_pack_and_unpack(elem_bytes, trim):
             off_bad = off.clone(); off_bad[B] -= 1                        # last item one byte short
             flags = e.wire_unpack(kind, data_bad, off_bad, outs, T=T, elem_bytes=elem_bytes).cpu().numpy()
             assert flags[1] == 1 and flags[B - 1] == 1 and not flags[[0] + list(range(2, B - 1))].any(), kind
+            # offsets that run backwards or leave the buffer mark the item and read nothing of it
+            off_bad = off.clone(); off_bad[3] = off_bad[2] - 8
+            off_bad[B] = data.numel() + 4096
+            flags = e.wire_unpack(kind, data, off_bad, outs, T=T, elem_bytes=elem_bytes).cpu().numpy()
+            assert flags[2] == 1 and flags[B - 1] == 1 and not flags[[0, 1] + list(range(4, B - 1))].any(), kind
     finally:
         e.close()
 
