@@ -264,6 +264,11 @@ int rzk_wire_pack_dev(rzk_engine *e, size_t B, const rzk_wire_tok *toks, size_t 
                       int elem_bytes, int trim, uint8_t *out, size_t out_capacity, uint64_t *offsets, uint64_t *total_bytes, void *stream);
 int rzk_wire_unpack_dev(rzk_engine *e, size_t B, const rzk_wire_tok *toks, size_t ntoks, const rzk_wire_stream *streams, int nstreams,
                         int elem_bytes, const uint8_t *in, size_t in_bytes, const uint64_t *offsets, uint32_t *flags, void *stream);
+/* Host forms (what the Rust shim binds): the streams, the bytes and the offsets are HOST arrays; ok_bitmap bit i = item i parsed. */
+int rzk_wire_pack(rzk_engine *e, size_t B, const rzk_wire_tok *toks, size_t ntoks, const rzk_wire_stream *streams, int nstreams,
+                  int elem_bytes, int trim, uint8_t *out, size_t out_capacity, uint64_t *offsets, uint64_t *total_bytes);
+int rzk_wire_unpack(rzk_engine *e, size_t B, const rzk_wire_tok *toks, size_t ntoks, const rzk_wire_stream *streams, int nstreams,
+                    int elem_bytes, const uint8_t *in, size_t in_bytes, const uint64_t *offsets, uint8_t *ok_bitmap);
 
 /* ---------------------------------------------------------------- Fiat-Shamir challenges on the device
  * NOT in the reference, which is interactive (open.rs:143-158 draws d from the verifier's RNG; README.md:16 names the
@@ -284,6 +289,13 @@ int rzk_open_prove_fs_batch_dev(rzk_engine *e, size_t B, const int32_t *x, const
                                 size_t prefix_len, int32_t *c, int32_t *t, int8_t *d, int32_t *z, uint32_t *flags, void *stream);
 int rzk_open_verify_fs_batch_dev(rzk_engine *e, size_t B, const int32_t *c, const int32_t *t, const int32_t *z, const uint8_t *prefix,
                                  size_t prefix_len, int8_t *d, uint32_t *flags, void *stream);
+/* Host forms (host pointers, chunked pipeline): prove = commit + challenge + response with r, y supplied (ok bitmap: the commit
+ * constraint, as rzk_open_commit_batch); verify returns the verdict bitmap.  A proof is (c, t, z); d is returned to the prover
+ * for inspection only and is recomputed by the verifier. */
+int rzk_open_prove_fs_batch(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r, const int32_t *y, const uint8_t *prefix,
+                            size_t prefix_len, int32_t *c, int32_t *t, int8_t *d, int32_t *z, uint8_t *ok_bitmap);
+int rzk_open_verify_fs_batch(rzk_engine *e, size_t B, const int32_t *c, const int32_t *t, const int32_t *z, const uint8_t *prefix,
+                             size_t prefix_len, uint8_t *verify_bitmap);
 
 /* Counters for the benchmark harness: kernels launched by this engine since creation. */
 uint64_t rzk_kernel_launches(const rzk_engine *e);

@@ -255,4 +255,49 @@ int rzk_open_verify_fs_batch_dev(rzk_engine *e, size_t B, const int32_t *c, cons
     return dev_verify_first(e, B, z, t, c, 2, d, 1, nullptr, flags, 1, s);                      // open.rs:162-174
 }
 
+// ---- host entry points (host pointers, chunked pipeline as the other host calls) ----
+
+int rzk_open_prove_fs_batch(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r, const int32_t *y, const uint8_t *prefix,
+                            size_t prefix_len, int32_t *c, int32_t *t, int8_t *d, int32_t *z, uint8_t *ok)
+{
+    RZK_TRY(check_ready(e));
+    if (any_null({x, r, y, c, t, d, z, ok})) return fail(e, RZK_ERR_INVALID, "null argument");
+    {
+        Guard g(e->device);
+        RZK_TRY(fs_stage_prefix(e, prefix, prefix_len, e->pipe[0].stream));       // once; every pipeline stream reads it
+        RZK_CUDA(e, cudaStreamSynchronize(e->pipe[0].stream));
+    }
+    const uint64_t *pre = reinterpret_cast<const uint64_t *>(e->d_fs_prefix);
+    const uint32_t lanes = (uint32_t)(prefix_len / 8);
+    std::vector<HArr> a = {{x, nullptr, kPolyBytes}, {r, nullptr, 3 * kN}, {y, nullptr, 3 * kPolyBytes},
+                           {nullptr, c, 2 * kPolyBytes}, {nullptr, t, kPolyBytes}, {nullptr, d, kN}, {nullptr, z, 3 * kPolyBytes}};
+    return run_chunked(e, B, a, 2 * sizeof(uint32_t), ok, [&](size_t n, void **p, char *sc, uint32_t *fl, cudaStream_t s, uint32_t *rm) {
+        RZK_TRY(dev_open_commit(e, n, (const int32_t *)p[0], (const int8_t *)p[1], (const int32_t *)p[2], (int32_t *)p[3], (int32_t *)p[4], fl, s, rm));
+        const rzk_wire_stream segs[2] = {{p[3], 2, DT_I32}, {p[4], 1, DT_I32}};
+        RZK_TRY(dev_fs_challenge(e, n, pre, lanes, segs, nullptr, 2, (int8_t *)p[5], s));
+        return dev_respond(e, n, (const int32_t *)p[2], (const int8_t *)p[1], (const int8_t *)p[5], 1, (int32_t *)p[6], (uint32_t *)sc, s);
+    });
+}
+
+int rzk_open_verify_fs_batch(rzk_engine *e, size_t B, const int32_t *c, const int32_t *t, const int32_t *z, const uint8_t *prefix,
+                             size_t prefix_len, uint8_t *bm)
+{
+    RZK_TRY(check_ready(e));
+    if (any_null({c, t, z, bm})) return fail(e, RZK_ERR_INVALID, "null argument");
+    {
+        Guard g(e->device);
+        RZK_TRY(fs_stage_prefix(e, prefix, prefix_len, e->pipe[0].stream));
+        RZK_CUDA(e, cudaStreamSynchronize(e->pipe[0].stream));
+    }
+    const uint64_t *pre = reinterpret_cast<const uint64_t *>(e->d_fs_prefix);
+    const uint32_t lanes = (uint32_t)(prefix_len / 8);
+    std::vector<HArr> a = {{c, nullptr, 2 * kPolyBytes}, {t, nullptr, kPolyBytes}, {z, nullptr, 3 * kPolyBytes}};
+    return run_chunked(e, B, a, kN, bm, [&](size_t n, void **p, char *sc, uint32_t *fl, cudaStream_t s, uint32_t *) {
+        const rzk_wire_stream segs[2] = {{p[0], 2, DT_I32}, {p[1], 1, DT_I32}};
+        RZK_TRY(dev_fs_challenge(e, n, pre, lanes, segs, nullptr, 2, (int8_t *)sc, s));
+        return dev_verify_first(e, n, (const int32_t *)p[2], (const int32_t *)p[1], (const int32_t *)p[0], 2, (const int8_t *)sc, 1,
+                                nullptr, fl, 1, s);
+    });
+}
+
 }  // extern "C"

@@ -330,4 +330,83 @@ int rzk_wire_unpack_dev(rzk_engine *e, size_t B, const rzk_wire_tok *toks, size_
     return body();
 }
 
+// ---- host forms: the streams, the bytes and the offsets are host arrays (staged through device buffers of the call) ----
+
+namespace {
+struct WireStage {
+    std::vector<void *> dev;
+    ~WireStage() { for (void *p : dev) if (p) cudaFree(p); }
+    int alloc(rzk_engine *e, void **out, size_t bytes)
+    {
+        *out = nullptr;
+        RZK_CUDA(e, cudaMalloc(out, std::max<size_t>(bytes, 16)));
+        dev.push_back(*out);
+        return RZK_OK;
+    }
+};
+size_t wire_stream_bytes(const rzk_wire_stream &s, size_t B) { return B * s.polys_per_item * (size_t)kN * (s.dtype == DT_I8 ? 1 : 4); }
+}  // namespace
+
+int rzk_wire_pack(rzk_engine *e, size_t B, const rzk_wire_tok *toks, size_t ntoks, const rzk_wire_stream *streams, int nstreams,
+                  int elem_bytes, int trim, uint8_t *out, size_t out_capacity, uint64_t *offsets, uint64_t *total_bytes)
+{
+    RZK_TRY(check_ready(e, false));
+    if (!streams || !offsets || !total_bytes || nstreams < 1 || nstreams > kWireMaxStreams) return fail(e, RZK_ERR_INVALID, "wire: bad argument");
+    Guard g(e->device);
+    WireStage st;
+    rzk_wire_stream ds[kWireMaxStreams];
+    for (int i = 0; i < nstreams; ++i) {
+        ds[i] = streams[i];
+        if (!streams[i].base) continue;
+        void *p;
+        RZK_TRY(st.alloc(e, &p, wire_stream_bytes(streams[i], B)));
+        RZK_CUDA(e, cudaMemcpy(p, streams[i].base, wire_stream_bytes(streams[i], B), cudaMemcpyHostToDevice));
+        ds[i].base = p;
+    }
+    void *d_off, *d_out = nullptr;
+    RZK_TRY(st.alloc(e, &d_off, (B + 1) * sizeof(uint64_t)));
+    RZK_TRY(rzk_wire_pack_dev(e, B, toks, ntoks, ds, nstreams, elem_bytes, trim, nullptr, 0, (uint64_t *)d_off, total_bytes, nullptr));
+    RZK_CUDA(e, cudaMemcpy(offsets, d_off, (B + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (!out) return RZK_OK;                                  // size query
+    if (*total_bytes > out_capacity) return fail(e, RZK_ERR_INVALID, "wire: output buffer too small (total_bytes holds the size needed)");
+    RZK_TRY(st.alloc(e, &d_out, *total_bytes));
+    RZK_TRY(rzk_wire_pack_dev(e, B, toks, ntoks, ds, nstreams, elem_bytes, trim, (uint8_t *)d_out, *total_bytes, (uint64_t *)d_off, total_bytes, nullptr));
+    RZK_CUDA(e, cudaMemcpy(out, d_out, *total_bytes, cudaMemcpyDeviceToHost));
+    return RZK_OK;
+}
+
+int rzk_wire_unpack(rzk_engine *e, size_t B, const rzk_wire_tok *toks, size_t ntoks, const rzk_wire_stream *streams, int nstreams,
+                    int elem_bytes, const uint8_t *in, size_t in_bytes, const uint64_t *offsets, uint8_t *ok_bitmap)
+{
+    RZK_TRY(check_ready(e, false));
+    if (!streams || !in || !offsets || !ok_bitmap || nstreams < 1 || nstreams > kWireMaxStreams) return fail(e, RZK_ERR_INVALID, "wire: bad argument");
+    Guard g(e->device);
+    WireStage st;
+    rzk_wire_stream ds[kWireMaxStreams];
+    for (int i = 0; i < nstreams; ++i) {
+        ds[i] = streams[i];
+        if (!streams[i].base) continue;
+        void *p;
+        RZK_TRY(st.alloc(e, &p, wire_stream_bytes(streams[i], B)));
+        RZK_CUDA(e, cudaMemset(p, 0, wire_stream_bytes(streams[i], B)));
+        ds[i].base = p;
+    }
+    void *d_in, *d_off, *d_flags, *d_bm;
+    RZK_TRY(st.alloc(e, &d_in, in_bytes));
+    RZK_TRY(st.alloc(e, &d_off, (B + 1) * sizeof(uint64_t)));
+    RZK_TRY(st.alloc(e, &d_flags, (B + 1) * sizeof(uint32_t)));
+    RZK_TRY(st.alloc(e, &d_bm, (B + 7) / 8 + 1));
+    RZK_CUDA(e, cudaMemcpy(d_in, in, in_bytes, cudaMemcpyHostToDevice));
+    RZK_CUDA(e, cudaMemcpy(d_off, offsets, (B + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    RZK_CUDA(e, cudaMemset(d_flags, 0, (B + 1) * sizeof(uint32_t)));
+    RZK_TRY(rzk_wire_unpack_dev(e, B, toks, ntoks, ds, nstreams, elem_bytes, (const uint8_t *)d_in, in_bytes, (const uint64_t *)d_off,
+                                (uint32_t *)d_flags, nullptr));
+    RZK_TRY(rzk_flags_to_bitmap_dev(e, B, (const uint32_t *)d_flags, (uint8_t *)d_bm, nullptr, nullptr));
+    RZK_CUDA(e, cudaMemcpy(ok_bitmap, d_bm, (B + 7) / 8, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < nstreams; ++i)
+        if (streams[i].base)
+            RZK_CUDA(e, cudaMemcpy(const_cast<void *>(streams[i].base), ds[i].base, wire_stream_bytes(streams[i], B), cudaMemcpyDeviceToHost));
+    return RZK_OK;
+}
+
 }  // extern "C"

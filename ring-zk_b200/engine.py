@@ -105,7 +105,8 @@ EXPORTS = sorted(list(_SIGS) + list(_GROUP_SIGS) + ["rzk_group_create", "rzk_gro
                                 "rzk_sigma", "rzk_commit_bound", "rzk_verify_bound", "rzk_small_limit",
                                 "rzk_set_key", "rzk_host_alloc", "rzk_host_free", "rzk_kernel_launches",
                                 "rzk_wire_layout", "rzk_wire_pack_dev", "rzk_wire_unpack_dev",
-                                "rzk_fs_challenge_dev", "rzk_open_prove_fs_batch_dev", "rzk_open_verify_fs_batch_dev"])
+                                "rzk_fs_challenge_dev", "rzk_open_prove_fs_batch_dev", "rzk_open_verify_fs_batch_dev",
+                                "rzk_wire_pack", "rzk_wire_unpack", "rzk_open_prove_fs_batch", "rzk_open_verify_fs_batch"])
 
 
 def lib():
@@ -170,6 +171,14 @@ def lib():
     L.rzk_open_prove_fs_batch_dev.argtypes = [_VP, C.c_size_t, _VP, _VP, _VP, C.c_char_p, C.c_size_t, _VP, _VP, _VP, _VP, _VP, _VP]
     L.rzk_open_verify_fs_batch_dev.restype = C.c_int
     L.rzk_open_verify_fs_batch_dev.argtypes = [_VP, C.c_size_t, _VP, _VP, _VP, C.c_char_p, C.c_size_t, _VP, _VP, _VP]
+    L.rzk_open_prove_fs_batch.restype = C.c_int
+    L.rzk_open_prove_fs_batch.argtypes = [_VP, C.c_size_t, _VP, _VP, _VP, C.c_char_p, C.c_size_t, _VP, _VP, _VP, _VP, _VP]
+    L.rzk_open_verify_fs_batch.restype = C.c_int
+    L.rzk_open_verify_fs_batch.argtypes = [_VP, C.c_size_t, _VP, _VP, _VP, C.c_char_p, C.c_size_t, _VP]
+    L.rzk_wire_pack.restype = C.c_int
+    L.rzk_wire_pack.argtypes = [_VP, C.c_size_t, _VP, C.c_size_t, _VP, C.c_int, C.c_int, C.c_int, _VP, C.c_size_t, _VP, C.POINTER(C.c_uint64)]
+    L.rzk_wire_unpack.restype = C.c_int
+    L.rzk_wire_unpack.argtypes = [_VP, C.c_size_t, _VP, C.c_size_t, _VP, C.c_int, C.c_int, _VP, C.c_size_t, _VP, _VP]
     _lib = L
     return L
 
@@ -430,6 +439,65 @@ class Engine:
         rc = self.L.rzk_open_verify_fs_batch_dev(self.h, c.shape[0], _ptr(c), _ptr(t), _ptr(z), prefix, len(prefix), _ptr(d), _ptr(flags), stream)
         if rc != RZK_OK:
             raise RzkError(rc, self.last_error())
+
+    # ---- host forms of the Fiat-Shamir proofs and of the wire format (numpy arrays) ----
+    def open_prove_fs_host(self, x, r, y, prefix: bytes):
+        """rzk_open_prove_fs_batch: numpy x [B][1][N] i32, r [B][3][N] i8, y [B][3][N] i32 -> dict(c, t, d, z, ok bitmap)"""
+        B, N = x.shape[0], self.N
+        c, t, z = np.empty((B, 2, N), np.int32), np.empty((B, 1, N), np.int32), np.empty((B, 3, N), np.int32)
+        d, ok = np.empty((B, N), np.int8), np.zeros((B + 7) // 8, np.uint8)
+        rc = self.L.rzk_open_prove_fs_batch(self.h, B, _ptr(x, np.int32), _ptr(r, np.int8), _ptr(y, np.int32), prefix, len(prefix),
+                                            _ptr(c), _ptr(t), _ptr(d), _ptr(z), _ptr(ok))
+        if rc != RZK_OK:
+            raise RzkError(rc, self.last_error())
+        return dict(c=c, t=t, d=d, z=z, ok=ok)
+
+    def open_verify_fs_host(self, c, t, z, prefix: bytes):
+        B = c.shape[0]
+        bm = np.zeros((B + 7) // 8, np.uint8)
+        rc = self.L.rzk_open_verify_fs_batch(self.h, B, _ptr(c, np.int32), _ptr(t, np.int32), _ptr(z, np.int32), prefix, len(prefix), _ptr(bm))
+        if rc != RZK_OK:
+            raise RzkError(rc, self.last_error())
+        return bm
+
+    @staticmethod
+    def _wire_args_host(kind, T, arrays):
+        toks = wire_layout(kind, T)
+        ctoks = (WireTok * len(toks))(*[WireTok(*t) for t in toks])
+        cs = (WireStream * len(arrays))()
+        for i, a in enumerate(arrays):
+            if a.dtype not in (np.int32, np.int8) or not a.flags["C_CONTIGUOUS"]:
+                raise TypeError("wire streams are C-contiguous int32 / int8 arrays [B][polys][N]")
+            cs[i] = WireStream(a.ctypes.data, int(np.prod(a.shape[1:-1])) if a.ndim > 2 else 1, 1 if a.dtype == np.int8 else 0)
+        return ctoks, cs
+
+    def wire_pack_host(self, kind, arrays, T=0, elem_bytes=8, trim=True):
+        """rzk_wire_pack: numpy arrays in -> (bytes, offsets [B + 1] uint64)"""
+        B = arrays[0].shape[0]
+        ctoks, cs = self._wire_args_host(kind, T, arrays)
+        off = np.zeros(B + 1, np.uint64)
+        total = C.c_uint64(0)
+        args = (self.h, B, ctoks, len(ctoks), cs, len(cs), elem_bytes, 1 if trim else 0)
+        rc = self.L.rzk_wire_pack(*args, None, 0, off.ctypes.data, C.byref(total))
+        if rc != RZK_OK:
+            raise RzkError(rc, self.last_error())
+        out = np.zeros(max(int(total.value), 1), np.uint8)
+        rc = self.L.rzk_wire_pack(*args, out.ctypes.data, int(total.value), off.ctypes.data, C.byref(total))
+        if rc != RZK_OK:
+            raise RzkError(rc, self.last_error())
+        return out[: int(total.value)].tobytes(), off
+
+    def wire_unpack_host(self, kind, data: bytes, offsets, arrays, T=0, elem_bytes=8):
+        """rzk_wire_unpack into the preallocated numpy `arrays`; returns the ok bitmap (bit i: item i parsed)"""
+        B = len(offsets) - 1
+        ctoks, cs = self._wire_args_host(kind, T, arrays)
+        buf = np.frombuffer(data, np.uint8)
+        off = np.ascontiguousarray(offsets, np.uint64)
+        ok = np.zeros((B + 7) // 8, np.uint8)
+        rc = self.L.rzk_wire_unpack(self.h, B, ctoks, len(ctoks), cs, len(cs), elem_bytes, buf.ctypes.data, buf.size, off.ctypes.data, ok.ctypes.data)
+        if rc != RZK_OK:
+            raise RzkError(rc, self.last_error())
+        return ok
 
     # ---- wire format: device tensors in, device bytes out (and back) ----
     @staticmethod

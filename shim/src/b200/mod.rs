@@ -16,6 +16,7 @@
 //! NOT COMPILED in the environment this was written in (no Rust toolchain there); it follows the header one to one.
 
 pub mod ffi;
+pub mod wire;
 
 use std::ffi::CStr;
 use std::os::raw::c_int;
@@ -177,7 +178,7 @@ fn status(rc: c_int, msg: *const std::os::raw::c_char) -> B200Error {
 // (|v| <= (Q - 1) / 2 < 2^31) fits i32.
 
 /// Appends the N coefficients of `p` to `out` as i32.
-pub(crate) fn push_poly<const N: usize>(out: &mut Vec<i32>, p: &Polynomial<Z, N>) {
+pub fn push_poly<const N: usize>(out: &mut Vec<i32>, p: &Polynomial<Z, N>) {
     let start = out.len();
     out.extend(p.iter().map(|c| Into::<i64>::into(c.clone()) as i32));
     out.resize(start + N, 0);
@@ -197,7 +198,7 @@ pub(crate) fn push_poly_i8<const N: usize>(out: &mut Vec<i8>, p: &Polynomial<Z, 
 }
 
 /// Appends every polynomial of a (rows x 1) matrix.
-pub(crate) fn push_mat<const N: usize>(out: &mut Vec<i32>, m: &Mat<Z, N>) {
+pub fn push_mat<const N: usize>(out: &mut Vec<i32>, m: &Mat<Z, N>) {
     for row in &m.polynomials {
         for p in row {
             push_poly(out, p);
@@ -247,4 +248,23 @@ pub(crate) fn bit(bitmap: &[u8], i: usize) -> bool {
 /// the reference's own shape asserts are.
 pub(crate) fn assert_default_shape(params: &Params<Z>) {
     assert!(params.n == 1 && params.k == 3 && params.l == 1, "the B200 engine accelerates (n, k, l) = (1, 3, 1) only");
+}
+
+/// Transcript prefix of the Fiat-Shamir entry points (docs/FIAT_SHAMIR.md of the engine's repository):
+/// `tag` (ASCII, zero padded to 32 bytes) || key digest (32 bytes: SHAKE128-256 of a11 || a12 || a22 as int32 LE canonical
+/// coefficients, computed by the caller with the hash crate of its choice) || q u64 || N u32 || kappa u32 || T u32 || b u32 ||
+/// session (a multiple of 8 bytes), all little endian.
+pub fn fs_prefix<const N: usize>(tag: &str, key_digest: &[u8; 32], params: &Params<Z>, terms: u32, session: &[u8]) -> Vec<u8> {
+    assert!(tag.len() <= 32 && session.len() % 8 == 0);
+    let mut p = vec![0u8; 32];
+    p[..tag.len()].copy_from_slice(tag.as_bytes());
+    p.extend_from_slice(key_digest);
+    p.extend_from_slice(&(Q as u64).to_le_bytes());
+    p.extend_from_slice(&(N as u32).to_le_bytes());
+    p.extend_from_slice(&(params.kappa as u32).to_le_bytes());
+    p.extend_from_slice(&terms.to_le_bytes());
+    let b: i64 = params.b.clone().into();
+    p.extend_from_slice(&(b as u32).to_le_bytes());
+    p.extend_from_slice(session);
+    p
 }

@@ -92,9 +92,93 @@ impl<const N: usize> OpenProofProver<Z, N> {
         be.check_or_panic(rc)?;
         Ok((0..b).map(|i| OpenProofResponse { z: b200::mat_from::<N>(&z[i * k * N..(i + 1) * k * N], k) }).collect())
     }
+
+    /// NOT in the reference (an extension; `README.md:16` names the transform as a possibility): non-interactive Open proofs
+    /// for B messages.  The challenge of instance i is `SampleInBall(SHAKE128(prefix || c_i || t_i))` computed on the device
+    /// between `commit` and `create_response` (docs/FIAT_SHAMIR.md of the engine's repository; `prefix` = domain tag, key
+    /// digest, shape words and an optional session id, a multiple of 8 bytes -- `b200::fs_prefix`).  Randomness is drawn
+    /// exactly as `commit_batch` draws it (`r`, then `y`, per instance).  A proof is `(OpenProofCommitment, OpenProofResponse)`.
+    pub fn prove_batch_fs(
+        &self,
+        rng: &mut impl RngExt,
+        xs: Vec<Vec<Polynomial<Z, N>>>,
+        prefix: &[u8],
+        be: &mut Backend,
+    ) -> Result<Vec<(Opening<Z, N>, OpenProofCommitment<Z, N>, OpenProofResponse<Z, N>)>, B200Error> {
+        b200::assert_default_shape(&self.params);
+        assert_eq!(prefix.len() % 8, 0, "the transcript prefix is a multiple of 8 bytes");
+        let e = match *be {
+            Backend::Engine(e) => e,
+            Backend::Group(_) => return Err(B200Error::Unsupported("the Fiat-Shamir entry points take a single engine".into())),
+        };
+        let b = xs.len();
+        let mut rs = Vec::with_capacity(b);
+        let (mut xf, mut rf, mut yf) = (Vec::with_capacity(b * N), Vec::with_capacity(b * 3 * N), Vec::with_capacity(b * 3 * N));
+        for x in &xs {
+            assert_eq!(self.params.l, x.len()); // commit.rs:95
+            let r = draw_commit_randomness::<N>(rng, &self.params);
+            let y = b200::draw_masking::<N>(rng, &self.params);
+            b200::push_poly(&mut xf, &x[0]);
+            b200::push_mat_i8(&mut rf, &r);
+            b200::push_mat(&mut yf, &y);
+            rs.push(r);
+        }
+        let (rows, n, k) = (self.params.n + self.params.l, self.params.n, self.params.k);
+        let (mut c, mut t, mut z) = (vec![0i32; b * rows * N], vec![0i32; b * n * N], vec![0i32; b * k * N]);
+        let mut d = vec![0i8; b * N];
+        let mut ok = vec![0u8; (b + 7) / 8];
+        let rc = unsafe {
+            ffi::rzk_open_prove_fs_batch(e, b, xf.as_ptr(), rf.as_ptr(), yf.as_ptr(), prefix.as_ptr(), prefix.len(), c.as_mut_ptr(), t.as_mut_ptr(), d.as_mut_ptr(), z.as_mut_ptr(), ok.as_mut_ptr())
+        };
+        be.check_or_panic(rc)?;
+        Ok(xs
+            .into_iter()
+            .zip(rs)
+            .enumerate()
+            .map(|(i, (x, r))| {
+                (
+                    Opening { x, r, f: None },
+                    OpenProofCommitment {
+                        c: Commitment { c: b200::mat_from::<N>(&c[i * rows * N..(i + 1) * rows * N], rows) },
+                        t: b200::polys_from::<N>(&t[i * n * N..(i + 1) * n * N], n),
+                    },
+                    OpenProofResponse { z: b200::mat_from::<N>(&z[i * k * N..(i + 1) * k * N], k) },
+                )
+            })
+            .collect())
+    }
 }
 
 impl<const N: usize> OpenProofVerifier<Z, N> {
+    /// Verifies non-interactive Open proofs made by `OpenProofProver::prove_batch_fs` with the same `prefix`: the challenge is
+    /// recomputed from `(c, t)` on the device, then `open.rs:162-174`.  NOT in the reference (see `prove_batch_fs`).
+    pub fn verify_batch_fs(
+        &self,
+        proofs: &[(OpenProofCommitment<Z, N>, OpenProofResponse<Z, N>)],
+        prefix: &[u8],
+        be: &mut Backend,
+    ) -> Result<Vec<bool>, B200Error> {
+        b200::assert_default_shape(&self.params);
+        assert_eq!(prefix.len() % 8, 0, "the transcript prefix is a multiple of 8 bytes");
+        let e = match *be {
+            Backend::Engine(e) => e,
+            Backend::Group(_) => return Err(B200Error::Unsupported("the Fiat-Shamir entry points take a single engine".into())),
+        };
+        let b = proofs.len();
+        let (mut cf, mut tf, mut zf) = (Vec::with_capacity(b * 2 * N), Vec::with_capacity(b * N), Vec::with_capacity(b * 3 * N));
+        for (com, resp) in proofs {
+            b200::push_mat(&mut cf, &com.c.c);
+            for t in &com.t {
+                b200::push_poly(&mut tf, t);
+            }
+            b200::push_mat(&mut zf, &resp.z);
+        }
+        let mut bm = vec![0u8; (b + 7) / 8];
+        let rc = unsafe { ffi::rzk_open_verify_fs_batch(e, b, cf.as_ptr(), tf.as_ptr(), zf.as_ptr(), prefix.as_ptr(), prefix.len(), bm.as_mut_ptr()) };
+        be.check_or_panic(rc)?;
+        Ok((0..b).map(|i| b200::bit(&bm, i)).collect())
+    }
+
     /// `generate_challenge` (`open.rs:143-158`) for B commitments.  Host side only (no ring arithmetic): it is the
     /// sequential method in a loop, kept here so that a batch flow reads the same as the single-instance one.
     pub fn generate_challenge_batch(

@@ -88,3 +88,31 @@ def test_non_interactive_open_proofs():
     _, proofs2 = prover.prove_batch_fs(rng, X, session=b"session1")
     assert verifier.verify_batch_fs(proofs2, session=b"session1").all()
     ck.engine.close()
+
+
+def test_host_entry_points_match_the_device_chain():
+    """rzk_open_prove_fs_batch / rzk_open_verify_fs_batch (host pointers, chunked pipeline: what the Rust shim binds) against the
+    interactive host entry points driven with the hashlib challenge, over more than one pipeline chunk"""
+    rng = np.random.default_rng(21)
+    s = pkg.synth.Synth(21, N=N)
+    e = engine.Engine(N=N, device=0)
+    try:
+        e.set_key_blocks(*s.key())
+        B = 8192 + 77
+        x, r, y = s.message(B), s.small(B), s.gaussian(B)
+        pre = b"ring-zk/fs/open/v1".ljust(32, b"\0") + bytes(range(32)) + bytes(24)
+        o = e.open_prove_fs_host(x, r, y, pre)
+        assert engine.unpack_bitmap(o["ok"], B).all()
+        c, t, _ = e.open_commit(x, r, y)
+        assert (o["c"] == c).all() and (o["t"] == t).all()
+        idx = [0, 1, 8191, 8192, B - 1] + list(rng.integers(0, B, 12))
+        for i in idx:
+            assert (o["d"][i] == fs_ref.challenge(pre, [c[i], t[i]], N, 36)).all(), i
+        assert (o["z"] == e.open_respond(y, r, o["d"])).all()
+        assert engine.unpack_bitmap(e.open_verify_fs_host(o["c"], o["t"], o["z"], pre), B).all()
+        zt = o["z"].copy(); zt[5, 0, 3] += 1; zt[B - 1, 2, 511] -= 1
+        v = engine.unpack_bitmap(e.open_verify_fs_host(o["c"], o["t"], zt, pre), B)
+        assert not v[5] and not v[B - 1] and v.sum() == B - 2
+        assert not engine.unpack_bitmap(e.open_verify_fs_host(o["c"], o["t"], o["z"], pre[:-8] + b"other-id"), B).any()
+    finally:
+        e.close()

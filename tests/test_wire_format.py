@@ -129,3 +129,26 @@ def test_device_pack_reproduces_the_reference_pin():
         assert out[:36].cpu().numpy().tobytes() == struct.pack("<QQQiii", 1, 1, 3, 1, 2, 3)
     finally:
         e.close()
+
+
+@pytest.mark.gpu
+def test_host_forms_of_pack_and_unpack():
+    """rzk_wire_pack / rzk_wire_unpack (host arrays: what the Rust shim binds) == the field-by-field serialisers, and back"""
+    rng = np.random.default_rng(12)
+    B, T = 19, 3
+    e = engine.Engine(N=N, device=0)
+    try:
+        for kind, (streams, direct) in _messages(rng, B, T).items():
+            data, off = e.wire_pack_host(kind, streams, T=T)
+            want = [direct(i, elem_bytes=8, trim=True) for i in range(B)]
+            assert data == b"".join(want) and list(np.diff(off.astype(np.int64))) == [len(w) for w in want], kind
+            outs = [np.full_like(a, 55) for a in streams]
+            ok = e.wire_unpack_host(kind, data, off, outs, T=T)
+            assert engine.unpack_bitmap(ok, B).all(), kind
+            for a, b in zip(streams, outs):
+                assert (a == b).all(), kind
+            bad = bytearray(data); bad[int(off[2]) + 3] ^= 0x40
+            ok = engine.unpack_bitmap(e.wire_unpack_host(kind, bytes(bad), off, outs, T=T), B)
+            assert not ok[2] and ok.sum() == B - 1, kind
+    finally:
+        e.close()
