@@ -178,7 +178,7 @@ fn status(rc: c_int, msg: *const std::os::raw::c_char) -> B200Error {
 // (|v| <= (Q - 1) / 2 < 2^31) fits i32.
 
 /// Appends the N coefficients of `p` to `out` as i32.
-pub fn push_poly<const N: usize>(out: &mut Vec<i32>, p: &Polynomial<Z, N>) {
+pub(crate) fn push_poly<const N: usize>(out: &mut Vec<i32>, p: &Polynomial<Z, N>) {
     let start = out.len();
     out.extend(p.iter().map(|c| Into::<i64>::into(c.clone()) as i32));
     out.resize(start + N, 0);
@@ -198,7 +198,7 @@ pub(crate) fn push_poly_i8<const N: usize>(out: &mut Vec<i8>, p: &Polynomial<Z, 
 }
 
 /// Appends every polynomial of a (rows x 1) matrix.
-pub fn push_mat<const N: usize>(out: &mut Vec<i32>, m: &Mat<Z, N>) {
+pub(crate) fn push_mat<const N: usize>(out: &mut Vec<i32>, m: &Mat<Z, N>) {
     for row in &m.polynomials {
         for p in row {
             push_poly(out, p);

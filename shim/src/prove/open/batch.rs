@@ -220,3 +220,18 @@ impl<const N: usize> OpenProofVerifier<Z, N> {
         Ok((0..b).map(|i| b200::bit(&bm, i)).collect())
     }
 }
+
+impl<const N: usize> OpenProofCommitment<Z, N> {
+    /// The messages of a batch in the crate's own bincode encoding, packed by the engine (`b200::wire::pack`,
+    /// `RZK_MSG_OPEN_COMMITMENT`): `&bytes[off[i]..off[i + 1]] == bincode::serialize(&coms[i])`.
+    pub fn to_wire_batch(coms: &[Self], be: &mut Backend) -> Result<(Vec<u8>, Vec<u64>), B200Error> {
+        let (mut cf, mut tf) = (Vec::with_capacity(coms.len() * 2 * N), Vec::with_capacity(coms.len() * N));
+        for c in coms {
+            b200::push_mat(&mut cf, &c.c.c);
+            for t in &c.t {
+                b200::push_poly(&mut tf, t);
+            }
+        }
+        b200::wire::pack(be, ffi::RZK_MSG_OPEN_COMMITMENT, 0, coms.len(), &[b200::wire::Stream::I32(&cf, 2), b200::wire::Stream::I32(&tf, 1)])
+    }
+}

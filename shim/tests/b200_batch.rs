@@ -121,7 +121,7 @@ fn unsupported_parameters_keep_the_cpu_path() {
 fn non_interactive_open_proofs_and_the_wire_format() {
     // the extension of docs/FIAT_SHAMIR.md: a proof is (commitment, response); the challenge comes from the transcript.
     // Cross-checked against the interactive methods: with the challenge the engine derived, the sequential verifier accepts.
-    use ring_zk::b200::{ffi, fs_prefix, wire};
+    use ring_zk::b200::fs_prefix;
     let params = Params::default();
     let ck = params.generate_commitment_key::<N>(&mut StdRng::seed_from_u64(31));
     let mut be = Backend::new(&ck, &params, -1).expect("a B200 and libringzk_b200.so");
@@ -134,16 +134,9 @@ fn non_interactive_open_proofs_and_the_wire_format() {
     let other = fs_prefix::<N>("ring-zk/fs/open/v1", &digest, &params, 0, b"session2");
     assert!(verifier.verify_batch_fs(&pairs, &other, &mut be).unwrap().iter().all(|&v| !v));
     // the commitments cross the wire in the crate's own encoding: what the engine packs is what bincode produces
-    let mut cf = Vec::new();
-    let mut tf = Vec::new();
-    for (c, _) in &pairs {
-        ring_zk::b200::push_mat(&mut cf, &c.c.c);
-        for t in &c.t {
-            ring_zk::b200::push_poly(&mut tf, t);
-        }
-    }
-    let (bytes, off) = wire::pack(&mut be, ffi::RZK_MSG_OPEN_COMMITMENT, 0, B, &[wire::Stream::I32(&cf, 2), wire::Stream::I32(&tf, 1)]).unwrap();
-    for (i, (c, _)) in pairs.iter().enumerate() {
+    let coms: Vec<_> = pairs.iter().map(|(c, _)| c.clone()).collect();
+    let (bytes, off) = ring_zk::OpenProofCommitment::to_wire_batch(&coms, &mut be).unwrap();
+    for (i, c) in coms.iter().enumerate() {
         assert_eq!(&bytes[off[i] as usize..off[i + 1] as usize], &bincode::serialize(c).unwrap()[..]);
     }
 }
