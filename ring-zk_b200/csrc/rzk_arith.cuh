@@ -122,6 +122,68 @@ RZK_HD void gs_bfly(uint32_t &x, uint32_t &y, uint32_t w, uint32_t wp, uint32_t 
     y = shoup_mul(w, wp, d, p);
 }
 
+// ---------------------------------------------------------------- signed lazy arithmetic for one small prime
+// For an auxiliary prime 2^26 < p < 2^31 / 29 every residue is kept as ANY int32 representative and nothing is corrected
+// inside a butterfly.  Twiddles and key images are stored centred, w in (-p/2, p/2), with the signed Shoup companion
+// w' = round(w * 2^32 / p) (fits int32).  For any |y| < 2^31:
+//     t = y*w - floor(y*w' / 2^32) * p   is congruent to y*w and lies in (-p/4, 5p/4)
+// (y*w'/2^32 = y*w/p + e with |e| <= |y| / 2^33 < 1/4, and the floor takes off less than one more).
+// `mp` is -p as a 32-bit word (a separate operand so that the product term is one multiply-add, no negation).
+RZK_HD int32_t mulhi_s32(int32_t a, int32_t b)
+{
+#if defined(__CUDA_ARCH__)
+    return __mulhi(a, b);
+#else
+    return (int32_t)(((int64_t)a * (int64_t)b) >> 32);
+#endif
+}
+
+// acc + y*w (mod p), lazy: |result| <= |acc| + 5p/4
+RZK_HD uint32_t sshoup_mac(uint32_t w, uint32_t wp, uint32_t y, uint32_t mp, uint32_t acc)
+{
+    const uint32_t q = (uint32_t)mulhi_s32((int32_t)y, (int32_t)wp);
+    return q * mp + (w * y + acc);
+}
+
+// Cooley-Tukey (forward) butterfly, four instructions: x' = x + t, y' = x - t = 2x - x'.  Magnitudes grow by 5p/4 per stage.
+RZK_HD void ct_bfly_s(uint32_t &x, uint32_t &y, uint32_t w, uint32_t wp, uint32_t mp)
+{
+    const uint32_t xo = sshoup_mac(w, wp, y, mp, x);
+    y = x + x - xo;
+    x = xo;
+}
+
+// Gentleman-Sande (inverse) butterfly, five instructions: x' = x + y (magnitude doubles), y' = (x - y) * w (back to 5p/4).
+// Needs |x| + |y| < 2^31: the callers reduce the few elements whose run of sums would exceed that (sreduce).
+RZK_HD void gs_bfly_s(uint32_t &x, uint32_t &y, uint32_t w, uint32_t wp, uint32_t mp)
+{
+    const uint32_t s = x + y, d = x - y;
+    x = s;
+    y = sshoup_mac(w, wp, d, mp, 0u);
+}
+
+// v -> v - floor(v / 2^SH) * p for 2^SH <= p < 2^SH + 2^SH/640: a representative in (-p/20, 21p/20) from any |v| < 2^31
+template <int SH>
+RZK_HD uint32_t sreduce(uint32_t v, uint32_t mp)
+{
+    const uint32_t q = (uint32_t)((int32_t)v >> SH);
+    return q * mp + v;
+}
+
+// Integer-valued double |v| < 2^31 -> the centred residue mod p as a double (exact; p odd, v/p never within 2^-12 of a half
+// integer for the values the split-key program produces: the true result is below p/2 - 2^14 in magnitude).
+RZK_HD double center_p_f64(double v, double p, double pinv)
+{
+    const double magic = 6755399441055744.0;                    // 1.5 * 2^52
+#if defined(__CUDA_ARCH__)
+    const double k = __dadd_rn(__fma_rn(v, pinv, magic), -magic);
+    return __fma_rn(-k, p, v);
+#else
+    const double k = (__builtin_fma(v, pinv, magic)) - magic;
+    return __builtin_fma(-k, p, v);
+#endif
+}
+
 // Canonical centred representative of an arbitrary i32 representative of a class mod q
 // (what ZqI64::from(i64) does).  q < 2^32 < 2q so one step suffices.
 RZK_HD int32_t canon_q(int32_t v, uint32_t q)

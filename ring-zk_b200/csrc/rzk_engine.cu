@@ -65,7 +65,7 @@ struct SpAcc1Global<SP, std::enable_if_t<!std::is_void<SP>::value && SP::kAcc1Gl
 
 template <int NP, int MODE, bool KEY = true>
 struct VmSmem {
-    static constexpr int kKP = (MODE == MODE_SPLITKEY) ? 2 * kKeyPolys : kKeyPolys;   // key images per prime
+    static constexpr int kKP = mode_sk(MODE) ? 2 * kKeyPolys : kKeyPolys;   // key images per prime
     static constexpr int kG1 = NP * 2 * kG1Words;
     static constexpr int kG2 = NP * 2 * kLanes * kG2Words;
     static constexpr int kKey = KEY ? NP * kKP * 2 * kPadWords : 0;
@@ -354,6 +354,7 @@ struct rzk_engine {
     uint32_t *d_g2tab = nullptr;
     uint32_t *d_keytab = nullptr;
     uint32_t *d_keytab2 = nullptr;  // split-key images (lo/hi) for prime slot 0, [6][2][576]
+    uint32_t *d_keytab3 = nullptr;  // split-key images for the small prime of MODE_SPLITKEY_S (slot kSignedSlot), signed Shoup form
     uint32_t *d_gstash[kPipe + 1] = {};   // residue stash of the three-prime programs, [SM][warp][half warp][kStashWordsMax]:
                                     // one per pipeline stream (their kernels may overlap) + one for the `_dev` entry points
     int32_t *d_partial[kPipe + 1] = {};   // segment results of product sums cut into segments (small batches), per stream as above
@@ -367,6 +368,7 @@ struct rzk_engine {
     uint32_t *h_range = nullptr;    // pinned host copy of the range word (single-chunk calls)
     bool has_key = false;
     bool generic_commit = false;    // b > kSplitKeyLimit: every commitment runs the two-prime program (exact for any int8 r)
+    bool small_commit = false;      // b == 1 (Params::default()): the split-key program modulo the small prime, signed lazy arithmetic
     uint64_t sigma = 0, cbound = 0, vbound = 0;
     uint32_t small_lim = 0;
     PipeSlot pipe[kPipe];
@@ -387,6 +389,7 @@ struct rzk_engine {
     uint32_t static_respond = 0;
     uint32_t mulsum2_pp = 2;        //   mulsum2_pp phase mixing of the two-accumulator product-sum program (0 / 9 = off)
     uint32_t commit_pp = 2;         //   commit_pp  phase mixing of the split-key commitment program (0 / 9 = off)
+    uint32_t commit_small = 1;      //   commit_small  0: engines with b = 1 use the 30-bit split-key program too (A/B)
     uint32_t ld128 = 0;             //   ld128      OP_FWD fetches int32 rows with 128-bit loads + a shared-memory redistribution (A/B)
     uint32_t verify_pp = 22;        //   verify_pp  phase mixing of the Open verify program with the rotation sum (two staggered groups)
     uint32_t verify_w_pp = 21;      //   verify_w_pp  the same for the Linear / Sum first-equation program with two rotation sums (+2 % on Linear verify)
@@ -433,7 +436,7 @@ void fill_common(const rzk_engine *e, VmLaunch &K, int np, uint32_t n_items, uin
     K.q = (uint32_t)q;
     K.kqh = (q << 29) + (q - 1) / 2;
     K.qd = (double)q; K.qinvd = 1.0 / (double)q;
-    K.p0d = (double)K.pc[0].p; K.p0qinvd = (double)K.pc[0].p / (double)q;
+    K.p0d = (double)K.pc[0].p; K.p0qinvd = (double)K.pc[0].p / (double)q; K.p0invd = 1.0 / (double)K.pc[0].p;
     K.m30 = (uint32_t)((1ull << 62) / q);
     K.norm_abs_lim[0] = (uint32_t)e->cbound; K.norm_sq_lim[0] = (e->cbound + 1) * (e->cbound + 1) - 1;
     K.norm_abs_lim[1] = (uint32_t)e->vbound; K.norm_sq_lim[1] = (e->vbound + 1) * (e->vbound + 1) - 1;
@@ -520,6 +523,7 @@ int launch_sp(rzk_engine *e, VmLaunch &K, cudaStream_t s, uint32_t pp_program = 
 {
     if (e->no_static) {      // RZK_NO_STATIC=1: run the same program through the generic interpreter
         if (SP::kMode == MODE_SPLITKEY) return launch_vm<1, MODE_SPLITKEY>(e, K, s);
+        if (SP::kMode == MODE_SPLITKEY_S) return launch_vm<1, MODE_SPLITKEY_S>(e, K, s);
         if (SP::kMode == MODE_SPLIT) return launch_vm<2, MODE_SPLIT>(e, K, s);
         return SP::kNP == 1 ? launch_vm<1, MODE_SEQ>(e, K, s) : launch_vm<3, MODE_SEQ>(e, K, s);
     }
@@ -569,6 +573,7 @@ constexpr size_t kPolyBytes = (size_t)kN * sizeof(int32_t);
 // ---- phase lowering on device pointers (scratch supplied by the caller of these helpers) ----
 
 constexpr uint32_t kSplitKeyLimit = 15;    // |r| bound of MODE_SPLITKEY: 2*512*2^15*15 < p/2
+constexpr uint32_t kSmallCommitLimit = 1;  // |r| bound of MODE_SPLITKEY_S on the transformed rows: 2*512*2^15 + 127 < kStaticPrimeS/2
 
 // c = [a1;a2].r + [0;x]  (commit.rs:88-128).
 // Default: the split-key program, exact for |r| <= 15 on the transformed rows.  An item outside that range is marked
@@ -598,9 +603,18 @@ int dev_commit(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r, int32
             if (masked) { K.item_mask = rmark; K.mask_div = flag_div; K.any_item = rmark_any; }
             return launch_np(e, 2, K, s);
         }
+        K.rmark = rmark; K.rmark_any = rmark_any;
+        if (e->small_commit) {
+            // b = 1: one small prime, signed lazy arithmetic (MODE_SPLITKEY_S); rows with |r| > 1 are redone like the others
+            K.pc[0] = make_prime_consts(kSignedSlot);
+            K.p0d = (double)K.pc[0].p; K.p0invd = 1.0 / (double)K.pc[0].p;
+            K.small_lim = kSmallCommitLimit;
+            K.keytab = e->d_keytab3;
+            if (norm_vacuous) return launch_sp<SPCommitSplitKeyS>(e, K, s, e->commit_pp);
+            return launch_vm<1, MODE_SPLITKEY_S>(e, K, s);
+        }
         K.small_lim = kSplitKeyLimit;
         K.keytab = e->d_keytab2;
-        K.rmark = rmark; K.rmark_any = rmark_any;
         // measured best for this program: the two halves of the CTA alternate their multiply-heavy windows (rzk_vm_exec.cuh pp_*)
         if (norm_vacuous) return launch_sp<SPCommitSplitKey>(e, K, s, e->commit_pp);
         return launch_vm<1, MODE_SPLITKEY>(e, K, s);
@@ -1021,6 +1035,7 @@ int rzk_create(const rzk_params *params, int device, rzk_engine **out)
     *out = nullptr;
     const rzk_params &P = *params;
     if (kPrimeList[0] != kStaticPrime0) return fail(nullptr, RZK_ERR_INVALID, "prime slot 0 differs from kStaticPrime0");
+    if (kPrimeList[kSignedSlot] != kStaticPrimeS) return fail(nullptr, RZK_ERR_INVALID, "the signed prime slot differs from kStaticPrimeS");
     if (P.N != kN || P.n != 1 || P.k != 3 || P.l != 1)
         return fail(nullptr, RZK_ERR_UNSUPPORTED, "only N=512, (n,k,l)=(1,3,1) is accelerated");
     if (P.q != 3515337053LL || P.b < 1 || P.b > 127 || P.kappa < 1)
@@ -1082,9 +1097,10 @@ int rzk_create(const rzk_params *params, int device, rzk_engine **out)
             const char *p = strstr(tu, key.c_str());
             if (p && (p == tu || p[-1] == ',')) dst = (uint32_t)atoi(p + key.size());
         };
-        val("cta_sync", e->cta_sync); val("pp", e->pp_mode); val("commit_pp", e->commit_pp);
+        val("cta_sync", e->cta_sync); val("pp", e->pp_mode); val("commit_pp", e->commit_pp); val("commit_small", e->commit_small);
         val("mulsum2_pp", e->mulsum2_pp); val("static_respond", e->static_respond); val("verify_pp", e->verify_pp); val("verify_w_pp", e->verify_w_pp); val("ld128", e->ld128);
     }
+    e->small_commit = P.b == 1 && e->commit_small != 0;
     Guard g(device);
     cudaDeviceProp prop;
     ce = cudaGetDeviceProperties(&prop, device);
@@ -1108,6 +1124,7 @@ int rzk_create(const rzk_params *params, int device, rzk_engine **out)
     if (rc == RZK_OK) cu(cudaMemcpy(e->d_g2tab, g2.data(), g2.size() * sizeof(uint32_t), cudaMemcpyHostToDevice), "cudaMemcpy(g2)");
     cu(cudaMalloc(&e->d_keytab, (size_t)kNumPrimeSlots * kKeyPolys * 2 * kPadWords * sizeof(uint32_t)), "cudaMalloc(key)");
     cu(cudaMalloc(&e->d_keytab2, (size_t)2 * kKeyPolys * 2 * kPadWords * sizeof(uint32_t)), "cudaMalloc(key2)");
+    cu(cudaMalloc(&e->d_keytab3, (size_t)2 * kKeyPolys * 2 * kPadWords * sizeof(uint32_t)), "cudaMalloc(key3)");
     cu(cudaMalloc(&e->d_misc, 64), "cudaMalloc(misc)");
     cu(cudaMallocHost(&e->h_range, 64), "cudaMallocHost(range)");
     if (rc == RZK_OK) cu(cudaMemset(e->d_misc, 0, 64), "cudaMemset(misc)");
@@ -1131,6 +1148,7 @@ void rzk_destroy(rzk_engine *e)
     if (e->d_g2tab) cudaFree(e->d_g2tab);
     if (e->d_keytab) cudaFree(e->d_keytab);
     if (e->d_keytab2) cudaFree(e->d_keytab2);
+    if (e->d_keytab3) cudaFree(e->d_keytab3);
     if (e->d_need) cudaFree(e->d_need);
     if (e->d_fs_prefix) cudaFree(e->d_fs_prefix);
     if (e->d_wire_toks) cudaFree(e->d_wire_toks);
@@ -1171,7 +1189,7 @@ int rzk_set_key(rzk_engine *e, const int64_t *a1, const int64_t *a2)
             key_image(T, cen.data(), &img[((size_t)s * kKeyPolys + kk) * 2 * kPadWords]);
         }
     }
-    std::vector<uint32_t> img2((size_t)2 * kKeyPolys * 2 * kPadWords, 0);
+    std::vector<uint32_t> img2((size_t)2 * kKeyPolys * 2 * kPadWords, 0), img3(img2.size(), 0);
     for (int kk = 0; kk < kKeyPolys; ++kk) {
         for (int i = 0; i < kN; ++i) {
             int64_t r = polys[kk][i] % q;
@@ -1179,10 +1197,12 @@ int rzk_set_key(rzk_engine *e, const int64_t *a1, const int64_t *a2)
             cen[i] = r;
         }
         key_image_split(prime_tables(0), cen.data(), &img2[(size_t)kk * 4 * kPadWords]);
+        key_image_split_signed(prime_tables(kSignedSlot), cen.data(), &img3[(size_t)kk * 4 * kPadWords]);
     }
     RZK_CUDA(e, cudaDeviceSynchronize());
     RZK_CUDA(e, cudaMemcpy(e->d_keytab, img.data(), img.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     RZK_CUDA(e, cudaMemcpy(e->d_keytab2, img2.data(), img2.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    RZK_CUDA(e, cudaMemcpy(e->d_keytab3, img3.data(), img3.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     e->has_key = true;
     return RZK_OK;
 }

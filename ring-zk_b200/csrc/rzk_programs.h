@@ -325,6 +325,13 @@ struct SPCommitSplitKey {        // streams: 0 = x (i32), 1 = r (i8), 2 = c out
     static constexpr uint8_t dtype[kMaxStreams] = {DT_I32, DT_I8, DT_I32};
 };
 
+struct SPCommitSplitKeyS {       // the same program modulo the small prime with signed lazy arithmetic (|r| <= 1: Params::default())
+    static constexpr int kPreload = RZK_PRELOAD;
+    static constexpr int kNP = 1, kMode = 3 /* MODE_SPLITKEY_S */;
+    static constexpr Prog prog = [] { Prog p; prog_commit_splitkey(p, 0, 1, 2, false); p.end(); return p; }();
+    static constexpr uint8_t dtype[kMaxStreams] = {DT_I32, DT_I8, DT_I32};
+};
+
 struct SPKeyMatVecT {            // streams: 0 = y (i32), 1 = t out
     static constexpr int kPreload = RZK_PRELOAD;
     static constexpr int kNP = 2, kMode = 1 /* MODE_SPLIT */;

@@ -9,8 +9,22 @@ namespace rzk {
 
 const uint32_t kPrimeList[kNumPrimeSlots] = {      // slot 0 is also the compile-time prime of the split-key program (kStaticPrime0)
     1073692673u, 1073668097u, 1073655809u,   // < 2^30
-    195198977u, 195186689u, 195162113u,      // < 2^32 / 22
+    67153921u, 91672577u, 91611137u,         // small primes for the signed lazy arithmetic (rzk_arith.cuh): slot 3 = kStaticPrimeS = 2^26 + 45057
 };
+
+bool slot_is_signed(int slot) { return slot >= 3; }
+
+// w in [0, p) -> centred value and signed Shoup companion round(w * 2^32 / p), both as 32-bit words
+void signed_shoup_pair(uint32_t w, uint32_t p, uint32_t &wc, uint32_t &wcp)
+{
+    int64_t c = (int64_t)w;
+    if (c > (int64_t)(p - 1) / 2) c -= (int64_t)p;
+    const __int128 num = ((__int128)c << 32) * 2 + (__int128)p;          // floor((2 c 2^32 + p) / (2 p)) = round(c 2^32 / p)
+    __int128 qv = num / (2 * (__int128)p);
+    if (num % (2 * (__int128)p) < 0) --qv;                               // floor for negative numerators
+    wc = (uint32_t)(int32_t)c;
+    wcp = (uint32_t)(int32_t)qv;
+}
 
 uint32_t mod_pow(uint32_t b, uint64_t e, uint32_t p)
 {
@@ -34,7 +48,7 @@ static int brv9(int x)
     return r;
 }
 
-static void build(PrimeTables &T, uint32_t p)
+static void build(PrimeTables &T, uint32_t p, bool signed_form)
 {
     memset(&T, 0, sizeof(T));
     T.p = p;
@@ -78,6 +92,14 @@ static void build(PrimeTables &T, uint32_t p)
             }
         }
     }
+    if (signed_form) {
+        // the kernel-side tables of a signed slot hold (centred w, signed companion); T.tw keeps the canonical residues
+        for (int d = 0; d < 2; ++d) {
+            for (int idx = 0; idx < 32; ++idx) signed_shoup_pair(T.tw[d][idx][0], p, T.g1[d][idx][0], T.g1[d][idx][1]);
+            for (int t = 0; t < kLanes; ++t)
+                for (int w = 0; w < kG2Words; w += 2) signed_shoup_pair(T.g2[d][t][w], p, T.g2[d][t][w], T.g2[d][t][w + 1]);
+        }
+    }
 }
 
 const PrimeTables &prime_tables(int slot)
@@ -85,7 +107,7 @@ const PrimeTables &prime_tables(int slot)
     static PrimeTables tabs[kNumPrimeSlots];
     static std::once_flag once[kNumPrimeSlots];
     if (slot < 0 || slot >= kNumPrimeSlots) throw std::out_of_range("prime slot");
-    std::call_once(once[slot], [slot] { build(tabs[slot], kPrimeList[slot]); });
+    std::call_once(once[slot], [slot] { build(tabs[slot], kPrimeList[slot], slot_is_signed(slot)); });
     return tabs[slot];
 }
 
@@ -190,6 +212,20 @@ void key_image(const PrimeTables &T, const int64_t *poly, uint32_t *out)
         out[pad_index(i)] = w;
         out[kPadWords + pad_index(i)] = shoup_companion(w, T.p);
     }
+}
+
+// the signed-slot form of a key image: centred residues with signed Shoup companions
+static void key_image_to_signed(const PrimeTables &T, uint32_t *out)
+{
+    for (int i = 0; i < kN; ++i)
+        signed_shoup_pair(out[pad_index(i)], T.p, out[pad_index(i)], out[kPadWords + pad_index(i)]);
+}
+
+void key_image_split_signed(const PrimeTables &T, const int64_t *poly, uint32_t *out)
+{
+    key_image_split(T, poly, out);
+    key_image_to_signed(T, out);
+    key_image_to_signed(T, out + 2 * kPadWords);
 }
 
 void key_image_split(const PrimeTables &T, const int64_t *poly, uint32_t *out)

@@ -123,7 +123,7 @@ struct VmLaunch {
     uint64_t kqh;              // q * 2^29 + (q-1)/2   (reduce_q_centered offset)
     double qd, qinvd;          // q and 1/q as doubles (reduce_q_centered_f64)
     double p0d, p0qinvd;       // prime 0 and p0 / q as doubles (crt2_mod_q_f64)
-    uint64_t pad64_;
+    double p0invd;             // 1 / prime 0 (center_p_f64, MODE_SPLITKEY_S)
     uint64_t norm_sq_lim[2];   // (bound+1)^2 - 1 for [0]=commit, [1]=verify constraint
     uint32_t norm_abs_lim[2];  // bound
     uint32_t q;

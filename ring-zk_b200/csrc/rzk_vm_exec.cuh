@@ -57,8 +57,16 @@ struct uint2 { uint32_t x, y; };
 
 namespace rzk {
 
-enum { MODE_SEQ = 0, MODE_SPLIT = 1, MODE_SPLITKEY = 2 };
+enum { MODE_SEQ = 0, MODE_SPLIT = 1, MODE_SPLITKEY = 2, MODE_SPLITKEY_S = 3 };
+// MODE_SPLITKEY_S: the split-key commitment for |r| <= 1 (Params::default(): b = 1) modulo ONE SMALL prime with signed lazy
+// arithmetic (rzk_arith.cuh): |a_lo r1 + a_lo' r2 + r0| <= 2^25 + 127 < p/2 for p = 67153921, and 2^31 / p = 31.98 leaves room
+// for nine forward stages without any correction (4-instruction butterflies) and for inverse stages that only reduce the
+// few elements whose run of sums would overflow (14 of 288 per transform).  Same program, same data flow as MODE_SPLITKEY.
+constexpr bool mode_sk(int mode) { return mode == MODE_SPLITKEY || mode == MODE_SPLITKEY_S; }
 constexpr uint32_t kStaticPrime0 = 1073692673u;      // kPrimeList[0] (rzk_tables.cpp); 4p - 1 < 2^32
+constexpr uint32_t kStaticPrimeS = 67153921u;        // kPrimeList[kSignedSlot]: 2^26 + 45057, == 1 (mod 4096)
+constexpr int kSignedSlot = 3;                       // its slot: twiddles and key images in the signed Shoup form
+constexpr int kSignedShift = 26;                     // floor(log2 p) (sreduce)
 constexpr uint32_t kAddCap = 0xFFFFFFFEu;            // >= 4p - 2 for every p < 2^30: min(a + b, kAddCap) == a + b in the butterflies
 
 struct Lane {
@@ -259,6 +267,105 @@ RZK_VM void inv_g1(uint32_t (&a)[kElems], const uint32_t *g1tab, uint32_t p, uin
     g1_stage<0, 1>(a, g1, p, p2, z, cap);
 }
 
+// ---- signed lazy transforms (MODE_SPLITKEY_S; rzk_arith.cuh): same geometry, same table layout (w centred, w' signed)
+template <int S, int DIR>
+RZK_VM void g1_stage_s(uint32_t (&a)[kElems], const uint2 *g1, uint32_t mp)
+{
+    constexpr int half = 16 >> S;
+    RZK_UNROLL
+    for (int b = 0; b < (1 << S); ++b) {
+        const uint2 w = g1[(1 << S) + b];
+        RZK_UNROLL
+        for (int j = 0; j < half; ++j) {
+            const int i0 = b * 2 * half + j;
+            if (DIR == 0) ct_bfly_s(a[i0], a[i0 + half], w.x, w.y, mp);
+            else gs_bfly_s(a[i0], a[i0 + half], w.x, w.y, mp);
+        }
+    }
+}
+
+template <int S, int DIR>
+RZK_VM void g2_stage_s(uint32_t (&a)[kElems], const uint4 *tw4, uint32_t mp)
+{
+    constexpr int half = 256 >> S;                // 8,4,2,1
+    constexpr int nb = 1 << (S - 4);              // 2,4,8,16 blocks
+    constexpr int base = (S == 5) ? 0 : (S == 6) ? 1 : (S == 7) ? 3 : 7;
+    RZK_UNROLL
+    for (int b2 = 0; b2 < nb / 2; ++b2) {
+        const uint4 q = tw4[base + b2];
+        RZK_UNROLL
+        for (int j = 0; j < half; ++j) {
+            const int i0 = (2 * b2) * 2 * half + j;
+            if (DIR == 0) ct_bfly_s(a[i0], a[i0 + half], q.x, q.y, mp);
+            else gs_bfly_s(a[i0], a[i0 + half], q.x, q.y, mp);
+        }
+        RZK_UNROLL
+        for (int j = 0; j < half; ++j) {
+            const int i0 = (2 * b2 + 1) * 2 * half + j;
+            if (DIR == 0) ct_bfly_s(a[i0], a[i0 + half], q.z, q.w, mp);
+            else gs_bfly_s(a[i0], a[i0 + half], q.z, q.w, mp);
+        }
+    }
+}
+
+// forward: inputs |a| <= 127, every stage adds at most 5p/4: below 11.3 p + 127 at the end, no correction anywhere
+RZK_VM void fwd_g1_s(uint32_t (&a)[kElems], const uint32_t *g1tab, uint32_t mp)
+{
+    const uint2 *g1 = reinterpret_cast<const uint2 *>(g1tab);
+    g1_stage_s<0, 0>(a, g1, mp);
+    g1_stage_s<1, 0>(a, g1, mp);
+    g1_stage_s<2, 0>(a, g1, mp);
+    g1_stage_s<3, 0>(a, g1, mp);
+    g1_stage_s<4, 0>(a, g1, mp);
+}
+
+RZK_VM void fwd_g2_s(uint32_t (&a)[kElems], const uint32_t *tw, uint32_t mp)
+{
+    const uint4 *tw4 = reinterpret_cast<const uint4 *>(tw);
+    g2_stage_s<5, 0>(a, tw4, mp);
+    g2_stage_s<6, 0>(a, tw4, mp);
+    g2_stage_s<7, 0>(a, tw4, mp);
+    g2_stage_s<8, 0>(a, tw4, mp);
+}
+
+// inverse: a sum output doubles the magnitude, a product output resets it to 5p/4; a butterfly needs |x| + |y| < 2^31 =
+// 31.98 p.  Inputs: at most two key products, |a| <= 5p/2.  Element e has taken the sum path at a stage exactly when the bit
+// of e that the stage pairs is clear, so the magnitudes are known at compile time:
+//   contiguous layout (distances 1, 2, 4, 8): the elements with bits 0..2 clear reach 20 p after three stages and are reduced
+//   before the fourth; after it the elements with bit 3 clear, bit 2 clear and one of bits 1, 0 set hold 5 p or 10 p and are
+//   reduced as well, so that every lane enters the strided layout with at most 5p/2 per element (the history of the first four
+//   stages depends on the LANE there, so it has to be uniform);
+//   strided layout (distances 1 .. 16): again the elements with bits 0..2 clear before the fourth stage.
+// 14 reductions (two instructions each) per transform; the results stay below 20.2 p < 2^31.
+RZK_VM void inv_g2_s(uint32_t (&a)[kElems], const uint32_t *tw, uint32_t mp)
+{
+    const uint4 *tw4 = reinterpret_cast<const uint4 *>(tw);
+    g2_stage_s<8, 1>(a, tw4, mp);
+    g2_stage_s<7, 1>(a, tw4, mp);
+    g2_stage_s<6, 1>(a, tw4, mp);
+    RZK_UNROLL
+    for (int e = 0; e < kElems; e += 8) a[e] = sreduce<kSignedShift>(a[e], mp);
+    g2_stage_s<5, 1>(a, tw4, mp);
+    RZK_UNROLL
+    for (int e = 0; e < kElems; e += 16) {
+        a[e + 1] = sreduce<kSignedShift>(a[e + 1], mp);
+        a[e + 2] = sreduce<kSignedShift>(a[e + 2], mp);
+        a[e + 3] = sreduce<kSignedShift>(a[e + 3], mp);
+    }
+}
+
+RZK_VM void inv_g1_s(uint32_t (&a)[kElems], const uint32_t *g1tab, uint32_t mp)
+{
+    const uint2 *g1 = reinterpret_cast<const uint2 *>(g1tab);
+    g1_stage_s<4, 1>(a, g1, mp);
+    g1_stage_s<3, 1>(a, g1, mp);
+    g1_stage_s<2, 1>(a, g1, mp);
+    RZK_UNROLL
+    for (int e = 0; e < kElems; e += 8) a[e] = sreduce<kSignedShift>(a[e], mp);
+    g1_stage_s<1, 1>(a, g1, mp);
+    g1_stage_s<0, 1>(a, g1, mp);
+}
+
 // ---------------------------------------------------------------- global memory
 
 RZK_VM uint64_t stream_poly(const Stream &s, uint32_t item, uint32_t off)
@@ -279,6 +386,7 @@ RZK_VM uint4 rot_ld128(const void *p)
 }
 
 
+template <bool SGN = false>
 RZK_VM void op_fwd(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const Op &op, int it, uint32_t dtype)
 {
     const Stream st = K.st[op.a];
@@ -327,8 +435,12 @@ RZK_VM void op_fwd(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const Op
             for (int m = 0; m < kElems; ++m) mx = umax32(mx, (uint32_t)v[m] + K.small_lim);
             L.rerr |= (mx > 2u * K.small_lim) ? 1u : 0u;
         }
-        // centred value + 2p lies in (0, 4p): a valid lazy input of the forward butterflies
-        if (op.b & FWD_SCALED) {
+        if constexpr (SGN) {
+            // signed lazy form: the small operand itself is the input (the program checks |v| <= small_lim first)
+            RZK_UNROLL
+            for (int m = 0; m < kElems; ++m) L.cur[m] = (uint32_t)v[m];
+        } else if (op.b & FWD_SCALED) {
+            // centred value + 2p lies in (0, 4p): a valid lazy input of the forward butterflies
             RZK_UNROLL
             for (int m = 0; m < kElems; ++m)
                 L.cur[m] = shoup_mul(pc.rn, pc.rnp, (uint32_t)v[m] + pc.p2, pc.p);
@@ -339,7 +451,8 @@ RZK_VM void op_fwd(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const Op
 #if defined(__CUDA_ARCH__)
         pp_acquire(K);
 #endif
-        fwd_g1(L.cur, ctx.g1 + (L.pi * 2 + 0) * kG1Words, pc.p, pc.p2, pc.pad_, L.cap);
+        if constexpr (SGN) fwd_g1_s(L.cur, ctx.g1 + (L.pi * 2 + 0) * kG1Words, 0u - pc.p);
+        else fwd_g1(L.cur, ctx.g1 + (L.pi * 2 + 0) * kG1Words, pc.p, pc.p2, pc.pad_, L.cap);
         RZK_UNROLL
         for (int m = 0; m < kElems; ++m) {
             const int i = t + kLanes * m;
@@ -355,7 +468,8 @@ RZK_VM void op_fwd(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const Op
             const uint4 q = row[j];
             L.cur[4 * j + 0] = q.x; L.cur[4 * j + 1] = q.y; L.cur[4 * j + 2] = q.z; L.cur[4 * j + 3] = q.w;
         }
-        fwd_g2(L.cur, ctx.g2 + ((L.pi * 2 + 0) * kLanes + t) * kG2Words, L.pc.p, L.pc.p2, L.pc.pad_, L.cap);
+        if constexpr (SGN) fwd_g2_s(L.cur, ctx.g2 + ((L.pi * 2 + 0) * kLanes + t) * kG2Words, 0u - L.pc.p);
+        else fwd_g2(L.cur, ctx.g2 + ((L.pi * 2 + 0) * kLanes + t) * kG2Words, L.pc.p, L.pc.p2, L.pc.pad_, L.cap);
     }
     RZK_SYNC();
 #if defined(__CUDA_ARCH__)
@@ -382,6 +496,43 @@ RZK_VM void mac_key(uint32_t (&acc)[kElems], const uint32_t (&cur)[kElems], cons
             // (a first, positive term is already in [0, 2p): no correction)
             acc[e] = (init && !neg) ? tt : csub((init ? 0u : acc[e]) + tt, p2);
         }
+    }
+}
+
+// signed lazy form (MODE_SPLITKEY_S): three instructions per term, the accumulation rides on the first multiply-add;
+// |acc| grows by 5p/4 per term.  Key rows hold centred values with signed Shoup companions.
+RZK_VM void mac_key_s(uint32_t (&acc)[kElems], const uint32_t (&cur)[kElems], const uint32_t *krow, int t, uint32_t flags, uint32_t mp)
+{
+    const uint4 *w4 = reinterpret_cast<const uint4 *>(krow + 36 * t);
+    const uint4 *wp4 = reinterpret_cast<const uint4 *>(krow + kPadWords + 36 * t);
+    const bool init = flags & MAC_INIT;
+    RZK_UNROLL
+    for (int j = 0; j < 8; ++j) {
+        const uint4 w = w4[j], wp = wp4[j];
+        const uint32_t ww[4] = {w.x, w.y, w.z, w.w}, wwp[4] = {wp.x, wp.y, wp.z, wp.w};
+        RZK_UNROLL
+        for (int c = 0; c < 4; ++c) {
+            const int e = 4 * j + c;
+            acc[e] = sshoup_mac(ww[c], wwp[c], cur[e], mp, init ? 0u : acc[e]);
+        }
+    }
+}
+
+RZK_VM void mac_key_smem_s(uint32_t *acc1, const uint32_t (&cur)[kElems], const uint32_t *krow, int t, uint32_t flags, uint32_t mp)
+{
+    const uint4 *w4 = reinterpret_cast<const uint4 *>(krow + 36 * t);
+    const uint4 *wp4 = reinterpret_cast<const uint4 *>(krow + kPadWords + 36 * t);
+    uint4 *a4 = reinterpret_cast<uint4 *>(acc1);
+    const bool init = flags & MAC_INIT;
+    RZK_UNROLL
+    for (int j = 0; j < 8; ++j) {
+        const uint4 w = w4[j], wp = wp4[j];
+        uint4 a = init ? uint4{0u, 0u, 0u, 0u} : a4[j * kLanes + t];
+        a.x = sshoup_mac(w.x, wp.x, cur[4 * j + 0], mp, a.x);
+        a.y = sshoup_mac(w.y, wp.y, cur[4 * j + 1], mp, a.y);
+        a.z = sshoup_mac(w.z, wp.z, cur[4 * j + 2], mp, a.z);
+        a.w = sshoup_mac(w.w, wp.w, cur[4 * j + 3], mp, a.w);
+        a4[j * kLanes + t] = a;
     }
 }
 
@@ -992,7 +1143,8 @@ RZK_VM void inv_core(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const 
                 L.cur[4 * j + 0] = a.x; L.cur[4 * j + 1] = a.y; L.cur[4 * j + 2] = a.z; L.cur[4 * j + 3] = a.w;
             }
         }
-        inv_g2(L.cur, ctx.g2 + ((L.pi * 2 + 1) * kLanes + t) * kG2Words, pc.p, pc.p2, pc.pad_, L.cap);
+        if constexpr (MODE == MODE_SPLITKEY_S) inv_g2_s(L.cur, ctx.g2 + ((L.pi * 2 + 1) * kLanes + t) * kG2Words, 0u - pc.p);
+        else inv_g2(L.cur, ctx.g2 + ((L.pi * 2 + 1) * kLanes + t) * kG2Words, pc.p, pc.p2, pc.pad_, L.cap);
         uint4 *row = reinterpret_cast<uint4 *>(ctx.buf + 36 * t);
         RZK_UNROLL
         for (int j = 0; j < 8; ++j) {
@@ -1010,9 +1162,13 @@ RZK_VM void inv_core(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const 
             const int i = t + kLanes * m;
             L.cur[m] = ctx.buf[i + ((i >> 5) << 2)];
         }
-        inv_g1(L.cur, ctx.g1 + (L.pi * 2 + 1) * kG1Words, pc.p, pc.p2, pc.pad_, L.cap);
-        RZK_UNROLL
-        for (int m = 0; m < kElems; ++m) L.cur[m] = csub(L.cur[m], pc.p);     // [0,2p) -> [0,p)
+        if constexpr (MODE == MODE_SPLITKEY_S) {
+            inv_g1_s(L.cur, ctx.g1 + (L.pi * 2 + 1) * kG1Words, 0u - pc.p);    // any representative below 20.2 p: centred in the epilogue
+        } else {
+            inv_g1(L.cur, ctx.g1 + (L.pi * 2 + 1) * kG1Words, pc.p, pc.p2, pc.pad_, L.cap);
+            RZK_UNROLL
+            for (int m = 0; m < kElems; ++m) L.cur[m] = csub(L.cur[m], pc.p);     // [0,2p) -> [0,p)
+        }
     }
     RZK_SYNC();
 #if defined(__CUDA_ARCH__)
@@ -1057,6 +1213,13 @@ RZK_VM void inv_core(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const 
                     // integer (|lo| < 2^29, |small| < 2^7): one add instead of a conversion and a DADD
                     const int32_t lo = small ? (int32_t)v0 + small[li_][j % CNT] : (int32_t)v0;
                     V[li_][j % CNT] = f64_exact_fma(f64_exact_i32((int32_t)v1), 65536.0, f64_exact_i32(lo));
+                } else if (MODE == MODE_SPLITKEY_S) {
+                    // the residues arrive as arbitrary representatives (|v| < 20.2 p + 2^7 < 2^31): centred on the FP64 pipe,
+                    // v - p * rint(v / p), exact because the true parts are below p/2 - 2^14 in magnitude
+                    const int32_t lo = small ? (int32_t)v0 + small[li_][j % CNT] : (int32_t)v0;
+                    const double lod = center_p_f64(f64_exact_i32(lo), K.p0d, K.p0invd);
+                    const double hid = center_p_f64(f64_exact_i32((int32_t)v1), K.p0d, K.p0invd);
+                    V[li_][j % CNT] = f64_exact_fma(hid, 65536.0, lod);
                 } else {
                     V[li_][j % CNT] = crt2_mod_q_f64(K, v0, v1);
                 }
@@ -1253,10 +1416,10 @@ template <int NP, int MODE>
 RZK_VM void vm_run_item(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs)
 {
     static_assert(MODE != MODE_SPLIT || NP == 2, "MODE_SPLIT maps the two half warps to two primes");
-    static_assert(MODE != MODE_SPLITKEY || NP == 1, "MODE_SPLITKEY works modulo one prime");
+    static_assert(!mode_sk(MODE) || NP == 1, "MODE_SPLITKEY works modulo one prime");
     constexpr int RED_N = (MODE != MODE_SEQ) ? 32 : 16;
     constexpr int PRIME_ITERS = (MODE != MODE_SEQ) ? 1 : NP;
-    constexpr int KP = (MODE == MODE_SPLITKEY) ? 2 * kKeyPolys : kKeyPolys;     // key images per prime
+    constexpr int KP = mode_sk(MODE) ? 2 * kKeyPolys : kKeyPolys;     // key images per prime
     RZK_EACH_LANE { RZK_LANE; L.fail = 0; L.rerr = 0; }
     int pc = 0;
     RZK_NOUNROLL
@@ -1272,7 +1435,7 @@ RZK_VM void vm_run_item(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs)
         for (int prime_iter = 0; prime_iter < PRIME_ITERS; ++prime_iter) {
             RZK_EACH_LANE {
                 RZK_LANE;
-                L.pi = (MODE == MODE_SPLIT) ? ctx.hw : (MODE == MODE_SPLITKEY ? 0 : prime_iter);
+                L.pi = (MODE == MODE_SPLIT) ? ctx.hw : (mode_sk(MODE) ? 0 : prime_iter);
                 L.pc = K.pc[L.pi];
                 L.cap = kAddCap;
             }
@@ -1286,16 +1449,21 @@ RZK_VM void vm_run_item(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs)
 #if defined(__CUDA_ARCH__)
                     cta_lockstep(K);
 #endif
-                    op_fwd(K, lanes, ctxs, op, it, K.st[op.a].dtype);
+                    op_fwd<MODE == MODE_SPLITKEY_S>(K, lanes, ctxs, op, it, K.st[op.a].dtype);
                     break;
                 case OP_MACK:
                     RZK_EACH_LANE {
                         RZK_LANE;
                         // MODE_SPLITKEY: half warp h uses the lo (h = 0) / hi (h = 1) image of key poly b
-                        const int kidx = (MODE == MODE_SPLITKEY) ? (2 * (int)op.b + ctx.hw) : (int)op.b;
+                        const int kidx = mode_sk(MODE) ? (2 * (int)op.b + ctx.hw) : (int)op.b;
                         const uint32_t *krow = ctx.key + ((L.pi * KP + kidx) * 2) * kPadWords;
-                        if (op.a == 0) mac_key(L.acc0, L.cur, krow, t, op.c, L.pc.p, L.pc.p2);
-                        else mac_key_smem(ctx.acc1, L.cur, krow, t, op.c, L.pc.p, L.pc.p2);
+                        if constexpr (MODE == MODE_SPLITKEY_S) {
+                            if (op.a == 0) mac_key_s(L.acc0, L.cur, krow, t, op.c, 0u - L.pc.p);
+                            else mac_key_smem_s(ctx.acc1, L.cur, krow, t, op.c, 0u - L.pc.p);
+                        } else {
+                            if (op.a == 0) mac_key(L.acc0, L.cur, krow, t, op.c, L.pc.p, L.pc.p2);
+                            else mac_key_smem(ctx.acc1, L.cur, krow, t, op.c, L.pc.p, L.pc.p2);
+                        }
                     }
                     break;
                 case OP_MACV:
@@ -1457,7 +1625,7 @@ template <class SP, int NP, int MODE, int PC>
 RZK_VM void sp_exec(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int it, int prime_iter)
 {
     constexpr Op op = SP::prog.ops[PC];
-    constexpr int KP = (MODE == MODE_SPLITKEY) ? 2 * kKeyPolys : kKeyPolys;
+    constexpr int KP = mode_sk(MODE) ? 2 * kKeyPolys : kKeyPolys;
     if constexpr (op.code == OP_SEG || op.code == OP_END || op.code == OP_ENDLOOP) {
         return;
     } else if constexpr (op.code == OP_LOOP) {
@@ -1469,7 +1637,7 @@ RZK_VM void sp_exec(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int it,
         constexpr int next = sp_skip_epilogue(SP::prog, PC + 1);
         {
             typename Epi<MODE>::V_t V[RZK_NL][Epi<MODE>::kCount];
-            if constexpr (MODE == MODE_SPLITKEY && SP::prog.ops[PC + 1].code == OP_ADDP && SP::dtype[SP::prog.ops[PC + 1].a] == DT_I8 &&
+            if constexpr (mode_sk(MODE) && SP::prog.ops[PC + 1].code == OP_ADDP && SP::dtype[SP::prog.ops[PC + 1].a] == DT_I8 &&
                           !(SP::prog.ops[PC + 1].c & MAC_NEG)) {
                 constexpr Op e0 = SP::prog.ops[PC + 1];
                 int32_t small[RZK_NL][Epi<MODE>::kCount];
@@ -1506,14 +1674,20 @@ RZK_VM void sp_exec(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int it,
             if (K.cta_sync < 8 || SP::prog.ops[PC - 1].code == OP_SEG) cta_lockstep(K);
 #endif
             constexpr uint32_t dt = SP::dtype[op.a];
-            op_fwd(K, lanes, ctxs, op, it, dt);
+            op_fwd<MODE == MODE_SPLITKEY_S>(K, lanes, ctxs, op, it, dt);
         } else if constexpr (op.code == OP_MACK) {
             RZK_EACH_LANE {
                 RZK_LANE;
-                const int kidx = (MODE == MODE_SPLITKEY) ? (2 * (int)op.b + ctx.hw) : (int)op.b;
+                const int kidx = mode_sk(MODE) ? (2 * (int)op.b + ctx.hw) : (int)op.b;
                 const uint32_t *krow = ctx.key + ((L.pi * KP + kidx) * 2) * kPadWords;
-                if constexpr (op.a == 0) mac_key(L.acc0, L.cur, krow, t, op.c, L.pc.p, L.pc.p2);
-                else mac_key_smem(ctx.acc1, L.cur, krow, t, op.c, L.pc.p, L.pc.p2);
+                if constexpr (MODE == MODE_SPLITKEY_S) {
+                    static_assert(MODE != MODE_SPLITKEY_S || !(op.c & MAC_NEG), "the signed lazy key products have no negated form");
+                    if constexpr (op.a == 0) mac_key_s(L.acc0, L.cur, krow, t, op.c, 0u - L.pc.p);
+                    else mac_key_smem_s(ctx.acc1, L.cur, krow, t, op.c, 0u - L.pc.p);
+                } else {
+                    if constexpr (op.a == 0) mac_key(L.acc0, L.cur, krow, t, op.c, L.pc.p, L.pc.p2);
+                    else mac_key_smem(ctx.acc1, L.cur, krow, t, op.c, L.pc.p, L.pc.p2);
+                }
             }
         } else if constexpr (op.code == OP_MACV) {
             RZK_EACH_LANE {
@@ -1567,9 +1741,12 @@ RZK_VM void sp_segments(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs)
         for (int prime_iter = 0; prime_iter < PRIME_ITERS; ++prime_iter) {
             RZK_EACH_LANE {
                 RZK_LANE;
-                L.pi = (MODE == MODE_SPLIT) ? ctx.hw : (MODE == MODE_SPLITKEY ? 0 : prime_iter);
+                L.pi = (MODE == MODE_SPLIT) ? ctx.hw : (mode_sk(MODE) ? 0 : prime_iter);
                 L.pc = K.pc[L.pi];
                 L.cap = kAddCap;
+                if (MODE == MODE_SPLITKEY_S) {
+                    L.pc.p = kStaticPrimeS; L.pc.p2 = 2u * kStaticPrimeS; L.pc.half = (kStaticPrimeS - 1u) / 2u;
+                }
                 if (MODE == MODE_SPLITKEY) {
                     // one fixed prime (slot 0, checked at key setup): its constants become immediates
                     L.pc.p = kStaticPrime0; L.pc.p2 = 2u * kStaticPrime0; L.pc.half = (kStaticPrime0 - 1u) / 2u;

@@ -56,14 +56,15 @@ struct Emu {
         memset(&K, 0, sizeof(K));
         g1.assign((size_t)np * 2 * kG1Words, 0);
         g2.resize((size_t)np * 2 * kLanes * kG2Words);
-        key.resize((size_t)np * kKeyPolys * 2 * kPadWords * (mode == MODE_SPLITKEY ? 2 : 1));
+        key.resize((size_t)np * kKeyPolys * 2 * kPadWords * (mode_sk(mode) ? 2 : 1));
         for (int i = 0; i < np; ++i) {
             slots[i] = sl[i];
             const PrimeTables &T = prime_tables(sl[i]);
             for (int d = 0; d < 2; ++d) memcpy(&g1[((size_t)i * 2 + d) * kG1Words], T.g1[d], sizeof(T.g1[d]));
             memcpy(&g2[(size_t)i * 2 * kLanes * kG2Words], T.g2, sizeof(T.g2));
             for (int k = 0; k < kKeyPolys; ++k) {
-                if (mode == MODE_SPLITKEY) key_image_split(T, keypolys + (size_t)k * kN, &key[(size_t)k * 4 * kPadWords]);
+                if (mode == MODE_SPLITKEY_S) key_image_split_signed(T, keypolys + (size_t)k * kN, &key[(size_t)k * 4 * kPadWords]);
+                else if (mode == MODE_SPLITKEY) key_image_split(T, keypolys + (size_t)k * kN, &key[(size_t)k * 4 * kPadWords]);
                 else key_image(T, keypolys + (size_t)k * kN, &key[((size_t)i * kKeyPolys + k) * 2 * kPadWords]);
             }
             K.pc[i] = make_prime_consts(sl[i]);
@@ -72,7 +73,7 @@ struct Emu {
         K.q = (uint32_t)Q;
         K.kqh = ((uint64_t)Q << 29) + (uint64_t)(Q - 1) / 2;
         K.qd = (double)Q; K.qinvd = 1.0 / (double)Q;
-        K.p0d = (double)K.pc[0].p; K.p0qinvd = (double)K.pc[0].p / (double)Q;
+        K.p0d = (double)K.pc[0].p; K.p0qinvd = (double)K.pc[0].p / (double)Q; K.p0invd = 1.0 / (double)K.pc[0].p;
         K.m30 = (uint32_t)((1ull << 62) / (uint64_t)Q);
         rzko_params P = rzko_default_params(kN);
         uint64_t cb = rzko_commit_bound(&P), vb = rzko_verify_bound(&P);
@@ -121,6 +122,7 @@ struct Emu {
             }
             if constexpr (!std::is_void<SP>::value) vm_run_static<SP>(K, lanes, ctxs);
             else if (mode == MODE_SPLITKEY) vm_run_item<1, MODE_SPLITKEY>(K, lanes, ctxs);
+            else if (mode == MODE_SPLITKEY_S) vm_run_item<1, MODE_SPLITKEY_S>(K, lanes, ctxs);
             else if (np == 1) vm_run_item<1, MODE_SEQ>(K, lanes, ctxs);
             else if (np == 2) vm_run_item<2, MODE_SPLIT>(K, lanes, ctxs);
             else vm_run_item<3, MODE_SEQ>(K, lanes, ctxs);
@@ -553,6 +555,53 @@ int main(int argc, char **argv)
             }
         }
         printf("mulsum T=%d ok, ops=%d\n", T, pr.n);
+    }
+
+    // ---------------- split-key commit modulo the small prime, signed lazy arithmetic (|r| <= 1) ----------------
+    {
+        const int LS[1] = {kSignedSlot};
+        for (int pass = 0; pass < 3; ++pass) {
+            std::vector<int8_t> r1(r.size());
+            for (size_t i = 0; i < r1.size(); ++i) r1[i] = (int8_t)((int)(rnd() % 3) - 1);
+            if (pass == 1) for (size_t i = 0; i < r1.size(); ++i) r1[i] = (i % (3 * N) < N) ? (int8_t)((i & 1) ? 127 : -128) : (int8_t)1;   // worst case of the bound: r0 at the int8 limits, r1 = r2 = 1
+            if (pass == 2) for (size_t i = 0; i < r1.size(); ++i) r1[i] = (i % (3 * N) < N) ? (int8_t)-128 : (int8_t)((i & 1) ? 1 : -1);
+            std::vector<int32_t> c_s(B * 2 * N, 0);
+            auto r1_64 = widen8(r1);
+            std::vector<int64_t> c2(B * 2 * N);
+            std::vector<uint8_t> ok2(B);
+            rzko_commit_batch(&P, a1.data(), a2.data(), B, x64.data(), r1_64.data(), c2.data(), ok2.data(), 1);
+            {
+                Emu E(1, LS, keyp.data(), B, MODE_SPLITKEY_S);
+                Prog pr;
+                prog_commit_splitkey(pr, 0, 1, 2);
+                pr.end(); pr.install(E.K);
+                E.K.small_lim = 1;
+                E.stream(0, x.data(), 1, DT_I32); E.stream(1, r1.data(), 3, DT_I8); E.stream(2, c_s.data(), 2, DT_I32);
+                E.run(B);
+                CHECK(same(c_s, c2), "signed split-key commit mismatch (pass %d)", pass);
+                for (int b = 0; b < B; ++b) CHECK(E.flags[b] == 0, "signed split-key flags[%d]=%u", b, E.flags[b]);
+            }
+            {
+                std::fill(c_s.begin(), c_s.end(), 0);
+                Emu E(1, LS, keyp.data(), B, MODE_SPLITKEY_S);
+                SPCommitSplitKeyS::prog.install(E.K);
+                E.K.small_lim = 1;
+                E.stream(0, x.data(), 1, DT_I32); E.stream(1, r1.data(), 3, DT_I8); E.stream(2, c_s.data(), 2, DT_I32);
+                E.run<SPCommitSplitKeyS>(B);
+                CHECK(same(c_s, c2), "static signed split-key commit mismatch (pass %d)", pass);
+                for (int b = 0; b < B; ++b) CHECK(E.flags[b] == 0, "static signed split-key flags");
+                if (pass == 0) {
+                    // |r| = 2 on a transformed row must raise the range flag; on row 0 it must not
+                    r1[2 * N + 3] = 2;
+                    if (B > 1) r1[(size_t)3 * N + 5] = 100;
+                    E.flags.assign(B, 0); E.K.flags = E.flags.data();
+                    E.run<SPCommitSplitKeyS>(B);
+                    CHECK(E.flags[0] == FLAG_RANGE, "signed split-key range flag item 0: %u", E.flags[0]);
+                    if (B > 1) CHECK(E.flags[1] == 0, "signed split-key range flag item 1: %u", E.flags[1]);
+                }
+            }
+        }
+        printf("signed split-key commit ok\n");
     }
 
     // ---------------- compile-time programs (vm_run_static) against the same oracle outputs ----------------
