@@ -99,6 +99,18 @@ int rzk_sync(rzk_engine *e, void *stream);
 int rzk_commit_batch(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r,
                      int32_t *c, uint8_t *ok_bitmap);
 
+/* The same commitment with the randomness packed at 2 bits per coefficient -- what Params::default() (b = 1, r in {-1, 0, 1},
+ * commit.rs:96-101 via polynomial.rs:14-23) needs: 384 bytes per commitment cross the bus instead of 1536.
+ *   r2 [B][3][N/4] bytes: coefficient i of a row is the two's-complement field (0, 1, -2 -> 2, -1 -> 3) in bits
+ *   2(i & 3) .. 2(i & 3) + 1 of byte i >> 2.  Unpacked on the device (rzk_unpack_r2_dev), then exactly rzk_commit_batch.
+ * rzk_pack_r2 is the host-side packer (no engine, plain CPU loop; RZK_ERR_RANGE for an entry outside [-2, 1],
+ * count = number of coefficients, a multiple of 4); rzk_unpack_r2_dev expands count coefficients (a multiple of 16) between
+ * device arrays on `stream`. */
+int rzk_commit_batch_r2(rzk_engine *e, size_t B, const int32_t *x, const uint8_t *r2,
+                        int32_t *c, uint8_t *ok_bitmap);
+int rzk_pack_r2(size_t count, const int8_t *r, uint8_t *r2);
+int rzk_unpack_r2_dev(rzk_engine *e, size_t count, const uint8_t *r2, int8_t *r, void *stream);
+
 /* Commitment::verify (commit.rs:173-210): check_commit_constraint(r), then
  *   f == NULL (Opening.f = None):  [a1;a2].r + [0;x] == c
  *   f != NULL (Some(f)):           f*c == [a1;a2].r + f*[0;x]          f [B][N] i8 (challenge-space polynomial)
@@ -315,6 +327,7 @@ const char *rzk_group_last_error(const rzk_group *g);
 int rzk_group_set_key(rzk_group *g, const int64_t *a1, const int64_t *a2);
 uint64_t rzk_group_kernel_launches(const rzk_group *g);
 int rzk_group_commit_batch(rzk_group *g, size_t B, const int32_t *x, const int8_t *r, int32_t *c, uint8_t *ok_bitmap);
+int rzk_group_commit_batch_r2(rzk_group *g, size_t B, const int32_t *x, const uint8_t *r2, int32_t *c, uint8_t *ok_bitmap);
 int rzk_group_commitment_verify_batch(rzk_group *g, size_t B, const int32_t *c, const int32_t *x, const int8_t *r,
                                       const int8_t *f, uint8_t *verify_bitmap);
 int rzk_group_open_commit_batch(rzk_group *g, size_t B, const int32_t *x, const int8_t *r, const int32_t *y,

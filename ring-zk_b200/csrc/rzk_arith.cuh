@@ -59,6 +59,15 @@ RZK_HD double f64_exact_i32(int32_t v)
     return (double)v;
 #endif
 }
+// the same from the biased word u = v + 2^31 (mod 2^32)
+RZK_HD double f64_exact_biased(uint32_t u)
+{
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(__hiloint2double(0x43300000, (int)u), -4503601774854144.0);
+#else
+    return (double)(int32_t)(u ^ 0x80000000u);
+#endif
+}
 RZK_HD double f64_exact_fma(double a, double b, double c)
 {
 #if defined(__CUDA_ARCH__)
@@ -153,6 +162,15 @@ RZK_HD void ct_bfly_s(uint32_t &x, uint32_t &y, uint32_t w, uint32_t wp, uint32_
     x = xo;
 }
 
+// The first forward stage of an operand with |y| <= 1 (the range MODE_SPLITKEY_S admits; larger entries are flagged by the
+// program's range check and their item is redone): y*w needs no reduction at all, |y*w| < p/2.  Two instructions.
+RZK_HD void ct_bfly_s_tiny(uint32_t &x, uint32_t &y, uint32_t w)
+{
+    const uint32_t xo = w * y + x;
+    y = x + x - xo;
+    x = xo;
+}
+
 // Gentleman-Sande (inverse) butterfly, five instructions: x' = x + y (magnitude doubles), y' = (x - y) * w (back to 5p/4).
 // Needs |x| + |y| < 2^31: the callers reduce the few elements whose run of sums would exceed that (sreduce).
 RZK_HD void gs_bfly_s(uint32_t &x, uint32_t &y, uint32_t w, uint32_t wp, uint32_t mp)
@@ -160,6 +178,15 @@ RZK_HD void gs_bfly_s(uint32_t &x, uint32_t &y, uint32_t w, uint32_t wp, uint32_
     const uint32_t s = x + y, d = x - y;
     x = s;
     y = sshoup_mac(w, wp, d, mp, 0u);
+}
+
+// The last inverse stage hands its outputs over with the bias 2^31 added (the third operand of the add, the addend of the
+// first multiply-add: free), which is the form the exact int32 -> binary64 conversion wants (f64_exact_biased).
+RZK_HD void gs_bfly_s_biased(uint32_t &x, uint32_t &y, uint32_t w, uint32_t wp, uint32_t mp)
+{
+    const uint32_t s = x + y + 0x80000000u, d = x - y;
+    x = s;
+    y = sshoup_mac(w, wp, d, mp, 0x80000000u);
 }
 
 // v -> v - floor(v / 2^SH) * p for 2^SH <= p < 2^SH + 2^SH/640: a representative in (-p/20, 21p/20) from any |v| < 2^31

@@ -310,6 +310,25 @@ __global__ void rzk_partial_reduce_kernel(size_t n_coeffs, uint32_t segs, const 
     else if (r != 0) atomicOr(&flags[one_flag_word ? 0 : inst], FLAG_FAIL);
 }
 
+// 2-bit packed randomness (rzk_commit_batch_r2): one thread per 32-bit word = 16 coefficients, two's complement fields
+// (0, 1, -2, -1), coefficient i of a row in bits 2(i & 3) .. of byte i >> 2; written as 16 int8 (one 128-bit store)
+__global__ void rzk_unpack_r2_kernel(size_t nwords, const uint32_t *__restrict__ src, uint4 *__restrict__ dst)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += stride) {
+        const uint32_t w = src[i];
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t b = (w >> (8 * k)) & 0xffu;
+            // spread the four fields to four bytes, then sign-extend every 2-bit field: (f ^ 2) - 2
+            const uint32_t f = (b & 3u) | ((b & 0xcu) << 6) | ((b & 0x30u) << 12) | ((b & 0xc0u) << 18);
+            o[k] = __vsub4(f ^ 0x02020202u, 0x02020202u);
+        }
+        dst[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 // ZqI64::from(i64) for whole arrays: any representative -> canonical centred i32
 __global__ void rzk_pack_i64_kernel(size_t n, const int64_t *__restrict__ src, int32_t *__restrict__ dst, int64_t q)
 {
@@ -376,6 +395,7 @@ struct rzk_engine {
     size_t scratch_cap = 0;
     uint64_t launches = 0;
     uint32_t chunk_items = 8192;    // host pipeline: items per chunk (RZK_CHUNK_ITEMS)
+    uint32_t chunk_ramp = 1;        // host pipeline: a batch of several chunks starts with smaller ones (RZK_CHUNK_RAMP=0: off)
     // RZK_TEST_LOWERING: alternative lowerings of the same phases, for the differential tests (tools/soak.py) -- results are
     // identical in every setting.  Comma-separated tokens:
     uint32_t no_static = 0;         //   generic    the runtime-decoded interpreter instead of the compile-time programs
@@ -389,6 +409,7 @@ struct rzk_engine {
     uint32_t static_respond = 0;
     uint32_t mulsum2_pp = 2;        //   mulsum2_pp phase mixing of the two-accumulator product-sum program (0 / 9 = off)
     uint32_t commit_pp = 2;         //   commit_pp  phase mixing of the split-key commitment program (0 / 9 = off)
+    uint32_t wave_fit = 1;          //   wave_fit   fit the warps per CTA to the wave count of the batch (launch_vm); 0 = always the maximum
     uint32_t commit_small = 1;      //   commit_small  0: engines with b = 1 use the 30-bit split-key program too (A/B)
     uint32_t ld128 = 0;             //   ld128      OP_FWD fetches int32 rows with 128-bit loads + a shared-memory redistribution (A/B)
     uint32_t verify_pp = 22;        //   verify_pp  phase mixing of the Open verify program with the rotation sum (two staggered groups)
@@ -493,6 +514,20 @@ int launch_vm(rzk_engine *e, VmLaunch &K, cudaStream_t s, uint32_t pp_program = 
     const uint32_t want = (uint32_t)((K.n_items + (uint64_t)e->num_sms * per_warp - 1) / ((uint64_t)e->num_sms * per_warp));
     // (but at least 4: the whole CTA stages the tables, which is what a single call on one item waits for)
     if ((uint32_t)warps > want) warps = (int)std::max<uint32_t>(want, (uint32_t)std::min(4, warps));
+    // Items cost the same, so a launch takes ceil(items / resident items) waves and its last wave may be nearly empty
+    // (2^14 Linear instances on 16 warps of half-warp items: 3.46 waves, billed as 4).  A CTA with a few warps less can need
+    // the same number of waves, each of them shorter: pick the warp count in [warps - 4, warps] with the fewest warp-waves.
+    if (e->wave_fit && !K.item_mask && warps > 8) {
+        const uint64_t sms = (uint64_t)e->num_sms;
+        auto cost = [&](int w) { return ((K.n_items + sms * per_warp * w - 1) / (sms * per_warp * w)) * (uint64_t)w; };
+        // (a phase-mixed program needs its groups of equal size)
+        const uint32_t ppw = e->pp_mode ? e->pp_mode : pp_program;
+        const int div = (ppw && ppw != 9 && !std::is_void<SP>::value) ? (ppw >= 10 ? (int)(ppw / 10) : 2) : 1;
+        int best = warps;
+        for (int w = warps - 1; w >= warps - 4; --w)
+            if (w % div == 0 && cost(w) * 100 < cost(best) * 97) best = w;          // (3 % margin: fewer resident warps hide less latency)
+        warps = best;
+    }
     // phase mixing: RZK_PP for every static program (experiments), else the program's own setting
     const uint32_t pp = e->pp_mode ? e->pp_mode : pp_program;
     const uint32_t pp_groups = pp >= 10 ? pp / 10 : 2u;
@@ -942,7 +977,16 @@ int run_chunked(rzk_engine *e, size_t B, std::vector<HArr> &arrs, size_t scratch
     }
     // the range word is cleared on the first stream; the other streams are only used (and must wait) when the batch
     // spans several chunks -- a single call on one item stays on one stream with one synchronisation at the end
-    const size_t nchunks = (B + chunk - 1) / chunk;
+    // The first results can only start down the bus once the first chunk is up and computed, and the download is the longer
+    // direction of a commitment batch: a batch of several chunks therefore starts with small ones (chunk / 8, / 8, / 4, / 2)
+    // so that the download engine is busy almost from the start (measured: +4 % end to end at 2^16 commitments)
+    auto chunk_len = [&](int ci) -> size_t {
+        if (!e->chunk_ramp || B < 2 * chunk || chunk < 512) return chunk;
+        const size_t div = ci < 2 ? 8 : ci == 2 ? 4 : ci == 3 ? 2 : 1;
+        return chunk / div / 8 * 8;
+    };
+    size_t nchunks = 0;
+    for (size_t c0 = 0; c0 < B; c0 += chunk_len((int)nchunks), ++nchunks) {}
     RZK_CUDA(e, cudaMemsetAsync(e->d_misc, 0, sizeof(uint32_t), e->pipe[0].stream));
     if (nchunks > 1) RZK_CUDA(e, cudaStreamSynchronize(e->pipe[0].stream));
     std::vector<void *> dptr(arrs.size());
@@ -950,8 +994,8 @@ int run_chunked(rzk_engine *e, size_t B, std::vector<HArr> &arrs, size_t scratch
     // the arenas: every stream is drained first
     auto body = [&]() -> int {
         int ci = 0;
-        for (size_t c0 = 0; c0 < B; c0 += chunk, ++ci) {
-            const size_t n = std::min(chunk, B - c0);
+        for (size_t c0 = 0, n = 0; c0 < B; c0 += n, ++ci) {
+            n = std::min(chunk_len(ci), B - c0);
             PipeSlot &ps = e->pipe[ci % kPipe];
             cudaStream_t s = ps.stream;
             for (size_t i = 0; i < arrs.size(); ++i) {
@@ -1076,6 +1120,7 @@ int rzk_create(const rzk_params *params, int device, rzk_engine **out)
     e->sigma = sigma; e->cbound = cbound; e->vbound = vbound; e->small_lim = small_lim;
     e->generic_commit = (uint64_t)P.b > kSplitKeyLimit;
     if (const char *cs = getenv("RZK_CHUNK_ITEMS")) e->chunk_items = (uint32_t)std::max(8, atoi(cs));
+    if (const char *cs = getenv("RZK_CHUNK_RAMP")) e->chunk_ramp = (uint32_t)atoi(cs);
     auto has_token = [](const char *list, const char *tok) {
         const size_t n = strlen(tok);
         for (const char *p = list; p && *p;) {
@@ -1097,7 +1142,7 @@ int rzk_create(const rzk_params *params, int device, rzk_engine **out)
             const char *p = strstr(tu, key.c_str());
             if (p && (p == tu || p[-1] == ',')) dst = (uint32_t)atoi(p + key.size());
         };
-        val("cta_sync", e->cta_sync); val("pp", e->pp_mode); val("commit_pp", e->commit_pp); val("commit_small", e->commit_small);
+        val("cta_sync", e->cta_sync); val("pp", e->pp_mode); val("commit_pp", e->commit_pp); val("commit_small", e->commit_small); val("wave_fit", e->wave_fit);
         val("mulsum2_pp", e->mulsum2_pp); val("static_respond", e->static_respond); val("verify_pp", e->verify_pp); val("verify_w_pp", e->verify_w_pp); val("ld128", e->ld128);
     }
     e->small_commit = P.b == 1 && e->commit_small != 0;
@@ -1408,6 +1453,49 @@ int rzk_commit_batch(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r,
     });
 }
 
+int rzk_pack_r2(size_t count, const int8_t *r, uint8_t *r2)
+{
+    if (!r || !r2 || (count & 3)) return RZK_ERR_INVALID;
+    for (size_t i = 0; i < count; i += 4) {
+        uint32_t b = 0;
+        for (int k = 0; k < 4; ++k) {
+            const int v = r[i + k];
+            if (v < -2 || v > 1) return RZK_ERR_RANGE;
+            b |= ((uint32_t)v & 3u) << (2 * k);
+        }
+        r2[i >> 2] = (uint8_t)b;
+    }
+    return RZK_OK;
+}
+
+int rzk_unpack_r2_dev(rzk_engine *e, size_t count, const uint8_t *r2, int8_t *r, void *stream)
+{
+    RZK_TRY(check_ready(e, false));
+    if (any_null({r2, r})) return fail(e, RZK_ERR_INVALID, "null argument");
+    if (count & 15) return fail(e, RZK_ERR_INVALID, "count must be a multiple of 16 coefficients");
+    if (count == 0) return RZK_OK;
+    Guard g(e->device);
+    const size_t nwords = count / 16;
+    const unsigned blocks = (unsigned)std::min<size_t>((nwords + 255) / 256, (size_t)e->num_sms * 8);
+    rzk_unpack_r2_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(nwords, reinterpret_cast<const uint32_t *>(r2), reinterpret_cast<uint4 *>(r));
+    RZK_CUDA(e, cudaGetLastError());
+    e->launches++;
+    return RZK_OK;
+}
+
+int rzk_commit_batch_r2(rzk_engine *e, size_t B, const int32_t *x, const uint8_t *r2, int32_t *c, uint8_t *ok)
+{
+    RZK_TRY(check_ready(e));
+    if (any_null({x, r2, c, ok})) return fail(e, RZK_ERR_INVALID, "null argument");
+    // 384 bytes of randomness per commitment cross the bus instead of 1536; the int8 rows the program reads are unpacked
+    // into the chunk's scratch by a small kernel on the same stream
+    std::vector<HArr> a = {{x, nullptr, kPolyBytes}, {r2, nullptr, 3 * kN / 4}, {nullptr, c, 2 * kPolyBytes}};
+    return run_chunked(e, B, a, 3 * kN, ok, [&](size_t n, void **d, char *sc, uint32_t *fl, cudaStream_t s, uint32_t *rm) {
+        RZK_TRY(rzk_unpack_r2_dev(e, n * 3 * kN, (const uint8_t *)d[1], (int8_t *)sc, s));
+        return dev_commit(e, n, (const int32_t *)d[0], (const int8_t *)sc, (int32_t *)d[2], fl, s, rm);
+    });
+}
+
 int rzk_open_commit_batch(rzk_engine *e, size_t B, const int32_t *x, const int8_t *r, const int32_t *y,
                           int32_t *c, int32_t *t, uint8_t *ok)
 {
@@ -1685,6 +1773,13 @@ int rzk_group_commit_batch(rzk_group *g, size_t B, const int32_t *x, const int8_
 {
     return group_run(g, B, [&](rzk_engine *e, size_t s, size_t n) {
         return rzk_commit_batch(e, n, POLY(x, 1, s), POLY(r, 3, s), POLY(c, 2, s), BITS(ok, s));
+    });
+}
+
+int rzk_group_commit_batch_r2(rzk_group *g, size_t B, const int32_t *x, const uint8_t *r2, int32_t *c, uint8_t *ok)
+{
+    return group_run(g, B, [&](rzk_engine *e, size_t s, size_t n) {
+        return rzk_commit_batch_r2(e, n, POLY(x, 1, s), r2 + s * (3 * kN / 4), POLY(c, 2, s), BITS(ok, s));
     });
 }
 

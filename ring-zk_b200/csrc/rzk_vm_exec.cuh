@@ -268,7 +268,8 @@ RZK_VM void inv_g1(uint32_t (&a)[kElems], const uint32_t *g1tab, uint32_t p, uin
 }
 
 // ---- signed lazy transforms (MODE_SPLITKEY_S; rzk_arith.cuh): same geometry, same table layout (w centred, w' signed)
-template <int S, int DIR>
+// SPECIAL: forward -- the tiny-input first stage (ct_bfly_s_tiny); inverse -- the biased last stage (gs_bfly_s_biased)
+template <int S, int DIR, bool BIASED = false>
 RZK_VM void g1_stage_s(uint32_t (&a)[kElems], const uint2 *g1, uint32_t mp)
 {
     constexpr int half = 16 >> S;
@@ -278,7 +279,9 @@ RZK_VM void g1_stage_s(uint32_t (&a)[kElems], const uint2 *g1, uint32_t mp)
         RZK_UNROLL
         for (int j = 0; j < half; ++j) {
             const int i0 = b * 2 * half + j;
-            if (DIR == 0) ct_bfly_s(a[i0], a[i0 + half], w.x, w.y, mp);
+            if (DIR == 0 && BIASED) ct_bfly_s_tiny(a[i0], a[i0 + half], w.x);      // (forward: the flag marks the tiny-input first stage)
+            else if (DIR == 0) ct_bfly_s(a[i0], a[i0 + half], w.x, w.y, mp);
+            else if (BIASED) gs_bfly_s_biased(a[i0], a[i0 + half], w.x, w.y, mp);
             else gs_bfly_s(a[i0], a[i0 + half], w.x, w.y, mp);
         }
     }
@@ -312,7 +315,7 @@ RZK_VM void g2_stage_s(uint32_t (&a)[kElems], const uint4 *tw4, uint32_t mp)
 RZK_VM void fwd_g1_s(uint32_t (&a)[kElems], const uint32_t *g1tab, uint32_t mp)
 {
     const uint2 *g1 = reinterpret_cast<const uint2 *>(g1tab);
-    g1_stage_s<0, 0>(a, g1, mp);
+    g1_stage_s<0, 0, true>(a, g1, mp);     // |a| <= 1 here
     g1_stage_s<1, 0>(a, g1, mp);
     g1_stage_s<2, 0>(a, g1, mp);
     g1_stage_s<3, 0>(a, g1, mp);
@@ -363,7 +366,7 @@ RZK_VM void inv_g1_s(uint32_t (&a)[kElems], const uint32_t *g1tab, uint32_t mp)
     RZK_UNROLL
     for (int e = 0; e < kElems; e += 8) a[e] = sreduce<kSignedShift>(a[e], mp);
     g1_stage_s<1, 1>(a, g1, mp);
-    g1_stage_s<0, 1>(a, g1, mp);
+    g1_stage_s<0, 1, true>(a, g1, mp);      // outputs carry the bias 2^31 (f64_exact_biased)
 }
 
 // ---------------------------------------------------------------- global memory
@@ -1216,9 +1219,10 @@ RZK_VM void inv_core(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const 
                 } else if (MODE == MODE_SPLITKEY_S) {
                     // the residues arrive as arbitrary representatives (|v| < 20.2 p + 2^7 < 2^31): centred on the FP64 pipe,
                     // v - p * rint(v / p), exact because the true parts are below p/2 - 2^14 in magnitude
-                    const int32_t lo = small ? (int32_t)v0 + small[li_][j % CNT] : (int32_t)v0;
-                    const double lod = center_p_f64(f64_exact_i32(lo), K.p0d, K.p0invd);
-                    const double hid = center_p_f64(f64_exact_i32((int32_t)v1), K.p0d, K.p0invd);
+                    // (the words carry the bias 2^31 of the last inverse stage, the form the exact conversion takes)
+                    const uint32_t lo = small ? v0 + (uint32_t)small[li_][j % CNT] : v0;
+                    const double lod = center_p_f64(f64_exact_biased(lo), K.p0d, K.p0invd);
+                    const double hid = center_p_f64(f64_exact_biased(v1), K.p0d, K.p0invd);
                     V[li_][j % CNT] = f64_exact_fma(hid, 65536.0, lod);
                 } else {
                     V[li_][j % CNT] = crt2_mod_q_f64(K, v0, v1);

@@ -50,6 +50,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+def pack_r2(r):
+    """rzk_pack_r2 (plain CPU loop in the library): int8 entries in [-2, 1] -> two's-complement 2-bit fields, four per byte."""
+    r = np.ascontiguousarray(r, dtype=np.int8)
+    out = np.empty(r.shape[:-1] + (r.shape[-1] // 4,), np.uint8)
+    rc = lib().rzk_pack_r2(r.size, r.ctypes.data, out.ctypes.data)
+    if rc != 0:
+        raise RzkError(rc, "rzk_pack_r2: an entry outside [-2, 1] (or a count that is not a multiple of 4)")
+    return out
+
+
 class RzkError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"{_ERRNAMES.get(code, code)}: {msg}")
@@ -67,6 +77,8 @@ _VP = C.c_void_p
 # name -> argument kinds after the engine handle ('z' size_t, 'u' uint32, 'p' pointer)
 _SIGS = {
     "rzk_commit_batch": "zpppp",
+    "rzk_commit_batch_r2": "zpppp",
+    "rzk_unpack_r2_dev": "zppp",
     "rzk_commitment_verify_batch": "zppppp",
     "rzk_commitment_verify_batch_dev": "zpppppp",
     "rzk_open_commit_batch": "zpppppp",
@@ -96,12 +108,12 @@ _SIGS = {
     "rzk_unpack_i64": "zpp",
     "rzk_sync": "p",
 }
-_GROUP_HOST = ["rzk_commit_batch", "rzk_commitment_verify_batch", "rzk_open_commit_batch", "rzk_open_respond_batch",
+_GROUP_HOST = ["rzk_commit_batch", "rzk_commit_batch_r2", "rzk_commitment_verify_batch", "rzk_open_commit_batch", "rzk_open_respond_batch",
                "rzk_open_verify_batch", "rzk_linear_commit_batch", "rzk_linear_respond_batch", "rzk_linear_verify_batch",
                "rzk_sum_commit_batch", "rzk_sum_respond_batch", "rzk_sum_verify_batch"]
 _GROUP_SIGS = {n.replace("rzk_", "rzk_group_", 1): _SIGS[n] for n in _GROUP_HOST}
 EXPORTS = sorted(list(_SIGS) + list(_GROUP_SIGS) + ["rzk_group_create", "rzk_group_destroy", "rzk_group_size", "rzk_group_last_error",
-                                                    "rzk_group_set_key", "rzk_group_kernel_launches"] + ["rzk_default_params", "rzk_create", "rzk_destroy", "rzk_last_error", "rzk_device",
+                                                    "rzk_group_set_key", "rzk_group_kernel_launches"] + ["rzk_default_params", "rzk_create", "rzk_destroy", "rzk_last_error", "rzk_device", "rzk_pack_r2",
                                 "rzk_sigma", "rzk_commit_bound", "rzk_verify_bound", "rzk_small_limit",
                                 "rzk_set_key", "rzk_host_alloc", "rzk_host_free", "rzk_kernel_launches",
                                 "rzk_wire_layout", "rzk_wire_pack_dev", "rzk_wire_unpack_dev",
@@ -125,6 +137,8 @@ def lib():
         fn.argtypes = [_VP] + [kinds[c] for c in sig]
     L.rzk_default_params.restype = RzkParams
     L.rzk_default_params.argtypes = [C.c_int32]
+    L.rzk_pack_r2.restype = C.c_int
+    L.rzk_pack_r2.argtypes = [C.c_size_t, _VP, _VP]
     L.rzk_create.restype = C.c_int
     L.rzk_create.argtypes = [C.POINTER(RzkParams), C.c_int, C.POINTER(_VP)]
     L.rzk_destroy.argtypes = [_VP]
@@ -310,6 +324,14 @@ class Engine:
         c = np.empty((B, 2, N), np.int32)
         ok = np.zeros((B + 7) // 8, np.uint8)
         self._call("rzk_commit_batch", B, _ptr(x, np.int32), _ptr(r, np.int8), _ptr(c), _ptr(ok))
+        return c, ok
+
+    def commit_r2(self, x, r2):
+        """rzk_commit_batch_r2: the randomness packed at 2 bits per coefficient (pack_r2), [B][3][N/4] uint8."""
+        B, N = x.shape[0], self.N
+        c = np.empty((B, 2, N), np.int32)
+        ok = np.zeros((B + 7) // 8, np.uint8)
+        self._call("rzk_commit_batch_r2", B, _ptr(x, np.int32), _ptr(r2, np.uint8), _ptr(c), _ptr(ok))
         return c, ok
 
     def commitment_verify(self, c, x, r, f=None):

@@ -213,6 +213,24 @@ pub(crate) fn push_mat_i8<const N: usize>(out: &mut Vec<i8>, m: &Mat<Z, N>) {
     }
 }
 
+/// The 2-bit packing of `rzk_commit_batch_r2` (two's-complement fields, four coefficients per byte, low bits first) for
+/// randomness with every entry in [-2, 1] -- `Params::default()` draws r from {-1, 0, 1}.  `None` if an entry does not fit.
+pub(crate) fn pack_r2(r: &[i8]) -> Option<Vec<u8>> {
+    debug_assert_eq!(r.len() % 4, 0);
+    let mut out = Vec::with_capacity(r.len() / 4);
+    for quad in r.chunks_exact(4) {
+        let mut b = 0u8;
+        for (k, &v) in quad.iter().enumerate() {
+            if !(-2..=1).contains(&v) {
+                return None;
+            }
+            b |= ((v as u8) & 3) << (2 * k);
+        }
+        out.push(b);
+    }
+    Some(out)
+}
+
 /// N coefficients -> Polynomial (full length; `Polynomial ==` compares values, padding zeros included on both sides
 /// of every comparison the protocols make, since every engine output is full length).
 pub(crate) fn poly_from<const N: usize>(v: &[i32]) -> Polynomial<Z, N> {

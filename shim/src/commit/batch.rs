@@ -48,10 +48,16 @@ pub(crate) fn commit_with<const N: usize>(
     let rows = params.n + params.l;
     let mut c = vec![0i32; b * rows * N];
     let mut ok = vec![0u8; (b + 7) / 8];
+    // randomness in {-1, 0, 1} (b = 1, the default) crosses the bus at 2 bits per coefficient: 384 bytes per commitment
+    // instead of 1536 (`rzk_commit_batch_r2`); anything wider goes as int8
+    let bound: i64 = params.b.clone().into();
+    let r2 = if bound == 1 { b200::pack_r2(&rf) } else { None };
     let rc = unsafe {
-        match *be {
-            Backend::Engine(e) => ffi::rzk_commit_batch(e, b, xf.as_ptr(), rf.as_ptr(), c.as_mut_ptr(), ok.as_mut_ptr()),
-            Backend::Group(g) => ffi::rzk_group_commit_batch(g, b, xf.as_ptr(), rf.as_ptr(), c.as_mut_ptr(), ok.as_mut_ptr()),
+        match (&*be, &r2) {
+            (Backend::Engine(e), Some(p)) => ffi::rzk_commit_batch_r2(*e, b, xf.as_ptr(), p.as_ptr(), c.as_mut_ptr(), ok.as_mut_ptr()),
+            (Backend::Group(g), Some(p)) => ffi::rzk_group_commit_batch_r2(*g, b, xf.as_ptr(), p.as_ptr(), c.as_mut_ptr(), ok.as_mut_ptr()),
+            (Backend::Engine(e), None) => ffi::rzk_commit_batch(*e, b, xf.as_ptr(), rf.as_ptr(), c.as_mut_ptr(), ok.as_mut_ptr()),
+            (Backend::Group(g), None) => ffi::rzk_group_commit_batch(*g, b, xf.as_ptr(), rf.as_ptr(), c.as_mut_ptr(), ok.as_mut_ptr()),
         }
     };
     be.check_or_panic(rc)?;

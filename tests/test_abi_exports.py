@@ -44,6 +44,23 @@ def test_default_params_and_no_device_error():
         assert ei.value.code == engine.RZK_ERR_CUDA
 
 
+def test_pack_r2_host_helper():
+    """rzk_pack_r2 (pure CPU): two's-complement 2-bit fields, low bits first; entries outside [-2, 1] are refused."""
+    import numpy as np
+    r = np.array([0, 1, -1, -2, 1, 1, 0, -1], np.int8)
+    out = engine.pack_r2(r)
+    assert out.tolist() == [0 | (1 << 2) | (3 << 4) | (2 << 6), 1 | (1 << 2) | (0 << 4) | (3 << 6)]
+    rng = np.random.default_rng(0)
+    big = rng.integers(-2, 2, size=(5, 3, 512)).astype(np.int8)
+    p = engine.pack_r2(big)
+    fields = np.stack([(p >> (2 * k)) & 3 for k in range(4)], axis=-1).reshape(big.shape).astype(np.int8)
+    assert (((fields ^ 2) - 2) == big).all()
+    with pytest.raises(engine.RzkError):
+        engine.pack_r2(np.array([0, 0, 0, 2], np.int8))
+    with pytest.raises(engine.RzkError):
+        engine.pack_r2(np.array([0, 0, 0], np.int8))
+
+
 def test_unsupported_params_rejected():
     L = engine.lib()
     P = L.rzk_default_params(16)

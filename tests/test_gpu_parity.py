@@ -438,6 +438,57 @@ def test_masked_redo_full_batch_one_bad_item(setup):
     assert UB(sc["ok"], Bs).all()
 
 
+@pytest.mark.parametrize("B", [1, 37, 9000])
+def test_commit_packed_randomness(setup, B):
+    """rzk_commit_batch_r2: the randomness at 2 bits per coefficient (what Params::default() needs) gives the commitments of
+    rzk_commit_batch and of the oracle bit for bit, across chunk boundaries of the host pipeline (8192 items), and an entry
+    -2 (representable, outside the small-prime program's range) is redone by the masked launch like any other."""
+    eng, o, s = setup
+    x, r = s.message(B, ragged=True), s.small(B)
+    if B > 5:
+        r[3, 1, 17] = -2; r[B - 1, 2, 511] = -2; r[4, 0, :] = -2
+    r2 = engine.pack_r2(r)
+    assert r2.shape == (B, 3, N // 4) and r2.dtype == np.uint8
+    c, ok = eng.commit_r2(x, r2)
+    c8, ok8 = eng.commit(x, r)
+    assert (c == c8).all() and (ok == ok8).all()
+    nb = min(B, 64)
+    c_o, ok_o = o.commit_batch(x[:nb], r[:nb])
+    assert (c[:nb] == c_o).all() and (UB(ok, B)[:nb] == ok_o.astype(bool)).all()
+    c_o, _ = o.commit_batch(x[B - 1:], r[B - 1:])
+    assert (c[B - 1:] == c_o).all()
+    with pytest.raises(engine.RzkError):
+        bad = r.copy(); bad[0, 0, 0] = 2
+        engine.pack_r2(bad)
+
+
+def test_thirty_bit_split_key_program_still_exact():
+    """Engines with b = 1 commit modulo the small prime (signed lazy arithmetic); the 30-bit split-key program serves
+    2 <= b <= 15 and stays selectable for b = 1 (RZK_TUNE=commit_small=0): both give the oracle's commitments."""
+    import os
+    s = synth.Synth(17, N=N)
+    a1p, a2p = s.key()
+    o = orc.Oracle(orc.Params(N=N), a1p, a2p)
+    B = 130
+    x, r = s.message(B, ragged=True), s.small(B)
+    c_o, _ = o.commit_batch(x, r)
+    old = os.environ.get("RZK_TUNE")
+    os.environ["RZK_TUNE"] = "commit_small=0"
+    try:
+        eng = engine.Engine(N=N, device=0)
+    finally:
+        if old is None:
+            os.environ.pop("RZK_TUNE")
+        else:
+            os.environ["RZK_TUNE"] = old
+    try:
+        eng.set_key_blocks(a1p, a2p)
+        c, ok = eng.commit(x, r)
+        assert (c == c_o).all() and UB(ok, B).all()
+    finally:
+        eng.close()
+
+
 def test_large_b_runs_generic_commit():
     """b > 15 (accepted while b * kappa <= 74): every commitment runs the two-prime program, exact for any int8 r, on the host
     AND on the `_dev` entry points (no garbage c behind a FLAG_RANGE bit)."""
