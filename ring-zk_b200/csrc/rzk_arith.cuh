@@ -154,6 +154,17 @@ RZK_HD uint32_t sshoup_mac(uint32_t w, uint32_t wp, uint32_t y, uint32_t mp, uin
     return q * mp + (w * y + acc);
 }
 
+// Signed Montgomery product a b 2^-32 (mod p) for int32 representatives a, b; pinv = p^-1 mod 2^32.
+// m p has the low word of a b, so the difference of the (floor) high words is exact: |result| <= |a b| / 2^32 + p/2 + 1.
+RZK_HD uint32_t smont_mul(uint32_t a, uint32_t b, uint32_t p, uint32_t pinv)
+{
+    const uint32_t lo = a * b;
+    const int32_t hi = mulhi_s32((int32_t)a, (int32_t)b);
+    const uint32_t m = lo * pinv;
+    const int32_t mh = mulhi_s32((int32_t)m, (int32_t)p);
+    return (uint32_t)(hi - mh);
+}
+
 // Cooley-Tukey (forward) butterfly, four instructions: x' = x + t, y' = x - t = 2x - x'.  Magnitudes grow by 5p/4 per stage.
 RZK_HD void ct_bfly_s(uint32_t &x, uint32_t &y, uint32_t w, uint32_t wp, uint32_t mp)
 {

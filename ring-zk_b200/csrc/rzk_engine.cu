@@ -42,7 +42,7 @@ template <int NP, int MODE>
 #ifndef RZK_SEQ3_WARPS
 #define RZK_SEQ3_WARPS 16      // three-prime programs: chunked epilogue + residue stash in global memory (rzk_vm_exec.cuh ChunkedEpi)
 #endif
-struct VmCfg { static constexpr int kMaxWarps = (MODE != MODE_SEQ) ? RZK_SPLIT_WARPS : (NP == 1 ? 12 : RZK_SEQ3_WARPS); };
+struct VmCfg { static constexpr int kMaxWarps = !mode_seq(MODE) ? RZK_SPLIT_WARPS : (NP == 1 ? 12 : RZK_SEQ3_WARPS); };
 
 // does a compile-time program multiply by the resident key (OP_MACK)?  Programs that do not (the three-prime product
 // sums) leave the key images out of shared memory, which is what lets their two-accumulator form keep 16 warps.
@@ -131,7 +131,7 @@ __device__ __forceinline__ void stage_int_tables(const VmLaunch &K, uint32_t *s_
 template <int NP, int MODE, class SP = void>
 __global__ void __launch_bounds__(VmCfg<NP, MODE>::kMaxWarps * 32, 1) rzk_vm_kernel(const __grid_constant__ VmLaunch K)
 {
-    constexpr bool SPLIT = (MODE != MODE_SEQ);      // one warp per item
+    constexpr bool SPLIT = !mode_seq(MODE);      // one warp per item
     extern __shared__ __align__(16) uint32_t smem[];
     constexpr bool KEY = sp_uses_key<SP>();
     using S = VmSmem<NP, MODE, KEY>;
@@ -409,6 +409,7 @@ struct rzk_engine {
     uint32_t static_respond = 0;
     uint32_t mulsum2_pp = 2;        //   mulsum2_pp phase mixing of the two-accumulator product-sum program (0 / 9 = off)
     uint32_t commit_pp = 2;         //   commit_pp  phase mixing of the split-key commitment program (0 / 9 = off)
+    uint32_t mulsum_small = 1;      //   mulsum_small  0: product sums of up to 64 terms use the 30-bit primes too (A/B)
     uint32_t wave_fit = 1;          //   wave_fit   fit the warps per CTA to the wave count of the batch (launch_vm); 0 = always the maximum
     uint32_t commit_small = 1;      //   commit_small  0: engines with b = 1 use the 30-bit split-key program too (A/B)
     uint32_t ld128 = 0;             //   ld128      OP_FWD fetches int32 rows with 128-bit loads + a shared-memory redistribution (A/B)
@@ -448,9 +449,10 @@ struct Guard {
     ~Guard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-void fill_common(const rzk_engine *e, VmLaunch &K, int np, uint32_t n_items, uint32_t flag_div, uint32_t *flags)
+void fill_common(const rzk_engine *e, VmLaunch &K, int np, uint32_t n_items, uint32_t flag_div, uint32_t *flags, bool small_primes = false)
 {
-    static const int slots[3] = {0, 1, 2};
+    static const int slots30[3] = {0, 1, 2}, slots26[3] = {kSignedSlot, kSignedSlot + 1, kSignedSlot + 2};
+    const int *slots = small_primes ? slots26 : slots30;
     const uint64_t q = (uint64_t)e->P.q;
     for (int i = 0; i < np; ++i) K.pc[i] = make_prime_consts(slots[i]);
     K.crt = make_crt_consts(slots, np, q);
@@ -462,7 +464,7 @@ void fill_common(const rzk_engine *e, VmLaunch &K, int np, uint32_t n_items, uin
     K.norm_abs_lim[0] = (uint32_t)e->cbound; K.norm_sq_lim[0] = (e->cbound + 1) * (e->cbound + 1) - 1;
     K.norm_abs_lim[1] = (uint32_t)e->vbound; K.norm_sq_lim[1] = (e->vbound + 1) * (e->vbound + 1) - 1;
     K.small_lim = e->small_lim;
-    K.ld128 = e->ld128;
+    K.ld128 = small_primes ? 0u : e->ld128;
     K.n_items = n_items;
     K.np = (uint32_t)np;
     if (flags) { K.flags = flags; K.flag_div = flag_div; }
@@ -485,7 +487,7 @@ int launch_vm(rzk_engine *e, VmLaunch &K, cudaStream_t s, uint32_t pp_program = 
 {
     if (K.n_items == 0) return RZK_OK;
     if (K.n_items >= (1u << 28)) return fail(e, RZK_ERR_INVALID, "more than 2^28 items in one launch");
-    constexpr bool SPLIT = (MODE != MODE_SEQ);
+    constexpr bool SPLIT = !mode_seq(MODE);
     auto kern = rzk_vm_kernel<NP, MODE, SP>;
     if (SpAcc1Global<SP>::value != (K.acc1_global != 0) && !std::is_void<SP>::value)
         return fail(e, RZK_ERR_INVALID, "program and kernel disagree on where accumulator 1 lives");
@@ -559,6 +561,7 @@ int launch_sp(rzk_engine *e, VmLaunch &K, cudaStream_t s, uint32_t pp_program = 
     if (e->no_static) {      // RZK_NO_STATIC=1: run the same program through the generic interpreter
         if (SP::kMode == MODE_SPLITKEY) return launch_vm<1, MODE_SPLITKEY>(e, K, s);
         if (SP::kMode == MODE_SPLITKEY_S) return launch_vm<1, MODE_SPLITKEY_S>(e, K, s);
+        if (SP::kMode == MODE_SEQ_S) return launch_vm<3, MODE_SEQ_S>(e, K, s);
         if (SP::kMode == MODE_SPLIT) return launch_vm<2, MODE_SPLIT>(e, K, s);
         return SP::kNP == 1 ? launch_vm<1, MODE_SEQ>(e, K, s) : launch_vm<3, MODE_SEQ>(e, K, s);
     }
@@ -830,12 +833,20 @@ int dev_mulsum(rzk_engine *e, size_t B, uint32_t T, const int32_t *a, const int3
     prog_mulsum(p, (int)T, 0, 1, sub0 ? 2 : -1, sub1 ? 3 : -1, out ? 4 : -1, out ? FIN_STORE : FIN_CMPZ);
     p.end();
     p.install(K);
-    fill_common(e, K, 3, (uint32_t)B, 1, flags);
+    // up to 64 terms fit the three small primes (any int32 operands: 64 * 512 * 2^62 < p3 p4 p5 / 2): signed lazy arithmetic
+    const bool small = e->mulsum_small && T <= (uint32_t)kSignedMaxTerms;
+    fill_common(e, K, 3, (uint32_t)B, 1, flags, small);
     set_stream(K, 0, a, T, DT_I32); set_stream(K, 1, b, T, DT_I32);
     if (sub0) set_stream(K, 2, sub0, 1, DT_I32);
     if (sub1) set_stream(K, 3, sub1, 1, DT_I32);
     if (out) set_stream(K, 4, out, 1, DT_I32);
     K.loop_count = T - 1;
+    if (small) {
+        if (out && !sub0 && !sub1) return launch_sp<SPMulSum0S>(e, K, s);
+        if (out && sub0 && !sub1) return launch_sp<SPMulSum1S>(e, K, s);
+        if (!out && sub0 && sub1) return launch_sp<SPMulSumCmpS>(e, K, s);
+        return launch_vm<3, MODE_SEQ_S>(e, K, s);
+    }
     if (out && !sub0 && !sub1) return launch_sp<SPMulSum0>(e, K, s);
     if (out && sub0 && !sub1) return launch_sp<SPMulSum1>(e, K, s);
     if (!out && sub0 && sub1) return launch_sp<SPMulSumCmp>(e, K, s);
@@ -851,10 +862,12 @@ int dev_mulsum2(rzk_engine *e, size_t B, uint32_t T, const int32_t *a, const int
     prog_mulsum2(p, (int)T, 0, 1, 2, 3, 4, 5);
     p.end();
     p.install(K);
-    fill_common(e, K, 3, (uint32_t)B, 1, flags);
+    const bool small = e->mulsum_small && T <= (uint32_t)kSignedMaxTerms;
+    fill_common(e, K, 3, (uint32_t)B, 1, flags, small);
     set_stream(K, 0, a, T, DT_I32); set_stream(K, 1, b, T, DT_I32); set_stream(K, 2, c, T, DT_I32);
     set_stream(K, 3, sub, 1, DT_I32); set_stream(K, 4, out0, 1, DT_I32); set_stream(K, 5, out1, 1, DT_I32);
     K.loop_count = T - 1;
+    if (small) return launch_sp<SPMulSum2S>(e, K, s, e->mulsum2_pp);
     // phase mixing between the CTA halves (as for the commitment program) measured +3.4 % on this kernel at 2^12 x 64 terms;
     // on the single-accumulator product sums, A.y and the verify programs it measured within +-1 % or slower and stays off
     return launch_sp<SPMulSum2>(e, K, s, e->mulsum2_pp);
@@ -1142,7 +1155,7 @@ int rzk_create(const rzk_params *params, int device, rzk_engine **out)
             const char *p = strstr(tu, key.c_str());
             if (p && (p == tu || p[-1] == ',')) dst = (uint32_t)atoi(p + key.size());
         };
-        val("cta_sync", e->cta_sync); val("pp", e->pp_mode); val("commit_pp", e->commit_pp); val("commit_small", e->commit_small); val("wave_fit", e->wave_fit);
+        val("cta_sync", e->cta_sync); val("pp", e->pp_mode); val("commit_pp", e->commit_pp); val("commit_small", e->commit_small); val("wave_fit", e->wave_fit); val("mulsum_small", e->mulsum_small);
         val("mulsum2_pp", e->mulsum2_pp); val("static_respond", e->static_respond); val("verify_pp", e->verify_pp); val("verify_w_pp", e->verify_w_pp); val("ld128", e->ld128);
     }
     e->small_commit = P.b == 1 && e->commit_small != 0;

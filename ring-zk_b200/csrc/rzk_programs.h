@@ -410,10 +410,17 @@ struct SPMulSum2 {               // streams: 0 = a, 1 = b, 2 = c, 3 = sub, 4 = o
     static constexpr uint8_t dtype[kMaxStreams] = {DT_I32, DT_I32, DT_I32, DT_I32, DT_I32, DT_I32};
 };
 
+// the same product sums modulo the three small primes with signed lazy arithmetic (MODE_SEQ_S, up to kSignedMaxTerms terms)
+struct SPMulSum0S { static constexpr int kNP = 3, kMode = 4; static constexpr Prog prog = SPMulSum0::prog; static constexpr uint8_t dtype[kMaxStreams] = {DT_I32, DT_I32, DT_I32, DT_I32, DT_I32}; };
+struct SPMulSum1S { static constexpr int kNP = 3, kMode = 4; static constexpr Prog prog = SPMulSum1::prog; static constexpr uint8_t dtype[kMaxStreams] = {DT_I32, DT_I32, DT_I32, DT_I32, DT_I32}; };
+struct SPMulSum2S { static constexpr int kNP = 3, kMode = 4; static constexpr Prog prog = SPMulSum2::prog; static constexpr uint8_t dtype[kMaxStreams] = {DT_I32, DT_I32, DT_I32, DT_I32, DT_I32, DT_I32}; };
+
 struct SPMulSumCmp {             // streams: 0 = a, 1 = b, 2 = sub0, 3 = sub1  sum a_i*b_i - sub0 - sub1 == 0
     static constexpr int kNP = 3, kMode = 0;
     static constexpr Prog prog = [] { Prog p; prog_mulsum(p, 2, 0, 1, 2, 3, -1, FIN_CMPZ); p.end(); return p; }();
     static constexpr uint8_t dtype[kMaxStreams] = {DT_I32, DT_I32, DT_I32, DT_I32, DT_I32};
 };
+
+struct SPMulSumCmpS { static constexpr int kNP = 3, kMode = 4; static constexpr Prog prog = SPMulSumCmp::prog; static constexpr uint8_t dtype[kMaxStreams] = {DT_I32, DT_I32, DT_I32, DT_I32, DT_I32}; };
 
 }  // namespace rzk

@@ -9,7 +9,8 @@ namespace rzk {
 
 const uint32_t kPrimeList[kNumPrimeSlots] = {      // slot 0 is also the compile-time prime of the split-key program (kStaticPrime0)
     1073692673u, 1073668097u, 1073655809u,   // < 2^30
-    67153921u, 91672577u, 91611137u,         // small primes for the signed lazy arithmetic (rzk_arith.cuh): slot 3 = kStaticPrimeS = 2^26 + 45057
+    67153921u, 67219457u, 67227649u,         // the three smallest primes == 1 (mod 4096) above 2^26, for the signed lazy arithmetic
+                                             // (rzk_arith.cuh): slot 3 = kStaticPrimeS = 2^26 + 45057; product 2^78.006
 };
 
 bool slot_is_signed(int slot) { return slot >= 3; }
@@ -160,6 +161,7 @@ PrimeC make_prime_consts(int slot)
     c.pinv = T.pinv;
     c.rn = T.rn;
     c.rnp = T.rnp;
+    if (slot_is_signed(slot)) signed_shoup_pair(T.rn, T.p, c.rn, c.rnp);       // centred R N^-1 with its signed companion
     c.slot = (uint32_t)slot;
     c.half = (T.p - 1) / 2;
     return c;

@@ -9,7 +9,7 @@ namespace rzk {
 
 // Global static list of auxiliary NTT primes, all == 1 (mod 4096):
 //   slots 0..2 : the three largest below 2^30   (Harvey lazy range [0,4p) fits 32 bits)
-//   slots 3..5 : small primes (2^26 .. 2^26.5) for the signed lazy arithmetic of rzk_arith.cuh; their kernel-side tables (g1, g2,
+//   slots 3..5 : the three smallest primes above 2^26 for the signed lazy arithmetic of rzk_arith.cuh; their kernel-side tables (g1, g2,
 //                key images) hold centred values with signed Shoup companions round(w * 2^32 / p).  Slot 3 is the compile-time
 //                prime of the b = 1 split-key commitment program (kStaticPrimeS, MODE_SPLITKEY_S)
 extern const uint32_t kPrimeList[kNumPrimeSlots];

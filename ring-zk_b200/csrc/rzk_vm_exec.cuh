@@ -57,7 +57,13 @@ struct uint2 { uint32_t x, y; };
 
 namespace rzk {
 
-enum { MODE_SEQ = 0, MODE_SPLIT = 1, MODE_SPLITKEY = 2, MODE_SPLITKEY_S = 3 };
+enum { MODE_SEQ = 0, MODE_SPLIT = 1, MODE_SPLITKEY = 2, MODE_SPLITKEY_S = 3, MODE_SEQ_S = 4 };
+// MODE_SEQ_S: MODE_SEQ with three SMALL primes (slots 3..5, all within 2^17 above 2^26) and signed lazy arithmetic -- the
+// large x large product sums of up to 64 terms (64 * 512 * 2^62 < p3 p4 p5 / 2 = 2^77.0): forward transforms of four
+// instructions per butterfly, Montgomery products of five, reductions only where a run of sums needs one.
+constexpr bool mode_seq(int mode) { return mode == MODE_SEQ || mode == MODE_SEQ_S; }
+constexpr bool mode_signed(int mode) { return mode == MODE_SPLITKEY_S || mode == MODE_SEQ_S; }
+constexpr int kSignedMaxTerms = 64;                  // terms of a product sum the three small primes hold for ANY int32 operands
 // MODE_SPLITKEY_S: the split-key commitment for |r| <= 1 (Params::default(): b = 1) modulo ONE SMALL prime with signed lazy
 // arithmetic (rzk_arith.cuh): |a_lo r1 + a_lo' r2 + r0| <= 2^25 + 127 < p/2 for p = 67153921, and 2^31 / p = 31.98 leaves room
 // for nine forward stages without any correction (4-instruction butterflies) and for inverse stages that only reduce the
@@ -311,11 +317,13 @@ RZK_VM void g2_stage_s(uint32_t (&a)[kElems], const uint4 *tw4, uint32_t mp)
     }
 }
 
-// forward: inputs |a| <= 127, every stage adds at most 5p/4: below 11.3 p + 127 at the end, no correction anywhere
+// forward: inputs |a| <= 5p/4 (a reduced or Shoup-scaled int32 operand; tiny for int8 rows), every stage adds at most 5p/4:
+// below 12.5 p at the end, no correction anywhere
+template <bool TINY>      // TINY: every input is in {-1, 0, 1}
 RZK_VM void fwd_g1_s(uint32_t (&a)[kElems], const uint32_t *g1tab, uint32_t mp)
 {
     const uint2 *g1 = reinterpret_cast<const uint2 *>(g1tab);
-    g1_stage_s<0, 0, true>(a, g1, mp);     // |a| <= 1 here
+    g1_stage_s<0, 0, TINY>(a, g1, mp);
     g1_stage_s<1, 0>(a, g1, mp);
     g1_stage_s<2, 0>(a, g1, mp);
     g1_stage_s<3, 0>(a, g1, mp);
@@ -357,6 +365,7 @@ RZK_VM void inv_g2_s(uint32_t (&a)[kElems], const uint32_t *tw, uint32_t mp)
     }
 }
 
+template <bool BIASED>
 RZK_VM void inv_g1_s(uint32_t (&a)[kElems], const uint32_t *g1tab, uint32_t mp)
 {
     const uint2 *g1 = reinterpret_cast<const uint2 *>(g1tab);
@@ -366,7 +375,7 @@ RZK_VM void inv_g1_s(uint32_t (&a)[kElems], const uint32_t *g1tab, uint32_t mp)
     RZK_UNROLL
     for (int e = 0; e < kElems; e += 8) a[e] = sreduce<kSignedShift>(a[e], mp);
     g1_stage_s<1, 1>(a, g1, mp);
-    g1_stage_s<0, 1, true>(a, g1, mp);      // outputs carry the bias 2^31 (f64_exact_biased)
+    g1_stage_s<0, 1, BIASED>(a, g1, mp);    // BIASED: the outputs carry the bias 2^31 (f64_exact_biased)
 }
 
 // ---------------------------------------------------------------- global memory
@@ -389,7 +398,7 @@ RZK_VM uint4 rot_ld128(const void *p)
 }
 
 
-template <bool SGN = false>
+template <bool SGN = false, bool TINY = false>
 RZK_VM void op_fwd(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const Op &op, int it, uint32_t dtype)
 {
     const Stream st = K.st[op.a];
@@ -429,7 +438,7 @@ RZK_VM void op_fwd(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const Op
         } else {
             const int32_t *src = reinterpret_cast<const int32_t *>(st.base) + poly * kN;
             RZK_UNROLL
-            for (int m = 0; m < kElems; ++m) v[m] = lift_in(src[t + kLanes * m], K.q);
+            for (int m = 0; m < kElems; ++m) v[m] = SGN ? src[t + kLanes * m] : lift_in(src[t + kLanes * m], K.q);
         }
         if (op.b & FWD_CHECK_SMALL) {
             // |v| <= lim  <=>  (uint32)(v + lim) <= 2 lim: one add-and-max per coefficient (VIADDMNMX)
@@ -439,9 +448,19 @@ RZK_VM void op_fwd(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const Op
             L.rerr |= (mx > 2u * K.small_lim) ? 1u : 0u;
         }
         if constexpr (SGN) {
-            // signed lazy form: the small operand itself is the input (the program checks |v| <= small_lim first)
-            RZK_UNROLL
-            for (int m = 0; m < kElems; ++m) L.cur[m] = (uint32_t)v[m];
+            // signed lazy form: an int8 operand is its own input; an int32 operand (ANY representative, |v| <= 2^31) is brought
+            // below 5p/4 -- by the Shoup product with R N^-1 that a Montgomery operand needs anyway, or by one shift-reduce
+            const uint32_t mp = 0u - pc.p;
+            if (dtype == DT_I8) {
+                RZK_UNROLL
+                for (int m = 0; m < kElems; ++m) L.cur[m] = (uint32_t)v[m];
+            } else if (op.b & FWD_SCALED) {
+                RZK_UNROLL
+                for (int m = 0; m < kElems; ++m) L.cur[m] = sshoup_mac(pc.rn, pc.rnp, (uint32_t)v[m], mp, 0u);
+            } else {
+                RZK_UNROLL
+                for (int m = 0; m < kElems; ++m) L.cur[m] = sreduce<kSignedShift>((uint32_t)v[m], mp);
+            }
         } else if (op.b & FWD_SCALED) {
             // centred value + 2p lies in (0, 4p): a valid lazy input of the forward butterflies
             RZK_UNROLL
@@ -454,7 +473,7 @@ RZK_VM void op_fwd(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const Op
 #if defined(__CUDA_ARCH__)
         pp_acquire(K);
 #endif
-        if constexpr (SGN) fwd_g1_s(L.cur, ctx.g1 + (L.pi * 2 + 0) * kG1Words, 0u - pc.p);
+        if constexpr (SGN) fwd_g1_s<TINY>(L.cur, ctx.g1 + (L.pi * 2 + 0) * kG1Words, 0u - pc.p);
         else fwd_g1(L.cur, ctx.g1 + (L.pi * 2 + 0) * kG1Words, pc.p, pc.p2, pc.pad_, L.cap);
         RZK_UNROLL
         for (int m = 0; m < kElems; ++m) {
@@ -559,6 +578,76 @@ RZK_VM void mac_var(uint32_t (&acc)[kElems], const uint32_t (&cur)[kElems], cons
     }
 }
 
+// signed lazy form (MODE_SEQ_S): acc +- slot (.) cur as a signed Montgomery product, five instructions per term.
+// |cur| <= 12.5 p, |slot| <= 1.06 p: the product a b 2^-32 (mod p) comes out below 0.71 p in magnitude, so an accumulator
+// may take 32 terms between two reductions (sp_exec / vm_run_item reduce it every 32nd iteration of a loop).
+RZK_VM void mac_var_s(uint32_t (&acc)[kElems], const uint32_t (&cur)[kElems], const uint32_t *slot, int t,
+                      uint32_t flags, uint32_t p, uint32_t pinv)
+{
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(slot);
+    const bool init = flags & MAC_INIT, neg = flags & MAC_NEG;
+    RZK_UNROLL
+    for (int j = 0; j < 8; ++j) {
+        const uint4 s = s4[j * kLanes + t];
+        const uint32_t ss[4] = {s.x, s.y, s.z, s.w};
+        RZK_UNROLL
+        for (int c = 0; c < 4; ++c) {
+            const int e = 4 * j + c;
+            const uint32_t tt = smont_mul(cur[e], ss[c], p, pinv);
+            const uint32_t a0 = init ? 0u : acc[e];
+            acc[e] = neg ? a0 - tt : a0 + tt;
+        }
+    }
+}
+
+RZK_VM void mac_var_smem_s(uint32_t *acc1, const uint32_t (&cur)[kElems], const uint32_t *slot, int t,
+                           uint32_t flags, uint32_t p, uint32_t pinv)
+{
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(slot);
+    uint4 *a4 = reinterpret_cast<uint4 *>(acc1);
+    const bool init = flags & MAC_INIT, neg = flags & MAC_NEG;
+    RZK_UNROLL
+    for (int j = 0; j < 8; ++j) {
+        const uint4 s = s4[j * kLanes + t];
+        uint4 a = init ? uint4{0u, 0u, 0u, 0u} : a4[j * kLanes + t];
+        const uint32_t t0 = smont_mul(cur[4 * j + 0], s.x, p, pinv), t1 = smont_mul(cur[4 * j + 1], s.y, p, pinv);
+        const uint32_t t2 = smont_mul(cur[4 * j + 2], s.z, p, pinv), t3 = smont_mul(cur[4 * j + 3], s.w, p, pinv);
+        a.x = neg ? a.x - t0 : a.x + t0; a.y = neg ? a.y - t1 : a.y + t1;
+        a.z = neg ? a.z - t2 : a.z + t2; a.w = neg ? a.w - t3 : a.w + t3;
+        a4[j * kLanes + t] = a;
+    }
+}
+
+RZK_VM bool ops_use_acc1(const Op *ops)
+{
+    bool any = false;
+    RZK_NOUNROLL
+    for (int i = 0; i < kMaxOps && ops[i].code != OP_END; ++i)
+        any = any || ((ops[i].code == OP_MACV || ops[i].code == OP_INV) && ops[i].a == 1);
+    return any;
+}
+
+// every 32nd term of a looped product sum: the accumulators back below 1.06 p
+RZK_VM void reduce_accumulators_s(Lane *lanes, const LaneCtx *ctxs, bool with_acc1)
+{
+    RZK_EACH_LANE {
+        RZK_LANE;
+        const uint32_t mp = 0u - L.pc.p;
+        RZK_UNROLL
+        for (int e = 0; e < kElems; ++e) L.acc0[e] = sreduce<kSignedShift>(L.acc0[e], mp);
+        if (with_acc1) {
+            uint4 *a4 = reinterpret_cast<uint4 *>(ctx.acc1);
+            RZK_UNROLL
+            for (int j = 0; j < 8; ++j) {
+                uint4 a = a4[j * kLanes + t];
+                a.x = sreduce<kSignedShift>(a.x, mp); a.y = sreduce<kSignedShift>(a.y, mp);
+                a.z = sreduce<kSignedShift>(a.z, mp); a.w = sreduce<kSignedShift>(a.w, mp);
+                a4[j * kLanes + t] = a;
+            }
+        }
+    }
+}
+
 // accumulator-1 variants: the accumulator is the lane-private shared-memory slot
 RZK_VM void mac_key_smem(uint32_t *acc1, const uint32_t (&cur)[kElems], const uint32_t *krow, int t,
                          uint32_t flags, uint32_t p, uint32_t p2)
@@ -599,13 +688,23 @@ RZK_VM void mac_var_smem(uint32_t *acc1, const uint32_t (&cur)[kElems], const ui
     }
 }
 
+template <bool SGN = false>
 RZK_VM void op_st(Lane *lanes, const LaneCtx *ctxs, const Op &op)
 {
     RZK_EACH_LANE {
         RZK_LANE;
         const PrimeC &pc = L.pc;
         uint4 *s4 = reinterpret_cast<uint4 *>(ctx.slot);
-        if (op.b & ST_RAW) {            // operand of a Shoup product with the key: any 32-bit value is valid
+        if (SGN && !(op.b & ST_RAW)) {      // signed Montgomery operand: a representative below 1.06 p (one shift-reduce)
+            const uint32_t mp = 0u - pc.p;
+            RZK_UNROLL
+            for (int j = 0; j < 8; ++j) {
+                uint4 q;
+                q.x = sreduce<kSignedShift>(L.cur[4 * j + 0], mp); q.y = sreduce<kSignedShift>(L.cur[4 * j + 1], mp);
+                q.z = sreduce<kSignedShift>(L.cur[4 * j + 2], mp); q.w = sreduce<kSignedShift>(L.cur[4 * j + 3], mp);
+                s4[j * kLanes + t] = q;
+            }
+        } else if (op.b & ST_RAW) {            // operand of a Shoup product with the key: any 32-bit value is valid
             RZK_UNROLL
             for (int j = 0; j < 8; ++j) {
                 uint4 q;
@@ -675,14 +774,14 @@ RZK_VM void op_stg(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const Op
 // Number of coefficients a lane finishes: in the warp-per-item modes two half warps share an item.
 template <int MODE>
 struct Epi {
-    static constexpr int kCount = (MODE != MODE_SEQ) ? 16 : 32;
+    static constexpr int kCount = (!mode_seq(MODE)) ? 16 : 32;
     // Warp-per-item modes: the epilogue value is an exact integer in a double and the reduction mod q runs on the FP64
     // pipe (three FMAs), which relieves the FMA-heavy pipe of the wide multiplies and the mulhi per coefficient.
     //   MODE_SPLITKEY: |lo + 2^16 hi + plain terms| < 2^47.
     //   MODE_SPLIT:    the Garner digit h1 (centred) enters as (p0 * h1) mod q through an exact FMA product
     //                  (crt2_mod_q_f64), so the value is a0 + r + plain terms, < 2^35.
     // MODE_SEQ (1 or 3 primes) stays in int64
-    typedef typename std::conditional<MODE != MODE_SEQ, double, int64_t>::type V_t;
+    typedef typename std::conditional<!mode_seq(MODE), double, int64_t>::type V_t;
 };
 
 // coefficient index m (in the G1 layout, i = t + 16*m) of epilogue element j
@@ -690,7 +789,7 @@ template <int MODE>
 // Warp-per-item modes: half warp h finishes the rows m = 2j + h, so the two half warps of a warp touch ADJACENT 64-byte
 // segments of every row they read or write in the epilogue (coefficients t + 32j and t + 16 + 32j: one 128-byte line per
 // warp instruction) and 32 consecutive words of the rotation sum's extended row (OP_ROT: one conflict-free wavefront).
-RZK_VM int epi_m(const LaneCtx &ctx, int j) { return (MODE != MODE_SEQ) ? (2 * j + ctx.hw) : j; }
+RZK_VM int epi_m(const LaneCtx &ctx, int j) { return (!mode_seq(MODE)) ? (2 * j + ctx.hw) : j; }
 
 // OP_ADDP in two halves: the loads (issued BEFORE the inverse transform by the compile-time programs, so that their latency
 // -- an L2 hit, ~300 cycles -- is covered by the butterflies instead of stalling the epilogue) and the accumulation.
@@ -721,7 +820,7 @@ RZK_VM void op_addp_apply(typename Epi<MODE>::V_t (&V)[RZK_NL][Epi<MODE>::kCount
     constexpr int CNT = Epi<MODE>::kCount;
     const bool neg = op.c & MAC_NEG;
     RZK_EACH_LANE {
-        if constexpr (MODE != MODE_SEQ) {
+        if constexpr (!mode_seq(MODE)) {
             RZK_UNROLL
             for (int j = 0; j < CNT; ++j) V[li_][j] += neg ? -f64_exact_i32(v[li_][j]) : f64_exact_i32(v[li_][j]);
         } else {
@@ -750,7 +849,7 @@ RZK_VM void op_fin(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, typename
         int32_t res[CNT];
         RZK_UNROLL
         for (int j = 0; j < CNT; ++j) {
-            if constexpr (MODE != MODE_SEQ) res[j] = reduce_q_centered_f64(V[li_][j], K.qd, K.qinvd);
+            if constexpr (!mode_seq(MODE)) res[j] = reduce_q_centered_f64(V[li_][j], K.qd, K.qinvd);
             else res[j] = reduce_q_centered(V[li_][j], K.q, K.m30, K.kqh);
         }
         if (op.b & FIN_CMPZ) {
@@ -844,7 +943,7 @@ RZK_VM uint32_t rot_ctz(uint32_t v)       // v != 0
 template <int MODE>
 RZK_VM void op_rot(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, typename Epi<MODE>::V_t (&V)[RZK_NL][Epi<MODE>::kCount], const Op &op, int it)
 {
-    if constexpr (MODE != MODE_SEQ) {
+    if constexpr (!mode_seq(MODE)) {
         constexpr int CNT = Epi<MODE>::kCount;
         const Stream sc = K.st[op.a], sd = K.st[op.b];
         const bool neg = op.c & MAC_NEG;          // V -= c*d: every term's sign flips
@@ -1054,7 +1153,7 @@ RZK_VM double crt2_mod_q_f64(const VmLaunch &K, uint32_t a0, uint32_t a1)
 // same lane, L2-resident), and only four 64-bit values are live at a time.  That keeps the kernel within 128 registers
 // (16 warps per SM instead of the 8 that 223 registers allowed) and takes 4 KB per half warp out of shared memory.
 template <int NP, int MODE>
-struct ChunkedEpi { static constexpr bool value = (MODE == MODE_SEQ && NP == 3); };
+struct ChunkedEpi { static constexpr bool value = (mode_seq(MODE) && NP == 3); };
 constexpr int kEpiChunk = 4;
 
 template <int NP>
@@ -1146,7 +1245,12 @@ RZK_VM void inv_core(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const 
                 L.cur[4 * j + 0] = a.x; L.cur[4 * j + 1] = a.y; L.cur[4 * j + 2] = a.z; L.cur[4 * j + 3] = a.w;
             }
         }
-        if constexpr (MODE == MODE_SPLITKEY_S) inv_g2_s(L.cur, ctx.g2 + ((L.pi * 2 + 1) * kLanes + t) * kG2Words, 0u - pc.p);
+        if constexpr (MODE == MODE_SEQ_S) {
+            // a product sum of up to 33 terms since its last reduction: back below 1.06 p (the inverse admits 5p/2)
+            RZK_UNROLL
+            for (int e = 0; e < kElems; ++e) L.cur[e] = sreduce<kSignedShift>(L.cur[e], 0u - pc.p);
+        }
+        if constexpr (mode_signed(MODE)) inv_g2_s(L.cur, ctx.g2 + ((L.pi * 2 + 1) * kLanes + t) * kG2Words, 0u - pc.p);
         else inv_g2(L.cur, ctx.g2 + ((L.pi * 2 + 1) * kLanes + t) * kG2Words, pc.p, pc.p2, pc.pad_, L.cap);
         uint4 *row = reinterpret_cast<uint4 *>(ctx.buf + 36 * t);
         RZK_UNROLL
@@ -1166,7 +1270,18 @@ RZK_VM void inv_core(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const 
             L.cur[m] = ctx.buf[i + ((i >> 5) << 2)];
         }
         if constexpr (MODE == MODE_SPLITKEY_S) {
-            inv_g1_s(L.cur, ctx.g1 + (L.pi * 2 + 1) * kG1Words, 0u - pc.p);    // any representative below 20.2 p: centred in the epilogue
+            inv_g1_s<true>(L.cur, ctx.g1 + (L.pi * 2 + 1) * kG1Words, 0u - pc.p);    // any representative below 20.2 p: centred in the epilogue
+        } else if constexpr (MODE == MODE_SEQ_S) {
+            // the Garner recombination wants the canonical residue in [0, p): shift-reduce to (-0.06 p, 1.06 p), lift the
+            // negative ones by p, one conditional subtraction
+            const uint32_t mp = 0u - pc.p;
+            inv_g1_s<false>(L.cur, ctx.g1 + (L.pi * 2 + 1) * kG1Words, mp);
+            RZK_UNROLL
+            for (int m = 0; m < kElems; ++m) {
+                const uint32_t r = sreduce<kSignedShift>(L.cur[m], mp);
+                const uint32_t lifted = r + (((uint32_t)((int32_t)r >> 31)) & pc.p);
+                L.cur[m] = csub(lifted, pc.p);
+            }
         } else {
             inv_g1(L.cur, ctx.g1 + (L.pi * 2 + 1) * kG1Words, pc.p, pc.p2, pc.pad_, L.cap);
             RZK_UNROLL
@@ -1177,7 +1292,7 @@ RZK_VM void inv_core(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const 
 #if defined(__CUDA_ARCH__)
     pp_release(K, *ctxs[0].pp_count);
 #endif
-    if (MODE != MODE_SEQ) {
+    if (!mode_seq(MODE)) {
         // MODE_SPLIT: half warp 0 holds residues mod p0, half warp 1 mod p1, both for all 512
         // coefficients.  MODE_SPLITKEY: half warp 0 holds the lo part, half warp 1 the hi part.
         // Lane (h, t) finishes the rows m = 2j + h (epi_m): it keeps its own value of those
@@ -1270,7 +1385,7 @@ template <int NP, int MODE>
 RZK_VM int op_inv(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int q, int it, int prime_iter)
 {
     const Op op = K.ops[q];
-    const bool last = (MODE != MODE_SEQ) || (prime_iter == NP - 1);
+    const bool last = (!mode_seq(MODE)) || (prime_iter == NP - 1);
     typename Epi<MODE>::V_t V[RZK_NL][Epi<MODE>::kCount];
     inv_core<NP, MODE>(K, lanes, ctxs, op, prime_iter, V);
     ++q;
@@ -1309,7 +1424,7 @@ template <int MODE>
 RZK_VM void op_norm(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const Op &op, uint32_t dtype)
 {
     constexpr int CNT = Epi<MODE>::kCount;
-    constexpr int RED_N = (MODE != MODE_SEQ) ? 32 : 16;
+    constexpr int RED_N = (!mode_seq(MODE)) ? 32 : 16;
     const Stream st = K.st[op.a];
     const uint32_t abs_lim = K.norm_abs_lim[op.b];
     const uint64_t sq_lim = K.norm_sq_lim[op.b];
@@ -1421,8 +1536,8 @@ RZK_VM void vm_run_item(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs)
 {
     static_assert(MODE != MODE_SPLIT || NP == 2, "MODE_SPLIT maps the two half warps to two primes");
     static_assert(!mode_sk(MODE) || NP == 1, "MODE_SPLITKEY works modulo one prime");
-    constexpr int RED_N = (MODE != MODE_SEQ) ? 32 : 16;
-    constexpr int PRIME_ITERS = (MODE != MODE_SEQ) ? 1 : NP;
+    constexpr int RED_N = (!mode_seq(MODE)) ? 32 : 16;
+    constexpr int PRIME_ITERS = (!mode_seq(MODE)) ? 1 : NP;
     constexpr int KP = mode_sk(MODE) ? 2 * kKeyPolys : kKeyPolys;     // key images per prime
     RZK_EACH_LANE { RZK_LANE; L.fail = 0; L.rerr = 0; }
     int pc = 0;
@@ -1453,7 +1568,7 @@ RZK_VM void vm_run_item(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs)
 #if defined(__CUDA_ARCH__)
                     cta_lockstep(K);
 #endif
-                    op_fwd<MODE == MODE_SPLITKEY_S>(K, lanes, ctxs, op, it, K.st[op.a].dtype);
+                    op_fwd<mode_signed(MODE), MODE == MODE_SPLITKEY_S>(K, lanes, ctxs, op, it, K.st[op.a].dtype);
                     break;
                 case OP_MACK:
                     RZK_EACH_LANE {
@@ -1473,12 +1588,17 @@ RZK_VM void vm_run_item(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs)
                 case OP_MACV:
                     RZK_EACH_LANE {
                         RZK_LANE;
-                        if (op.a == 0) mac_var(L.acc0, L.cur, ctx.slot, t, op.c, L.pc.p, L.pc.p2, L.pc.pinv);
-                        else mac_var_smem(ctx.acc1, L.cur, ctx.slot, t, op.c, L.pc.p, L.pc.p2, L.pc.pinv);
+                        if constexpr (MODE == MODE_SEQ_S) {
+                            if (op.a == 0) mac_var_s(L.acc0, L.cur, ctx.slot, t, op.c, L.pc.p, L.pc.pinv);
+                            else mac_var_smem_s(ctx.acc1, L.cur, ctx.slot, t, op.c, L.pc.p, L.pc.pinv);
+                        } else {
+                            if (op.a == 0) mac_var(L.acc0, L.cur, ctx.slot, t, op.c, L.pc.p, L.pc.p2, L.pc.pinv);
+                            else mac_var_smem(ctx.acc1, L.cur, ctx.slot, t, op.c, L.pc.p, L.pc.p2, L.pc.pinv);
+                        }
                     }
                     break;
                 case OP_ST:
-                    op_st(lanes, ctxs, op);
+                    op_st<mode_signed(MODE)>(lanes, ctxs, op);
                     break;
                 case OP_STG:
                     op_stg(K, lanes, ctxs, op);
@@ -1504,6 +1624,7 @@ RZK_VM void vm_run_item(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs)
                     loop_start = q + 1; loop_cnt = op.off; it = 0;
                     break;
                 case OP_ENDLOOP:
+                    if constexpr (MODE == MODE_SEQ_S) { if ((it & 31) == 31) reduce_accumulators_s(lanes, ctxs, ops_use_acc1(K.ops)); }
                     if (++it < loop_cnt) { q = loop_start; continue; }
                     it = 0;
                     break;
@@ -1531,6 +1652,13 @@ template <class SP, class = void>
 struct SpPreload { static constexpr int value = 0; };
 template <class SP>
 struct SpPreload<SP, std::void_t<decltype(SP::kPreload)>> { static constexpr int value = SP::kPreload; };
+
+constexpr bool sp_uses_acc1(const Prog &p)
+{
+    for (int i = 0; i < kMaxOps && p.ops[i].code != OP_END; ++i)
+        if ((p.ops[i].code == OP_MACV || p.ops[i].code == OP_MACK || p.ops[i].code == OP_INV) && p.ops[i].a == 1) return true;
+    return false;
+}
 
 constexpr int sp_find_endloop(const Prog &p, int pc)
 {
@@ -1635,7 +1763,10 @@ RZK_VM void sp_exec(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int it,
     } else if constexpr (op.code == OP_LOOP) {
         constexpr int end = sp_find_endloop(SP::prog, PC);
         RZK_NOUNROLL
-        for (int i = 0; i < (int)K.loop_count; ++i) sp_exec<SP, NP, MODE, PC + 1>(K, lanes, ctxs, i, prime_iter);
+        for (int i = 0; i < (int)K.loop_count; ++i) {
+            sp_exec<SP, NP, MODE, PC + 1>(K, lanes, ctxs, i, prime_iter);
+            if constexpr (MODE == MODE_SEQ_S) { if ((i & 31) == 31) reduce_accumulators_s(lanes, ctxs, sp_uses_acc1(SP::prog)); }
+        }
         sp_exec<SP, NP, MODE, end + 1>(K, lanes, ctxs, 0, prime_iter);
     } else if constexpr (op.code == OP_INV) {
         constexpr int next = sp_skip_epilogue(SP::prog, PC + 1);
@@ -1648,7 +1779,7 @@ RZK_VM void sp_exec(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int it,
                 op_addp_load<MODE>(K, ctxs, small, e0, it, DT_I8);
                 inv_core<NP, MODE>(K, lanes, ctxs, op, prime_iter, V, small);
                 sp_epilogue<SP, MODE, PC + 2>(K, lanes, ctxs, V, it);
-            } else if constexpr (MODE != MODE_SEQ && SpPreload<SP>::value > 0) {
+            } else if constexpr (!mode_seq(MODE) && SpPreload<SP>::value > 0) {
                 constexpr int NPRE = sp_count_addp(SP::prog, PC + 1) < SpPreload<SP>::value ? sp_count_addp(SP::prog, PC + 1) : SpPreload<SP>::value;
                 int32_t pre[NPRE > 0 ? NPRE : 1][RZK_NL][Epi<MODE>::kCount];
                 sp_preload<SP, MODE, PC + 1, 0, NPRE>(K, ctxs, pre, it);
@@ -1665,7 +1796,7 @@ RZK_VM void sp_exec(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int it,
                         sp_epilogue_chunk<SP, PC + 1>(K, lanes, ctxs, V4, it, j);
                     }
                 }
-            } else if ((MODE != MODE_SEQ) || prime_iter == NP - 1) sp_epilogue<SP, MODE, PC + 1>(K, lanes, ctxs, V, it);
+            } else if ((!mode_seq(MODE)) || prime_iter == NP - 1) sp_epilogue<SP, MODE, PC + 1>(K, lanes, ctxs, V, it);
             }
         }
         sp_exec<SP, NP, MODE, next>(K, lanes, ctxs, it, prime_iter);
@@ -1678,7 +1809,7 @@ RZK_VM void sp_exec(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int it,
             if (K.cta_sync < 8 || SP::prog.ops[PC - 1].code == OP_SEG) cta_lockstep(K);
 #endif
             constexpr uint32_t dt = SP::dtype[op.a];
-            op_fwd<MODE == MODE_SPLITKEY_S>(K, lanes, ctxs, op, it, dt);
+            op_fwd<mode_signed(MODE), MODE == MODE_SPLITKEY_S>(K, lanes, ctxs, op, it, dt);
         } else if constexpr (op.code == OP_MACK) {
             RZK_EACH_LANE {
                 RZK_LANE;
@@ -1696,11 +1827,16 @@ RZK_VM void sp_exec(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int it,
         } else if constexpr (op.code == OP_MACV) {
             RZK_EACH_LANE {
                 RZK_LANE;
-                if constexpr (op.a == 0) mac_var(L.acc0, L.cur, ctx.slot, t, op.c, L.pc.p, L.pc.p2, L.pc.pinv);
-                else mac_var_smem(ctx.acc1, L.cur, ctx.slot, t, op.c, L.pc.p, L.pc.p2, L.pc.pinv);
+                if constexpr (MODE == MODE_SEQ_S) {
+                    if constexpr (op.a == 0) mac_var_s(L.acc0, L.cur, ctx.slot, t, op.c, L.pc.p, L.pc.pinv);
+                    else mac_var_smem_s(ctx.acc1, L.cur, ctx.slot, t, op.c, L.pc.p, L.pc.pinv);
+                } else {
+                    if constexpr (op.a == 0) mac_var(L.acc0, L.cur, ctx.slot, t, op.c, L.pc.p, L.pc.p2, L.pc.pinv);
+                    else mac_var_smem(ctx.acc1, L.cur, ctx.slot, t, op.c, L.pc.p, L.pc.p2, L.pc.pinv);
+                }
             }
         } else if constexpr (op.code == OP_ST) {
-            op_st(lanes, ctxs, op);
+            op_st<mode_signed(MODE)>(lanes, ctxs, op);
         } else if constexpr (op.code == OP_STG) {
             op_stg(K, lanes, ctxs, op);
         } else if constexpr (op.code == OP_MACG) {
@@ -1740,7 +1876,7 @@ RZK_VM void sp_segments(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs)
 {
     constexpr Op op = SP::prog.ops[PC];
     if constexpr (op.code == OP_SEG) {
-        constexpr int PRIME_ITERS = (MODE != MODE_SEQ) ? 1 : NP;
+        constexpr int PRIME_ITERS = (!mode_seq(MODE)) ? 1 : NP;
         RZK_NOUNROLL
         for (int prime_iter = 0; prime_iter < PRIME_ITERS; ++prime_iter) {
             RZK_EACH_LANE {
@@ -1768,7 +1904,7 @@ template <class SP>
 RZK_VM void vm_run_static(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs)
 {
     constexpr int NP = SP::kNP, MODE = SP::kMode;
-    constexpr int RED_N = (MODE != MODE_SEQ) ? 32 : 16;
+    constexpr int RED_N = (!mode_seq(MODE)) ? 32 : 16;
     RZK_EACH_LANE { RZK_LANE; L.fail = 0; L.rerr = 0; }
     sp_norms<SP, NP, MODE, 0>(K, lanes, ctxs);
     sp_segments<SP, NP, MODE, sp_first_seg(SP::prog)>(K, lanes, ctxs);

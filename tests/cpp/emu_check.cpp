@@ -95,7 +95,7 @@ struct Emu {
     void run(uint32_t n_items)
     {
         K.n_items = n_items;
-        const bool split = (mode != MODE_SEQ);
+        const bool split = !mode_seq(mode);
         static std::vector<uint32_t> gst;
         if (K.acc1_global) { gst.assign((size_t)2 * kSlotWords, 0xDEADBEEFu); K.gstash = gst.data(); }   // as the kernel: accumulator 1 outside the region
         layout_hw(K, split);
@@ -123,6 +123,7 @@ struct Emu {
             if constexpr (!std::is_void<SP>::value) vm_run_static<SP>(K, lanes, ctxs);
             else if (mode == MODE_SPLITKEY) vm_run_item<1, MODE_SPLITKEY>(K, lanes, ctxs);
             else if (mode == MODE_SPLITKEY_S) vm_run_item<1, MODE_SPLITKEY_S>(K, lanes, ctxs);
+            else if (mode == MODE_SEQ_S) vm_run_item<3, MODE_SEQ_S>(K, lanes, ctxs);
             else if (np == 1) vm_run_item<1, MODE_SEQ>(K, lanes, ctxs);
             else if (np == 2) vm_run_item<2, MODE_SPLIT>(K, lanes, ctxs);
             else vm_run_item<3, MODE_SEQ>(K, lanes, ctxs);
@@ -553,6 +554,74 @@ int main(int argc, char **argv)
                 CHECK(o0 == r0, "mulsum2 out0 differs (T=%d pass %d)", TT, pass);
                 CHECK(o1 == r1, "mulsum2 out1 differs (T=%d pass %d)", TT, pass);
             }
+        }
+        // ---- the same product sums modulo the three small primes, signed lazy arithmetic (MODE_SEQ_S) ----
+        {
+            const int LS3[3] = {kSignedSlot, kSignedSlot + 1, kSignedSlot + 2};
+            std::vector<int32_t> o_i(B * N, 0), o_s(B * N, 0);
+            Emu EI(3, LS3, keyp.data(), B, MODE_SEQ_S);
+            pr.install(EI.K);
+            EI.stream(0, gs.data(), T, DT_I32); EI.stream(1, xs.data(), T, DT_I32); EI.stream(2, sub.data(), 1, DT_I32);
+            EI.stream(3, o_i.data(), 1, DT_I32);
+            EI.run(B);
+            CHECK(o_i == out_e, "signed mulsum (interpreted) differs");
+            Emu ES(3, LS3, keyp.data(), B, MODE_SEQ_S);
+            SPMulSum1S::prog.install(ES.K);
+            ES.K.loop_count = T - 1;
+            ES.stream(0, gs.data(), T, DT_I32); ES.stream(1, xs.data(), T, DT_I32); ES.stream(2, sub.data(), 1, DT_I32);
+            ES.stream(4, o_s.data(), 1, DT_I32);
+            ES.run<SPMulSum1S>(B);
+            CHECK(o_s == out_e, "signed mulsum (static) differs");
+            // two accumulators, and the compare form (a tampered plain term must flag exactly its item)
+            std::vector<int32_t> cs2(xs.size());
+            for (size_t i = 0; i < cs2.size(); ++i) cs2[i] = xs[(i * 7 + 3) % xs.size()];
+            std::vector<int32_t> r0(B * N, 0), r1(B * N, 0), o0(B * N, 0), o1(B * N, 0);
+            Emu EA(3, L2, keyp.data(), B);
+            SPMulSum2::prog.install(EA.K); EA.K.loop_count = T - 1;
+            EA.stream(0, gs.data(), T, DT_I32); EA.stream(1, xs.data(), T, DT_I32); EA.stream(2, cs2.data(), T, DT_I32);
+            EA.stream(3, sub.data(), 1, DT_I32); EA.stream(4, r0.data(), 1, DT_I32); EA.stream(5, r1.data(), 1, DT_I32);
+            EA.run<SPMulSum2>(B);
+            Emu E2(3, LS3, keyp.data(), B, MODE_SEQ_S);
+            SPMulSum2S::prog.install(E2.K); E2.K.loop_count = T - 1;
+            E2.stream(0, gs.data(), T, DT_I32); E2.stream(1, xs.data(), T, DT_I32); E2.stream(2, cs2.data(), T, DT_I32);
+            E2.stream(3, sub.data(), 1, DT_I32); E2.stream(4, o0.data(), 1, DT_I32); E2.stream(5, o1.data(), 1, DT_I32);
+            E2.run<SPMulSum2S>(B);
+            CHECK(o0 == r0 && o1 == r1, "signed mulsum2 differs");
+            std::vector<int32_t> zero(B * N, 0);
+            Emu EC(3, LS3, keyp.data(), B, MODE_SEQ_S);
+            SPMulSumCmpS::prog.install(EC.K); EC.K.loop_count = T - 1;
+            EC.stream(0, gs.data(), T, DT_I32); EC.stream(1, xs.data(), T, DT_I32); EC.stream(2, r0.data(), 1, DT_I32);
+            EC.stream(3, zero.data(), 1, DT_I32);
+            EC.run<SPMulSumCmpS>(B);
+            for (int b = 0; b < B; ++b) CHECK(EC.flags[b] == 0, "signed mulsum compare: honest item %d flagged", b);
+            r0[(size_t)(B - 1) * N + 77] ^= 1;
+            EC.flags.assign(B, 0); EC.K.flags = EC.flags.data();
+            EC.run<SPMulSumCmpS>(B);
+            for (int b = 0; b < B; ++b) CHECK(EC.flags[b] == (b == B - 1 ? FLAG_FAIL : 0u), "signed mulsum compare: item %d flag %u", b, EC.flags[b]);
+            // 64 terms at the extremes of int32: the edge of the three small primes' range (64 * 512 * 2^62 < P/2), and the
+            // accumulator reduction every 32nd term
+            const int TB = 64;
+            std::vector<int32_t> gb((size_t)2 * TB * N), xb(gb.size()), ob(2 * N, 0), oref(2 * N, 0);
+            for (size_t i = 0; i < gb.size(); ++i) {
+                gb[i] = i < (size_t)TB * N ? INT32_MIN : rnd_q();
+                xb[i] = i < (size_t)TB * N ? ((i % N == 0) ? INT32_MIN : INT32_MAX) : rnd_q();      // X^N = -1: every wrapped term flips sign again
+            }
+            for (int which = 0; which < 2; ++which) {
+                Emu EB(3, which ? LS3 : L2, keyp.data(), 2, which ? MODE_SEQ_S : MODE_SEQ);
+                SPMulSum0::prog.install(EB.K); EB.K.loop_count = TB - 1;
+                EB.stream(0, gb.data(), TB, DT_I32); EB.stream(1, xb.data(), TB, DT_I32); EB.stream(4, which ? ob.data() : oref.data(), 1, DT_I32);
+                if (which) EB.run<SPMulSum0S>(2); else EB.run<SPMulSum0>(2);
+            }
+            CHECK(ob == oref, "signed mulsum, 64 terms at the int32 extremes, differs from the 30-bit primes");
+            auto gb64 = widen(gb), xb64 = widen(xb);
+            for (auto *v : {&gb64, &xb64}) for (auto &c : *v) c = rzko_center(c, Q);
+            std::vector<int64_t> accb(N), tmpb(N);
+            for (int i = 0; i < TB; ++i) {
+                rzko_poly_mul(&P, xb64.data() + (size_t)i * N, gb64.data() + (size_t)i * N, i ? tmpb.data() : accb.data());
+                if (i) rzko_poly_add(&P, accb.data(), tmpb.data(), accb.data());
+            }
+            for (size_t i = 0; i < N; ++i) CHECK(accb[i] == ob[i], "signed mulsum 64 terms vs oracle coef %zu", i);
+            printf("signed product sums ok\n");
         }
         printf("mulsum T=%d ok, ops=%d\n", T, pr.n);
     }
