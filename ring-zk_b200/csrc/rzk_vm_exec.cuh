@@ -53,6 +53,10 @@ struct uint4 { uint32_t x, y, z, w; };
 struct uint2 { uint32_t x, y; };
 #endif
 
+#ifndef RZK_SMALL_LATE
+#define RZK_SMALL_LATE 1      // MODE_SPLITKEY_S: fetch the int8 plain term of an epilogue after the inverse transform instead of before
+#endif
+
 #define RZK_LANE Lane &L = lanes[li_]; const LaneCtx &ctx = ctxs[li_]; const int t = ctx.t; (void)t; (void)L; (void)ctx
 
 namespace rzk {
@@ -446,6 +450,11 @@ RZK_VM void op_fwd(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const Op
             RZK_UNROLL
             for (int m = 0; m < kElems; ++m) mx = umax32(mx, (uint32_t)v[m] + K.small_lim);
             L.rerr |= (mx > 2u * K.small_lim) ? 1u : 0u;
+#if defined(__CUDA_ARCH__)
+            // (materialise the verdict here: left alone the compiler sinks the whole check to the end of the item and keeps --
+            // spills -- the 32 inputs across every transform)
+            asm volatile("" : "+r"(L.rerr));
+#endif
         }
         if constexpr (SGN) {
             // signed lazy form: an int8 operand is its own input; an int32 operand (ANY representative, |v| <= 2^31) is brought
@@ -793,7 +802,20 @@ RZK_VM int epi_m(const LaneCtx &ctx, int j) { return (!mode_seq(MODE)) ? (2 * j 
 
 // OP_ADDP in two halves: the loads (issued BEFORE the inverse transform by the compile-time programs, so that their latency
 // -- an L2 hit, ~300 cycles -- is covered by the butterflies instead of stalling the epilogue) and the accumulation.
-template <int MODE>
+// one int8 with a load the compilers keep where it is written (relaxed, gpu scope): a plain load of read-only data is hoisted
+// to the top of the item loop and its 16 results are then spilled across the transforms
+RZK_VM int32_t ld_i8_pinned(const int8_t *p)
+{
+#if defined(__CUDA_ARCH__)
+    int32_t v;
+    asm volatile("ld.relaxed.gpu.global.s8 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+#else
+    return *p;
+#endif
+}
+
+template <int MODE, bool PINNED = false>
 RZK_VM void op_addp_load(const VmLaunch &K, const LaneCtx *ctxs, int32_t (&v)[RZK_NL][Epi<MODE>::kCount], const Op &op, int it, uint32_t dtype)
 {
     constexpr int CNT = Epi<MODE>::kCount;
@@ -805,7 +827,7 @@ RZK_VM void op_addp_load(const VmLaunch &K, const LaneCtx *ctxs, int32_t (&v)[RZ
         if (dtype == DT_I8) {
             const int8_t *src = reinterpret_cast<const int8_t *>(st.base) + poly * kN;
             RZK_UNROLL
-            for (int j = 0; j < CNT; ++j) v[li_][j] = src[t + kLanes * epi_m<MODE>(ctx, j)];
+            for (int j = 0; j < CNT; ++j) v[li_][j] = PINNED ? ld_i8_pinned(src + t + kLanes * epi_m<MODE>(ctx, j)) : (int32_t)src[t + kLanes * epi_m<MODE>(ctx, j)];
         } else {
             const int32_t *src = reinterpret_cast<const int32_t *>(st.base) + poly * kN;
             RZK_UNROLL
@@ -1224,9 +1246,11 @@ RZK_VM void op_fin_chunk(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, in
 template <int NP, int MODE>
 RZK_VM void inv_core(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const Op &op, int prime_iter,
                      typename Epi<MODE>::V_t (&V)[RZK_NL][Epi<MODE>::kCount],
-                     const int32_t (*small)[Epi<MODE>::kCount] = nullptr)
+                     const int32_t (*small)[Epi<MODE>::kCount] = nullptr, const Op *small_late = nullptr, int it = 0)
 {
     constexpr int CNT = Epi<MODE>::kCount;
+    int32_t small_buf[RZK_NL][CNT];      // `small_late`: the int8 plain term is fetched AFTER the transform (no 16 registers held across it)
+    (void)small_buf;
     RZK_SYNC();      // every OP_LD of the partner half warp has finished (the slot may overlay this buffer)
 #if defined(__CUDA_ARCH__)
     pp_acquire(K);
@@ -1292,6 +1316,9 @@ RZK_VM void inv_core(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const 
 #if defined(__CUDA_ARCH__)
     pp_release(K, *ctxs[0].pp_count);
 #endif
+    if constexpr (!mode_seq(MODE)) {
+        if (small_late) { op_addp_load<MODE, true>(K, ctxs, small_buf, *small_late, it, DT_I8); small = small_buf; }
+    }
     if (!mode_seq(MODE)) {
         // MODE_SPLIT: half warp 0 holds residues mod p0, half warp 1 mod p1, both for all 512
         // coefficients.  MODE_SPLITKEY: half warp 0 holds the lo part, half warp 1 the hi part.
@@ -1775,9 +1802,14 @@ RZK_VM void sp_exec(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int it,
             if constexpr (mode_sk(MODE) && SP::prog.ops[PC + 1].code == OP_ADDP && SP::dtype[SP::prog.ops[PC + 1].a] == DT_I8 &&
                           !(SP::prog.ops[PC + 1].c & MAC_NEG)) {
                 constexpr Op e0 = SP::prog.ops[PC + 1];
-                int32_t small[RZK_NL][Epi<MODE>::kCount];
-                op_addp_load<MODE>(K, ctxs, small, e0, it, DT_I8);
-                inv_core<NP, MODE>(K, lanes, ctxs, op, prime_iter, V, small);
+                if constexpr (MODE == MODE_SPLITKEY_S && RZK_SMALL_LATE) {
+                    const Op e0c = e0;
+                    inv_core<NP, MODE>(K, lanes, ctxs, op, prime_iter, V, nullptr, &e0c, it);
+                } else {
+                    int32_t small[RZK_NL][Epi<MODE>::kCount];
+                    op_addp_load<MODE>(K, ctxs, small, e0, it, DT_I8);
+                    inv_core<NP, MODE>(K, lanes, ctxs, op, prime_iter, V, small);
+                }
                 sp_epilogue<SP, MODE, PC + 2>(K, lanes, ctxs, V, it);
             } else if constexpr (!mode_seq(MODE) && SpPreload<SP>::value > 0) {
                 constexpr int NPRE = sp_count_addp(SP::prog, PC + 1) < SpPreload<SP>::value ? sp_count_addp(SP::prog, PC + 1) : SpPreload<SP>::value;
