@@ -48,7 +48,8 @@ MEASURED_IMAD_TPS = 18.1        # T IMAD/s, profiles/r1_imad_bench.jsonl
 MEASURED_MULMOD_TPS = 4.617     # T Shoup-mulmods/s, same file
 METRIC = "commitments/s"
 UNIT = "commitments/s"
-COMMIT_KERNEL = ("rzk_vm_kernel<1, MODE_SPLITKEY, SPCommitSplitKey> (integer split-key program, CTA halves phase-mixed)", "commit_int_splitkey")
+COMMIT_KERNEL = ("rzk_vm_kernel<1, MODE_SPLITKEY_S, SPCommitSplitKeyS> (split-key program modulo one 26-bit prime, signed lazy arithmetic, "
+                 "CTA halves phase-mixed)", "commit_splitkey_s")
 WORKLOAD = "configs[1]: batched commitment generation, 2^16 messages/GPU at N=512, Params::default(), one shared key"
 
 
