@@ -1473,19 +1473,24 @@ RZK_VM void op_norm(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const O
             } else if (abs_lim < (1u << 21)) {
                 // Bounds below 2^21 (the default parameters): a coefficient can only pass if its int32 value is
                 // already the small canonical residue (a non-canonical int32 representative is > 1.3e9 in magnitude
-                // once centred), so |v| < 2^21 is tested on the raw value and the squares are summed exactly in binary64
-                // (512 * 2^42 < 2^53) on the FP64 pipe, which these integer kernels leave idle.
-                const int32_t *src = reinterpret_cast<const int32_t *>(st.base) + poly * kN;
-                double acc = 0.0;
-                uint32_t rng = 0;
+                // once centred), so |v| < 2^21 is tested on the raw value -- one add-and-max per coefficient -- and the
+                // squares are summed in a 64-bit integer (one IMAD.WIDE each; exact whenever the range test passes:
+                // CNT * 2^42 < 2^63).  Any partition of the 512 coefficients works for a norm: CNT contiguous words per
+                // lane, fetched with 128-bit loads (the warp reads the 2 KB row as one contiguous run).
+                const int32_t *src = reinterpret_cast<const int32_t *>(st.base) + poly * kN + ctx.ridx * CNT;
+                int64_t acc = 0;
+                uint32_t mx = 0;
                 RZK_UNROLL
-                for (int j = 0; j < CNT; ++j) {
-                    const int32_t v = src[t + kLanes * epi_m<MODE>(ctx, j)];
-                    rng |= (uint32_t)v + (1u << 21);
-                    const double dv = f64_exact_i32(v);
-                    acc = f64_exact_fma(dv, dv, acc);
+                for (int j = 0; j < CNT / 4; ++j) {
+                    const uint4 q4 = rot_ld128(src + 4 * j);
+                    const int32_t vv[4] = {(int32_t)q4.x, (int32_t)q4.y, (int32_t)q4.z, (int32_t)q4.w};
+                    RZK_UNROLL
+                    for (int e = 0; e < 4; ++e) {
+                        mx = umax32(mx, (uint32_t)vv[e] + (1u << 21));
+                        acc += (int64_t)vv[e] * (int64_t)vv[e];
+                    }
                 }
-                bad = (rng >> 22) ? 1u : 0u;
+                bad = (mx >> 22) ? 1u : 0u;
                 s = bad ? 0ull : (uint64_t)acc;
             } else {
                 const int32_t *src = reinterpret_cast<const int32_t *>(st.base) + poly * kN;
@@ -1500,17 +1505,21 @@ RZK_VM void op_norm(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const O
             }
             L.fail |= bad;
 #if defined(__CUDA_ARCH__)
+            // RED_N lane sums that are each at most sq_lim / RED_N cannot exceed the bound together (an honest response sits at
+            // a quarter of it): one vote then replaces the reduction; otherwise
             // sum over the lanes that own the item (half warp in MODE_SEQ, full warp otherwise)
-            uint32_t lo = (uint32_t)s, hi = (uint32_t)(s >> 32);
-            RZK_UNROLL
-            for (int d = RED_N / 2; d >= 1; d >>= 1) {
-                const uint32_t olo = __shfl_xor_sync(0xffffffffu, lo, d);
-                const uint32_t ohi = __shfl_xor_sync(0xffffffffu, hi, d);
-                const uint64_t sum = (((uint64_t)hi << 32) | lo) + (((uint64_t)ohi << 32) | olo);
-                lo = (uint32_t)sum; hi = (uint32_t)(sum >> 32);
+            if (__any_sync(0xffffffffu, s > sq_lim / (uint64_t)RED_N)) {
+                uint32_t lo = (uint32_t)s, hi = (uint32_t)(s >> 32);
+                RZK_UNROLL
+                for (int d = RED_N / 2; d >= 1; d >>= 1) {
+                    const uint32_t olo = __shfl_xor_sync(0xffffffffu, lo, d);
+                    const uint32_t ohi = __shfl_xor_sync(0xffffffffu, hi, d);
+                    const uint64_t sum = (((uint64_t)hi << 32) | lo) + (((uint64_t)ohi << 32) | olo);
+                    lo = (uint32_t)sum; hi = (uint32_t)(sum >> 32);
+                }
+                const uint64_t tot = ((uint64_t)hi << 32) | lo;
+                L.fail |= (tot > sq_lim) ? 1u : 0u;
             }
-            const uint64_t tot = ((uint64_t)hi << 32) | lo;
-            L.fail |= (tot > sq_lim) ? 1u : 0u;
         }
 #else
             ctx.red[2 * ctx.ridx] = (uint32_t)s;
