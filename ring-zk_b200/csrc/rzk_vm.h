@@ -185,16 +185,14 @@ inline ProgNeeds scan_needs(const Op *ops)
 
 // Lists the input streams of a program (read by OP_FWD / OP_ADDP / OP_NORM / OP_ROT) for prefetching, with the number of
 // leading polynomials of each row group that are actually read.
-constexpr uint32_t kWholePrefetchRows = 8;
 inline void list_prefetch(VmLaunch &K)
 {
     bool is_out[kMaxStreams] = {}, is_in[kMaxStreams] = {};
     uint32_t used[kMaxStreams] = {};
     bool in_loop = false;
-    // (a looped stream of more than 8 rows per item is prefetched term by term inside the loop instead -- sp_loop_prefetch)
     auto touch = [&](int s, uint32_t off, uint32_t cnt, bool whole) {
         is_in[s] = true;
-        const uint32_t hi = (whole && K.st[s].stride <= kWholePrefetchRows) ? K.st[s].stride : off + cnt;
+        const uint32_t hi = whole ? K.st[s].stride : off + cnt;
         if (hi > used[s]) used[s] = hi;
     };
     for (int i = 0; i < kMaxOps && K.ops[i].code != OP_END; ++i) {

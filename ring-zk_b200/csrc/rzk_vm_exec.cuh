@@ -1788,29 +1788,6 @@ constexpr int sp_skip_epilogue(const Prog &p, int pc)
     return pc;
 }
 
-// L2 prefetch of the rows that iteration `it` of a loop body will transform (every OP_FWD of the body that steps through its
-// stream): one 128-byte line per lane.  A product sum of T terms walks T rows per stream and item, once per prime -- hundreds
-// of KB per resident half warp, far more than L2 holds for a whole wave -- so the rows are asked for one term ahead instead
-// of all at once when the item starts (list_prefetch keeps the item-level prefetch for the first term only).
-template <class SP, int PC>
-RZK_VM void sp_loop_prefetch(const VmLaunch &K, const LaneCtx *ctxs, int it)
-{
-    constexpr Op op = SP::prog.ops[PC];
-    if constexpr (op.code != OP_ENDLOOP && op.code != OP_END) {
-#if defined(__CUDA_ARCH__)
-        if constexpr (op.code == OP_FWD && op.step != 0) {
-            const LaneCtx &ctx = ctxs[0];
-            const Stream st = K.st[op.a];
-            constexpr uint32_t esz = (SP::dtype[op.a] == DT_I8) ? 1u : 4u;
-            const uint64_t poly = stream_poly(st, ctx.item, (uint32_t)op.off + (uint32_t)it * op.step);
-            const char *row = reinterpret_cast<const char *>(st.base) + poly * (kN * esz);
-            if ((uint32_t)ctx.t * 128u < kN * esz) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + ctx.t * 128));
-        }
-#endif
-        sp_loop_prefetch<SP, PC + 1>(K, ctxs, it);
-    }
-}
-
 // executes ops from PC up to (not including) the next OP_SEG / OP_END / OP_ENDLOOP
 template <class SP, int NP, int MODE, int PC>
 RZK_VM void sp_exec(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int it, int prime_iter)
@@ -1821,10 +1798,8 @@ RZK_VM void sp_exec(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int it,
         return;
     } else if constexpr (op.code == OP_LOOP) {
         constexpr int end = sp_find_endloop(SP::prog, PC);
-        if (K.loop_count) sp_loop_prefetch<SP, PC + 1>(K, ctxs, 0);
         RZK_NOUNROLL
         for (int i = 0; i < (int)K.loop_count; ++i) {
-            if (i + 1 < (int)K.loop_count) sp_loop_prefetch<SP, PC + 1>(K, ctxs, i + 1);
             sp_exec<SP, NP, MODE, PC + 1>(K, lanes, ctxs, i, prime_iter);
             if constexpr (MODE == MODE_SEQ_S) { if ((i & 31) == 31) reduce_accumulators_s(lanes, ctxs, sp_uses_acc1(SP::prog)); }
         }
