@@ -1446,6 +1446,59 @@ RZK_VM int op_inv(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, int q, in
     }
 }
 
+// The verifier's norm check in the warp-per-item modes on the device (int32 rows, bound below 2^21: see op_norm): straight-line
+// code with the NEXT row in flight while the current one is squared -- the rows are the item's first touch of global memory, and
+// each exposed L2 / DRAM latency is overlapped with the arithmetic of the row before.
+#if defined(__CUDA_ARCH__)
+template <int MODE>
+__device__ __forceinline__ void op_norm_fast32(const VmLaunch &K, Lane &L, const LaneCtx &ctx, const Op &op)
+{
+    constexpr int CNT = Epi<MODE>::kCount;
+    static_assert(CNT == 16, "warp-per-item modes");
+    const Stream st = K.st[op.a];
+    const uint64_t sq_lim = K.norm_sq_lim[op.b];
+    const uint64_t lane_lim = sq_lim >> 5;
+    const int32_t *src = reinterpret_cast<const int32_t *>(st.base) + stream_poly(st, ctx.item, (uint32_t)op.off) * kN + ctx.ridx * CNT;
+    uint4 cur[CNT / 4], nxt[CNT / 4];
+    RZK_UNROLL
+    for (int j = 0; j < CNT / 4; ++j) cur[j] = rot_ld128(src + 4 * j);
+    RZK_NOUNROLL
+    for (int c = 0; c < (int)op.c; ++c) {
+        if (c + 1 < (int)op.c) {
+            RZK_UNROLL
+            for (int j = 0; j < CNT / 4; ++j) nxt[j] = rot_ld128(src + (size_t)(c + 1) * kN + 4 * j);
+        }
+        int64_t acc = 0;
+        uint32_t mx = 0;
+        RZK_UNROLL
+        for (int j = 0; j < CNT / 4; ++j) {
+            const int32_t vv[4] = {(int32_t)cur[j].x, (int32_t)cur[j].y, (int32_t)cur[j].z, (int32_t)cur[j].w};
+            RZK_UNROLL
+            for (int e = 0; e < 4; ++e) {
+                mx = umax32(mx, (uint32_t)vv[e] + (1u << 21));
+                acc += (int64_t)vv[e] * (int64_t)vv[e];
+            }
+        }
+        const uint32_t bad = (mx >> 22) ? 1u : 0u;
+        const uint64_t s = bad ? 0ull : (uint64_t)acc;
+        L.fail |= bad;
+        if (__any_sync(0xffffffffu, s > lane_lim)) {
+            uint32_t lo = (uint32_t)s, hi = (uint32_t)(s >> 32);
+            RZK_UNROLL
+            for (int d = 16; d >= 1; d >>= 1) {
+                const uint32_t olo = __shfl_xor_sync(0xffffffffu, lo, d);
+                const uint32_t ohi = __shfl_xor_sync(0xffffffffu, hi, d);
+                const uint64_t sum = (((uint64_t)hi << 32) | lo) + (((uint64_t)ohi << 32) | olo);
+                lo = (uint32_t)sum; hi = (uint32_t)(sum >> 32);
+            }
+            L.fail |= ((((uint64_t)hi << 32) | lo) > sq_lim) ? 1u : 0u;
+        }
+        RZK_UNROLL
+        for (int j = 0; j < CNT / 4; ++j) cur[j] = nxt[j];
+    }
+}
+#endif
+
 // params.rs:102-118 via polynomial.rs:60-73: floor(sqrt(sum c^2)) <= bound  <=>  sum c^2 < (bound+1)^2
 template <int MODE>
 RZK_VM void op_norm(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const Op &op, uint32_t dtype)
@@ -1455,6 +1508,11 @@ RZK_VM void op_norm(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const O
     const Stream st = K.st[op.a];
     const uint32_t abs_lim = K.norm_abs_lim[op.b];
     const uint64_t sq_lim = K.norm_sq_lim[op.b];
+#if defined(__CUDA_ARCH__)
+    if constexpr (!mode_seq(MODE)) {
+        if (dtype != DT_I8 && abs_lim < (1u << 21)) { op_norm_fast32<MODE>(K, lanes[0], ctxs[0], op); return; }
+    }
+#endif
     RZK_NOUNROLL
     for (int c = 0; c < (int)op.c; ++c) {
         RZK_EACH_LANE {
