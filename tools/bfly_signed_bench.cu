@@ -42,6 +42,25 @@ __global__ void k(uint32_t *out, const uint32_t *tw, uint32_t p, uint32_t zero, 
                 const uint32_t q = __umulhi(wp, d);
                 v[i] = s;
                 v[i + ILP] = w * d - q * p;
+            } else if (KIND >= 7 && KIND <= 10) {
+                // signed lazy CT whose Shoup quotient floor(y * w' / 2^32) comes from the FP64 pipe, bit-identical to mulhi:
+                //   Ys = y * 2^-32 exactly (pair lo = y ^ 2^31, hi = 0x41300000 is 2^20 + (y + 2^31) 2^-32; minus 2^20 + 1/2),
+                //   Wd = w' exactly (pair lo = w' ^ 2^31, hi = 0x43300000, minus 2^52 + 2^31), q = low word of fma.rd(Ys, Wd, 1.5 * 2^52)
+                // KIND 7: every butterfly; 8: every second; 9: two of three; 10: every butterfly, w' converted once per 4 butterflies
+                const bool fp = KIND == 7 || KIND == 10 || (KIND == 8 && (i & 1)) || (KIND == 9 && (i % 3) != 0);
+                uint32_t q;
+                if (fp) {
+                    const double ys = __hiloint2double(0x41300000, (int)(y ^ 0x80000000u)) - 1048576.5;
+                    const uint32_t wpc = (KIND == 10) ? stw[(2 * (i & ~3) + 1) & 63] : wp;
+                    const double wd = __hiloint2double(0x43300000, (int)(wpc ^ 0x80000000u)) - 4503601774854144.0;
+                    q = (uint32_t)__double2loint(__fma_rd(ys, wd, 6755399441055744.0));
+                } else {
+                    q = (uint32_t)__mulhi((int)y, (int)wp);
+                }
+                const uint32_t t0 = y * w + x;
+                const uint32_t xo = q * mp + t0;
+                v[i] = xo;
+                v[i + ILP] = x + x - xo;
             } else if (KIND == 4) {       // signed GS, adds forced onto the ALU pipe (add-and-max with a bound that never binds)
                 const uint32_t s = (uint32_t)max((int)(x + y), -0x7fffffff);
                 const uint32_t d = (uint32_t)max((int)(x - y), -0x7fffffff);
@@ -84,7 +103,7 @@ void run(int warps_per_sm, uint32_t *d, uint32_t *tw, int sms)
     const int threads = warps_per_sm >= 8 ? 256 : warps_per_sm * 32, blocks = sms * (warps_per_sm * 32 / threads);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    const uint32_t p = KIND & 1 ? 68718593u : 1073692673u;
+    const uint32_t p = (KIND & 1) || KIND >= 7 ? 68718593u : 1073692673u;
     k<ILP, KIND><<<blocks, threads>>>(d, tw, p, 0u, 0u - p);
     cudaDeviceSynchronize();
     float best = 1e30f;
@@ -98,7 +117,7 @@ void run(int warps_per_sm, uint32_t *d, uint32_t *tw, int sms)
     }
     double ops = (double)blocks * threads * ITERS * ILP;
     double rate = ops / (best * 1e-3);
-    const char *names[7] = {"harvey_ct", "signed_ct", "harvey_gs", "signed_gs", "signed_gs_alu", "unsigned_lazy_gs", "signed_ct_alu"};
+    const char *names[11] = {"harvey_ct", "signed_ct", "harvey_gs", "signed_gs", "signed_gs_alu", "unsigned_lazy_gs", "signed_ct_alu", "signed_ct_fp64q", "signed_ct_fp64q_1of2", "signed_ct_fp64q_2of3", "signed_ct_fp64q_w4"};
     printf("{\"kind\": \"%s\", \"warps_per_sm\": %d, \"ilp\": %d, \"ms\": %.4f, \"Tbfly_per_s\": %.3f, \"bfly_per_clk_per_sm_at_1965MHz\": %.2f}\n",
            names[KIND], warps_per_sm, ILP, best, rate / 1e12, rate / sms / 1.965e9);
 }
@@ -111,6 +130,6 @@ int main()
     cudaMalloc(&tw, 256);
     cudaMemset(tw, 0x5a, 256);
     const int sms = prop.multiProcessorCount;
-    for (int w : {4, 8, 16}) { run<16, 0>(w, d, tw, sms); run<16, 1>(w, d, tw, sms); run<16, 2>(w, d, tw, sms); run<16, 3>(w, d, tw, sms); run<16, 4>(w, d, tw, sms); run<16, 5>(w, d, tw, sms); run<16, 6>(w, d, tw, sms); }
+    for (int w : {8, 16}) { run<16, 7>(w, d, tw, sms); run<16, 8>(w, d, tw, sms); run<16, 9>(w, d, tw, sms); run<16, 10>(w, d, tw, sms); run<16, 0>(w, d, tw, sms); run<16, 1>(w, d, tw, sms); run<16, 2>(w, d, tw, sms); run<16, 3>(w, d, tw, sms); run<16, 4>(w, d, tw, sms); run<16, 5>(w, d, tw, sms); run<16, 6>(w, d, tw, sms); }
     return 0;
 }
