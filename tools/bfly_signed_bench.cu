@@ -61,6 +61,23 @@ __global__ void k(uint32_t *out, const uint32_t *tw, uint32_t p, uint32_t zero, 
                 const uint32_t xo = q * mp + t0;
                 v[i] = xo;
                 v[i + ILP] = x + x - xo;
+            } else if (KIND == 11) {      // (diagnostic, wrong arithmetic) signed GS whose quotient does not wait for the difference
+                const uint32_t sm = x + y, d = x - y;
+                const uint32_t q = (uint32_t)__mulhi((int)x, (int)wp);
+                v[i] = sm;
+                v[i + ILP] = q * mp + d * w;
+            } else if (KIND == 12) {      // (diagnostic) signed GS without the sum output: 4 instructions
+                const uint32_t d = x - y;
+                const uint32_t q = (uint32_t)__mulhi((int)d, (int)wp);
+                v[i] = y;
+                v[i + ILP] = q * mp + d * w;
+            } else if (KIND == 13) {      // signed GS, product from x*w - y*w (no wait on d for the low product): 6 instructions
+                const uint32_t sm = x + y, d = x - y;
+                const uint32_t q = (uint32_t)__mulhi((int)d, (int)wp);
+                const uint32_t t1 = x * w;
+                const uint32_t t2 = t1 - y * w;
+                v[i] = sm;
+                v[i + ILP] = q * mp + t2;
             } else if (KIND == 4) {       // signed GS, adds forced onto the ALU pipe (add-and-max with a bound that never binds)
                 const uint32_t s = (uint32_t)max((int)(x + y), -0x7fffffff);
                 const uint32_t d = (uint32_t)max((int)(x - y), -0x7fffffff);
@@ -103,7 +120,7 @@ void run(int warps_per_sm, uint32_t *d, uint32_t *tw, int sms)
     const int threads = warps_per_sm >= 8 ? 256 : warps_per_sm * 32, blocks = sms * (warps_per_sm * 32 / threads);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    const uint32_t p = (KIND & 1) || KIND >= 7 ? 68718593u : 1073692673u;
+    const uint32_t p = (KIND & 1) || KIND >= 7 ? 68718593u : 1073692673u;   // (the rate does not depend on the value)
     k<ILP, KIND><<<blocks, threads>>>(d, tw, p, 0u, 0u - p);
     cudaDeviceSynchronize();
     float best = 1e30f;
@@ -117,7 +134,7 @@ void run(int warps_per_sm, uint32_t *d, uint32_t *tw, int sms)
     }
     double ops = (double)blocks * threads * ITERS * ILP;
     double rate = ops / (best * 1e-3);
-    const char *names[11] = {"harvey_ct", "signed_ct", "harvey_gs", "signed_gs", "signed_gs_alu", "unsigned_lazy_gs", "signed_ct_alu", "signed_ct_fp64q", "signed_ct_fp64q_1of2", "signed_ct_fp64q_2of3", "signed_ct_fp64q_w4"};
+    const char *names[14] = {"harvey_ct", "signed_ct", "harvey_gs", "signed_gs", "signed_gs_alu", "unsigned_lazy_gs", "signed_ct_alu", "signed_ct_fp64q", "signed_ct_fp64q_1of2", "signed_ct_fp64q_2of3", "signed_ct_fp64q_w4", "diag_gs_q_indep", "diag_gs_no_sum", "signed_gs_split_product"};
     printf("{\"kind\": \"%s\", \"warps_per_sm\": %d, \"ilp\": %d, \"ms\": %.4f, \"Tbfly_per_s\": %.3f, \"bfly_per_clk_per_sm_at_1965MHz\": %.2f}\n",
            names[KIND], warps_per_sm, ILP, best, rate / 1e12, rate / sms / 1.965e9);
 }
@@ -130,6 +147,6 @@ int main()
     cudaMalloc(&tw, 256);
     cudaMemset(tw, 0x5a, 256);
     const int sms = prop.multiProcessorCount;
-    for (int w : {8, 16}) { run<16, 7>(w, d, tw, sms); run<16, 8>(w, d, tw, sms); run<16, 9>(w, d, tw, sms); run<16, 10>(w, d, tw, sms); run<16, 0>(w, d, tw, sms); run<16, 1>(w, d, tw, sms); run<16, 2>(w, d, tw, sms); run<16, 3>(w, d, tw, sms); run<16, 4>(w, d, tw, sms); run<16, 5>(w, d, tw, sms); run<16, 6>(w, d, tw, sms); }
+    for (int w : {8, 16}) { run<16, 11>(w, d, tw, sms); run<16, 12>(w, d, tw, sms); run<16, 13>(w, d, tw, sms); run<8, 3>(w, d, tw, sms); run<8, 1>(w, d, tw, sms); run<16, 7>(w, d, tw, sms); run<16, 8>(w, d, tw, sms); run<16, 9>(w, d, tw, sms); run<16, 10>(w, d, tw, sms); run<16, 0>(w, d, tw, sms); run<16, 1>(w, d, tw, sms); run<16, 2>(w, d, tw, sms); run<16, 3>(w, d, tw, sms); run<16, 4>(w, d, tw, sms); run<16, 5>(w, d, tw, sms); run<16, 6>(w, d, tw, sms); }
     return 0;
 }
