@@ -69,7 +69,8 @@ struct VmSmem {
     static constexpr int kG1 = NP * 2 * kG1Words;
     static constexpr int kG2 = NP * 2 * kLanes * kG2Words;
     static constexpr int kKey = KEY ? NP * kKP * 2 * kPadWords : 0;
-    static constexpr int kTables = (kG1 + kG2 + kKey + 3) / 4 * 4;
+    static constexpr int kTw = (mode_signed(MODE) && RZK_INV_DIT) ? NP * kTwistWords : 0;   // output twists of the signed slots' inverse
+    static constexpr int kTables = (kG1 + kG2 + kKey + kTw + 3) / 4 * 4;
     static size_t bytes(int warps, uint32_t hw_words) { return sizeof(uint32_t) * ((size_t)kTables + (size_t)warps * 2 * hw_words); }
 };
 
@@ -107,19 +108,21 @@ __device__ __forceinline__ void tma_wait(uint64_t *bar)
 
 // stages the twiddles and the key images of the NP primes of a launch
 template <int NP, int MODE, bool KEY = true>
-__device__ __forceinline__ void stage_int_tables(const VmLaunch &K, uint32_t *s_g1, uint32_t *s_g2, uint32_t *s_key, uint64_t *bar,
-                                                 bool issue)
+__device__ __forceinline__ void stage_int_tables(const VmLaunch &K, uint32_t *s_g1, uint32_t *s_g2, uint32_t *s_key, uint32_t *s_tw,
+                                                 uint64_t *bar, bool issue)
 {
     using S = VmSmem<NP, MODE, KEY>;
     constexpr uint32_t g1b = 2 * kG1Words * 4, g2b = 2 * kLanes * kG2Words * 4, keyb = KEY ? S::kKP * 2 * kPadWords * 4 : 0;
     static_assert(g1b % 16 == 0 && g2b % 16 == 0 && keyb % 16 == 0, "bulk copies move multiples of 16 bytes");
     if (issue) {
-        tma_expect(bar, NP * (g1b + g2b + keyb));
+        constexpr uint32_t twb = S::kTw ? kTwistWords * 4 : 0;
+        tma_expect(bar, NP * (g1b + g2b + keyb + twb));
         for (int i = 0; i < NP; ++i) {
             const uint32_t slot = K.pc[i].slot;
             tma_load(s_g1 + i * 2 * kG1Words, K.g1tab + (size_t)slot * (2 * kG1Words), g1b, bar);
             tma_load(s_g2 + i * (2 * kLanes * kG2Words), K.g2tab + (size_t)slot * (2 * kLanes * kG2Words), g2b, bar);
             if constexpr (KEY) tma_load(s_key + i * (S::kKP * 2 * kPadWords), K.keytab + (size_t)i * (S::kKP * 2 * kPadWords), keyb, bar);
+            if constexpr (S::kTw != 0) tma_load(s_tw + i * kTwistWords, K.twist[i], kTwistWords * 4, bar);
         }
     }
 }
@@ -139,6 +142,7 @@ __global__ void __launch_bounds__(VmCfg<NP, MODE>::kMaxWarps * 32, 1) rzk_vm_ker
     uint32_t *s_g1 = smem;
     uint32_t *s_g2 = s_g1 + S::kG1;
     uint32_t *s_key = s_g2 + S::kG2;
+    uint32_t *s_tw = s_key + S::kKey;
     uint32_t *s_hw = smem + S::kTables;
     const int nthreads = blockDim.x, warps = nthreads >> 5;
 
@@ -146,7 +150,7 @@ __global__ void __launch_bounds__(VmCfg<NP, MODE>::kMaxWarps * 32, 1) rzk_vm_ker
     __shared__ __align__(8) uint64_t s_bar;
     if (threadIdx.x == 0) tma_init(&s_bar);
     __syncthreads();
-    stage_int_tables<NP, MODE, KEY>(K, s_g1, s_g2, s_key, &s_bar, threadIdx.x == 0);
+    stage_int_tables<NP, MODE, KEY>(K, s_g1, s_g2, s_key, s_tw, &s_bar, threadIdx.x == 0);
     tma_wait(&s_bar);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, hw = lane >> 4, t = lane & 15;
@@ -166,6 +170,7 @@ __global__ void __launch_bounds__(VmCfg<NP, MODE>::kMaxWarps * 32, 1) rzk_vm_ker
     ctx.g1 = s_g1;
     ctx.g2 = s_g2;
     ctx.key = s_key;
+    ctx.twist = s_tw;
     ctx.t = t;
     ctx.hw = hw;
 
@@ -374,6 +379,7 @@ struct rzk_engine {
     uint32_t *d_keytab = nullptr;
     uint32_t *d_keytab2 = nullptr;  // split-key images (lo/hi) for prime slot 0, [6][2][576]
     uint32_t *d_keytab3 = nullptr;  // split-key images for the small prime of MODE_SPLITKEY_S (slot kSignedSlot), signed Shoup form
+    uint32_t *d_twist = nullptr;    // output twists psi^-i of the signed slots' decimation-in-time inverse, [kNumPrimeSlots][512][2]
     uint32_t *d_gstash[kPipe + 1] = {};   // residue stash of the three-prime programs, [SM][warp][half warp][kStashWordsMax]:
                                     // one per pipeline stream (their kernels may overlap) + one for the `_dev` entry points
     int32_t *d_partial[kPipe + 1] = {};   // segment results of product sums cut into segments (small batches), per stream as above
@@ -500,6 +506,7 @@ int launch_vm(rzk_engine *e, VmLaunch &K, cudaStream_t s, uint32_t pp_program = 
             RZK_CUDA(e, cudaMalloc(&e->d_gstash[si], sizeof(uint32_t) * (size_t)e->num_sms * VmCfg<NP, MODE>::kMaxWarps * 2 * kStashWordsMax));
         K.gstash = e->d_gstash[si];
     }
+    for (int i = 0; i < kMaxPrimes; ++i) K.twist[i] = e->d_twist + (size_t)(K.pc[i].slot < (uint32_t)kNumPrimeSlots ? K.pc[i].slot : 0u) * kN * 2;
     layout_hw(K, SPLIT);
     if (!rot_layout_ok(K.ops, SPLIT, K.acc1_global != 0))
         return fail(e, RZK_ERR_INVALID, "OP_ROT needs a warp-per-item program without operand slot and without a second accumulator in shared memory");
@@ -1180,6 +1187,13 @@ int rzk_create(const rzk_params *params, int device, rzk_engine **out)
     if (rc == RZK_OK) cu(cudaMemcpy(e->d_g1tab, g1.data(), g1.size() * sizeof(uint32_t), cudaMemcpyHostToDevice), "cudaMemcpy(g1)");
     cu(cudaMalloc(&e->d_g2tab, g2.size() * sizeof(uint32_t)), "cudaMalloc(g2)");
     if (rc == RZK_OK) cu(cudaMemcpy(e->d_g2tab, g2.data(), g2.size() * sizeof(uint32_t), cudaMemcpyHostToDevice), "cudaMemcpy(g2)");
+    {
+        std::vector<uint32_t> tw((size_t)kNumPrimeSlots * kN * 2, 0);
+        for (int s = 0; s < kNumPrimeSlots; ++s)
+            if (slot_is_signed(s)) memcpy(&tw[(size_t)s * kN * 2], prime_tables(s).twist, sizeof(uint32_t) * kN * 2);
+        cu(cudaMalloc(&e->d_twist, tw.size() * sizeof(uint32_t)), "cudaMalloc(twist)");
+        if (rc == RZK_OK) cu(cudaMemcpy(e->d_twist, tw.data(), tw.size() * sizeof(uint32_t), cudaMemcpyHostToDevice), "cudaMemcpy(twist)");
+    }
     cu(cudaMalloc(&e->d_keytab, (size_t)kNumPrimeSlots * kKeyPolys * 2 * kPadWords * sizeof(uint32_t)), "cudaMalloc(key)");
     cu(cudaMalloc(&e->d_keytab2, (size_t)2 * kKeyPolys * 2 * kPadWords * sizeof(uint32_t)), "cudaMalloc(key2)");
     cu(cudaMalloc(&e->d_keytab3, (size_t)2 * kKeyPolys * 2 * kPadWords * sizeof(uint32_t)), "cudaMalloc(key3)");
@@ -1207,6 +1221,7 @@ void rzk_destroy(rzk_engine *e)
     if (e->d_keytab) cudaFree(e->d_keytab);
     if (e->d_keytab2) cudaFree(e->d_keytab2);
     if (e->d_keytab3) cudaFree(e->d_keytab3);
+    if (e->d_twist) cudaFree(e->d_twist);
     if (e->d_need) cudaFree(e->d_need);
     if (e->d_fs_prefix) cudaFree(e->d_fs_prefix);
     if (e->d_wire_toks) cudaFree(e->d_wire_toks);

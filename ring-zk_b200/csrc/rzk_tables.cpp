@@ -100,6 +100,32 @@ static void build(PrimeTables &T, uint32_t p, bool signed_form)
             for (int t = 0; t < kLanes; ++t)
                 for (int w = 0; w < kG2Words; w += 2) signed_shoup_pair(T.g2[d][t][w], p, T.g2[d][t][w], T.g2[d][t][w + 1]);
         }
+#if RZK_INV_DIT
+        // Inverse of a signed slot in decimation-in-time form (rzk_vm_exec.cuh inv_g2_dit / inv_g1_dit): the forward output is the
+        // cyclic DFT of (a_j psi^j) in bit-reversed order, so the inverse is a cyclic DIT transform on that order -- stage m = 2 .. N:
+        // a[k+j], a[k+j+m/2] <- a[k+j] +- w_m^j a[k+j+m/2], w_m = psi^(-2N/m) -- followed by the twist a_i *= psi^-i (N^-1 rides on the
+        // key images / the pre-scaled operand as before).  Twiddles depend on the position inside a block, so the roles of the two
+        // tables swap: g1[1] holds the lane-uniform twiddles of the contiguous-layout stages m = 4, 8, 16 (j = 1 .. m/2-1 at
+        // index m/4 - 1 + j - 1 ... packed 0 .. 10) and, at index 16 + t, lane t's twiddle of stage m = 32; g2[1][t] holds lane t's
+        // twiddles of the stages m = 64 .. 512 (j = t + 16 a, a = 0 .. m/32 - 1: 2 + 4 + 8 + 16 pairs).
+        auto wpow = [&](int m, int j) { return mod_pow(T.psi_inv, (uint64_t)(2 * kN / m) * (uint64_t)j, p); };
+        memset(T.g1[1], 0, sizeof(T.g1[1]));
+        int idx = 0;
+        for (int m = 4; m <= 16; m <<= 1)
+            for (int j = 1; j < m / 2; ++j, ++idx) signed_shoup_pair(wpow(m, j), p, T.g1[1][idx][0], T.g1[1][idx][1]);
+        for (int t = 0; t < kLanes; ++t) signed_shoup_pair(wpow(32, t), p, T.g1[1][16 + t][0], T.g1[1][16 + t][1]);
+        for (int t = 0; t < kLanes; ++t) {
+            int w = 0;
+            for (int m = 64; m <= kN; m <<= 1)
+                for (int a = 0; a < m / 32; ++a, w += 2) signed_shoup_pair(wpow(m, t + 16 * a), p, T.g2[1][t][w], T.g2[1][t][w + 1]);
+        }
+        // twist psi^-i in the order the strided layout reads it with 128-bit loads: coefficient i = t + 16 m lives in pair
+        // ((m >> 1) * 16 + t) * 2 + (m & 1), so lane t's uint4 number k holds the pairs of its registers m = 2k and 2k + 1
+        for (int i = 0; i < kN; ++i) {
+            const int t = i & 15, m = i >> 4, slot = ((m >> 1) * 16 + t) * 2 + (m & 1);
+            signed_shoup_pair(mod_pow(T.psi_inv, (uint64_t)i, p), p, T.twist[slot][0], T.twist[slot][1]);
+        }
+#endif
     }
 }
 

@@ -26,6 +26,10 @@ constexpr int kPadWords = 576;     // 512 + 4 words of padding per 32 (conflict-
 constexpr int kBufWords = 592;     // transpose buffer per half-warp (+16: bank shift between halves)
 constexpr int kSlotWords = 512;    // lane-private slot (uint4 chunks interleaved over lanes)
 constexpr int kG2Words = 60;       // lane-specific twiddle words per (direction, prime, lane)
+#ifndef RZK_INV_DIT
+#define RZK_INV_DIT 1      // signed slots: inverse transform in decimation-in-time form (Cooley-Tukey butterflies + output twist); 0 = Gentleman-Sande (A/B)
+#endif
+constexpr int kTwistWords = 1024;  // output twist of a signed slot's inverse: 512 (w, w') pairs
 constexpr int kG1Words = 66;       // lane-uniform twiddle words per (prime, direction): 32 (w, w') pairs + 2 pad
                                    // (66 = 2 mod 32: the two half warps of a SPLIT warp hit different banks)
 constexpr int kKeyPolys = 3;       // non-trivial key polynomials a1'[0], a1'[1], a2'[0] at (n,k,l)=(1,3,1)
@@ -136,6 +140,7 @@ struct VmLaunch {
     const uint32_t *g1tab;     // device, [prime slot][dir][kG1Words]
     const uint32_t *g2tab;     // device, [prime slot][dir][16][60]
     const uint32_t *keytab;    // device, [prime slot][3][2][576]
+    const uint32_t *twist[kMaxPrimes];   // device; signed slots (RZK_INV_DIT): the output twists psi^-i of the decimation-in-time inverse, staged into shared memory
     // shared-memory layout of one half-warp region (words); sized from what the program uses
     uint32_t hw_words;         // == 16 (mod 32): the two half warps of a warp sit 16 banks apart
     uint32_t off_slot, off_acc1, off_stash;
@@ -244,6 +249,7 @@ struct PrimeTables {
     uint32_t g2[2][kLanes][kG2Words];      // [dir][lane][...]
     uint32_t psi, psi_inv, ninv, r, rn, rnp, pinv;
     uint32_t tw[2][kN][2];                 // full tables (reference transform, key setup)
+    uint32_t twist[kN][2];                 // signed slots: (centred psi^-i, signed companion) in the lane order of inv_g1_dit (rzk_tables.cpp)
 };
 
 }  // namespace rzk

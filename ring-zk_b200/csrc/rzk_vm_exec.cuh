@@ -99,6 +99,7 @@ struct LaneCtx {
     const uint32_t *g1;    // staged [np][2][kG1Words]
     const uint32_t *g2;    // staged [np][2][16][60]
     const uint32_t *key;   // staged [np][3][2][576]
+    const uint32_t *twist; // staged [np][kTwistWords] (signed modes, RZK_INV_DIT)
     uint32_t item;         // item index (clamped to n_items-1 for idle lanes)
     int t;                 // lane within the half warp, 0..15
     int hw;                // half warp within the warp, 0..1
@@ -380,6 +381,102 @@ RZK_VM void inv_g1_s(uint32_t (&a)[kElems], const uint32_t *g1tab, uint32_t mp)
     for (int e = 0; e < kElems; e += 8) a[e] = sreduce<kSignedShift>(a[e], mp);
     g1_stage_s<1, 1>(a, g1, mp);
     g1_stage_s<0, 1, BIASED>(a, g1, mp);    // BIASED: the outputs carry the bias 2^31 (f64_exact_biased)
+}
+
+// ---- inverse of a signed slot in decimation-in-time form (RZK_INV_DIT; tables: rzk_tables.cpp) --------------------------
+// The forward output is the cyclic DFT of (a_j psi^j) in bit-reversed order, so its inverse is a cyclic decimation-in-time
+// transform on that order -- stage m = 2 .. N pairs a[k+j] with a[k+j+m/2] and multiplies the SECOND operand by w_m^j before
+// the add / subtract -- followed by the twist a_i *= psi^-i.  That is the forward (Cooley-Tukey) butterfly, four instructions
+// and the multiply-first order the pipes like (15.2 against 12.1 butterflies per clock and SM for the Gentleman-Sande form,
+// profiles/r2g_bfly_signed.jsonl); the 511 butterflies with j = 0 need no multiplication at all (two instructions), and the
+// twist (three instructions per coefficient) hands every output over below 5p/4, with the bias of the conversion for free.
+// 620 instructions per lane and transform instead of 748.  Magnitudes in units of p (inputs <= 5/2: two key products, or a
+// reduced accumulator): a butterfly without a multiplication doubles, one with a multiplication adds 5/4 to its first operand.
+// Contiguous layout: after m = 2 everything is <= 5; after m = 4 the elements e = 0, 2 (mod 4) hold 10, the others 6.25;
+// after m = 8 e = 0, 4 (mod 8) hold 20 -- the elements e = 0 (mod 8) are reduced there (4 of 32 per lane) -- so that m = 16
+// ends with at most 21.25 (e = 4, 12 mod 16).  The five strided stages multiply every second operand (also lane 0's w = 1)
+// and add 5/4 each: below 27.5 < 31.98.
+RZK_VM void ct_bfly_s_one(uint32_t &x, uint32_t &y)
+{
+    const uint32_t s = x + y;
+    y = x - y;
+    x = s;
+}
+
+RZK_VM void inv_g2_dit(uint32_t (&a)[kElems], const uint32_t *g1tab, uint32_t mp)
+{
+    const uint2 *u = reinterpret_cast<const uint2 *>(g1tab);
+    RZK_UNROLL
+    for (int e = 0; e < kElems; e += 2) ct_bfly_s_one(a[e], a[e + 1]);
+    {
+        const uint2 w = u[0];
+        RZK_UNROLL
+        for (int k = 0; k < kElems; k += 4) {
+            ct_bfly_s_one(a[k], a[k + 2]);
+            ct_bfly_s(a[k + 1], a[k + 3], w.x, w.y, mp);
+        }
+    }
+    RZK_UNROLL
+    for (int j = 0; j < 4; ++j) {
+        RZK_UNROLL
+        for (int k = 0; k < kElems; k += 8) {
+            if (j == 0) ct_bfly_s_one(a[k], a[k + 4]);
+            else { const uint2 w = u[j]; ct_bfly_s(a[k + j], a[k + j + 4], w.x, w.y, mp); }
+        }
+    }
+    RZK_UNROLL
+    for (int e = 0; e < kElems; e += 8) a[e] = sreduce<kSignedShift>(a[e], mp);
+    RZK_UNROLL
+    for (int j = 0; j < 8; ++j) {
+        RZK_UNROLL
+        for (int k = 0; k < kElems; k += 16) {
+            if (j == 0) ct_bfly_s_one(a[k], a[k + 8]);
+            else { const uint2 w = u[3 + j]; ct_bfly_s(a[k + j], a[k + j + 8], w.x, w.y, mp); }
+        }
+    }
+}
+
+template <bool BIASED>
+RZK_VM void inv_g1_dit(uint32_t (&a)[kElems], const uint32_t *g1tab, const uint32_t *g2lane, const uint32_t *twist, int t, uint32_t mp)
+{
+    const uint2 *u = reinterpret_cast<const uint2 *>(g1tab);
+    const uint2 *l = reinterpret_cast<const uint2 *>(g2lane);      // lane t's pairs: stage m = 64 at 0, 128 at 2, 256 at 6, 512 at 14
+    {
+        const uint2 w = u[16 + t];
+        RZK_UNROLL
+        for (int k = 0; k < kElems; k += 2) ct_bfly_s(a[k], a[k + 1], w.x, w.y, mp);
+    }
+    RZK_UNROLL
+    for (int c = 0; c < 2; ++c) {
+        const uint2 w = l[c];
+        RZK_UNROLL
+        for (int k = 0; k < kElems; k += 4) ct_bfly_s(a[k + c], a[k + c + 2], w.x, w.y, mp);
+    }
+    RZK_UNROLL
+    for (int c = 0; c < 4; ++c) {
+        const uint2 w = l[2 + c];
+        RZK_UNROLL
+        for (int k = 0; k < kElems; k += 8) ct_bfly_s(a[k + c], a[k + c + 4], w.x, w.y, mp);
+    }
+    RZK_UNROLL
+    for (int c = 0; c < 8; ++c) {
+        const uint2 w = l[6 + c];
+        RZK_UNROLL
+        for (int k = 0; k < kElems; k += 16) ct_bfly_s(a[k + c], a[k + c + 8], w.x, w.y, mp);
+    }
+    RZK_UNROLL
+    for (int c = 0; c < 16; ++c) {
+        const uint2 w = l[14 + c];
+        ct_bfly_s(a[c], a[c + 16], w.x, w.y, mp);
+    }
+    const uint4 *tw = reinterpret_cast<const uint4 *>(twist) + t;       // uint4 k of lane t: the pairs of its registers 2k and 2k + 1
+    RZK_UNROLL
+    for (int k = 0; k < kElems / 2; ++k) {
+        const uint4 w = tw[kLanes * k];
+        // BIASED: the outputs carry the bias 2^31 (f64_exact_biased)
+        a[2 * k] = sshoup_mac(w.x, w.y, a[2 * k], mp, BIASED ? 0x80000000u : 0u);
+        a[2 * k + 1] = sshoup_mac(w.z, w.w, a[2 * k + 1], mp, BIASED ? 0x80000000u : 0u);
+    }
 }
 
 // ---------------------------------------------------------------- global memory
@@ -1274,7 +1371,11 @@ RZK_VM void inv_core(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const 
             RZK_UNROLL
             for (int e = 0; e < kElems; ++e) L.cur[e] = sreduce<kSignedShift>(L.cur[e], 0u - pc.p);
         }
+#if RZK_INV_DIT
+        if constexpr (mode_signed(MODE)) inv_g2_dit(L.cur, ctx.g1 + (L.pi * 2 + 1) * kG1Words, 0u - pc.p);
+#else
         if constexpr (mode_signed(MODE)) inv_g2_s(L.cur, ctx.g2 + ((L.pi * 2 + 1) * kLanes + t) * kG2Words, 0u - pc.p);
+#endif
         else inv_g2(L.cur, ctx.g2 + ((L.pi * 2 + 1) * kLanes + t) * kG2Words, pc.p, pc.p2, pc.pad_, L.cap);
         uint4 *row = reinterpret_cast<uint4 *>(ctx.buf + 36 * t);
         RZK_UNROLL
@@ -1294,12 +1395,20 @@ RZK_VM void inv_core(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const 
             L.cur[m] = ctx.buf[i + ((i >> 5) << 2)];
         }
         if constexpr (MODE == MODE_SPLITKEY_S) {
+#if RZK_INV_DIT
+            inv_g1_dit<true>(L.cur, ctx.g1 + (L.pi * 2 + 1) * kG1Words, ctx.g2 + ((L.pi * 2 + 1) * kLanes + t) * kG2Words, ctx.twist + L.pi * kTwistWords, t, 0u - pc.p);
+#else
             inv_g1_s<true>(L.cur, ctx.g1 + (L.pi * 2 + 1) * kG1Words, 0u - pc.p);    // any representative below 20.2 p: centred in the epilogue
+#endif
         } else if constexpr (MODE == MODE_SEQ_S) {
             // the Garner recombination wants the canonical residue in [0, p): shift-reduce to (-0.06 p, 1.06 p), lift the
             // negative ones by p, one conditional subtraction
             const uint32_t mp = 0u - pc.p;
+#if RZK_INV_DIT
+            inv_g1_dit<false>(L.cur, ctx.g1 + (L.pi * 2 + 1) * kG1Words, ctx.g2 + ((L.pi * 2 + 1) * kLanes + t) * kG2Words, ctx.twist + L.pi * kTwistWords, t, mp);
+#else
             inv_g1_s<false>(L.cur, ctx.g1 + (L.pi * 2 + 1) * kG1Words, mp);
+#endif
             RZK_UNROLL
             for (int m = 0; m < kElems; ++m) {
                 const uint32_t r = sreduce<kSignedShift>(L.cur[m], mp);

@@ -45,7 +45,7 @@ struct Emu {
     int np;
     int mode;
     int slots[3];
-    std::vector<uint32_t> g1, g2, key, flags;
+    std::vector<uint32_t> g1, g2, key, twist, flags;
     VmLaunch K;
     std::vector<uint32_t> region;     // two half-warp regions
 
@@ -56,6 +56,7 @@ struct Emu {
         memset(&K, 0, sizeof(K));
         g1.assign((size_t)np * 2 * kG1Words, 0);
         g2.resize((size_t)np * 2 * kLanes * kG2Words);
+        twist.assign((size_t)np * kTwistWords, 0);
         key.resize((size_t)np * kKeyPolys * 2 * kPadWords * (mode_sk(mode) ? 2 : 1));
         for (int i = 0; i < np; ++i) {
             slots[i] = sl[i];
@@ -68,6 +69,7 @@ struct Emu {
                 else key_image(T, keypolys + (size_t)k * kN, &key[((size_t)i * kKeyPolys + k) * 2 * kPadWords]);
             }
             K.pc[i] = make_prime_consts(sl[i]);
+            memcpy(&twist[(size_t)i * kTwistWords], T.twist, sizeof(T.twist));
         }
         K.crt = make_crt_consts(sl, np, (uint64_t)Q);
         K.q = (uint32_t)Q;
@@ -114,7 +116,7 @@ struct Emu {
                 c.acc1 = K.acc1_global ? c.stash : mine + K.off_acc1;
                 c.red = split ? region.data() : mine;
                 c.ridx = split ? li : (li & 15);
-                c.g1 = g1.data(); c.g2 = g2.data(); c.key = key.data();
+                c.g1 = g1.data(); c.g2 = g2.data(); c.key = key.data(); c.twist = twist.data();
                 c.t = li & 15; c.hw = hw;
                 const uint32_t item = base + (split ? 0 : hw);
                 c.active = item < n_items;
