@@ -675,6 +675,50 @@ int main(int argc, char **argv)
         printf("signed split-key commit ok\n");
     }
 
+#if RZK_INV_DIT
+    // ---------------- decimation-in-time inverse of the signed slots at the extremes of its lazy range ----------------
+    // Every input is the representative c + 2p or c - 2p of a residue c (|v| up to 5p/2, the bound inv_g2_dit / inv_g1_dit
+    // admit), all of one sign or alternating -- the inputs that drive the running sums furthest -- and the outputs must still
+    // be the exact inverse transform (times N: the scaling rides elsewhere) modulo p.
+    for (int slot = kSignedSlot; slot < kNumPrimeSlots; ++slot) {
+        const PrimeTables &T = prime_tables(slot);
+        const uint32_t p = T.p, mp = 0u - p;
+        for (int pattern = 0; pattern < 4; ++pattern) {
+            std::vector<uint32_t> res(N), ref(N);
+            uint64_t st = 0x9e3779b97f4a7c15ull * (uint64_t)(slot * 4 + pattern + 1);
+            uint32_t a[kLanes][kElems];
+            for (size_t i = 0; i < N; ++i) {
+                st = st * 6364136223846793005ull + 1442695040888963407ull;
+                const uint32_t r = (uint32_t)((st >> 33) % p);
+                ref[i] = r;
+                int64_t c = (int64_t)r; if (c > (int64_t)(p - 1) / 2) c -= p;
+                const int sign = pattern == 0 ? 1 : pattern == 1 ? -1 : pattern == 2 ? ((i & 1) ? 1 : -1) : (((i >> 3) & 1) ? 1 : -1);
+                a[i >> 5][i & 31] = (uint32_t)(int32_t)(c + sign * 2 * (int64_t)p);           // contiguous layout: lane i / 32, element i % 32
+            }
+            ntt_inverse_ref(T, ref.data());                                                     // includes N^-1
+            uint32_t buf[kN];
+            for (int t = 0; t < kLanes; ++t) {
+                inv_g2_dit(a[t], &T.g1[1][0][0], mp);
+                for (int e = 0; e < kElems; ++e) buf[32 * t + e] = a[t][e];
+            }
+            for (int t = 0; t < kLanes; ++t) {
+                uint32_t b[kElems];
+                for (int m = 0; m < kElems; ++m) b[m] = buf[t + kLanes * m];                    // strided layout
+                inv_g1_dit<false>(b, &T.g1[1][0][0], &T.g2[1][t][0], &T.twist[0][0], t, mp);
+                for (int m = 0; m < kElems; ++m) res[t + kLanes * m] = b[m];
+            }
+            for (size_t i = 0; i < N; ++i) {
+                const int64_t v = (int64_t)(int32_t)res[i];
+                CHECK(v > -(int64_t)p * 5 / 4 - 2 && v < (int64_t)p * 5 / 4 + 2, "DIT inverse output %zu outside 5p/4 (slot %d pattern %d)", i, slot, pattern);
+                const uint32_t got = (uint32_t)(((v % (int64_t)p) + p) % p);
+                const uint32_t want = (uint32_t)((uint64_t)ref[i] * kN % p);
+                CHECK(got == want, "DIT inverse coefficient %zu (slot %d pattern %d)", i, slot, pattern);
+            }
+        }
+    }
+    printf("signed DIT inverse at the range extremes ok\n");
+#endif
+
     // ---------------- compile-time programs (vm_run_static) against the same oracle outputs ----------------
     {
         const int L1[1] = {0};
