@@ -379,7 +379,7 @@ struct rzk_engine {
     uint32_t *d_keytab = nullptr;
     uint32_t *d_keytab2 = nullptr;  // split-key images (lo/hi) for prime slot 0, [6][2][576]
     uint32_t *d_keytab3 = nullptr;  // split-key images for the small prime of MODE_SPLITKEY_S (slot kSignedSlot), signed Shoup form
-    uint32_t *d_twist = nullptr;    // output twists psi^-i of the signed slots' decimation-in-time inverse, [kNumPrimeSlots][512][2]
+    uint32_t *d_twist = nullptr;    // output twists of the signed slots' decimation-in-time inverse, [kNumPrimeSlots][psi^-i, psi^-i R N^-1][kTwistWords]
     uint32_t *d_gstash[kPipe + 1] = {};   // residue stash of the three-prime programs, [SM][warp][half warp][kStashWordsMax]:
                                     // one per pipeline stream (their kernels may overlap) + one for the `_dev` entry points
     int32_t *d_partial[kPipe + 1] = {};   // segment results of product sums cut into segments (small batches), per stream as above
@@ -506,7 +506,9 @@ int launch_vm(rzk_engine *e, VmLaunch &K, cudaStream_t s, uint32_t pp_program = 
             RZK_CUDA(e, cudaMalloc(&e->d_gstash[si], sizeof(uint32_t) * (size_t)e->num_sms * VmCfg<NP, MODE>::kMaxWarps * 2 * kStashWordsMax));
         K.gstash = e->d_gstash[si];
     }
-    for (int i = 0; i < kMaxPrimes; ++i) K.twist[i] = e->d_twist + (size_t)(K.pc[i].slot < (uint32_t)kNumPrimeSlots ? K.pc[i].slot : 0u) * kN * 2;
+    // (the product-sum programs, MODE_SEQ_S, take the twist that also carries R N^-1)
+    for (int i = 0; i < kMaxPrimes; ++i)
+        K.twist[i] = e->d_twist + ((size_t)(K.pc[i].slot < (uint32_t)kNumPrimeSlots ? K.pc[i].slot : 0u) * 2 + (MODE == MODE_SEQ_S ? 1 : 0)) * kTwistWords;
     layout_hw(K, SPLIT);
     if (!rot_layout_ok(K.ops, SPLIT, K.acc1_global != 0))
         return fail(e, RZK_ERR_INVALID, "OP_ROT needs a warp-per-item program without operand slot and without a second accumulator in shared memory");
@@ -1188,9 +1190,12 @@ int rzk_create(const rzk_params *params, int device, rzk_engine **out)
     cu(cudaMalloc(&e->d_g2tab, g2.size() * sizeof(uint32_t)), "cudaMalloc(g2)");
     if (rc == RZK_OK) cu(cudaMemcpy(e->d_g2tab, g2.data(), g2.size() * sizeof(uint32_t), cudaMemcpyHostToDevice), "cudaMemcpy(g2)");
     {
-        std::vector<uint32_t> tw((size_t)kNumPrimeSlots * kN * 2, 0);
+        std::vector<uint32_t> tw((size_t)kNumPrimeSlots * 2 * kTwistWords, 0);      // [slot][plain, times R N^-1][kTwistWords]
         for (int s = 0; s < kNumPrimeSlots; ++s)
-            if (slot_is_signed(s)) memcpy(&tw[(size_t)s * kN * 2], prime_tables(s).twist, sizeof(uint32_t) * kN * 2);
+            if (slot_is_signed(s)) {
+                memcpy(&tw[((size_t)s * 2 + 0) * kTwistWords], prime_tables(s).twist, sizeof(uint32_t) * kTwistWords);
+                memcpy(&tw[((size_t)s * 2 + 1) * kTwistWords], prime_tables(s).twist_rn, sizeof(uint32_t) * kTwistWords);
+            }
         cu(cudaMalloc(&e->d_twist, tw.size() * sizeof(uint32_t)), "cudaMalloc(twist)");
         if (rc == RZK_OK) cu(cudaMemcpy(e->d_twist, tw.data(), tw.size() * sizeof(uint32_t), cudaMemcpyHostToDevice), "cudaMemcpy(twist)");
     }

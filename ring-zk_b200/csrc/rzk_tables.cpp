@@ -124,6 +124,7 @@ static void build(PrimeTables &T, uint32_t p, bool signed_form)
         for (int i = 0; i < kN; ++i) {
             const int t = i & 15, m = i >> 4, slot = ((m >> 1) * 16 + t) * 2 + (m & 1);
             signed_shoup_pair(mod_pow(T.psi_inv, (uint64_t)i, p), p, T.twist[slot][0], T.twist[slot][1]);
+            signed_shoup_pair((uint32_t)((uint64_t)mod_pow(T.psi_inv, (uint64_t)i, p) * T.rn % p), p, T.twist_rn[slot][0], T.twist_rn[slot][1]);
         }
 #endif
     }

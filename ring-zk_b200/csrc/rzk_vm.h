@@ -250,6 +250,8 @@ struct PrimeTables {
     uint32_t psi, psi_inv, ninv, r, rn, rnp, pinv;
     uint32_t tw[2][kN][2];                 // full tables (reference transform, key setup)
     uint32_t twist[kN][2];                 // signed slots: (centred psi^-i, signed companion) in the lane order of inv_g1_dit (rzk_tables.cpp)
+    uint32_t twist_rn[kN][2];              // the same times R N^-1 (R = 2^32): the twist of the product-sum programs (MODE_SEQ_S), whose
+                                           // Montgomery products then take both operands as plain transforms
 };
 
 }  // namespace rzk

@@ -560,7 +560,9 @@ RZK_VM void op_fwd(const VmLaunch &K, Lane *lanes, const LaneCtx *ctxs, const Op
             if (dtype == DT_I8) {
                 RZK_UNROLL
                 for (int m = 0; m < kElems; ++m) L.cur[m] = (uint32_t)v[m];
-            } else if (op.b & FWD_SCALED) {
+            } else if ((op.b & FWD_SCALED) && !RZK_INV_DIT) {
+                // (with the decimation-in-time inverse the factor R N^-1 of a Montgomery operand rides on the output twist instead:
+                // PrimeTables::twist_rn, selected for MODE_SEQ_S at launch -- two multiplies less per coefficient)
                 RZK_UNROLL
                 for (int m = 0; m < kElems; ++m) L.cur[m] = sshoup_mac(pc.rn, pc.rnp, (uint32_t)v[m], mp, 0u);
             } else {

@@ -69,7 +69,7 @@ struct Emu {
                 else key_image(T, keypolys + (size_t)k * kN, &key[((size_t)i * kKeyPolys + k) * 2 * kPadWords]);
             }
             K.pc[i] = make_prime_consts(sl[i]);
-            memcpy(&twist[(size_t)i * kTwistWords], T.twist, sizeof(T.twist));
+            memcpy(&twist[(size_t)i * kTwistWords], mode == MODE_SEQ_S ? T.twist_rn : T.twist, sizeof(T.twist));
         }
         K.crt = make_crt_consts(sl, np, (uint64_t)Q);
         K.q = (uint32_t)Q;
