@@ -70,8 +70,10 @@ constexpr bool mode_signed(int mode) { return mode == MODE_SPLITKEY_S || mode ==
 constexpr int kSignedMaxTerms = 64;                  // terms of a product sum the three small primes hold for ANY int32 operands
 // MODE_SPLITKEY_S: the split-key commitment for |r| <= 1 (Params::default(): b = 1) modulo ONE SMALL prime with signed lazy
 // arithmetic (rzk_arith.cuh): |a_lo r1 + a_lo' r2 + r0| <= 2^25 + 127 < p/2 for p = 67153921, and 2^31 / p = 31.98 leaves room
-// for nine forward stages without any correction (4-instruction butterflies) and for inverse stages that only reduce the
-// few elements whose run of sums would overflow (14 of 288 per transform).  Same program, same data flow as MODE_SPLITKEY.
+// for nine forward stages without any correction (4-instruction butterflies) and for an inverse in decimation-in-time form
+// (inv_g2_dit / inv_g1_dit: the same butterflies, 511 of them without a multiplication, four reductions per lane, then the
+// twist psi^-i; the Gentleman-Sande form with its 14 reductions per transform is the RZK_INV_DIT=0 build).  Same program,
+// same data flow as MODE_SPLITKEY.
 constexpr bool mode_sk(int mode) { return mode == MODE_SPLITKEY || mode == MODE_SPLITKEY_S; }
 constexpr uint32_t kStaticPrime0 = 1073692673u;      // kPrimeList[0] (rzk_tables.cpp); 4p - 1 < 2^32
 constexpr uint32_t kStaticPrimeS = 67153921u;        // kPrimeList[kSignedSlot]: 2^26 + 45057, == 1 (mod 4096)
