@@ -26,6 +26,9 @@
  *   - Host entry points take host pointers (pinned memory recommended: rzk_host_alloc)
  *     and pipeline H2D / kernels / D2H over chunks.  `_dev` entry points take device
  *     pointers, enqueue on the given cudaStream_t (as void*) and do not synchronise.
+ *     Device arrays must be 16-byte aligned (cudaMalloc and framework allocations are; every row of a batch-major array
+ *     then is, since a polynomial is 2048 or 512 bytes): the kernels read rows with 128-bit loads.  Host pointers of the
+ *     host entry points need no particular alignment.
  *   - One engine is bound to one CUDA device and is externally synchronised.
  *   - The randomness r, y, d is drawn by the caller (host side, seeded RNG) and passed in; the
  *     protocol entry points sample nothing.  (Optional, separate: rzk_sample_*_dev, below.)
